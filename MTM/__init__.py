@@ -1,0 +1,26 @@
+"""Drop-in ``import MTM`` shim: resolves to the B200-native package in
+``multitemplatematching-python_b200/`` (the directory name is not a valid Python
+identifier, so it is loaded by path under the module name ``mtm_b200``)."""
+import importlib.util
+import os
+import sys
+
+_PKG_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "multitemplatematching-python_b200")
+
+
+def _load():
+    if "mtm_b200" in sys.modules:
+        return sys.modules["mtm_b200"]
+    spec = importlib.util.spec_from_file_location("mtm_b200", os.path.join(_PKG_DIR, "__init__.py"),
+                                                  submodule_search_locations=[_PKG_DIR])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["mtm_b200"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+_impl = _load()
+from mtm_b200 import (NMS, Hit, BBox, TemplateTuple, __version__, computeScoreMap, drawBoxesOnGray,  # noqa: E402,F401
+                      drawBoxesOnRGB, findMatches, matchTemplates)
+
+__all__ = ["NMS"]

@@ -1,0 +1,122 @@
+/* mtm_b200.h -- C ABI of libmtm_b200.so, the B200-native replacement for the
+ * third-party kernels on the hot path of MTM 2.0.1 (MultiTemplateMatching-Python).
+ *
+ * Plain C, no torch / numpy types.  Every entry point names the reference call
+ * site (file:line under the reference tree) it stands in for.  All functions
+ * return MTM_OK (0) or a negative mtm_status; a human-readable message for the
+ * last failure on a context is available through mtm_last_error().  There is no
+ * CPU fallback: without a CUDA device mtm_create() fails with MTM_ERR_CUDA.
+ *
+ * Threading: a context owns one CUDA stream and its device workspaces; calls on
+ * the same context must not overlap (the Python layer holds a lock).  Use one
+ * context per GPU / per concurrent caller.
+ */
+#ifndef MTM_B200_H
+#define MTM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MTM_ABI_VERSION 1
+
+typedef enum mtm_status {
+    MTM_OK = 0,
+    MTM_ERR_INVALID = -1,      /* bad argument (shape, dtype, null pointer, state)          */
+    MTM_ERR_CUDA = -2,         /* CUDA runtime / driver failure (message has the details)   */
+    MTM_ERR_CAPACITY = -3,     /* caller's hit buffer too small; *n_hits holds the need     */
+    MTM_ERR_UNSUPPORTED = -4   /* valid for the reference, not implemented on the GPU yet   */
+} mtm_status;
+
+typedef enum mtm_dtype { MTM_U8 = 0, MTM_F32 = 1 } mtm_dtype;
+
+/* cv2.TM_* codes, MTM/__init__.py:56 `method` */
+typedef enum mtm_method {
+    MTM_TM_SQDIFF = 0, MTM_TM_SQDIFF_NORMED = 1, MTM_TM_CCORR = 2,
+    MTM_TM_CCORR_NORMED = 3, MTM_TM_CCOEFF = 4, MTM_TM_CCOEFF_NORMED = 5
+} mtm_method;
+
+/* Numerator kernel selection (mtm_set_option MTM_OPT_PATH). */
+typedef enum mtm_path { MTM_PATH_AUTO = 0, MTM_PATH_DIRECT = 1, MTM_PATH_TENSOR = 2 } mtm_path;
+typedef enum mtm_option { MTM_OPT_PATH = 0 } mtm_option;
+
+/* Device/host mirror of the reference's Hit tuple (label, (x, y, w, h), score),
+ * MTM/NMS.py:18; `tmpl` indexes the template list instead of carrying the label. */
+typedef struct mtm_hit {
+    int32_t tmpl;
+    int32_t x, y, w, h;
+    float score;
+} mtm_hit;
+
+typedef struct mtm_counters {
+    int64_t kernel_launches;   /* kernels of this library launched since the last reset */
+    int64_t h2d_bytes;
+    int64_t d2h_bytes;
+} mtm_counters;
+
+typedef struct mtm_ctx mtm_ctx;
+
+/* ---- lifetime ------------------------------------------------------------- */
+int mtm_abi_version(void);
+int mtm_create(int device, mtm_ctx** out);
+int mtm_destroy(mtm_ctx* ctx);
+/* ctx may be NULL: returns the message of the last failed mtm_create(). */
+const char* mtm_last_error(const mtm_ctx* ctx);
+/* Run on an existing CUDA stream (cudaStream_t passed as void*), e.g. the
+ * caller's timing stream; NULL restores the context's own stream. */
+int mtm_set_stream(mtm_ctx* ctx, void* cuda_stream);
+int mtm_synchronize(mtm_ctx* ctx);
+int mtm_set_option(mtm_ctx* ctx, int option, int64_t value);
+int mtm_get_counters(mtm_ctx* ctx, mtm_counters* out);
+int mtm_reset_counters(mtm_ctx* ctx);
+/* CUDA-event stopwatch on the context's stream (bench.py): begin, work, end -> ms. */
+int mtm_timer_begin(mtm_ctx* ctx);
+int mtm_timer_end(mtm_ctx* ctx, float* elapsed_ms);
+
+/* ---- inputs ---------------------------------------------------------------
+ * mtm_set_image: the `image` operand of cv2.matchTemplate (MTM/__init__.py:92)
+ * after MTM's searchBox crop (MTM/__init__.py:140-144).  `pixels` is a host
+ * pointer to H rows of W*C elements, rows `row_stride_bytes` apart (a cropped
+ * numpy view needs no host copy).  Uploads and builds the per-channel window
+ * statistics (what OpenCV's integral() provides to common_matchTemplate).
+ * mtm_set_image_device: same with a DEVICE pointer (inputs already in HBM). */
+int mtm_set_image(mtm_ctx* ctx, const void* pixels, int H, int W, int C, int dtype,
+                  int64_t row_stride_bytes);
+int mtm_set_image_device(mtm_ctx* ctx, const void* d_pixels, int H, int W, int C, int dtype,
+                         int64_t row_stride_bytes);
+/* mtm_set_templates: the `listTemplates` arrays (MTM/__init__.py:95,147-167),
+ * each contiguous h[i] x w[i] x C, same dtype/C as the image. */
+int mtm_set_templates(mtm_ctx* ctx, int n, const void* const* pixels,
+                      const int32_t* h, const int32_t* w, int C, int dtype);
+
+/* ---- the hot path ---------------------------------------------------------
+ * mtm_score_map: cv2.matchTemplate(image, template, method) at
+ * MTM/__init__.py:92 for template `tmpl`; writes (H-h+1)*(W-w+1) floats. */
+int mtm_score_map(mtm_ctx* ctx, int tmpl, int method, float* out_host, int64_t out_elems);
+
+/* mtm_find_matches: the per-template loop of MTM.findMatches
+ * (MTM/__init__.py:172-175 -> _multi_compute :179-244): score map, then
+ * cv2.minMaxLoc (n_object == 1, :225-230) or _findLocalMax_/_findLocalMin_
+ * (:231-235 -> skimage peak_local_max :45, scipy find_peaks :34/:40, 1x1 map
+ * :25-30).  n_object < 0 means inf.  Hits come back in template order, each
+ * template's peaks in the reference's order.  Offsets are NOT added. */
+int mtm_find_matches(mtm_ctx* ctx, int method, int64_t n_object, double score_threshold,
+                     mtm_hit* hits, int capacity, int* n_hits);
+
+/* mtm_nms: MTM.NMS (MTM/NMS.py:20-84) including cv2.dnn.NMSBoxes (:78).
+ * keep[] receives indices into hits[] in output order. */
+int mtm_nms(mtm_ctx* ctx, const mtm_hit* hits, int n, double score_threshold,
+            int sort_ascending, int64_t n_object, double max_overlap,
+            int32_t* keep, int* n_keep);
+
+/* mtm_match_templates: MTM.matchTemplates after validation
+ * (MTM/__init__.py:289-296): find + NMS fused on the device, one D2H copy. */
+int mtm_match_templates(mtm_ctx* ctx, int method, int64_t n_object, double score_threshold,
+                        double max_overlap, mtm_hit* hits, int capacity, int* n_hits);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MTM_B200_H */

@@ -1,0 +1,231 @@
+"""ctypes binding of libmtm_b200.so (include/mtm_b200.h).  No CPU fallback:
+loading fails loudly when the library has not been built, and creating a
+context fails loudly when there is no sm_100 GPU."""
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmtm_b200.so")
+
+MTM_OK, MTM_ERR_INVALID, MTM_ERR_CUDA, MTM_ERR_CAPACITY, MTM_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
+MTM_U8, MTM_F32 = 0, 1
+PATH_AUTO, PATH_DIRECT, PATH_TENSOR = 0, 1, 2
+OPT_PATH = 0
+
+HIT_DTYPE = np.dtype([("tmpl", "<i4"), ("x", "<i4"), ("y", "<i4"), ("w", "<i4"), ("h", "<i4"), ("score", "<f4")])
+assert HIT_DTYPE.itemsize == 24
+
+
+class Counters(ctypes.Structure):
+    _fields_ = [("kernel_launches", ctypes.c_int64), ("h2d_bytes", ctypes.c_int64), ("d2h_bytes", ctypes.c_int64)]
+
+
+# name -> (restype, argtypes); mirrors include/mtm_b200.h one to one
+_P = ctypes.c_void_p
+_SIGNATURES = {
+    "mtm_abi_version": (ctypes.c_int, []),
+    "mtm_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(_P)]),
+    "mtm_destroy": (ctypes.c_int, [_P]),
+    "mtm_last_error": (ctypes.c_char_p, [_P]),
+    "mtm_set_stream": (ctypes.c_int, [_P, _P]),
+    "mtm_synchronize": (ctypes.c_int, [_P]),
+    "mtm_set_option": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int64]),
+    "mtm_get_counters": (ctypes.c_int, [_P, ctypes.POINTER(Counters)]),
+    "mtm_reset_counters": (ctypes.c_int, [_P]),
+    "mtm_timer_begin": (ctypes.c_int, [_P]),
+    "mtm_timer_end": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_float)]),
+    "mtm_set_image": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64]),
+    "mtm_set_image_device": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64]),
+    "mtm_set_templates": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(_P), ctypes.POINTER(ctypes.c_int32),
+                                         ctypes.POINTER(ctypes.c_int32), ctypes.c_int, ctypes.c_int]),
+    "mtm_score_map": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, _P, ctypes.c_int64]),
+    "mtm_find_matches": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int64, ctypes.c_double, _P, ctypes.c_int,
+                                        ctypes.POINTER(ctypes.c_int)]),
+    "mtm_nms": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int64, ctypes.c_double,
+                               _P, ctypes.POINTER(ctypes.c_int)]),
+    "mtm_match_templates": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_double, _P,
+                                           ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
+}
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def load():
+    """dlopen libmtm_b200.so and declare every entry point (no GPU needed for this)."""
+    global _lib
+    with _lib_lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    "libmtm_b200.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'` "
+                    "or `python multitemplatematching-python_b200/build.py`. There is no CPU fallback." % LIB_PATH)
+            lib = ctypes.CDLL(LIB_PATH)
+            for name, (res, args) in _SIGNATURES.items():
+                fn = getattr(lib, name)      # AttributeError if the library lacks a declared symbol
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    return _lib
+
+
+class NativeError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libmtm_b200 error %d: %s" % (code, msg))
+        self.code = code
+        self.msg = msg
+
+
+def _dtype_code(arr):
+    if arr.dtype == np.uint8:
+        return MTM_U8
+    if arr.dtype == np.float32:
+        return MTM_F32
+    raise TypeError("unsupported dtype %s" % arr.dtype)
+
+
+class Context:
+    """One CUDA stream + device workspaces on one GPU.  Not re-entrant (guarded by a lock)."""
+
+    def __init__(self, device=0):
+        self._lib = load()
+        handle = _P()
+        rc = self._lib.mtm_create(int(device), ctypes.byref(handle))
+        if rc != MTM_OK:
+            raise NativeError(rc, (self._lib.mtm_last_error(None) or b"").decode())
+        self._h = handle
+        self.device = int(device)
+        self.lock = threading.RLock()
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.mtm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != MTM_OK:
+            raise NativeError(rc, (self._lib.mtm_last_error(self._h) or b"").decode())
+
+    # -- plumbing ---------------------------------------------------------------
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self._lib.mtm_set_stream(self._h, _P(cuda_stream_ptr or 0)))
+
+    def synchronize(self):
+        self._check(self._lib.mtm_synchronize(self._h))
+
+    def set_path(self, path):
+        self._check(self._lib.mtm_set_option(self._h, OPT_PATH, int(path)))
+
+    def counters(self):
+        c = Counters()
+        self._check(self._lib.mtm_get_counters(self._h, ctypes.byref(c)))
+        return {"kernel_launches": c.kernel_launches, "h2d_bytes": c.h2d_bytes, "d2h_bytes": c.d2h_bytes}
+
+    def reset_counters(self):
+        self._check(self._lib.mtm_reset_counters(self._h))
+
+    def timer_begin(self):
+        self._check(self._lib.mtm_timer_begin(self._h))
+
+    def timer_end(self):
+        ms = ctypes.c_float()
+        self._check(self._lib.mtm_timer_end(self._h, ctypes.byref(ms)))
+        return float(ms.value)
+
+    # -- inputs -----------------------------------------------------------------
+    @staticmethod
+    def _image_view(image):
+        """Returns (array kept alive, H, W, C, row_stride) with rows internally contiguous."""
+        if image.ndim not in (2, 3):
+            raise ValueError("image must be 2-D (grayscale) or 3-D (H, W, C)")
+        C = 1 if image.ndim == 2 else image.shape[2]
+        item = image.dtype.itemsize
+        inner_ok = (image.strides[1] == item * C) and (image.ndim == 2 or image.strides[2] == item)
+        if not inner_ok or image.strides[0] < image.shape[1] * C * item:
+            image = np.ascontiguousarray(image)
+        return image, image.shape[0], image.shape[1], C, image.strides[0]
+
+    def set_image(self, image):
+        arr, H, W, C, stride = self._image_view(image)
+        self._check(self._lib.mtm_set_image(self._h, _P(arr.ctypes.data), H, W, C, _dtype_code(arr), stride))
+
+    def set_image_device(self, dev_ptr, H, W, C, row_stride, dtype=MTM_U8):
+        self._check(self._lib.mtm_set_image_device(self._h, _P(dev_ptr), H, W, C, dtype, row_stride))
+
+    def set_templates(self, templates):
+        arrs = [np.ascontiguousarray(t) for t in templates]
+        n = len(arrs)
+        if n == 0:
+            raise ValueError("empty template list")
+        C = 1 if arrs[0].ndim == 2 else arrs[0].shape[2]
+        code = _dtype_code(arrs[0])
+        for a in arrs:
+            if (1 if a.ndim == 2 else a.shape[2]) != C or _dtype_code(a) != code:
+                raise ValueError("templates must share dtype and channel count")
+        ptrs = (_P * n)(*[a.ctypes.data for a in arrs])
+        hs = (ctypes.c_int32 * n)(*[a.shape[0] for a in arrs])
+        ws = (ctypes.c_int32 * n)(*[a.shape[1] for a in arrs])
+        self._check(self._lib.mtm_set_templates(self._h, n, ptrs, hs, ws, C, code))
+        self._tmpl_shapes = [a.shape[:2] for a in arrs]
+
+    # -- hot path ---------------------------------------------------------------
+    def score_map(self, tmpl, method, map_shape):
+        out = np.empty(map_shape, np.float32)
+        self._check(self._lib.mtm_score_map(self._h, int(tmpl), int(method), _P(out.ctypes.data), out.size))
+        return out
+
+    def _hits_call(self, fn, args, capacity=4096):
+        while True:
+            buf = np.empty(capacity, HIT_DTYPE)
+            n = ctypes.c_int(0)
+            rc = fn(self._h, *args, _P(buf.ctypes.data), capacity, ctypes.byref(n))
+            if rc == MTM_ERR_CAPACITY:
+                capacity = max(2 * capacity, int(n.value))
+                continue
+            self._check(rc)
+            return buf[: n.value]
+
+    def find_matches(self, method, n_object, score_threshold):
+        return self._hits_call(self._lib.mtm_find_matches, (int(method), int(n_object), float(score_threshold)))
+
+    def match_templates(self, method, n_object, score_threshold, max_overlap):
+        return self._hits_call(self._lib.mtm_match_templates,
+                               (int(method), int(n_object), float(score_threshold), float(max_overlap)))
+
+    def nms(self, hits, score_threshold, sort_ascending, n_object, max_overlap):
+        hits = np.ascontiguousarray(hits, HIT_DTYPE)
+        n = hits.shape[0]
+        keep = np.empty(max(n, 1), np.int32)
+        nk = ctypes.c_int(0)
+        self._check(self._lib.mtm_nms(self._h, _P(hits.ctypes.data), n, float(score_threshold), int(bool(sort_ascending)),
+                                      int(n_object), float(max_overlap), _P(keep.ctypes.data), ctypes.byref(nk)))
+        return keep[: nk.value]
+
+
+_default = {}
+_default_lock = threading.Lock()
+
+
+def default_context(device=None):
+    """Lazily created per-device context used by the module-level API."""
+    if device is None:
+        device = int(os.environ.get("MTM_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    with _default_lock:
+        ctx = _default.get(device)
+        if ctx is None:
+            ctx = _default[device] = Context(device)
+    return ctx

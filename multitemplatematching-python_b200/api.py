@@ -1,0 +1,225 @@
+"""Host-side mirror of the MTM 2.0.1 API for the sliding-window NCC hot path.
+
+Same names, argument order, defaults, return types and exception types as the
+reference (``MTM/__init__.py:56,95,247`` and ``MTM/NMS.py:20``); every array
+operation is executed by libmtm_b200.so on a B200 (see include/mtm_b200.h).
+There is no CPU fallback: input combinations whose GPU kernel is not written yet
+raise ``NotImplementedError``.
+"""
+import warnings
+
+import numpy as np
+
+from . import _native
+
+__all__ = ["computeScoreMap", "findMatches", "matchTemplates", "NMS"]
+
+TM_SQDIFF, TM_SQDIFF_NORMED, TM_CCORR, TM_CCORR_NORMED, TM_CCOEFF, TM_CCOEFF_NORMED = range(6)
+_INF = float("inf")
+
+
+def _cv_error(msg):
+    try:
+        import cv2
+        return cv2.error(msg)
+    except Exception:                      # cv2 is optional for the compute path
+        return ValueError(msg)
+
+
+def _dtype_policy(template, image, mask):
+    """MTM/__init__.py:67-74."""
+    if template.dtype == "float64" or image.dtype == "float64":
+        raise ValueError("64-bit images not supported, max 32-bit")
+    if not (template.dtype == "uint8" and image.dtype == "uint8"):
+        template = np.float32(template)
+        image = np.float32(image)
+        if mask is not None:
+            mask = np.float32(mask)
+    return template, image, mask
+
+
+def _mask_policy(template, mask, method):
+    """MTM/__init__.py:76-88."""
+    if mask is not None:
+        if method not in (0, 3):
+            mask = None
+            warnings.warn("Template matching method not compatible with use of mask (only 0/TM_SQDIFF or 3/TM_CCORR_NORMED).\n-> Ignoring mask.")
+        elif not (mask.shape == template.shape and mask.dtype == template.dtype):
+            mask = None
+            warnings.warn("Mask does not have the same dimension or bit depth than the template.\n-> Ignoring mask.")
+    return mask
+
+
+def _require_gpu_support(image, templates, mask=None):
+    if mask is not None:
+        raise NotImplementedError("masked template matching (methods 0/3 with a mask) has no B200 kernel yet")
+    if image.dtype != np.uint8 or any(t.dtype != np.uint8 for t in templates):
+        raise NotImplementedError("only uint8 images/templates have a B200 kernel so far (float32 path is next)")
+
+
+def computeScoreMap(template, image, method=TM_CCOEFF_NORMED, mask=None, *, context=None):
+    """Score map of ``template`` over ``image`` -- ``MTM.computeScoreMap`` (MTM/__init__.py:56-92).
+
+    Note the argument order (template, image), the reverse of ``cv2.matchTemplate``.
+    Returns a float32 array of shape (H-h+1, W-w+1).
+    """
+    template, image, mask = _dtype_policy(template, image, mask)
+    mask = _mask_policy(template, mask, method)
+    if template.ndim != image.ndim or any(t > i for t, i in zip(template.shape, image.shape)) \
+            or template.shape[2:] != image.shape[2:]:
+        raise _cv_error("matchTemplate: template must not be larger than the image and must have the same channels")
+    _require_gpu_support(image, [template], mask)
+    ctx = context or _native.default_context()
+    with ctx.lock:
+        ctx.set_image(image)
+        ctx.set_templates([template])
+        return ctx.score_map(0, method, (image.shape[0] - template.shape[0] + 1, image.shape[1] - template.shape[1] + 1))
+
+
+def _validate_search(listTemplates, image, N_object, searchBox):
+    """Argument checks of MTM.findMatches (MTM/__init__.py:129-167).  Returns the
+    (possibly cropped) image view and the offsets."""
+    if N_object != _INF and not isinstance(N_object, int):
+        raise TypeError("N_object must be an integer")
+    if image.shape[0] == 0:
+        raise ValueError("Image has a height of 0.")
+    if image.shape[1] == 0:
+        raise ValueError("Image has a width of 0.")
+    xOffset = yOffset = 0
+    if searchBox is not None:
+        xOffset, yOffset, searchWidth, searchHeight = searchBox
+        image = image[yOffset:yOffset + searchHeight, xOffset:xOffset + searchWidth]
+    for index, tempTuple in enumerate(listTemplates):
+        if not isinstance(tempTuple, tuple) or len(tempTuple) < 2:
+            raise ValueError("listTemplates should be a list of tuples as ('name','array') or ('name', 'array', 'mask')")
+        tempName, tempImage = tempTuple[0], tempTuple[1]
+        if tempImage.shape[0] == 0:
+            raise ValueError(f"Template '{tempName}' has a height of 0.")
+        if tempImage.shape[1] == 0:
+            raise ValueError(f"Template '{tempName}' has a width of 0.")
+        if not all(t <= i for t, i in zip(tempImage.shape, image.shape)):
+            fitIn = "searchBox" if (searchBox is not None) else "image"
+            raise ValueError("Template '{}' at index {} in the list of templates is larger than {}.".format(tempName, index, fitIn))
+    return image, xOffset, yOffset
+
+
+def _prepare(listTemplates, image, method):
+    """Per-template mask / dtype policy of _multi_compute + computeScoreMap
+    (MTM/__init__.py:207-222, 67-88) applied to the whole list."""
+    names, arrays = [], []
+    img = image
+    for tempTuple in listTemplates:
+        name, template = tempTuple[:2]
+        mask = None
+        if len(tempTuple) >= 3:
+            if method in (0, 3):
+                mask = tempTuple[2]
+            else:
+                warnings.warn("Template matching method not supporting the use of Mask. Use 0/TM_SQDIFF or 3/TM_CCORR_NORMED.")
+        template, img_t, mask = _dtype_policy(template, image, mask)
+        mask = _mask_policy(template, mask, method)
+        if template.ndim != img_t.ndim or template.shape[2:] != img_t.shape[2:]:
+            raise _cv_error("matchTemplate: image and template must have the same number of dimensions/channels")
+        _require_gpu_support(img_t, [template], mask)
+        img = img_t
+        names.append(name)
+        arrays.append(template)
+    return names, arrays, img
+
+
+def _native_n_object(N_object):
+    if N_object == _INF:
+        return -1
+    return 1 if N_object == 1 else -1      # only "exactly one" changes the peak search (MTM/__init__.py:225)
+
+
+def _to_hits(raw, names, xOffset, yOffset):
+    return [(names[int(r["tmpl"])], (int(r["x"]) + xOffset, int(r["y"]) + yOffset, int(r["w"]), int(r["h"])), r["score"])
+            for r in raw]
+
+
+def findMatches(listTemplates, image, method=TM_CCOEFF_NORMED, N_object=_INF, score_threshold=0.5,
+                searchBox=None, *, context=None):
+    """All candidate hits before NMS -- ``MTM.findMatches`` (MTM/__init__.py:95-177).
+
+    Hits are returned in template-list order (the reference appends them in
+    thread-completion order, so any order it can produce is a permutation of this
+    one), each template's hits in the order its peak finder yields them.
+    """
+    image, xOffset, yOffset = _validate_search(listTemplates, image, N_object, searchBox)
+    if len(listTemplates) == 0:
+        return []
+    names, arrays, img = _prepare(listTemplates, image, method)
+    ctx = context or _native.default_context()
+    with ctx.lock:
+        ctx.set_image(img)
+        ctx.set_templates(arrays)
+        raw = ctx.find_matches(method, _native_n_object(N_object), score_threshold)
+    return _to_hits(raw, names, xOffset, yOffset)
+
+
+def matchTemplates(listTemplates, image, method=TM_CCOEFF_NORMED, N_object=_INF, score_threshold=0.5,
+                   maxOverlap=0.25, searchBox=None, *, context=None):
+    """Best non-overlapping hits -- ``MTM.matchTemplates`` (MTM/__init__.py:247-296).
+
+    Search, peak extraction, sorting and NMS all run on the device; one small
+    device->host copy brings back the final hit list.
+    """
+    if maxOverlap < 0 or maxOverlap > 1:
+        raise ValueError("Maximal overlap between bounding box is in range [0-1]")
+    if method == 0:
+        # the reference searches first and rejects TM_SQDIFF afterwards (MTM/__init__.py:289-292)
+        findMatches(listTemplates, image, method, N_object, score_threshold, searchBox, context=context)
+        raise ValueError("The method TM_SQDIFF is not supported. Use TM_SQDIFF_NORMED instead.")
+    crop, xOffset, yOffset = _validate_search(listTemplates, image, N_object, searchBox)
+    if len(listTemplates) == 0:
+        return []
+    names, arrays, img = _prepare(listTemplates, crop, method)
+    finite = N_object != _INF
+    nms_threshold = (1 - score_threshold) if method == 1 else score_threshold
+    if (finite and N_object < 1) or nms_threshold < 0:
+        # rare corners whose behaviour depends on the pre-NMS list length (nHits<=1 short-cut before
+        # the [:N_object] cut, NMSBoxes' score_threshold>=0 assertion): run the two stages separately
+        hits = findMatches(listTemplates, image, method, N_object, score_threshold, searchBox, context=context)
+        return NMS(hits, score_threshold, method == 1, N_object, maxOverlap, context=context)
+    n_dev = int(N_object) if finite else -1
+    ctx = context or _native.default_context()
+    with ctx.lock:
+        ctx.set_image(img)
+        ctx.set_templates(arrays)
+        raw = ctx.match_templates(method, n_dev, score_threshold, maxOverlap)
+    return _to_hits(raw, names, xOffset, yOffset)
+
+
+def NMS(listHit, scoreThreshold=0.5, sortAscending=False, N_object=_INF, maxOverlap=0.5, *, context=None):
+    """Non-maxima suppression of a hit list -- ``MTM.NMS.NMS`` (MTM/NMS.py:20-84)."""
+    nHits = len(listHit)
+    if nHits <= 1:
+        return listHit[:]
+    boxes = [hit[1] for hit in listHit]
+    scores = [hit[2] for hit in listHit]
+    raw = np.zeros(nHits, _native.HIT_DTYPE)
+    raw["tmpl"] = np.arange(nHits)
+    b = np.asarray(boxes, dtype=np.int64).reshape(nHits, 4)
+    raw["x"], raw["y"], raw["w"], raw["h"] = b[:, 0], b[:, 1], b[:, 2], b[:, 3]
+    ctx = context or _native.default_context()
+    if N_object == 1:
+        raw["score"] = np.asarray(scores, dtype=np.float32)
+        with ctx.lock:
+            keep = ctx.nms(raw, 0.0, sortAscending, 1, maxOverlap)
+        return [listHit[int(i)] for i in keep]
+    if sortAscending:
+        # list plumbing of MTM/NMS.py:73-75 (keeps Python's own float semantics for `1 - score`)
+        scores = [1 - s for s in scores]
+        scoreThreshold = 1 - scoreThreshold
+    if scoreThreshold < 0 or maxOverlap < 0:
+        raise _cv_error("NMSBoxes: score_threshold >= 0 and nms_threshold >= 0 are required")
+    raw["score"] = np.asarray(scores, dtype=np.float32)
+    finite = N_object != _INF
+    n_dev = int(N_object) if (finite and N_object > 1) else -1
+    with ctx.lock:
+        keep = ctx.nms(raw, scoreThreshold, False, n_dev, maxOverlap)
+    keep = [int(i) for i in keep]
+    if finite:
+        keep = keep[:N_object]
+    return [listHit[i] for i in keep]

@@ -1,0 +1,458 @@
+// mtm_api.cu -- the C ABI of libmtm_b200.so (include/mtm_b200.h): context, uploads,
+// and the host-side sequencing of the kernels.  No arithmetic happens here.
+#include "mtm_internal.cuh"
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+static thread_local std::string g_create_err;
+
+int mtm_fail(mtm_ctx* ctx, int code, const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_create_err = buf;
+    return code;
+}
+
+template <typename T>
+int mtm_reserve(mtm_ctx* ctx, T*& ptr, size_t& cap, size_t need)
+{
+    if (need <= cap && ptr) return MTM_OK;
+    if (ptr) { MTM_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); MTM_CUDA(ctx, cudaFree(ptr)); ptr = nullptr; cap = 0; }
+    const size_t want = need + need / 8 + 64;
+    MTM_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ptr), want * sizeof(T)));
+    MTM_CUDA(ctx, cudaMemsetAsync(ptr, 0, want * sizeof(T), ctx->stream));
+    cap = want;
+    return MTM_OK;
+}
+
+template <typename T>
+static int reserve_pinned(mtm_ctx* ctx, T*& ptr, size_t& cap, size_t need)
+{
+    if (need <= cap && ptr) return MTM_OK;
+    if (ptr) { MTM_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); MTM_CUDA(ctx, cudaFreeHost(ptr)); ptr = nullptr; cap = 0; }
+    const size_t want = need + need / 8 + 64;
+    MTM_CUDA(ctx, cudaMallocHost(reinterpret_cast<void**>(&ptr), want * sizeof(T)));
+    cap = want;
+    return MTM_OK;
+}
+
+#define MTM_TRY(expr) do { int rc__ = (expr); if (rc__ != MTM_OK) return rc__; } while (0)
+#define MTM_ENTER(ctx)                                                        \
+    if (!(ctx)) return MTM_ERR_INVALID;                                       \
+    MTM_CUDA(ctx, cudaSetDevice((ctx)->device))
+
+static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+static int reserve_hits(mtm_ctx* ctx, int cap)
+{
+    cap = next_pow2(std::max(cap, 1024));
+    if (cap <= ctx->hit_cap) return MTM_OK;
+    MTM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_blockA) cudaFree(ctx->d_blockA);
+    if (ctx->d_blockB) cudaFree(ctx->d_blockB);
+    if (ctx->d_keep) cudaFree(ctx->d_keep);
+    ctx->d_blockA = ctx->d_blockB = nullptr; ctx->d_keep = nullptr; ctx->hit_cap = 0;
+    const size_t bytes = MTM_HIT_HEADER + (size_t)cap * sizeof(DevHit);
+    MTM_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_blockA), bytes));
+    MTM_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_blockB), bytes));
+    MTM_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_keep), (size_t)cap * sizeof(int32_t)));
+    MTM_CUDA(ctx, cudaMemsetAsync(ctx->d_blockA, 0, bytes, ctx->stream));
+    MTM_CUDA(ctx, cudaMemsetAsync(ctx->d_blockB, 0, bytes, ctx->stream));
+    ctx->hit_cap = cap;
+    MTM_TRY(reserve_pinned(ctx, ctx->h_stage, ctx->h_stage_cap, bytes));
+    return MTM_OK;
+}
+
+extern "C" {
+
+int mtm_abi_version(void) { return MTM_ABI_VERSION; }
+
+const char* mtm_last_error(const mtm_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int mtm_create(int device, mtm_ctx** out)
+{
+    if (!out) return mtm_fail(nullptr, MTM_ERR_INVALID, "mtm_create: null output pointer");
+    *out = nullptr;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return mtm_fail(nullptr, MTM_ERR_CUDA, "mtm_create: no CUDA device (%s); libmtm_b200 has no CPU fallback",
+                        e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= n_dev)
+        return mtm_fail(nullptr, MTM_ERR_INVALID, "mtm_create: device %d out of range [0, %d)", device, n_dev);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+        return mtm_fail(nullptr, MTM_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return mtm_fail(nullptr, MTM_ERR_CUDA, "mtm_create: device %d is sm_%d%d; libmtm_b200 is built for sm_100a only",
+                        device, prop.major, prop.minor);
+    mtm_ctx* ctx = new mtm_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    auto bail = [&](const char* what, cudaError_t err) {
+        int rc = mtm_fail(nullptr, MTM_ERR_CUDA, "%s: %s", what, cudaGetErrorString(err));
+        delete ctx;
+        return rc;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    ctx->stream = ctx->own_stream;
+    if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
+    int rc = reserve_hits(ctx, 1 << 16);
+    if (rc != MTM_OK) { g_create_err = ctx->err; mtm_destroy(ctx); return rc; }
+    *out = ctx;
+    return MTM_OK;
+}
+
+int mtm_destroy(mtm_ctx* ctx)
+{
+    if (!ctx) return MTM_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->img.pix); cudaFree(ctx->img.sat_s); cudaFree(ctx->img.sat_q); cudaFree(ctx->scratch);
+    cudaFree(ctx->d_meta); cudaFree(ctx->d_tmpl); cudaFree(ctx->d_maps); cudaFree(ctx->d_order);
+    cudaFree(ctx->d_blockA); cudaFree(ctx->d_blockB); cudaFree(ctx->d_keep);
+    cudaFree(ctx->d_nontrivial); cudaFree(ctx->d_best);
+    cudaFreeHost(ctx->h_tmpl_stage); cudaFreeHost(ctx->h_stage); cudaFreeHost(ctx->h_geom);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return MTM_OK;
+}
+
+int mtm_set_stream(mtm_ctx* ctx, void* cuda_stream)
+{
+    MTM_ENTER(ctx);
+    MTM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return MTM_OK;
+}
+
+int mtm_synchronize(mtm_ctx* ctx)
+{
+    MTM_ENTER(ctx);
+    MTM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MTM_OK;
+}
+
+int mtm_set_option(mtm_ctx* ctx, int option, int64_t value)
+{
+    if (!ctx) return MTM_ERR_INVALID;
+    if (option == MTM_OPT_PATH && value >= MTM_PATH_AUTO && value <= MTM_PATH_TENSOR) { ctx->path = (int)value; return MTM_OK; }
+    return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_option: unknown option %d / value %lld", option, (long long)value);
+}
+
+int mtm_get_counters(mtm_ctx* ctx, mtm_counters* out)
+{
+    if (!ctx || !out) return MTM_ERR_INVALID;
+    *out = ctx->ctr;
+    return MTM_OK;
+}
+
+int mtm_reset_counters(mtm_ctx* ctx)
+{
+    if (!ctx) return MTM_ERR_INVALID;
+    ctx->ctr = mtm_counters{};
+    return MTM_OK;
+}
+
+int mtm_timer_begin(mtm_ctx* ctx)
+{
+    MTM_ENTER(ctx);
+    MTM_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    return MTM_OK;
+}
+
+int mtm_timer_end(mtm_ctx* ctx, float* elapsed_ms)
+{
+    MTM_ENTER(ctx);
+    if (!elapsed_ms) return MTM_ERR_INVALID;
+    MTM_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    MTM_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+    MTM_CUDA(ctx, cudaEventElapsedTime(elapsed_ms, ctx->ev0, ctx->ev1));
+    return MTM_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------
+static int set_image_impl(mtm_ctx* ctx, const void* pixels, int H, int W, int C, int dtype,
+                          int64_t row_stride, bool on_device)
+{
+    MTM_ENTER(ctx);
+    if (!pixels || H <= 0 || W <= 0) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_image: empty image (%d x %d)", H, W);
+    if (C < 1 || C > MTM_MAX_CH) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_image: %d channels (1..4 supported)", C);
+    if (dtype != MTM_U8) return mtm_fail(ctx, MTM_ERR_UNSUPPORTED, "mtm_set_image: only uint8 images are implemented on the GPU path");
+    if ((int64_t)W * C > 66000) return mtm_fail(ctx, MTM_ERR_UNSUPPORTED, "mtm_set_image: rows wider than 66000 bytes");
+    if (row_stride < (int64_t)W * C) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_image: row stride %lld < %d", (long long)row_stride, W * C);
+    ImageDev& im = ctx->img;
+    const int64_t pitch = (((int64_t)W * C + 64 * C + 64) + 127) / 128 * 128;
+    const bool reshape = (im.H != H || im.W != W || im.C != C);
+    MTM_TRY(mtm_reserve(ctx, im.pix, ctx->img_cap, (size_t)(H * pitch + 256)));
+    if (reshape) MTM_CUDA(ctx, cudaMemsetAsync(im.pix, 0, ctx->img_cap, ctx->stream));
+    im.pitch = pitch; im.H = H; im.W = W; im.C = C;
+    im.sat_pitch = ((int64_t)W + 1 + 3) / 4 * 4;
+    MTM_CUDA(ctx, cudaMemcpy2DAsync(im.pix, (size_t)pitch, pixels, (size_t)row_stride, (size_t)W * C, (size_t)H,
+                                    on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+    if (!on_device) ctx->ctr.h2d_bytes += (int64_t)H * W * C;
+    MTM_TRY(mtm_reserve(ctx, im.sat_s, ctx->sat_s_cap, (size_t)C * (H + 1) * im.sat_pitch));
+    MTM_TRY(mtm_reserve(ctx, im.sat_q, ctx->sat_q_cap, (size_t)(H + 1) * im.sat_pitch));
+    MTM_TRY(mtm_reserve(ctx, ctx->scratch, ctx->scratch_cap, (size_t)(C + 1) * H * W));
+    ctx->img_dtype = dtype;
+    ctx->geometry_valid = false;
+    MTM_TRY(launch_build_sat(ctx));
+    return MTM_OK;
+}
+
+static int ensure_geometry(mtm_ctx* ctx)
+{
+    if (ctx->img.H == 0) return mtm_fail(ctx, MTM_ERR_INVALID, "no image set (call mtm_set_image first)");
+    if (ctx->n_tmpl == 0) return mtm_fail(ctx, MTM_ERR_INVALID, "no templates set (call mtm_set_templates first)");
+    if (ctx->geometry_valid) return MTM_OK;
+    if (ctx->tmpl_C != ctx->img.C || ctx->tmpl_dtype != ctx->img_dtype)
+        return mtm_fail(ctx, MTM_ERR_INVALID, "image and templates differ in channel count or dtype");
+    const int n = ctx->n_tmpl;
+    int64_t off = 0;
+    for (int t = 0; t < n; ++t) {
+        TmplMeta& m = ctx->h_meta[t];
+        if (m.h > ctx->img.H || m.w > ctx->img.W)
+            return mtm_fail(ctx, MTM_ERR_INVALID, "template %d (%d x %d) is larger than the image (%d x %d)", t, m.h, m.w,
+                            ctx->img.H, ctx->img.W);
+        m.mh = ctx->img.H - m.h + 1;
+        m.mw = ctx->img.W - m.w + 1;
+        m.map_off = off;
+        off += ((int64_t)m.mh * m.mw + 31) / 32 * 32;
+        ctx->h_geom[t].map_off = m.map_off; ctx->h_geom[t].mh = m.mh; ctx->h_geom[t].mw = m.mw;
+    }
+    ctx->maps_total = off;
+    MTM_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_meta, sizeof(TmplMeta), ctx->h_geom, sizeof(TmplGeom), sizeof(TmplGeom),
+                                    (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    MTM_TRY(mtm_reserve(ctx, ctx->d_maps, ctx->maps_cap, (size_t)off));
+    ctx->geometry_valid = true;
+    return MTM_OK;
+}
+
+// Score maps of every template (tmpl < 0) or of one template, grouped by template size.
+static int compute_maps(mtm_ctx* ctx, int method, int tmpl)
+{
+    if (method < 0 || method > 5) return mtm_fail(ctx, MTM_ERR_INVALID, "unknown method %d", method);
+    const int n = ctx->n_tmpl;
+    int i = 0;
+    while (i < n) {
+        const TmplMeta& a = ctx->h_meta[ctx->h_order[i]];
+        int j = i + 1;
+        while (j < n && ctx->h_meta[ctx->h_order[j]].h == a.h && ctx->h_meta[ctx->h_order[j]].w == a.w) ++j;
+        if (tmpl < 0) {
+            MTM_TRY(launch_ncc_direct(ctx, method, i, j - i));
+        } else {
+            for (int k = i; k < j; ++k)
+                if (ctx->h_order[k] == tmpl) MTM_TRY(launch_ncc_direct(ctx, method, k, 1));
+        }
+        i = j;
+    }
+    return MTM_OK;
+}
+
+// Downloads header + hits of a block into h_stage.  Returns the raw count in *n_raw.
+static int download_block(mtm_ctx* ctx, const uint8_t* d_block, int* n_raw, int* n_valid)
+{
+    const int PRE = 256;
+    const int pre = std::min(PRE, ctx->hit_cap);
+    const size_t first = MTM_HIT_HEADER + (size_t)pre * sizeof(DevHit);
+    MTM_CUDA(ctx, cudaMemcpyAsync(ctx->h_stage, d_block, first, cudaMemcpyDeviceToHost, ctx->stream));
+    MTM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->ctr.d2h_bytes += (int64_t)first;
+    const int32_t* hdr = reinterpret_cast<const int32_t*>(ctx->h_stage);
+    const int n = hdr[0];
+    *n_valid = n;
+    *n_raw = std::max(hdr[0], hdr[1]);
+    if (n > pre && n <= ctx->hit_cap) {
+        const size_t rest = (size_t)(n - pre) * sizeof(DevHit);
+        MTM_CUDA(ctx, cudaMemcpyAsync(ctx->h_stage + first, d_block + first, rest, cudaMemcpyDeviceToHost, ctx->stream));
+        MTM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->ctr.d2h_bytes += (int64_t)rest;
+    }
+    return MTM_OK;
+}
+
+static void copy_out(const mtm_ctx* ctx, mtm_hit* hits, int n)
+{
+    const DevHit* src = reinterpret_cast<const DevHit*>(ctx->h_stage + MTM_HIT_HEADER);
+    for (int i = 0; i < n; ++i) {
+        hits[i].tmpl = src[i].tmpl; hits[i].x = src[i].x; hits[i].y = src[i].y;
+        hits[i].w = src[i].w; hits[i].h = src[i].h; hits[i].score = src[i].score;
+    }
+}
+
+extern "C" {
+
+int mtm_set_image(mtm_ctx* ctx, const void* pixels, int H, int W, int C, int dtype, int64_t row_stride_bytes)
+{
+    return set_image_impl(ctx, pixels, H, W, C, dtype, row_stride_bytes, false);
+}
+
+int mtm_set_image_device(mtm_ctx* ctx, const void* d_pixels, int H, int W, int C, int dtype, int64_t row_stride_bytes)
+{
+    return set_image_impl(ctx, d_pixels, H, W, C, dtype, row_stride_bytes, true);
+}
+
+int mtm_set_templates(mtm_ctx* ctx, int n, const void* const* pixels, const int32_t* h, const int32_t* w, int C, int dtype)
+{
+    MTM_ENTER(ctx);
+    if (n <= 0 || !pixels || !h || !w) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_templates: empty template list");
+    if (C < 1 || C > MTM_MAX_CH) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_templates: %d channels (1..4 supported)", C);
+    if (dtype != MTM_U8) return mtm_fail(ctx, MTM_ERR_UNSUPPORTED, "mtm_set_templates: only uint8 templates are implemented on the GPU path");
+    // the previous upload may still be reading the pinned staging buffers
+    MTM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->h_meta.assign(n, TmplMeta{});
+    size_t total = 0;
+    for (int t = 0; t < n; ++t) {
+        if (!pixels[t] || h[t] <= 0 || w[t] <= 0)
+            return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_templates: template %d is empty", t);
+        TmplMeta& m = ctx->h_meta[t];
+        m.h = h[t]; m.w = w[t];
+        m.wp = (w[t] * C + 3) / 4 * 4;
+        m.pix_off = (int64_t)total;
+        total += ((size_t)m.wp * m.h + 15) / 16 * 16;
+    }
+    MTM_TRY(reserve_pinned(ctx, ctx->h_tmpl_stage, ctx->tmpl_stage_cap, total));
+    MTM_TRY(reserve_pinned(ctx, ctx->h_geom, ctx->geom_cap, (size_t)n));
+    memset(ctx->h_tmpl_stage, 0, total);
+    for (int t = 0; t < n; ++t) {
+        const TmplMeta& m = ctx->h_meta[t];
+        const uint8_t* src = static_cast<const uint8_t*>(pixels[t]);
+        uint8_t* dst = ctx->h_tmpl_stage + m.pix_off;
+        const size_t row = (size_t)m.w * C;
+        for (int y = 0; y < m.h; ++y) memcpy(dst + (size_t)y * m.wp, src + (size_t)y * row, row);
+    }
+    MTM_TRY(mtm_reserve(ctx, ctx->d_tmpl, ctx->tmpl_cap, total + 64));
+    MTM_TRY(mtm_reserve(ctx, ctx->d_meta, ctx->meta_cap, (size_t)n));
+    MTM_TRY(mtm_reserve(ctx, ctx->d_order, ctx->order_cap, (size_t)n));
+    MTM_TRY(mtm_reserve(ctx, ctx->d_nontrivial, ctx->per_tmpl_cap, (size_t)n));
+    MTM_TRY(mtm_reserve(ctx, ctx->d_best, ctx->best_cap, (size_t)n));
+    MTM_CUDA(ctx, cudaMemcpyAsync(ctx->d_tmpl, ctx->h_tmpl_stage, total, cudaMemcpyHostToDevice, ctx->stream));
+    MTM_CUDA(ctx, cudaMemcpyAsync(ctx->d_meta, ctx->h_meta.data(), (size_t)n * sizeof(TmplMeta), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h_order.resize(n);
+    for (int t = 0; t < n; ++t) ctx->h_order[t] = t;
+    std::stable_sort(ctx->h_order.begin(), ctx->h_order.end(), [&](int a, int b) {
+        const TmplMeta &x = ctx->h_meta[a], &y = ctx->h_meta[b];
+        return x.h != y.h ? x.h < y.h : x.w < y.w;
+    });
+    MTM_CUDA(ctx, cudaMemcpyAsync(ctx->d_order, ctx->h_order.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    // h_meta / h_order are pageable: the copies above are staged synchronously by the runtime.
+    ctx->ctr.h2d_bytes += (int64_t)total + (int64_t)n * (sizeof(TmplMeta) + sizeof(int32_t));
+    ctx->n_tmpl = n; ctx->tmpl_C = C; ctx->tmpl_dtype = dtype;
+    ctx->geometry_valid = false;
+    MTM_TRY(launch_tmpl_stats(ctx));
+    return MTM_OK;
+}
+
+int mtm_score_map(mtm_ctx* ctx, int tmpl, int method, float* out_host, int64_t out_elems)
+{
+    MTM_ENTER(ctx);
+    MTM_TRY(ensure_geometry(ctx));
+    if (tmpl < 0 || tmpl >= ctx->n_tmpl) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_score_map: template index %d out of range", tmpl);
+    const TmplMeta& m = ctx->h_meta[tmpl];
+    const int64_t need = (int64_t)m.mh * m.mw;
+    if (!out_host || out_elems < need) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_score_map: output buffer holds %lld floats, need %lld",
+                                                       (long long)out_elems, (long long)need);
+    MTM_TRY(compute_maps(ctx, method, tmpl));
+    MTM_CUDA(ctx, cudaMemcpyAsync(out_host, ctx->d_maps + m.map_off, (size_t)need * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    MTM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->ctr.d2h_bytes += need * (int64_t)sizeof(float);
+    return MTM_OK;
+}
+
+int mtm_find_matches(mtm_ctx* ctx, int method, int64_t n_object, double score_threshold,
+                     mtm_hit* hits, int capacity, int* n_hits)
+{
+    MTM_ENTER(ctx);
+    if (!n_hits || (capacity > 0 && !hits)) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_find_matches: null output");
+    MTM_TRY(ensure_geometry(ctx));
+    MTM_TRY(compute_maps(ctx, method, -1));
+    const int minimize = method_is_min(method) ? 1 : 0;
+    for (int attempt = 0; attempt < 8; ++attempt) {
+        MTM_TRY(launch_peaks(ctx, method, n_object, (float)score_threshold, score_threshold));
+        if (n_object != 1) MTM_TRY(launch_sort_hits(ctx, 0, minimize, 0, 1));
+        int n_raw = 0, n = 0;
+        MTM_TRY(download_block(ctx, ctx->d_blockA, &n_raw, &n));
+        if (n_raw > ctx->hit_cap) { MTM_TRY(reserve_hits(ctx, n_raw)); continue; }
+        *n_hits = n;
+        if (n > capacity) return mtm_fail(ctx, MTM_ERR_CAPACITY, "mtm_find_matches: %d hits, caller capacity %d", n, capacity);
+        copy_out(ctx, hits, n);
+        return MTM_OK;
+    }
+    return mtm_fail(ctx, MTM_ERR_CUDA, "mtm_find_matches: hit buffer kept overflowing");
+}
+
+int mtm_match_templates(mtm_ctx* ctx, int method, int64_t n_object, double score_threshold,
+                        double max_overlap, mtm_hit* hits, int capacity, int* n_hits)
+{
+    MTM_ENTER(ctx);
+    if (!n_hits || (capacity > 0 && !hits)) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_match_templates: null output");
+    if (method == MTM_TM_SQDIFF) return mtm_fail(ctx, MTM_ERR_INVALID, "The method TM_SQDIFF is not supported. Use TM_SQDIFF_NORMED instead.");
+    MTM_TRY(ensure_geometry(ctx));
+    MTM_TRY(compute_maps(ctx, method, -1));
+    const int minimize = method_is_min(method) ? 1 : 0;
+    const int ascending = (method == MTM_TM_SQDIFF_NORMED) ? 1 : 0;
+    const float thr_nms = ascending ? (float)(1.0 - score_threshold) : (float)score_threshold;
+    for (int attempt = 0; attempt < 8; ++attempt) {
+        MTM_TRY(launch_peaks(ctx, method, n_object, (float)score_threshold, score_threshold));
+        if (n_object != 1) {
+            MTM_TRY(launch_sort_hits(ctx, 0, minimize, 0, 1));
+            MTM_TRY(launch_sort_hits(ctx, 1, minimize, ascending, 0));
+        }
+        MTM_TRY(launch_nms(ctx, thr_nms, ascending, n_object, (float)max_overlap));
+        int n_raw = 0, n = 0;
+        MTM_TRY(download_block(ctx, ctx->d_blockB, &n_raw, &n));
+        if (n_raw > ctx->hit_cap) { MTM_TRY(reserve_hits(ctx, n_raw)); continue; }
+        *n_hits = n;
+        if (n > capacity) return mtm_fail(ctx, MTM_ERR_CAPACITY, "mtm_match_templates: %d hits, caller capacity %d", n, capacity);
+        copy_out(ctx, hits, n);
+        return MTM_OK;
+    }
+    return mtm_fail(ctx, MTM_ERR_CUDA, "mtm_match_templates: hit buffer kept overflowing");
+}
+
+int mtm_nms(mtm_ctx* ctx, const mtm_hit* hits, int n, double score_threshold, int sort_ascending,
+            int64_t n_object, double max_overlap, int32_t* keep, int* n_keep)
+{
+    MTM_ENTER(ctx);
+    if (n < 0 || !n_keep || (n > 0 && (!hits || !keep))) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_nms: null argument");
+    if (n == 0) { *n_keep = 0; return MTM_OK; }
+    MTM_TRY(reserve_hits(ctx, n));
+    MTM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int32_t* hdr = reinterpret_cast<int32_t*>(ctx->h_stage);
+    memset(hdr, 0, MTM_HIT_HEADER);
+    hdr[0] = n;
+    DevHit* dst = reinterpret_cast<DevHit*>(ctx->h_stage + MTM_HIT_HEADER);
+    for (int i = 0; i < n; ++i) {
+        dst[i].tmpl = hits[i].tmpl; dst[i].x = hits[i].x; dst[i].y = hits[i].y; dst[i].w = hits[i].w; dst[i].h = hits[i].h;
+        dst[i].score = hits[i].score; dst[i].seq = i; dst[i].key = 0.f;
+    }
+    const size_t bytes = MTM_HIT_HEADER + (size_t)n * sizeof(DevHit);
+    MTM_CUDA(ctx, cudaMemcpyAsync(ctx->d_blockA, ctx->h_stage, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->ctr.h2d_bytes += (int64_t)bytes;
+    const int ascending = sort_ascending ? 1 : 0;
+    const float thr_nms = ascending ? (float)(1.0 - score_threshold) : (float)score_threshold;
+    MTM_TRY(launch_sort_hits(ctx, 1, 0, ascending, 0));
+    MTM_TRY(launch_nms(ctx, thr_nms, ascending, n_object, (float)max_overlap));
+    int n_raw = 0, nk = 0;
+    MTM_TRY(download_block(ctx, ctx->d_blockB, &n_raw, &nk));
+    const DevHit* src = reinterpret_cast<const DevHit*>(ctx->h_stage + MTM_HIT_HEADER);
+    for (int i = 0; i < nk; ++i) keep[i] = src[i].seq;
+    *n_keep = nk;
+    return MTM_OK;
+}
+
+}  // extern "C"
+
+template int mtm_reserve<uint8_t>(mtm_ctx*, uint8_t*&, size_t&, size_t);

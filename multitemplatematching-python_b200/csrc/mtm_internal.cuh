@@ -1,0 +1,134 @@
+// mtm_internal.cuh -- shared declarations of libmtm_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/mtm_b200.h"
+
+#define MTM_MAX_CH 4
+#define MTM_HIT_HEADER 32      // bytes: int32 count[8]; count[0] = number of hits (may exceed capacity)
+
+// Device-side record of one hit (32 bytes); the public mtm_hit is its 24-byte prefix.
+struct DevHit {
+    int32_t tmpl;
+    int32_t x, y, w, h;
+    float score;
+    int32_t seq;     // tie-break rank: position in the canonical (template, peak) order / input order
+    float key;       // NMS sort key: score, or 1-score when sortAscending
+};
+
+// Per-template constants (host fills geometry, tmpl_stats_kernel fills the statistics).
+struct TmplGeom {         // image-dependent part, re-uploaded when the image size changes
+    int64_t map_off;      // element offset of the template's score map in the map arena
+    int32_t mh, mw;       // score map size
+};
+struct TmplMeta {
+    int64_t map_off;      // -- TmplGeom prefix (16 bytes) --
+    int32_t mh, mw;
+    int64_t pix_off;      // byte offset of the packed template in the template arena
+    int32_t h, w;         // template size (pixels)
+    int32_t wp;           // packed row pitch in bytes (w*C rounded up to 4, zero padded)
+    int32_t is_const;     // templNorm < DBL_EPSILON (OpenCV: TM_CCOEFF_NORMED map := 1)
+    double mean[MTM_MAX_CH];   // meanStdDev mean per channel
+    double sum2;               // sum T^2 over all channels  (templSum2 after "/= invArea")
+    double norm_ccoeff;        // sqrt(sum_c var_c) / sqrt(invArea)
+    double norm_plain;         // sqrt(sum_c var_c + mean_c^2) / sqrt(invArea)
+    double inv_area;
+};
+
+struct ImageDev {
+    uint8_t* pix = nullptr;      // u8, interleaved channels, zero padded rows
+    int64_t pitch = 0;           // bytes
+    int H = 0, W = 0, C = 0;
+    uint32_t* sat_s = nullptr;   // C tables of (H+1) x sat_pitch, wrap-around u32 (window sums < 2^32)
+    unsigned long long* sat_q = nullptr;  // (H+1) x sat_pitch, sum over channels of I^2
+    int64_t sat_pitch = 0;       // elements
+};
+
+struct mtm_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    mtm_counters ctr{};
+    int path = MTM_PATH_AUTO;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int sm_count = 0;
+
+    // image
+    ImageDev img;
+    size_t img_cap = 0, sat_s_cap = 0, sat_q_cap = 0, scratch_cap = 0;
+    uint32_t* scratch = nullptr;         // row-prefix scratch for the SAT build
+    int img_dtype = -1;
+
+    // templates
+    int n_tmpl = 0;
+    std::vector<TmplMeta> h_meta;
+    TmplMeta* d_meta = nullptr; size_t meta_cap = 0;
+    uint8_t* d_tmpl = nullptr; size_t tmpl_cap = 0;
+    uint8_t* h_tmpl_stage = nullptr; size_t tmpl_stage_cap = 0;   // pinned
+    int tmpl_C = 0, tmpl_dtype = -1;
+    bool geometry_valid = false;         // map offsets computed for (image, templates)
+
+    // score maps
+    float* d_maps = nullptr; size_t maps_cap = 0;   // elements
+    int64_t maps_total = 0;
+    int maps_method = -1;                // method the resident maps were computed with (-1: stale)
+
+    int32_t* d_order = nullptr; size_t order_cap = 0;   // template indices sorted by (h, w)
+    std::vector<int32_t> h_order;
+    TmplGeom* h_geom = nullptr; size_t geom_cap = 0;     // pinned
+
+    // hits: two device blocks, each = HitHeader + DevHit[hit_cap]
+    uint8_t* d_blockA = nullptr; uint8_t* d_blockB = nullptr;
+    int hit_cap = 0;                     // device capacity per block (power of two)
+    int32_t* d_nontrivial = nullptr;     // per template: some pixel is not a 3x3 max
+    unsigned long long* d_best = nullptr;// per template arg-max key
+    int32_t* d_keep = nullptr;           // kept indices (capacity hit_cap)
+    size_t per_tmpl_cap = 0, best_cap = 0;
+    uint8_t* h_stage = nullptr; size_t h_stage_cap = 0;   // pinned up/download buffer
+
+    int32_t* countA() const { return reinterpret_cast<int32_t*>(d_blockA); }
+    int32_t* countB() const { return reinterpret_cast<int32_t*>(d_blockB); }
+    DevHit* hitsA() const { return reinterpret_cast<DevHit*>(d_blockA + MTM_HIT_HEADER); }
+    DevHit* hitsB() const { return reinterpret_cast<DevHit*>(d_blockB + MTM_HIT_HEADER); }
+};
+
+int mtm_fail(mtm_ctx* ctx, int code, const char* fmt, ...);
+#define MTM_CUDA(ctx, call)                                                          \
+    do {                                                                             \
+        cudaError_t e__ = (call);                                                    \
+        if (e__ != cudaSuccess)                                                      \
+            return mtm_fail(ctx, MTM_ERR_CUDA, "%s failed: %s (%s:%d)", #call,       \
+                            cudaGetErrorString(e__), __FILE__, __LINE__);            \
+    } while (0)
+#define MTM_LAUNCH_CHECK(ctx)                                                        \
+    do {                                                                             \
+        (ctx)->ctr.kernel_launches++;                                                \
+        MTM_CUDA(ctx, cudaGetLastError());                                           \
+    } while (0)
+
+template <typename T>
+int mtm_reserve(mtm_ctx* ctx, T*& ptr, size_t& cap, size_t need_elems);
+
+// ---- kernels (defined in the .cu files) -------------------------------------
+int launch_build_sat(mtm_ctx* ctx);
+int launch_tmpl_stats(mtm_ctx* ctx);
+// templates d_order[first .. first+count) share (h, w)
+int launch_ncc_direct(mtm_ctx* ctx, int method, int first, int count);
+// raw (unsorted) peaks of every template -> block A
+int launch_peaks(mtm_ctx* ctx, int method, int64_t n_object, float thr32, double thr64);
+// in-place sort of block A (mode 0: findMatches order, mode 1: NMSBoxes order)
+int launch_sort_hits(mtm_ctx* ctx, int mode, int minimize, int ascending_key, int check_trivial);
+// block A (sorted mode 1) -> block B
+int launch_nms(mtm_ctx* ctx, float thr32, int ascending, int64_t n_object, float max_overlap);
+
+// ---- shared device helpers ----------------------------------------------------
+__host__ __device__ inline bool method_is_min(int method) { return method == 0 || method == 1; }
+
+__device__ __forceinline__ uint32_t ordered_f32(float f) {
+    f += 0.0f;                                    // -0 -> +0
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}

@@ -1,0 +1,194 @@
+// nms.cu -- K7: hit ordering and greedy IoU suppression on the device.
+//
+//  * sort_hits_kernel : bitonic sort of the hit buffer (single CTA, no host sync;
+//      the count is read from device memory).
+//      mode 0 = the order MTM.findMatches produces when templates are visited in
+//               list order (MTM/__init__.py:172-175,238-244): template index, then
+//               the peak finder's order (descending score with row-major ties for
+//               peak_local_max; ascending index for the 1-D find_peaks maps);
+//      mode 1 = cv2.dnn.NMSBoxes' std::stable_sort by descending score
+//               (GetMaxScoreIndex), ties keep list order (seq).
+//  * nms_kernel : MTM.NMS (MTM/NMS.py:20-84): the nHits<=1 and N_object==1
+//      short-cuts, the 'score > threshold' filter, NMSFast_'s greedy loop with
+//      rectOverlap = 1.f - (float)jaccardDistance(Rect_<int>) and the [:N_object] cut.
+#include "mtm_internal.cuh"
+#include <math_constants.h>
+
+namespace {
+
+struct SortCtx {
+    const TmplMeta* meta;
+    int mode;
+    int minimize;
+};
+
+__device__ __forceinline__ bool hit_less(const DevHit& a, const DevHit& b, const SortCtx& s)
+{
+    if (s.mode == 0) {
+        if (a.tmpl != b.tmpl) return a.tmpl < b.tmpl;
+        if (a.tmpl == 0x7fffffff) return false;
+        const TmplMeta& tm = s.meta[a.tmpl];
+        const long long la = (long long)a.y * tm.mw + a.x, lb = (long long)b.y * tm.mw + b.x;
+        if (tm.mh != 1 && tm.mw != 1) {
+            const float ka = s.minimize ? -a.score : a.score, kb = s.minimize ? -b.score : b.score;
+            if (ka != kb) return ka > kb;
+        }
+        return la < lb;
+    }
+    if (a.key != b.key) return a.key > b.key;
+    return a.seq < b.seq;
+}
+
+__device__ __forceinline__ DevHit load_hit(const DevHit* p)
+{
+    DevHit h;
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = q[0], b = q[1];
+    *reinterpret_cast<uint4*>(&h) = a;
+    *(reinterpret_cast<uint4*>(&h) + 1) = b;
+    return h;
+}
+__device__ __forceinline__ void store_hit(DevHit* p, const DevHit& h)
+{
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = *reinterpret_cast<const uint4*>(&h);
+    q[1] = *(reinterpret_cast<const uint4*>(&h) + 1);
+}
+
+// count[0] = number of hits.  mode 0 drops the hits of "trivial" templates (constant map
+// rule of peak_local_max) and, when assign_seq, numbers the survivors.
+__global__ void __launch_bounds__(1024, 1)
+sort_hits_kernel(DevHit* __restrict__ hits, int cap, int32_t* __restrict__ count, const TmplMeta* __restrict__ meta,
+                 const int32_t* __restrict__ nontrivial, int mode, int minimize, int ascending_key, int check_trivial)
+{
+    __shared__ int dead;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    int n = count[0];
+    if (n > cap) n = cap;                       // overflow is reported by the host from count[0]
+    if (tid == 0) dead = 0;
+    __syncthreads();
+    int npad = 1;
+    while (npad < n) npad <<= 1;
+    // pre-pass
+    for (int i = tid; i < npad; i += nth) {
+        if (i >= n) {
+            DevHit s;
+            s.tmpl = 0x7fffffff; s.x = s.y = s.w = s.h = 0; s.score = 0.f; s.seq = 0x7fffffff; s.key = -CUDART_INF_F;
+            store_hit(hits + i, s);
+        } else if (mode == 0) {
+            if (check_trivial && !nontrivial[hits[i].tmpl]) {
+                hits[i].tmpl = 0x7fffffff;
+                hits[i].key = -CUDART_INF_F;
+                hits[i].seq = 0x7fffffff;
+                atomicAdd(&dead, 1);
+            }
+        } else {
+            hits[i].key = ascending_key ? 1.0f - hits[i].score : hits[i].score;
+        }
+    }
+    __syncthreads();
+    SortCtx sc{meta, mode, minimize};
+    for (int k = 2; k <= npad; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < npad; i += nth) {
+                const int l = i ^ j;
+                if (l > i) {
+                    DevHit a = load_hit(hits + i), b = load_hit(hits + l);
+                    const bool up = ((i & k) == 0);
+                    const bool swap = up ? hit_less(b, a, sc) : hit_less(a, b, sc);
+                    if (swap) { store_hit(hits + i, b); store_hit(hits + l, a); }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (mode == 0) {
+        const int live = n - dead;
+        for (int i = tid; i < live; i += nth) hits[i].seq = i;
+        if (tid == 0) { count[1] = live; if (count[0] <= cap) count[0] = live; }
+    }
+}
+
+__device__ __forceinline__ float rect_overlap(const DevHit& a, const DevHit& b)
+{
+    const int Aa = a.w * a.h, Ab = b.w * b.h;
+    if (Aa + Ab <= 0) return 1.0f;                       // jaccardDistance() == 0
+    const int x1 = max(a.x, b.x), y1 = max(a.y, b.y);
+    const int iw = min(a.x + a.w, b.x + b.w) - x1, ih = min(a.y + a.h, b.y + b.h) - y1;
+    const double Aab = (iw > 0 && ih > 0) ? (double)(iw * ih) : 0.0;
+    const double dist = 1.0 - Aab / ((double)(Aa + Ab) - Aab);
+    return 1.0f - (float)dist;
+}
+
+// hits sorted with mode 1.  out[] receives the kept hits in output order, out_count[0] their number.
+__global__ void __launch_bounds__(1024, 1)
+nms_kernel(const DevHit* __restrict__ hits, int cap, const int32_t* __restrict__ count, DevHit* __restrict__ out,
+           int32_t* __restrict__ out_count, int32_t* __restrict__ keep, float thr32, int ascending,
+           long long n_object, float max_overlap)
+{
+    __shared__ int s_kept;
+    __shared__ unsigned long long s_best;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    int n = count[0];
+    if (tid == 0) out_count[1] = n;                       // raw count: lets the host see an overflow
+    if (n > cap) n = cap;
+    if (n <= 1) {                                         // MTM/NMS.py:53-55: no thresholding
+        if (tid == 0) { if (n == 1) { out[0] = hits[0]; keep[0] = 0; } out_count[0] = n; }
+        return;
+    }
+    if (n_object == 1) {                                  // MTM/NMS.py:61-69: best raw score, first in list order
+        if (tid == 0) s_best = 0ull;
+        __syncthreads();
+        unsigned long long k = 0ull;
+        for (int i = tid; i < n; i += nth) {
+            const float v = ascending ? -hits[i].score : hits[i].score;
+            const unsigned long long key = ((unsigned long long)ordered_f32(v) << 32) |
+                                           (unsigned long long)(0xFFFFFFFFu - (uint32_t)hits[i].seq);
+            k = key > k ? key : k;
+        }
+        atomicMax(&s_best, k);
+        __syncthreads();
+        for (int i = tid; i < n; i += nth) {
+            const float v = ascending ? -hits[i].score : hits[i].score;
+            const unsigned long long key = ((unsigned long long)ordered_f32(v) << 32) |
+                                           (unsigned long long)(0xFFFFFFFFu - (uint32_t)hits[i].seq);
+            if (key == s_best) { out[0] = hits[i]; keep[0] = i; out_count[0] = 1; }
+        }
+        return;
+    }
+    if (tid == 0) s_kept = 0;
+    __syncthreads();
+    const long long limit = n_object < 0 ? (long long)n : n_object;
+    for (int i = 0; i < n; ++i) {
+        const DevHit cand = hits[i];
+        if (!(cand.key > thr32)) break;                   // sorted by key: the rest fails too
+        const int kept = s_kept;
+        if (kept >= limit) break;
+        int sup = 0;
+        for (int k = tid; k < kept; k += nth) {
+            if (!(rect_overlap(cand, hits[keep[k]]) <= max_overlap)) sup = 1;
+        }
+        sup = __syncthreads_or(sup);
+        if (!sup && tid == 0) { keep[kept] = i; out[kept] = cand; s_kept = kept + 1; }
+        __syncthreads();
+    }
+    if (tid == 0) out_count[0] = (s_kept < limit) ? s_kept : (int)limit;
+}
+
+}  // namespace
+
+int launch_sort_hits(mtm_ctx* ctx, int mode, int minimize, int ascending_key, int check_trivial)
+{
+    sort_hits_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->hitsA(), ctx->hit_cap, ctx->countA(), ctx->d_meta,
+                                                  ctx->d_nontrivial, mode, minimize, ascending_key, check_trivial);
+    MTM_LAUNCH_CHECK(ctx);
+    return MTM_OK;
+}
+
+int launch_nms(mtm_ctx* ctx, float thr32, int ascending, int64_t n_object, float max_overlap)
+{
+    nms_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->hitsA(), ctx->hit_cap, ctx->countA(), ctx->hitsB(), ctx->countB(),
+                                            ctx->d_keep, thr32, ascending, (long long)n_object, max_overlap);
+    MTM_LAUNCH_CHECK(ctx);
+    return MTM_OK;
+}

@@ -1,0 +1,188 @@
+// peaks.cu -- K5/K6: peak extraction from the fp32 score maps on the device.
+//
+//  * peaks2d_kernel  : skimage.feature.peak_local_max(map, threshold_abs=thr,
+//                      exclude_border=False) as called at MTM/__init__.py:45
+//                      (3x3 maximum, borders included, strict '> thr', constant
+//                      map -> no peaks, whole plateaus kept).
+//  * peaks1d_kernel  : the degenerate maps of MTM/__init__.py:25-41 -- 1x1 map
+//                      ('>= thr') and 1xn / nx1 maps (scipy.signal.find_peaks
+//                      with height=thr: strict neighbours, plateau midpoint,
+//                      edges excluded, float64 comparison, ascending order).
+//  * argbest_kernel  : cv2.minMaxLoc (MTM/__init__.py:226): global max (min for
+//                      methods 0/1), first occurrence in row-major order.
+// For methods 0/1 (MTM/__init__.py:51-53, 232-233) the map and the threshold are
+// negated, exactly like _findLocalMin_.  HBM-bound: one 4-byte read per score
+// pixel (neighbours come from L1/L2).
+#include "mtm_internal.cuh"
+
+namespace {
+
+__global__ void peaks2d_kernel(const TmplMeta* __restrict__ meta, const float* __restrict__ maps,
+                               float thr32, int minimize, DevHit* __restrict__ hits, int cap,
+                               int32_t* __restrict__ count, int32_t* __restrict__ nontrivial)
+{
+    const TmplMeta& tm = meta[blockIdx.y];
+    const int mh = tm.mh, mw = tm.mw;
+    if (mh == 1 || mw == 1) return;                          // handled by peaks1d_kernel
+    const int64_t n = (int64_t)mh * mw;
+    const float* m = maps + tm.map_off;
+    const float sgn = minimize ? -1.0f : 1.0f;
+    int any_nonmax = 0;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int y = (int)(idx / mw), x = (int)(idx - (int64_t)y * mw);
+        const float raw = m[idx];
+        const float v = sgn * raw;
+        bool is_max = true;
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+            const int yy = y + dy;
+            if (yy < 0 || yy >= mh) continue;
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int xx = x + dx;
+                if (xx < 0 || xx >= mw || (dx == 0 && dy == 0)) continue;
+                if (sgn * m[(int64_t)yy * mw + xx] > v) is_max = false;
+            }
+        }
+        if (!is_max) any_nonmax = 1;
+        if (is_max && v > thr32) {
+            const int slot = atomicAdd(count, 1);
+            if (slot < cap) {
+                DevHit h;
+                h.tmpl = blockIdx.y; h.x = x; h.y = y; h.w = tm.w; h.h = tm.h;
+                h.score = raw; h.seq = 0; h.key = 0.f;
+                hits[slot] = h;
+            }
+        }
+    }
+    if (__syncthreads_or(any_nonmax) && threadIdx.x == 0) atomicOr(&nontrivial[blockIdx.y], 1);
+}
+
+// One thread per degenerate template (these maps have at most max(H, W) entries).
+__global__ void peaks1d_kernel(const TmplMeta* __restrict__ meta, int n_tmpl, const float* __restrict__ maps,
+                               float thr32, double thr64, int minimize, DevHit* __restrict__ hits, int cap,
+                               int32_t* __restrict__ count, int32_t* __restrict__ nontrivial)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tmpl) return;
+    const TmplMeta& tm = meta[t];
+    if (tm.mh != 1 && tm.mw != 1) return;
+    nontrivial[t] = 1;                                        // the "constant map" rule is 2-D only
+    const float* m = maps + tm.map_off;
+    const double sgn = minimize ? -1.0 : 1.0;
+    auto emit = [&](int i) {
+        const int slot = atomicAdd(count, 1);
+        if (slot < cap) {
+            DevHit h;
+            h.tmpl = t; h.w = tm.w; h.h = tm.h; h.score = m[i]; h.seq = 0; h.key = 0.f;
+            if (tm.mh == 1) { h.x = i; h.y = 0; } else { h.x = 0; h.y = i; }
+            hits[slot] = h;
+        }
+    };
+    const int n = tm.mh * tm.mw;
+    if (n == 1) {                                             // MTM/__init__.py:25-30, float32 '>='
+        const float v = minimize ? -m[0] : m[0];
+        if (v >= thr32) emit(0);
+        return;
+    }
+    int i = 1;                                                // scipy _local_maxima_1d
+    while (i < n - 1) {
+        const double vi = sgn * (double)m[i];
+        if (sgn * (double)m[i - 1] < vi) {
+            int ahead = i + 1;
+            while (ahead < n - 1 && sgn * (double)m[ahead] == vi) ++ahead;
+            if (sgn * (double)m[ahead] < vi) {
+                const int mid = (i + ahead - 1) / 2;
+                if (sgn * (double)m[mid] >= thr64) emit(mid);
+                i = ahead;
+            }
+        }
+        ++i;
+    }
+}
+
+__global__ void argbest_kernel(const TmplMeta* __restrict__ meta, const float* __restrict__ maps,
+                               int minimize, unsigned long long* __restrict__ best)
+{
+    const TmplMeta& tm = meta[blockIdx.y];
+    const int64_t n = (int64_t)tm.mh * tm.mw;
+    const float* m = maps + tm.map_off;
+    unsigned long long k = 0ull;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const float v = minimize ? -m[idx] : m[idx];
+        const unsigned long long key =
+            ((unsigned long long)ordered_f32(v) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)idx);
+        k = key > k ? key : k;
+    }
+    for (int d = 16; d; d >>= 1) {
+        const unsigned long long o = __shfl_down_sync(0xffffffffu, k, d);
+        k = o > k ? o : k;
+    }
+    if ((threadIdx.x & 31) == 0 && k) atomicMax(&best[blockIdx.y], k);
+}
+
+__global__ void emit_best_kernel(const TmplMeta* __restrict__ meta, int n_tmpl, const float* __restrict__ maps,
+                                 const unsigned long long* __restrict__ best, DevHit* __restrict__ hits,
+                                 int32_t* __restrict__ count)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0) count[0] = n_tmpl;
+    if (t >= n_tmpl) return;
+    const TmplMeta& tm = meta[t];
+    const uint32_t idx = 0xFFFFFFFFu - (uint32_t)(best[t] & 0xFFFFFFFFull);
+    DevHit h;
+    h.tmpl = t; h.y = (int)(idx / (uint32_t)tm.mw); h.x = (int)(idx - (uint32_t)h.y * (uint32_t)tm.mw);
+    h.w = tm.w; h.h = tm.h; h.score = maps[tm.map_off + idx]; h.seq = t; h.key = 0.f;
+    hits[t] = h;
+}
+
+}  // namespace
+
+// Fills block A (hits + count[0]) with the raw (unsorted) peaks of every template.
+int launch_peaks(mtm_ctx* ctx, int method, int64_t n_object, float thr32, double thr64)
+{
+    const int nt = ctx->n_tmpl;
+    const int minimize = method_is_min(method) ? 1 : 0;
+    int64_t max_px = 0;
+    for (int t = 0; t < nt; ++t) {
+        const int64_t n = (int64_t)ctx->h_meta[t].mh * ctx->h_meta[t].mw;
+        if (n >= (1ll << 32)) return mtm_fail(ctx, MTM_ERR_UNSUPPORTED, "score map larger than 2^32 pixels");
+        max_px = n > max_px ? n : max_px;
+    }
+    MTM_CUDA(ctx, cudaMemsetAsync(ctx->countA(), 0, MTM_HIT_HEADER, ctx->stream));
+    int bx = (int)((max_px + 255) / 256);
+    const int bx_cap = ctx->sm_count * 16;
+    if (bx > bx_cap) bx = bx_cap;
+    if (bx < 1) bx = 1;
+    if (n_object == 1) {
+        MTM_CUDA(ctx, cudaMemsetAsync(ctx->d_best, 0, nt * sizeof(unsigned long long), ctx->stream));
+        argbest_kernel<<<dim3(bx, nt), 256, 0, ctx->stream>>>(ctx->d_meta, ctx->d_maps, minimize, ctx->d_best);
+        MTM_LAUNCH_CHECK(ctx);
+        emit_best_kernel<<<(nt + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_meta, nt, ctx->d_maps, ctx->d_best,
+                                                                   ctx->hitsA(), ctx->countA());
+        MTM_LAUNCH_CHECK(ctx);
+        return MTM_OK;
+    }
+    MTM_CUDA(ctx, cudaMemsetAsync(ctx->d_nontrivial, 0, nt * sizeof(int32_t), ctx->stream));
+    bool any2d = false, any1d = false;
+    for (int t = 0; t < nt; ++t) {
+        if (ctx->h_meta[t].mh == 1 || ctx->h_meta[t].mw == 1) any1d = true; else any2d = true;
+    }
+    const float t32 = minimize ? -thr32 : thr32;
+    const double t64 = minimize ? -thr64 : thr64;
+    if (any2d) {
+        peaks2d_kernel<<<dim3(bx, nt), 256, 0, ctx->stream>>>(ctx->d_meta, ctx->d_maps, t32, minimize,
+                                                              ctx->hitsA(), ctx->hit_cap, ctx->countA(),
+                                                              ctx->d_nontrivial);
+        MTM_LAUNCH_CHECK(ctx);
+    }
+    if (any1d) {
+        peaks1d_kernel<<<(nt + 63) / 64, 64, 0, ctx->stream>>>(ctx->d_meta, nt, ctx->d_maps, t32, t64, minimize,
+                                                               ctx->hitsA(), ctx->hit_cap, ctx->countA(),
+                                                               ctx->d_nontrivial);
+        MTM_LAUNCH_CHECK(ctx);
+    }
+    return MTM_OK;
+}

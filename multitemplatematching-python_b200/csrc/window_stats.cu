@@ -1,0 +1,166 @@
+// window_stats.cu -- K1: per-channel window statistics of the image and the
+// template statistics, i.e. what OpenCV's integral(img, sum, sqsum, CV_64F) and
+// meanStdDev(templ) feed into common_matchTemplate (third-party; call site
+// MTM/__init__.py:92).  Everything is exact integer arithmetic:
+//   sat_s[c] : (H+1)x(W+1) summed-area table of channel c, u32 with wrap-around
+//              (any window sum < 2^32 is recovered exactly by the 4-corner
+//              difference modulo 2^32);
+//   sat_q    : (H+1)x(W+1) summed-area table of sum_c I_c^2, u64.
+// HBM-bound: reads H*W*C bytes once, writes (4C+8) B per pixel.
+#include "mtm_internal.cuh"
+
+namespace {
+
+// One warp per image row: inclusive prefix along x of every channel and of the
+// squared norm.  Output (scratch): C planes of u32 [H][W] then one u32 plane [H][W]
+// (row prefixes of squares stay < 2^32 for W*C < 66051).
+template <int C>
+__global__ void sat_rows_kernel(const uint8_t* __restrict__ img, int64_t pitch, int H, int W,
+                                uint32_t* __restrict__ scratch)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= H) return;
+    const uint8_t* row = img + (int64_t)warp * pitch;
+    const int64_t plane = (int64_t)H * W;
+    uint32_t carry[C + 1];
+#pragma unroll
+    for (int c = 0; c <= C; ++c) carry[c] = 0;
+    for (int x0 = 0; x0 < W; x0 += 32) {
+        const int x = x0 + lane;
+        uint32_t v[C + 1];
+        v[C] = 0;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            uint32_t p = (x < W) ? row[(int64_t)x * C + c] : 0u;
+            v[c] = p;
+            v[C] += p * p;
+        }
+#pragma unroll
+        for (int c = 0; c <= C; ++c) {
+            uint32_t s = v[c];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t n = __shfl_up_sync(0xffffffffu, s, d);
+                if (lane >= d) s += n;
+            }
+            s += carry[c];
+            if (x < W) scratch[c * plane + (int64_t)warp * W + x] = s;
+            carry[c] = __shfl_sync(0xffffffffu, s, 31);
+        }
+    }
+}
+
+// Column pass.  Block = 32 SAT columns x 32 row chunks; two sweeps over the chunk
+// (chunk total -> exclusive scan over chunks -> running prefix).  blockIdx.y picks
+// the table: 0..C-1 -> sat_s[c] (u32), C -> sat_q (u64).
+__global__ void sat_cols_kernel(const uint32_t* __restrict__ scratch, int H, int W, int C,
+                                uint32_t* __restrict__ sat_s, unsigned long long* __restrict__ sat_q,
+                                int64_t sat_pitch)
+{
+    __shared__ unsigned long long part[32][33];
+    const int cx = threadIdx.x, ry = threadIdx.y;
+    const int sx = blockIdx.x * 32 + cx;          // SAT column, 0..W
+    const int table = blockIdx.y;
+    const int64_t plane = (int64_t)H * W;
+    const uint32_t* src = scratch + table * plane;
+    const int rc = (H + 31) / 32;
+    const int y0 = ry * rc, y1 = min(H, y0 + rc);
+    const bool live = (sx >= 1 && sx <= W);
+    unsigned long long tot = 0;
+    if (live) {
+        for (int y = y0; y < y1; ++y) tot += src[(int64_t)y * W + (sx - 1)];
+    }
+    part[ry][cx] = tot;
+    __syncthreads();
+    unsigned long long run = 0;
+    for (int k = 0; k < ry; ++k) run += part[k][cx];
+    if (sx > W) return;
+    const bool is_q = (table == C);
+    const int64_t sat_plane = (int64_t)(H + 1) * sat_pitch;
+    uint32_t* ds = sat_s + (is_q ? 0 : table * sat_plane);
+    if (ry == 0) {                                 // SAT row 0 is all zeros
+        if (is_q) sat_q[sx] = 0ull; else ds[sx] = 0u;
+    }
+    for (int y = y0; y < y1; ++y) {
+        if (live) run += src[(int64_t)y * W + (sx - 1)];
+        const int64_t o = (int64_t)(y + 1) * sat_pitch + sx;
+        if (is_q) sat_q[o] = run; else ds[o] = (uint32_t)run;
+    }
+}
+
+// One block per template: integer sums -> OpenCV's meanStdDev-derived constants.
+__global__ void tmpl_stats_kernel(const uint8_t* __restrict__ tmpl, TmplMeta* __restrict__ meta, int C)
+{
+    TmplMeta& m = meta[blockIdx.x];
+    const uint8_t* p = tmpl + m.pix_off;
+    long long s[MTM_MAX_CH] = {0, 0, 0, 0}, q[MTM_MAX_CH] = {0, 0, 0, 0};
+    const int n = m.h * m.w;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int y = i / m.w, x = i - y * m.w;
+        for (int c = 0; c < C; ++c) {
+            long long v = p[(int64_t)y * m.wp + x * C + c];
+            s[c] += v;
+            q[c] += v * v;
+        }
+    }
+    __shared__ long long red[2 * MTM_MAX_CH][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int c = 0; c < MTM_MAX_CH; ++c) {
+        long long a = s[c], b = q[c];
+        for (int d = 16; d; d >>= 1) {
+            a += __shfl_down_sync(0xffffffffu, a, d);
+            b += __shfl_down_sync(0xffffffffu, b, d);
+        }
+        if (lane == 0) { red[c][wid] = a; red[MTM_MAX_CH + c][wid] = b; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int nw = blockDim.x >> 5;
+        const double inv_area = 1.0 / ((double)m.h * (double)m.w);
+        double norm = 0.0, mean2 = 0.0;
+        for (int c = 0; c < MTM_MAX_CH; ++c) {
+            long long a = 0, b = 0;
+            for (int k = 0; k < nw; ++k) { a += red[c][k]; b += red[MTM_MAX_CH + c][k]; }
+            const double mean = (double)a * inv_area;
+            const double var = fmax((double)b * inv_area - mean * mean, 0.0);
+            m.mean[c] = (c < C) ? mean : 0.0;
+            if (c < C) { norm += var; mean2 += mean * mean; }
+        }
+        const double sum2 = norm + mean2;
+        m.inv_area = inv_area;
+        m.is_const = norm < 2.220446049250313e-16 ? 1 : 0;      // DBL_EPSILON
+        m.sum2 = sum2 / inv_area;
+        m.norm_ccoeff = sqrt(norm) / sqrt(inv_area);
+        m.norm_plain = sqrt(sum2) / sqrt(inv_area);
+    }
+}
+
+}  // namespace
+
+int launch_build_sat(mtm_ctx* ctx)
+{
+    ImageDev& im = ctx->img;
+    const int H = im.H, W = im.W, C = im.C;
+    const int warps_per_block = 4;
+    dim3 g1((H + warps_per_block - 1) / warps_per_block), b1(32 * warps_per_block);
+    switch (C) {
+        case 1: sat_rows_kernel<1><<<g1, b1, 0, ctx->stream>>>(im.pix, im.pitch, H, W, ctx->scratch); break;
+        case 2: sat_rows_kernel<2><<<g1, b1, 0, ctx->stream>>>(im.pix, im.pitch, H, W, ctx->scratch); break;
+        case 3: sat_rows_kernel<3><<<g1, b1, 0, ctx->stream>>>(im.pix, im.pitch, H, W, ctx->scratch); break;
+        case 4: sat_rows_kernel<4><<<g1, b1, 0, ctx->stream>>>(im.pix, im.pitch, H, W, ctx->scratch); break;
+        default: return mtm_fail(ctx, MTM_ERR_INVALID, "unsupported channel count %d", C);
+    }
+    MTM_LAUNCH_CHECK(ctx);
+    dim3 g2((W + 1 + 31) / 32, C + 1), b2(32, 32);
+    sat_cols_kernel<<<g2, b2, 0, ctx->stream>>>(ctx->scratch, H, W, C, im.sat_s, im.sat_q, im.sat_pitch);
+    MTM_LAUNCH_CHECK(ctx);
+    return MTM_OK;
+}
+
+int launch_tmpl_stats(mtm_ctx* ctx)
+{
+    tmpl_stats_kernel<<<ctx->n_tmpl, 256, 0, ctx->stream>>>(ctx->d_tmpl, ctx->d_meta, ctx->tmpl_C);
+    MTM_LAUNCH_CHECK(ctx);
+    return MTM_OK;
+}

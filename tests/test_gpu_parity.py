@@ -1,0 +1,173 @@
+"""-m gpu parity tests: the CUDA path (through the C ABI) against the oracle and the
+golden vectors made by the unmodified reference.  Bars: score maps within 1e-4 of
+the exact restatement (north_star), hit lists identical after NMS."""
+import numpy as np
+import pytest
+
+from helpers import assert_hits_equal, assert_map_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _hits_from_json(rows):
+    return [(r[0], tuple(r[1]), r[2]) for r in rows]
+
+
+def test_score_map_c1_fish(mtm, golden):
+    from oracle import golden_cases as gc, ncc_exact
+    kind, temps, img, kw = gc.build("c1_fish256_map")
+    got = mtm.computeScoreMap(temps[0][1], img, **kw)
+    ref = np.load(gc.GOLDEN_DIR + "/c1_fish256_map.npy")          # unmodified reference (cv2)
+    exact = ncc_exact.match_template_exact(img, temps[0][1])
+    assert got.dtype == np.float32 and got.shape == (193, 193)
+    assert_map_close(got, exact, cv=ref)
+    assert int(got.argmax()) == golden["c1_fish256_map"]["argmax"]
+
+
+@pytest.mark.parametrize("shape,tshape,seed", [
+    ((97, 131), (16, 16), 0), ((64, 64), (64, 64), 1), ((150, 70), (31, 7), 2), ((80, 300), (5, 64), 3),
+    ((200, 200), (1, 1), 4), ((129, 257), (33, 65), 5), ((70, 90), (70, 13), 6), ((90, 70), (13, 70), 7),
+    ((300, 340), (100, 130), 8),
+])
+def test_score_map_random(mtm, shape, tshape, seed):
+    import cv2
+    from oracle import ncc_exact
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, 256, shape, dtype=np.uint8)
+    tmpl = rng.integers(0, 256, tshape, dtype=np.uint8)
+    got = mtm.computeScoreMap(tmpl, img)
+    exact = ncc_exact.match_template_exact(img, tmpl, use_fft=False)
+    cv = cv2.matchTemplate(img, tmpl, cv2.TM_CCOEFF_NORMED)
+    assert_map_close(got, exact, cv=cv)
+
+
+@pytest.mark.parametrize("method", [0, 1, 2, 3, 4, 5])
+def test_score_map_all_methods(mtm, method):
+    from oracle import ncc_exact, synth
+    rng = np.random.default_rng(40 + method)
+    tmpl = synth.make_template(rng, 21, 34)
+    img, _ = synth.make_scene(120, 160, [tmpl], 2, seed=40 + method)
+    got = mtm.computeScoreMap(tmpl, img, method=method)
+    exact = ncc_exact.match_template_exact(img, tmpl, method=method, use_fft=False)
+    assert_map_close(got, exact, tol=1e-4)
+
+
+def test_score_map_rgb(mtm):
+    import cv2
+    from oracle import ncc_exact
+    rng = np.random.default_rng(9)
+    img = rng.integers(0, 256, (90, 120, 3), dtype=np.uint8)
+    tmpl = np.ascontiguousarray(img[20:45, 30:71]) // 2 + rng.integers(0, 100, (25, 41, 3), dtype=np.uint8)
+    got = mtm.computeScoreMap(tmpl.astype(np.uint8), img)
+    exact = ncc_exact.match_template_exact(img, tmpl.astype(np.uint8), use_fft=False)
+    cv = cv2.matchTemplate(img, tmpl.astype(np.uint8), cv2.TM_CCOEFF_NORMED)
+    assert_map_close(got, exact, cv=cv)
+
+
+def test_flat_and_constant_inputs(mtm):
+    """OpenCV rules: constant template -> all ones; exactly flat window -> 0; never NaN."""
+    img = np.full((40, 50), 7, np.uint8)
+    img[10:20, 10:20] = 200
+    const_t = np.full((8, 8), 31, np.uint8)
+    assert np.all(mtm.computeScoreMap(const_t, img) == 1.0)
+    t = np.arange(64, dtype=np.uint8).reshape(8, 8)
+    m = mtm.computeScoreMap(t, img)
+    assert np.isfinite(m).all() and m[0, 40] == 0.0 and m[30, 0] == 0.0
+
+
+GOLDEN_MATCH = ["t3_downscaled", "c1_fish256_n1", "c1_fish256_inf", "fish512_multi", "fish512_multi_n3",
+                "synth_rot8", "synth_mixed", "synth_mixed_n5", "synth_searchbox", "synth_exact_fit"]
+
+
+@pytest.mark.parametrize("name", GOLDEN_MATCH)
+def test_match_templates_golden(mtm, golden, name):
+    from oracle import golden_cases as gc
+    kind, temps, img, kw = gc.build(name)
+    assert kind == "match"
+    got = mtm.matchTemplates(temps, img, **kw)
+    assert_hits_equal(got, _hits_from_json(golden[name]))
+    for h in got:
+        assert isinstance(h[0], str) and isinstance(h[2], np.float32) and all(isinstance(v, int) for v in h[1])
+
+
+@pytest.mark.parametrize("name", ["t3_full", "t3_searchbox"])
+def test_match_templates_tutorial3_fullres(mtm, golden, name):
+    """Known answers owned by the reference: Tutorial3-SpeedingUp.ipynb cells 10 / 14."""
+    from oracle import golden_cases as gc
+    kind, temps, img, kw = gc.build(name)
+    got = mtm.matchTemplates(temps, img, **kw)
+    assert_hits_equal(got, _hits_from_json(golden[name]))
+    nb = gc.NOTEBOOK_ANSWERS[name]
+    assert got[0][0] == nb[0][0] and got[0][1] == nb[0][1] and abs(float(got[0][2]) - nb[0][2]) <= 1e-4
+
+
+@pytest.mark.parametrize("name", ["c1_fish256_find", "fish512_find", "synth_row_map", "synth_col_map"])
+def test_find_matches_golden(mtm, golden, name):
+    from oracle import golden_cases as gc
+    kind, temps, img, kw = gc.build(name)
+    got = mtm.findMatches(temps, img, **kw)
+    assert_hits_equal(got, _hits_from_json(golden[name]), ordered=False)
+
+
+def test_find_matches_order_is_reference_order(mtm):
+    """Template order, then descending score (the order one reference worker produces)."""
+    from oracle import golden_cases as gc, mtm_port
+    kind, temps, img, kw = gc.build("fish512_find")
+    got = mtm.findMatches(temps, img, **kw)
+    want = mtm_port.find_matches(temps, img, **kw)
+    assert_hits_equal(got, want)
+
+
+def test_nms_demo_and_random(mtm, golden):
+    from oracle import mtm_port
+    demo = [("1", (780, 350, 700, 480), 0.8), ("1", (806, 416, 716, 442), 0.6), ("1", (1074, 530, 680, 390), 0.4)]
+    got = mtm.NMS(demo, scoreThreshold=0.3, sortAscending=False, maxOverlap=0.5, N_object=2)
+    assert [(g[0], tuple(g[1])) for g in got] == [(w[0], tuple(w[1])) for w in golden["nms_demo"]]
+    rng = np.random.default_rng(5)
+    for trial in range(20):
+        n = int(rng.integers(2, 200))
+        hits = [("L%d" % i, (int(rng.integers(0, 300)), int(rng.integers(0, 300)), int(rng.integers(1, 80)),
+                             int(rng.integers(1, 80))), np.float32(rng.integers(0, 50) / 50.0)) for i in range(n)]
+        for asc in (False, True):
+            for nobj in (float("inf"), 1, 3, 0):
+                kw = dict(scoreThreshold=0.3, sortAscending=asc, N_object=nobj, maxOverlap=float(rng.integers(0, 5)) / 8)
+                assert mtm.NMS(hits, **kw) == mtm_port.nms(hits, **kw), (trial, kw)
+
+
+@pytest.mark.parametrize("cfg", ["C2", "C4"])
+def test_baseline_configs_full_size(mtm, cfg):
+    """BASELINE.json configs at full size against the CPU port (live cv2)."""
+    from oracle import mtm_port, synth
+    image, temps, params = synth.config(cfg)
+    got = mtm.matchTemplates(temps, image, **params)
+    want = mtm_port.match_templates(temps, image, **params)
+    assert len(want) > 0
+    assert_hits_equal(got, want)
+
+
+def test_c3_large_template_properties(mtm):
+    """C3 (4096^2, 256^2 template): too large for the direct oracle -> FFT-exact oracle on the map."""
+    from oracle import ncc_exact, synth
+    image, temps, params = synth.config("C3")
+    got = mtm.computeScoreMap(temps[0][1], image)
+    exact = ncc_exact.match_template_exact(image, temps[0][1], use_fft=True)
+    assert_map_close(got, exact)
+
+
+def test_validation_errors_match_reference(mtm):
+    img = np.zeros((50, 60), np.uint8)
+    t = np.zeros((10, 10), np.uint8)
+    with pytest.raises(ValueError, match="Maximal overlap"):
+        mtm.matchTemplates([("a", t)], img, maxOverlap=1.5)
+    with pytest.raises(TypeError, match="N_object must be an integer"):
+        mtm.matchTemplates([("a", t)], img, N_object=np.int64(2))
+    with pytest.raises(ValueError, match="larger than image"):
+        mtm.matchTemplates([("big", np.pad(img, 1))], img)
+    with pytest.raises(ValueError, match="larger than searchBox"):
+        mtm.matchTemplates([("a", t)], img, searchBox=(0, 0, 5, 5))
+    with pytest.raises(ValueError, match="list of tuples"):
+        mtm.matchTemplates([["a", t]], img)
+    with pytest.raises(ValueError, match="TM_SQDIFF is not supported"):
+        mtm.matchTemplates([("a", t)], img, method=0)
+    with pytest.raises(ValueError, match="64-bit"):
+        mtm.computeScoreMap(t.astype(np.float64), img)
