@@ -20,7 +20,10 @@ def _load():
 
 
 _impl = _load()
-from mtm_b200 import (NMS, Hit, BBox, TemplateTuple, __version__, computeScoreMap, drawBoxesOnGray,  # noqa: E402,F401
+from mtm_b200 import (BBox, TemplateTuple, __version__, computeScoreMap, drawBoxesOnGray,  # noqa: E402,F401
                       drawBoxesOnRGB, findMatches, matchTemplates)
+# as in the reference (MTM/__init__.py:13): importing the submodule first, then rebinding the
+# name, leaves ``MTM.NMS`` bound to the FUNCTION while ``from MTM.NMS import NMS`` also works
+from .NMS import NMS, Hit  # noqa: E402,F401
 
 __all__ = ["NMS"]

@@ -1,0 +1,79 @@
+"""CPU tests: the C-ABI library loads and exports every declared symbol; the host
+layer validates like the reference and fails loudly (no fallback) without a GPU."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    text = open(os.path.join(ROOT, "include", "mtm_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mtm_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(mtm):
+    import ctypes
+    from mtm_b200 import _native
+    lib = _native.load()
+    declared = _declared_functions()
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(lib, name), "libmtm_b200.so lacks %s" % name
+    assert sorted(_native.exported_symbols()) == declared            # the binding covers the whole header
+    assert lib.mtm_abi_version() == 1
+    assert ctypes.sizeof(ctypes.c_int32) * 5 + 4 == _native.HIT_DTYPE.itemsize
+
+
+def test_no_gpu_means_loud_failure_not_fallback(mtm):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from mtm_b200 import _native
+    with pytest.raises(_native.NativeError, match="no CUDA device|no CPU fallback"):
+        _native.Context(0)
+    img = np.zeros((32, 32), np.uint8)
+    with pytest.raises(RuntimeError):
+        mtm.matchTemplates([("a", img[:8, :8])], img)
+
+
+def test_validation_precedes_device_work(mtm):
+    img = np.zeros((50, 60), np.uint8)
+    t = np.zeros((10, 10), np.uint8)
+    with pytest.raises(ValueError, match="Maximal overlap"):
+        mtm.matchTemplates([("a", t)], img, maxOverlap=-0.1)
+    with pytest.raises(TypeError, match="N_object must be an integer"):
+        mtm.findMatches([("a", t)], img, N_object=2.0)
+    with pytest.raises(ValueError, match="height of 0"):
+        mtm.findMatches([("a", t)], np.zeros((0, 5), np.uint8))
+    with pytest.raises(ValueError, match="width of 0"):
+        mtm.findMatches([("a", np.zeros((3, 0), np.uint8))], img)
+    with pytest.raises(ValueError, match="'big' at index 1 in the list of templates is larger than image"):
+        mtm.findMatches([("a", t), ("big", np.zeros((51, 5), np.uint8))], img)
+    with pytest.raises(ValueError, match="larger than searchBox"):
+        mtm.findMatches([("a", t)], img, searchBox=(0, 0, 9, 9))
+    with pytest.raises(ValueError, match="list of tuples"):
+        mtm.findMatches([("a",)], img)
+    with pytest.raises(ValueError, match="64-bit images not supported"):
+        mtm.computeScoreMap(t, img.astype(np.float64))
+    assert mtm.NMS([]) == [] and mtm.NMS([("a", (0, 0, 1, 1), 0.1)]) == [("a", (0, 0, 1, 1), 0.1)]
+
+
+def test_api_surface_matches_reference(mtm):
+    import inspect
+    assert mtm.__version__ == "2.0.1" and mtm.__all__ == ["NMS"]
+    sig = inspect.signature(mtm.matchTemplates)
+    assert list(sig.parameters)[:7] == ["listTemplates", "image", "method", "N_object", "score_threshold", "maxOverlap", "searchBox"]
+    assert sig.parameters["maxOverlap"].default == 0.25 and sig.parameters["method"].default == 5
+    assert sig.parameters["N_object"].default == float("inf") and sig.parameters["score_threshold"].default == 0.5
+    sig = inspect.signature(mtm.NMS)
+    assert list(sig.parameters)[:5] == ["listHit", "scoreThreshold", "sortAscending", "N_object", "maxOverlap"]
+    assert sig.parameters["maxOverlap"].default == 0.5
+    assert list(inspect.signature(mtm.computeScoreMap).parameters)[:4] == ["template", "image", "method", "mask"]
+    assert list(inspect.signature(mtm.findMatches).parameters)[:6] == ["listTemplates", "image", "method", "N_object", "score_threshold", "searchBox"]
+    from MTM.NMS import NMS
+    assert NMS is mtm.NMS
+    assert callable(mtm.drawBoxesOnRGB) and callable(mtm.drawBoxesOnGray)

@@ -1,0 +1,124 @@
+"""CPU tests: pin the oracle (restated algorithms) against the golden vectors made by
+the unmodified reference, the reference's own known answers, and live cv2/scipy."""
+import cv2
+import numpy as np
+import pytest
+
+from helpers import assert_hits_equal
+
+
+def _hits_from_json(rows):
+    return [(r[0], tuple(r[1]), r[2]) for r in rows]
+
+
+def test_area_downscale_matches_cv2_inter_area():
+    from oracle import golden_cases as gc
+    fish = gc.fish()
+    for f in (4, 8):
+        want = cv2.resize(fish, (2048 // f, 2048 // f), interpolation=cv2.INTER_AREA)
+        assert np.array_equal(gc.area_downscale(fish, f), want)
+
+
+@pytest.mark.parametrize("name", ["t3_downscaled", "c1_fish256_n1", "c1_fish256_inf", "fish512_multi",
+                                  "fish512_multi_n3", "synth_rot8", "synth_mixed", "synth_mixed_n5",
+                                  "synth_searchbox", "synth_exact_fit", "t3_searchbox"])
+def test_port_reproduces_reference_match(golden, name):
+    from oracle import golden_cases as gc, mtm_port
+    kind, temps, img, kw = gc.build(name)
+    got = mtm_port.match_templates(temps, img, **kw)
+    assert_hits_equal(got, _hits_from_json(golden[name]), tol=1e-6)
+    if name in gc.NOTEBOOK_ANSWERS:                      # stored notebook outputs (cv2 4.7 -> 4.13: ~1e-6)
+        nb = gc.NOTEBOOK_ANSWERS[name]
+        assert got[0][:2] == nb[0][:2] and abs(float(got[0][2]) - nb[0][2]) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["c1_fish256_find", "fish512_find", "synth_row_map", "synth_col_map"])
+def test_port_reproduces_reference_find(golden, name):
+    from oracle import golden_cases as gc, mtm_port
+    kind, temps, img, kw = gc.build(name)
+    got = mtm_port.find_matches(temps, img, **kw)
+    assert_hits_equal(got, _hits_from_json(golden[name]), tol=1e-6, ordered=False)
+
+
+def test_port_nms_demo(golden):
+    from oracle import mtm_port
+    demo = [("1", (780, 350, 700, 480), 0.8), ("1", (806, 416, 716, 442), 0.6), ("1", (1074, 530, 680, 390), 0.4)]
+    got = mtm_port.nms(demo, scoreThreshold=0.3, sortAscending=False, maxOverlap=0.5, N_object=2)
+    assert [g[1] for g in got] == [tuple(w[1]) for w in golden["nms_demo"]] == [demo[0][1], demo[2][1]]
+
+
+def test_exact_ncc_matches_reference_map(golden):
+    """Exact restatement vs the reference's own cv2 map (C1): cv2's fp32 noise only."""
+    from oracle import golden_cases as gc, ncc_exact
+    kind, temps, img, kw = gc.build("c1_fish256_map")
+    ref = np.load(gc.GOLDEN_DIR + "/c1_fish256_map.npy")
+    exact = ncc_exact.match_template_exact(img, temps[0][1])
+    assert np.max(np.abs(exact - ref)) < 5e-5
+    assert int(exact.argmax()) == golden["c1_fish256_map"]["argmax"]
+
+
+@pytest.mark.parametrize("method", [0, 1, 2, 3, 4, 5])
+def test_exact_ncc_all_methods_vs_cv2(method):
+    from oracle import ncc_exact, synth
+    rng = np.random.default_rng(method)
+    tmpl = synth.make_template(rng, 19, 27)
+    img, _ = synth.make_scene(90, 110, [tmpl], 2, seed=method)
+    exact = ncc_exact.match_template_exact(img, tmpl, method=method, use_fft=False)
+    cv = cv2.matchTemplate(img, tmpl, method)
+    scale = max(1.0, float(np.abs(cv).max()))
+    assert np.max(np.abs(exact.astype(np.float64) - cv)) <= 2e-5 * scale
+
+
+def test_exact_ncc_rgb_and_fft_twin():
+    from oracle import ncc_exact
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, (70, 95, 3), dtype=np.uint8)
+    tmpl = rng.integers(0, 256, (12, 21, 3), dtype=np.uint8)
+    assert np.array_equal(ncc_exact.cc_direct(img, tmpl), ncc_exact.cc_fft(img, tmpl))
+    exact = ncc_exact.match_template_exact(img, tmpl, use_fft=False)
+    assert np.max(np.abs(exact - cv2.matchTemplate(img, tmpl, cv2.TM_CCOEFF_NORMED))) < 2e-5
+    g = rng.integers(0, 256, (200, 230), dtype=np.uint8)
+    t = rng.integers(0, 256, (64, 50), dtype=np.uint8)
+    assert np.array_equal(ncc_exact.cc_direct(g, t), ncc_exact.cc_fft(g, t))
+
+
+def test_exact_ncc_degenerate_rules():
+    from oracle import ncc_exact
+    img = np.full((30, 40), 9, np.uint8)
+    img[5:12, 5:12] = 180
+    assert np.all(ncc_exact.match_template_exact(img, np.full((6, 6), 3, np.uint8)) == 1.0)
+    t = np.arange(36, dtype=np.uint8).reshape(6, 6)
+    m = ncc_exact.match_template_exact(img, t)
+    cv = cv2.matchTemplate(img, t, cv2.TM_CCOEFF_NORMED)
+    assert m[20, 30] == 0.0 and cv[20, 30] == 0.0 and np.isfinite(m).all()
+
+
+def test_nms_port_matches_cv2():
+    from oracle import nms_port
+    rng = np.random.default_rng(0)
+    for trial in range(200):
+        n = int(rng.integers(1, 60))
+        boxes = [(int(rng.integers(0, 100)), int(rng.integers(0, 100)), int(rng.integers(1, 40)), int(rng.integers(1, 40)))
+                 for _ in range(n)]
+        scores = [float(np.float32(rng.integers(0, 20) / 20.0)) for _ in range(n)]
+        thr, ov = float(rng.integers(0, 10)) / 10, float(rng.integers(0, 9)) / 8
+        want = list(cv2.dnn.NMSBoxes(boxes, scores, thr, ov))
+        assert nms_port.nms_boxes(boxes, scores, thr, ov) == [int(i) for i in want]
+    # touching boxes are kept at maxOverlap=0, a 1-px overlap is suppressed
+    assert nms_port.nms_boxes([(0, 0, 10, 10), (10, 0, 10, 10), (9, 0, 10, 10)], [0.9, 0.8, 0.7], 0.1, 0.0) == [0, 1]
+
+
+def test_peak_finders_restated():
+    from scipy.signal import find_peaks
+    from oracle import peaks
+    rng = np.random.default_rng(1)
+    for _ in range(100):
+        x = rng.integers(0, 6, int(rng.integers(1, 40))).astype(np.float32) / 5
+        h = float(rng.integers(0, 6)) / 5
+        assert np.array_equal(peaks.find_peaks_height(x, h), find_peaks(x, height=h)[0])
+    m = np.zeros((5, 6), np.float32)
+    assert len(peaks.peak_local_max(m, -1.0)) == 0                       # constant map -> no peaks
+    m[2, 3] = 0.9; m[0, 0] = 0.9; m[4, 5] = 0.5; m[2, 4] = 0.9          # plateau (2,3)-(2,4), border peaks
+    got = peaks.peak_local_max(m, 0.4).tolist()
+    assert got == [[0, 0], [2, 3], [2, 4], [4, 5]]
+    assert peaks.peak_local_max(m, 0.5).tolist() == [[0, 0], [2, 3], [2, 4]]   # strict threshold
