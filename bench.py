@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the MTM hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C2|C3|C4|C5]
+
+One "step" = one full ``matchTemplates`` pass (score maps -> peaks -> NMS) of the
+workload's template set over one synthetic image.  Default workload (N=1): C2 =
+BASELINE.json configs[1]: 1920x1080 uint8 image, 8 templates 64x64 (2 bases x 4
+rot90), score_threshold 0.5, maxOverlap 0.25.
+
+* ``value``  : template-matches/s with inputs resident in HBM (device image pool
+               larger than L2, rotated every step; templates resident), timed with
+               CUDA events on the library's stream, max over ranks.
+* ``e2e``    : the same metric through the public Python API ``MTM.matchTemplates``
+               with HOST (pinned) image/template arrays: H2D of image + templates
+               and D2H of the hit list inside the timed region.
+* ``roofline``: the numerator kernel (ncc_direct / ncc_tc), bracketed by CUDA events
+               inside the same timed region (MTM_OPT_TIME_NCC).
+* ``cpu_baseline`` / ``--impl reference``: the CPU port of the reference on live
+               OpenCV (oracle/mtm_port.py; /root/reference cannot travel to the GPU
+               box), its own thread pool + cv2's threads, same workload.
+
+N > 1 (torchrun, one rank per GPU, weak scaling): every rank runs the workload's
+template set over its own image stream; no data-path collective is needed for
+independent images (SURVEY.md 8e, C5 partitioning); the max-over-ranks time comes
+from an all-reduce(MAX) of the device-timed durations.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "template-matches/sec"
+L2_BYTES = 126 * 1024 * 1024
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def build_workload(name, n_images):
+    """Seeded synthetic inputs of SURVEY.md 8(d); the image pool is made of circular
+    shifts of a few generated scenes (distinct memory, same statistics)."""
+    from oracle import synth
+    base_imgs = []
+    image0, templates, params = synth.config(name, seed=0)
+    base_imgs.append(image0)
+    for k in range(1, min(4, n_images)):
+        img, _, _ = synth.config(name, seed=0, image_index=k)
+        base_imgs.append(img)
+    pool = []
+    for i in range(n_images):
+        b = base_imgs[i % len(base_imgs)]
+        s = i // len(base_imgs)
+        pool.append(np.ascontiguousarray(np.roll(b, (37 * s, 101 * s), axis=(0, 1))))
+    return pool, templates, params
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.FIELDS,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        self.f.close()
+        os.unlink(self.f.name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def cpu_port_run(pool, templates, params, steps, warmup):
+    """Times the CPU port (reference orchestration on live cv2).  Returns (sec/step, info)."""
+    import cv2
+    from oracle import mtm_port
+    for i in range(warmup):
+        mtm_port.match_templates(templates, pool[i % len(pool)], **params)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        mtm_port.match_templates(templates, pool[i % len(pool)], **params)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    info = {"cores": os.cpu_count(), "pool_workers": round(os.cpu_count() * .5), "cv2": cv2.__version__,
+            "cv2_threads": cv2.getNumThreads(), "ipp": bool(cv2.ipp.useIPP())}
+    return dt, info
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--path", default="auto", choices=["auto", "direct", "tensor"])
+    ap.add_argument("--cpu-steps", type=int, default=None, help="steps of the cpu_baseline sample (default: ~15 s)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    from oracle import synth
+
+    # ------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        steps = args.steps if args.steps is not None else 30
+        warmup = args.warmup if args.warmup is not None else 3
+        pool, templates, params = build_workload(args.workload, 8)
+        dt, info = cpu_port_run(pool, templates, params, steps, warmup)
+        n_t = len(templates)
+        macs = synth.macs(pool[0].shape, templates)
+        value = n_t / dt
+        line = {"metric": METRIC, "value": value, "unit": "matches/s", "n_gpus": args.gpus, "steps": steps,
+                "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8", "data": "synthetic", "impl": "reference",
+                "config": {"workload": args.workload, "image": list(pool[0].shape), "templates": n_t,
+                           "template_shape": list(templates[0][1].shape), "score_threshold": params["score_threshold"],
+                           "maxOverlap": params["maxOverlap"]},
+                "gpix_corr_per_s": macs / dt / 1e9,
+                "cpu_baseline": {"value": value, "unit": "matches/s", "cores": info["cores"], "kind": "port",
+                                 "sample": "%d full %s steps (all templates, whole image)" % (steps, args.workload),
+                                 **{k: info[k] for k in ("pool_workers", "cv2", "cv2_threads", "ipp")}},
+                "e2e": {"value": value, "unit": "matches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    import torch.distributed as dist
+    steps = args.steps if args.steps is not None else 300
+    warmup = args.warmup if args.warmup is not None else 10
+    warmup = max(warmup, 3)
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import MTM
+    from mtm_b200 import _native
+    ctx = _native.Context(local_rank)
+    if args.path != "auto":
+        ctx.set_path({"direct": _native.PATH_DIRECT, "tensor": _native.PATH_TENSOR}[args.path])
+
+    img_bytes = None
+    pool_n = 8
+    probe, templates, params = build_workload(args.workload, 1)
+    img_bytes = probe[0].nbytes
+    pool_n = max(8, int(np.ceil(1.5 * L2_BYTES / img_bytes)))          # image pool > L2
+    pool_n = min(pool_n, 128)
+    pool, templates, params = build_workload(args.workload, pool_n)
+    # rank-dependent rotation so that ranks do not process identical streams
+    pool = pool[rank % len(pool):] + pool[:rank % len(pool)]
+    H, W = pool[0].shape[:2]
+    n_t = len(templates)
+    macs = synth.macs(pool[0].shape, templates)
+    n_obj = -1 if params["N_object"] == float("inf") else int(params["N_object"])
+    thr, ov = params["score_threshold"], params["maxOverlap"]
+
+    # device-resident pool (torch = device memory plumbing only) and pinned host pool
+    d_pool = torch.empty((pool_n, H, W), dtype=torch.uint8, device="cuda")
+    h_pool = []
+    for i, im in enumerate(pool):
+        hp = torch.from_numpy(im).pin_memory()
+        h_pool.append(hp)
+        d_pool[i].copy_(hp, non_blocking=True)
+    torch.cuda.synchronize()
+    h_np = [hp.numpy() for hp in h_pool]
+    tmpl_arrays = [t[1] for t in templates]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.synchronize()
+
+    def resident_step(i):
+        ctx.set_image_device(d_pool[i % pool_n].data_ptr(), H, W, 1, W)
+        return ctx.match_templates(5, n_obj, thr, ov)
+
+    # ---------------- value: inputs resident in HBM ----------------
+    ctx.set_templates(tmpl_arrays)
+    for i in range(warmup):
+        hits = resident_step(i)
+    n_hits_last = len(hits)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ctx.reset_counters()
+    ctx.set_time_ncc(True)
+    ctx.timer_begin()
+    for i in range(steps):
+        resident_step(warmup + i)
+    ms = ctx.timer_end()
+    ctx.set_time_ncc(False)
+    ctr = ctx.counters()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    t_ms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_max = float(t_ms.item())
+    value = world * n_t * steps / (ms_max * 1e-3)
+
+    # ---------------- e2e: public API, host buffers ----------------
+    e2e_steps = max(10, steps // 3)
+    for i in range(3):
+        MTM.matchTemplates(templates, h_np[i % pool_n], score_threshold=thr, maxOverlap=ov,
+                           N_object=params["N_object"], context=ctx)
+    barrier()
+    ctx.reset_counters()
+    ctx.timer_begin()
+    for i in range(e2e_steps):
+        MTM.matchTemplates(templates, h_np[(3 + i) % pool_n], score_threshold=thr, maxOverlap=ov,
+                           N_object=params["N_object"], context=ctx)
+    e_ms = ctx.timer_end()
+    ectr = ctx.counters()
+    barrier()
+    e_t = torch.tensor([e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e_t, op=dist.ReduceOp.MAX)
+    e2e_value = world * n_t * e2e_steps / (float(e_t.item()) * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---------------- roofline of the numerator kernel ----------------
+    peaks = load_peaks()
+    ncc_ms_per_step = ctr["ncc_ms"] / steps
+    ncc_launches_per_step = ctr["ncc_launches"] / steps
+    ach_tflops = 2.0 * macs / (ncc_ms_per_step * 1e-3) / 1e12 if ncc_ms_per_step > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "ncc numerator (+fused normalisation)",
+                "achieved": ach_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": ach_tflops / peaks["bf16_tflops"], "traffic": None,
+                "peak_source": "%s bf16 dense burst (MEASURED_PEAKS.json)" % peaks["source"],
+                "algorithmic_flops_per_step": 2.0 * macs, "launches_per_step": ncc_launches_per_step,
+                "kernel_ms_per_step": ncc_ms_per_step, "kernel_share_of_step": ncc_ms_per_step / (ms / steps)}
+
+    # ---------------- cpu baseline (bounded sample, rank 0, N == 1 only) ----------------
+    cpu = None
+    if world == 1:
+        dt1, _ = cpu_port_run(pool, templates, params, 1, 1)
+        cpu_steps = args.cpu_steps if args.cpu_steps is not None else int(min(200, max(3, round(15.0 / dt1))))
+        dt, info = cpu_port_run(pool, templates, params, cpu_steps, 1)
+        cpu = {"value": n_t / dt, "unit": "matches/s", "cores": info["cores"], "kind": "port",
+               "sample": "%d full %s steps (all templates, whole image), %.1f s" % (cpu_steps, args.workload, dt * cpu_steps),
+               "ms_per_step": dt * 1e3, **{k: info[k] for k in ("pool_workers", "cv2", "cv2_threads", "ipp")}}
+
+    line = {"metric": METRIC, "value": value, "unit": "matches/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": args.workload, "image": [H, W], "templates": n_t,
+                       "template_shape": list(templates[0][1].shape), "score_threshold": thr, "maxOverlap": ov,
+                       "N_object": "inf" if n_obj < 0 else n_obj, "per_gpu": "whole template set over its own image stream",
+                       "l2_policy": "inputs larger than L2: %d-image device pool (%.0f MB) rotated every step"
+                                    % (pool_n, pool_n * img_bytes / 1e6),
+                       "hits_last_step": n_hits_last, "path": args.path},
+            "gpix_corr_per_s": world * macs * steps / (ms_max * 1e-3) / 1e9,
+            "gpu_launches": int(ctr["kernel_launches"]),
+            "gpu_launches_per_step": ctr["kernel_launches"] / steps,
+            "e2e": {"value": e2e_value, "unit": "matches/s", "steps": e2e_steps,
+                    "ms_per_step": float(e_t.item()) / e2e_steps,
+                    "h2d_bytes_per_step": ectr["h2d_bytes"] / e2e_steps, "d2h_bytes_per_step": ectr["d2h_bytes"] / e2e_steps,
+                    "api": "MTM.matchTemplates(listTemplates, image) with pinned host arrays"},
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -40,7 +40,10 @@ typedef enum mtm_method {
 
 /* Numerator kernel selection (mtm_set_option MTM_OPT_PATH). */
 typedef enum mtm_path { MTM_PATH_AUTO = 0, MTM_PATH_DIRECT = 1, MTM_PATH_TENSOR = 2 } mtm_path;
-typedef enum mtm_option { MTM_OPT_PATH = 0 } mtm_option;
+typedef enum mtm_option {
+    MTM_OPT_PATH = 0,          /* mtm_path */
+    MTM_OPT_TIME_NCC = 1       /* 1: bracket the numerator kernels with CUDA events (roofline timing) */
+} mtm_option;
 
 /* Device/host mirror of the reference's Hit tuple (label, (x, y, w, h), score),
  * MTM/NMS.py:18; `tmpl` indexes the template list instead of carrying the label. */
@@ -54,6 +57,8 @@ typedef struct mtm_counters {
     int64_t kernel_launches;   /* kernels of this library launched since the last reset */
     int64_t h2d_bytes;
     int64_t d2h_bytes;
+    int64_t ncc_launches;      /* numerator (K2/K3) kernel launches timed with MTM_OPT_TIME_NCC   */
+    double ncc_ms;             /* their summed device time in ms (CUDA events on the ctx stream) */
 } mtm_counters;
 
 typedef struct mtm_ctx mtm_ctx;

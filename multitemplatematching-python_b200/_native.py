@@ -13,14 +13,15 @@ LIB_PATH = os.path.join(HERE, "libmtm_b200.so")
 MTM_OK, MTM_ERR_INVALID, MTM_ERR_CUDA, MTM_ERR_CAPACITY, MTM_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 MTM_U8, MTM_F32 = 0, 1
 PATH_AUTO, PATH_DIRECT, PATH_TENSOR = 0, 1, 2
-OPT_PATH = 0
+OPT_PATH, OPT_TIME_NCC = 0, 1
 
 HIT_DTYPE = np.dtype([("tmpl", "<i4"), ("x", "<i4"), ("y", "<i4"), ("w", "<i4"), ("h", "<i4"), ("score", "<f4")])
 assert HIT_DTYPE.itemsize == 24
 
 
 class Counters(ctypes.Structure):
-    _fields_ = [("kernel_launches", ctypes.c_int64), ("h2d_bytes", ctypes.c_int64), ("d2h_bytes", ctypes.c_int64)]
+    _fields_ = [("kernel_launches", ctypes.c_int64), ("h2d_bytes", ctypes.c_int64), ("d2h_bytes", ctypes.c_int64),
+                ("ncc_launches", ctypes.c_int64), ("ncc_ms", ctypes.c_double)]
 
 
 # name -> (restype, argtypes); mirrors include/mtm_b200.h one to one
@@ -133,7 +134,11 @@ class Context:
     def counters(self):
         c = Counters()
         self._check(self._lib.mtm_get_counters(self._h, ctypes.byref(c)))
-        return {"kernel_launches": c.kernel_launches, "h2d_bytes": c.h2d_bytes, "d2h_bytes": c.d2h_bytes}
+        return {"kernel_launches": c.kernel_launches, "h2d_bytes": c.h2d_bytes, "d2h_bytes": c.d2h_bytes,
+                "ncc_launches": c.ncc_launches, "ncc_ms": c.ncc_ms}
+
+    def set_time_ncc(self, on):
+        self._check(self._lib.mtm_set_option(self._h, OPT_TIME_NCC, 1 if on else 0))
 
     def reset_counters(self):
         self._check(self._lib.mtm_reset_counters(self._h))

@@ -47,6 +47,21 @@ static int reserve_pinned(mtm_ctx* ctx, T*& ptr, size_t& cap, size_t need)
     if (!(ctx)) return MTM_ERR_INVALID;                                       \
     MTM_CUDA(ctx, cudaSetDevice((ctx)->device))
 
+// Folds the pending MTM_OPT_TIME_NCC event bracket into the counters (needs the events complete).
+static int harvest_ncc_time(mtm_ctx* ctx, bool wait)
+{
+    if (!ctx->ncc_pending) return MTM_OK;
+    if (wait) MTM_CUDA(ctx, cudaEventSynchronize(ctx->ev_ncc1));
+    float ms = 0.f;
+    cudaError_t e = cudaEventElapsedTime(&ms, ctx->ev_ncc0, ctx->ev_ncc1);
+    if (e == cudaErrorNotReady) { (void)cudaGetLastError(); return MTM_OK; }
+    MTM_CUDA(ctx, e);
+    ctx->ctr.ncc_ms += ms;
+    ctx->ctr.ncc_launches += ctx->ncc_pending_launches;
+    ctx->ncc_pending = 0;
+    return MTM_OK;
+}
+
 static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 static int reserve_hits(mtm_ctx* ctx, int cap)
@@ -105,6 +120,8 @@ int mtm_create(int device, mtm_ctx** out)
     ctx->stream = ctx->own_stream;
     if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreate(&ctx->ev_ncc0)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreate(&ctx->ev_ncc1)) != cudaSuccess) return bail("cudaEventCreate", e);
     int rc = reserve_hits(ctx, 1 << 16);
     if (rc != MTM_OK) { g_create_err = ctx->err; mtm_destroy(ctx); return rc; }
     *out = ctx;
@@ -120,9 +137,12 @@ int mtm_destroy(mtm_ctx* ctx)
     cudaFree(ctx->d_meta); cudaFree(ctx->d_tmpl); cudaFree(ctx->d_maps); cudaFree(ctx->d_order);
     cudaFree(ctx->d_blockA); cudaFree(ctx->d_blockB); cudaFree(ctx->d_keep);
     cudaFree(ctx->d_nontrivial); cudaFree(ctx->d_best);
+    cudaFree(ctx->d_slabs); cudaFree(ctx->d_wS); cudaFree(ctx->d_wR);
     cudaFreeHost(ctx->h_tmpl_stage); cudaFreeHost(ctx->h_stage); cudaFreeHost(ctx->h_geom);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_ncc0) cudaEventDestroy(ctx->ev_ncc0);
+    if (ctx->ev_ncc1) cudaEventDestroy(ctx->ev_ncc1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return MTM_OK;
@@ -147,12 +167,15 @@ int mtm_set_option(mtm_ctx* ctx, int option, int64_t value)
 {
     if (!ctx) return MTM_ERR_INVALID;
     if (option == MTM_OPT_PATH && value >= MTM_PATH_AUTO && value <= MTM_PATH_TENSOR) { ctx->path = (int)value; return MTM_OK; }
+    if (option == MTM_OPT_TIME_NCC) { ctx->time_ncc = value ? 1 : 0; return MTM_OK; }
     return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_option: unknown option %d / value %lld", option, (long long)value);
 }
 
 int mtm_get_counters(mtm_ctx* ctx, mtm_counters* out)
 {
     if (!ctx || !out) return MTM_ERR_INVALID;
+    MTM_CUDA(ctx, cudaSetDevice(ctx->device));
+    MTM_TRY(harvest_ncc_time(ctx, true));
     *out = ctx->ctr;
     return MTM_OK;
 }
@@ -208,6 +231,7 @@ static int set_image_impl(mtm_ctx* ctx, const void* pixels, int H, int W, int C,
     MTM_TRY(mtm_reserve(ctx, ctx->scratch, ctx->scratch_cap, (size_t)(C + 1) * H * W));
     ctx->img_dtype = dtype;
     ctx->geometry_valid = false;
+    ctx->moments_valid = false;
     MTM_TRY(launch_build_sat(ctx));
     return MTM_OK;
 }
@@ -240,12 +264,111 @@ static int ensure_geometry(mtm_ctx* ctx)
     return MTM_OK;
 }
 
+// Groups the (h, w)-sorted templates into tcgen05 launches and expands their Toeplitz slabs
+// (template-only work: done once per mtm_set_templates).  Leaves tc_ready false when some
+// template cannot take the tensor path (multi-channel, too large for shared memory, ...).
+static int plan_tensor_path(mtm_ctx* ctx)
+{
+    ctx->tc_groups.clear();
+    ctx->tc_ready = false;
+    ctx->moments_valid = false;
+    if (ctx->tmpl_C != 1 || ctx->tmpl_dtype != MTM_U8) return MTM_OK;
+    const int n = ctx->n_tmpl;
+    int64_t arena = 0;
+    int size_id = 0;
+    int i = 0;
+    while (i < n) {
+        const TmplMeta& a = ctx->h_meta[ctx->h_order[i]];
+        int j = i + 1;
+        while (j < n && ctx->h_meta[ctx->h_order[j]].h == a.h && ctx->h_meta[ctx->h_order[j]].w == a.w) ++j;
+        TcGroup ga{}, gb{};
+        const bool okA = tc_plan_group(0, a.h, a.w, ga), okB = tc_plan_group(1, a.h, a.w, gb);
+        if (!okA && !okB) return MTM_OK;
+        int k = i;
+        while (k < j) {
+            const int left = j - k;
+            // mode A wastes (8 - count)/8 of the M rows, mode B pays the wider Toeplitz band
+            const double effA = okA ? ga.eff * std::min(left, 8) / 8.0 : -1.0;
+            const double effB = okB ? gb.eff : -1.0;
+            TcGroup g = (effA >= effB) ? ga : gb;
+            g.first = k;
+            g.count = (g.mode == 0) ? std::min(left, 8) : 1;
+            g.size_id = size_id;
+            g.arena_off = arena;
+            arena += ((int64_t)g.h * g.slab_bytes + 127) / 128 * 128;
+            ctx->tc_groups.push_back(g);
+            k += g.count;
+        }
+        ++size_id;
+        i = j;
+    }
+    MTM_TRY(mtm_reserve(ctx, ctx->d_slabs, ctx->slabs_cap, (size_t)arena + 128));
+    for (const TcGroup& g : ctx->tc_groups) MTM_TRY(launch_toeplitz_prep(ctx, g));
+    ctx->size_map_off.assign(size_id, 0);
+    ctx->tc_ready = true;
+    return MTM_OK;
+}
+
+// Window moments (S, rsqrt(A*Q - S^2)) for every distinct template size; image-dependent.
+static int ensure_moments(mtm_ctx* ctx)
+{
+    if (ctx->moments_valid) return MTM_OK;
+    int64_t off = 0;
+    int last = -1;
+    for (const TcGroup& g : ctx->tc_groups) {
+        if (g.size_id == last) continue;
+        last = g.size_id;
+        ctx->size_map_off[g.size_id] = off;
+        off += ((int64_t)(ctx->img.H - g.h + 1) * (ctx->img.W - g.w + 1) + 31) / 32 * 32;
+    }
+    MTM_TRY(mtm_reserve(ctx, ctx->d_wS, ctx->wS_cap, (size_t)off));
+    MTM_TRY(mtm_reserve(ctx, ctx->d_wR, ctx->wR_cap, (size_t)off));
+    last = -1;
+    for (const TcGroup& g : ctx->tc_groups) {
+        if (g.size_id == last) continue;
+        last = g.size_id;
+        const int64_t o = ctx->size_map_off[g.size_id];
+        MTM_TRY(launch_window_moments(ctx, g.h, g.w, ctx->img.H - g.h + 1, ctx->img.W - g.w + 1, ctx->d_wS + o, ctx->d_wR + o));
+    }
+    ctx->moments_valid = true;
+    return MTM_OK;
+}
+
+static bool use_tensor_path(const mtm_ctx* ctx, int method)
+{
+    if (ctx->path == MTM_PATH_DIRECT || !ctx->tc_ready) return false;
+    for (const TcGroup& g : ctx->tc_groups)
+        if (!tc_path_supported(ctx, method, g.h, g.w)) return false;
+    return true;
+}
+
 // Score maps of every template (tmpl < 0) or of one template, grouped by template size.
 static int compute_maps(mtm_ctx* ctx, int method, int tmpl)
 {
     if (method < 0 || method > 5) return mtm_fail(ctx, MTM_ERR_INVALID, "unknown method %d", method);
     const int n = ctx->n_tmpl;
     int i = 0;
+    const bool tensor = use_tensor_path(ctx, method);
+    if (!tensor && ctx->path == MTM_PATH_TENSOR)
+        return mtm_fail(ctx, MTM_ERR_UNSUPPORTED, "tensor-core path requested but not available for these inputs/method");
+    if (tensor) MTM_TRY(ensure_moments(ctx));
+    const int64_t launches_before = ctx->ctr.kernel_launches;
+    if (ctx->time_ncc) {
+        MTM_TRY(harvest_ncc_time(ctx, true));
+        MTM_CUDA(ctx, cudaEventRecord(ctx->ev_ncc0, ctx->stream));
+    }
+    if (tensor) {
+        for (const TcGroup& g : ctx->tc_groups) {
+            if (tmpl >= 0) {
+                bool has = false;
+                for (int k = 0; k < g.count; ++k) has = has || ctx->h_order[g.first + k] == tmpl;
+                if (!has) continue;
+            }
+            const int64_t o = ctx->size_map_off[g.size_id];
+            MTM_TRY(launch_ncc_tc(ctx, g, ctx->d_wS + o, ctx->d_wR + o));
+        }
+        i = n;
+    }
     while (i < n) {
         const TmplMeta& a = ctx->h_meta[ctx->h_order[i]];
         int j = i + 1;
@@ -257,6 +380,11 @@ static int compute_maps(mtm_ctx* ctx, int method, int tmpl)
                 if (ctx->h_order[k] == tmpl) MTM_TRY(launch_ncc_direct(ctx, method, k, 1));
         }
         i = j;
+    }
+    if (ctx->time_ncc) {
+        MTM_CUDA(ctx, cudaEventRecord(ctx->ev_ncc1, ctx->stream));
+        ctx->ncc_pending = 1;
+        ctx->ncc_pending_launches = (int)(ctx->ctr.kernel_launches - launches_before);
     }
     return MTM_OK;
 }
@@ -352,6 +480,7 @@ int mtm_set_templates(mtm_ctx* ctx, int n, const void* const* pixels, const int3
     ctx->n_tmpl = n; ctx->tmpl_C = C; ctx->tmpl_dtype = dtype;
     ctx->geometry_valid = false;
     MTM_TRY(launch_tmpl_stats(ctx));
+    MTM_TRY(plan_tensor_path(ctx));
     return MTM_OK;
 }
 

@@ -35,6 +35,20 @@ struct TmplMeta {
     double norm_ccoeff;        // sqrt(sum_c var_c) / sqrt(invArea)
     double norm_plain;         // sqrt(sum_c var_c + mean_c^2) / sqrt(invArea)
     double inv_area;
+    long long isum;            // integer sum of the (single-channel) template: tensor-core epilogue
+    float inv_sqrt_d2;         // 1 / sqrt(A*sumT2 - sumT^2)
+    float pad_f;
+};
+
+// One launch of the tcgen05 kernel: `count` same-size templates d_order[first .. first+count).
+struct TcGroup {
+    int mode;                  // 0: 8 templates x 16 x-offsets, 1: 1 template x 128 x-offsets
+    int first, count;
+    int h, w, nk, a_kblk, slab_bytes, ds, N, R;
+    size_t smem;
+    int64_t arena_off;         // byte offset of the group's Toeplitz slabs in d_slabs
+    int size_id;               // index into the per-size window-moment maps
+    double eff;
 };
 
 struct ImageDev {
@@ -54,6 +68,8 @@ struct mtm_ctx {
     mtm_counters ctr{};
     int path = MTM_PATH_AUTO;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_ncc0 = nullptr, ev_ncc1 = nullptr;   // MTM_OPT_TIME_NCC bracket of the last compute_maps
+    int time_ncc = 0, ncc_pending = 0, ncc_pending_launches = 0;
     int sm_count = 0;
 
     // image
@@ -75,6 +91,16 @@ struct mtm_ctx {
     float* d_maps = nullptr; size_t maps_cap = 0;   // elements
     int64_t maps_total = 0;
     int maps_method = -1;                // method the resident maps were computed with (-1: stale)
+
+    // tensor-core path (ncc_tc.cu)
+    std::vector<TcGroup> tc_groups;                      // covers every template when tc_ready
+    bool tc_ready = false;
+    uint8_t* d_slabs = nullptr; size_t slabs_cap = 0;    // Toeplitz-expanded template rows
+    std::vector<int64_t> size_map_off;                   // per distinct (h, w): element offset of its moment maps
+    uint32_t* d_wS = nullptr; size_t wS_cap = 0;         // window sums S
+    float* d_wR = nullptr; size_t wR_cap = 0;            // rsqrt(A*Q - S^2)
+    bool moments_valid = false;
+    bool tc_attr_set = false;
 
     int32_t* d_order = nullptr; size_t order_cap = 0;   // template indices sorted by (h, w)
     std::vector<int32_t> h_order;
@@ -117,6 +143,12 @@ int launch_build_sat(mtm_ctx* ctx);
 int launch_tmpl_stats(mtm_ctx* ctx);
 // templates d_order[first .. first+count) share (h, w)
 int launch_ncc_direct(mtm_ctx* ctx, int method, int first, int count);
+// tensor-core path
+bool tc_path_supported(const mtm_ctx* ctx, int method, int h, int w);
+bool tc_plan_group(int mode, int h, int w, TcGroup& g);
+int launch_toeplitz_prep(mtm_ctx* ctx, const TcGroup& g);
+int launch_window_moments(mtm_ctx* ctx, int h, int w, int mh, int mw, uint32_t* S, float* rsD);
+int launch_ncc_tc(mtm_ctx* ctx, const TcGroup& g, const uint32_t* S, const float* rsD);
 // raw (unsorted) peaks of every template -> block A
 int launch_peaks(mtm_ctx* ctx, int method, int64_t n_object, float thr32, double thr64);
 // in-place sort of block A (mode 0: findMatches order, mode 1: NMSBoxes order)

@@ -1,0 +1,366 @@
+// ncc_tc.cu -- K3: sliding-window correlation on the 5th-gen tensor cores (tcgen05, sm_100a).
+//
+// The numerator of cv2.matchTemplate (MTM/__init__.py:92)
+//     CC[t](y, x) = sum_dy sum_dx I[y+dy][x+dx] * T_t[dy][dx]
+// is computed EXACTLY as an integer GEMM per template row dy:
+//     D[m][n] += A_dy[m][k] * B_dy[n][k]          tcgen05.mma kind::i8, u8 x u8 -> 32-bit in TMEM
+//   n (N, up to 256)  : output row y            B_dy[n][k] = I[y0 + n + dy][x0 + k]
+//   k (K = 32*nk)     : image column in the tile
+//   m (M = 128)       : (template, x-offset)    A_dy[m][k] = T_t[dy][k - j]   (banded / Toeplitz)
+// so the image tile is loaded ONCE into shared memory and every dy just moves the B
+// descriptor's start address by one 16-byte row (no-swizzle K-major layout
+// [k-block][row][16 B], SBO = 128 B, LBO = rows*16 B).  The Toeplitz A slabs are
+// expanded once per template set (toeplitz_prep_kernel) and streamed per dy with
+// cp.async.bulk + mbarrier into a 4-stage ring.
+//   mode A: m = (t, r):  8 templates x 16 x-offsets     slab [k-block][t][r][16 B]
+//   mode B: m = (q', r): 1 template x 128 x-offsets, x = x0 + 16*(7-q') + r; slab
+//           [block b][r][16 B] with LBO = 256 B so that consecutive K blocks alias the next
+//           row groups (the band is shift-invariant) -- 8x less slab data.
+// Accumulators (128 lanes x N columns, 32-bit) live in TMEM; the epilogue reads them with
+// tcgen05.ld and applies OpenCV's normalisation in exact-integer + fp32 form:
+//     score = (A*CC - S*sumT) * rsqrt(A*Q - S^2) * rsqrt(A*sumT2 - sumT^2),  clamped to [-1, 1],
+// with S and rsqrt(A*Q - S^2) precomputed per window size (window_moments_kernel).
+// Roofline: tensor pipe (kind::i8, 8192 MAC/clk/SM); useful fraction w / (32*nk).
+#include "mtm_internal.cuh"
+#include "ncc_epilogue.cuh"
+#include <algorithm>
+
+namespace {
+
+constexpr int TC_THREADS = 256;
+constexpr int TC_STAGES = 4;
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    // try_wait suspends for a bounded time per call; a barrier that never completes (a bug, not a
+    // load condition) traps instead of hanging the GPU.
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
+        if (spins > (1u << 24)) __trap();
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, no-swizzle shared-memory matrix descriptor (sm_100 "version 1").
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+
+struct TcParams {
+    const uint8_t* img; int64_t pitch; int H, W;
+    const uint8_t* slabs;             // this group's Toeplitz slabs: h slabs of slab_bytes
+    int slab_bytes;
+    int a_kblk;                       // bytes between consecutive K blocks of a slab (2048 mode A, 256 mode B)
+    int nk;                           // K chunks (32 bytes each) per dy
+    int ds;                           // slabs (dy values) per ring stage
+    int mode;                         // 0 = A (8 templates x 16 x), 1 = B (1 template x 128 x)
+    int N;                            // output rows per tile == MMA N == TMEM columns used
+    int R;                            // image tile rows = N + h - 1
+    int h, w, mh, mw;
+    const TmplMeta* meta; const int32_t* order; int count;
+    const uint32_t* S; const float* rsD;   // window moments of this (h, w): [mh][mw]
+    float* maps;
+};
+
+// One CTA = one output tile.  Warp 0: slab producer, warp 1: MMA issuer, then all 8 warps: epilogue.
+__global__ void __launch_bounds__(TC_THREADS, 1)
+ncc_tc_kernel(const TcParams p)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int kb_img = 2 * p.nk;                               // 16-byte K blocks of the image tile
+    const uint32_t tile_bytes = (uint32_t)kb_img * p.R * 16;
+    const uint32_t stage_bytes = (uint32_t)p.ds * p.slab_bytes;
+    uint8_t* tile = smem;
+    uint8_t* ring = smem + ((tile_bytes + 127) & ~127u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + TC_STAGES * stage_bytes);
+    uint64_t* full = bars;                                     // [TC_STAGES]
+    uint64_t* empty = bars + TC_STAGES;                        // [TC_STAGES]
+    uint64_t* accum = bars + 2 * TC_STAGES;                    // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
+
+    const int xw = p.mode == 0 ? 16 : 128;
+    const int x0 = blockIdx.x * xw, y0 = blockIdx.y * p.N;
+    const uint32_t tmem_cols = p.N < 32 ? 32u : (uint32_t)p.N;
+
+    if (tid == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(accum, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
+
+    // ---- stage the image tile: rows [y0, y0+R) x bytes [x0, x0 + 32*nk), layout [k-block][row][16 B]
+    {
+        const int pieces = kb_img * p.R;
+        for (int idx = tid; idx < pieces; idx += TC_THREADS) {
+            const int c = idx / p.R, r = idx - c * p.R;
+            const int gy = y0 + r;
+            const int64_t gb = (int64_t)x0 + 16 * c;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (gy < p.H && gb + 16 <= p.pitch) v = *reinterpret_cast<const uint4*>(p.img + (int64_t)gy * p.pitch + gb);
+            *reinterpret_cast<uint4*>(tile + (size_t)idx * 16) = v;
+        }
+    }
+    fence_async_smem();                                        // generic-proxy writes -> visible to the MMA (async proxy)
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot;
+
+    const int n_iters = (p.h + p.ds - 1) / p.ds;
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < n_iters; ++it) {
+                const int s = it % TC_STAGES;
+                if (it >= TC_STAGES) mbar_wait(&empty[s], ((it / TC_STAGES) - 1) & 1);
+                const int rows = min(p.ds, p.h - it * p.ds);
+                const uint32_t bytes = (uint32_t)rows * p.slab_bytes;
+                mbar_expect_tx(&full[s], bytes);
+                bulk_g2s(ring + (size_t)s * stage_bytes, p.slabs + (size_t)it * stage_bytes, bytes, &full[s]);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = (2u << 4) | ((uint32_t)(p.N >> 3) << 17) | ((128u >> 4) << 24);   // S32 accum, u8 x u8, K-major
+            const uint32_t tile_addr = smem_u32(tile), ring_addr = smem_u32(ring);
+            const uint32_t lbo_b = (uint32_t)p.R * 16;
+            for (int it = 0; it < n_iters; ++it) {
+                const int s = it % TC_STAGES;
+                mbar_wait(&full[s], (it / TC_STAGES) & 1);
+                tc_fence_after();
+                const int rows = min(p.ds, p.h - it * p.ds);
+                for (int d = 0; d < rows; ++d) {
+                    const int dy = it * p.ds + d;
+                    const uint32_t a_base = ring_addr + s * stage_bytes + d * p.slab_bytes;
+                    const uint32_t b_base = tile_addr + dy * 16;
+                    for (int i = 0; i < p.nk; ++i) {
+                        const uint64_t ad = umma_desc(a_base + 2 * i * p.a_kblk, (uint32_t)p.a_kblk, 128);
+                        const uint64_t bd = umma_desc(b_base + 2 * i * lbo_b, lbo_b, 128);
+                        umma_i8(tmem_d, ad, bd, idesc, (dy | i) != 0);
+                    }
+                }
+                umma_commit(&empty[s]);                        // frees the ring slot when these MMAs retire
+            }
+            umma_commit(accum);                                // all MMAs of the tile retired -> epilogue may read TMEM
+        }
+        __syncwarp();
+    }
+
+    // ---- epilogue: all 8 warps.  warp%4 selects the TMEM lane quarter, warp/4 the column half.
+    mbar_wait(accum, 0);
+    tc_fence_after();
+    {
+        const int m = 32 * (warp & 3) + lane;
+        int x, tsel;
+        if (p.mode == 0) { tsel = m >> 4; x = x0 + (m & 15); }
+        else { tsel = 0; x = x0 + 16 * (7 - (m >> 4)) + (m & 15); }
+        const bool live = (tsel < p.count) && (x < p.mw);
+        const TmplMeta* tm = live ? &p.meta[p.order[tsel]] : nullptr;
+        const long long area = (long long)p.h * p.w;
+        const long long sumT = live ? tm->isum : 0;
+        const float ct = live ? tm->inv_sqrt_d2 : 0.f;
+        const bool is_const = live ? (tm->is_const != 0) : false;
+        float* out = live ? p.maps + tm->map_off : nullptr;
+        const int half = p.N >> 1;                             // N >= 32: each warp pair splits the columns
+        const int c_begin = (warp >> 2) * half, c_end = c_begin + half;
+        for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c0, v);
+            if (!live) continue;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const int y = y0 + c0 + k;
+                if (y >= p.mh) break;
+                const int64_t o = (int64_t)y * p.mw + x;
+                const float rs = p.rsD[o];
+                const long long n1 = area * (long long)v[k] - (long long)p.S[o] * sumT;
+                float r = (float)n1 * rs * ct;
+                r = fminf(1.0f, fmaxf(-1.0f, r));
+                out[o] = is_const ? 1.0f : r;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_d, tmem_cols);
+}
+
+// Expands the templates of one group into Toeplitz slabs (see the header comment).
+__global__ void toeplitz_prep_kernel(const uint8_t* __restrict__ tmpl, const TmplMeta* __restrict__ meta,
+                                     const int32_t* __restrict__ order, int count, int mode, int h, int w,
+                                     int nk, int slab_bytes, uint8_t* __restrict__ slabs)
+{
+    const int pieces_per_slab = slab_bytes / 16;
+    const int64_t total = (int64_t)h * pieces_per_slab;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int dy = (int)(idx / pieces_per_slab);
+        const int pc = (int)(idx - (int64_t)dy * pieces_per_slab);
+        int t, r, ubase;                                   // ubase: template column of byte 0 of this piece
+        if (mode == 0) { const int c = pc >> 7; t = (pc >> 4) & 7; r = pc & 15; ubase = 16 * c - r; }
+        else { const int b = pc >> 4; t = 0; r = pc & 15; ubase = 16 * (b - 7) - r; }
+        uint8_t bytes[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) bytes[k] = 0;
+        if (t < count) {
+            const TmplMeta& tm = meta[order[t]];
+            const uint8_t* row = tmpl + tm.pix_off + (int64_t)dy * tm.wp;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const int col = ubase + k;
+                if (col >= 0 && col < w) bytes[k] = row[col];
+            }
+        }
+        *reinterpret_cast<uint4*>(slabs + (int64_t)dy * slab_bytes + (int64_t)pc * 16) = *reinterpret_cast<const uint4*>(bytes);
+    }
+}
+
+// S = window sum, rsD = rsqrt(A*Q - S^2) (0 for an exactly flat window), per window position.
+__global__ void window_moments_kernel(SatView sat, int h, int w, int mh, int mw, uint32_t* __restrict__ S,
+                                      float* __restrict__ rsD)
+{
+    const int64_t n = (int64_t)mh * mw;
+    const unsigned long long area = (unsigned long long)h * w;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int y = (int)(idx / mw), x = (int)(idx - (int64_t)y * mw);
+        const uint32_t s = sat_window_s(sat.s, sat.pitch, y, x, h, w);
+        const unsigned long long q = sat_window_q(sat.q, sat.pitch, y, x, h, w);
+        const unsigned long long d1 = area * q - (unsigned long long)s * s;
+        S[idx] = s;
+        rsD[idx] = d1 ? rsqrtf((float)d1) : 0.0f;
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------ host side
+bool tc_path_supported(const mtm_ctx* ctx, int method, int h, int w)
+{
+    if (ctx->img.C != 1 || method != MTM_TM_CCOEFF_NORMED) return false;
+    if ((long long)h * w < 16 || (double)h * w * 65025.0 >= 4294967296.0) return false;   // 32-bit exact range; tiny windows -> fp64 path
+    return true;
+}
+
+// Plans a group of `count` same-size templates.  Returns false when the tile does not fit shared memory.
+bool tc_plan_group(int mode, int h, int w, TcGroup& g)
+{
+    g.mode = mode; g.h = h; g.w = w;
+    const int nx = mode == 0 ? 16 : 128;
+    g.nk = (w + nx - 1 + 31) / 32;
+    g.a_kblk = mode == 0 ? 2048 : 256;
+    g.slab_bytes = mode == 0 ? 2 * g.nk * 2048 : (7 + 2 * g.nk) * 256;
+    g.ds = 1;
+    while ((g.ds + 1) * g.slab_bytes <= 16384 && g.ds < h) ++g.ds;
+    const size_t ring = (size_t)TC_STAGES * g.ds * g.slab_bytes;
+    const int candidates[4] = {256, 128, 64, 32};
+    g.N = 0;
+    for (int pass = 0; pass < 2 && !g.N; ++pass) {
+        const size_t budget = pass == 0 ? 110 * 1024 : 224 * 1024;       // first try 2 CTAs per SM
+        for (int n : candidates) {
+            const size_t tile = ((size_t)2 * g.nk * (n + h - 1) * 16 + 127) & ~(size_t)127;
+            if (tile + ring + 256 <= budget && (n + h - 1) * 16 < (1 << 18)) { g.N = n; break; }
+        }
+    }
+    if (!g.N) return false;
+    g.R = g.N + h - 1;
+    g.smem = (((size_t)2 * g.nk * g.R * 16 + 127) & ~(size_t)127) + ring + 256;
+    g.eff = (double)w / (32.0 * g.nk);
+    return true;
+}
+
+int launch_toeplitz_prep(mtm_ctx* ctx, const TcGroup& g)
+{
+    const int64_t pieces = (int64_t)g.h * (g.slab_bytes / 16);
+    const int blocks = (int)std::min<int64_t>((pieces + 255) / 256, 4096);
+    toeplitz_prep_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_tmpl, ctx->d_meta, ctx->d_order + g.first, g.count, g.mode,
+                                                         g.h, g.w, g.nk, g.slab_bytes, ctx->d_slabs + g.arena_off);
+    MTM_LAUNCH_CHECK(ctx);
+    return MTM_OK;
+}
+
+int launch_window_moments(mtm_ctx* ctx, int h, int w, int mh, int mw, uint32_t* S, float* rsD)
+{
+    const ImageDev& im = ctx->img;
+    SatView sv{im.sat_s, im.sat_q, im.sat_pitch, (int64_t)(im.H + 1) * im.sat_pitch};
+    const int64_t n = (int64_t)mh * mw;
+    const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 16);
+    window_moments_kernel<<<blocks, 256, 0, ctx->stream>>>(sv, h, w, mh, mw, S, rsD);
+    MTM_LAUNCH_CHECK(ctx);
+    return MTM_OK;
+}
+
+int launch_ncc_tc(mtm_ctx* ctx, const TcGroup& g, const uint32_t* S, const float* rsD)
+{
+    const ImageDev& im = ctx->img;
+    TcParams p{};
+    p.img = im.pix; p.pitch = im.pitch; p.H = im.H; p.W = im.W;
+    p.slabs = ctx->d_slabs + g.arena_off; p.slab_bytes = g.slab_bytes; p.a_kblk = g.a_kblk; p.nk = g.nk; p.ds = g.ds;
+    p.mode = g.mode; p.N = g.N; p.R = g.R; p.h = g.h; p.w = g.w;
+    p.mh = im.H - g.h + 1; p.mw = im.W - g.w + 1;
+    p.meta = ctx->d_meta; p.order = ctx->d_order + g.first; p.count = g.count;
+    p.S = S; p.rsD = rsD; p.maps = ctx->d_maps;
+    if (!ctx->tc_attr_set) {
+        MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ctx->tc_attr_set = true;
+    }
+    const int xw = g.mode == 0 ? 16 : 128;
+    dim3 grid((p.mw + xw - 1) / xw, (p.mh + g.N - 1) / g.N);
+    ncc_tc_kernel<<<grid, TC_THREADS, g.smem, ctx->stream>>>(p);
+    MTM_LAUNCH_CHECK(ctx);
+    return MTM_OK;
+}

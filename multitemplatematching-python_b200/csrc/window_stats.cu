@@ -122,6 +122,11 @@ __global__ void tmpl_stats_kernel(const uint8_t* __restrict__ tmpl, TmplMeta* __
         for (int c = 0; c < MTM_MAX_CH; ++c) {
             long long a = 0, b = 0;
             for (int k = 0; k < nw; ++k) { a += red[c][k]; b += red[MTM_MAX_CH + c][k]; }
+            if (c == 0) {
+                const long long d2 = (long long)m.h * m.w * b - a * a;      // exact; > 0 unless the template is constant
+                m.isum = a;
+                m.inv_sqrt_d2 = d2 > 0 ? (float)(1.0 / sqrt((double)d2)) : 0.0f;
+            }
             const double mean = (double)a * inv_area;
             const double var = fmax((double)b * inv_area - mean * mean, 0.0);
             m.mean[c] = (c < C) ? mean : 0.0;

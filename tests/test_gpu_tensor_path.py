@@ -1,0 +1,102 @@
+"""-m gpu tests of the tcgen05 (tensor-core) numerator kernel against the exact oracle
+and against the dp4a direct kernel (both are exact-integer numerators: the maps may
+differ only by the fp32-vs-fp64 normalisation, far below the 1e-4 bar)."""
+import numpy as np
+import pytest
+
+from helpers import assert_hits_equal, assert_map_close
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctxs():
+    import MTM  # noqa: F401
+    from mtm_b200 import _native
+    t = _native.Context(0)
+    t.set_path(_native.PATH_TENSOR)
+    d = _native.Context(0)
+    d.set_path(_native.PATH_DIRECT)
+    yield t, d
+    t.close()
+    d.close()
+
+
+def _maps(mtm, ctx, temps, img):
+    return [mtm.computeScoreMap(t, img, context=ctx) for t in temps]
+
+
+@pytest.mark.parametrize("shape,tshape,n_t,seed", [
+    ((200, 300), (64, 64), 8, 0),       # mode A, full group
+    ((130, 170), (32, 32), 5, 1),       # mode A, partial group
+    ((300, 310), (48, 37), 1, 2),       # mode B
+    ((90, 140), (16, 16), 1, 3),        # mode B, small
+    ((260, 420), (100, 130), 2, 4),     # two templates -> mode B twice or A padded
+    ((70, 75), (64, 64), 3, 5),         # image barely larger than the template
+    ((400, 200), (17, 90), 11, 6),      # 8 + 3, non-square
+])
+def test_tensor_path_maps_vs_exact(mtm, ctxs, shape, tshape, n_t, seed):
+    from oracle import ncc_exact, synth
+    ct, cd = ctxs
+    rng = np.random.default_rng(seed)
+    temps = [synth.make_template(rng, *tshape) for _ in range(n_t)]
+    img, _ = synth.make_scene(shape[0], shape[1], temps[:3], 2, seed=seed)
+    labelled = [("t%d" % i, t) for i, t in enumerate(temps)]
+    # whole-list call exercises the grouped launch; single calls exercise mode B
+    with ct.lock:
+        ct.set_image(img)
+        ct.set_templates(temps)
+        got = [ct.score_map(i, 5, (shape[0] - tshape[0] + 1, shape[1] - tshape[1] + 1)) for i in range(n_t)]
+    for i, t in enumerate(temps):
+        exact = ncc_exact.match_template_exact(img, t, use_fft=False)
+        assert_map_close(got[i], exact)
+        direct = mtm.computeScoreMap(t, img, context=cd)
+        assert np.max(np.abs(got[i] - direct)) <= 2e-6
+    hits_t = mtm.matchTemplates(labelled, img, score_threshold=0.5, context=ct)
+    hits_d = mtm.matchTemplates(labelled, img, score_threshold=0.5, context=cd)
+    assert_hits_equal(hits_t, hits_d, tol=2e-6)
+
+
+def test_tensor_path_uniform_noise_and_bright(mtm, ctxs):
+    """Saturated inputs: 255*255*h*w up to 4.26e9 needs the full unsigned 32-bit accumulator range."""
+    from oracle import ncc_exact
+    ct, _ = ctxs
+    rng = np.random.default_rng(11)
+    img = rng.integers(250, 256, (300, 330), dtype=np.uint8)
+    tmpl = rng.integers(250, 256, (256, 256), dtype=np.uint8)
+    got = mtm.computeScoreMap(tmpl, img, context=ct)
+    exact = ncc_exact.match_template_exact(img, tmpl, use_fft=True)
+    assert_map_close(got, exact)
+    img2 = rng.integers(0, 256, (150, 190), dtype=np.uint8)
+    t2 = rng.integers(0, 256, (40, 40), dtype=np.uint8)
+    assert_map_close(mtm.computeScoreMap(t2, img2, context=ct), ncc_exact.match_template_exact(img2, t2, use_fft=False))
+
+
+def test_tensor_path_flat_and_constant(mtm, ctxs):
+    ct, _ = ctxs
+    img = np.full((60, 80), 7, np.uint8)
+    img[10:30, 10:30] = 200
+    assert np.all(mtm.computeScoreMap(np.full((8, 8), 31, np.uint8), img, context=ct) == 1.0)
+    t = np.arange(64, dtype=np.uint8).reshape(8, 8)
+    m = mtm.computeScoreMap(t, img, context=ct)
+    assert np.isfinite(m).all() and m[0, 60] == 0.0 and m[45, 0] == 0.0
+
+
+@pytest.mark.parametrize("cfg", ["C2", "C4"])
+def test_tensor_path_baseline_configs(mtm, ctxs, cfg):
+    from oracle import mtm_port, synth
+    ct, _ = ctxs
+    image, temps, params = synth.config(cfg)
+    got = mtm.matchTemplates(temps, image, context=ct, **params)
+    want = mtm_port.match_templates(temps, image, **params)
+    assert len(want) > 0
+    assert_hits_equal(got, want)
+
+
+def test_tensor_path_c3(mtm, ctxs):
+    from oracle import ncc_exact, synth
+    ct, _ = ctxs
+    image, temps, params = synth.config("C3")
+    got = mtm.computeScoreMap(temps[0][1], image, context=ct)
+    exact = ncc_exact.match_template_exact(image, temps[0][1], use_fft=True)
+    assert_map_close(got, exact)
