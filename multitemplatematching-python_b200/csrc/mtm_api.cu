@@ -390,7 +390,7 @@ static int compute_maps(mtm_ctx* ctx, int method, int tmpl)
 }
 
 // Downloads header + hits of a block into h_stage.  Returns the raw count in *n_raw.
-static int download_block(mtm_ctx* ctx, const uint8_t* d_block, int* n_raw, int* n_valid)
+static int download_block(mtm_ctx* ctx, const uint8_t* d_block, int* n_raw, int* n_valid, int* declined = nullptr)
 {
     const int PRE = 256;
     const int pre = std::min(PRE, ctx->hit_cap);
@@ -402,6 +402,7 @@ static int download_block(mtm_ctx* ctx, const uint8_t* d_block, int* n_raw, int*
     const int n = hdr[0];
     *n_valid = n;
     *n_raw = std::max(hdr[0], hdr[1]);
+    if (declined) { *declined = hdr[2]; if (hdr[2]) return MTM_OK; }
     if (n > pre && n <= ctx->hit_cap) {
         const size_t rest = (size_t)(n - pre) * sizeof(DevHit);
         MTM_CUDA(ctx, cudaMemcpyAsync(ctx->h_stage + first, d_block + first, rest, cudaMemcpyDeviceToHost, ctx->stream));
@@ -510,9 +511,18 @@ int mtm_find_matches(mtm_ctx* ctx, int method, int64_t n_object, double score_th
     const int minimize = method_is_min(method) ? 1 : 0;
     for (int attempt = 0; attempt < 8; ++attempt) {
         MTM_TRY(launch_peaks(ctx, method, n_object, (float)score_threshold, score_threshold));
-        if (n_object != 1) MTM_TRY(launch_sort_hits(ctx, 0, minimize, 0, 1));
-        int n_raw = 0, n = 0;
-        MTM_TRY(download_block(ctx, ctx->d_blockA, &n_raw, &n));
+        int n_raw = 0, n = 0, declined = 0;
+        if (n_object != 1) {
+            MTM_TRY(launch_finalize_small(ctx, minimize, 1, 0, 0, 0.f, 0, -1, 0.f));
+            MTM_TRY(download_block(ctx, ctx->d_blockA, &n_raw, &n, &declined));
+            if (declined) {                                  // more than 1024 raw hits: general path
+                if (n_raw > ctx->hit_cap) { MTM_TRY(reserve_hits(ctx, n_raw)); continue; }
+                MTM_TRY(launch_sort_hits(ctx, 0, minimize, 0, 1));
+                MTM_TRY(download_block(ctx, ctx->d_blockA, &n_raw, &n));
+            }
+        } else {
+            MTM_TRY(download_block(ctx, ctx->d_blockA, &n_raw, &n));
+        }
         if (n_raw > ctx->hit_cap) { MTM_TRY(reserve_hits(ctx, n_raw)); continue; }
         *n_hits = n;
         if (n > capacity) return mtm_fail(ctx, MTM_ERR_CAPACITY, "mtm_find_matches: %d hits, caller capacity %d", n, capacity);
@@ -535,13 +545,19 @@ int mtm_match_templates(mtm_ctx* ctx, int method, int64_t n_object, double score
     const float thr_nms = ascending ? (float)(1.0 - score_threshold) : (float)score_threshold;
     for (int attempt = 0; attempt < 8; ++attempt) {
         MTM_TRY(launch_peaks(ctx, method, n_object, (float)score_threshold, score_threshold));
-        if (n_object != 1) {
-            MTM_TRY(launch_sort_hits(ctx, 0, minimize, 0, 1));
-            MTM_TRY(launch_sort_hits(ctx, 1, minimize, ascending, 0));
+        int n_raw = 0, n = 0, declined = 0;
+        MTM_TRY(launch_finalize_small(ctx, minimize, n_object != 1, n_object == 1, 1, thr_nms, ascending, n_object,
+                                      (float)max_overlap));
+        MTM_TRY(download_block(ctx, ctx->d_blockB, &n_raw, &n, &declined));
+        if (declined) {                                      // more than 1024 raw hits: general path
+            if (n_raw > ctx->hit_cap) { MTM_TRY(reserve_hits(ctx, n_raw)); continue; }
+            if (n_object != 1) {
+                MTM_TRY(launch_sort_hits(ctx, 0, minimize, 0, 1));
+                MTM_TRY(launch_sort_hits(ctx, 1, minimize, ascending, 0));
+            }
+            MTM_TRY(launch_nms(ctx, thr_nms, ascending, n_object, (float)max_overlap));
+            MTM_TRY(download_block(ctx, ctx->d_blockB, &n_raw, &n));
         }
-        MTM_TRY(launch_nms(ctx, thr_nms, ascending, n_object, (float)max_overlap));
-        int n_raw = 0, n = 0;
-        MTM_TRY(download_block(ctx, ctx->d_blockB, &n_raw, &n));
         if (n_raw > ctx->hit_cap) { MTM_TRY(reserve_hits(ctx, n_raw)); continue; }
         *n_hits = n;
         if (n > capacity) return mtm_fail(ctx, MTM_ERR_CAPACITY, "mtm_match_templates: %d hits, caller capacity %d", n, capacity);
@@ -572,10 +588,14 @@ int mtm_nms(mtm_ctx* ctx, const mtm_hit* hits, int n, double score_threshold, in
     ctx->ctr.h2d_bytes += (int64_t)bytes;
     const int ascending = sort_ascending ? 1 : 0;
     const float thr_nms = ascending ? (float)(1.0 - score_threshold) : (float)score_threshold;
-    MTM_TRY(launch_sort_hits(ctx, 1, 0, ascending, 0));
-    MTM_TRY(launch_nms(ctx, thr_nms, ascending, n_object, (float)max_overlap));
-    int n_raw = 0, nk = 0;
-    MTM_TRY(download_block(ctx, ctx->d_blockB, &n_raw, &nk));
+    int n_raw = 0, nk = 0, declined = 0;
+    MTM_TRY(launch_finalize_small(ctx, 0, 0, 1, 1, thr_nms, ascending, n_object, (float)max_overlap));
+    MTM_TRY(download_block(ctx, ctx->d_blockB, &n_raw, &nk, &declined));
+    if (declined) {
+        MTM_TRY(launch_sort_hits(ctx, 1, 0, ascending, 0));
+        MTM_TRY(launch_nms(ctx, thr_nms, ascending, n_object, (float)max_overlap));
+        MTM_TRY(download_block(ctx, ctx->d_blockB, &n_raw, &nk));
+    }
     const DevHit* src = reinterpret_cast<const DevHit*>(ctx->h_stage + MTM_HIT_HEADER);
     for (int i = 0; i < nk; ++i) keep[i] = src[i].seq;
     *n_keep = nk;

@@ -44,7 +44,9 @@ struct TmplMeta {
 struct TcGroup {
     int mode;                  // 0: 8 templates x 16 x-offsets, 1: 1 template x 128 x-offsets
     int first, count;
+    int variant;               // 0: SS (Toeplitz slabs streamed from HBM/L2), 1: TS (A built into TMEM on the fly)
     int h, w, nk, a_kblk, slab_bytes, ds, N, R;
+    int row_stride, slots;     // TS variant
     size_t smem;
     int64_t arena_off;         // byte offset of the group's Toeplitz slabs in d_slabs
     int size_id;               // index into the per-size window-moment maps
@@ -153,6 +155,9 @@ int launch_ncc_tc(mtm_ctx* ctx, const TcGroup& g, const uint32_t* S, const float
 int launch_peaks(mtm_ctx* ctx, int method, int64_t n_object, float thr32, double thr64);
 // in-place sort of block A (mode 0: findMatches order, mode 1: NMSBoxes order)
 int launch_sort_hits(mtm_ctx* ctx, int mode, int minimize, int ascending_key, int check_trivial);
+// fast path (raw count <= 1024): sort(s) [+ NMS] in one launch; sets header[2] = 1 when it declines
+int launch_finalize_small(mtm_ctx* ctx, int minimize, int check_trivial, int presorted, int do_nms, float thr32,
+                          int ascending, int64_t n_object, float max_overlap);
 // block A (sorted mode 1) -> block B
 int launch_nms(mtm_ctx* ctx, float thr32, int ascending, int64_t n_object, float max_overlap);
 

@@ -24,6 +24,9 @@
 #include "mtm_internal.cuh"
 #include "ncc_epilogue.cuh"
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
 
 namespace {
 
@@ -98,6 +101,33 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+
+
+// Normalise 16 consecutive accumulator columns (output rows y_first .. y_first+15) of one lane.
+// Loads are issued for all 16 rows up front (addresses clamped, stores predicated) so that one
+// L2 round trip covers the whole batch.
+__device__ __forceinline__ void epilogue16(const uint32_t (&v)[16], int y_first, int mh, int mw, int x, long long area,
+                                           long long sumT, float ct, bool is_const, const uint32_t* __restrict__ S,
+                                           const float* __restrict__ rsD, float* __restrict__ out)
+{
+    float rs[16];
+    uint32_t sw[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int y = min(y_first + k, mh - 1);
+        const int64_t o = (int64_t)y * mw + x;
+        rs[k] = __ldg(rsD + o);
+        sw[k] = __ldg(S + o);
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int y = y_first + k;
+        const long long n1 = area * (long long)v[k] - (long long)sw[k] * sumT;
+        float r = (float)n1 * rs[k] * ct;
+        r = fminf(1.0f, fmaxf(-1.0f, r));
+        if (y < mh) out[(int64_t)y * mw + x] = is_const ? 1.0f : r;
+    }
 }
 
 struct TcParams {
@@ -222,23 +252,199 @@ ncc_tc_kernel(const TcParams p)
         for (int c0 = c_begin; c0 < c_end; c0 += 16) {
             uint32_t v[16];
             tmem_ld16(tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c0, v);
-            if (!live) continue;
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const int y = y0 + c0 + k;
-                if (y >= p.mh) break;
-                const int64_t o = (int64_t)y * p.mw + x;
-                const float rs = p.rsD[o];
-                const long long n1 = area * (long long)v[k] - (long long)p.S[o] * sumT;
-                float r = (float)n1 * rs * ct;
-                r = fminf(1.0f, fmaxf(-1.0f, r));
-                out[o] = is_const ? 1.0f : r;
-            }
+            if (!live || y0 + c0 >= p.mh) continue;
+            epilogue16(v, y0 + c0, p.mh, p.mw, x, area, sumT, ct, is_const, p.S, p.rsD, out);
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc(tmem_d, tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Variant "TS" (mode A): the Toeplitz operand never exists in memory.  Four producer warps
+// build each thread's A row (lane m = 16*t + r holds T_t[dy][u - r], u = 0 .. 32*nk) in
+// registers from the compact template rows staged in shared memory, and write it straight
+// into TMEM with tcgen05.st; the MMA takes A from TMEM ([a_tmem] operand) and B (image rows)
+// from shared memory.  Per dy the CTA reads 8*w template bytes instead of a 2*nk*2048-byte slab,
+// so neither L2 nor shared-memory bandwidth sits between the templates and the tensor pipe.
+// TMEM budget per CTA: 128 accumulator columns (N = 128 output rows) + 128 columns of A ring.
+struct TsParams {
+    const uint8_t* img; int64_t pitch; int H, W;
+    const uint8_t* tmpl;
+    int nk, N, R, h, w, wp, mh, mw;
+    int row_stride;                   // bytes between staged template rows in shared memory
+    int tmpl_stride;                  // bytes between staged templates (h*row_stride + 16: bank skew)
+    long long pix_off[8];             // byte offsets of the group's templates in the template arena
+    int slots;                        // A ring depth (TMEM slots of 8*nk columns)
+    const TmplMeta* meta; const int32_t* order; int count;
+    const uint32_t* S; const float* rsD;
+    float* maps;
+    long long* prof;                  // optional: per-CTA phase clocks
+};
+
+__device__ __forceinline__ void umma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int TS_MAX_SLOTS = 8;
+
+__global__ void __launch_bounds__(TC_THREADS, 2)
+ncc_tc_ts_kernel(const TsParams p)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int kb_img = 2 * p.nk;
+    const uint32_t tile_bytes = ((uint32_t)kb_img * p.R * 16 + 127) & ~127u;
+    const uint32_t rows_bytes = ((uint32_t)8 * p.tmpl_stride + 127) & ~127u;
+    uint8_t* tile = smem;
+    uint8_t* trows = smem + tile_bytes;                         // [t][dy][row_stride]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(trows + rows_bytes);
+    uint64_t* a_full = bars;                                    // [slots]  128 producer arrivals
+    uint64_t* a_empty = bars + TS_MAX_SLOTS;                    // [slots]  tcgen05.commit
+    uint64_t* accum = bars + 2 * TS_MAX_SLOTS;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TS_MAX_SLOTS + 1);
+
+    const int x0 = blockIdx.x * 16, y0 = blockIdx.y * p.N;
+    long long t_begin = 0, t_loaded = 0, t_main = 0;
+    if (p.prof && tid == 0) t_begin = clock64();
+
+    if (tid == 0) {
+        for (int s = 0; s < p.slots; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1); }
+        mbar_init(accum, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) tmem_alloc(tmem_slot, 256);
+
+    // ---- stage the image tile [k-block][row][16 B] and the compact template rows
+    {
+        const int pieces = kb_img * p.R;
+        for (int idx = tid; idx < pieces; idx += TC_THREADS) {
+            const int c = idx / p.R, r = idx - c * p.R;
+            const int gy = y0 + r;
+            const int64_t gb = (int64_t)x0 + 16 * c;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (gy < p.H && gb + 16 <= p.pitch) v = *reinterpret_cast<const uint4*>(p.img + (int64_t)gy * p.pitch + gb);
+            *reinterpret_cast<uint4*>(tile + (size_t)idx * 16) = v;
+        }
+        // compact template rows: [t][dy][row_stride]; packed rows are 16-byte aligned multiples of 4 bytes
+        const int wq = p.wp >> 2;
+        const int rows = 8 * p.h;
+        for (int rw = warp; rw < rows; rw += TC_THREADS / 32) {       // one warp per (t, dy) row
+            const int t = rw / p.h, dy = rw - t * p.h;
+            uint32_t* dst = reinterpret_cast<uint32_t*>(trows + (size_t)t * p.tmpl_stride + (size_t)dy * p.row_stride);
+            const uint32_t* src = (t < p.count)
+                ? reinterpret_cast<const uint32_t*>(p.tmpl + p.pix_off[t] + (int64_t)dy * p.wp) : nullptr;
+            for (int g = lane; g < wq; g += 32) dst[g] = src ? __ldg(src + g) : 0u;
+        }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_d = tmem_base;                           // columns [0, N)
+    const uint32_t tmem_a = tmem_base + 128;                     // columns [128, 256): A ring
+    const int slot_cols = 8 * p.nk;
+    if (p.prof && tid == 0) t_loaded = clock64();
+
+    if (warp < 4) {
+        // ===== A producers: thread m = 32*warp + lane owns TMEM lane m = (t, r) =====
+        const int m = 32 * warp + lane;
+        const int t = m >> 4, r = m & 15;
+        const int a = r >> 2, sh = 8 * (r & 3);
+        const int wq = p.wp >> 2;
+        const uint32_t* rows_t = reinterpret_cast<const uint32_t*>(trows + (size_t)t * p.tmpl_stride);
+        const uint32_t lane_addr = tmem_a + ((uint32_t)(32 * warp) << 16);
+        const int rsq = p.row_stride >> 2;
+        for (int dy = 0; dy < p.h; ++dy) {
+            const int s = dy % p.slots;
+            if (dy >= p.slots) {
+                if (lane == 0) mbar_wait(&a_empty[s], ((dy / p.slots) - 1) & 1);
+                __syncwarp();
+            }
+            tc_fence_after();
+            const uint32_t* row = rows_t + (size_t)dy * rsq;
+            int k = -a - 1;
+            uint32_t lo = (k >= 0 && k < wq) ? row[k] : 0u;
+            for (int i = 0; i < p.nk; ++i) {
+                uint32_t v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    ++k;
+                    const uint32_t hi = (k >= 0 && k < wq) ? row[k] : 0u;
+                    v[j] = __funnelshift_l(lo, hi, sh);
+                    lo = hi;
+                }
+                tmem_st8(lane_addr + (uint32_t)(s * slot_cols + 8 * i), v);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_full[s]);
+        }
+    } else if (warp == 4) {
+        if (lane == 0) {
+            const uint32_t idesc = (2u << 4) | ((uint32_t)(p.N >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t tile_addr = smem_u32(tile);
+            const uint32_t lbo_b = (uint32_t)p.R * 16;
+            for (int dy = 0; dy < p.h; ++dy) {
+                const int s = dy % p.slots;
+                mbar_wait(&a_full[s], (dy / p.slots) & 1);
+                tc_fence_after();
+                for (int i = 0; i < p.nk; ++i) {
+                    const uint64_t bd = umma_desc(tile_addr + dy * 16 + 2 * i * lbo_b, lbo_b, 128);
+                    umma_i8_ts(tmem_d, tmem_a + (uint32_t)(s * slot_cols + 8 * i), bd, idesc, (dy | i) != 0);
+                }
+                umma_commit(&a_empty[s]);
+            }
+            umma_commit(accum);
+        }
+        __syncwarp();
+    }
+
+    // ===== epilogue: all 8 warps =====
+    mbar_wait(accum, 0);
+    tc_fence_after();
+    if (p.prof && tid == 0) t_main = clock64();
+    {
+        const int m = 32 * (warp & 3) + lane;
+        const int tsel = m >> 4, x = x0 + (m & 15);
+        const bool live = (tsel < p.count) && (x < p.mw);
+        const TmplMeta* tm = live ? &p.meta[p.order[tsel]] : nullptr;
+        const long long area = (long long)p.h * p.w;
+        const long long sumT = live ? tm->isum : 0;
+        const float ct = live ? tm->inv_sqrt_d2 : 0.f;
+        const bool is_const = live ? (tm->is_const != 0) : false;
+        float* out = live ? p.maps + tm->map_off : nullptr;
+        const int half = p.N >> 1;
+        const int c_begin = (warp >> 2) * half, c_end = c_begin + half;
+        for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c0, v);
+            if (!live || y0 + c0 >= p.mh) continue;
+            epilogue16(v, y0 + c0, p.mh, p.mw, x, area, sumT, ct, is_const, p.S, p.rsD, out);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem_base, 256);
+    if (p.prof && tid == 0) {
+        long long* q = p.prof + 4 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x);
+        q[0] = t_loaded - t_begin; q[1] = t_main - t_loaded; q[2] = clock64() - t_main; q[3] = t_begin;
+    }
 }
 
 // Expands the templates of one group into Toeplitz slabs (see the header comment).
@@ -299,9 +505,23 @@ bool tc_path_supported(const mtm_ctx* ctx, int method, int h, int w)
 // Plans a group of `count` same-size templates.  Returns false when the tile does not fit shared memory.
 bool tc_plan_group(int mode, int h, int w, TcGroup& g)
 {
-    g.mode = mode; g.h = h; g.w = w;
+    g.mode = mode; g.h = h; g.w = w; g.variant = 0;
     const int nx = mode == 0 ? 16 : 128;
     g.nk = (w + nx - 1 + 31) / 32;
+    if (mode == 0 && g.nk <= 5 && !getenv("MTM_B200_NO_TS")) {
+        // TS variant: A generated into TMEM, N = 128 output rows, compact template rows resident in smem
+        const int wp = (w + 3) / 4 * 4;
+        g.row_stride = wp + 4;
+        g.N = 128; g.R = g.N + h - 1;
+        g.slots = std::min(TS_MAX_SLOTS, 128 / (8 * g.nk));
+        const size_t tile = ((size_t)2 * g.nk * g.R * 16 + 127) & ~(size_t)127;
+        const size_t rows = ((size_t)8 * ((size_t)h * g.row_stride + 16) + 127) & ~(size_t)127;
+        if (tile + rows + 256 <= 224 * 1024 && g.R * 16 < (1 << 18)) {
+            g.variant = 1; g.smem = tile + rows + 256; g.slab_bytes = 0; g.ds = 0; g.a_kblk = 0;
+            g.eff = (double)w / (32.0 * g.nk);
+            return true;
+        }
+    }
     g.a_kblk = mode == 0 ? 2048 : 256;
     g.slab_bytes = mode == 0 ? 2 * g.nk * 2048 : (7 + 2 * g.nk) * 256;
     g.ds = 1;
@@ -325,6 +545,7 @@ bool tc_plan_group(int mode, int h, int w, TcGroup& g)
 
 int launch_toeplitz_prep(mtm_ctx* ctx, const TcGroup& g)
 {
+    if (g.variant == 1) return MTM_OK;                      // the TS variant builds A on the fly
     const int64_t pieces = (int64_t)g.h * (g.slab_bytes / 16);
     const int blocks = (int)std::min<int64_t>((pieces + 255) / 256, 4096);
     toeplitz_prep_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_tmpl, ctx->d_meta, ctx->d_order + g.first, g.count, g.mode,
@@ -344,8 +565,42 @@ int launch_window_moments(mtm_ctx* ctx, int h, int w, int mh, int mw, uint32_t* 
     return MTM_OK;
 }
 
+static int launch_ncc_tc_ts(mtm_ctx* ctx, const TcGroup& g, const uint32_t* S, const float* rsD)
+{
+    const ImageDev& im = ctx->img;
+    TsParams p{};
+    p.img = im.pix; p.pitch = im.pitch; p.H = im.H; p.W = im.W;
+    p.tmpl = ctx->d_tmpl;
+    p.nk = g.nk; p.N = g.N; p.R = g.R; p.h = g.h; p.w = g.w; p.wp = (g.w + 3) / 4 * 4;
+    p.mh = im.H - g.h + 1; p.mw = im.W - g.w + 1;
+    p.row_stride = g.row_stride; p.slots = g.slots; p.tmpl_stride = g.h * g.row_stride + 16;
+    for (int t = 0; t < 8; ++t) p.pix_off[t] = t < g.count ? ctx->h_meta[ctx->h_order[g.first + t]].pix_off : 0;
+    p.meta = ctx->d_meta; p.order = ctx->d_order + g.first; p.count = g.count;
+    p.S = S; p.rsD = rsD; p.maps = ctx->d_maps;
+    MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    dim3 grid((p.mw + 15) / 16, (p.mh + g.N - 1) / g.N);
+    static const bool prof = getenv("MTM_B200_PROF") != nullptr;       // debug: per-CTA phase clocks to stderr
+    long long* d_prof = nullptr;
+    const size_t n_cta = (size_t)grid.x * grid.y;
+    if (prof) { MTM_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&d_prof), n_cta * 4 * sizeof(long long))); p.prof = d_prof; }
+    ncc_tc_ts_kernel<<<grid, TC_THREADS, g.smem, ctx->stream>>>(p);
+    MTM_LAUNCH_CHECK(ctx);
+    if (prof) {
+        std::vector<long long> hp(n_cta * 4);
+        MTM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        MTM_CUDA(ctx, cudaMemcpy(hp.data(), d_prof, hp.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        cudaFree(d_prof);
+        double a = 0, b = 0, c = 0; long long t0 = hp[3], t1 = 0;
+        for (size_t i = 0; i < n_cta; ++i) { a += hp[4*i]; b += hp[4*i+1]; c += hp[4*i+2]; t0 = std::min(t0, hp[4*i+3]); t1 = std::max(t1, hp[4*i+3] + hp[4*i] + hp[4*i+1] + hp[4*i+2]); }
+        fprintf(stderr, "[mtm prof] ts kernel: %zu CTAs, mean clocks load=%.0f main=%.0f epilogue=%.0f, span=%lld (smem %zu B, nk=%d, h=%d)\n",
+                n_cta, a / n_cta, b / n_cta, c / n_cta, t1 - t0, g.smem, g.nk, g.h);
+    }
+    return MTM_OK;
+}
+
 int launch_ncc_tc(mtm_ctx* ctx, const TcGroup& g, const uint32_t* S, const float* rsD)
 {
+    if (g.variant == 1) return launch_ncc_tc_ts(ctx, g, S, rsD);
     const ImageDev& im = ctx->img;
     TcParams p{};
     p.img = im.pix; p.pitch = im.pitch; p.H = im.H; p.W = im.W;

@@ -175,7 +175,136 @@ nms_kernel(const DevHit* __restrict__ hits, int cap, const int32_t* __restrict__
     if (tid == 0) out_count[0] = (s_kept < limit) ? s_kept : (int)limit;
 }
 
+// ---- fast path: the whole post-peak pipeline in ONE launch when the raw hit list is small ----
+// (the common case: tens of hits).  Shared-memory bitonic sorts + the greedy scan; falls through
+// (out_count[2] = 1) to the general multi-kernel path when there are more than FIN_CAP raw hits.
+constexpr int FIN_CAP = 1024;
+
+__device__ void smem_bitonic(DevHit* sh, int npad, const SortCtx& sc)
+{
+    const int tid = threadIdx.x, nth = blockDim.x;
+    for (int k = 2; k <= npad; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < npad; i += nth) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const DevHit a = sh[i], b = sh[l];
+                    const bool up = ((i & k) == 0);
+                    const bool swap = up ? hit_less(b, a, sc) : hit_less(a, b, sc);
+                    if (swap) { sh[i] = b; sh[l] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// do_nms == 0: findMatches order -> written back to `hits` (block A), count[0]/[1] updated.
+// do_nms == 1: ... then MTM.NMS -> `out` (block B), out_count[0] = kept, out_count[1] = raw count.
+__global__ void __launch_bounds__(1024, 1)
+finalize_small_kernel(DevHit* __restrict__ hits, int cap, int32_t* __restrict__ count, const TmplMeta* __restrict__ meta,
+                      const int32_t* __restrict__ nontrivial, int minimize, int check_trivial, int presorted, int do_nms,
+                      DevHit* __restrict__ out, int32_t* __restrict__ out_count, float thr32, int ascending,
+                      long long n_object, float max_overlap)
+{
+    __shared__ DevHit sh[FIN_CAP];
+    __shared__ int s_live, s_kept;
+    __shared__ unsigned long long s_best;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int n_raw = count[0];
+    int32_t* flag_hdr = do_nms ? out_count : count;
+    if (n_raw > FIN_CAP) { if (tid == 0) { flag_hdr[2] = 1; if (do_nms) out_count[1] = n_raw; } return; }
+    if (tid == 0) { s_live = 0; s_kept = 0; s_best = 0ull; flag_hdr[2] = 0; }
+    __syncthreads();
+    int npad = 1;
+    while (npad < n_raw) npad <<= 1;
+    int dead_local = 0;
+    for (int i = tid; i < npad; i += nth) {
+        DevHit h;
+        if (i < n_raw) {
+            h = load_hit(hits + i);
+            if (check_trivial && !nontrivial[h.tmpl]) { h.tmpl = 0x7fffffff; h.key = -CUDART_INF_F; h.seq = 0x7fffffff; dead_local++; }
+        } else {
+            h.tmpl = 0x7fffffff; h.x = h.y = h.w = h.h = 0; h.score = 0.f; h.seq = 0x7fffffff; h.key = -CUDART_INF_F;
+        }
+        sh[i] = h;
+    }
+    if (dead_local) atomicAdd(&s_live, dead_local);
+    __syncthreads();
+    const int n = n_raw - s_live;                               // live hits (s_live counted the dead ones)
+    __syncthreads();
+    if (!presorted) {
+        SortCtx sc0{meta, 0, minimize};
+        smem_bitonic(sh, npad, sc0);
+        for (int i = tid; i < n; i += nth) sh[i].seq = i;
+        __syncthreads();
+    }
+    if (!do_nms) {
+        for (int i = tid; i < n; i += nth) store_hit(hits + i, sh[i]);
+        if (tid == 0) { count[0] = n; count[1] = n; }
+        return;
+    }
+    if (tid == 0) out_count[1] = n_raw;
+    // ---- MTM.NMS (MTM/NMS.py:20-84) ----
+    if (n <= 1) {
+        if (tid == 0) { if (n == 1) out[0] = sh[0]; out_count[0] = n; }
+        return;
+    }
+    if (n_object == 1) {
+        unsigned long long kbest = 0ull;
+        for (int i = tid; i < n; i += nth) {
+            const float v = ascending ? -sh[i].score : sh[i].score;
+            const unsigned long long key = ((unsigned long long)ordered_f32(v) << 32) |
+                                           (unsigned long long)(0xFFFFFFFFu - (uint32_t)sh[i].seq);
+            kbest = key > kbest ? key : kbest;
+        }
+        atomicMax(&s_best, kbest);
+        __syncthreads();
+        for (int i = tid; i < n; i += nth) {
+            const float v = ascending ? -sh[i].score : sh[i].score;
+            const unsigned long long key = ((unsigned long long)ordered_f32(v) << 32) |
+                                           (unsigned long long)(0xFFFFFFFFu - (uint32_t)sh[i].seq);
+            if (key == s_best) { out[0] = sh[i]; out_count[0] = 1; }
+        }
+        return;
+    }
+    for (int i = tid; i < npad; i += nth)
+        if (i < n) sh[i].key = ascending ? 1.0f - sh[i].score : sh[i].score;
+    __syncthreads();
+    SortCtx sc1{meta, 1, minimize};
+    smem_bitonic(sh, npad, sc1);
+    // greedy scan; kept hits are compacted to the front of `out` (global) and mirrored in smem order list
+    __shared__ unsigned short kept_idx[FIN_CAP];
+    const long long limit = n_object < 0 ? (long long)n : n_object;
+    for (int i = 0; i < n; ++i) {
+        const DevHit cand = sh[i];
+        if (!(cand.key > thr32)) break;
+        const int kept = s_kept;
+        if (kept >= limit) break;
+        int sup = 0;
+        for (int k = tid; k < kept; k += nth)
+            if (!(rect_overlap(cand, sh[kept_idx[k]]) <= max_overlap)) sup = 1;
+        sup = __syncthreads_or(sup);
+        if (!sup && tid == 0) { kept_idx[kept] = (unsigned short)i; s_kept = kept + 1; }
+        __syncthreads();
+    }
+    const int kept = (s_kept < limit) ? s_kept : (int)limit;
+    for (int k = tid; k < kept; k += nth) store_hit(out + k, sh[kept_idx[k]]);
+    if (tid == 0) out_count[0] = kept;
+}
+
 }  // namespace
+
+int launch_finalize_small(mtm_ctx* ctx, int minimize, int check_trivial, int presorted, int do_nms, float thr32,
+                          int ascending, int64_t n_object, float max_overlap)
+{
+    finalize_small_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->hitsA(), ctx->hit_cap, ctx->countA(), ctx->d_meta,
+                                                       ctx->d_nontrivial, minimize, check_trivial, presorted, do_nms,
+                                                       ctx->hitsB(), ctx->countB(), thr32, ascending, (long long)n_object,
+                                                       max_overlap);
+    MTM_LAUNCH_CHECK(ctx);
+    return MTM_OK;
+}
 
 int launch_sort_hits(mtm_ctx* ctx, int mode, int minimize, int ascending_key, int check_trivial)
 {

@@ -17,6 +17,9 @@
 
 namespace {
 
+// Streaming pass: one aligned float4 per thread.  The "every pixel is a 3x3 maximum" rule of
+// peak_local_max only fires for a constant map, i.e. iff no pixel differs from pixel 0; the 3x3
+// test (8 extra loads, L1/L2 hits) is only run for the pixels above the threshold.
 __global__ void peaks2d_kernel(const TmplMeta* __restrict__ meta, const float* __restrict__ maps,
                                float thr32, int minimize, DevHit* __restrict__ hits, int cap,
                                int32_t* __restrict__ count, int32_t* __restrict__ nontrivial)
@@ -25,38 +28,52 @@ __global__ void peaks2d_kernel(const TmplMeta* __restrict__ meta, const float* _
     const int mh = tm.mh, mw = tm.mw;
     if (mh == 1 || mw == 1) return;                          // handled by peaks1d_kernel
     const int64_t n = (int64_t)mh * mw;
-    const float* m = maps + tm.map_off;
+    const float* m = maps + tm.map_off;                      // 128-byte aligned (map offsets are multiples of 32)
     const float sgn = minimize ? -1.0f : 1.0f;
-    int any_nonmax = 0;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
-         idx += (int64_t)gridDim.x * blockDim.x) {
-        const int y = (int)(idx / mw), x = (int)(idx - (int64_t)y * mw);
-        const float raw = m[idx];
-        const float v = sgn * raw;
-        bool is_max = true;
+    const float m0 = m[0];
+    int differs = 0;
+    for (int64_t base = 4 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x); base < n;
+         base += 4 * (int64_t)gridDim.x * blockDim.x) {
+        float v4[4];
+        if (base + 4 <= n) {
+            const float4 q = *reinterpret_cast<const float4*>(m + base);
+            v4[0] = q.x; v4[1] = q.y; v4[2] = q.z; v4[3] = q.w;
+        } else {
 #pragma unroll
-        for (int dy = -1; dy <= 1; ++dy) {
-            const int yy = y + dy;
-            if (yy < 0 || yy >= mh) continue;
-#pragma unroll
-            for (int dx = -1; dx <= 1; ++dx) {
-                const int xx = x + dx;
-                if (xx < 0 || xx >= mw || (dx == 0 && dy == 0)) continue;
-                if (sgn * m[(int64_t)yy * mw + xx] > v) is_max = false;
-            }
+            for (int k = 0; k < 4; ++k) v4[k] = (base + k < n) ? m[base + k] : m0;
         }
-        if (!is_max) any_nonmax = 1;
-        if (is_max && v > thr32) {
-            const int slot = atomicAdd(count, 1);
-            if (slot < cap) {
-                DevHit h;
-                h.tmpl = blockIdx.y; h.x = x; h.y = y; h.w = tm.w; h.h = tm.h;
-                h.score = raw; h.seq = 0; h.key = 0.f;
-                hits[slot] = h;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float raw = v4[k];
+            if (raw != m0) differs = 1;
+            const float v = sgn * raw;
+            if (!(v > thr32) || base + k >= n) continue;
+            const int64_t idx = base + k;
+            const int y = (int)(idx / mw), x = (int)(idx - (int64_t)y * mw);
+            bool is_max = true;
+#pragma unroll
+            for (int dy = -1; dy <= 1; ++dy) {
+                const int yy = y + dy;
+                if (yy < 0 || yy >= mh) continue;
+#pragma unroll
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const int xx = x + dx;
+                    if (xx < 0 || xx >= mw || (dx == 0 && dy == 0)) continue;
+                    if (sgn * m[(int64_t)yy * mw + xx] > v) is_max = false;
+                }
+            }
+            if (is_max) {
+                const int slot = atomicAdd(count, 1);
+                if (slot < cap) {
+                    DevHit h;
+                    h.tmpl = blockIdx.y; h.x = x; h.y = y; h.w = tm.w; h.h = tm.h;
+                    h.score = raw; h.seq = 0; h.key = 0.f;
+                    hits[slot] = h;
+                }
             }
         }
     }
-    if (__syncthreads_or(any_nonmax) && threadIdx.x == 0) atomicOr(&nontrivial[blockIdx.y], 1);
+    if (__syncthreads_or(differs) && threadIdx.x == 0 && !nontrivial[blockIdx.y]) atomicOr(&nontrivial[blockIdx.y], 1);
 }
 
 // One thread per degenerate template (these maps have at most max(H, W) entries).
@@ -152,8 +169,8 @@ int launch_peaks(mtm_ctx* ctx, int method, int64_t n_object, float thr32, double
         max_px = n > max_px ? n : max_px;
     }
     MTM_CUDA(ctx, cudaMemsetAsync(ctx->countA(), 0, MTM_HIT_HEADER, ctx->stream));
-    int bx = (int)((max_px + 255) / 256);
-    const int bx_cap = ctx->sm_count * 16;
+    int bx = (int)((max_px + 1023) / 1024);
+    const int bx_cap = ctx->sm_count * 8;
     if (bx > bx_cap) bx = bx_cap;
     if (bx < 1) bx = 1;
     if (n_object == 1) {

@@ -11,65 +11,84 @@
 
 namespace {
 
-// One warp per image row: inclusive prefix along x of every channel and of the
-// squared norm.  Output (scratch): C planes of u32 [H][W] then one u32 plane [H][W]
-// (row prefixes of squares stay < 2^32 for W*C < 66051).
+// One block (256 threads) per image row: inclusive prefix along x of every channel and of the
+// squared norm.  Each thread owns a contiguous run of pixels; runs are combined with a block
+// scan.  Output (scratch): C planes of u32 [H][W] then one u32 plane [H][W] (row prefixes of
+// squares stay < 2^32 for W*C < 66051).
 template <int C>
-__global__ void sat_rows_kernel(const uint8_t* __restrict__ img, int64_t pitch, int H, int W,
-                                uint32_t* __restrict__ scratch)
+__global__ void __launch_bounds__(256)
+sat_rows_kernel(const uint8_t* __restrict__ img, int64_t pitch, int H, int W, uint32_t* __restrict__ scratch)
 {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (warp >= H) return;
-    const uint8_t* row = img + (int64_t)warp * pitch;
+    __shared__ uint32_t wsum[C + 1][8];
+    const int y = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint8_t* row = img + (int64_t)y * pitch;
     const int64_t plane = (int64_t)H * W;
-    uint32_t carry[C + 1];
+    const int per = (W + 255) / 256;
+    const int xa = min(W, tid * per), xb = min(W, xa + per);
+    uint32_t tot[C + 1];
 #pragma unroll
-    for (int c = 0; c <= C; ++c) carry[c] = 0;
-    for (int x0 = 0; x0 < W; x0 += 32) {
-        const int x = x0 + lane;
-        uint32_t v[C + 1];
-        v[C] = 0;
+    for (int c = 0; c <= C; ++c) tot[c] = 0;
+    for (int x = xa; x < xb; ++x) {
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-            uint32_t p = (x < W) ? row[(int64_t)x * C + c] : 0u;
-            v[c] = p;
-            v[C] += p * p;
+            const uint32_t p = row[(int64_t)x * C + c];
+            tot[c] += p;
+            tot[C] += p * p;
         }
+    }
+    uint32_t excl[C + 1];
 #pragma unroll
-        for (int c = 0; c <= C; ++c) {
-            uint32_t s = v[c];
+    for (int c = 0; c <= C; ++c) {
+        uint32_t s = tot[c];
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                uint32_t n = __shfl_up_sync(0xffffffffu, s, d);
-                if (lane >= d) s += n;
-            }
-            s += carry[c];
-            if (x < W) scratch[c * plane + (int64_t)warp * W + x] = s;
-            carry[c] = __shfl_sync(0xffffffffu, s, 31);
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, s, d);
+            if (lane >= d) s += n;
         }
+        if (lane == 31) wsum[c][wid] = s;
+        excl[c] = s - tot[c];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c <= C; ++c) {
+        uint32_t base = 0;
+        for (int k = 0; k < wid; ++k) base += wsum[c][k];
+        excl[c] += base;
+    }
+    for (int x = xa; x < xb; ++x) {
+        uint32_t sq = 0;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const uint32_t p = row[(int64_t)x * C + c];
+            excl[c] += p;
+            sq += p * p;
+            scratch[c * plane + (int64_t)y * W + x] = excl[c];
+        }
+        excl[C] += sq;
+        scratch[C * plane + (int64_t)y * W + x] = excl[C];
     }
 }
 
-// Column pass.  Block = 32 SAT columns x 32 row chunks; two sweeps over the chunk
-// (chunk total -> exclusive scan over chunks -> running prefix).  blockIdx.y picks
-// the table: 0..C-1 -> sat_s[c] (u32), C -> sat_q (u64).
-__global__ void sat_cols_kernel(const uint32_t* __restrict__ scratch, int H, int W, int C,
-                                uint32_t* __restrict__ sat_s, unsigned long long* __restrict__ sat_q,
-                                int64_t sat_pitch)
+// Column pass.  Block = 32 SAT columns x 32 row chunks: chunk total -> exclusive scan over the
+// chunks -> running prefix (second sweep re-reads the chunk from L1/L2; loads are batched 8 deep).
+// blockIdx.y picks the table: 0..C-1 -> sat_s[c] (u32), C -> sat_q (u64).
+__global__ void __launch_bounds__(1024, 1)
+sat_cols_kernel(const uint32_t* __restrict__ scratch, int H, int W, int C,
+                uint32_t* __restrict__ sat_s, unsigned long long* __restrict__ sat_q, int64_t sat_pitch)
 {
     __shared__ unsigned long long part[32][33];
     const int cx = threadIdx.x, ry = threadIdx.y;
     const int sx = blockIdx.x * 32 + cx;          // SAT column, 0..W
     const int table = blockIdx.y;
     const int64_t plane = (int64_t)H * W;
-    const uint32_t* src = scratch + table * plane;
     const int rc = (H + 31) / 32;
     const int y0 = ry * rc, y1 = min(H, y0 + rc);
     const bool live = (sx >= 1 && sx <= W);
+    const uint32_t* src = scratch + table * plane + (live ? sx - 1 : 0);
     unsigned long long tot = 0;
     if (live) {
-        for (int y = y0; y < y1; ++y) tot += src[(int64_t)y * W + (sx - 1)];
+#pragma unroll 8
+        for (int y = y0; y < y1; ++y) tot += __ldg(src + (int64_t)y * W);
     }
     part[ry][cx] = tot;
     __syncthreads();
@@ -82,8 +101,9 @@ __global__ void sat_cols_kernel(const uint32_t* __restrict__ scratch, int H, int
     if (ry == 0) {                                 // SAT row 0 is all zeros
         if (is_q) sat_q[sx] = 0ull; else ds[sx] = 0u;
     }
+#pragma unroll 8
     for (int y = y0; y < y1; ++y) {
-        if (live) run += src[(int64_t)y * W + (sx - 1)];
+        if (live) run += __ldg(src + (int64_t)y * W);
         const int64_t o = (int64_t)(y + 1) * sat_pitch + sx;
         if (is_q) sat_q[o] = run; else ds[o] = (uint32_t)run;
     }
@@ -147,8 +167,7 @@ int launch_build_sat(mtm_ctx* ctx)
 {
     ImageDev& im = ctx->img;
     const int H = im.H, W = im.W, C = im.C;
-    const int warps_per_block = 4;
-    dim3 g1((H + warps_per_block - 1) / warps_per_block), b1(32 * warps_per_block);
+    dim3 g1(H), b1(256);
     switch (C) {
         case 1: sat_rows_kernel<1><<<g1, b1, 0, ctx->stream>>>(im.pix, im.pitch, H, W, ctx->scratch); break;
         case 2: sat_rows_kernel<2><<<g1, b1, 0, ctx->stream>>>(im.pix, im.pitch, H, W, ctx->scratch); break;
