@@ -137,7 +137,7 @@ int mtm_destroy(mtm_ctx* ctx)
     cudaFree(ctx->d_meta); cudaFree(ctx->d_tmpl); cudaFree(ctx->d_maps); cudaFree(ctx->d_order);
     cudaFree(ctx->d_blockA); cudaFree(ctx->d_blockB); cudaFree(ctx->d_keep);
     cudaFree(ctx->d_nontrivial); cudaFree(ctx->d_best);
-    cudaFree(ctx->d_slabs); cudaFree(ctx->d_wS); cudaFree(ctx->d_wR);
+    cudaFree(ctx->d_slabs); cudaFree(ctx->d_wS); cudaFree(ctx->d_wR); cudaFree(ctx->d_sizes);
     cudaFreeHost(ctx->h_tmpl_stage); cudaFreeHost(ctx->h_stage); cudaFreeHost(ctx->h_geom);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -228,7 +228,7 @@ static int set_image_impl(mtm_ctx* ctx, const void* pixels, int H, int W, int C,
     if (!on_device) ctx->ctr.h2d_bytes += (int64_t)H * W * C;
     MTM_TRY(mtm_reserve(ctx, im.sat_s, ctx->sat_s_cap, (size_t)C * (H + 1) * im.sat_pitch));
     MTM_TRY(mtm_reserve(ctx, im.sat_q, ctx->sat_q_cap, (size_t)(H + 1) * im.sat_pitch));
-    MTM_TRY(mtm_reserve(ctx, ctx->scratch, ctx->scratch_cap, (size_t)(C + 1) * H * W));
+    MTM_TRY(mtm_reserve(ctx, ctx->scratch, ctx->scratch_cap, (size_t)(C + 1) * H * ((W + 3) / 4 * 4)));
     ctx->img_dtype = dtype;
     ctx->geometry_valid = false;
     ctx->moments_valid = false;
@@ -254,9 +254,25 @@ static int ensure_geometry(mtm_ctx* ctx)
         m.mw = ctx->img.W - m.w + 1;
         m.map_off = off;
         off += ((int64_t)m.mh * m.mw + 31) / 32 * 32;
-        ctx->h_geom[t].map_off = m.map_off; ctx->h_geom[t].mh = m.mh; ctx->h_geom[t].mw = m.mw;
     }
     ctx->maps_total = off;
+    ctx->moments_valid = false;
+    // window-moment maps: one pair per distinct size, in (h, w)-sorted order
+    ctx->h_sizes.clear();
+    int64_t moff = 0;
+    for (int k = 0; k < n; ++k) {
+        TmplMeta& m = ctx->h_meta[ctx->h_order[k]];
+        if (ctx->h_sizes.empty() || ctx->h_sizes.back().h != m.h || ctx->h_sizes.back().w != m.w) {
+            ctx->h_sizes.push_back(SizeDesc{m.h, m.w, m.mh, m.mw, moff});
+            moff += ((int64_t)m.mh * m.mw + 31) / 32 * 32;
+        }
+        m.mom_off = ctx->h_sizes.back().off;
+    }
+    ctx->moments_total = moff;
+    for (int t = 0; t < n; ++t) {
+        const TmplMeta& m = ctx->h_meta[t];
+        ctx->h_geom[t].map_off = m.map_off; ctx->h_geom[t].mh = m.mh; ctx->h_geom[t].mw = m.mw; ctx->h_geom[t].mom_off = m.mom_off;
+    }
     MTM_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_meta, sizeof(TmplMeta), ctx->h_geom, sizeof(TmplGeom), sizeof(TmplGeom),
                                     (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     MTM_TRY(mtm_reserve(ctx, ctx->d_maps, ctx->maps_cap, (size_t)off));
@@ -274,37 +290,61 @@ static int plan_tensor_path(mtm_ctx* ctx)
     ctx->moments_valid = false;
     if (ctx->tmpl_C != 1 || ctx->tmpl_dtype != MTM_U8) return MTM_OK;
     const int n = ctx->n_tmpl;
+    // Cost model (tensor-pipe clocks per output pixel, up to a constant): a mode-A launch serves up to
+    // 8 templates for h*nk/16, a mode-B launch one template for h*nk/128.  Templates are visited in
+    // (h, w) order; a template joins the open mode-A group (zero padded to the group's size) while
+    // that is cheaper than handling it alone.
+    auto cost = [](const TcGroup& g) { return (double)g.h * g.nk / (g.mode == 0 ? 16.0 : 128.0); };
+    auto alone = [&](int h, int w, TcGroup& best) {
+        TcGroup a{}, b{};
+        const bool okA = tc_plan_group(0, h, w, a), okB = tc_plan_group(1, h, w, b);
+        if (!okA && !okB) return false;
+        best = (okA && (!okB || cost(a) <= cost(b))) ? a : b;
+        return true;
+    };
     int64_t arena = 0;
-    int size_id = 0;
+    auto emit = [&](TcGroup g, int first, int count, int h_min, int w_min) {
+        g.first = first; g.count = count; g.h_min = h_min; g.w_min = w_min;
+        g.arena_off = arena;
+        arena += ((int64_t)g.h * g.slab_bytes + 127) / 128 * 128;
+        ctx->tc_groups.push_back(g);
+    };
     int i = 0;
     while (i < n) {
-        const TmplMeta& a = ctx->h_meta[ctx->h_order[i]];
-        int j = i + 1;
-        while (j < n && ctx->h_meta[ctx->h_order[j]].h == a.h && ctx->h_meta[ctx->h_order[j]].w == a.w) ++j;
-        TcGroup ga{}, gb{};
-        const bool okA = tc_plan_group(0, a.h, a.w, ga), okB = tc_plan_group(1, a.h, a.w, gb);
-        if (!okA && !okB) return MTM_OK;
-        int k = i;
-        while (k < j) {
-            const int left = j - k;
-            // mode A wastes (8 - count)/8 of the M rows, mode B pays the wider Toeplitz band
-            const double effA = okA ? ga.eff * std::min(left, 8) / 8.0 : -1.0;
-            const double effB = okB ? gb.eff : -1.0;
-            TcGroup g = (effA >= effB) ? ga : gb;
-            g.first = k;
-            g.count = (g.mode == 0) ? std::min(left, 8) : 1;
-            g.size_id = size_id;
-            g.arena_off = arena;
-            arena += ((int64_t)g.h * g.slab_bytes + 127) / 128 * 128;
-            ctx->tc_groups.push_back(g);
-            k += g.count;
+        const TmplMeta& m0 = ctx->h_meta[ctx->h_order[i]];
+        TcGroup solo{};
+        if (!alone(m0.h, m0.w, solo)) return MTM_OK;
+        TcGroup open{};
+        bool have_open = tc_plan_group(0, m0.h, m0.w, open);
+        double solo_sum = cost(solo);
+        int j = i + 1, hg = m0.h, wg = m0.w, h_min = m0.h, w_min = m0.w;
+        while (have_open && j < n && j - i < 8) {
+            const TmplMeta& mj = ctx->h_meta[ctx->h_order[j]];
+            TcGroup sj{}, grown{};
+            if (!alone(mj.h, mj.w, sj)) return MTM_OK;
+            const int hg2 = std::max(hg, mj.h), wg2 = std::max(wg, mj.w);
+            if (!tc_plan_group(0, hg2, wg2, grown)) break;
+            if (grown.variant == 1 && (mj.h != m0.h || mj.w != m0.w)) break;   // TS variant: same-size groups only
+            if (cost(grown) > cost(open) + cost(sj)) break;          // cheaper to start a new group
+            open = grown; hg = hg2; wg = wg2;
+            h_min = std::min(h_min, mj.h); w_min = std::min(w_min, mj.w);
+            solo_sum += cost(sj);
+            ++j;
         }
-        ++size_id;
+        if (have_open && cost(open) <= solo_sum) {
+            emit(open, i, j - i, h_min, w_min);
+        } else {                                                     // members are cheaper one by one
+            for (int k = i; k < j; ++k) {
+                const TmplMeta& mk = ctx->h_meta[ctx->h_order[k]];
+                TcGroup sk{};
+                if (!alone(mk.h, mk.w, sk)) return MTM_OK;
+                emit(sk, k, 1, mk.h, mk.w);
+            }
+        }
         i = j;
     }
     MTM_TRY(mtm_reserve(ctx, ctx->d_slabs, ctx->slabs_cap, (size_t)arena + 128));
     for (const TcGroup& g : ctx->tc_groups) MTM_TRY(launch_toeplitz_prep(ctx, g));
-    ctx->size_map_off.assign(size_id, 0);
     ctx->tc_ready = true;
     return MTM_OK;
 }
@@ -313,23 +353,12 @@ static int plan_tensor_path(mtm_ctx* ctx)
 static int ensure_moments(mtm_ctx* ctx)
 {
     if (ctx->moments_valid) return MTM_OK;
-    int64_t off = 0;
-    int last = -1;
-    for (const TcGroup& g : ctx->tc_groups) {
-        if (g.size_id == last) continue;
-        last = g.size_id;
-        ctx->size_map_off[g.size_id] = off;
-        off += ((int64_t)(ctx->img.H - g.h + 1) * (ctx->img.W - g.w + 1) + 31) / 32 * 32;
-    }
-    MTM_TRY(mtm_reserve(ctx, ctx->d_wS, ctx->wS_cap, (size_t)off));
-    MTM_TRY(mtm_reserve(ctx, ctx->d_wR, ctx->wR_cap, (size_t)off));
-    last = -1;
-    for (const TcGroup& g : ctx->tc_groups) {
-        if (g.size_id == last) continue;
-        last = g.size_id;
-        const int64_t o = ctx->size_map_off[g.size_id];
-        MTM_TRY(launch_window_moments(ctx, g.h, g.w, ctx->img.H - g.h + 1, ctx->img.W - g.w + 1, ctx->d_wS + o, ctx->d_wR + o));
-    }
+    MTM_TRY(mtm_reserve(ctx, ctx->d_wS, ctx->wS_cap, (size_t)ctx->moments_total));
+    MTM_TRY(mtm_reserve(ctx, ctx->d_wR, ctx->wR_cap, (size_t)ctx->moments_total));
+    MTM_TRY(mtm_reserve(ctx, ctx->d_sizes, ctx->sizes_cap, ctx->h_sizes.size()));
+    MTM_CUDA(ctx, cudaMemcpyAsync(ctx->d_sizes, ctx->h_sizes.data(), ctx->h_sizes.size() * sizeof(SizeDesc),
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    MTM_TRY(launch_window_moments(ctx));
     ctx->moments_valid = true;
     return MTM_OK;
 }
@@ -364,8 +393,7 @@ static int compute_maps(mtm_ctx* ctx, int method, int tmpl)
                 for (int k = 0; k < g.count; ++k) has = has || ctx->h_order[g.first + k] == tmpl;
                 if (!has) continue;
             }
-            const int64_t o = ctx->size_map_off[g.size_id];
-            MTM_TRY(launch_ncc_tc(ctx, g, ctx->d_wS + o, ctx->d_wR + o));
+            MTM_TRY(launch_ncc_tc(ctx, g));
         }
         i = n;
     }

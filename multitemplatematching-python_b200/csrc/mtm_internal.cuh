@@ -22,10 +22,12 @@ struct DevHit {
 struct TmplGeom {         // image-dependent part, re-uploaded when the image size changes
     int64_t map_off;      // element offset of the template's score map in the map arena
     int32_t mh, mw;       // score map size
+    int64_t mom_off;      // element offset of its window-moment maps (shared by templates of one size)
 };
 struct TmplMeta {
-    int64_t map_off;      // -- TmplGeom prefix (16 bytes) --
+    int64_t map_off;      // -- TmplGeom prefix (24 bytes) --
     int32_t mh, mw;
+    int64_t mom_off;
     int64_t pix_off;      // byte offset of the packed template in the template arena
     int32_t h, w;         // template size (pixels)
     int32_t wp;           // packed row pitch in bytes (w*C rounded up to 4, zero padded)
@@ -40,7 +42,14 @@ struct TmplMeta {
     float pad_f;
 };
 
-// One launch of the tcgen05 kernel: `count` same-size templates d_order[first .. first+count).
+// One distinct template size: where its window-moment maps live (window_moments_kernel, batched).
+struct SizeDesc {
+    int32_t h, w, mh, mw;
+    int64_t off;
+};
+
+// One launch of the tcgen05 kernel: `count` templates d_order[first .. first+count); (h, w) is the
+// group's padded size (mode A may mix sizes: smaller templates are zero padded in the Toeplitz slabs).
 struct TcGroup {
     int mode;                  // 0: 8 templates x 16 x-offsets, 1: 1 template x 128 x-offsets
     int first, count;
@@ -49,7 +58,7 @@ struct TcGroup {
     int row_stride, slots;     // TS variant
     size_t smem;
     int64_t arena_off;         // byte offset of the group's Toeplitz slabs in d_slabs
-    int size_id;               // index into the per-size window-moment maps
+    int h_min, w_min;          // smallest member (largest score map): the tile grid covers its map
     double eff;
 };
 
@@ -91,14 +100,15 @@ struct mtm_ctx {
 
     // score maps
     float* d_maps = nullptr; size_t maps_cap = 0;   // elements
-    int64_t maps_total = 0;
+    int64_t maps_total = 0, moments_total = 0;
     int maps_method = -1;                // method the resident maps were computed with (-1: stale)
 
     // tensor-core path (ncc_tc.cu)
     std::vector<TcGroup> tc_groups;                      // covers every template when tc_ready
     bool tc_ready = false;
     uint8_t* d_slabs = nullptr; size_t slabs_cap = 0;    // Toeplitz-expanded template rows
-    std::vector<int64_t> size_map_off;                   // per distinct (h, w): element offset of its moment maps
+    std::vector<SizeDesc> h_sizes;                       // distinct (h, w) of the current templates
+    SizeDesc* d_sizes = nullptr; size_t sizes_cap = 0;
     uint32_t* d_wS = nullptr; size_t wS_cap = 0;         // window sums S
     float* d_wR = nullptr; size_t wR_cap = 0;            // rsqrt(A*Q - S^2)
     bool moments_valid = false;
@@ -149,8 +159,8 @@ int launch_ncc_direct(mtm_ctx* ctx, int method, int first, int count);
 bool tc_path_supported(const mtm_ctx* ctx, int method, int h, int w);
 bool tc_plan_group(int mode, int h, int w, TcGroup& g);
 int launch_toeplitz_prep(mtm_ctx* ctx, const TcGroup& g);
-int launch_window_moments(mtm_ctx* ctx, int h, int w, int mh, int mw, uint32_t* S, float* rsD);
-int launch_ncc_tc(mtm_ctx* ctx, const TcGroup& g, const uint32_t* S, const float* rsD);
+int launch_window_moments(mtm_ctx* ctx);
+int launch_ncc_tc(mtm_ctx* ctx, const TcGroup& g);
 // raw (unsorted) peaks of every template -> block A
 int launch_peaks(mtm_ctx* ctx, int method, int64_t n_object, float thr32, double thr64);
 // in-place sort of block A (mode 0: findMatches order, mode 1: NMSBoxes order)

@@ -240,20 +240,24 @@ ncc_tc_kernel(const TcParams p)
         int x, tsel;
         if (p.mode == 0) { tsel = m >> 4; x = x0 + (m & 15); }
         else { tsel = 0; x = x0 + 16 * (7 - (m >> 4)) + (m & 15); }
-        const bool live = (tsel < p.count) && (x < p.mw);
-        const TmplMeta* tm = live ? &p.meta[p.order[tsel]] : nullptr;
-        const long long area = (long long)p.h * p.w;
-        const long long sumT = live ? tm->isum : 0;
-        const float ct = live ? tm->inv_sqrt_d2 : 0.f;
-        const bool is_const = live ? (tm->is_const != 0) : false;
-        float* out = live ? p.maps + tm->map_off : nullptr;
+        // per-lane template geometry: a mode-A group may mix template sizes
+        const TmplMeta* tm = (tsel < p.count) ? &p.meta[p.order[tsel]] : nullptr;
+        const int t_mh = tm ? tm->mh : 0, t_mw = tm ? tm->mw : 0;
+        const bool live = tm && (x < t_mw);
+        const long long area = tm ? (long long)tm->h * tm->w : 0;
+        const long long sumT = tm ? tm->isum : 0;
+        const float ct = tm ? tm->inv_sqrt_d2 : 0.f;
+        const bool is_const = tm ? (tm->is_const != 0) : false;
+        float* out = tm ? p.maps + tm->map_off : nullptr;
+        const uint32_t* Sm = tm ? p.S + tm->mom_off : nullptr;
+        const float* Rm = tm ? p.rsD + tm->mom_off : nullptr;
         const int half = p.N >> 1;                             // N >= 32: each warp pair splits the columns
         const int c_begin = (warp >> 2) * half, c_end = c_begin + half;
         for (int c0 = c_begin; c0 < c_end; c0 += 16) {
             uint32_t v[16];
             tmem_ld16(tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c0, v);
-            if (!live || y0 + c0 >= p.mh) continue;
-            epilogue16(v, y0 + c0, p.mh, p.mw, x, area, sumT, ct, is_const, p.S, p.rsD, out);
+            if (!live || y0 + c0 >= t_mh) continue;
+            epilogue16(v, y0 + c0, t_mh, t_mw, x, area, sumT, ct, is_const, Sm, Rm, out);
         }
     }
     tc_fence_before();
@@ -299,8 +303,37 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// One lane's A row for one dy: output word j = funnel(W[j-A-1], W[j-A], 8s) with W[k] = template word k
+// (row word k + 4 behind the 16-byte zero border).  Every 8 output words consume exactly two 16-byte
+// chunks, so the chunk alignment (4 - A) % 4 is a compile-time constant of the producer warp.
+template <int A>
+__device__ __forceinline__ void ts_build_row(const uint4* __restrict__ row, int sh, int nk, uint32_t taddr)
+{
+    constexpr int C0 = (A == 0) ? 1 : 0;                    // chunk of row word 4 - A
+    constexpr int P0 = (A == 0) ? 0 : 4 - A;                // its position inside the chunk
+    uint32_t lo = 0u;                                       // W[-A-1] lies in the zero border
+    for (int i = 0; i < nk; ++i) {
+        const uint4 q0 = row[C0 + 2 * i], q1 = row[C0 + 2 * i + 1];
+        uint4 q2 = make_uint4(0u, 0u, 0u, 0u);
+        if (P0 != 0) q2 = row[C0 + 2 * i + 2];
+        const uint32_t w[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+        uint32_t v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t hi = w[P0 + j];
+            v[j] = __funnelshift_l(lo, hi, sh);
+            lo = hi;
+        }
+        tmem_st8(taddr + (uint32_t)(8 * i), v);
+    }
+}
+
 constexpr int TS_MAX_SLOTS = 8;
 
+// TMEM lane m <-> (a, t, s) = (m >> 5, (m >> 2) & 7, m & 3): template t, x-offset r = 4a + s.  The word
+// part `a` of the shift is uniform per producer warp, so every lane of a template reads the SAME
+// 16-byte chunks of the (zero-bordered) template row -- broadcast LDS.128 -- and only the byte part
+// `s` is a per-lane funnel shift.
 __global__ void __launch_bounds__(TC_THREADS, 2)
 ncc_tc_ts_kernel(const TsParams p)
 {
@@ -310,9 +343,9 @@ ncc_tc_ts_kernel(const TsParams p)
     const uint32_t tile_bytes = ((uint32_t)kb_img * p.R * 16 + 127) & ~127u;
     const uint32_t rows_bytes = ((uint32_t)8 * p.tmpl_stride + 127) & ~127u;
     uint8_t* tile = smem;
-    uint8_t* trows = smem + tile_bytes;                         // [t][dy][row_stride]
+    uint8_t* trows = smem + tile_bytes;                         // [t][dy][row_stride], 16 zero bytes before each row
     uint64_t* bars = reinterpret_cast<uint64_t*>(trows + rows_bytes);
-    uint64_t* a_full = bars;                                    // [slots]  128 producer arrivals
+    uint64_t* a_full = bars;                                    // [slots]  4 producer-warp arrivals
     uint64_t* a_empty = bars + TS_MAX_SLOTS;                    // [slots]  tcgen05.commit
     uint64_t* accum = bars + 2 * TS_MAX_SLOTS;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TS_MAX_SLOTS + 1);
@@ -328,7 +361,7 @@ ncc_tc_ts_kernel(const TsParams p)
     }
     if (warp == 4) tmem_alloc(tmem_slot, 256);
 
-    // ---- stage the image tile [k-block][row][16 B] and the compact template rows
+    // ---- stage the image tile [k-block][row][16 B] and the zero-bordered template rows
     {
         const int pieces = kb_img * p.R;
         for (int idx = tid; idx < pieces; idx += TC_THREADS) {
@@ -339,15 +372,16 @@ ncc_tc_ts_kernel(const TsParams p)
             if (gy < p.H && gb + 16 <= p.pitch) v = *reinterpret_cast<const uint4*>(p.img + (int64_t)gy * p.pitch + gb);
             *reinterpret_cast<uint4*>(tile + (size_t)idx * 16) = v;
         }
-        // compact template rows: [t][dy][row_stride]; packed rows are 16-byte aligned multiples of 4 bytes
-        const int wq = p.wp >> 2;
-        const int rows = 8 * p.h;
-        for (int rw = warp; rw < rows; rw += TC_THREADS / 32) {       // one warp per (t, dy) row
+        // row = [16 B zeros][wp template bytes][zeros ...] ; row_stride/4 words, all written here
+        const int rsq = p.row_stride >> 2, wq = p.wp >> 2;
+        const int total = 8 * p.h * rsq;
+        for (int idx = tid; idx < total; idx += TC_THREADS) {
+            const int rw = idx / rsq, g = idx - rw * rsq;              // rw = t*h + dy
             const int t = rw / p.h, dy = rw - t * p.h;
-            uint32_t* dst = reinterpret_cast<uint32_t*>(trows + (size_t)t * p.tmpl_stride + (size_t)dy * p.row_stride);
-            const uint32_t* src = (t < p.count)
-                ? reinterpret_cast<const uint32_t*>(p.tmpl + p.pix_off[t] + (int64_t)dy * p.wp) : nullptr;
-            for (int g = lane; g < wq; g += 32) dst[g] = src ? __ldg(src + g) : 0u;
+            uint32_t v = 0u;
+            if (t < p.count && g >= 4 && g - 4 < wq)
+                v = __ldg(reinterpret_cast<const uint32_t*>(p.tmpl + p.pix_off[t] + (int64_t)dy * p.wp) + (g - 4));
+            reinterpret_cast<uint32_t*>(trows + (size_t)t * p.tmpl_stride + (size_t)dy * p.row_stride)[g] = v;
         }
     }
     fence_async_smem();
@@ -361,49 +395,51 @@ ncc_tc_ts_kernel(const TsParams p)
     if (p.prof && tid == 0) t_loaded = clock64();
 
     if (warp < 4) {
-        // ===== A producers: thread m = 32*warp + lane owns TMEM lane m = (t, r) =====
-        const int m = 32 * warp + lane;
-        const int t = m >> 4, r = m & 15;
-        const int a = r >> 2, sh = 8 * (r & 3);
-        const int wq = p.wp >> 2;
-        const uint32_t* rows_t = reinterpret_cast<const uint32_t*>(trows + (size_t)t * p.tmpl_stride);
+        // ===== A producers: warp a = word shift; lane = (t, s) =====
+        const int a = warp, t = lane >> 2, sh = 8 * (lane & 3);
+        // A word j of lane (a, t, s) = bytes T[4(j - a) - s ..]; with the 16-byte zero border the needed
+        // words start at row word index 3 - a.  Read aligned 16-byte chunks starting at chunk 0.
+        const uint8_t* rows_t = trows + (size_t)t * p.tmpl_stride;
         const uint32_t lane_addr = tmem_a + ((uint32_t)(32 * warp) << 16);
-        const int rsq = p.row_stride >> 2;
+        const bool pf = p.prof && warp == 0 && lane == 0;
+        long long c_wait = 0, c_build = 0, c_store = 0;
         for (int dy = 0; dy < p.h; ++dy) {
             const int s = dy % p.slots;
+            long long c0 = pf ? clock64() : 0;
             if (dy >= p.slots) {
                 if (lane == 0) mbar_wait(&a_empty[s], ((dy / p.slots) - 1) & 1);
                 __syncwarp();
             }
             tc_fence_after();
-            const uint32_t* row = rows_t + (size_t)dy * rsq;
-            int k = -a - 1;
-            uint32_t lo = (k >= 0 && k < wq) ? row[k] : 0u;
-            for (int i = 0; i < p.nk; ++i) {
-                uint32_t v[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    ++k;
-                    const uint32_t hi = (k >= 0 && k < wq) ? row[k] : 0u;
-                    v[j] = __funnelshift_l(lo, hi, sh);
-                    lo = hi;
-                }
-                tmem_st8(lane_addr + (uint32_t)(s * slot_cols + 8 * i), v);
+            long long c1 = pf ? clock64() : 0;
+            const uint4* row = reinterpret_cast<const uint4*>(rows_t + (size_t)dy * p.row_stride);
+            const uint32_t slot_addr = lane_addr + (uint32_t)(s * slot_cols);
+            switch (a) {                                            // warp-uniform: compile-time word alignment
+                case 0: ts_build_row<0>(row, sh, p.nk, slot_addr); break;
+                case 1: ts_build_row<1>(row, sh, p.nk, slot_addr); break;
+                case 2: ts_build_row<2>(row, sh, p.nk, slot_addr); break;
+                default: ts_build_row<3>(row, sh, p.nk, slot_addr); break;
             }
+            long long c2 = pf ? clock64() : 0;
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&a_full[s]);
+            if (pf) { const long long c3 = clock64(); c_wait += c1 - c0; c_build += c2 - c1; c_store += c3 - c2; }
         }
+        if (pf) { long long* q = p.prof + 8 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x); q[4] = c_wait; q[5] = c_build; q[6] = c_store; }
     } else if (warp == 4) {
         if (lane == 0) {
             const uint32_t idesc = (2u << 4) | ((uint32_t)(p.N >> 3) << 17) | ((128u >> 4) << 24);
             const uint32_t tile_addr = smem_u32(tile);
             const uint32_t lbo_b = (uint32_t)p.R * 16;
+            long long m_wait = 0;
             for (int dy = 0; dy < p.h; ++dy) {
                 const int s = dy % p.slots;
+                const long long c0 = p.prof ? clock64() : 0;
                 mbar_wait(&a_full[s], (dy / p.slots) & 1);
                 tc_fence_after();
+                if (p.prof) m_wait += clock64() - c0;
                 for (int i = 0; i < p.nk; ++i) {
                     const uint64_t bd = umma_desc(tile_addr + dy * 16 + 2 * i * lbo_b, lbo_b, 128);
                     umma_i8_ts(tmem_d, tmem_a + (uint32_t)(s * slot_cols + 8 * i), bd, idesc, (dy | i) != 0);
@@ -411,6 +447,7 @@ ncc_tc_ts_kernel(const TsParams p)
                 umma_commit(&a_empty[s]);
             }
             umma_commit(accum);
+            if (p.prof) p.prof[8 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x) + 7] = m_wait;
         }
         __syncwarp();
     }
@@ -421,7 +458,7 @@ ncc_tc_ts_kernel(const TsParams p)
     if (p.prof && tid == 0) t_main = clock64();
     {
         const int m = 32 * (warp & 3) + lane;
-        const int tsel = m >> 4, x = x0 + (m & 15);
+        const int tsel = (m >> 2) & 7, x = x0 + 4 * (m >> 5) + (m & 3);
         const bool live = (tsel < p.count) && (x < p.mw);
         const TmplMeta* tm = live ? &p.meta[p.order[tsel]] : nullptr;
         const long long area = (long long)p.h * p.w;
@@ -435,14 +472,14 @@ ncc_tc_ts_kernel(const TsParams p)
             uint32_t v[16];
             tmem_ld16(tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c0, v);
             if (!live || y0 + c0 >= p.mh) continue;
-            epilogue16(v, y0 + c0, p.mh, p.mw, x, area, sumT, ct, is_const, p.S, p.rsD, out);
+            epilogue16(v, y0 + c0, p.mh, p.mw, x, area, sumT, ct, is_const, p.S + tm->mom_off, p.rsD + tm->mom_off, out);
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 4) tmem_dealloc(tmem_base, 256);
     if (p.prof && tid == 0) {
-        long long* q = p.prof + 4 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x);
+        long long* q = p.prof + 8 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x);
         q[0] = t_loaded - t_begin; q[1] = t_main - t_loaded; q[2] = clock64() - t_main; q[3] = t_begin;
     }
 }
@@ -464,31 +501,35 @@ __global__ void toeplitz_prep_kernel(const uint8_t* __restrict__ tmpl, const Tmp
 #pragma unroll
         for (int k = 0; k < 16; ++k) bytes[k] = 0;
         if (t < count) {
-            const TmplMeta& tm = meta[order[t]];
+            const TmplMeta& tm = meta[order[t]];                 // members smaller than the group are zero padded
             const uint8_t* row = tmpl + tm.pix_off + (int64_t)dy * tm.wp;
+            if (dy < tm.h) {
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const int col = ubase + k;
-                if (col >= 0 && col < w) bytes[k] = row[col];
+                for (int k = 0; k < 16; ++k) {
+                    const int col = ubase + k;
+                    if (col >= 0 && col < tm.w) bytes[k] = row[col];
+                }
             }
         }
         *reinterpret_cast<uint4*>(slabs + (int64_t)dy * slab_bytes + (int64_t)pc * 16) = *reinterpret_cast<const uint4*>(bytes);
     }
 }
 
-// S = window sum, rsD = rsqrt(A*Q - S^2) (0 for an exactly flat window), per window position.
-__global__ void window_moments_kernel(SatView sat, int h, int w, int mh, int mw, uint32_t* __restrict__ S,
+// S = window sum, rsD = rsqrt(A*Q - S^2) (0 for an exactly flat window), per window position, for
+// every distinct template size in one launch (blockIdx.y = size).
+__global__ void window_moments_kernel(SatView sat, const SizeDesc* __restrict__ sizes, uint32_t* __restrict__ S,
                                       float* __restrict__ rsD)
 {
-    const int64_t n = (int64_t)mh * mw;
-    const unsigned long long area = (unsigned long long)h * w;
+    const SizeDesc sd = sizes[blockIdx.y];
+    const int64_t n = (int64_t)sd.mh * sd.mw;
+    const unsigned long long area = (unsigned long long)sd.h * sd.w;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int y = (int)(idx / mw), x = (int)(idx - (int64_t)y * mw);
-        const uint32_t s = sat_window_s(sat.s, sat.pitch, y, x, h, w);
-        const unsigned long long q = sat_window_q(sat.q, sat.pitch, y, x, h, w);
+        const int y = (int)(idx / sd.mw), x = (int)(idx - (int64_t)y * sd.mw);
+        const uint32_t s = sat_window_s(sat.s, sat.pitch, y, x, sd.h, sd.w);
+        const unsigned long long q = sat_window_q(sat.q, sat.pitch, y, x, sd.h, sd.w);
         const unsigned long long d1 = area * q - (unsigned long long)s * s;
-        S[idx] = s;
-        rsD[idx] = d1 ? rsqrtf((float)d1) : 0.0f;
+        S[sd.off + idx] = s;
+        rsD[sd.off + idx] = d1 ? rsqrtf((float)d1) : 0.0f;
     }
 }
 
@@ -508,14 +549,14 @@ bool tc_plan_group(int mode, int h, int w, TcGroup& g)
     g.mode = mode; g.h = h; g.w = w; g.variant = 0;
     const int nx = mode == 0 ? 16 : 128;
     g.nk = (w + nx - 1 + 31) / 32;
-    if (mode == 0 && g.nk <= 5 && !getenv("MTM_B200_NO_TS")) {
+    if (mode == 0 && g.nk <= 5 && getenv("MTM_B200_TS")) {      // experimental: off by default (SS is faster today)
         // TS variant: A generated into TMEM, N = 128 output rows, compact template rows resident in smem
-        const int wp = (w + 3) / 4 * 4;
-        g.row_stride = wp + 4;
+        int rs = 16 + 32 * g.nk + 16;
+        g.row_stride = rs;
         g.N = 128; g.R = g.N + h - 1;
         g.slots = std::min(TS_MAX_SLOTS, 128 / (8 * g.nk));
         const size_t tile = ((size_t)2 * g.nk * g.R * 16 + 127) & ~(size_t)127;
-        const size_t rows = ((size_t)8 * ((size_t)h * g.row_stride + 16) + 127) & ~(size_t)127;
+        const size_t rows = ((size_t)8 * ((size_t)h * g.row_stride + 16) + 127) & ~(size_t)127;   // +16: bank skew between templates
         if (tile + rows + 256 <= 224 * 1024 && g.R * 16 < (1 << 18)) {
             g.variant = 1; g.smem = tile + rows + 256; g.slab_bytes = 0; g.ds = 0; g.a_kblk = 0;
             g.eff = (double)w / (32.0 * g.nk);
@@ -554,18 +595,19 @@ int launch_toeplitz_prep(mtm_ctx* ctx, const TcGroup& g)
     return MTM_OK;
 }
 
-int launch_window_moments(mtm_ctx* ctx, int h, int w, int mh, int mw, uint32_t* S, float* rsD)
+int launch_window_moments(mtm_ctx* ctx)
 {
     const ImageDev& im = ctx->img;
     SatView sv{im.sat_s, im.sat_q, im.sat_pitch, (int64_t)(im.H + 1) * im.sat_pitch};
-    const int64_t n = (int64_t)mh * mw;
-    const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 16);
-    window_moments_kernel<<<blocks, 256, 0, ctx->stream>>>(sv, h, w, mh, mw, S, rsD);
+    int64_t n = 0;
+    for (const SizeDesc& sd : ctx->h_sizes) n = std::max<int64_t>(n, (int64_t)sd.mh * sd.mw);
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 16));
+    window_moments_kernel<<<dim3(blocks, (unsigned)ctx->h_sizes.size()), 256, 0, ctx->stream>>>(sv, ctx->d_sizes, ctx->d_wS, ctx->d_wR);
     MTM_LAUNCH_CHECK(ctx);
     return MTM_OK;
 }
 
-static int launch_ncc_tc_ts(mtm_ctx* ctx, const TcGroup& g, const uint32_t* S, const float* rsD)
+static int launch_ncc_tc_ts(mtm_ctx* ctx, const TcGroup& g)
 {
     const ImageDev& im = ctx->img;
     TsParams p{};
@@ -576,39 +618,39 @@ static int launch_ncc_tc_ts(mtm_ctx* ctx, const TcGroup& g, const uint32_t* S, c
     p.row_stride = g.row_stride; p.slots = g.slots; p.tmpl_stride = g.h * g.row_stride + 16;
     for (int t = 0; t < 8; ++t) p.pix_off[t] = t < g.count ? ctx->h_meta[ctx->h_order[g.first + t]].pix_off : 0;
     p.meta = ctx->d_meta; p.order = ctx->d_order + g.first; p.count = g.count;
-    p.S = S; p.rsD = rsD; p.maps = ctx->d_maps;
+    p.S = ctx->d_wS; p.rsD = ctx->d_wR; p.maps = ctx->d_maps;
     MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     dim3 grid((p.mw + 15) / 16, (p.mh + g.N - 1) / g.N);
     static const bool prof = getenv("MTM_B200_PROF") != nullptr;       // debug: per-CTA phase clocks to stderr
     long long* d_prof = nullptr;
     const size_t n_cta = (size_t)grid.x * grid.y;
-    if (prof) { MTM_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&d_prof), n_cta * 4 * sizeof(long long))); p.prof = d_prof; }
+    if (prof) { MTM_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&d_prof), n_cta * 8 * sizeof(long long))); p.prof = d_prof; }
     ncc_tc_ts_kernel<<<grid, TC_THREADS, g.smem, ctx->stream>>>(p);
     MTM_LAUNCH_CHECK(ctx);
     if (prof) {
-        std::vector<long long> hp(n_cta * 4);
+        std::vector<long long> hp(n_cta * 8);
         MTM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         MTM_CUDA(ctx, cudaMemcpy(hp.data(), d_prof, hp.size() * sizeof(long long), cudaMemcpyDeviceToHost));
         cudaFree(d_prof);
-        double a = 0, b = 0, c = 0; long long t0 = hp[3], t1 = 0;
-        for (size_t i = 0; i < n_cta; ++i) { a += hp[4*i]; b += hp[4*i+1]; c += hp[4*i+2]; t0 = std::min(t0, hp[4*i+3]); t1 = std::max(t1, hp[4*i+3] + hp[4*i] + hp[4*i+1] + hp[4*i+2]); }
-        fprintf(stderr, "[mtm prof] ts kernel: %zu CTAs, mean clocks load=%.0f main=%.0f epilogue=%.0f, span=%lld (smem %zu B, nk=%d, h=%d)\n",
-                n_cta, a / n_cta, b / n_cta, c / n_cta, t1 - t0, g.smem, g.nk, g.h);
+        double a = 0, b = 0, c = 0, pw = 0, pb = 0, ps = 0, mw = 0;
+        for (size_t i = 0; i < n_cta; ++i) { a += hp[8*i]; b += hp[8*i+1]; c += hp[8*i+2]; pw += hp[8*i+4]; pb += hp[8*i+5]; ps += hp[8*i+6]; mw += hp[8*i+7]; }
+        fprintf(stderr, "[mtm prof] ts kernel: %zu CTAs, mean clocks load=%.0f main=%.0f epilogue=%.0f | producer wait=%.0f build=%.0f store=%.0f | mma wait=%.0f (smem %zu B, nk=%d, h=%d)\n",
+                n_cta, a / n_cta, b / n_cta, c / n_cta, pw / n_cta, pb / n_cta, ps / n_cta, mw / n_cta, g.smem, g.nk, g.h);
     }
     return MTM_OK;
 }
 
-int launch_ncc_tc(mtm_ctx* ctx, const TcGroup& g, const uint32_t* S, const float* rsD)
+int launch_ncc_tc(mtm_ctx* ctx, const TcGroup& g)
 {
-    if (g.variant == 1) return launch_ncc_tc_ts(ctx, g, S, rsD);
+    if (g.variant == 1) return launch_ncc_tc_ts(ctx, g);
     const ImageDev& im = ctx->img;
     TcParams p{};
     p.img = im.pix; p.pitch = im.pitch; p.H = im.H; p.W = im.W;
     p.slabs = ctx->d_slabs + g.arena_off; p.slab_bytes = g.slab_bytes; p.a_kblk = g.a_kblk; p.nk = g.nk; p.ds = g.ds;
     p.mode = g.mode; p.N = g.N; p.R = g.R; p.h = g.h; p.w = g.w;
-    p.mh = im.H - g.h + 1; p.mw = im.W - g.w + 1;
+    p.mh = im.H - g.h_min + 1; p.mw = im.W - g.w_min + 1;      // tile grid covers the largest member map
     p.meta = ctx->d_meta; p.order = ctx->d_order + g.first; p.count = g.count;
-    p.S = S; p.rsD = rsD; p.maps = ctx->d_maps;
+    p.S = ctx->d_wS; p.rsD = ctx->d_wR; p.maps = ctx->d_maps;
     if (!ctx->tc_attr_set) {
         MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         ctx->tc_attr_set = true;

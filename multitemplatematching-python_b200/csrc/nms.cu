@@ -27,16 +27,23 @@ __device__ __forceinline__ bool hit_less(const DevHit& a, const DevHit& b, const
     if (s.mode == 0) {
         if (a.tmpl != b.tmpl) return a.tmpl < b.tmpl;
         if (a.tmpl == 0x7fffffff) return false;
-        const TmplMeta& tm = s.meta[a.tmpl];
-        const long long la = (long long)a.y * tm.mw + a.x, lb = (long long)b.y * tm.mw + b.x;
-        if (tm.mh != 1 && tm.mw != 1) {
+        // prepared by prep_mode0(): seq = row-major index in the map, key = 1 for 1-D (find_peaks) maps
+        if (a.key == 0.0f) {
             const float ka = s.minimize ? -a.score : a.score, kb = s.minimize ? -b.score : b.score;
             if (ka != kb) return ka > kb;
         }
-        return la < lb;
+        return a.seq < b.seq;
     }
     if (a.key != b.key) return a.key > b.key;
     return a.seq < b.seq;
+}
+
+// mode-0 sort keys are cached in the hit itself so that comparisons never touch global memory
+__device__ __forceinline__ void prep_mode0(DevHit& h, const TmplMeta* __restrict__ meta)
+{
+    const TmplMeta& tm = meta[h.tmpl];
+    h.seq = h.y * tm.mw + h.x;
+    h.key = (tm.mh == 1 || tm.mw == 1) ? 1.0f : 0.0f;
 }
 
 __device__ __forceinline__ DevHit load_hit(const DevHit* p)
@@ -81,6 +88,10 @@ sort_hits_kernel(DevHit* __restrict__ hits, int cap, int32_t* __restrict__ count
                 hits[i].key = -CUDART_INF_F;
                 hits[i].seq = 0x7fffffff;
                 atomicAdd(&dead, 1);
+            } else {
+                DevHit h = load_hit(hits + i);
+                prep_mode0(h, meta);
+                store_hit(hits + i, h);
             }
         } else {
             hits[i].key = ascending_key ? 1.0f - hits[i].score : hits[i].score;
@@ -201,7 +212,7 @@ __device__ void smem_bitonic(DevHit* sh, int npad, const SortCtx& sc)
 
 // do_nms == 0: findMatches order -> written back to `hits` (block A), count[0]/[1] updated.
 // do_nms == 1: ... then MTM.NMS -> `out` (block B), out_count[0] = kept, out_count[1] = raw count.
-__global__ void __launch_bounds__(1024, 1)
+__global__ void __launch_bounds__(256, 1)
 finalize_small_kernel(DevHit* __restrict__ hits, int cap, int32_t* __restrict__ count, const TmplMeta* __restrict__ meta,
                       const int32_t* __restrict__ nontrivial, int minimize, int check_trivial, int presorted, int do_nms,
                       DevHit* __restrict__ out, int32_t* __restrict__ out_count, float thr32, int ascending,
@@ -224,6 +235,7 @@ finalize_small_kernel(DevHit* __restrict__ hits, int cap, int32_t* __restrict__ 
         if (i < n_raw) {
             h = load_hit(hits + i);
             if (check_trivial && !nontrivial[h.tmpl]) { h.tmpl = 0x7fffffff; h.key = -CUDART_INF_F; h.seq = 0x7fffffff; dead_local++; }
+            else if (!presorted) prep_mode0(h, meta);
         } else {
             h.tmpl = 0x7fffffff; h.x = h.y = h.w = h.h = 0; h.score = 0.f; h.seq = 0x7fffffff; h.key = -CUDART_INF_F;
         }
@@ -273,22 +285,27 @@ finalize_small_kernel(DevHit* __restrict__ hits, int cap, int32_t* __restrict__ 
     __syncthreads();
     SortCtx sc1{meta, 1, minimize};
     smem_bitonic(sh, npad, sc1);
-    // greedy scan; kept hits are compacted to the front of `out` (global) and mirrored in smem order list
+    // greedy scan by warp 0 alone (warp votes instead of block barriers); kept_idx lists the survivors
     __shared__ unsigned short kept_idx[FIN_CAP];
     const long long limit = n_object < 0 ? (long long)n : n_object;
-    for (int i = 0; i < n; ++i) {
-        const DevHit cand = sh[i];
-        if (!(cand.key > thr32)) break;
-        const int kept = s_kept;
-        if (kept >= limit) break;
-        int sup = 0;
-        for (int k = tid; k < kept; k += nth)
-            if (!(rect_overlap(cand, sh[kept_idx[k]]) <= max_overlap)) sup = 1;
-        sup = __syncthreads_or(sup);
-        if (!sup && tid == 0) { kept_idx[kept] = (unsigned short)i; s_kept = kept + 1; }
-        __syncthreads();
+    if (tid < 32) {
+        int kept = 0;
+        for (int i = 0; i < n && kept < limit; ++i) {
+            const DevHit cand = sh[i];
+            if (!(cand.key > thr32)) break;
+            int sup = 0;
+            for (int k = tid; k < kept; k += 32)
+                if (!(rect_overlap(cand, sh[kept_idx[k]]) <= max_overlap)) sup = 1;
+            if (!__any_sync(0xffffffffu, sup)) {
+                if (tid == 0) kept_idx[kept] = (unsigned short)i;
+                ++kept;
+                __syncwarp();
+            }
+        }
+        if (tid == 0) s_kept = kept;
     }
-    const int kept = (s_kept < limit) ? s_kept : (int)limit;
+    __syncthreads();
+    const int kept = s_kept;
     for (int k = tid; k < kept; k += nth) store_hit(out + k, sh[kept_idx[k]]);
     if (tid == 0) out_count[0] = kept;
 }
@@ -298,7 +315,7 @@ finalize_small_kernel(DevHit* __restrict__ hits, int cap, int32_t* __restrict__ 
 int launch_finalize_small(mtm_ctx* ctx, int minimize, int check_trivial, int presorted, int do_nms, float thr32,
                           int ascending, int64_t n_object, float max_overlap)
 {
-    finalize_small_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->hitsA(), ctx->hit_cap, ctx->countA(), ctx->d_meta,
+    finalize_small_kernel<<<1, 256, 0, ctx->stream>>>(ctx->hitsA(), ctx->hit_cap, ctx->countA(), ctx->d_meta,
                                                        ctx->d_nontrivial, minimize, check_trivial, presorted, do_nms,
                                                        ctx->hitsB(), ctx->countB(), thr32, ascending, (long long)n_object,
                                                        max_overlap);

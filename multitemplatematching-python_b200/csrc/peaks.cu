@@ -165,7 +165,7 @@ int launch_peaks(mtm_ctx* ctx, int method, int64_t n_object, float thr32, double
     int64_t max_px = 0;
     for (int t = 0; t < nt; ++t) {
         const int64_t n = (int64_t)ctx->h_meta[t].mh * ctx->h_meta[t].mw;
-        if (n >= (1ll << 32)) return mtm_fail(ctx, MTM_ERR_UNSUPPORTED, "score map larger than 2^32 pixels");
+        if (n >= (1ll << 31)) return mtm_fail(ctx, MTM_ERR_UNSUPPORTED, "score map larger than 2^31 pixels");
         max_px = n > max_px ? n : max_px;
     }
     MTM_CUDA(ctx, cudaMemsetAsync(ctx->countA(), 0, MTM_HIT_HEADER, ctx->stream));

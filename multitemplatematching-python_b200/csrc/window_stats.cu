@@ -17,12 +17,12 @@ namespace {
 // squares stay < 2^32 for W*C < 66051).
 template <int C>
 __global__ void __launch_bounds__(256)
-sat_rows_kernel(const uint8_t* __restrict__ img, int64_t pitch, int H, int W, uint32_t* __restrict__ scratch)
+sat_rows_kernel(const uint8_t* __restrict__ img, int64_t pitch, int H, int W, int SP, uint32_t* __restrict__ scratch)
 {
     __shared__ uint32_t wsum[C + 1][8];
     const int y = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint8_t* row = img + (int64_t)y * pitch;
-    const int64_t plane = (int64_t)H * W;
+    const int64_t plane = (int64_t)H * SP;
     const int per = (W + 255) / 256;
     const int xa = min(W, tid * per), xb = min(W, xa + per);
     uint32_t tot[C + 1];
@@ -62,10 +62,53 @@ sat_rows_kernel(const uint8_t* __restrict__ img, int64_t pitch, int H, int W, ui
             const uint32_t p = row[(int64_t)x * C + c];
             excl[c] += p;
             sq += p * p;
-            scratch[c * plane + (int64_t)y * W + x] = excl[c];
+            scratch[c * plane + (int64_t)y * SP + x] = excl[c];
         }
         excl[C] += sq;
-        scratch[C * plane + (int64_t)y * W + x] = excl[C];
+        scratch[C * plane + (int64_t)y * SP + x] = excl[C];
+    }
+}
+
+// Single-channel fast path: each thread owns `per4` aligned 32-bit words (4 pixels each) of the row;
+// 16-byte stores into the (4-aligned pitch) scratch rows.
+__global__ void __launch_bounds__(256)
+sat_rows_c1_kernel(const uint8_t* __restrict__ img, int64_t pitch, int H, int W, int SP, uint32_t* __restrict__ scratch)
+{
+    __shared__ uint32_t wsum[2][8];
+    const int y = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t* row = reinterpret_cast<const uint32_t*>(img + (int64_t)y * pitch);
+    const int64_t plane = (int64_t)H * SP;
+    const int nwords = (W + 3) >> 2;
+    const int per4 = (nwords + 255) / 256;
+    const int wa = min(nwords, tid * per4), wb = min(nwords, wa + per4);
+    uint32_t ts = 0, tq = 0;
+    for (int k = wa; k < wb; ++k) {
+        uint32_t v = __ldg(row + k);
+        if (4 * k + 4 > W) v &= (1u << (8 * (W - 4 * k))) - 1u;        // last word: drop the padding bytes
+        ts += __dp4a(v, 0x01010101u, 0u);
+        tq += __dp4a(v, v, 0u);
+    }
+    uint32_t s = ts, q = tq;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t ns = __shfl_up_sync(0xffffffffu, s, d), nq = __shfl_up_sync(0xffffffffu, q, d);
+        if (lane >= d) { s += ns; q += nq; }
+    }
+    if (lane == 31) { wsum[0][wid] = s; wsum[1][wid] = q; }
+    __syncthreads();
+    uint32_t es = s - ts, eq = q - tq;
+    for (int k = 0; k < wid; ++k) { es += wsum[0][k]; eq += wsum[1][k]; }
+    uint4* ds = reinterpret_cast<uint4*>(scratch + (int64_t)y * SP);
+    uint4* dq = reinterpret_cast<uint4*>(scratch + plane + (int64_t)y * SP);
+    for (int k = wa; k < wb; ++k) {
+        uint32_t v = __ldg(row + k);
+        if (4 * k + 4 > W) v &= (1u << (8 * (W - 4 * k))) - 1u;
+        const uint32_t p0 = v & 255u, p1 = (v >> 8) & 255u, p2 = (v >> 16) & 255u, p3 = v >> 24;
+        uint4 a, b;
+        a.x = es + p0; a.y = a.x + p1; a.z = a.y + p2; a.w = a.z + p3; es = a.w;
+        b.x = eq + p0 * p0; b.y = b.x + p1 * p1; b.z = b.y + p2 * p2; b.w = b.z + p3 * p3; eq = b.w;
+        ds[k] = a;                                                       // columns >= W of the padded row are never read
+        dq[k] = b;
     }
 }
 
@@ -73,14 +116,14 @@ sat_rows_kernel(const uint8_t* __restrict__ img, int64_t pitch, int H, int W, ui
 // chunks -> running prefix (second sweep re-reads the chunk from L1/L2; loads are batched 8 deep).
 // blockIdx.y picks the table: 0..C-1 -> sat_s[c] (u32), C -> sat_q (u64).
 __global__ void __launch_bounds__(1024, 1)
-sat_cols_kernel(const uint32_t* __restrict__ scratch, int H, int W, int C,
+sat_cols_kernel(const uint32_t* __restrict__ scratch, int H, int W, int C, int SP,
                 uint32_t* __restrict__ sat_s, unsigned long long* __restrict__ sat_q, int64_t sat_pitch)
 {
     __shared__ unsigned long long part[32][33];
     const int cx = threadIdx.x, ry = threadIdx.y;
     const int sx = blockIdx.x * 32 + cx;          // SAT column, 0..W
     const int table = blockIdx.y;
-    const int64_t plane = (int64_t)H * W;
+    const int64_t plane = (int64_t)H * SP;
     const int rc = (H + 31) / 32;
     const int y0 = ry * rc, y1 = min(H, y0 + rc);
     const bool live = (sx >= 1 && sx <= W);
@@ -88,7 +131,7 @@ sat_cols_kernel(const uint32_t* __restrict__ scratch, int H, int W, int C,
     unsigned long long tot = 0;
     if (live) {
 #pragma unroll 8
-        for (int y = y0; y < y1; ++y) tot += __ldg(src + (int64_t)y * W);
+        for (int y = y0; y < y1; ++y) tot += __ldg(src + (int64_t)y * SP);
     }
     part[ry][cx] = tot;
     __syncthreads();
@@ -103,7 +146,7 @@ sat_cols_kernel(const uint32_t* __restrict__ scratch, int H, int W, int C,
     }
 #pragma unroll 8
     for (int y = y0; y < y1; ++y) {
-        if (live) run += __ldg(src + (int64_t)y * W);
+        if (live) run += __ldg(src + (int64_t)y * SP);
         const int64_t o = (int64_t)(y + 1) * sat_pitch + sx;
         if (is_q) sat_q[o] = run; else ds[o] = (uint32_t)run;
     }
@@ -167,17 +210,18 @@ int launch_build_sat(mtm_ctx* ctx)
 {
     ImageDev& im = ctx->img;
     const int H = im.H, W = im.W, C = im.C;
+    const int SP = (W + 3) / 4 * 4;                    // scratch row pitch (elements), 16-byte aligned rows
     dim3 g1(H), b1(256);
     switch (C) {
-        case 1: sat_rows_kernel<1><<<g1, b1, 0, ctx->stream>>>(im.pix, im.pitch, H, W, ctx->scratch); break;
-        case 2: sat_rows_kernel<2><<<g1, b1, 0, ctx->stream>>>(im.pix, im.pitch, H, W, ctx->scratch); break;
-        case 3: sat_rows_kernel<3><<<g1, b1, 0, ctx->stream>>>(im.pix, im.pitch, H, W, ctx->scratch); break;
-        case 4: sat_rows_kernel<4><<<g1, b1, 0, ctx->stream>>>(im.pix, im.pitch, H, W, ctx->scratch); break;
+        case 1: sat_rows_c1_kernel<<<g1, b1, 0, ctx->stream>>>(im.pix, im.pitch, H, W, SP, ctx->scratch); break;
+        case 2: sat_rows_kernel<2><<<g1, b1, 0, ctx->stream>>>(im.pix, im.pitch, H, W, SP, ctx->scratch); break;
+        case 3: sat_rows_kernel<3><<<g1, b1, 0, ctx->stream>>>(im.pix, im.pitch, H, W, SP, ctx->scratch); break;
+        case 4: sat_rows_kernel<4><<<g1, b1, 0, ctx->stream>>>(im.pix, im.pitch, H, W, SP, ctx->scratch); break;
         default: return mtm_fail(ctx, MTM_ERR_INVALID, "unsupported channel count %d", C);
     }
     MTM_LAUNCH_CHECK(ctx);
     dim3 g2((W + 1 + 31) / 32, C + 1), b2(32, 32);
-    sat_cols_kernel<<<g2, b2, 0, ctx->stream>>>(ctx->scratch, H, W, C, im.sat_s, im.sat_q, im.sat_pitch);
+    sat_cols_kernel<<<g2, b2, 0, ctx->stream>>>(ctx->scratch, H, W, C, SP, im.sat_s, im.sat_q, im.sat_pitch);
     MTM_LAUNCH_CHECK(ctx);
     return MTM_OK;
 }

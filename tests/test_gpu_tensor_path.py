@@ -57,6 +57,29 @@ def test_tensor_path_maps_vs_exact(mtm, ctxs, shape, tshape, n_t, seed):
     assert_hits_equal(hits_t, hits_d, tol=2e-6)
 
 
+def test_tensor_path_mixed_size_groups(mtm, ctxs):
+    """C5-style template sets: different sizes share one tcgen05 launch (zero-padded Toeplitz slabs)."""
+    from oracle import ncc_exact, synth
+    ct, cd = ctxs
+    rng = np.random.default_rng(21)
+    sides = np.linspace(16, 52, 13).round().astype(int)
+    temps = [synth.make_template(rng, int(s), int(s + (i % 3) * 5)) for i, s in enumerate(sides)]
+    order = rng.permutation(len(temps))                       # list order != size order
+    temps = [temps[i] for i in order]
+    img, _ = synth.make_scene(230, 310, temps[:4], 2, seed=21)
+    labelled = [("t%d" % i, t) for i, t in enumerate(temps)]
+    with ct.lock:
+        ct.set_image(img)
+        ct.set_templates(temps)
+        got = [ct.score_map(i, 5, (img.shape[0] - t.shape[0] + 1, img.shape[1] - t.shape[1] + 1)) for i, t in enumerate(temps)]
+    for i, t in enumerate(temps):
+        assert_map_close(got[i], ncc_exact.match_template_exact(img, t, use_fft=False))
+    hits_t = mtm.matchTemplates(labelled, img, score_threshold=0.45, context=ct)
+    hits_d = mtm.matchTemplates(labelled, img, score_threshold=0.45, context=cd)
+    assert len(hits_d) > 0
+    assert_hits_equal(hits_t, hits_d, tol=2e-6)
+
+
 def test_tensor_path_uniform_noise_and_bright(mtm, ctxs):
     """Saturated inputs: 255*255*h*w up to 4.26e9 needs the full unsigned 32-bit accumulator range."""
     from oracle import ncc_exact
