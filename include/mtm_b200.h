@@ -121,6 +121,18 @@ int mtm_nms(mtm_ctx* ctx, const mtm_hit* hits, int n, double score_threshold,
 int mtm_match_templates(mtm_ctx* ctx, int method, int64_t n_object, double score_threshold,
                         double max_overlap, mtm_hit* hits, int capacity, int* n_hits);
 
+/* Pipelined form of mtm_match_templates for streams of images (the caller's loop over images,
+ * e.g. the 16-image batch of BASELINE.json configs[4]): _async enqueues the whole search + NMS of
+ * the CURRENT image/templates and the copy of its result into pinned memory, and returns without
+ * waiting; _collect waits for that slot and hands the hits over.  Up to MTM_MAX_INFLIGHT
+ * submissions may be in flight, so the GPU runs back to back while the host prepares the next
+ * image.  Limited to the fused fast path: a submission with more than 1024 raw peaks makes
+ * _collect return MTM_ERR_CAPACITY (re-run that image with mtm_match_templates). */
+#define MTM_MAX_INFLIGHT 8
+int mtm_match_templates_async(mtm_ctx* ctx, int method, int64_t n_object, double score_threshold,
+                              double max_overlap, int slot);
+int mtm_match_templates_collect(mtm_ctx* ctx, int slot, mtm_hit* hits, int capacity, int* n_hits);
+
 #ifdef __cplusplus
 }
 #endif

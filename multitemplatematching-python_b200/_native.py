@@ -49,7 +49,11 @@ _SIGNATURES = {
                                _P, ctypes.POINTER(ctypes.c_int)]),
     "mtm_match_templates": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_double, _P,
                                            ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
+    "mtm_match_templates_async": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_double,
+                                                 ctypes.c_int]),
+    "mtm_match_templates_collect": (ctypes.c_int, [_P, ctypes.c_int, _P, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
 }
+MAX_INFLIGHT = 8
 
 _lib = None
 _lib_lock = threading.Lock()
@@ -210,6 +214,21 @@ class Context:
     def match_templates(self, method, n_object, score_threshold, max_overlap):
         return self._hits_call(self._lib.mtm_match_templates,
                                (int(method), int(n_object), float(score_threshold), float(max_overlap)))
+
+    def match_templates_async(self, method, n_object, score_threshold, max_overlap, slot):
+        """Enqueue search + NMS of the current image/templates; results via match_templates_collect(slot)."""
+        self._check(self._lib.mtm_match_templates_async(self._h, int(method), int(n_object), float(score_threshold),
+                                                        float(max_overlap), int(slot)))
+
+    def match_templates_collect(self, slot):
+        """Hits of an earlier match_templates_async(slot); None when that image needs the synchronous path."""
+        buf = np.empty(1024, HIT_DTYPE)
+        n = ctypes.c_int(0)
+        rc = self._lib.mtm_match_templates_collect(self._h, int(slot), _P(buf.ctypes.data), 1024, ctypes.byref(n))
+        if rc == MTM_ERR_CAPACITY:
+            return None
+        self._check(rc)
+        return buf[: n.value]
 
     def nms(self, hits, score_threshold, sort_ascending, n_object, max_overlap):
         hits = np.ascontiguousarray(hits, HIT_DTYPE)

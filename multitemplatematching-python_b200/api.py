@@ -12,7 +12,7 @@ import numpy as np
 
 from . import _native
 
-__all__ = ["computeScoreMap", "findMatches", "matchTemplates", "NMS"]
+__all__ = ["computeScoreMap", "findMatches", "matchTemplates", "matchTemplatesBatch", "NMS"]
 
 TM_SQDIFF, TM_SQDIFF_NORMED, TM_CCORR, TM_CCORR_NORMED, TM_CCOEFF, TM_CCOEFF_NORMED = range(6)
 _INF = float("inf")
@@ -189,6 +189,57 @@ def matchTemplates(listTemplates, image, method=TM_CCOEFF_NORMED, N_object=_INF,
         ctx.set_templates(arrays)
         raw = ctx.match_templates(method, n_dev, score_threshold, maxOverlap)
     return _to_hits(raw, names, xOffset, yOffset)
+
+
+def matchTemplatesBatch(listTemplates, images, method=TM_CCOEFF_NORMED, N_object=_INF, score_threshold=0.5,
+                        maxOverlap=0.25, searchBox=None, *, context=None):
+    """``[matchTemplates(listTemplates, im, ...) for im in images]`` as one pipelined submission.
+
+    The reference has no batch entry point (users loop over images, e.g. the 16-image batch of
+    BASELINE.json configs[4]); here the templates are uploaded once and the images stream through the
+    GPU back to back (``mtm_match_templates_async`` / ``_collect``): no per-image host synchronisation.
+    Results are identical to the per-image calls.
+    """
+    images = list(images)
+    if maxOverlap < 0 or maxOverlap > 1:
+        raise ValueError("Maximal overlap between bounding box is in range [0-1]")
+    finite = N_object != _INF
+    nms_threshold = (1 - score_threshold) if method == 1 else score_threshold
+    if method == 0 or len(listTemplates) == 0 or (finite and N_object < 1) or nms_threshold < 0:
+        return [matchTemplates(listTemplates, im, method, N_object, score_threshold, maxOverlap, searchBox,
+                               context=context) for im in images]
+    ctx = context or _native.default_context()
+    n_dev = int(N_object) if finite else -1
+    depth = _native.MAX_INFLIGHT
+    results = [None] * len(images)
+    pending = {}                                   # slot -> (image index, names, offsets, keep-alive)
+    names = None
+
+    def collect(slot):
+        i, nm, xo, yo, _keep = pending.pop(slot)
+        raw = ctx.match_templates_collect(slot)
+        results[i] = None if raw is None else _to_hits(raw, nm, xo, yo)
+
+    with ctx.lock:
+        for i, image in enumerate(images):
+            crop, xOffset, yOffset = _validate_search(listTemplates, image, N_object, searchBox)
+            nm, arrays, img = _prepare(listTemplates, crop, method)
+            if names is None:
+                ctx.set_templates(arrays)          # templates are the same objects for every image
+                names = nm
+            slot = i % depth
+            if slot in pending:
+                collect(slot)
+            ctx.set_image(img)
+            ctx.match_templates_async(method, n_dev, score_threshold, maxOverlap, slot)
+            pending[slot] = (i, nm, xOffset, yOffset, img)
+        for slot in sorted(pending, key=lambda s: pending[s][0]):
+            collect(slot)
+    for i, r in enumerate(results):                # images that exceeded the fused fast path
+        if r is None:
+            results[i] = matchTemplates(listTemplates, images[i], method, N_object, score_threshold, maxOverlap,
+                                        searchBox, context=context)
+    return results
 
 
 def NMS(listHit, scoreThreshold=0.5, sortAscending=False, N_object=_INF, maxOverlap=0.5, *, context=None):

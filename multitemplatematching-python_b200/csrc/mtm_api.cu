@@ -47,18 +47,22 @@ static int reserve_pinned(mtm_ctx* ctx, T*& ptr, size_t& cap, size_t need)
     if (!(ctx)) return MTM_ERR_INVALID;                                       \
     MTM_CUDA(ctx, cudaSetDevice((ctx)->device))
 
-// Folds the pending MTM_OPT_TIME_NCC event bracket into the counters (needs the events complete).
-static int harvest_ncc_time(mtm_ctx* ctx, bool wait)
+// Folds completed MTM_OPT_TIME_NCC event brackets into the counters.  `all`: wait for every pending
+// bracket; otherwise only wait when the ring is full.
+static int harvest_ncc_time(mtm_ctx* ctx, bool all)
 {
-    if (!ctx->ncc_pending) return MTM_OK;
-    if (wait) MTM_CUDA(ctx, cudaEventSynchronize(ctx->ev_ncc1));
-    float ms = 0.f;
-    cudaError_t e = cudaEventElapsedTime(&ms, ctx->ev_ncc0, ctx->ev_ncc1);
-    if (e == cudaErrorNotReady) { (void)cudaGetLastError(); return MTM_OK; }
-    MTM_CUDA(ctx, e);
-    ctx->ctr.ncc_ms += ms;
-    ctx->ctr.ncc_launches += ctx->ncc_pending_launches;
-    ctx->ncc_pending = 0;
+    while (ctx->ncc_tail != ctx->ncc_head) {
+        const int k = ctx->ncc_tail % MTM_NCC_RING;
+        const bool full = (ctx->ncc_head - ctx->ncc_tail) >= MTM_NCC_RING;
+        if (all || full) MTM_CUDA(ctx, cudaEventSynchronize(ctx->ev_ncc[k][1]));
+        float ms = 0.f;
+        cudaError_t e = cudaEventElapsedTime(&ms, ctx->ev_ncc[k][0], ctx->ev_ncc[k][1]);
+        if (e == cudaErrorNotReady) { (void)cudaGetLastError(); return MTM_OK; }
+        MTM_CUDA(ctx, e);
+        ctx->ctr.ncc_ms += ms;
+        ctx->ctr.ncc_launches += ctx->ncc_launches_of[k];
+        ctx->ncc_tail++;
+    }
     return MTM_OK;
 }
 
@@ -120,8 +124,9 @@ int mtm_create(int device, mtm_ctx** out)
     ctx->stream = ctx->own_stream;
     if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
-    if ((e = cudaEventCreate(&ctx->ev_ncc0)) != cudaSuccess) return bail("cudaEventCreate", e);
-    if ((e = cudaEventCreate(&ctx->ev_ncc1)) != cudaSuccess) return bail("cudaEventCreate", e);
+    for (int k = 0; k < MTM_NCC_RING; ++k)
+        for (int j = 0; j < 2; ++j)
+            if ((e = cudaEventCreate(&ctx->ev_ncc[k][j])) != cudaSuccess) return bail("cudaEventCreate", e);
     int rc = reserve_hits(ctx, 1 << 16);
     if (rc != MTM_OK) { g_create_err = ctx->err; mtm_destroy(ctx); return rc; }
     *out = ctx;
@@ -138,11 +143,13 @@ int mtm_destroy(mtm_ctx* ctx)
     cudaFree(ctx->d_blockA); cudaFree(ctx->d_blockB); cudaFree(ctx->d_keep);
     cudaFree(ctx->d_nontrivial); cudaFree(ctx->d_best);
     cudaFree(ctx->d_slabs); cudaFree(ctx->d_wS); cudaFree(ctx->d_wR); cudaFree(ctx->d_sizes);
+    for (int k = 0; k < MTM_MAX_INFLIGHT; ++k) { cudaFree(ctx->d_slot[k]); cudaFreeHost(ctx->h_slot[k]); if (ctx->ev_slot[k]) cudaEventDestroy(ctx->ev_slot[k]); }
     cudaFreeHost(ctx->h_tmpl_stage); cudaFreeHost(ctx->h_stage); cudaFreeHost(ctx->h_geom);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-    if (ctx->ev_ncc0) cudaEventDestroy(ctx->ev_ncc0);
-    if (ctx->ev_ncc1) cudaEventDestroy(ctx->ev_ncc1);
+    for (int k = 0; k < MTM_NCC_RING; ++k)
+        for (int j = 0; j < 2; ++j)
+            if (ctx->ev_ncc[k][j]) cudaEventDestroy(ctx->ev_ncc[k][j]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return MTM_OK;
@@ -241,6 +248,7 @@ static int ensure_geometry(mtm_ctx* ctx)
     if (ctx->img.H == 0) return mtm_fail(ctx, MTM_ERR_INVALID, "no image set (call mtm_set_image first)");
     if (ctx->n_tmpl == 0) return mtm_fail(ctx, MTM_ERR_INVALID, "no templates set (call mtm_set_templates first)");
     if (ctx->geometry_valid) return MTM_OK;
+    MTM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // h_geom (pinned) may still feed an earlier async copy
     if (ctx->tmpl_C != ctx->img.C || ctx->tmpl_dtype != ctx->img_dtype)
         return mtm_fail(ctx, MTM_ERR_INVALID, "image and templates differ in channel count or dtype");
     const int n = ctx->n_tmpl;
@@ -383,8 +391,8 @@ static int compute_maps(mtm_ctx* ctx, int method, int tmpl)
     if (tensor) MTM_TRY(ensure_moments(ctx));
     const int64_t launches_before = ctx->ctr.kernel_launches;
     if (ctx->time_ncc) {
-        MTM_TRY(harvest_ncc_time(ctx, true));
-        MTM_CUDA(ctx, cudaEventRecord(ctx->ev_ncc0, ctx->stream));
+        MTM_TRY(harvest_ncc_time(ctx, false));
+        MTM_CUDA(ctx, cudaEventRecord(ctx->ev_ncc[ctx->ncc_head % MTM_NCC_RING][0], ctx->stream));
     }
     if (tensor) {
         for (const TcGroup& g : ctx->tc_groups) {
@@ -410,9 +418,10 @@ static int compute_maps(mtm_ctx* ctx, int method, int tmpl)
         i = j;
     }
     if (ctx->time_ncc) {
-        MTM_CUDA(ctx, cudaEventRecord(ctx->ev_ncc1, ctx->stream));
-        ctx->ncc_pending = 1;
-        ctx->ncc_pending_launches = (int)(ctx->ctr.kernel_launches - launches_before);
+        const int k = ctx->ncc_head % MTM_NCC_RING;
+        MTM_CUDA(ctx, cudaEventRecord(ctx->ev_ncc[k][1], ctx->stream));
+        ctx->ncc_launches_of[k] = (int)(ctx->ctr.kernel_launches - launches_before);
+        ctx->ncc_head++;
     }
     return MTM_OK;
 }
@@ -593,6 +602,64 @@ int mtm_match_templates(mtm_ctx* ctx, int method, int64_t n_object, double score
         return MTM_OK;
     }
     return mtm_fail(ctx, MTM_ERR_CUDA, "mtm_match_templates: hit buffer kept overflowing");
+}
+
+int mtm_match_templates_async(mtm_ctx* ctx, int method, int64_t n_object, double score_threshold,
+                              double max_overlap, int slot)
+{
+    MTM_ENTER(ctx);
+    if (slot < 0 || slot >= MTM_MAX_INFLIGHT) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_match_templates_async: slot %d out of range", slot);
+    if (ctx->slot_busy[slot]) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_match_templates_async: slot %d not collected yet", slot);
+    if (method == MTM_TM_SQDIFF) return mtm_fail(ctx, MTM_ERR_INVALID, "The method TM_SQDIFF is not supported. Use TM_SQDIFF_NORMED instead.");
+    const size_t bytes = MTM_HIT_HEADER + (size_t)MTM_SLOT_HITS * sizeof(DevHit);
+    if (!ctx->d_slot[slot]) {
+        MTM_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_slot[slot]), bytes));
+        MTM_CUDA(ctx, cudaMemsetAsync(ctx->d_slot[slot], 0, bytes, ctx->stream));
+        MTM_CUDA(ctx, cudaMallocHost(reinterpret_cast<void**>(&ctx->h_slot[slot]), bytes));
+        MTM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_slot[slot], cudaEventDisableTiming));
+    }
+    MTM_TRY(ensure_geometry(ctx));
+    MTM_TRY(compute_maps(ctx, method, -1));
+    const int minimize = method_is_min(method) ? 1 : 0;
+    const int ascending = (method == MTM_TM_SQDIFF_NORMED) ? 1 : 0;
+    const float thr_nms = ascending ? (float)(1.0 - score_threshold) : (float)score_threshold;
+    MTM_TRY(launch_peaks(ctx, method, n_object, (float)score_threshold, score_threshold));
+    MTM_TRY(launch_finalize_small(ctx, minimize, n_object != 1, n_object == 1, 1, thr_nms, ascending, n_object,
+                                  (float)max_overlap, ctx->d_slot[slot]));
+    // header + the first 256 hits ride along; _collect fetches the (rare) remainder
+    const size_t first = MTM_HIT_HEADER + 256 * sizeof(DevHit);
+    MTM_CUDA(ctx, cudaMemcpyAsync(ctx->h_slot[slot], ctx->d_slot[slot], first, cudaMemcpyDeviceToHost, ctx->stream));
+    MTM_CUDA(ctx, cudaEventRecord(ctx->ev_slot[slot], ctx->stream));
+    ctx->ctr.d2h_bytes += (int64_t)first;
+    ctx->slot_busy[slot] = true;
+    return MTM_OK;
+}
+
+int mtm_match_templates_collect(mtm_ctx* ctx, int slot, mtm_hit* hits, int capacity, int* n_hits)
+{
+    MTM_ENTER(ctx);
+    if (slot < 0 || slot >= MTM_MAX_INFLIGHT || !ctx->slot_busy[slot])
+        return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_match_templates_collect: slot %d has no submission in flight", slot);
+    if (!n_hits || (capacity > 0 && !hits)) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_match_templates_collect: null output");
+    MTM_CUDA(ctx, cudaEventSynchronize(ctx->ev_slot[slot]));
+    ctx->slot_busy[slot] = false;
+    const int32_t* hdr = reinterpret_cast<const int32_t*>(ctx->h_slot[slot]);
+    const int n = hdr[0];
+    *n_hits = n;
+    if (hdr[2]) { *n_hits = hdr[1]; return mtm_fail(ctx, MTM_ERR_CAPACITY, "mtm_match_templates_collect: %d raw peaks exceed the fast path; use mtm_match_templates", hdr[1]); }
+    if (n > capacity) return mtm_fail(ctx, MTM_ERR_CAPACITY, "mtm_match_templates_collect: %d hits, caller capacity %d", n, capacity);
+    if (n > 256) {
+        const size_t first = MTM_HIT_HEADER + 256 * sizeof(DevHit), rest = (size_t)(n - 256) * sizeof(DevHit);
+        MTM_CUDA(ctx, cudaMemcpyAsync(ctx->h_slot[slot] + first, ctx->d_slot[slot] + first, rest, cudaMemcpyDeviceToHost, ctx->stream));
+        MTM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->ctr.d2h_bytes += (int64_t)rest;
+    }
+    const DevHit* src = reinterpret_cast<const DevHit*>(ctx->h_slot[slot] + MTM_HIT_HEADER);
+    for (int i = 0; i < n; ++i) {
+        hits[i].tmpl = src[i].tmpl; hits[i].x = src[i].x; hits[i].y = src[i].y;
+        hits[i].w = src[i].w; hits[i].h = src[i].h; hits[i].score = src[i].score;
+    }
+    return MTM_OK;
 }
 
 int mtm_nms(mtm_ctx* ctx, const mtm_hit* hits, int n, double score_threshold, int sort_ascending,

@@ -7,6 +7,8 @@
 #include "../../include/mtm_b200.h"
 
 #define MTM_MAX_CH 4
+#define MTM_NCC_RING 16
+#define MTM_SLOT_HITS 1024      // hits a slot of the asynchronous API can return (== the fused fast path)
 #define MTM_HIT_HEADER 32      // bytes: int32 count[8]; count[0] = number of hits (may exceed capacity)
 
 // Device-side record of one hit (32 bytes); the public mtm_hit is its 24-byte prefix.
@@ -79,8 +81,10 @@ struct mtm_ctx {
     mtm_counters ctr{};
     int path = MTM_PATH_AUTO;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    cudaEvent_t ev_ncc0 = nullptr, ev_ncc1 = nullptr;   // MTM_OPT_TIME_NCC bracket of the last compute_maps
-    int time_ncc = 0, ncc_pending = 0, ncc_pending_launches = 0;
+    // MTM_OPT_TIME_NCC: ring of event pairs bracketing the numerator kernels of recent compute_maps calls
+    cudaEvent_t ev_ncc[MTM_NCC_RING][2] = {};
+    int ncc_launches_of[MTM_NCC_RING] = {};
+    int time_ncc = 0, ncc_head = 0, ncc_tail = 0;       // [tail, head) are recorded but not yet folded into ctr
     int sm_count = 0;
 
     // image
@@ -127,6 +131,12 @@ struct mtm_ctx {
     size_t per_tmpl_cap = 0, best_cap = 0;
     uint8_t* h_stage = nullptr; size_t h_stage_cap = 0;   // pinned up/download buffer
 
+    // asynchronous submissions (mtm_match_templates_async / _collect): per-slot result blocks
+    uint8_t* d_slot[MTM_MAX_INFLIGHT] = {};        // header + DevHit[MTM_SLOT_HITS]
+    uint8_t* h_slot[MTM_MAX_INFLIGHT] = {};        // pinned mirrors
+    cudaEvent_t ev_slot[MTM_MAX_INFLIGHT] = {};
+    bool slot_busy[MTM_MAX_INFLIGHT] = {};
+
     int32_t* countA() const { return reinterpret_cast<int32_t*>(d_blockA); }
     int32_t* countB() const { return reinterpret_cast<int32_t*>(d_blockB); }
     DevHit* hitsA() const { return reinterpret_cast<DevHit*>(d_blockA + MTM_HIT_HEADER); }
@@ -167,7 +177,7 @@ int launch_peaks(mtm_ctx* ctx, int method, int64_t n_object, float thr32, double
 int launch_sort_hits(mtm_ctx* ctx, int mode, int minimize, int ascending_key, int check_trivial);
 // fast path (raw count <= 1024): sort(s) [+ NMS] in one launch; sets header[2] = 1 when it declines
 int launch_finalize_small(mtm_ctx* ctx, int minimize, int check_trivial, int presorted, int do_nms, float thr32,
-                          int ascending, int64_t n_object, float max_overlap);
+                          int ascending, int64_t n_object, float max_overlap, uint8_t* out_block = nullptr);
 // block A (sorted mode 1) -> block B
 int launch_nms(mtm_ctx* ctx, float thr32, int ascending, int64_t n_object, float max_overlap);
 

@@ -313,11 +313,13 @@ finalize_small_kernel(DevHit* __restrict__ hits, int cap, int32_t* __restrict__ 
 }  // namespace
 
 int launch_finalize_small(mtm_ctx* ctx, int minimize, int check_trivial, int presorted, int do_nms, float thr32,
-                          int ascending, int64_t n_object, float max_overlap)
+                          int ascending, int64_t n_object, float max_overlap, uint8_t* out_block)
 {
+    uint8_t* ob = out_block ? out_block : ctx->d_blockB;
     finalize_small_kernel<<<1, 256, 0, ctx->stream>>>(ctx->hitsA(), ctx->hit_cap, ctx->countA(), ctx->d_meta,
                                                        ctx->d_nontrivial, minimize, check_trivial, presorted, do_nms,
-                                                       ctx->hitsB(), ctx->countB(), thr32, ascending, (long long)n_object,
+                                                       reinterpret_cast<DevHit*>(ob + MTM_HIT_HEADER),
+                                                       reinterpret_cast<int32_t*>(ob), thr32, ascending, (long long)n_object,
                                                        max_overlap);
     MTM_LAUNCH_CHECK(ctx);
     return MTM_OK;

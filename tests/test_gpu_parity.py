@@ -200,3 +200,20 @@ def test_validation_errors_match_reference(mtm):
         mtm.matchTemplates([("a", t)], img, method=0)
     with pytest.raises(ValueError, match="64-bit"):
         mtm.computeScoreMap(t.astype(np.float64), img)
+
+
+def test_match_templates_batch_equals_loop(mtm):
+    """Pipelined batch entry point == the per-image calls (incl. a >1024-raw-peak image that
+    falls back to the synchronous path, and searchBox offsets)."""
+    from oracle import synth
+    rng = np.random.default_rng(77)
+    temps = [("t%d" % i, synth.make_template(rng, 24 + 4 * i, 30)) for i in range(5)]
+    images = [synth.make_scene(200, 260, [t[1] for t in temps], 2, seed=100 + k)[0] for k in range(11)]
+    for kw in (dict(score_threshold=0.5, maxOverlap=0.25), dict(score_threshold=0.4, N_object=3),
+               dict(N_object=1), dict(score_threshold=-0.0, maxOverlap=0.3), dict(score_threshold=0.5, searchBox=(10, 20, 180, 150))):
+        want = [mtm.matchTemplates(temps, im, **kw) for im in images]
+        got = mtm.matchTemplatesBatch(temps, images, **kw)
+        assert len(got) == len(want)
+        for g, w in zip(got, want):
+            assert [(a[0], a[1]) for a in g] == [(b[0], b[1]) for b in w]
+            assert all(a[2] == b[2] for a, b in zip(g, w))
