@@ -53,8 +53,8 @@ def _mask_policy(template, mask, method):
 def _require_gpu_support(image, templates, mask=None):
     if mask is not None:
         raise NotImplementedError("masked template matching (methods 0/3 with a mask) has no B200 kernel yet")
-    if image.dtype != np.uint8 or any(t.dtype != np.uint8 for t in templates):
-        raise NotImplementedError("only uint8 images/templates have a B200 kernel so far (float32 path is next)")
+    if image.dtype not in (np.uint8, np.float32) or any(t.dtype != image.dtype for t in templates):
+        raise NotImplementedError("unsupported dtype combination %s / %s" % (image.dtype, [t.dtype for t in templates]))
 
 
 def computeScoreMap(template, image, method=TM_CCOEFF_NORMED, mask=None, *, context=None):

@@ -5,6 +5,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
+#include <utility>
 
 static thread_local std::string g_create_err;
 
@@ -65,6 +67,27 @@ static int harvest_ncc_time(mtm_ctx* ctx, bool all)
     }
     return MTM_OK;
 }
+
+// Debug aid (MTM_B200_STAGES=1): CUDA events between the stages of a call, printed at its end.
+struct StageMarks {
+    std::vector<std::pair<const char*, cudaEvent_t>> ev;
+    bool on = getenv("MTM_B200_STAGES") != nullptr;
+    void mark(mtm_ctx* ctx, const char* name) {
+        if (!on) return;
+        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, ctx->stream); ev.emplace_back(name, e);
+    }
+    void report(mtm_ctx* ctx) {
+        if (!on || ev.size() < 2) return;
+        cudaStreamSynchronize(ctx->stream);
+        fprintf(stderr, "[mtm stages]");
+        for (size_t i = 1; i < ev.size(); ++i) { float ms = 0; cudaEventElapsedTime(&ms, ev[i - 1].second, ev[i].second); fprintf(stderr, " %s=%.1fus", ev[i].first, ms * 1e3f); }
+        float tot = 0; cudaEventElapsedTime(&tot, ev.front().second, ev.back().second);
+        fprintf(stderr, " total=%.1fus\n", tot * 1e3f);
+        for (auto& p : ev) cudaEventDestroy(p.second);
+        ev.clear();
+    }
+};
+static StageMarks g_marks;
 
 static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
@@ -142,6 +165,7 @@ int mtm_destroy(mtm_ctx* ctx)
     cudaFree(ctx->d_meta); cudaFree(ctx->d_tmpl); cudaFree(ctx->d_maps); cudaFree(ctx->d_order);
     cudaFree(ctx->d_blockA); cudaFree(ctx->d_blockB); cudaFree(ctx->d_keep);
     cudaFree(ctx->d_nontrivial); cudaFree(ctx->d_best);
+    cudaFree(ctx->img.pixf); cudaFree(ctx->img.satf_s); cudaFree(ctx->img.satf_q); cudaFree(ctx->d_tmpl_centred);
     cudaFree(ctx->d_slabs); cudaFree(ctx->d_wS); cudaFree(ctx->d_wR); cudaFree(ctx->d_sizes);
     for (int k = 0; k < MTM_MAX_INFLIGHT; ++k) { cudaFree(ctx->d_slot[k]); cudaFreeHost(ctx->h_slot[k]); if (ctx->ev_slot[k]) cudaEventDestroy(ctx->ev_slot[k]); }
     cudaFreeHost(ctx->h_tmpl_stage); cudaFreeHost(ctx->h_stage); cudaFreeHost(ctx->h_geom);
@@ -220,18 +244,40 @@ static int set_image_impl(mtm_ctx* ctx, const void* pixels, int H, int W, int C,
     MTM_ENTER(ctx);
     if (!pixels || H <= 0 || W <= 0) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_image: empty image (%d x %d)", H, W);
     if (C < 1 || C > MTM_MAX_CH) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_image: %d channels (1..4 supported)", C);
-    if (dtype != MTM_U8) return mtm_fail(ctx, MTM_ERR_UNSUPPORTED, "mtm_set_image: only uint8 images are implemented on the GPU path");
-    if ((int64_t)W * C > 66000) return mtm_fail(ctx, MTM_ERR_UNSUPPORTED, "mtm_set_image: rows wider than 66000 bytes");
-    if (row_stride < (int64_t)W * C) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_image: row stride %lld < %d", (long long)row_stride, W * C);
+    if (dtype != MTM_U8 && dtype != MTM_F32) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_image: unknown dtype %d", dtype);
+    if ((int64_t)W * C > 66000) return mtm_fail(ctx, MTM_ERR_UNSUPPORTED, "mtm_set_image: rows wider than 66000 elements");
+    const int64_t esz = dtype == MTM_F32 ? 4 : 1;
+    if (row_stride < (int64_t)W * C * esz) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_image: row stride %lld < %lld", (long long)row_stride, (long long)W * C * esz);
     ImageDev& im = ctx->img;
+    if (dtype == MTM_F32) {
+        if (C == 2) return mtm_fail(ctx, MTM_ERR_UNSUPPORTED, "mtm_set_image: 2-channel float32 images");
+        im.pitch_e = ((int64_t)W * C + 3) / 4 * 4;
+        MTM_TRY(mtm_reserve(ctx, im.pixf, ctx->imgf_cap, (size_t)(H * im.pitch_e + 64)));
+        im.H = H; im.W = W; im.C = C;
+        im.sat_pitch = ((int64_t)W + 1 + 3) / 4 * 4;
+        g_marks.mark(ctx, "begin");
+        MTM_CUDA(ctx, cudaMemcpy2DAsync(im.pixf, (size_t)im.pitch_e * 4, pixels, (size_t)row_stride, (size_t)W * C * 4, (size_t)H,
+                                        on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+        if (!on_device) ctx->ctr.h2d_bytes += (int64_t)H * W * C * 4;
+        MTM_TRY(mtm_reserve(ctx, im.satf_s, ctx->satf_s_cap, (size_t)C * (H + 1) * im.sat_pitch));
+        MTM_TRY(mtm_reserve(ctx, im.satf_q, ctx->satf_q_cap, (size_t)(H + 1) * im.sat_pitch));
+        MTM_TRY(mtm_reserve(ctx, ctx->scratch, ctx->scratch_cap, (size_t)2 * (C + 1) * H * W + 16));
+        ctx->img_dtype = dtype;
+        ctx->geometry_valid = false;
+        ctx->moments_valid = false;
+        MTM_TRY(launch_build_sat_f32(ctx));
+        return MTM_OK;
+    }
     const int64_t pitch = (((int64_t)W * C + 64 * C + 64) + 127) / 128 * 128;
     const bool reshape = (im.H != H || im.W != W || im.C != C);
     MTM_TRY(mtm_reserve(ctx, im.pix, ctx->img_cap, (size_t)(H * pitch + 256)));
     if (reshape) MTM_CUDA(ctx, cudaMemsetAsync(im.pix, 0, ctx->img_cap, ctx->stream));
     im.pitch = pitch; im.H = H; im.W = W; im.C = C;
     im.sat_pitch = ((int64_t)W + 1 + 3) / 4 * 4;
+    g_marks.mark(ctx, "begin");
     MTM_CUDA(ctx, cudaMemcpy2DAsync(im.pix, (size_t)pitch, pixels, (size_t)row_stride, (size_t)W * C, (size_t)H,
                                     on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+    g_marks.mark(ctx, "copy_image");
     if (!on_device) ctx->ctr.h2d_bytes += (int64_t)H * W * C;
     MTM_TRY(mtm_reserve(ctx, im.sat_s, ctx->sat_s_cap, (size_t)C * (H + 1) * im.sat_pitch));
     MTM_TRY(mtm_reserve(ctx, im.sat_q, ctx->sat_q_cap, (size_t)(H + 1) * im.sat_pitch));
@@ -240,6 +286,7 @@ static int set_image_impl(mtm_ctx* ctx, const void* pixels, int H, int W, int C,
     ctx->geometry_valid = false;
     ctx->moments_valid = false;
     MTM_TRY(launch_build_sat(ctx));
+    g_marks.mark(ctx, "sat");
     return MTM_OK;
 }
 
@@ -409,11 +456,12 @@ static int compute_maps(mtm_ctx* ctx, int method, int tmpl)
         const TmplMeta& a = ctx->h_meta[ctx->h_order[i]];
         int j = i + 1;
         while (j < n && ctx->h_meta[ctx->h_order[j]].h == a.h && ctx->h_meta[ctx->h_order[j]].w == a.w) ++j;
+        const bool f32 = (ctx->img_dtype == MTM_F32);
         if (tmpl < 0) {
-            MTM_TRY(launch_ncc_direct(ctx, method, i, j - i));
+            MTM_TRY(f32 ? launch_ncc_direct_f32(ctx, method, i, j - i) : launch_ncc_direct(ctx, method, i, j - i));
         } else {
             for (int k = i; k < j; ++k)
-                if (ctx->h_order[k] == tmpl) MTM_TRY(launch_ncc_direct(ctx, method, k, 1));
+                if (ctx->h_order[k] == tmpl) MTM_TRY(f32 ? launch_ncc_direct_f32(ctx, method, k, 1) : launch_ncc_direct(ctx, method, k, 1));
         }
         i = j;
     }
@@ -475,7 +523,28 @@ int mtm_set_templates(mtm_ctx* ctx, int n, const void* const* pixels, const int3
     MTM_ENTER(ctx);
     if (n <= 0 || !pixels || !h || !w) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_templates: empty template list");
     if (C < 1 || C > MTM_MAX_CH) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_templates: %d channels (1..4 supported)", C);
-    if (dtype != MTM_U8) return mtm_fail(ctx, MTM_ERR_UNSUPPORTED, "mtm_set_templates: only uint8 templates are implemented on the GPU path");
+    if (dtype != MTM_U8 && dtype != MTM_F32) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_templates: unknown dtype %d", dtype);
+    const int esz = dtype == MTM_F32 ? 4 : 1;
+    // Same template set as last time (content hash)?  Then everything derived from it -- packed pixels,
+    // statistics, Toeplitz slabs, launch plan -- is still resident: nothing to upload or recompute.
+    {
+        uint64_t hsh = 0x9E3779B97F4A7C15ull ^ ((uint64_t)n << 32) ^ ((uint64_t)C << 8) ^ (uint64_t)dtype;
+        auto mix = [&](uint64_t v) { hsh ^= v; hsh *= 0x100000001B3ull; hsh ^= hsh >> 29; };
+        for (int t = 0; t < n; ++t) {
+            if (!pixels[t] || h[t] <= 0 || w[t] <= 0)
+                return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_templates: template %d is empty", t);
+            mix(((uint64_t)(uint32_t)h[t] << 32) | (uint32_t)w[t]);
+            const size_t bytes = (size_t)h[t] * w[t] * C * esz;
+            const uint8_t* b = static_cast<const uint8_t*>(pixels[t]);
+            size_t k = 0;
+            for (; k + 8 <= bytes; k += 8) { uint64_t v; memcpy(&v, b + k, 8); mix(v); }
+            uint64_t tail = 0;
+            if (k < bytes) { memcpy(&tail, b + k, bytes - k); mix(tail ^ ((uint64_t)(bytes - k) << 56)); }
+        }
+        if (ctx->n_tmpl == n && ctx->tmpl_hash == hsh && ctx->tmpl_C == C && ctx->tmpl_dtype == dtype && ctx->tmpl_hash_valid) return MTM_OK;
+        ctx->tmpl_hash = hsh;
+        ctx->tmpl_hash_valid = false;           // set again once the upload below has been queued
+    }
     // the previous upload may still be reading the pinned staging buffers
     MTM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->h_meta.assign(n, TmplMeta{});
@@ -485,7 +554,7 @@ int mtm_set_templates(mtm_ctx* ctx, int n, const void* const* pixels, const int3
             return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_templates: template %d is empty", t);
         TmplMeta& m = ctx->h_meta[t];
         m.h = h[t]; m.w = w[t];
-        m.wp = (w[t] * C + 3) / 4 * 4;
+        m.wp = (w[t] * C * esz + 3) / 4 * 4;
         m.pix_off = (int64_t)total;
         total += ((size_t)m.wp * m.h + 15) / 16 * 16;
     }
@@ -496,7 +565,7 @@ int mtm_set_templates(mtm_ctx* ctx, int n, const void* const* pixels, const int3
         const TmplMeta& m = ctx->h_meta[t];
         const uint8_t* src = static_cast<const uint8_t*>(pixels[t]);
         uint8_t* dst = ctx->h_tmpl_stage + m.pix_off;
-        const size_t row = (size_t)m.w * C;
+        const size_t row = (size_t)m.w * C * esz;
         for (int y = 0; y < m.h; ++y) memcpy(dst + (size_t)y * m.wp, src + (size_t)y * row, row);
     }
     MTM_TRY(mtm_reserve(ctx, ctx->d_tmpl, ctx->tmpl_cap, total + 64));
@@ -517,8 +586,14 @@ int mtm_set_templates(mtm_ctx* ctx, int n, const void* const* pixels, const int3
     ctx->ctr.h2d_bytes += (int64_t)total + (int64_t)n * (sizeof(TmplMeta) + sizeof(int32_t));
     ctx->n_tmpl = n; ctx->tmpl_C = C; ctx->tmpl_dtype = dtype;
     ctx->geometry_valid = false;
-    MTM_TRY(launch_tmpl_stats(ctx));
+    if (dtype == MTM_F32) {
+        MTM_TRY(mtm_reserve(ctx, ctx->d_tmpl_centred, ctx->tmplc_cap, total + 64));
+        MTM_TRY(launch_tmpl_stats_f32(ctx));
+    } else {
+        MTM_TRY(launch_tmpl_stats(ctx));
+    }
     MTM_TRY(plan_tensor_path(ctx));
+    ctx->tmpl_hash_valid = true;
     return MTM_OK;
 }
 
@@ -576,16 +651,22 @@ int mtm_match_templates(mtm_ctx* ctx, int method, int64_t n_object, double score
     if (!n_hits || (capacity > 0 && !hits)) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_match_templates: null output");
     if (method == MTM_TM_SQDIFF) return mtm_fail(ctx, MTM_ERR_INVALID, "The method TM_SQDIFF is not supported. Use TM_SQDIFF_NORMED instead.");
     MTM_TRY(ensure_geometry(ctx));
+    g_marks.mark(ctx, "geometry");
     MTM_TRY(compute_maps(ctx, method, -1));
+    g_marks.mark(ctx, "moments+ncc");
     const int minimize = method_is_min(method) ? 1 : 0;
     const int ascending = (method == MTM_TM_SQDIFF_NORMED) ? 1 : 0;
     const float thr_nms = ascending ? (float)(1.0 - score_threshold) : (float)score_threshold;
     for (int attempt = 0; attempt < 8; ++attempt) {
         MTM_TRY(launch_peaks(ctx, method, n_object, (float)score_threshold, score_threshold));
+        g_marks.mark(ctx, "peaks");
         int n_raw = 0, n = 0, declined = 0;
         MTM_TRY(launch_finalize_small(ctx, minimize, n_object != 1, n_object == 1, 1, thr_nms, ascending, n_object,
                                       (float)max_overlap));
+        g_marks.mark(ctx, "finalize");
         MTM_TRY(download_block(ctx, ctx->d_blockB, &n_raw, &n, &declined));
+        g_marks.mark(ctx, "download");
+        g_marks.report(ctx);
         if (declined) {                                      // more than 1024 raw hits: general path
             if (n_raw > ctx->hit_cap) { MTM_TRY(reserve_hits(ctx, n_raw)); continue; }
             if (n_object != 1) {

@@ -71,6 +71,9 @@ struct ImageDev {
     uint32_t* sat_s = nullptr;   // C tables of (H+1) x sat_pitch, wrap-around u32 (window sums < 2^32)
     unsigned long long* sat_q = nullptr;  // (H+1) x sat_pitch, sum over channels of I^2
     int64_t sat_pitch = 0;       // elements
+    // float32 images (MTM/__init__.py:71-74): pixels + float64 summed-area tables
+    float* pixf = nullptr; int64_t pitch_e = 0;
+    double* satf_s = nullptr; double* satf_q = nullptr;
 };
 
 struct mtm_ctx {
@@ -89,7 +92,7 @@ struct mtm_ctx {
 
     // image
     ImageDev img;
-    size_t img_cap = 0, sat_s_cap = 0, sat_q_cap = 0, scratch_cap = 0;
+    size_t img_cap = 0, sat_s_cap = 0, sat_q_cap = 0, scratch_cap = 0, imgf_cap = 0, satf_s_cap = 0, satf_q_cap = 0;
     uint32_t* scratch = nullptr;         // row-prefix scratch for the SAT build
     int img_dtype = -1;
 
@@ -98,8 +101,10 @@ struct mtm_ctx {
     std::vector<TmplMeta> h_meta;
     TmplMeta* d_meta = nullptr; size_t meta_cap = 0;
     uint8_t* d_tmpl = nullptr; size_t tmpl_cap = 0;
+    uint8_t* d_tmpl_centred = nullptr; size_t tmplc_cap = 0;   // float32 templates minus their mean
     uint8_t* h_tmpl_stage = nullptr; size_t tmpl_stage_cap = 0;   // pinned
     int tmpl_C = 0, tmpl_dtype = -1;
+    uint64_t tmpl_hash = 0; bool tmpl_hash_valid = false;   // content hash of the resident template set
     bool geometry_valid = false;         // map offsets computed for (image, templates)
 
     // score maps
@@ -165,6 +170,10 @@ int launch_build_sat(mtm_ctx* ctx);
 int launch_tmpl_stats(mtm_ctx* ctx);
 // templates d_order[first .. first+count) share (h, w)
 int launch_ncc_direct(mtm_ctx* ctx, int method, int first, int count);
+// float32 branch (ncc_float.cu)
+int launch_build_sat_f32(mtm_ctx* ctx);
+int launch_tmpl_stats_f32(mtm_ctx* ctx);
+int launch_ncc_direct_f32(mtm_ctx* ctx, int method, int first, int count);
 // tensor-core path
 bool tc_path_supported(const mtm_ctx* ctx, int method, int h, int w);
 bool tc_plan_group(int mode, int h, int w, TcGroup& g);

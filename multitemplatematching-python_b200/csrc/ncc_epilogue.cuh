@@ -29,10 +29,9 @@ __device__ __forceinline__ unsigned long long sat_window_q(const unsigned long l
     return b[w] - a[w] - b[0] + a[0];
 }
 
-// cc: exact sum I*T over all channels.  S[c]: window sum per channel.  Q: window sum of squares.
+// cc: sum I*T over all channels.  S[c]: window sum per channel.  Q: window sum of squares.
 template <int C>
-__device__ __forceinline__ float ncc_epilogue(int method, double cc, const uint32_t (&S)[C],
-                                              unsigned long long Q, const TmplMeta& tm)
+__device__ __forceinline__ float ncc_epilogue_f64(int method, double cc, const double (&S)[C], double Q, const TmplMeta& tm)
 {
     if (method == MTM_TM_CCORR) return (float)cc;
     double num = cc;
@@ -45,14 +44,14 @@ __device__ __forceinline__ float ncc_epilogue(int method, double cc, const uint3
     if (coeff) {
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-            const double t = (double)S[c];
+            const double t = S[c];
             wnd_mean2 += t * t;
             num -= t * tm.mean[c];
         }
         wnd_mean2 *= tm.inv_area;
     }
     if (normed || sqdiff) {
-        wnd_sum2 = (double)Q;
+        wnd_sum2 = Q;
         if (sqdiff) num = fmax(wnd_sum2 - 2.0 * num + tm.sum2, 0.0);
     }
     if (normed) {
@@ -67,4 +66,15 @@ __device__ __forceinline__ float ncc_epilogue(int method, double cc, const uint3
         else num = (method != MTM_TM_SQDIFF_NORMED) ? 0.0 : 1.0;
     }
     return (float)num;
+}
+
+// Exact-integer window sums (uint8 images).
+template <int C>
+__device__ __forceinline__ float ncc_epilogue(int method, double cc, const uint32_t (&S)[C],
+                                              unsigned long long Q, const TmplMeta& tm)
+{
+    double Sd[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) Sd[c] = (double)S[c];
+    return ncc_epilogue_f64<C>(method, cc, Sd, (double)Q, tm);
 }

@@ -47,8 +47,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
 {
     uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    // the suspend-time hint (ns) lets the hardware park the thread instead of spinning: a polling lane
+    // must not starve a producer warp that shares its scheduler (highest warp id wins the arbiter)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(200000u) : "memory");
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
@@ -56,7 +58,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
     // try_wait suspends for a bounded time per call; a barrier that never completes (a bug, not a
     // load condition) traps instead of hanging the GPU.
     for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
-        if (spins > (1u << 24)) __trap();
+        if (spins > (1u << 16)) __trap();
     }
 }
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
@@ -233,7 +235,10 @@ ncc_tc_kernel(const TcParams p)
     }
 
     // ---- epilogue: all 8 warps.  warp%4 selects the TMEM lane quarter, warp/4 the column half.
-    mbar_wait(accum, 0);
+    // Only the MMA warp polls the accumulator barrier; everybody else blocks in bar.sync (no issue
+    // slots stolen from the producer / MMA lanes while the main loop runs).
+    if (warp == 1) { if (lane == 0) mbar_wait(accum, 0); __syncwarp(); }
+    __syncthreads();
     tc_fence_after();
     {
         const int m = 32 * (warp & 3) + lane;
@@ -285,6 +290,7 @@ struct TsParams {
     const uint32_t* S; const float* rsD;
     float* maps;
     long long* prof;                  // optional: per-CTA phase clocks
+    int dbg;                          // debug: 1 = skip tcgen05.st, 2 = skip the LDS (timing experiments only)
 };
 
 __device__ __forceinline__ void umma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
@@ -307,15 +313,17 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
 // (row word k + 4 behind the 16-byte zero border).  Every 8 output words consume exactly two 16-byte
 // chunks, so the chunk alignment (4 - A) % 4 is a compile-time constant of the producer warp.
 template <int A>
-__device__ __forceinline__ void ts_build_row(const uint4* __restrict__ row, int sh, int nk, uint32_t taddr)
+__device__ __forceinline__ void ts_build_row(const uint4* __restrict__ row, int sh, int nk, uint32_t taddr, int dbg)
 {
     constexpr int C0 = (A == 0) ? 1 : 0;                    // chunk of row word 4 - A
     constexpr int P0 = (A == 0) ? 0 : 4 - A;                // its position inside the chunk
     uint32_t lo = 0u;                                       // W[-A-1] lies in the zero border
     for (int i = 0; i < nk; ++i) {
-        const uint4 q0 = row[C0 + 2 * i], q1 = row[C0 + 2 * i + 1];
-        uint4 q2 = make_uint4(0u, 0u, 0u, 0u);
-        if (P0 != 0) q2 = row[C0 + 2 * i + 2];
+        uint4 q0 = make_uint4(1u, 2u, 3u, 4u), q1 = q0, q2 = make_uint4(0u, 0u, 0u, 0u);
+        if (!(dbg & 2)) {
+            q0 = row[C0 + 2 * i]; q1 = row[C0 + 2 * i + 1];
+            if (P0 != 0) q2 = row[C0 + 2 * i + 2];
+        }
         const uint32_t w[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
         uint32_t v[8];
 #pragma unroll
@@ -324,7 +332,8 @@ __device__ __forceinline__ void ts_build_row(const uint4* __restrict__ row, int 
             v[j] = __funnelshift_l(lo, hi, sh);
             lo = hi;
         }
-        tmem_st8(taddr + (uint32_t)(8 * i), v);
+        if (!(dbg & 1)) tmem_st8(taddr + (uint32_t)(8 * i), v);
+        else if (v[0] == 0xdeadbeefu && v[7] == 0x12345u) asm volatile("trap;");   // keep v alive
     }
 }
 
@@ -415,10 +424,10 @@ ncc_tc_ts_kernel(const TsParams p)
             const uint4* row = reinterpret_cast<const uint4*>(rows_t + (size_t)dy * p.row_stride);
             const uint32_t slot_addr = lane_addr + (uint32_t)(s * slot_cols);
             switch (a) {                                            // warp-uniform: compile-time word alignment
-                case 0: ts_build_row<0>(row, sh, p.nk, slot_addr); break;
-                case 1: ts_build_row<1>(row, sh, p.nk, slot_addr); break;
-                case 2: ts_build_row<2>(row, sh, p.nk, slot_addr); break;
-                default: ts_build_row<3>(row, sh, p.nk, slot_addr); break;
+                case 0: ts_build_row<0>(row, sh, p.nk, slot_addr, p.dbg); break;
+                case 1: ts_build_row<1>(row, sh, p.nk, slot_addr, p.dbg); break;
+                case 2: ts_build_row<2>(row, sh, p.nk, slot_addr, p.dbg); break;
+                default: ts_build_row<3>(row, sh, p.nk, slot_addr, p.dbg); break;
             }
             long long c2 = pf ? clock64() : 0;
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -452,8 +461,9 @@ ncc_tc_ts_kernel(const TsParams p)
         __syncwarp();
     }
 
-    // ===== epilogue: all 8 warps =====
-    mbar_wait(accum, 0);
+    // ===== epilogue: all 8 warps (only the MMA warp polls; the rest blocks in bar.sync) =====
+    if (warp == 4) { if (lane == 0) mbar_wait(accum, 0); __syncwarp(); }
+    __syncthreads();
     tc_fence_after();
     if (p.prof && tid == 0) t_main = clock64();
     {
@@ -625,6 +635,7 @@ static int launch_ncc_tc_ts(mtm_ctx* ctx, const TcGroup& g)
     long long* d_prof = nullptr;
     const size_t n_cta = (size_t)grid.x * grid.y;
     if (prof) { MTM_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&d_prof), n_cta * 8 * sizeof(long long))); p.prof = d_prof; }
+    p.dbg = getenv("MTM_B200_TS_DBG") ? atoi(getenv("MTM_B200_TS_DBG")) : 0;
     ncc_tc_ts_kernel<<<grid, TC_THREADS, g.smem, ctx->stream>>>(p);
     MTM_LAUNCH_CHECK(ctx);
     if (prof) {

@@ -35,6 +35,7 @@ __device__ __forceinline__ bool hit_less(const DevHit& a, const DevHit& b, const
         return a.seq < b.seq;
     }
     if (a.key != b.key) return a.key > b.key;
+    if (s.mode == 2 && a.tmpl != b.tmpl) return a.tmpl < b.tmpl;   // canonical list order without sorting into it first
     return a.seq < b.seq;
 }
 
@@ -245,19 +246,26 @@ finalize_small_kernel(DevHit* __restrict__ hits, int cap, int32_t* __restrict__ 
     __syncthreads();
     const int n = n_raw - s_live;                               // live hits (s_live counted the dead ones)
     __syncthreads();
-    if (!presorted) {
+    if (!presorted && !do_nms) {                                // findMatches order
         SortCtx sc0{meta, 0, minimize};
         smem_bitonic(sh, npad, sc0);
-        for (int i = tid; i < n; i += nth) sh[i].seq = i;
-        __syncthreads();
-    }
-    if (!do_nms) {
         for (int i = tid; i < n; i += nth) store_hit(hits + i, sh[i]);
+        for (int i = tid; i < n; i += nth) hits[i].seq = i;
         if (tid == 0) { count[0] = n; count[1] = n; }
         return;
     }
     if (tid == 0) out_count[1] = n_raw;
     // ---- MTM.NMS (MTM/NMS.py:20-84) ----
+    // NMSBoxes' stable sort by descending key of the canonical (template, peak order) list ==
+    // ONE sort by (key desc, template asc, row-major index asc): mode 2.  Presorted input
+    // (standalone mtm_nms, N_object == 1) keeps its own seq: mode 1.
+    if (!presorted) {
+        for (int i = tid; i < npad; i += nth)
+            if (sh[i].tmpl != 0x7fffffff) sh[i].key = ascending ? 1.0f - sh[i].score : sh[i].score;   // seq = row-major index (prep_mode0)
+        __syncthreads();
+        SortCtx sc2{meta, 2, minimize};
+        smem_bitonic(sh, npad, sc2);
+    }
     if (n <= 1) {
         if (tid == 0) { if (n == 1) out[0] = sh[0]; out_count[0] = n; }
         return;
@@ -280,11 +288,13 @@ finalize_small_kernel(DevHit* __restrict__ hits, int cap, int32_t* __restrict__ 
         }
         return;
     }
-    for (int i = tid; i < npad; i += nth)
-        if (i < n) sh[i].key = ascending ? 1.0f - sh[i].score : sh[i].score;
-    __syncthreads();
-    SortCtx sc1{meta, 1, minimize};
-    smem_bitonic(sh, npad, sc1);
+    if (presorted) {
+        for (int i = tid; i < npad; i += nth)
+            if (i < n) sh[i].key = ascending ? 1.0f - sh[i].score : sh[i].score;
+        __syncthreads();
+        SortCtx sc1{meta, 1, minimize};
+        smem_bitonic(sh, npad, sc1);
+    }
     // greedy scan by warp 0 alone (warp votes instead of block barriers); kept_idx lists the survivors
     __shared__ unsigned short kept_idx[FIN_CAP];
     const long long limit = n_object < 0 ? (long long)n : n_object;
@@ -294,8 +304,13 @@ finalize_small_kernel(DevHit* __restrict__ hits, int cap, int32_t* __restrict__ 
             const DevHit cand = sh[i];
             if (!(cand.key > thr32)) break;
             int sup = 0;
-            for (int k = tid; k < kept; k += 32)
-                if (!(rect_overlap(cand, sh[kept_idx[k]]) <= max_overlap)) sup = 1;
+            for (int k = tid; k < kept; k += 32) {
+                const DevHit& o = sh[kept_idx[k]];
+                // disjoint boxes have overlap 1.f - (float)1.0 == 0 <= max_overlap: skip the fp64 division
+                const bool meet = (cand.x < o.x + o.w && o.x < cand.x + cand.w && cand.y < o.y + o.h && o.y < cand.y + cand.h) ||
+                                  (cand.w * cand.h + o.w * o.h <= 0);          // degenerate rects: keep OpenCV's rule
+                if (meet && !(rect_overlap(cand, o) <= max_overlap)) sup = 1;
+            }
             if (!__any_sync(0xffffffffu, sup)) {
                 if (tid == 0) kept_idx[kept] = (unsigned short)i;
                 ++kept;

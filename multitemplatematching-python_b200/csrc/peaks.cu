@@ -32,43 +32,52 @@ __global__ void peaks2d_kernel(const TmplMeta* __restrict__ meta, const float* _
     const float sgn = minimize ? -1.0f : 1.0f;
     const float m0 = m[0];
     int differs = 0;
-    for (int64_t base = 4 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x); base < n;
-         base += 4 * (int64_t)gridDim.x * blockDim.x) {
-        float v4[4];
-        if (base + 4 <= n) {
-            const float4 q = *reinterpret_cast<const float4*>(m + base);
-            v4[0] = q.x; v4[1] = q.y; v4[2] = q.z; v4[3] = q.w;
-        } else {
+    // each thread takes UNR aligned float4 per sweep (UNR independent 16-byte loads in flight)
+    constexpr int UNR = 4;
+    const int64_t sweep = 4 * (int64_t)gridDim.x * blockDim.x;
+    for (int64_t base0 = 4 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x); base0 < n; base0 += UNR * sweep) {
+        float4 q[UNR];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) v4[k] = (base + k < n) ? m[base + k] : m0;
+        for (int u = 0; u < UNR; ++u) {
+            const int64_t base = base0 + u * sweep;
+            if (base + 4 <= n) q[u] = __ldg(reinterpret_cast<const float4*>(m + base));
+            else {
+                q[u].x = (base + 0 < n) ? m[base + 0] : m0; q[u].y = (base + 1 < n) ? m[base + 1] : m0;
+                q[u].z = (base + 2 < n) ? m[base + 2] : m0; q[u].w = (base + 3 < n) ? m[base + 3] : m0;
+            }
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float raw = v4[k];
-            if (raw != m0) differs = 1;
-            const float v = sgn * raw;
-            if (!(v > thr32) || base + k >= n) continue;
-            const int64_t idx = base + k;
-            const int y = (int)(idx / mw), x = (int)(idx - (int64_t)y * mw);
-            bool is_max = true;
+        for (int u = 0; u < UNR; ++u) {
+            const int64_t base = base0 + u * sweep;
+            const float v4[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
 #pragma unroll
-            for (int dy = -1; dy <= 1; ++dy) {
-                const int yy = y + dy;
-                if (yy < 0 || yy >= mh) continue;
+            for (int k = 0; k < 4; ++k) {
+                const float raw = v4[k];
+                if (raw != m0) differs = 1;
+                const float v = sgn * raw;
+                if (!(v > thr32) || base + k >= n) continue;
+                const int64_t idx = base + k;
+                const int y = (int)(idx / mw), x = (int)(idx - (int64_t)y * mw);
+                bool is_max = true;
 #pragma unroll
-                for (int dx = -1; dx <= 1; ++dx) {
-                    const int xx = x + dx;
-                    if (xx < 0 || xx >= mw || (dx == 0 && dy == 0)) continue;
-                    if (sgn * m[(int64_t)yy * mw + xx] > v) is_max = false;
+                for (int dy = -1; dy <= 1; ++dy) {
+                    const int yy = y + dy;
+                    if (yy < 0 || yy >= mh) continue;
+#pragma unroll
+                    for (int dx = -1; dx <= 1; ++dx) {
+                        const int xx = x + dx;
+                        if (xx < 0 || xx >= mw || (dx == 0 && dy == 0)) continue;
+                        if (sgn * m[(int64_t)yy * mw + xx] > v) is_max = false;
+                    }
                 }
-            }
-            if (is_max) {
-                const int slot = atomicAdd(count, 1);
-                if (slot < cap) {
-                    DevHit h;
-                    h.tmpl = blockIdx.y; h.x = x; h.y = y; h.w = tm.w; h.h = tm.h;
-                    h.score = raw; h.seq = 0; h.key = 0.f;
-                    hits[slot] = h;
+                if (is_max) {
+                    const int slot = atomicAdd(count, 1);
+                    if (slot < cap) {
+                        DevHit h;
+                        h.tmpl = blockIdx.y; h.x = x; h.y = y; h.w = tm.w; h.h = tm.h;
+                        h.score = raw; h.seq = 0; h.key = 0.f;
+                        hits[slot] = h;
+                    }
                 }
             }
         }
@@ -169,7 +178,7 @@ int launch_peaks(mtm_ctx* ctx, int method, int64_t n_object, float thr32, double
         max_px = n > max_px ? n : max_px;
     }
     MTM_CUDA(ctx, cudaMemsetAsync(ctx->countA(), 0, MTM_HIT_HEADER, ctx->stream));
-    int bx = (int)((max_px + 1023) / 1024);
+    int bx = (int)((max_px + 4095) / 4096);
     const int bx_cap = ctx->sm_count * 8;
     if (bx > bx_cap) bx = bx_cap;
     if (bx < 1) bx = 1;

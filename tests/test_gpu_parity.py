@@ -202,6 +202,31 @@ def test_validation_errors_match_reference(mtm):
         mtm.computeScoreMap(t.astype(np.float64), img)
 
 
+@pytest.mark.parametrize("method,thr", [(1, 0.35), (3, 0.92), (2, 0.0), (4, 0.0)])
+def test_match_templates_other_methods_vs_port(mtm, method, thr):
+    """the other score methods through the whole pipeline (method 1 searches
+    local MINIMA and sorts ascending in the NMS, MTM/__init__.py:232-233, MTM/NMS.py:73-75)."""
+    from oracle import mtm_port, ncc_exact, synth
+    rng = np.random.default_rng(60 + method)
+    temps = [("a", synth.make_template(rng, 28, 28)), ("b", synth.make_template(rng, 20, 36))]
+    img, _ = synth.make_scene(180, 240, [t[1] for t in temps], 3, seed=60 + method)
+    if method in (2, 4):        # un-normalised scores: compare maps and the N_object=1 answer only
+        for name, t in temps:
+            assert_map_close(mtm.computeScoreMap(t, img, method=method),
+                             ncc_exact.match_template_exact(img, t, method=method, use_fft=False))
+        got = mtm.matchTemplates(temps, img, method=method, N_object=1)
+        want = mtm_port.match_templates(temps, img, method=method, N_object=1)
+        assert got[0][:2] == want[0][:2]
+        return
+    got = mtm.matchTemplates(temps, img, method=method, score_threshold=thr, maxOverlap=0.2)
+    want = mtm_port.match_templates(temps, img, method=method, score_threshold=thr, maxOverlap=0.2)
+    assert len(want) >= 2
+    assert_hits_equal(got, want)
+    got1 = mtm.matchTemplates(temps, img, method=method, N_object=1)
+    want1 = mtm_port.match_templates(temps, img, method=method, N_object=1)
+    assert_hits_equal(got1, want1)
+
+
 def test_match_templates_batch_equals_loop(mtm):
     """Pipelined batch entry point == the per-image calls (incl. a >1024-raw-peak image that
     falls back to the synchronous path, and searchBox offsets)."""

@@ -82,6 +82,19 @@ def test_exact_ncc_rgb_and_fft_twin():
     assert np.array_equal(ncc_exact.cc_direct(g, t), ncc_exact.cc_fft(g, t))
 
 
+@pytest.mark.parametrize("method", [0, 1, 2, 3, 4, 5])
+def test_exact_ncc_float32_vs_cv2(method):
+    """float32 branch of the dtype policy (MTM/__init__.py:71-74): oracle in float64 vs cv2's float64 DFT."""
+    from oracle import ncc_exact
+    rng = np.random.default_rng(100 + method)
+    img = (rng.random((80, 100)) * 4000 + 3000).astype(np.float32)
+    tmpl = (img[20:44, 30:61] + rng.normal(0, 50, (24, 31))).astype(np.float32)
+    exact = ncc_exact.match_template_exact(img, tmpl, method=method, use_fft=False)
+    cv = cv2.matchTemplate(img, tmpl, method)
+    scale = max(1.0, float(np.abs(cv).max()))
+    assert np.max(np.abs(exact.astype(np.float64) - cv)) <= 2e-5 * scale
+
+
 def test_exact_ncc_degenerate_rules():
     from oracle import ncc_exact
     img = np.full((30, 40), 9, np.uint8)
