@@ -302,9 +302,14 @@ def main():
     ncc_ms_per_step = ctr["ncc_ms"] / steps
     ncc_launches_per_step = ctr["ncc_launches"] / steps
     ach_tflops = 2.0 * macs / (ncc_ms_per_step * 1e-3) / 1e12 if ncc_ms_per_step > 0 else 0.0
+    traffic = None                      # dram bytes per launch from the committed `ncu --set full` capture
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(args.workload, {}).get("dram_bytes_per_launch")
     roofline = {"bound": "tensor", "kernel": "ncc numerator (+fused normalisation)",
                 "achieved": ach_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": ach_tflops / peaks["bf16_tflops"], "traffic": None,
+                "frac": ach_tflops / peaks["bf16_tflops"], "traffic": traffic,
                 "peak_source": "%s bf16 dense burst (MEASURED_PEAKS.json)" % peaks["source"],
                 "algorithmic_flops_per_step": 2.0 * macs, "launches_per_step": ncc_launches_per_step,
                 "kernel_ms_per_step": ncc_ms_per_step, "kernel_share_of_step": ncc_ms_per_step / (ms / steps)}

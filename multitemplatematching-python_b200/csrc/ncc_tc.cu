@@ -132,6 +132,60 @@ __device__ __forceinline__ void epilogue16(const uint32_t (&v)[16], int y_first,
     }
 }
 
+// Stage the image tile rows [y0, y0+R) x bytes [x0, x0 + 16*kb) into smem as [k-block][row][16 B].
+// Eight independent 16-byte loads per thread are in flight before the first store.
+__device__ __forceinline__ void stage_image_tile(uint8_t* __restrict__ tile, const uint8_t* __restrict__ img, int64_t pitch,
+                                                 int H, int x0, int y0, int R, int kb, int tid)
+{
+    const int pieces = kb * R;
+    for (int base = 0; base < pieces; base += 8 * TC_THREADS) {
+        uint4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int idx = base + u * TC_THREADS + tid;
+            v[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (idx < pieces) {
+                const int c = idx / R, r = idx - c * R;
+                const int gy = y0 + r;
+                const int64_t gb = (int64_t)x0 + 16 * c;
+                if (gy < H && gb + 16 <= pitch) v[u] = __ldg(reinterpret_cast<const uint4*>(img + (int64_t)gy * pitch + gb));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int idx = base + u * TC_THREADS + tid;
+            if (idx < pieces) *reinterpret_cast<uint4*>(tile + (size_t)idx * 16) = v[u];
+        }
+    }
+}
+
+// Window moments of 16 consecutive output rows of one lane (addresses clamped to the map).
+__device__ __forceinline__ void load_moments16(float (&rs)[16], uint32_t (&sw)[16], int y_first, int mh, int mw, int x,
+                                               const uint32_t* __restrict__ S, const float* __restrict__ rsD)
+{
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int y = min(y_first + k, mh - 1);
+        const int64_t o = (int64_t)y * mw + x;
+        rs[k] = __ldg(rsD + o);
+        sw[k] = __ldg(S + o);
+    }
+}
+
+__device__ __forceinline__ void normalise16(const uint32_t (&v)[16], const float (&rs)[16], const uint32_t (&sw)[16],
+                                            int y_first, int mh, int mw, int x, long long area, long long sumT, float ct,
+                                            bool is_const, float* __restrict__ out)
+{
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int y = y_first + k;
+        const long long n1 = area * (long long)v[k] - (long long)sw[k] * sumT;
+        float r = (float)n1 * rs[k] * ct;
+        r = fminf(1.0f, fmaxf(-1.0f, r));
+        if (y < mh) out[(int64_t)y * mw + x] = is_const ? 1.0f : r;
+    }
+}
+
 struct TcParams {
     const uint8_t* img; int64_t pitch; int H, W;
     const uint8_t* slabs;             // this group's Toeplitz slabs: h slabs of slab_bytes
@@ -149,7 +203,7 @@ struct TcParams {
 };
 
 // One CTA = one output tile.  Warp 0: slab producer, warp 1: MMA issuer, then all 8 warps: epilogue.
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 ncc_tc_kernel(const TcParams p)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -177,17 +231,7 @@ ncc_tc_kernel(const TcParams p)
     if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
 
     // ---- stage the image tile: rows [y0, y0+R) x bytes [x0, x0 + 32*nk), layout [k-block][row][16 B]
-    {
-        const int pieces = kb_img * p.R;
-        for (int idx = tid; idx < pieces; idx += TC_THREADS) {
-            const int c = idx / p.R, r = idx - c * p.R;
-            const int gy = y0 + r;
-            const int64_t gb = (int64_t)x0 + 16 * c;
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (gy < p.H && gb + 16 <= p.pitch) v = *reinterpret_cast<const uint4*>(p.img + (int64_t)gy * p.pitch + gb);
-            *reinterpret_cast<uint4*>(tile + (size_t)idx * 16) = v;
-        }
-    }
+    stage_image_tile(tile, p.img, p.pitch, p.H, x0, y0, p.R, kb_img, tid);
     fence_async_smem();                                        // generic-proxy writes -> visible to the MMA (async proxy)
     tc_fence_before();
     __syncthreads();
@@ -368,7 +412,8 @@ ncc_tc_ts_kernel(const TsParams p)
         mbar_init(accum, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) tmem_alloc(tmem_slot, 256);
+    const uint32_t tmem_total = p.N <= 128 ? 256u : 512u;        // N accumulator columns + the A ring
+    if (warp == 4) tmem_alloc(tmem_slot, tmem_total);
 
     // ---- stage the image tile [k-block][row][16 B] and the zero-bordered template rows
     {
@@ -399,7 +444,7 @@ ncc_tc_ts_kernel(const TsParams p)
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_d = tmem_base;                           // columns [0, N)
-    const uint32_t tmem_a = tmem_base + 128;                     // columns [128, 256): A ring
+    const uint32_t tmem_a = tmem_base + (p.N <= 128 ? 128u : 256u); // A ring behind the accumulator columns
     const int slot_cols = 8 * p.nk;
     if (p.prof && tid == 0) t_loaded = clock64();
 
@@ -487,7 +532,7 @@ ncc_tc_ts_kernel(const TsParams p)
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem_base, 256);
+    if (warp == 4) tmem_dealloc(tmem_base, tmem_total);
     if (p.prof && tid == 0) {
         long long* q = p.prof + 8 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x);
         q[0] = t_loaded - t_begin; q[1] = t_main - t_loaded; q[2] = clock64() - t_main; q[3] = t_begin;
@@ -563,8 +608,8 @@ bool tc_plan_group(int mode, int h, int w, TcGroup& g)
         // TS variant: A generated into TMEM, N = 128 output rows, compact template rows resident in smem
         int rs = 16 + 32 * g.nk + 16;
         g.row_stride = rs;
-        g.N = 128; g.R = g.N + h - 1;
-        g.slots = std::min(TS_MAX_SLOTS, 128 / (8 * g.nk));
+        g.N = getenv("MTM_B200_TS_N256") ? 256 : 128; g.R = g.N + h - 1;
+        g.slots = std::min(TS_MAX_SLOTS, g.N / (8 * g.nk));
         const size_t tile = ((size_t)2 * g.nk * g.R * 16 + 127) & ~(size_t)127;
         const size_t rows = ((size_t)8 * ((size_t)h * g.row_stride + 16) + 127) & ~(size_t)127;   // +16: bank skew between templates
         if (tile + rows + 256 <= 224 * 1024 && g.R * 16 < (1 << 18)) {
@@ -578,7 +623,8 @@ bool tc_plan_group(int mode, int h, int w, TcGroup& g)
     g.ds = 1;
     while ((g.ds + 1) * g.slab_bytes <= 16384 && g.ds < h) ++g.ds;
     const size_t ring = (size_t)TC_STAGES * g.ds * g.slab_bytes;
-    const int candidates[4] = {256, 128, 64, 32};
+    const int force_n = getenv("MTM_B200_FORCE_N") ? atoi(getenv("MTM_B200_FORCE_N")) : 0;   // experiments
+    const int candidates[4] = {force_n ? force_n : 256, force_n ? force_n : 128, force_n ? force_n : 64, force_n ? force_n : 32};
     g.N = 0;
     for (int pass = 0; pass < 2 && !g.N; ++pass) {
         const size_t budget = pass == 0 ? 110 * 1024 : 224 * 1024;       // first try 2 CTAs per SM
