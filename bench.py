@@ -140,6 +140,8 @@ def main():
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--path", default="auto", choices=["auto", "direct", "tensor"])
     ap.add_argument("--cpu-steps", type=int, default=None, help="steps of the cpu_baseline sample (default: ~15 s)")
+    ap.add_argument("--contexts", type=int, default=2,
+                    help="library contexts (CUDA streams) the resident-throughput loop alternates between")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -229,43 +231,71 @@ def main():
 
     DEPTH = 4                                   # submissions in flight (mtm_match_templates_async/_collect)
 
+    # extra contexts = extra CUDA streams: while one stream runs the (SM-filling) numerator kernel the
+    # other runs its small statistics / peak / NMS kernels and fills the wave tails
+    n_ctx = max(1, args.contexts)
+    ctxs = [ctx] + [_native.Context(local_rank) for _ in range(n_ctx - 1)]
+    for c in ctxs[1:]:
+        if args.path != "auto":
+            c.set_path({"direct": _native.PATH_DIRECT, "tensor": _native.PATH_TENSOR}[args.path])
+
     def resident_stream(first, count):
-        """`count` steps through the pipelined entry points; every result is collected before returning."""
+        """`count` steps through the pipelined entry points, round-robin over the contexts; every
+        result is collected (read on the host) before returning."""
         n_hits = 0
         for k in range(count):
-            slot = k % DEPTH
-            if k >= DEPTH:
-                r = ctx.match_templates_collect(slot)
+            c = ctxs[k % n_ctx]
+            slot = (k // n_ctx) % DEPTH
+            if k >= DEPTH * n_ctx:
+                r = c.match_templates_collect(slot)
                 n_hits += -1 if r is None else len(r)
-            ctx.set_image_device(d_pool[(first + k) % pool_n].data_ptr(), H, W, 1, W)
-            ctx.match_templates_async(5, n_obj, thr, ov, slot)
-        for k in range(max(0, count - DEPTH), count):
-            r = ctx.match_templates_collect(k % DEPTH)
+            c.set_image_device(d_pool[(first + k) % pool_n].data_ptr(), H, W, 1, W)
+            c.match_templates_async(5, n_obj, thr, ov, slot)
+        for k in range(max(0, count - DEPTH * n_ctx), count):
+            r = ctxs[k % n_ctx].match_templates_collect((k // n_ctx) % DEPTH)
             n_hits += -1 if r is None else len(r)
         return n_hits
 
     # ---------------- value: inputs resident in HBM ----------------
-    ctx.set_templates(tmpl_arrays)
+    for c in ctxs:
+        c.set_templates(tmpl_arrays)
     for i in range(warmup):
         hits = resident_step(i)
+    resident_stream(0, max(warmup, 2 * n_ctx * DEPTH))           # warm every context / slot
     n_hits_last = len(hits)
     barrier()
+    for c in ctxs:
+        c.synchronize()
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    ctx.reset_counters()
-    ctx.set_time_ncc(True)
+    for c in ctxs:
+        c.reset_counters()
+        c.set_time_ncc(True)
     ctx.timer_begin()
     resident_stream(warmup, steps)
-    ms = ctx.timer_end()
-    ctx.set_time_ncc(False)
-    ctr = ctx.counters()
+    for c in ctxs:
+        c.synchronize()
+    ms = ctx.timer_end()                                       # start event: before the first launch; end: after all streams drained
+    ctr = {"kernel_launches": 0, "ncc_ms": 0.0, "ncc_launches": 0}
+    for c in ctxs:
+        c.set_time_ncc(False)
+        cc = c.counters()
+        for k in ctr:
+            ctr[k] += cc[k]
     barrier()
     clocks = sampler.stop() if sampler else None
-    # latency form: one synchronous call per step (submit, wait, read the hits)
-    lat_steps = max(20, steps // 5)
+    # Second timed region, single stream, one synchronous call per step (submit, wait, read the hits):
+    # the per-step latency, and the region in which the numerator kernel is bracketed by CUDA events on
+    # its own stream WITHOUT another stream sharing the SMs (with several contexts the kernels of two
+    # streams overlap and their individual durations stop being meaningful).
+    lat_steps = max(20, steps // 3)
+    ctx.reset_counters()
+    ctx.set_time_ncc(True)
     ctx.timer_begin()
     for i in range(lat_steps):
         resident_step(warmup + steps + i)
     lat_ms = ctx.timer_end() / lat_steps
+    ctx.set_time_ncc(False)
+    lat_ctr = ctx.counters()
     barrier()
     t_ms = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -299,8 +329,9 @@ def main():
 
     # ---------------- roofline of the numerator kernel ----------------
     peaks = load_peaks()
-    ncc_ms_per_step = ctr["ncc_ms"] / steps
-    ncc_launches_per_step = ctr["ncc_launches"] / steps
+    ncc_ms_per_step = lat_ctr["ncc_ms"] / lat_steps
+    ncc_launches_per_step = lat_ctr["ncc_launches"] / lat_steps
+    ncc_ms_overlapped = ctr["ncc_ms"] / steps                    # same kernels inside the multi-stream region
     ach_tflops = 2.0 * macs / (ncc_ms_per_step * 1e-3) / 1e12 if ncc_ms_per_step > 0 else 0.0
     traffic = None                      # dram bytes per launch from the committed `ncu --set full` capture
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
@@ -312,7 +343,9 @@ def main():
                 "frac": ach_tflops / peaks["bf16_tflops"], "traffic": traffic,
                 "peak_source": "%s bf16 dense burst (MEASURED_PEAKS.json)" % peaks["source"],
                 "algorithmic_flops_per_step": 2.0 * macs, "launches_per_step": ncc_launches_per_step,
-                "kernel_ms_per_step": ncc_ms_per_step, "kernel_share_of_step": ncc_ms_per_step / (ms / steps)}
+                "kernel_ms_per_step": ncc_ms_per_step, "kernel_share_of_step": ncc_ms_per_step / lat_ms,
+                "timed_in": "single-stream synchronous region of this run (%d steps, %.3f ms/step)" % (lat_steps, lat_ms),
+                "kernel_ms_per_step_in_throughput_region": ncc_ms_overlapped}
 
     # ---------------- cpu baseline (bounded sample, rank 0, N == 1 only) ----------------
     cpu = None
@@ -333,8 +366,8 @@ def main():
                        "l2_policy": "inputs larger than L2: %d-image device pool (%.0f MB) rotated every step"
                                     % (pool_n, pool_n * img_bytes / 1e6),
                        "hits_last_step": n_hits_last, "path": args.path,
-                       "pipelining": "%d submissions in flight (mtm_match_templates_async/_collect); every step's hit list "
-                                     "is read back inside the timed region" % DEPTH},
+                       "pipelining": "%d contexts (streams) x %d submissions in flight (mtm_match_templates_async/_collect); "
+                                     "every step's hit list is read back inside the timed region" % (n_ctx, DEPTH)},
             "sync_ms_per_step": lat_ms,
             "gpix_corr_per_s": world * macs * steps / (ms_max * 1e-3) / 1e9,
             "gpu_launches": int(ctr["kernel_launches"]),

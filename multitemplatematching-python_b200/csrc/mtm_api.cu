@@ -161,7 +161,7 @@ int mtm_destroy(mtm_ctx* ctx)
     if (!ctx) return MTM_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    cudaFree(ctx->img.pix); cudaFree(ctx->img.sat_s); cudaFree(ctx->img.sat_q); cudaFree(ctx->scratch);
+    cudaFree(ctx->img.pix); cudaFree(ctx->img.sat_s); cudaFree(ctx->img.sat_q); cudaFree(ctx->img.sat_q32); cudaFree(ctx->scratch);
     cudaFree(ctx->d_meta); cudaFree(ctx->d_tmpl); cudaFree(ctx->d_maps); cudaFree(ctx->d_order);
     cudaFree(ctx->d_blockA); cudaFree(ctx->d_blockB); cudaFree(ctx->d_keep);
     cudaFree(ctx->d_nontrivial); cudaFree(ctx->d_best);
@@ -281,6 +281,7 @@ static int set_image_impl(mtm_ctx* ctx, const void* pixels, int H, int W, int C,
     if (!on_device) ctx->ctr.h2d_bytes += (int64_t)H * W * C;
     MTM_TRY(mtm_reserve(ctx, im.sat_s, ctx->sat_s_cap, (size_t)C * (H + 1) * im.sat_pitch));
     MTM_TRY(mtm_reserve(ctx, im.sat_q, ctx->sat_q_cap, (size_t)(H + 1) * im.sat_pitch));
+    MTM_TRY(mtm_reserve(ctx, im.sat_q32, ctx->sat_q32_cap, (size_t)(H + 1) * im.sat_pitch));
     MTM_TRY(mtm_reserve(ctx, ctx->scratch, ctx->scratch_cap, (size_t)(C + 1) * H * ((W + 3) / 4 * 4)));
     ctx->img_dtype = dtype;
     ctx->geometry_valid = false;

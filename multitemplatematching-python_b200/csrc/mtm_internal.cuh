@@ -70,6 +70,7 @@ struct ImageDev {
     int H = 0, W = 0, C = 0;
     uint32_t* sat_s = nullptr;   // C tables of (H+1) x sat_pitch, wrap-around u32 (window sums < 2^32)
     unsigned long long* sat_q = nullptr;  // (H+1) x sat_pitch, sum over channels of I^2
+    uint32_t* sat_q32 = nullptr;          // the same table modulo 2^32 (exact for window sums < 2^32: tensor path)
     int64_t sat_pitch = 0;       // elements
     // float32 images (MTM/__init__.py:71-74): pixels + float64 summed-area tables
     float* pixf = nullptr; int64_t pitch_e = 0;
@@ -92,7 +93,7 @@ struct mtm_ctx {
 
     // image
     ImageDev img;
-    size_t img_cap = 0, sat_s_cap = 0, sat_q_cap = 0, scratch_cap = 0, imgf_cap = 0, satf_s_cap = 0, satf_q_cap = 0;
+    size_t img_cap = 0, sat_s_cap = 0, sat_q_cap = 0, sat_q32_cap = 0, scratch_cap = 0, imgf_cap = 0, satf_s_cap = 0, satf_q_cap = 0;
     uint32_t* scratch = nullptr;         // row-prefix scratch for the SAT build
     int img_dtype = -1;
 

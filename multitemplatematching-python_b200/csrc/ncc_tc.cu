@@ -221,7 +221,8 @@ ncc_tc_kernel(const TcParams p)
 
     const int xw = p.mode == 0 ? 16 : 128;
     const int x0 = blockIdx.x * xw, y0 = blockIdx.y * p.N;
-    const uint32_t tmem_cols = p.N < 32 ? 32u : (uint32_t)p.N;
+    uint32_t tmem_cols = 32;                                    // tcgen05.alloc: power of two >= 32
+    while (tmem_cols < (uint32_t)p.N) tmem_cols <<= 1;
 
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -300,8 +301,9 @@ ncc_tc_kernel(const TcParams p)
         float* out = tm ? p.maps + tm->map_off : nullptr;
         const uint32_t* Sm = tm ? p.S + tm->mom_off : nullptr;
         const float* Rm = tm ? p.rsD + tm->mom_off : nullptr;
-        const int half = p.N >> 1;                             // N >= 32: each warp pair splits the columns
-        const int c_begin = (warp >> 2) * half, c_end = c_begin + half;
+        // N is a multiple of 16: the two warps of a lane quarter split the 16-column batches
+        const int batches = p.N >> 4, first = (batches + 1) >> 1;
+        const int c_begin = (warp >> 2) ? 16 * first : 0, c_end = (warp >> 2) ? p.N : 16 * first;
         for (int c0 = c_begin; c0 < c_end; c0 += 16) {
             uint32_t v[16];
             tmem_ld16(tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c0, v);
@@ -572,8 +574,8 @@ __global__ void toeplitz_prep_kernel(const uint8_t* __restrict__ tmpl, const Tmp
 
 // S = window sum, rsD = rsqrt(A*Q - S^2) (0 for an exactly flat window), per window position, for
 // every distinct template size in one launch (blockIdx.y = size).
-__global__ void window_moments_kernel(SatView sat, const SizeDesc* __restrict__ sizes, uint32_t* __restrict__ S,
-                                      float* __restrict__ rsD)
+__global__ void window_moments_kernel(SatView sat, const uint32_t* __restrict__ sat_q32, const SizeDesc* __restrict__ sizes,
+                                      uint32_t* __restrict__ S, float* __restrict__ rsD)
 {
     const SizeDesc sd = sizes[blockIdx.y];
     const int64_t n = (int64_t)sd.mh * sd.mw;
@@ -581,7 +583,8 @@ __global__ void window_moments_kernel(SatView sat, const SizeDesc* __restrict__ 
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
         const int y = (int)(idx / sd.mw), x = (int)(idx - (int64_t)y * sd.mw);
         const uint32_t s = sat_window_s(sat.s, sat.pitch, y, x, sd.h, sd.w);
-        const unsigned long long q = sat_window_q(sat.q, sat.pitch, y, x, sd.h, sd.w);
+        // window sums of squares < 2^32 on the tensor path (h*w <= 66051): the 32-bit wrap-around table is exact
+        const unsigned long long q = sat_window_s(sat_q32, sat.pitch, y, x, sd.h, sd.w);
         const unsigned long long d1 = area * q - (unsigned long long)s * s;
         S[sd.off + idx] = s;
         rsD[sd.off + idx] = d1 ? rsqrtf((float)d1) : 0.0f;
@@ -658,7 +661,7 @@ int launch_window_moments(mtm_ctx* ctx)
     int64_t n = 0;
     for (const SizeDesc& sd : ctx->h_sizes) n = std::max<int64_t>(n, (int64_t)sd.mh * sd.mw);
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 16));
-    window_moments_kernel<<<dim3(blocks, (unsigned)ctx->h_sizes.size()), 256, 0, ctx->stream>>>(sv, ctx->d_sizes, ctx->d_wS, ctx->d_wR);
+    window_moments_kernel<<<dim3(blocks, (unsigned)ctx->h_sizes.size()), 256, 0, ctx->stream>>>(sv, im.sat_q32, ctx->d_sizes, ctx->d_wS, ctx->d_wR);
     MTM_LAUNCH_CHECK(ctx);
     return MTM_OK;
 }
@@ -704,8 +707,27 @@ int launch_ncc_tc(mtm_ctx* ctx, const TcGroup& g)
     TcParams p{};
     p.img = im.pix; p.pitch = im.pitch; p.H = im.H; p.W = im.W;
     p.slabs = ctx->d_slabs + g.arena_off; p.slab_bytes = g.slab_bytes; p.a_kblk = g.a_kblk; p.nk = g.nk; p.ds = g.ds;
-    p.mode = g.mode; p.N = g.N; p.R = g.R; p.h = g.h; p.w = g.w;
+    p.mode = g.mode; p.h = g.h; p.w = g.w;
     p.mh = im.H - g.h_min + 1; p.mw = im.W - g.w_min + 1;      // tile grid covers the largest member map
+    // Tile height: the planned g.N is the largest that fits; a smaller multiple of 16 can cut the number
+    // of CTA waves (e.g. C2: 468 tiles of 256 rows = 1.58 waves of 296 slots -> 585 tiles of 208 rows =
+    // 1.98 waves).  Cost model: waves x (rows + fixed per-tile work expressed in rows).
+    const int xw_ = g.mode == 0 ? 16 : 128;
+    const int gx = (p.mw + xw_ - 1) / xw_;
+    const size_t ring = (size_t)TC_STAGES * g.ds * g.slab_bytes;
+    auto smem_for = [&](int n) { return (((size_t)2 * g.nk * (n + g.h - 1) * 16 + 127) & ~(size_t)127) + ring + 256; };
+    int bestN = g.N;
+    double best_cost = 1e300;
+    for (int n = g.N; n >= 32 && n >= g.N / 2; n -= 16) {
+        const int per_sm = (2 * smem_for(n) <= 226 * 1024) ? 2 : 1;          // TMEM (<= 256 columns) also allows 2
+        const long long tiles = (long long)gx * ((p.mh + n - 1) / n);
+        const long long waves = (tiles + (long long)per_sm * ctx->sm_count - 1) / ((long long)per_sm * ctx->sm_count);
+        const double cost = (double)waves * (n + 0.25 * g.h + 16.0) / per_sm;
+        if (cost < best_cost - 1e-9) { best_cost = cost; bestN = n; }
+    }
+    if (getenv("MTM_B200_FORCE_N")) bestN = g.N;
+    p.N = bestN; p.R = bestN + g.h - 1;
+    const size_t smem_bytes = smem_for(bestN);
     p.meta = ctx->d_meta; p.order = ctx->d_order + g.first; p.count = g.count;
     p.S = ctx->d_wS; p.rsD = ctx->d_wR; p.maps = ctx->d_maps;
     if (!ctx->tc_attr_set) {
@@ -713,8 +735,8 @@ int launch_ncc_tc(mtm_ctx* ctx, const TcGroup& g)
         ctx->tc_attr_set = true;
     }
     const int xw = g.mode == 0 ? 16 : 128;
-    dim3 grid((p.mw + xw - 1) / xw, (p.mh + g.N - 1) / g.N);
-    ncc_tc_kernel<<<grid, TC_THREADS, g.smem, ctx->stream>>>(p);
+    dim3 grid((p.mw + xw - 1) / xw, (p.mh + p.N - 1) / p.N);
+    ncc_tc_kernel<<<grid, TC_THREADS, smem_bytes, ctx->stream>>>(p);
     MTM_LAUNCH_CHECK(ctx);
     return MTM_OK;
 }

@@ -117,7 +117,8 @@ sat_rows_c1_kernel(const uint8_t* __restrict__ img, int64_t pitch, int H, int W,
 // blockIdx.y picks the table: 0..C-1 -> sat_s[c] (u32), C -> sat_q (u64).
 __global__ void __launch_bounds__(1024, 1)
 sat_cols_kernel(const uint32_t* __restrict__ scratch, int H, int W, int C, int SP,
-                uint32_t* __restrict__ sat_s, unsigned long long* __restrict__ sat_q, int64_t sat_pitch)
+                uint32_t* __restrict__ sat_s, unsigned long long* __restrict__ sat_q, uint32_t* __restrict__ sat_q32,
+                int64_t sat_pitch)
 {
     __shared__ unsigned long long part[32][33];
     const int cx = threadIdx.x, ry = threadIdx.y;
@@ -142,13 +143,13 @@ sat_cols_kernel(const uint32_t* __restrict__ scratch, int H, int W, int C, int S
     const int64_t sat_plane = (int64_t)(H + 1) * sat_pitch;
     uint32_t* ds = sat_s + (is_q ? 0 : table * sat_plane);
     if (ry == 0) {                                 // SAT row 0 is all zeros
-        if (is_q) sat_q[sx] = 0ull; else ds[sx] = 0u;
+        if (is_q) { sat_q[sx] = 0ull; sat_q32[sx] = 0u; } else ds[sx] = 0u;
     }
 #pragma unroll 8
     for (int y = y0; y < y1; ++y) {
         if (live) run += __ldg(src + (int64_t)y * SP);
         const int64_t o = (int64_t)(y + 1) * sat_pitch + sx;
-        if (is_q) sat_q[o] = run; else ds[o] = (uint32_t)run;
+        if (is_q) { sat_q[o] = run; sat_q32[o] = (uint32_t)run; } else ds[o] = (uint32_t)run;
     }
 }
 
@@ -221,7 +222,7 @@ int launch_build_sat(mtm_ctx* ctx)
     }
     MTM_LAUNCH_CHECK(ctx);
     dim3 g2((W + 1 + 31) / 32, C + 1), b2(32, 32);
-    sat_cols_kernel<<<g2, b2, 0, ctx->stream>>>(ctx->scratch, H, W, C, SP, im.sat_s, im.sat_q, im.sat_pitch);
+    sat_cols_kernel<<<g2, b2, 0, ctx->stream>>>(ctx->scratch, H, W, C, SP, im.sat_s, im.sat_q, im.sat_q32, im.sat_pitch);
     MTM_LAUNCH_CHECK(ctx);
     return MTM_OK;
 }
