@@ -1,8 +1,6 @@
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-timeout 300 python bench.py --cpu-steps 1 > gpurun_out/bench_r1_v11.json 2> gpurun_out/bench_err.log; tail -3 gpurun_out/bench_err.log; cat gpurun_out/bench_r1_v11.json
-timeout 300 python bench.py --contexts 1 --cpu-steps 1 > gpurun_out/bench_r1_v11_c1.json 2>> gpurun_out/bench_err.log; cat gpurun_out/bench_r1_v11_c1.json
-timeout 300 python bench.py --contexts 3 --cpu-steps 1 > gpurun_out/bench_r1_v11_c3.json 2>> gpurun_out/bench_err.log; cat gpurun_out/bench_r1_v11_c3.json
-timeout 300 python bench.py --workload C5 --contexts 1 --steps 16 --warmup 3 --cpu-steps 1 > gpurun_out/bench_r1_v11_C5.json 2>> gpurun_out/bench_err.log; cat gpurun_out/bench_r1_v11_C5.json
-timeout 300 python bench.py --workload C4 --contexts 1 --steps 50 --cpu-steps 1 > gpurun_out/bench_r1_v11_C4.json 2>> gpurun_out/bench_err.log; cat gpurun_out/bench_r1_v11_C4.json
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_final_C2.csv python bench.py --steps 3 --warmup 3 --cpu-steps 1 --contexts 1 > gpurun_out/ncu_bench.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:ncc_tc_kernel -s 6 -c 2 -o gpurun_out/prof_tc_final python bench.py --steps 3 --warmup 3 --cpu-steps 1 --contexts 1 > gpurun_out/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none -k regex:"peaks2d|finalize_small|sat_cols|window_moments" -s 8 -c 4 -o gpurun_out/prof_small_final python bench.py --steps 3 --warmup 3 --cpu-steps 1 --contexts 1 > gpurun_out/ncu_full2.log 2>&1
+ls -la gpurun_out | tail -8

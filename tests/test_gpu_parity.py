@@ -227,6 +227,24 @@ def test_match_templates_other_methods_vs_port(mtm, method, thr):
     assert_hits_equal(got1, want1)
 
 
+def test_hit_buffer_growth_beyond_device_capacity(mtm):
+    """> 65536 raw peaks: the device hit blocks are re-allocated and the search re-run (general
+    multi-kernel sort/NMS path); results must still equal the restated peak finder on the same map."""
+    from oracle import mtm_port, peaks
+    rng = np.random.default_rng(123)
+    img = rng.integers(0, 256, (820, 830), dtype=np.uint8)
+    t = rng.integers(0, 256, (3, 3), dtype=np.uint8)
+    got = mtm.findMatches([("n", t)], img, score_threshold=-1.0)
+    m = mtm.computeScoreMap(t, img)
+    want = peaks.peak_local_max(m, -1.0)
+    assert len(got) == len(want) > 65536
+    assert [(g[1][1], g[1][0]) for g in got] == [tuple(int(v) for v in p) for p in want.tolist()]
+    # and through NMS (N_object finite so the scan stops early)
+    top = mtm.matchTemplates([("n", t)], img, score_threshold=0.0, maxOverlap=0.0, N_object=40)
+    ref = mtm_port.nms([("n", (int(p[1]), int(p[0]), 3, 3), m[p[0], p[1]]) for p in want.tolist()], 0.0, False, 40, 0.0)
+    assert [(a[1]) for a in top] == [(b[1]) for b in ref]
+
+
 def test_match_templates_batch_equals_loop(mtm):
     """Pipelined batch entry point == the per-image calls (incl. a >1024-raw-peak image that
     falls back to the synchronous path, and searchBox offsets)."""
