@@ -96,6 +96,12 @@ int mtm_set_image_device(mtm_ctx* ctx, const void* d_pixels, int H, int W, int C
 int mtm_set_templates(mtm_ctx* ctx, int n, const void* const* pixels,
                       const int32_t* h, const int32_t* w, int C, int dtype);
 
+/* mtm_set_templates_masked: templates WITH masks, the `mask=` operand of cv2.matchTemplate
+ * (MTM/__init__.py:76-92, only honoured for TM_SQDIFF and TM_CCORR_NORMED).  masks[i] has the shape and
+ * dtype of pixels[i]; uint8 masks are binary (non-zero = use), float32 masks are weights (OpenCV). */
+int mtm_set_templates_masked(mtm_ctx* ctx, int n, const void* const* pixels, const void* const* masks,
+                             const int32_t* h, const int32_t* w, int C, int dtype);
+
 /* ---- the hot path ---------------------------------------------------------
  * mtm_score_map: cv2.matchTemplate(image, template, method) at
  * MTM/__init__.py:92 for template `tmpl`; writes (H-h+1)*(W-w+1) floats. */

@@ -42,6 +42,9 @@ _SIGNATURES = {
     "mtm_set_image_device": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64]),
     "mtm_set_templates": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(_P), ctypes.POINTER(ctypes.c_int32),
                                          ctypes.POINTER(ctypes.c_int32), ctypes.c_int, ctypes.c_int]),
+    "mtm_set_templates_masked": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(_P), ctypes.POINTER(_P),
+                                                ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
+                                                ctypes.c_int, ctypes.c_int]),
     "mtm_score_map": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, _P, ctypes.c_int64]),
     "mtm_find_matches": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int64, ctypes.c_double, _P, ctypes.c_int,
                                         ctypes.POINTER(ctypes.c_int)]),
@@ -190,6 +193,21 @@ class Context:
         ws = (ctypes.c_int32 * n)(*[a.shape[1] for a in arrs])
         self._check(self._lib.mtm_set_templates(self._h, n, ptrs, hs, ws, C, code))
         self._tmpl_shapes = [a.shape[:2] for a in arrs]
+
+    def set_templates_masked(self, templates, masks):
+        arrs = [np.ascontiguousarray(t) for t in templates]
+        mks = [np.ascontiguousarray(m) for m in masks]
+        n = len(arrs)
+        C = 1 if arrs[0].ndim == 2 else arrs[0].shape[2]
+        code = _dtype_code(arrs[0])
+        for a, m in zip(arrs, mks):
+            if (1 if a.ndim == 2 else a.shape[2]) != C or _dtype_code(a) != code or m.shape != a.shape or m.dtype != a.dtype:
+                raise ValueError("templates and masks must share shape, dtype and channel count")
+        tp = (_P * n)(*[a.ctypes.data for a in arrs])
+        mp = (_P * n)(*[m.ctypes.data for m in mks])
+        hs = (ctypes.c_int32 * n)(*[a.shape[0] for a in arrs])
+        ws = (ctypes.c_int32 * n)(*[a.shape[1] for a in arrs])
+        self._check(self._lib.mtm_set_templates_masked(self._h, n, tp, mp, hs, ws, C, code))
 
     # -- hot path ---------------------------------------------------------------
     def score_map(self, tmpl, method, map_shape):

@@ -51,8 +51,6 @@ def _mask_policy(template, mask, method):
 
 
 def _require_gpu_support(image, templates, mask=None):
-    if mask is not None:
-        raise NotImplementedError("masked template matching (methods 0/3 with a mask) has no B200 kernel yet")
     if image.dtype not in (np.uint8, np.float32) or any(t.dtype != image.dtype for t in templates):
         raise NotImplementedError("unsupported dtype combination %s / %s" % (image.dtype, [t.dtype for t in templates]))
 
@@ -72,8 +70,20 @@ def computeScoreMap(template, image, method=TM_CCOEFF_NORMED, mask=None, *, cont
     ctx = context or _native.default_context()
     with ctx.lock:
         ctx.set_image(image)
-        ctx.set_templates([template])
+        _upload_templates(ctx, [template], [mask])
         return ctx.score_map(0, method, (image.shape[0] - template.shape[0] + 1, image.shape[1] - template.shape[1] + 1))
+
+
+def _upload_templates(ctx, arrays, masks):
+    """Plain or masked template upload.  When at least one template carries a (valid) mask every
+    template goes through the masked kernels; templates without one get an all-ones mask, for which
+    OpenCV's masked and plain formulas of TM_SQDIFF / TM_CCORR_NORMED coincide."""
+    if all(m is None for m in masks):
+        ctx.set_templates(arrays)
+        return
+    one = 255 if arrays[0].dtype == np.uint8 else 1
+    full = [m if m is not None else np.full(a.shape, one, a.dtype) for a, m in zip(arrays, masks)]
+    ctx.set_templates_masked(arrays, full)
 
 
 def _validate_search(listTemplates, image, N_object, searchBox):
@@ -106,7 +116,7 @@ def _validate_search(listTemplates, image, N_object, searchBox):
 def _prepare(listTemplates, image, method):
     """Per-template mask / dtype policy of _multi_compute + computeScoreMap
     (MTM/__init__.py:207-222, 67-88) applied to the whole list."""
-    names, arrays = [], []
+    names, arrays, masks = [], [], []
     img = image
     for tempTuple in listTemplates:
         name, template = tempTuple[:2]
@@ -124,7 +134,8 @@ def _prepare(listTemplates, image, method):
         img = img_t
         names.append(name)
         arrays.append(template)
-    return names, arrays, img
+        masks.append(mask)
+    return names, arrays, img, masks
 
 
 def _native_n_object(N_object):
@@ -149,11 +160,11 @@ def findMatches(listTemplates, image, method=TM_CCOEFF_NORMED, N_object=_INF, sc
     image, xOffset, yOffset = _validate_search(listTemplates, image, N_object, searchBox)
     if len(listTemplates) == 0:
         return []
-    names, arrays, img = _prepare(listTemplates, image, method)
+    names, arrays, img, masks = _prepare(listTemplates, image, method)
     ctx = context or _native.default_context()
     with ctx.lock:
         ctx.set_image(img)
-        ctx.set_templates(arrays)
+        _upload_templates(ctx, arrays, masks)
         raw = ctx.find_matches(method, _native_n_object(N_object), score_threshold)
     return _to_hits(raw, names, xOffset, yOffset)
 
@@ -174,7 +185,7 @@ def matchTemplates(listTemplates, image, method=TM_CCOEFF_NORMED, N_object=_INF,
     crop, xOffset, yOffset = _validate_search(listTemplates, image, N_object, searchBox)
     if len(listTemplates) == 0:
         return []
-    names, arrays, img = _prepare(listTemplates, crop, method)
+    names, arrays, img, masks = _prepare(listTemplates, crop, method)
     finite = N_object != _INF
     nms_threshold = (1 - score_threshold) if method == 1 else score_threshold
     if (finite and N_object < 1) or nms_threshold < 0:
@@ -186,7 +197,7 @@ def matchTemplates(listTemplates, image, method=TM_CCOEFF_NORMED, N_object=_INF,
     ctx = context or _native.default_context()
     with ctx.lock:
         ctx.set_image(img)
-        ctx.set_templates(arrays)
+        _upload_templates(ctx, arrays, masks)
         raw = ctx.match_templates(method, n_dev, score_threshold, maxOverlap)
     return _to_hits(raw, names, xOffset, yOffset)
 
@@ -223,9 +234,9 @@ def matchTemplatesBatch(listTemplates, images, method=TM_CCOEFF_NORMED, N_object
     with ctx.lock:
         for i, image in enumerate(images):
             crop, xOffset, yOffset = _validate_search(listTemplates, image, N_object, searchBox)
-            nm, arrays, img = _prepare(listTemplates, crop, method)
+            nm, arrays, img, masks = _prepare(listTemplates, crop, method)
             if names is None:
-                ctx.set_templates(arrays)          # templates are the same objects for every image
+                _upload_templates(ctx, arrays, masks)   # templates are the same objects for every image
                 names = nm
             slot = i % depth
             if slot in pending:

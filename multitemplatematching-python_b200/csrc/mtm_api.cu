@@ -165,6 +165,7 @@ int mtm_destroy(mtm_ctx* ctx)
     cudaFree(ctx->d_meta); cudaFree(ctx->d_tmpl); cudaFree(ctx->d_maps); cudaFree(ctx->d_order);
     cudaFree(ctx->d_blockA); cudaFree(ctx->d_blockB); cudaFree(ctx->d_keep);
     cudaFree(ctx->d_nontrivial); cudaFree(ctx->d_best);
+    cudaFree(ctx->img.pixf2); cudaFree(ctx->d_raw_t); cudaFree(ctx->d_raw_m); cudaFree(ctx->d_maps2);
     cudaFree(ctx->img.pixf); cudaFree(ctx->img.satf_s); cudaFree(ctx->img.satf_q); cudaFree(ctx->d_tmpl_centred);
     cudaFree(ctx->d_slabs); cudaFree(ctx->d_wS); cudaFree(ctx->d_wR); cudaFree(ctx->d_sizes);
     for (int k = 0; k < MTM_MAX_INFLIGHT; ++k) { cudaFree(ctx->d_slot[k]); cudaFreeHost(ctx->h_slot[k]); if (ctx->ev_slot[k]) cudaEventDestroy(ctx->ev_slot[k]); }
@@ -265,6 +266,7 @@ static int set_image_impl(mtm_ctx* ctx, const void* pixels, int H, int W, int C,
         ctx->img_dtype = dtype;
         ctx->geometry_valid = false;
         ctx->moments_valid = false;
+        ctx->masked_image_valid = false;
         MTM_TRY(launch_build_sat_f32(ctx));
         return MTM_OK;
     }
@@ -286,6 +288,7 @@ static int set_image_impl(mtm_ctx* ctx, const void* pixels, int H, int W, int C,
     ctx->img_dtype = dtype;
     ctx->geometry_valid = false;
     ctx->moments_valid = false;
+    ctx->masked_image_valid = false;
     MTM_TRY(launch_build_sat(ctx));
     g_marks.mark(ctx, "sat");
     return MTM_OK;
@@ -297,7 +300,7 @@ static int ensure_geometry(mtm_ctx* ctx)
     if (ctx->n_tmpl == 0) return mtm_fail(ctx, MTM_ERR_INVALID, "no templates set (call mtm_set_templates first)");
     if (ctx->geometry_valid) return MTM_OK;
     MTM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // h_geom (pinned) may still feed an earlier async copy
-    if (ctx->tmpl_C != ctx->img.C || ctx->tmpl_dtype != ctx->img_dtype)
+    if (ctx->tmpl_C != ctx->img.C || (!ctx->masked && ctx->tmpl_dtype != ctx->img_dtype))
         return mtm_fail(ctx, MTM_ERR_INVALID, "image and templates differ in channel count or dtype");
     const int n = ctx->n_tmpl;
     int64_t off = 0;
@@ -427,12 +430,43 @@ static bool use_tensor_path(const mtm_ctx* ctx, int method)
     return true;
 }
 
+// Masked templates (methods 0 / 3): two plain fp32 correlations per template + the combine kernel.
+static int compute_maps_masked(mtm_ctx* ctx, int method)
+{
+    if (method != MTM_TM_SQDIFF && method != MTM_TM_CCORR_NORMED)
+        return mtm_fail(ctx, MTM_ERR_INVALID, "masks are only defined for TM_SQDIFF (0) and TM_CCORR_NORMED (3)");
+    ImageDev& im = ctx->img;
+    if (!ctx->masked_image_valid) {
+        if (ctx->img_dtype == MTM_U8) {
+            im.pitch_e = ((int64_t)im.W * im.C + 3) / 4 * 4;
+            MTM_TRY(mtm_reserve(ctx, im.pixf, ctx->imgf_cap, (size_t)(im.H * im.pitch_e + 64)));
+        }
+        MTM_TRY(mtm_reserve(ctx, im.pixf2, ctx->pixf2_cap, (size_t)(im.H * im.pitch_e + 64)));
+        MTM_TRY(launch_masked_image(ctx));
+        ctx->masked_image_valid = true;
+    }
+    MTM_TRY(mtm_reserve(ctx, ctx->d_maps2, ctx->maps2_cap, (size_t)ctx->maps_total));
+    const int n = ctx->n_tmpl;
+    int i = 0;
+    while (i < n) {
+        const TmplMeta& a = ctx->h_meta[ctx->h_order[i]];
+        int j = i + 1;
+        while (j < n && ctx->h_meta[ctx->h_order[j]].h == a.h && ctx->h_meta[ctx->h_order[j]].w == a.w) ++j;
+        MTM_TRY(launch_ncc_direct_f32(ctx, MTM_TM_CCORR, i, j - i, im.pixf, ctx->d_tmpl, ctx->d_maps));
+        MTM_TRY(launch_ncc_direct_f32(ctx, MTM_TM_CCORR, i, j - i, im.pixf2, ctx->d_tmpl_centred, ctx->d_maps2));
+        i = j;
+    }
+    MTM_TRY(launch_masked_combine(ctx, method, ctx->d_maps2));
+    return MTM_OK;
+}
+
 // Score maps of every template (tmpl < 0) or of one template, grouped by template size.
 static int compute_maps(mtm_ctx* ctx, int method, int tmpl)
 {
     if (method < 0 || method > 5) return mtm_fail(ctx, MTM_ERR_INVALID, "unknown method %d", method);
     const int n = ctx->n_tmpl;
     int i = 0;
+    if (ctx->masked) return compute_maps_masked(ctx, method);
     const bool tensor = use_tensor_path(ctx, method);
     if (!tensor && ctx->path == MTM_PATH_TENSOR)
         return mtm_fail(ctx, MTM_ERR_UNSUPPORTED, "tensor-core path requested but not available for these inputs/method");
@@ -587,6 +621,7 @@ int mtm_set_templates(mtm_ctx* ctx, int n, const void* const* pixels, const int3
     ctx->ctr.h2d_bytes += (int64_t)total + (int64_t)n * (sizeof(TmplMeta) + sizeof(int32_t));
     ctx->n_tmpl = n; ctx->tmpl_C = C; ctx->tmpl_dtype = dtype;
     ctx->geometry_valid = false;
+    ctx->masked = false;
     if (dtype == MTM_F32) {
         MTM_TRY(mtm_reserve(ctx, ctx->d_tmpl_centred, ctx->tmplc_cap, total + 64));
         MTM_TRY(launch_tmpl_stats_f32(ctx));
@@ -595,6 +630,64 @@ int mtm_set_templates(mtm_ctx* ctx, int n, const void* const* pixels, const int3
     }
     MTM_TRY(plan_tensor_path(ctx));
     ctx->tmpl_hash_valid = true;
+    return MTM_OK;
+}
+
+int mtm_set_templates_masked(mtm_ctx* ctx, int n, const void* const* pixels, const void* const* masks,
+                             const int32_t* h, const int32_t* w, int C, int dtype)
+{
+    MTM_ENTER(ctx);
+    if (n <= 0 || !pixels || !masks || !h || !w) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_templates_masked: empty template list");
+    if (C < 1 || C > MTM_MAX_CH || C == 2) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_templates_masked: %d channels (1, 3, 4 supported)", C);
+    if (dtype != MTM_U8 && dtype != MTM_F32) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_templates_masked: unknown dtype %d", dtype);
+    const int esz = dtype == MTM_F32 ? 4 : 1;
+    MTM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->tmpl_hash_valid = false;
+    ctx->h_meta.assign(n, TmplMeta{});
+    size_t total = 0;                                        // bytes of the float32 arenas (T*M^2 and M^2)
+    for (int t = 0; t < n; ++t) {
+        if (!pixels[t] || !masks[t] || h[t] <= 0 || w[t] <= 0)
+            return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_templates_masked: template %d is empty", t);
+        TmplMeta& m = ctx->h_meta[t];
+        m.h = h[t]; m.w = w[t];
+        m.wp = w[t] * C * 4;
+        m.pix_off = (int64_t)total;
+        total += ((size_t)m.wp * m.h + 15) / 16 * 16;
+    }
+    const size_t raw_total = total / 4 * esz;
+    MTM_TRY(reserve_pinned(ctx, ctx->h_tmpl_stage, ctx->tmpl_stage_cap, 2 * raw_total + 64));
+    MTM_TRY(reserve_pinned(ctx, ctx->h_geom, ctx->geom_cap, (size_t)n));
+    memset(ctx->h_tmpl_stage, 0, 2 * raw_total);
+    for (int t = 0; t < n; ++t) {
+        const TmplMeta& m = ctx->h_meta[t];
+        const size_t off = (size_t)m.pix_off / 4 * esz, bytes = (size_t)m.h * m.w * C * esz;
+        memcpy(ctx->h_tmpl_stage + off, pixels[t], bytes);
+        memcpy(ctx->h_tmpl_stage + raw_total + off, masks[t], bytes);
+    }
+    MTM_TRY(mtm_reserve(ctx, ctx->d_raw_t, ctx->raw_t_cap, raw_total + 64));
+    MTM_TRY(mtm_reserve(ctx, ctx->d_raw_m, ctx->raw_m_cap, raw_total + 64));
+    MTM_TRY(mtm_reserve(ctx, ctx->d_tmpl, ctx->tmpl_cap, total + 64));
+    MTM_TRY(mtm_reserve(ctx, ctx->d_tmpl_centred, ctx->tmplc_cap, total + 64));
+    MTM_TRY(mtm_reserve(ctx, ctx->d_meta, ctx->meta_cap, (size_t)n));
+    MTM_TRY(mtm_reserve(ctx, ctx->d_order, ctx->order_cap, (size_t)n));
+    MTM_TRY(mtm_reserve(ctx, ctx->d_nontrivial, ctx->per_tmpl_cap, (size_t)n));
+    MTM_TRY(mtm_reserve(ctx, ctx->d_best, ctx->best_cap, (size_t)n));
+    MTM_CUDA(ctx, cudaMemcpyAsync(ctx->d_raw_t, ctx->h_tmpl_stage, raw_total, cudaMemcpyHostToDevice, ctx->stream));
+    MTM_CUDA(ctx, cudaMemcpyAsync(ctx->d_raw_m, ctx->h_tmpl_stage + raw_total, raw_total, cudaMemcpyHostToDevice, ctx->stream));
+    MTM_CUDA(ctx, cudaMemcpyAsync(ctx->d_meta, ctx->h_meta.data(), (size_t)n * sizeof(TmplMeta), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h_order.resize(n);
+    for (int t = 0; t < n; ++t) ctx->h_order[t] = t;
+    std::stable_sort(ctx->h_order.begin(), ctx->h_order.end(), [&](int a, int b) {
+        const TmplMeta &x = ctx->h_meta[a], &y = ctx->h_meta[b];
+        return x.h != y.h ? x.h < y.h : x.w < y.w;
+    });
+    MTM_CUDA(ctx, cudaMemcpyAsync(ctx->d_order, ctx->h_order.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->ctr.h2d_bytes += (int64_t)2 * raw_total + (int64_t)n * (sizeof(TmplMeta) + sizeof(int32_t));
+    ctx->n_tmpl = n; ctx->tmpl_C = C; ctx->tmpl_dtype = MTM_F32;
+    ctx->geometry_valid = false;
+    ctx->masked = true;
+    ctx->tc_groups.clear(); ctx->tc_ready = false;
+    MTM_TRY(launch_masked_prep(ctx, ctx->d_raw_t, ctx->d_raw_m, dtype == MTM_F32));
     return MTM_OK;
 }
 

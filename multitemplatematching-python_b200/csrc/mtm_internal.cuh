@@ -74,6 +74,7 @@ struct ImageDev {
     int64_t sat_pitch = 0;       // elements
     // float32 images (MTM/__init__.py:71-74): pixels + float64 summed-area tables
     float* pixf = nullptr; int64_t pitch_e = 0;
+    float* pixf2 = nullptr;              // image squared (masked matching)
     double* satf_s = nullptr; double* satf_q = nullptr;
 };
 
@@ -107,6 +108,10 @@ struct mtm_ctx {
     int tmpl_C = 0, tmpl_dtype = -1;
     uint64_t tmpl_hash = 0; bool tmpl_hash_valid = false;   // content hash of the resident template set
     bool geometry_valid = false;         // map offsets computed for (image, templates)
+    bool masked = false;                 // templates carry masks (methods 0 / 3): d_tmpl = T*M^2, d_tmpl_centred = M^2
+    bool masked_image_valid = false;     // pixf / pixf2 hold the current image
+    uint8_t* d_raw_t = nullptr; uint8_t* d_raw_m = nullptr; size_t raw_t_cap = 0, raw_m_cap = 0;
+    float* d_maps2 = nullptr; size_t maps2_cap = 0; size_t pixf2_cap = 0;
 
     // score maps
     float* d_maps = nullptr; size_t maps_cap = 0;   // elements
@@ -174,7 +179,12 @@ int launch_ncc_direct(mtm_ctx* ctx, int method, int first, int count);
 // float32 branch (ncc_float.cu)
 int launch_build_sat_f32(mtm_ctx* ctx);
 int launch_tmpl_stats_f32(mtm_ctx* ctx);
-int launch_ncc_direct_f32(mtm_ctx* ctx, int method, int first, int count);
+int launch_ncc_direct_f32(mtm_ctx* ctx, int method, int first, int count, const float* img_override = nullptr,
+                          const uint8_t* tmpl_override = nullptr, float* maps_override = nullptr);
+// masked matching, methods 0 / 3 (ncc_float.cu)
+int launch_masked_prep(mtm_ctx* ctx, const uint8_t* d_raw_t, const uint8_t* d_raw_m, int is_f32);
+int launch_masked_image(mtm_ctx* ctx);
+int launch_masked_combine(mtm_ctx* ctx, int method, const float* mapsB);
 // tensor-core path
 bool tc_path_supported(const mtm_ctx* ctx, int method, int h, int w);
 bool tc_plan_group(int mode, int h, int w, TcGroup& g);

@@ -10,6 +10,7 @@
 // Bound: fp32 FMA pipe.  A tensor-core (bf16x3 / tf32) variant is the next step.
 #include "mtm_internal.cuh"
 #include "ncc_epilogue.cuh"
+#include <algorithm>
 
 namespace {
 
@@ -272,9 +273,15 @@ ncc_direct_f32_kernel(const FloatParams p)
             const int x = bx0 + XO * tx + i;
             if (x >= p.mw) continue;
             double S[C];
+            double Q = 0.0;
+            if (p.method != MTM_TM_CCORR) {                       // plain correlation needs no window statistics
 #pragma unroll
-            for (int c = 0; c < C; ++c) S[c] = satf_window(p.sat_s + c * p.sat_plane, p.sat_pitch, y, x, p.h, p.w);
-            const double Q = satf_window(p.sat_q, p.sat_pitch, y, x, p.h, p.w);
+                for (int c = 0; c < C; ++c) S[c] = satf_window(p.sat_s + c * p.sat_plane, p.sat_pitch, y, x, p.h, p.w);
+                Q = satf_window(p.sat_q, p.sat_pitch, y, x, p.h, p.w);
+            } else {
+#pragma unroll
+                for (int c = 0; c < C; ++c) S[c] = 0.0;
+            }
 #pragma unroll
             for (int t = 0; t < TT; ++t) {
                 if (t0 + t >= p.count) break;
@@ -310,7 +317,111 @@ int dispatch_f(mtm_ctx* ctx, const FloatParams& p, int TT, dim3 grid, size_t sme
     }
 }
 
+// ------------------------------------------------------------------ masked matching (methods 0 / 3)
+// OpenCV matchTemplateMask (third-party; reached from MTM/__init__.py:92 with mask=...):
+//   TM_SQDIFF        R = sum I^2 M^2 - 2 sum I (T M^2) + sum (T M)^2
+//   TM_CCORR_NORMED  R = sum I (T M^2) / sqrt( sum (T M)^2 * sum I^2 M^2 )
+// uint8 masks are binary (non-zero -> 1), float32 masks are weights; everything is float32.
+
+// raw template + mask (u8 or f32) -> T*M^2 into `tm2`, M^2 into `m2` (float layouts of the template arena);
+// meta.sum2 := sum (T*M)^2 in float64.  One block per template.
+__global__ void masked_prep_kernel(const uint8_t* __restrict__ raw_t, const uint8_t* __restrict__ raw_m, int is_f32,
+                                   float* __restrict__ tm2, float* __restrict__ m2, TmplMeta* __restrict__ meta, int C)
+{
+    TmplMeta& m = meta[blockIdx.x];
+    const int rowe = m.wp >> 2, n = m.h * m.w * C, we = m.w * C;
+    const int64_t raw_off = m.pix_off / 4 * (is_f32 ? 4 : 1);     // raw arrays are packed with the element size
+    float* q1 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(tm2) + m.pix_off);
+    float* q2 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(m2) + m.pix_off);
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int y = i / we, e = i - y * we;
+        float t, k;
+        if (is_f32) {
+            t = reinterpret_cast<const float*>(raw_t + raw_off)[(int64_t)y * we + e];
+            k = reinterpret_cast<const float*>(raw_m + raw_off)[(int64_t)y * we + e];
+        } else {
+            t = (float)raw_t[raw_off + (int64_t)y * we + e];
+            k = raw_m[raw_off + (int64_t)y * we + e] ? 1.0f : 0.0f;
+        }
+        const float tm = t * k;                                    // templ.mul(mask)
+        q1[(int64_t)y * rowe + e] = t * (k * k);                   // templ.mul(mask.mul(mask))
+        q2[(int64_t)y * rowe + e] = k * k;
+        acc += (double)tm * (double)tm;
+    }
+    __shared__ double red[32];
+    for (int d = 16; d; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) tot += red[k];
+        m.sum2 = tot;                                              // templ2_mask2_sum
+        m.is_const = 0; m.inv_area = 1.0 / ((double)m.h * m.w);
+    }
+}
+
+__global__ void u8_to_f32_sq_kernel(const uint8_t* __restrict__ src, int64_t src_pitch, const float* __restrict__ srcf,
+                                    float* __restrict__ dst, float* __restrict__ dst2, int64_t pitch_e, int H, int WE)
+{
+    const int64_t n = (int64_t)H * WE;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int y = (int)(i / WE), e = (int)(i - (int64_t)y * WE);
+        const float v = src ? (float)src[(int64_t)y * src_pitch + e] : srcf[(int64_t)y * pitch_e + e];
+        if (src) dst[(int64_t)y * pitch_e + e] = v;
+        dst2[(int64_t)y * pitch_e + e] = v * v;
+    }
+}
+
+// A = corr(I, T M^2), B = corr(I^2, M^2) (both fp32 maps) -> the masked score, in place into A.
+__global__ void masked_combine_kernel(float* __restrict__ A, const float* __restrict__ B, const TmplMeta* __restrict__ meta,
+                                      int method)
+{
+    const TmplMeta& tm = meta[blockIdx.y];
+    const int64_t n = (int64_t)tm.mh * tm.mw;
+    const double t2 = tm.sum2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float a = A[tm.map_off + i], b = B[tm.map_off + i];
+        float r;
+        if (method == MTM_TM_SQDIFF) r = (float)(-2.0 * (double)a + (double)b + t2);
+        else r = a / sqrtf((float)(t2 * (double)b));
+        A[tm.map_off + i] = r;
+    }
+}
+
 }  // namespace
+
+int launch_masked_prep(mtm_ctx* ctx, const uint8_t* d_raw_t, const uint8_t* d_raw_m, int is_f32)
+{
+    masked_prep_kernel<<<ctx->n_tmpl, 256, 0, ctx->stream>>>(d_raw_t, d_raw_m, is_f32, reinterpret_cast<float*>(ctx->d_tmpl),
+                                                           reinterpret_cast<float*>(ctx->d_tmpl_centred), ctx->d_meta, ctx->tmpl_C);
+    MTM_LAUNCH_CHECK(ctx);
+    return MTM_OK;
+}
+
+// float image (and its square) for the masked path; src is the u8 image or (srcf) the float image already resident
+int launch_masked_image(mtm_ctx* ctx)
+{
+    ImageDev& im = ctx->img;
+    const int WE = im.W * im.C;
+    const int64_t n = (int64_t)im.H * WE;
+    const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 16);
+    const bool from_u8 = (ctx->img_dtype == MTM_U8);
+    u8_to_f32_sq_kernel<<<blocks, 256, 0, ctx->stream>>>(from_u8 ? im.pix : nullptr, im.pitch, im.pixf, im.pixf, im.pixf2,
+                                                        im.pitch_e, im.H, WE);
+    MTM_LAUNCH_CHECK(ctx);
+    return MTM_OK;
+}
+
+int launch_masked_combine(mtm_ctx* ctx, int method, const float* mapsB)
+{
+    int64_t max_px = 1;
+    for (int t = 0; t < ctx->n_tmpl; ++t) max_px = std::max<int64_t>(max_px, (int64_t)ctx->h_meta[t].mh * ctx->h_meta[t].mw);
+    const int blocks = (int)std::min<int64_t>((max_px + 255) / 256, (int64_t)ctx->sm_count * 8);
+    masked_combine_kernel<<<dim3(blocks, ctx->n_tmpl), 256, 0, ctx->stream>>>(ctx->d_maps, mapsB, ctx->d_meta, method);
+    MTM_LAUNCH_CHECK(ctx);
+    return MTM_OK;
+}
 
 int launch_build_sat_f32(mtm_ctx* ctx)
 {
@@ -339,16 +450,19 @@ int launch_tmpl_stats_f32(mtm_ctx* ctx)
 }
 
 // Score maps of templates d_order[first .. first+count) (same size) for float32 inputs.
-int launch_ncc_direct_f32(mtm_ctx* ctx, int method, int first, int count)
+// img_override / tmpl_override / maps_override: the masked path (ncc_masked) runs two plain correlations
+// (image x T*M^2 and image^2 x M^2) through this kernel with method TM_CCORR.
+int launch_ncc_direct_f32(mtm_ctx* ctx, int method, int first, int count, const float* img_override,
+                          const uint8_t* tmpl_override, float* maps_override)
 {
     const ImageDev& im = ctx->img;
     const TmplMeta& m0 = ctx->h_meta[ctx->h_order[first]];
     FloatParams p{};
-    p.img = im.pixf; p.pitch_e = im.pitch_e; p.H = im.H; p.W = im.W;
+    p.img = img_override ? img_override : im.pixf; p.pitch_e = im.pitch_e; p.H = im.H; p.W = im.W;
     p.sat_s = im.satf_s; p.sat_q = im.satf_q; p.sat_pitch = im.sat_pitch; p.sat_plane = (int64_t)(im.H + 1) * im.sat_pitch;
-    p.centred = (method == MTM_TM_CCOEFF || method == MTM_TM_CCOEFF_NORMED) ? 1 : 0;
-    p.tmpl = reinterpret_cast<const float*>(p.centred ? ctx->d_tmpl_centred : ctx->d_tmpl);
-    p.meta = ctx->d_meta; p.order = ctx->d_order + first; p.maps = ctx->d_maps;
+    p.centred = (!tmpl_override && (method == MTM_TM_CCOEFF || method == MTM_TM_CCOEFF_NORMED)) ? 1 : 0;
+    p.tmpl = reinterpret_cast<const float*>(tmpl_override ? tmpl_override : (p.centred ? ctx->d_tmpl_centred : ctx->d_tmpl));
+    p.meta = ctx->d_meta; p.order = ctx->d_order + first; p.maps = maps_override ? maps_override : ctx->d_maps;
     p.count = count; p.h = m0.h; p.w = m0.w; p.mh = m0.mh; p.mw = m0.mw; p.method = method;
     const int C = im.C;
     const int we4 = (m0.w * C + 3) & ~3;

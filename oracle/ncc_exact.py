@@ -178,3 +178,42 @@ def match_template_exact(image, templ, method=TM_CCOEFF_NORMED, use_fft=None):
     cc = cc_fft(I, T) if use_fft else cc_direct(I, T)
     S, Q = window_sums(I, h, w)
     return epilogue(cc, S, Q, T, method)
+
+
+def _corr_valid_f64(I, K):
+    """sum_c sum I[y+dy, x+dx, c] * K[dy, dx, c] ('valid' region) in float64 via FFT."""
+    from scipy import fft as sfft
+    I = _as3(I).astype(np.float64)
+    K = _as3(K).astype(np.float64)
+    H, W, C = I.shape
+    h, w, _ = K.shape
+    fh, fw = sfft.next_fast_len(H, real=True), sfft.next_fast_len(W, real=True)
+    acc = np.zeros((H - h + 1, W - w + 1), np.float64)
+    for c in range(C):
+        Fi = sfft.rfft2(I[:, :, c], s=(fh, fw))
+        Fk = sfft.rfft2(K[::-1, ::-1, c], s=(fh, fw))
+        acc += sfft.irfft2(Fi * Fk, s=(fh, fw))[h - 1:H, w - 1:W]
+    return acc
+
+
+def match_template_masked_exact(image, templ, mask, method):
+    """``cv2.matchTemplate(image, templ, method, mask=mask)`` for TM_SQDIFF (0) and TM_CCORR_NORMED (3):
+    OpenCV ``matchTemplateMask`` (templmatch.cpp) restated in float64.  uint8 masks are binary
+    (non-zero -> 1), float32 masks are weights.  Reached from ``MTM/__init__.py:92`` when a template
+    tuple carries a mask and the method is 0 or 3 (``MTM/__init__.py:76-88, 213-217``)."""
+    I = _as3(image).astype(np.float64)
+    T = _as3(templ).astype(np.float64)
+    M = _as3(mask)
+    M = (M > 0).astype(np.float64) if M.dtype == np.uint8 else M.astype(np.float64)
+    if M.shape[2] == 1 and T.shape[2] > 1:
+        M = np.repeat(M, T.shape[2], axis=2)
+    M2 = M * M
+    cc = _corr_valid_f64(I, T * M2)
+    q = _corr_valid_f64(I * I, M2)
+    t2 = float(((T * M) ** 2).sum())
+    if method == TM_SQDIFF:
+        return (q - 2.0 * cc + t2).astype(np.float32)
+    if method == TM_CCORR_NORMED:
+        with np.errstate(divide="ignore", invalid="ignore"):
+            return (cc / np.sqrt(t2 * q)).astype(np.float32)
+    raise ValueError("masks are only defined for methods 0 and 3")

@@ -95,6 +95,24 @@ def test_exact_ncc_float32_vs_cv2(method):
     assert np.max(np.abs(exact.astype(np.float64) - cv)) <= 2e-5 * scale
 
 
+@pytest.mark.parametrize("method", [0, 3])
+def test_masked_restatement_vs_cv2(method):
+    """OpenCV matchTemplateMask (uint8 binary masks, float32 weight masks, 1 and 3 channels)."""
+    from oracle import ncc_exact
+    rng = np.random.default_rng(200 + method)
+    for shape_c in ((), (3,)):
+        img = rng.integers(0, 256, (50, 64) + shape_c, dtype=np.uint8)
+        t = rng.integers(0, 256, (11, 15) + shape_c, dtype=np.uint8)
+        m8 = (rng.random((11, 15) + shape_c) > 0.3).astype(np.uint8) * 255
+        got = ncc_exact.match_template_masked_exact(img, t, m8, method)
+        cv = cv2.matchTemplate(img, t, method, mask=m8)
+        assert np.max(np.abs(got - cv)) <= 2e-6 * max(1.0, float(np.abs(cv).max()))
+        mf = rng.random((11, 15) + shape_c).astype(np.float32)
+        got = ncc_exact.match_template_masked_exact(img.astype(np.float32), t.astype(np.float32), mf, method)
+        cv = cv2.matchTemplate(img.astype(np.float32), t.astype(np.float32), method, mask=mf)
+        assert np.max(np.abs(got - cv)) <= 2e-6 * max(1.0, float(np.abs(cv).max()))
+
+
 def test_exact_ncc_degenerate_rules():
     from oracle import ncc_exact
     img = np.full((30, 40), 9, np.uint8)
