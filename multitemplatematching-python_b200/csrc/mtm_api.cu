@@ -150,6 +150,8 @@ int mtm_create(int device, mtm_ctx** out)
     for (int k = 0; k < MTM_NCC_RING; ++k)
         for (int j = 0; j < 2; ++j)
             if ((e = cudaEventCreate(&ctx->ev_ncc[k][j])) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_cand), (size_t)MTM_CAND_CAP * sizeof(DevHit))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_cand_count), 64)) != cudaSuccess) return bail("cudaMalloc", e);
     int rc = reserve_hits(ctx, 1 << 16);
     if (rc != MTM_OK) { g_create_err = ctx->err; mtm_destroy(ctx); return rc; }
     *out = ctx;
@@ -164,7 +166,7 @@ int mtm_destroy(mtm_ctx* ctx)
     cudaFree(ctx->img.pix); cudaFree(ctx->img.sat_s); cudaFree(ctx->img.sat_q); cudaFree(ctx->img.sat_q32); cudaFree(ctx->scratch);
     cudaFree(ctx->d_meta); cudaFree(ctx->d_tmpl); cudaFree(ctx->d_maps); cudaFree(ctx->d_order);
     cudaFree(ctx->d_blockA); cudaFree(ctx->d_blockB); cudaFree(ctx->d_keep);
-    cudaFree(ctx->d_nontrivial); cudaFree(ctx->d_best);
+    cudaFree(ctx->d_nontrivial); cudaFree(ctx->d_best); cudaFree(ctx->d_cand); cudaFree(ctx->d_cand_count);
     cudaFree(ctx->img.pixf2); cudaFree(ctx->d_raw_t); cudaFree(ctx->d_raw_m); cudaFree(ctx->d_maps2);
     cudaFree(ctx->img.pixf); cudaFree(ctx->img.satf_s); cudaFree(ctx->img.satf_q); cudaFree(ctx->d_tmpl_centred);
     cudaFree(ctx->d_slabs); cudaFree(ctx->d_wS); cudaFree(ctx->d_wR); cudaFree(ctx->d_sizes);
@@ -460,13 +462,28 @@ static int compute_maps_masked(mtm_ctx* ctx, int method)
     return MTM_OK;
 }
 
+// May the numerator kernel's epilogue list the above-threshold pixels for the peak search?  Only for the
+// default method, the multi-object search and maps larger than the list (so that a constant map -- the one
+// case peak_local_max treats specially -- can never hide behind a short list).
+static void request_candidates(mtm_ctx* ctx, int method, int64_t n_object, double thr)
+{
+    ctx->cand_on = false;
+    if (method != MTM_TM_CCOEFF_NORMED || n_object == 1 || getenv("MTM_B200_NO_CAND")) return;
+    for (int t = 0; t < ctx->n_tmpl; ++t) {
+        const TmplMeta& m = ctx->h_meta[t];
+        if (m.mh == 1 || m.mw == 1 || (int64_t)m.mh * m.mw <= MTM_CAND_CAP) return;
+    }
+    ctx->cand_on = true;
+    ctx->cand_thr = (float)thr;
+}
+
 // Score maps of every template (tmpl < 0) or of one template, grouped by template size.
 static int compute_maps(mtm_ctx* ctx, int method, int tmpl)
 {
     if (method < 0 || method > 5) return mtm_fail(ctx, MTM_ERR_INVALID, "unknown method %d", method);
     const int n = ctx->n_tmpl;
     int i = 0;
-    if (ctx->masked) return compute_maps_masked(ctx, method);
+    if (ctx->masked) { ctx->cand_on = false; ctx->cand_valid = false; return compute_maps_masked(ctx, method); }
     const bool tensor = use_tensor_path(ctx, method);
     if (!tensor && ctx->path == MTM_PATH_TENSOR)
         return mtm_fail(ctx, MTM_ERR_UNSUPPORTED, "tensor-core path requested but not available for these inputs/method");
@@ -476,6 +493,9 @@ static int compute_maps(mtm_ctx* ctx, int method, int tmpl)
         MTM_TRY(harvest_ncc_time(ctx, false));
         MTM_CUDA(ctx, cudaEventRecord(ctx->ev_ncc[ctx->ncc_head % MTM_NCC_RING][0], ctx->stream));
     }
+    ctx->cand_on = ctx->cand_on && tensor && tmpl < 0;
+    ctx->cand_valid = false;
+    if (ctx->cand_on) MTM_CUDA(ctx, cudaMemsetAsync(ctx->d_cand_count, 0, sizeof(int32_t), ctx->stream));
     if (tensor) {
         for (const TcGroup& g : ctx->tc_groups) {
             if (tmpl >= 0) {
@@ -486,7 +506,9 @@ static int compute_maps(mtm_ctx* ctx, int method, int tmpl)
             MTM_TRY(launch_ncc_tc(ctx, g));
         }
         i = n;
+        ctx->cand_valid = ctx->cand_on;
     }
+    ctx->cand_on = false;
     while (i < n) {
         const TmplMeta& a = ctx->h_meta[ctx->h_order[i]];
         int j = i + 1;
@@ -713,6 +735,7 @@ int mtm_find_matches(mtm_ctx* ctx, int method, int64_t n_object, double score_th
     MTM_ENTER(ctx);
     if (!n_hits || (capacity > 0 && !hits)) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_find_matches: null output");
     MTM_TRY(ensure_geometry(ctx));
+    request_candidates(ctx, method, n_object, score_threshold);
     MTM_TRY(compute_maps(ctx, method, -1));
     const int minimize = method_is_min(method) ? 1 : 0;
     for (int attempt = 0; attempt < 8; ++attempt) {
@@ -721,6 +744,7 @@ int mtm_find_matches(mtm_ctx* ctx, int method, int64_t n_object, double score_th
         if (n_object != 1) {
             MTM_TRY(launch_finalize_small(ctx, minimize, 1, 0, 0, 0.f, 0, -1, 0.f));
             MTM_TRY(download_block(ctx, ctx->d_blockA, &n_raw, &n, &declined));
+            if (declined == 2) { ctx->cand_valid = false; continue; }      // candidate list overflowed: stream the maps
             if (declined) {                                  // more than 1024 raw hits: general path
                 if (n_raw > ctx->hit_cap) { MTM_TRY(reserve_hits(ctx, n_raw)); continue; }
                 MTM_TRY(launch_sort_hits(ctx, 0, minimize, 0, 1));
@@ -746,6 +770,7 @@ int mtm_match_templates(mtm_ctx* ctx, int method, int64_t n_object, double score
     if (method == MTM_TM_SQDIFF) return mtm_fail(ctx, MTM_ERR_INVALID, "The method TM_SQDIFF is not supported. Use TM_SQDIFF_NORMED instead.");
     MTM_TRY(ensure_geometry(ctx));
     g_marks.mark(ctx, "geometry");
+    request_candidates(ctx, method, n_object, score_threshold);
     MTM_TRY(compute_maps(ctx, method, -1));
     g_marks.mark(ctx, "moments+ncc");
     const int minimize = method_is_min(method) ? 1 : 0;
@@ -761,6 +786,7 @@ int mtm_match_templates(mtm_ctx* ctx, int method, int64_t n_object, double score
         MTM_TRY(download_block(ctx, ctx->d_blockB, &n_raw, &n, &declined));
         g_marks.mark(ctx, "download");
         g_marks.report(ctx);
+        if (declined == 2) { ctx->cand_valid = false; continue; }          // candidate list overflowed: stream the maps
         if (declined) {                                      // more than 1024 raw hits: general path
             if (n_raw > ctx->hit_cap) { MTM_TRY(reserve_hits(ctx, n_raw)); continue; }
             if (n_object != 1) {
@@ -794,6 +820,7 @@ int mtm_match_templates_async(mtm_ctx* ctx, int method, int64_t n_object, double
         MTM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_slot[slot], cudaEventDisableTiming));
     }
     MTM_TRY(ensure_geometry(ctx));
+    request_candidates(ctx, method, n_object, score_threshold);
     MTM_TRY(compute_maps(ctx, method, -1));
     const int minimize = method_is_min(method) ? 1 : 0;
     const int ascending = (method == MTM_TM_SQDIFF_NORMED) ? 1 : 0;

@@ -8,6 +8,7 @@
 
 #define MTM_MAX_CH 4
 #define MTM_NCC_RING 16
+#define MTM_CAND_CAP 32768      // above-threshold pixels the tensor-core epilogue may list per call
 #define MTM_SLOT_HITS 1024      // hits a slot of the asynchronous API can return (== the fused fast path)
 #define MTM_HIT_HEADER 32      // bytes: int32 count[8]; count[0] = number of hits (may exceed capacity)
 
@@ -142,6 +143,12 @@ struct mtm_ctx {
     size_t per_tmpl_cap = 0, best_cap = 0;
     uint8_t* h_stage = nullptr; size_t h_stage_cap = 0;   // pinned up/download buffer
 
+    // candidate list written by the tcgen05 epilogue (pixels above the threshold), consumed by verify_candidates
+    DevHit* d_cand = nullptr; int32_t* d_cand_count = nullptr;
+    bool cand_on = false;                // the current compute_maps call fills the list
+    bool cand_valid = false;             // the list belongs to the resident score maps
+    float cand_thr = 0.f;
+
     // asynchronous submissions (mtm_match_templates_async / _collect): per-slot result blocks
     uint8_t* d_slot[MTM_MAX_INFLIGHT] = {};        // header + DevHit[MTM_SLOT_HITS]
     uint8_t* h_slot[MTM_MAX_INFLIGHT] = {};        // pinned mirrors
@@ -192,7 +199,7 @@ int launch_toeplitz_prep(mtm_ctx* ctx, const TcGroup& g);
 int launch_window_moments(mtm_ctx* ctx);
 int launch_ncc_tc(mtm_ctx* ctx, const TcGroup& g);
 // raw (unsorted) peaks of every template -> block A
-int launch_peaks(mtm_ctx* ctx, int method, int64_t n_object, float thr32, double thr64);
+int launch_peaks(mtm_ctx* ctx, int method, int64_t n_object, float thr32, double thr64, bool allow_candidates = true);
 // in-place sort of block A (mode 0: findMatches order, mode 1: NMSBoxes order)
 int launch_sort_hits(mtm_ctx* ctx, int mode, int minimize, int ascending_key, int check_trivial);
 // fast path (raw count <= 1024): sort(s) [+ NMS] in one launch; sets header[2] = 1 when it declines

@@ -109,9 +109,15 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 // Normalise 16 consecutive accumulator columns (output rows y_first .. y_first+15) of one lane.
 // Loads are issued for all 16 rows up front (addresses clamped, stores predicated) so that one
 // L2 round trip covers the whole batch.
+// Pixels scoring above the threshold are also appended to the candidate list (a few thousand at most):
+// the 3x3 local-maximum test then only visits those instead of streaming every score map again.
+struct CandSink {
+    DevHit* list; int32_t* count; int cap; float thr; int tmpl, w, h;
+};
+
 __device__ __forceinline__ void epilogue16(const uint32_t (&v)[16], int y_first, int mh, int mw, int x, long long area,
                                            long long sumT, float ct, bool is_const, const uint32_t* __restrict__ S,
-                                           const float* __restrict__ rsD, float* __restrict__ out)
+                                           const float* __restrict__ rsD, float* __restrict__ out, const CandSink& sink)
 {
     float rs[16];
     uint32_t sw[16];
@@ -128,7 +134,18 @@ __device__ __forceinline__ void epilogue16(const uint32_t (&v)[16], int y_first,
         const long long n1 = area * (long long)v[k] - (long long)sw[k] * sumT;
         float r = (float)n1 * rs[k] * ct;
         r = fminf(1.0f, fmaxf(-1.0f, r));
-        if (y < mh) out[(int64_t)y * mw + x] = is_const ? 1.0f : r;
+        if (is_const) r = 1.0f;
+        if (y < mh) {
+            out[(int64_t)y * mw + x] = r;
+            if (sink.list && r > sink.thr) {
+                const int slot = atomicAdd(sink.count, 1);
+                if (slot < sink.cap) {
+                    DevHit c;
+                    c.tmpl = sink.tmpl; c.x = x; c.y = y; c.w = sink.w; c.h = sink.h; c.score = r; c.seq = 0; c.key = 0.f;
+                    sink.list[slot] = c;
+                }
+            }
+        }
     }
 }
 
@@ -200,6 +217,7 @@ struct TcParams {
     const TmplMeta* meta; const int32_t* order; int count;
     const uint32_t* S; const float* rsD;   // window moments of this (h, w): [mh][mw]
     float* maps;
+    DevHit* cand; int32_t* cand_count; int cand_cap; float cand_thr;   // optional candidate list (nullptr: off)
 };
 
 // One CTA = one output tile.  Warp 0: slab producer, warp 1: MMA issuer, then all 8 warps: epilogue.
@@ -301,6 +319,7 @@ ncc_tc_kernel(const TcParams p)
         float* out = tm ? p.maps + tm->map_off : nullptr;
         const uint32_t* Sm = tm ? p.S + tm->mom_off : nullptr;
         const float* Rm = tm ? p.rsD + tm->mom_off : nullptr;
+        CandSink sink{p.cand, p.cand_count, p.cand_cap, p.cand_thr, tm ? p.order[tsel] : 0, tm ? tm->w : 0, tm ? tm->h : 0};
         // N is a multiple of 16: the two warps of a lane quarter split the 16-column batches
         const int batches = p.N >> 4, first = (batches + 1) >> 1;
         const int c_begin = (warp >> 2) ? 16 * first : 0, c_end = (warp >> 2) ? p.N : 16 * first;
@@ -308,7 +327,7 @@ ncc_tc_kernel(const TcParams p)
             uint32_t v[16];
             tmem_ld16(tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c0, v);
             if (!live || y0 + c0 >= t_mh) continue;
-            epilogue16(v, y0 + c0, t_mh, t_mw, x, area, sumT, ct, is_const, Sm, Rm, out);
+            epilogue16(v, y0 + c0, t_mh, t_mw, x, area, sumT, ct, is_const, Sm, Rm, out, sink);
         }
     }
     tc_fence_before();
@@ -529,7 +548,7 @@ ncc_tc_ts_kernel(const TsParams p)
             uint32_t v[16];
             tmem_ld16(tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c0, v);
             if (!live || y0 + c0 >= p.mh) continue;
-            epilogue16(v, y0 + c0, p.mh, p.mw, x, area, sumT, ct, is_const, p.S + tm->mom_off, p.rsD + tm->mom_off, out);
+            epilogue16(v, y0 + c0, p.mh, p.mw, x, area, sumT, ct, is_const, p.S + tm->mom_off, p.rsD + tm->mom_off, out, CandSink{nullptr, nullptr, 0, 0.f, 0, 0, 0});
         }
     }
     tc_fence_before();
@@ -730,6 +749,7 @@ int launch_ncc_tc(mtm_ctx* ctx, const TcGroup& g)
     const size_t smem_bytes = smem_for(bestN);
     p.meta = ctx->d_meta; p.order = ctx->d_order + g.first; p.count = g.count;
     p.S = ctx->d_wS; p.rsD = ctx->d_wR; p.maps = ctx->d_maps;
+    if (ctx->cand_on) { p.cand = ctx->d_cand; p.cand_count = ctx->d_cand_count; p.cand_cap = MTM_CAND_CAP; p.cand_thr = ctx->cand_thr; }
     if (!ctx->tc_attr_set) {
         MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         ctx->tc_attr_set = true;

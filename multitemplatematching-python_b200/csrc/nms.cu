@@ -225,6 +225,7 @@ finalize_small_kernel(DevHit* __restrict__ hits, int cap, int32_t* __restrict__ 
     const int tid = threadIdx.x, nth = blockDim.x;
     const int n_raw = count[0];
     int32_t* flag_hdr = do_nms ? out_count : count;
+    if (count[3]) { if (tid == 0) { flag_hdr[2] = 2; if (do_nms) out_count[1] = 0; } return; }   // candidate list overflowed
     if (n_raw > FIN_CAP) { if (tid == 0) { flag_hdr[2] = 1; if (do_nms) out_count[1] = n_raw; } return; }
     if (tid == 0) { s_live = 0; s_kept = 0; s_best = 0ull; flag_hdr[2] = 0; }
     __syncthreads();

@@ -128,6 +128,40 @@ __global__ void peaks1d_kernel(const TmplMeta* __restrict__ meta, int n_tmpl, co
     }
 }
 
+// 3x3 test for the above-threshold pixels listed by the tensor-core epilogue (instead of streaming
+// every score map again).  count[3] = 1 reports a list overflow: the host re-runs peaks2d_kernel.
+__global__ void verify_candidates_kernel(const TmplMeta* __restrict__ meta, int n_tmpl, const float* __restrict__ maps,
+                                         const DevHit* __restrict__ cand, const int32_t* __restrict__ cand_count, int cand_cap,
+                                         DevHit* __restrict__ hits, int cap, int32_t* __restrict__ count,
+                                         int32_t* __restrict__ nontrivial)
+{
+    const int n = *cand_count;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid < n_tmpl) nontrivial[gid] = 1;           // only used for maps with more pixels than the list holds
+    if (n > cand_cap) { if (gid == 0) count[3] = 1; return; }
+    for (int i = gid; i < n; i += gridDim.x * blockDim.x) {
+        const DevHit c = cand[i];
+        const TmplMeta& tm = meta[c.tmpl];
+        const float* m = maps + tm.map_off;
+        bool is_max = true;
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+            const int yy = c.y + dy;
+            if (yy < 0 || yy >= tm.mh) continue;
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int xx = c.x + dx;
+                if (xx < 0 || xx >= tm.mw || (dx == 0 && dy == 0)) continue;
+                if (m[(int64_t)yy * tm.mw + xx] > c.score) is_max = false;
+            }
+        }
+        if (is_max) {
+            const int slot = atomicAdd(count, 1);
+            if (slot < cap) hits[slot] = c;
+        }
+    }
+}
+
 __global__ void argbest_kernel(const TmplMeta* __restrict__ meta, const float* __restrict__ maps,
                                int minimize, unsigned long long* __restrict__ best)
 {
@@ -167,7 +201,7 @@ __global__ void emit_best_kernel(const TmplMeta* __restrict__ meta, int n_tmpl, 
 }  // namespace
 
 // Fills block A (hits + count[0]) with the raw (unsorted) peaks of every template.
-int launch_peaks(mtm_ctx* ctx, int method, int64_t n_object, float thr32, double thr64)
+int launch_peaks(mtm_ctx* ctx, int method, int64_t n_object, float thr32, double thr64, bool allow_candidates)
 {
     const int nt = ctx->n_tmpl;
     const int minimize = method_is_min(method) ? 1 : 0;
@@ -188,6 +222,14 @@ int launch_peaks(mtm_ctx* ctx, int method, int64_t n_object, float thr32, double
         MTM_LAUNCH_CHECK(ctx);
         emit_best_kernel<<<(nt + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_meta, nt, ctx->d_maps, ctx->d_best,
                                                                    ctx->hitsA(), ctx->countA());
+        MTM_LAUNCH_CHECK(ctx);
+        return MTM_OK;
+    }
+    if (allow_candidates && ctx->cand_valid && ctx->cand_thr == thr32 && !minimize) {
+        // the epilogue of the numerator kernel already listed every pixel above the threshold
+        verify_candidates_kernel<<<64, 256, 0, ctx->stream>>>(ctx->d_meta, nt, ctx->d_maps, ctx->d_cand, ctx->d_cand_count,
+                                                             MTM_CAND_CAP, ctx->hitsA(), ctx->hit_cap, ctx->countA(),
+                                                             ctx->d_nontrivial);
         MTM_LAUNCH_CHECK(ctx);
         return MTM_OK;
     }
