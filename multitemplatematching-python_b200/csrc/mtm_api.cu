@@ -349,8 +349,9 @@ static int plan_tensor_path(mtm_ctx* ctx)
     ctx->tc_groups.clear();
     ctx->tc_ready = false;
     ctx->moments_valid = false;
-    if (ctx->tmpl_C != 1 || ctx->tmpl_dtype != MTM_U8) return MTM_OK;
+    if ((ctx->tmpl_C != 1 && ctx->tmpl_C != 3 && ctx->tmpl_C != 4) || ctx->tmpl_dtype != MTM_U8) return MTM_OK;
     const int n = ctx->n_tmpl;
+    const int TC = ctx->tmpl_C;
     // Cost model (tensor-pipe clocks per output pixel, up to a constant): a mode-A launch serves up to
     // 8 templates for h*nk/16, a mode-B launch one template for h*nk/128.  Templates are visited in
     // (h, w) order; a template joins the open mode-A group (zero padded to the group's size) while
@@ -358,7 +359,7 @@ static int plan_tensor_path(mtm_ctx* ctx)
     auto cost = [](const TcGroup& g) { return (double)g.h * g.nk / (g.mode == 0 ? 16.0 : 128.0); };
     auto alone = [&](int h, int w, TcGroup& best) {
         TcGroup a{}, b{};
-        const bool okA = tc_plan_group(0, h, w, a), okB = tc_plan_group(1, h, w, b);
+        const bool okA = tc_plan_group(0, h, w, TC, a), okB = tc_plan_group(1, h, w, TC, b);
         if (!okA && !okB) return false;
         best = (okA && (!okB || cost(a) <= cost(b))) ? a : b;
         return true;
@@ -376,7 +377,7 @@ static int plan_tensor_path(mtm_ctx* ctx)
         TcGroup solo{};
         if (!alone(m0.h, m0.w, solo)) return MTM_OK;
         TcGroup open{};
-        bool have_open = tc_plan_group(0, m0.h, m0.w, open);
+        bool have_open = tc_plan_group(0, m0.h, m0.w, TC, open);
         double solo_sum = cost(solo);
         int j = i + 1, hg = m0.h, wg = m0.w, h_min = m0.h, w_min = m0.w;
         while (have_open && j < n && j - i < 8) {
@@ -384,7 +385,7 @@ static int plan_tensor_path(mtm_ctx* ctx)
             TcGroup sj{}, grown{};
             if (!alone(mj.h, mj.w, sj)) return MTM_OK;
             const int hg2 = std::max(hg, mj.h), wg2 = std::max(wg, mj.w);
-            if (!tc_plan_group(0, hg2, wg2, grown)) break;
+            if (!tc_plan_group(0, hg2, wg2, TC, grown)) break;
             if (grown.variant == 1 && (mj.h != m0.h || mj.w != m0.w)) break;   // TS variant: same-size groups only
             if (cost(grown) > cost(open) + cost(sj)) break;          // cheaper to start a new group
             open = grown; hg = hg2; wg = wg2;
@@ -414,7 +415,7 @@ static int plan_tensor_path(mtm_ctx* ctx)
 static int ensure_moments(mtm_ctx* ctx)
 {
     if (ctx->moments_valid) return MTM_OK;
-    MTM_TRY(mtm_reserve(ctx, ctx->d_wS, ctx->wS_cap, (size_t)ctx->moments_total));
+    MTM_TRY(mtm_reserve(ctx, ctx->d_wS, ctx->wS_cap, (size_t)ctx->moments_total * ctx->img.C));
     MTM_TRY(mtm_reserve(ctx, ctx->d_wR, ctx->wR_cap, (size_t)ctx->moments_total));
     MTM_TRY(mtm_reserve(ctx, ctx->d_sizes, ctx->sizes_cap, ctx->h_sizes.size()));
     MTM_CUDA(ctx, cudaMemcpyAsync(ctx->d_sizes, ctx->h_sizes.data(), ctx->h_sizes.size() * sizeof(SizeDesc),

@@ -40,8 +40,8 @@ struct TmplMeta {
     double norm_ccoeff;        // sqrt(sum_c var_c) / sqrt(invArea)
     double norm_plain;         // sqrt(sum_c var_c + mean_c^2) / sqrt(invArea)
     double inv_area;
-    long long isum;            // integer sum of the (single-channel) template: tensor-core epilogue
-    float inv_sqrt_d2;         // 1 / sqrt(A*sumT2 - sumT^2)
+    long long isum[MTM_MAX_CH]; // integer sum of the template per channel: tensor-core epilogue
+    float inv_sqrt_d2;         // 1 / sqrt(sum_c (A*sumT2_c - sumT_c^2))
     float pad_f;
 };
 
@@ -194,7 +194,7 @@ int launch_masked_image(mtm_ctx* ctx);
 int launch_masked_combine(mtm_ctx* ctx, int method, const float* mapsB);
 // tensor-core path
 bool tc_path_supported(const mtm_ctx* ctx, int method, int h, int w);
-bool tc_plan_group(int mode, int h, int w, TcGroup& g);
+bool tc_plan_group(int mode, int h, int w, int C, TcGroup& g);
 int launch_toeplitz_prep(mtm_ctx* ctx, const TcGroup& g);
 int launch_window_moments(mtm_ctx* ctx);
 int launch_ncc_tc(mtm_ctx* ctx, const TcGroup& g);

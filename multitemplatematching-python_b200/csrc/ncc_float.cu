@@ -152,7 +152,8 @@ __global__ void tmplf_stats_kernel(const float* __restrict__ tmpl, float* __rest
         m.sum2 = sum2 / inv_area;
         m.norm_ccoeff = sqrt(norm) / sqrt(inv_area);
         m.norm_plain = sqrt(sum2) / sqrt(inv_area);
-        m.isum = 0; m.inv_sqrt_d2 = 0.f;
+        for (int c = 0; c < MTM_MAX_CH; ++c) m.isum[c] = 0;
+        m.inv_sqrt_d2 = 0.f;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x) {

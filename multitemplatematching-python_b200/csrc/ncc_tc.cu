@@ -149,6 +149,50 @@ __device__ __forceinline__ void epilogue16(const uint32_t (&v)[16], int y_first,
     }
 }
 
+// Multi-channel (interleaved RGB / RGBA) form: per-channel window sums, the squared sums share one table.
+//   N1 = A*CC - sum_c S_c*sumT_c ;  rsD already holds rsqrt(A*Q - sum_c S_c^2).
+template <int C>
+__device__ __forceinline__ void epilogue16_mc(const uint32_t (&v)[16], int y_first, int mh, int mw, int x, long long area,
+                                              const long long (&sumT)[MTM_MAX_CH], float ct, bool is_const,
+                                              const uint32_t* __restrict__ S, int64_t plane, const float* __restrict__ rsD,
+                                              float* __restrict__ out, const CandSink& sink)
+{
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        float rs[8];
+        uint32_t sw[8][C];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int y = min(y_first + 8 * half + k, mh - 1);
+            const int64_t o = (int64_t)y * mw + x;
+            rs[k] = __ldg(rsD + o);
+#pragma unroll
+            for (int c = 0; c < C; ++c) sw[k][c] = __ldg(S + c * plane + o);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int y = y_first + 8 * half + k;
+            long long n1 = area * (long long)v[8 * half + k];
+#pragma unroll
+            for (int c = 0; c < C; ++c) n1 -= (long long)sw[k][c] * sumT[c];
+            float r = (float)n1 * rs[k] * ct;
+            r = fminf(1.0f, fmaxf(-1.0f, r));
+            if (is_const) r = 1.0f;
+            if (y < mh) {
+                out[(int64_t)y * mw + x] = r;
+                if (sink.list && r > sink.thr) {
+                    const int slot = atomicAdd(sink.count, 1);
+                    if (slot < sink.cap) {
+                        DevHit cnd;
+                        cnd.tmpl = sink.tmpl; cnd.x = x; cnd.y = y; cnd.w = sink.w; cnd.h = sink.h; cnd.score = r; cnd.seq = 0; cnd.key = 0.f;
+                        sink.list[slot] = cnd;
+                    }
+                }
+            }
+        }
+    }
+}
+
 // Stage the image tile rows [y0, y0+R) x bytes [x0, x0 + 16*kb) into smem as [k-block][row][16 B].
 // Eight independent 16-byte loads per thread are in flight before the first store.
 __device__ __forceinline__ void stage_image_tile(uint8_t* __restrict__ tile, const uint8_t* __restrict__ img, int64_t pitch,
@@ -218,6 +262,7 @@ struct TcParams {
     const uint32_t* S; const float* rsD;   // window moments of this (h, w): [mh][mw]
     float* maps;
     DevHit* cand; int32_t* cand_count; int cand_cap; float cand_thr;   // optional candidate list (nullptr: off)
+    int C; int64_t mom_plane;         // channels (1, 3, 4) and the element stride between the per-channel S planes
 };
 
 // One CTA = one output tile.  Warp 0: slab producer, warp 1: MMA issuer, then all 8 warps: epilogue.
@@ -250,7 +295,7 @@ ncc_tc_kernel(const TcParams p)
     if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
 
     // ---- stage the image tile: rows [y0, y0+R) x bytes [x0, x0 + 32*nk), layout [k-block][row][16 B]
-    stage_image_tile(tile, p.img, p.pitch, p.H, x0, y0, p.R, kb_img, tid);
+    stage_image_tile(tile, p.img, p.pitch, p.H, x0 * p.C, y0, p.R, kb_img, tid);
     fence_async_smem();                                        // generic-proxy writes -> visible to the MMA (async proxy)
     tc_fence_before();
     __syncthreads();
@@ -313,7 +358,10 @@ ncc_tc_kernel(const TcParams p)
         const int t_mh = tm ? tm->mh : 0, t_mw = tm ? tm->mw : 0;
         const bool live = tm && (x < t_mw);
         const long long area = tm ? (long long)tm->h * tm->w : 0;
-        const long long sumT = tm ? tm->isum : 0;
+        const long long sumT = tm ? tm->isum[0] : 0;
+        long long sumT_c[MTM_MAX_CH];
+#pragma unroll
+        for (int c = 0; c < MTM_MAX_CH; ++c) sumT_c[c] = tm ? tm->isum[c] : 0;
         const float ct = tm ? tm->inv_sqrt_d2 : 0.f;
         const bool is_const = tm ? (tm->is_const != 0) : false;
         float* out = tm ? p.maps + tm->map_off : nullptr;
@@ -327,7 +375,9 @@ ncc_tc_kernel(const TcParams p)
             uint32_t v[16];
             tmem_ld16(tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c0, v);
             if (!live || y0 + c0 >= t_mh) continue;
-            epilogue16(v, y0 + c0, t_mh, t_mw, x, area, sumT, ct, is_const, Sm, Rm, out, sink);
+            if (p.C == 1) epilogue16(v, y0 + c0, t_mh, t_mw, x, area, sumT, ct, is_const, Sm, Rm, out, sink);
+            else if (p.C == 3) epilogue16_mc<3>(v, y0 + c0, t_mh, t_mw, x, area, sumT_c, ct, is_const, Sm, p.mom_plane, Rm, out, sink);
+            else epilogue16_mc<4>(v, y0 + c0, t_mh, t_mw, x, area, sumT_c, ct, is_const, Sm, p.mom_plane, Rm, out, sink);
         }
     }
     tc_fence_before();
@@ -538,7 +588,7 @@ ncc_tc_ts_kernel(const TsParams p)
         const bool live = (tsel < p.count) && (x < p.mw);
         const TmplMeta* tm = live ? &p.meta[p.order[tsel]] : nullptr;
         const long long area = (long long)p.h * p.w;
-        const long long sumT = live ? tm->isum : 0;
+        const long long sumT = live ? tm->isum[0] : 0;
         const float ct = live ? tm->inv_sqrt_d2 : 0.f;
         const bool is_const = live ? (tm->is_const != 0) : false;
         float* out = live ? p.maps + tm->map_off : nullptr;
@@ -563,7 +613,7 @@ ncc_tc_ts_kernel(const TsParams p)
 // Expands the templates of one group into Toeplitz slabs (see the header comment).
 __global__ void toeplitz_prep_kernel(const uint8_t* __restrict__ tmpl, const TmplMeta* __restrict__ meta,
                                      const int32_t* __restrict__ order, int count, int mode, int h, int w,
-                                     int nk, int slab_bytes, uint8_t* __restrict__ slabs)
+                                     int nk, int slab_bytes, int C, uint8_t* __restrict__ slabs)
 {
     const int pieces_per_slab = slab_bytes / 16;
     const int64_t total = (int64_t)h * pieces_per_slab;
@@ -571,7 +621,7 @@ __global__ void toeplitz_prep_kernel(const uint8_t* __restrict__ tmpl, const Tmp
         const int dy = (int)(idx / pieces_per_slab);
         const int pc = (int)(idx - (int64_t)dy * pieces_per_slab);
         int t, r, ubase;                                   // ubase: template column of byte 0 of this piece
-        if (mode == 0) { const int c = pc >> 7; t = (pc >> 4) & 7; r = pc & 15; ubase = 16 * c - r; }
+        if (mode == 0) { const int c = pc >> 7; t = (pc >> 4) & 7; r = pc & 15; ubase = 16 * c - C * r; }   // x-step = C bytes
         else { const int b = pc >> 4; t = 0; r = pc & 15; ubase = 16 * (b - 7) - r; }
         uint8_t bytes[16];
 #pragma unroll
@@ -583,7 +633,7 @@ __global__ void toeplitz_prep_kernel(const uint8_t* __restrict__ tmpl, const Tmp
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
                     const int col = ubase + k;
-                    if (col >= 0 && col < tm.w) bytes[k] = row[col];
+                    if (col >= 0 && col < tm.w * C) bytes[k] = row[col];
                 }
             }
         }
@@ -594,18 +644,21 @@ __global__ void toeplitz_prep_kernel(const uint8_t* __restrict__ tmpl, const Tmp
 // S = window sum, rsD = rsqrt(A*Q - S^2) (0 for an exactly flat window), per window position, for
 // every distinct template size in one launch (blockIdx.y = size).
 __global__ void window_moments_kernel(SatView sat, const uint32_t* __restrict__ sat_q32, const SizeDesc* __restrict__ sizes,
-                                      uint32_t* __restrict__ S, float* __restrict__ rsD)
+                                      uint32_t* __restrict__ S, float* __restrict__ rsD, int C, int64_t mom_plane)
 {
     const SizeDesc sd = sizes[blockIdx.y];
     const int64_t n = (int64_t)sd.mh * sd.mw;
     const unsigned long long area = (unsigned long long)sd.h * sd.w;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
         const int y = (int)(idx / sd.mw), x = (int)(idx - (int64_t)y * sd.mw);
-        const uint32_t s = sat_window_s(sat.s, sat.pitch, y, x, sd.h, sd.w);
-        // window sums of squares < 2^32 on the tensor path (h*w <= 66051): the 32-bit wrap-around table is exact
+        // window sums of squares < 2^32 on the tensor path (h*w*C <= 66051): the 32-bit wrap-around table is exact
         const unsigned long long q = sat_window_s(sat_q32, sat.pitch, y, x, sd.h, sd.w);
-        const unsigned long long d1 = area * q - (unsigned long long)s * s;
-        S[sd.off + idx] = s;
+        unsigned long long d1 = area * q;
+        for (int c = 0; c < C; ++c) {
+            const uint32_t s = sat_window_s(sat.s + c * sat.plane, sat.pitch, y, x, sd.h, sd.w);
+            d1 -= (unsigned long long)s * s;
+            S[c * mom_plane + sd.off + idx] = s;
+        }
         rsD[sd.off + idx] = d1 ? rsqrtf((float)d1) : 0.0f;
     }
 }
@@ -615,18 +668,20 @@ __global__ void window_moments_kernel(SatView sat, const uint32_t* __restrict__ 
 // ------------------------------------------------------------------------------ host side
 bool tc_path_supported(const mtm_ctx* ctx, int method, int h, int w)
 {
-    if (ctx->img.C != 1 || method != MTM_TM_CCOEFF_NORMED) return false;
-    if ((long long)h * w < 16 || (double)h * w * 65025.0 >= 4294967296.0) return false;   // 32-bit exact range; tiny windows -> fp64 path
+    const int C = ctx->img.C;
+    if ((C != 1 && C != 3 && C != 4) || method != MTM_TM_CCOEFF_NORMED) return false;
+    if ((long long)h * w < 16 || (double)h * w * C * 65025.0 >= 4294967296.0) return false;   // 32-bit exact range; tiny windows -> fp64 path
     return true;
 }
 
 // Plans a group of `count` same-size templates.  Returns false when the tile does not fit shared memory.
-bool tc_plan_group(int mode, int h, int w, TcGroup& g)
+bool tc_plan_group(int mode, int h, int w, int C, TcGroup& g)
 {
     g.mode = mode; g.h = h; g.w = w; g.variant = 0;
+    if (mode == 1 && C != 1) return false;                 // the aliased 128-offset layout needs a 1-byte x-step
     const int nx = mode == 0 ? 16 : 128;
-    g.nk = (w + nx - 1 + 31) / 32;
-    if (mode == 0 && g.nk <= 5 && getenv("MTM_B200_TS")) {      // experimental: off by default (SS is faster today)
+    g.nk = (w * C + (nx - 1) * C + 31) / 32;               // band: template row bytes + the largest x-shift
+    if (mode == 0 && C == 1 && g.nk <= 5 && getenv("MTM_B200_TS")) {      // experimental: off by default (SS is faster today)
         // TS variant: A generated into TMEM, N = 128 output rows, compact template rows resident in smem
         int rs = 16 + 32 * g.nk + 16;
         g.row_stride = rs;
@@ -658,7 +713,7 @@ bool tc_plan_group(int mode, int h, int w, TcGroup& g)
     if (!g.N) return false;
     g.R = g.N + h - 1;
     g.smem = (((size_t)2 * g.nk * g.R * 16 + 127) & ~(size_t)127) + ring + 256;
-    g.eff = (double)w / (32.0 * g.nk);
+    g.eff = (double)w * C / (32.0 * g.nk);
     return true;
 }
 
@@ -668,7 +723,7 @@ int launch_toeplitz_prep(mtm_ctx* ctx, const TcGroup& g)
     const int64_t pieces = (int64_t)g.h * (g.slab_bytes / 16);
     const int blocks = (int)std::min<int64_t>((pieces + 255) / 256, 4096);
     toeplitz_prep_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_tmpl, ctx->d_meta, ctx->d_order + g.first, g.count, g.mode,
-                                                         g.h, g.w, g.nk, g.slab_bytes, ctx->d_slabs + g.arena_off);
+                                                         g.h, g.w, g.nk, g.slab_bytes, ctx->tmpl_C, ctx->d_slabs + g.arena_off);
     MTM_LAUNCH_CHECK(ctx);
     return MTM_OK;
 }
@@ -680,7 +735,7 @@ int launch_window_moments(mtm_ctx* ctx)
     int64_t n = 0;
     for (const SizeDesc& sd : ctx->h_sizes) n = std::max<int64_t>(n, (int64_t)sd.mh * sd.mw);
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 16));
-    window_moments_kernel<<<dim3(blocks, (unsigned)ctx->h_sizes.size()), 256, 0, ctx->stream>>>(sv, im.sat_q32, ctx->d_sizes, ctx->d_wS, ctx->d_wR);
+    window_moments_kernel<<<dim3(blocks, (unsigned)ctx->h_sizes.size()), 256, 0, ctx->stream>>>(sv, im.sat_q32, ctx->d_sizes, ctx->d_wS, ctx->d_wR, im.C, ctx->moments_total);
     MTM_LAUNCH_CHECK(ctx);
     return MTM_OK;
 }
@@ -749,6 +804,7 @@ int launch_ncc_tc(mtm_ctx* ctx, const TcGroup& g)
     const size_t smem_bytes = smem_for(bestN);
     p.meta = ctx->d_meta; p.order = ctx->d_order + g.first; p.count = g.count;
     p.S = ctx->d_wS; p.rsD = ctx->d_wR; p.maps = ctx->d_maps;
+    p.C = im.C; p.mom_plane = ctx->moments_total;
     if (ctx->cand_on) { p.cand = ctx->d_cand; p.cand_count = ctx->d_cand_count; p.cand_cap = MTM_CAND_CAP; p.cand_thr = ctx->cand_thr; }
     if (!ctx->tc_attr_set) {
         MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

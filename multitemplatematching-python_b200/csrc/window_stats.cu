@@ -183,20 +183,19 @@ __global__ void tmpl_stats_kernel(const uint8_t* __restrict__ tmpl, TmplMeta* __
         const int nw = blockDim.x >> 5;
         const double inv_area = 1.0 / ((double)m.h * (double)m.w);
         double norm = 0.0, mean2 = 0.0;
+        long long d2_all = 0;
         for (int c = 0; c < MTM_MAX_CH; ++c) {
             long long a = 0, b = 0;
             for (int k = 0; k < nw; ++k) { a += red[c][k]; b += red[MTM_MAX_CH + c][k]; }
-            if (c == 0) {
-                const long long d2 = (long long)m.h * m.w * b - a * a;      // exact; > 0 unless the template is constant
-                m.isum = a;
-                m.inv_sqrt_d2 = d2 > 0 ? (float)(1.0 / sqrt((double)d2)) : 0.0f;
-            }
+            m.isum[c] = (c < C) ? a : 0;
+            if (c < C) d2_all += (long long)m.h * m.w * b - a * a;          // exact; > 0 unless the template is constant
             const double mean = (double)a * inv_area;
             const double var = fmax((double)b * inv_area - mean * mean, 0.0);
             m.mean[c] = (c < C) ? mean : 0.0;
             if (c < C) { norm += var; mean2 += mean * mean; }
         }
         const double sum2 = norm + mean2;
+        m.inv_sqrt_d2 = d2_all > 0 ? (float)(1.0 / sqrt((double)d2_all)) : 0.0f;
         m.inv_area = inv_area;
         m.is_const = norm < 2.220446049250313e-16 ? 1 : 0;      // DBL_EPSILON
         m.sum2 = sum2 / inv_area;

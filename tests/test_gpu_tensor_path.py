@@ -80,6 +80,33 @@ def test_tensor_path_mixed_size_groups(mtm, ctxs):
     assert_hits_equal(hits_t, hits_d, tol=2e-6)
 
 
+@pytest.mark.parametrize("C,n_t,tshape,seed", [(3, 8, (32, 32), 31), (3, 3, (40, 21), 32), (4, 2, (16, 48), 33), (3, 1, (64, 64), 34)])
+def test_tensor_path_rgb(mtm, ctxs, C, n_t, tshape, seed):
+    """Interleaved RGB / RGBA uint8 on the tcgen05 kernel (x-step = C bytes in the Toeplitz band,
+    per-channel window sums in the epilogue) against the exact oracle, cv2 and the dp4a kernel."""
+    import cv2
+    from oracle import ncc_exact
+    ct, cd = ctxs
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, 256, (150, 200, C), dtype=np.uint8)
+    temps = []
+    for k in range(n_t):
+        y, x = int(rng.integers(0, 150 - tshape[0])), int(rng.integers(0, 200 - tshape[1]))
+        t = img[y:y + tshape[0], x:x + tshape[1]].astype(np.int32) + rng.integers(-40, 40, tshape + (C,))
+        temps.append(np.clip(t, 0, 255).astype(np.uint8))
+    with ct.lock:
+        ct.set_image(img)
+        ct.set_templates(temps)
+        got = [ct.score_map(i, 5, (150 - tshape[0] + 1, 200 - tshape[1] + 1)) for i in range(n_t)]
+    for i, t in enumerate(temps):
+        exact = ncc_exact.match_template_exact(img, t, use_fft=False)
+        assert_map_close(got[i], exact, cv=cv2.matchTemplate(img, t, cv2.TM_CCOEFF_NORMED))
+        assert np.max(np.abs(got[i] - mtm.computeScoreMap(t, img, context=cd))) <= 2e-6
+    labelled = [("t%d" % i, t) for i, t in enumerate(temps)]
+    assert_hits_equal(mtm.matchTemplates(labelled, img, score_threshold=0.5, context=ct),
+                      mtm.matchTemplates(labelled, img, score_threshold=0.5, context=cd), tol=2e-6)
+
+
 def test_tensor_path_uniform_noise_and_bright(mtm, ctxs):
     """Saturated inputs: 255*255*h*w up to 4.26e9 needs the full unsigned 32-bit accumulator range."""
     from oracle import ncc_exact
