@@ -415,7 +415,7 @@ static int plan_tensor_path(mtm_ctx* ctx)
 static int ensure_moments(mtm_ctx* ctx)
 {
     if (ctx->moments_valid) return MTM_OK;
-    MTM_TRY(mtm_reserve(ctx, ctx->d_wS, ctx->wS_cap, (size_t)ctx->moments_total * ctx->img.C));
+    MTM_TRY(mtm_reserve(ctx, ctx->d_wS, ctx->wS_cap, (size_t)ctx->moments_total * std::max(2, ctx->img.C)));   // C == 1: interleaved {S, rsD}
     MTM_TRY(mtm_reserve(ctx, ctx->d_wR, ctx->wR_cap, (size_t)ctx->moments_total));
     MTM_TRY(mtm_reserve(ctx, ctx->d_sizes, ctx->sizes_cap, ctx->h_sizes.size()));
     MTM_CUDA(ctx, cudaMemcpyAsync(ctx->d_sizes, ctx->h_sizes.data(), ctx->h_sizes.size() * sizeof(SizeDesc),

@@ -129,6 +129,7 @@ struct mtm_ctx {
     float* d_wR = nullptr; size_t wR_cap = 0;            // rsqrt(A*Q - S^2)
     bool moments_valid = false;
     bool tc_attr_set = false;
+    bool tcp_attr_set = false;
 
     int32_t* d_order = nullptr; size_t order_cap = 0;   // template indices sorted by (h, w)
     std::vector<int32_t> h_order;

@@ -61,6 +61,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
         if (spins > (1u << 16)) __trap();
     }
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -115,24 +125,35 @@ struct CandSink {
     DevHit* list; int32_t* count; int cap; float thr; int tmpl, w, h;
 };
 
-__device__ __forceinline__ void epilogue16(const uint32_t (&v)[16], int y_first, int mh, int mw, int x, long long area,
-                                           long long sumT, float ct, bool is_const, const uint32_t* __restrict__ S,
-                                           const float* __restrict__ rsD, float* __restrict__ out, const CandSink& sink)
+__device__ __forceinline__ void prefetch_l1(const void* ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
+
+// Single channel: the window moments are interleaved {S, bits of rsqrt(A*Q - S^2)} so that one 8-byte load serves
+// a pixel.  `ahead` > 0: also pull the batch `ahead` rows further down into L1 (the next batch of this warp).
+__device__ __forceinline__ void prefetch_moments16(const uint2* __restrict__ SR, int y_first, int mh, int mw, int x)
 {
-    float rs[16];
-    uint32_t sw[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
         const int y = min(y_first + k, mh - 1);
-        const int64_t o = (int64_t)y * mw + x;
-        rs[k] = __ldg(rsD + o);
-        sw[k] = __ldg(S + o);
+        prefetch_l1(SR + (int64_t)y * mw + x);
     }
+}
+
+__device__ __forceinline__ void epilogue16(const uint32_t (&v)[16], int y_first, int mh, int mw, int x, long long area,
+                                           long long sumT, float ct, bool is_const, const uint2* __restrict__ SR,
+                                           float* __restrict__ out, const CandSink& sink, bool prefetch_next)
+{
+    uint2 m[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int y = min(y_first + k, mh - 1);
+        m[k] = __ldg(SR + (int64_t)y * mw + x);
+    }
+    if (prefetch_next) prefetch_moments16(SR, y_first + 16, mh, mw, x);
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
         const int y = y_first + k;
-        const long long n1 = area * (long long)v[k] - (long long)sw[k] * sumT;
-        float r = (float)n1 * rs[k] * ct;
+        const long long n1 = area * (long long)v[k] - (long long)m[k].x * sumT;
+        float r = (float)n1 * __uint_as_float(m[k].y) * ct;
         r = fminf(1.0f, fmaxf(-1.0f, r));
         if (is_const) r = 1.0f;
         if (y < mh) {
@@ -144,6 +165,38 @@ __device__ __forceinline__ void epilogue16(const uint32_t (&v)[16], int y_first,
                     c.tmpl = sink.tmpl; c.x = x; c.y = y; c.w = sink.w; c.h = sink.h; c.score = r; c.seq = 0; c.key = 0.f;
                     sink.list[slot] = c;
                 }
+            }
+        }
+    }
+}
+
+// Fast form of epilogue16 for the common case (all 16 rows inside the map, template not constant): 32-bit operands,
+// one running offset, no per-pixel bounds tests.  A <= 66051 and sumT <= 255*66051 fit 32 bits on the tensor path.
+__device__ __forceinline__ void epilogue16_fast(const uint32_t (&v)[16], int y_first, int mw, int x, uint32_t area, uint32_t sumT,
+                                                float ct, const uint2* __restrict__ SR, float* __restrict__ out,
+                                                const CandSink& sink, float thr, bool prefetch_next)
+{
+    const uint2* sr = SR + (int64_t)y_first * mw + x;
+    float* o = out + (int64_t)y_first * mw + x;
+    uint2 m[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) m[k] = __ldg(sr + (uint32_t)(k * mw));
+    if (prefetch_next) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) prefetch_l1(sr + (uint32_t)((16 + k) * mw));
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const long long n1 = (long long)((unsigned long long)area * v[k]) - (long long)((unsigned long long)m[k].x * sumT);
+        float r = (float)n1 * __uint_as_float(m[k].y) * ct;
+        r = fminf(1.0f, fmaxf(-1.0f, r));
+        o[(uint32_t)(k * mw)] = r;
+        if (r > thr) {
+            const int slot = atomicAdd(sink.count, 1);
+            if (slot < sink.cap) {
+                DevHit c;
+                c.tmpl = sink.tmpl; c.x = x; c.y = y_first + k; c.w = sink.w; c.h = sink.h; c.score = r; c.seq = 0; c.key = 0.f;
+                sink.list[slot] = c;
             }
         }
     }
@@ -195,15 +248,16 @@ __device__ __forceinline__ void epilogue16_mc(const uint32_t (&v)[16], int y_fir
 
 // Stage the image tile rows [y0, y0+R) x bytes [x0, x0 + 16*kb) into smem as [k-block][row][16 B].
 // Eight independent 16-byte loads per thread are in flight before the first store.
+template <int NT>
 __device__ __forceinline__ void stage_image_tile(uint8_t* __restrict__ tile, const uint8_t* __restrict__ img, int64_t pitch,
                                                  int H, int x0, int y0, int R, int kb, int tid)
 {
     const int pieces = kb * R;
-    for (int base = 0; base < pieces; base += 8 * TC_THREADS) {
+    for (int base = 0; base < pieces; base += 8 * NT) {
         uint4 v[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            const int idx = base + u * TC_THREADS + tid;
+            const int idx = base + u * NT + tid;
             v[u] = make_uint4(0u, 0u, 0u, 0u);
             if (idx < pieces) {
                 const int c = idx / R, r = idx - c * R;
@@ -214,36 +268,9 @@ __device__ __forceinline__ void stage_image_tile(uint8_t* __restrict__ tile, con
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            const int idx = base + u * TC_THREADS + tid;
+            const int idx = base + u * NT + tid;
             if (idx < pieces) *reinterpret_cast<uint4*>(tile + (size_t)idx * 16) = v[u];
         }
-    }
-}
-
-// Window moments of 16 consecutive output rows of one lane (addresses clamped to the map).
-__device__ __forceinline__ void load_moments16(float (&rs)[16], uint32_t (&sw)[16], int y_first, int mh, int mw, int x,
-                                               const uint32_t* __restrict__ S, const float* __restrict__ rsD)
-{
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        const int y = min(y_first + k, mh - 1);
-        const int64_t o = (int64_t)y * mw + x;
-        rs[k] = __ldg(rsD + o);
-        sw[k] = __ldg(S + o);
-    }
-}
-
-__device__ __forceinline__ void normalise16(const uint32_t (&v)[16], const float (&rs)[16], const uint32_t (&sw)[16],
-                                            int y_first, int mh, int mw, int x, long long area, long long sumT, float ct,
-                                            bool is_const, float* __restrict__ out)
-{
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        const int y = y_first + k;
-        const long long n1 = area * (long long)v[k] - (long long)sw[k] * sumT;
-        float r = (float)n1 * rs[k] * ct;
-        r = fminf(1.0f, fmaxf(-1.0f, r));
-        if (y < mh) out[(int64_t)y * mw + x] = is_const ? 1.0f : r;
     }
 }
 
@@ -263,7 +290,67 @@ struct TcParams {
     float* maps;
     DevHit* cand; int32_t* cand_count; int cand_cap; float cand_thr;   // optional candidate list (nullptr: off)
     int C; int64_t mom_plane;         // channels (1, 3, 4) and the element stride between the per-channel S planes
+    int stages, tiles_x, tiles_total; // persistent kernel: slab ring depth, tile grid width, number of tiles
+    long long* prof; int dbg;         // debug only (MTM_B200_PROF / MTM_B200_PDBG): per-CTA role clocks, phase knock-outs
 };
+
+// Epilogue of one tile for one of 8 epilogue warps: warp%4 selects the TMEM lane quarter, warp/4 the column half.
+__device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_d, int x0, int y0, int warp, int lane, int parts = 2)
+{
+    const int m = 32 * (warp & 3) + lane;
+    int x, tsel;
+    if (p.mode == 0) { tsel = m >> 4; x = x0 + (m & 15); }
+    else { tsel = 0; x = x0 + 16 * (7 - (m >> 4)) + (m & 15); }
+    // per-lane template geometry: a mode-A group may mix template sizes
+    const TmplMeta* tm = (tsel < p.count) ? &p.meta[p.order[tsel]] : nullptr;
+    const int t_mh = tm ? tm->mh : 0, t_mw = tm ? tm->mw : 0;
+    const bool live = tm && (x < t_mw);
+    const long long area = tm ? (long long)tm->h * tm->w : 0;
+    const long long sumT = tm ? tm->isum[0] : 0;
+    long long sumT_c[MTM_MAX_CH];
+#pragma unroll
+    for (int c = 0; c < MTM_MAX_CH; ++c) sumT_c[c] = tm ? tm->isum[c] : 0;
+    const float ct = tm ? tm->inv_sqrt_d2 : 0.f;
+    const bool is_const = tm ? (tm->is_const != 0) : false;
+    float* out = tm ? p.maps + tm->map_off : nullptr;
+    const uint32_t* Sm = tm ? p.S + tm->mom_off : nullptr;
+    const float* Rm = tm ? p.rsD + tm->mom_off : nullptr;
+    const uint2* SRm = tm ? reinterpret_cast<const uint2*>(p.S) + tm->mom_off : nullptr;   // C == 1: interleaved {S, rsD}
+    CandSink sink{p.cand, p.cand_count, p.cand_cap, p.cand_thr, tm ? p.order[tsel] : 0, tm ? tm->w : 0, tm ? tm->h : 0};
+    const float thr_eff = p.cand ? p.cand_thr : 3.0e38f;       // scores never exceed 1: no list, no candidates
+    // N is a multiple of 16: the `parts` warps of a lane quarter split the 16-column batches
+    const int batches = p.N >> 4, part = warp >> 2;
+    const int c_begin = 16 * ((batches * part) / parts), c_end = 16 * ((batches * (part + 1)) / parts);
+    for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c0, v);
+        if (!live || y0 + c0 >= t_mh) continue;
+        if (p.C == 1) {
+            // the prefetched rows of the next batch must exist: +32
+            if (!is_const && y0 + c0 + 32 <= t_mh) epilogue16_fast(v, y0 + c0, t_mw, x, (uint32_t)area, (uint32_t)sumT, ct, SRm, out, sink, thr_eff, c0 + 16 < c_end);
+            else epilogue16(v, y0 + c0, t_mh, t_mw, x, area, sumT, ct, is_const, SRm, out, sink, c0 + 16 < c_end);
+        }
+        else if (p.C == 3) epilogue16_mc<3>(v, y0 + c0, t_mh, t_mw, x, area, sumT_c, ct, is_const, Sm, p.mom_plane, Rm, out, sink);
+        else epilogue16_mc<4>(v, y0 + c0, t_mh, t_mw, x, area, sumT_c, ct, is_const, Sm, p.mom_plane, Rm, out, sink);
+    }
+}
+
+// Pulls the window moments of a warp's first batch of the tile into L1 while the accumulator is still being computed.
+__device__ __forceinline__ void epilogue_prefetch_first(const TcParams& p, int x0, int y0, int warp, int lane, int parts)
+{
+    if (p.C != 1) return;
+    const int m = 32 * (warp & 3) + lane;
+    int x, tsel;
+    if (p.mode == 0) { tsel = m >> 4; x = x0 + (m & 15); }
+    else { tsel = 0; x = x0 + 16 * (7 - (m >> 4)) + (m & 15); }
+    if (tsel >= p.count) return;
+    const TmplMeta* tm = &p.meta[p.order[tsel]];
+    const int t_mh = tm->mh, t_mw = tm->mw;
+    const int batches = p.N >> 4;
+    const int c_begin = 16 * ((batches * (warp >> 2)) / parts);
+    if (x >= t_mw || y0 + c_begin >= t_mh) return;
+    prefetch_moments16(reinterpret_cast<const uint2*>(p.S) + tm->mom_off, y0 + c_begin, t_mh, t_mw, x);
+}
 
 // One CTA = one output tile.  Warp 0: slab producer, warp 1: MMA issuer, then all 8 warps: epilogue.
 __global__ void __launch_bounds__(TC_THREADS, 2)
@@ -295,7 +382,7 @@ ncc_tc_kernel(const TcParams p)
     if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
 
     // ---- stage the image tile: rows [y0, y0+R) x bytes [x0, x0 + 32*nk), layout [k-block][row][16 B]
-    stage_image_tile(tile, p.img, p.pitch, p.H, x0 * p.C, y0, p.R, kb_img, tid);
+    stage_image_tile<TC_THREADS>(tile, p.img, p.pitch, p.H, x0 * p.C, y0, p.R, kb_img, tid);
     fence_async_smem();                                        // generic-proxy writes -> visible to the MMA (async proxy)
     tc_fence_before();
     __syncthreads();
@@ -348,41 +435,228 @@ ncc_tc_kernel(const TcParams p)
     if (warp == 1) { if (lane == 0) mbar_wait(accum, 0); __syncwarp(); }
     __syncthreads();
     tc_fence_after();
-    {
-        const int m = 32 * (warp & 3) + lane;
-        int x, tsel;
-        if (p.mode == 0) { tsel = m >> 4; x = x0 + (m & 15); }
-        else { tsel = 0; x = x0 + 16 * (7 - (m >> 4)) + (m & 15); }
-        // per-lane template geometry: a mode-A group may mix template sizes
-        const TmplMeta* tm = (tsel < p.count) ? &p.meta[p.order[tsel]] : nullptr;
-        const int t_mh = tm ? tm->mh : 0, t_mw = tm ? tm->mw : 0;
-        const bool live = tm && (x < t_mw);
-        const long long area = tm ? (long long)tm->h * tm->w : 0;
-        const long long sumT = tm ? tm->isum[0] : 0;
-        long long sumT_c[MTM_MAX_CH];
-#pragma unroll
-        for (int c = 0; c < MTM_MAX_CH; ++c) sumT_c[c] = tm ? tm->isum[c] : 0;
-        const float ct = tm ? tm->inv_sqrt_d2 : 0.f;
-        const bool is_const = tm ? (tm->is_const != 0) : false;
-        float* out = tm ? p.maps + tm->map_off : nullptr;
-        const uint32_t* Sm = tm ? p.S + tm->mom_off : nullptr;
-        const float* Rm = tm ? p.rsD + tm->mom_off : nullptr;
-        CandSink sink{p.cand, p.cand_count, p.cand_cap, p.cand_thr, tm ? p.order[tsel] : 0, tm ? tm->w : 0, tm ? tm->h : 0};
-        // N is a multiple of 16: the two warps of a lane quarter split the 16-column batches
-        const int batches = p.N >> 4, first = (batches + 1) >> 1;
-        const int c_begin = (warp >> 2) ? 16 * first : 0, c_end = (warp >> 2) ? p.N : 16 * first;
-        for (int c0 = c_begin; c0 < c_end; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c0, v);
-            if (!live || y0 + c0 >= t_mh) continue;
-            if (p.C == 1) epilogue16(v, y0 + c0, t_mh, t_mw, x, area, sumT, ct, is_const, Sm, Rm, out, sink);
-            else if (p.C == 3) epilogue16_mc<3>(v, y0 + c0, t_mh, t_mw, x, area, sumT_c, ct, is_const, Sm, p.mom_plane, Rm, out, sink);
-            else epilogue16_mc<4>(v, y0 + c0, t_mh, t_mw, x, area, sumT_c, ct, is_const, Sm, p.mom_plane, Rm, out, sink);
-        }
-    }
+    epilogue_tile(p, tmem_d, x0, y0, warp, lane);
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc(tmem_d, tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Persistent, warp-specialised form of the same tile computation: one CTA per SM walks the tiles
+// blockIdx.x, blockIdx.x + gridDim.x, ...  Two image-tile buffers in shared memory and two
+// accumulators in TMEM turn the three phases of a tile (stage the image rows / MMA / epilogue) into
+// a pipeline, so the tensor pipe works on tile i+1 while tile i is normalised and stored and the
+// rows of tile i+2 are fetched.
+//   warps 0 .. EW-1   epilogue (TMEM -> registers -> score map), warp%4 = TMEM lane quarter; EW = 8 or 16
+//   warp  EW          Toeplitz slab producer (cp.async.bulk into the ring, continuous over tiles)
+//   warp  EW+1        MMA issuer (one elected lane)
+//   warps EW+2, EW+3  image tile stagers (global -> registers -> shared memory, [k-block][row][16 B])
+// EW = 16 serves small templates, whose tiles spend longer in the epilogue than in the MMAs.
+constexpr int TCP_MAX_STAGES = 8;
+constexpr double TCP_EPI_CLK_PER_ROW = 100.0;   // measured: epilogue clocks per output row of a tile with 8 epilogue warps
+constexpr int TCP_STAGERS = 64;
+
+// MMAs of `rows` consecutive template rows: NK K-chunks each.  Only the low descriptor words move
+// (one 16-byte unit per image row, one slab per template row); they live in uniform registers.
+template <int NK>
+__device__ __forceinline__ void issue_rows(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t a_hi, uint32_t b_hi,
+                                           uint32_t a_kstep, uint32_t b_kstep, uint32_t slab_step, int rows, uint32_t idesc,
+                                           uint32_t accumulate)
+{
+    uint32_t al[NK], bl[NK];
+#pragma unroll
+    for (int k = 0; k < NK; ++k) { al[k] = a_lo + k * a_kstep; bl[k] = b_lo + k * b_kstep; }
+    for (int d = 0; d < rows; ++d) {
+#pragma unroll
+        for (int k = 0; k < NK; ++k) {
+            umma_i8(tmem_d, ((uint64_t)a_hi << 32) | al[k], ((uint64_t)b_hi << 32) | bl[k], idesc, accumulate);
+            accumulate = 1;
+            al[k] += slab_step; bl[k] += 1;
+        }
+    }
+}
+
+__device__ __forceinline__ void issue_rows_any(int nk, uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t a_hi, uint32_t b_hi,
+                                               uint32_t a_kstep, uint32_t b_kstep, uint32_t slab_step, int rows, uint32_t idesc,
+                                               uint32_t accumulate)
+{
+    switch (nk) {
+        case 1: issue_rows<1>(tmem_d, a_lo, b_lo, a_hi, b_hi, a_kstep, b_kstep, slab_step, rows, idesc, accumulate); break;
+        case 2: issue_rows<2>(tmem_d, a_lo, b_lo, a_hi, b_hi, a_kstep, b_kstep, slab_step, rows, idesc, accumulate); break;
+        case 3: issue_rows<3>(tmem_d, a_lo, b_lo, a_hi, b_hi, a_kstep, b_kstep, slab_step, rows, idesc, accumulate); break;
+        case 4: issue_rows<4>(tmem_d, a_lo, b_lo, a_hi, b_hi, a_kstep, b_kstep, slab_step, rows, idesc, accumulate); break;
+        case 5: issue_rows<5>(tmem_d, a_lo, b_lo, a_hi, b_hi, a_kstep, b_kstep, slab_step, rows, idesc, accumulate); break;
+        case 6: issue_rows<6>(tmem_d, a_lo, b_lo, a_hi, b_hi, a_kstep, b_kstep, slab_step, rows, idesc, accumulate); break;
+        default:
+            for (int d = 0; d < rows; ++d) {
+                for (int k = 0; k < nk; ++k) {
+                    umma_i8(tmem_d, ((uint64_t)a_hi << 32) | (a_lo + k * a_kstep), ((uint64_t)b_hi << 32) | (b_lo + k * b_kstep), idesc, accumulate);
+                    accumulate = 1;
+                }
+                a_lo += slab_step; b_lo += 1;
+            }
+    }
+}
+
+template <bool PROF, int EW>
+__global__ void __launch_bounds__(EW == 16 ? 640 : 512, 1)   // 512 caps the kernel at 128 registers: with EW = 8 (384 threads) other streams' small kernels still fit
+ncc_tc_persist_kernel(const TcParams p)
+{
+    constexpr int TCP_THREADS = 32 * (EW + 4);
+    constexpr int TCP_EPI_THREADS = 32 * EW;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* full = bars;                                      // [stages]  slab bytes landed
+    uint64_t* empty = bars + TCP_MAX_STAGES;                    // [stages]  tcgen05.commit
+    uint64_t* tile_full = bars + 2 * TCP_MAX_STAGES;            // [2] image tile staged (64 stager arrivals)
+    uint64_t* tile_empty = tile_full + 2;                       // [2] tcgen05.commit: MMAs reading the tile retired
+    uint64_t* acc_full = tile_full + 4;                         // [2] tcgen05.commit: accumulator complete
+    uint64_t* acc_empty = tile_full + 6;                        // [2] 256 epilogue arrivals: accumulator read out
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tile_full + 8);
+
+    const int kb_img = 2 * p.nk;
+    const uint32_t tile_bytes = ((uint32_t)kb_img * p.R * 16 + 127) & ~127u;
+    const uint32_t stage_bytes = (uint32_t)p.ds * p.slab_bytes;
+    uint8_t* tiles = smem + 256;
+    uint8_t* ring = tiles + 2 * tile_bytes;
+    const int xw = p.mode == 0 ? 16 : 128;
+    const int my_tiles = (p.tiles_total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    uint32_t tmem_cols = 32;                                    // two accumulators; tcgen05.alloc wants a power of two
+    while (tmem_cols < 2u * (uint32_t)p.N) tmem_cols <<= 1;
+    const uint32_t acc_stride = tmem_cols >> 1;
+
+    if (tid == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tile_full[b], TCP_STAGERS); mbar_init(&tile_empty[b], 1);
+            mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], TCP_EPI_THREADS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == EW) tmem_alloc(tmem_slot, tmem_cols);
+    // the first image tile is staged by the whole CTA (nothing else to do yet); the stagers take over from the second
+    stage_image_tile<TCP_THREADS>(tiles, p.img, p.pitch, p.H, ((int)blockIdx.x % p.tiles_x) * xw * p.C, ((int)blockIdx.x / p.tiles_x) * p.N,
+                                  p.R, kb_img, tid);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == EW) {
+        // ===== slab producer: the slab sequence of a tile repeats for every tile; the ring position runs on.
+        // The whole warp walks the loop (warp-uniform control flow, uniform registers); one elected lane issues.
+        int s = 0;
+        uint32_t ph = 1;                                        // parity of the previous use of slot s (fresh barrier: passes)
+        long long w_empty = 0;
+        const int ds = p.ds, h = p.h, stages = p.stages, slab_bytes = p.slab_bytes;
+        const uint8_t* slabs = p.slabs;
+        for (int i = 0; i < my_tiles; ++i) {
+            const uint8_t* src = slabs;
+            for (int dy = 0; dy < h; dy += ds) {
+                const long long c0 = PROF ? clock64() : 0;
+                mbar_wait(&empty[s], ph);
+                if (PROF) w_empty += clock64() - c0;
+                const uint32_t bytes = (uint32_t)min(ds, h - dy) * (uint32_t)slab_bytes;
+                if (elect_one()) {
+                    mbar_expect_tx(&full[s], bytes);
+                    bulk_g2s(ring + (size_t)s * stage_bytes, src, bytes, &full[s]);
+                }
+                src += stage_bytes;
+                if (++s == stages) { s = 0; ph ^= 1u; }
+            }
+        }
+        if (PROF && lane == 0) p.prof[16 * blockIdx.x + 8] = w_empty;
+        __syncwarp();
+    } else if (warp == EW + 1) {
+        // ===== MMA issuer: warp-uniform loop, one elected lane issues.  The issue loop is kept to a few
+        // instructions per MMA: a single warp retires an instruction every few clocks, an MMA lasts ~100.
+        const uint32_t idesc = (2u << 4) | ((uint32_t)(p.N >> 3) << 17) | ((128u >> 4) << 24);   // S32 accum, u8 x u8, K-major
+        const uint32_t lbo_b = (uint32_t)p.R * 16;
+        const int ds = p.ds, h = p.h, nk = p.nk, stages = p.stages;
+        const uint64_t a_desc0 = umma_desc(smem_u32(ring), (uint32_t)p.a_kblk, 128);
+        const uint32_t a_hi = (uint32_t)(a_desc0 >> 32), a_lo0 = (uint32_t)a_desc0;
+        const uint32_t a_kstep = (uint32_t)(2 * p.a_kblk) >> 4, b_kstep = (2 * lbo_b) >> 4;     // descriptor address unit: 16 B
+        const uint32_t slab_step = (uint32_t)p.slab_bytes >> 4, stage_step = stage_bytes >> 4;
+        int s = 0;
+        uint32_t ph = 0;
+        long long w_tile = 0, w_acc = 0, w_full = 0;
+        const long long m_begin = PROF ? clock64() : 0;
+        for (int i = 0; i < my_tiles; ++i) {
+            const int b = i & 1, u = i >> 1;
+            const long long c0 = PROF ? clock64() : 0;
+            mbar_wait(&tile_full[b], u & 1);
+            const long long c1 = PROF ? clock64() : 0;
+            mbar_wait(&acc_empty[b], (u & 1) ^ 1);              // fresh barrier: parity 1 passes
+            if (PROF) { w_tile += c1 - c0; w_acc += clock64() - c1; }
+            tc_fence_after();
+            const uint64_t b_desc0 = umma_desc(smem_u32(tiles + (size_t)b * tile_bytes), lbo_b, 128);
+            const uint32_t b_hi = (uint32_t)(b_desc0 >> 32), b_lo0 = (uint32_t)b_desc0;
+            const uint32_t tmem_d = tmem_base + (uint32_t)b * acc_stride;
+            for (int dy0 = 0; dy0 < h; dy0 += ds) {
+                const long long c2 = PROF ? clock64() : 0;
+                mbar_wait(&full[s], ph);
+                if (PROF) w_full += clock64() - c2;
+                tc_fence_after();
+                if (elect_one()) {
+                    if (!PROF || !(p.dbg & 2))
+                        issue_rows_any(nk, tmem_d, a_lo0 + (uint32_t)s * stage_step, b_lo0 + (uint32_t)dy0, a_hi, b_hi, a_kstep, b_kstep,
+                                       slab_step, min(ds, h - dy0), idesc, dy0 != 0);
+                    umma_commit(&empty[s]);                    // frees the ring slot when these MMAs retire
+                }
+                if (++s == stages) { s = 0; ph ^= 1u; }
+            }
+            if (elect_one()) {
+                umma_commit(&acc_full[b]);                     // epilogue may read this accumulator
+                umma_commit(&tile_empty[b]);                   // stagers may overwrite this image tile
+            }
+        }
+        if (PROF && lane == 0) {
+            long long* q = p.prof + 16 * blockIdx.x;
+            q[0] = w_tile; q[1] = w_acc; q[2] = w_full; q[3] = clock64() - m_begin;
+        }
+        __syncwarp();
+    } else if (warp >= EW + 2) {
+        // ===== image tile stagers =====
+        const int t = tid - 32 * (EW + 2);
+        long long w_te = 0, w_work = 0;
+        for (int i = 0; i < my_tiles; ++i) {
+            const int b = i & 1, u = i >> 1;
+            const int ti = (int)blockIdx.x + i * (int)gridDim.x;
+            const int x0 = (ti % p.tiles_x) * xw, y0 = (ti / p.tiles_x) * p.N;
+            const long long c0 = PROF ? clock64() : 0;
+            mbar_wait(&tile_empty[b], (u & 1) ^ 1);
+            const long long c1 = PROF ? clock64() : 0;
+            if (i > 0 && (!PROF || !(p.dbg & 4)))
+                stage_image_tile<TCP_STAGERS>(tiles + (size_t)b * tile_bytes, p.img, p.pitch, p.H, x0 * p.C, y0, p.R, kb_img, t);
+            fence_async_smem();                                // generic-proxy writes -> visible to the MMA (async proxy)
+            mbar_arrive(&tile_full[b]);
+            if (PROF) { w_te += c1 - c0; w_work += clock64() - c1; }
+        }
+        if (PROF && t == 0) { p.prof[16 * blockIdx.x + 6] = w_te; p.prof[16 * blockIdx.x + 7] = w_work; }
+    } else {
+        // ===== epilogue warps =====
+        long long w_af = 0, w_epi = 0;
+        for (int i = 0; i < my_tiles; ++i) {
+            const int b = i & 1, u = i >> 1;
+            const int ti = (int)blockIdx.x + i * (int)gridDim.x;
+            const int x0 = (ti % p.tiles_x) * xw, y0 = (ti / p.tiles_x) * p.N;
+            epilogue_prefetch_first(p, x0, y0, warp, lane, EW / 4);
+            const long long c0 = PROF ? clock64() : 0;
+            mbar_wait(&acc_full[b], u & 1);
+            const long long c1 = PROF ? clock64() : 0;
+            tc_fence_after();
+            if (!PROF || !(p.dbg & 1)) epilogue_tile(p, tmem_base + (uint32_t)b * acc_stride, x0, y0, warp, lane, EW / 4);
+            tc_fence_before();
+            mbar_arrive(&acc_empty[b]);
+            if (PROF) { w_af += c1 - c0; w_epi += clock64() - c1; }
+        }
+        if (PROF && tid == 0) { p.prof[16 * blockIdx.x + 4] = w_af; p.prof[16 * blockIdx.x + 5] = w_epi; }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == EW) tmem_dealloc(tmem_base, tmem_cols);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -418,10 +692,6 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v)
 {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                  ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 // One lane's A row for one dy: output word j = funnel(W[j-A-1], W[j-A], 8s) with W[k] = template word k
@@ -598,7 +868,8 @@ ncc_tc_ts_kernel(const TsParams p)
             uint32_t v[16];
             tmem_ld16(tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c0, v);
             if (!live || y0 + c0 >= p.mh) continue;
-            epilogue16(v, y0 + c0, p.mh, p.mw, x, area, sumT, ct, is_const, p.S + tm->mom_off, p.rsD + tm->mom_off, out, CandSink{nullptr, nullptr, 0, 0.f, 0, 0, 0});
+            epilogue16(v, y0 + c0, p.mh, p.mw, x, area, sumT, ct, is_const, reinterpret_cast<const uint2*>(p.S) + tm->mom_off, out,
+                       CandSink{nullptr, nullptr, 0, 0.f, 0, 0, 0}, false);
         }
     }
     tc_fence_before();
@@ -654,12 +925,16 @@ __global__ void window_moments_kernel(SatView sat, const uint32_t* __restrict__ 
         // window sums of squares < 2^32 on the tensor path (h*w*C <= 66051): the 32-bit wrap-around table is exact
         const unsigned long long q = sat_window_s(sat_q32, sat.pitch, y, x, sd.h, sd.w);
         unsigned long long d1 = area * q;
+        uint32_t s0 = 0;
         for (int c = 0; c < C; ++c) {
             const uint32_t s = sat_window_s(sat.s + c * sat.plane, sat.pitch, y, x, sd.h, sd.w);
             d1 -= (unsigned long long)s * s;
-            S[c * mom_plane + sd.off + idx] = s;
+            if (C > 1) S[c * mom_plane + sd.off + idx] = s;
+            s0 = s;
         }
-        rsD[sd.off + idx] = d1 ? rsqrtf((float)d1) : 0.0f;
+        const float rs = d1 ? rsqrtf((float)d1) : 0.0f;
+        if (C > 1) rsD[sd.off + idx] = rs;
+        else reinterpret_cast<uint2*>(S)[sd.off + idx] = make_uint2(s0, __float_as_uint(rs));   // one 8-byte load per pixel in the epilogue
     }
 }
 
@@ -783,6 +1058,94 @@ int launch_ncc_tc(mtm_ctx* ctx, const TcGroup& g)
     p.slabs = ctx->d_slabs + g.arena_off; p.slab_bytes = g.slab_bytes; p.a_kblk = g.a_kblk; p.nk = g.nk; p.ds = g.ds;
     p.mode = g.mode; p.h = g.h; p.w = g.w;
     p.mh = im.H - g.h_min + 1; p.mw = im.W - g.w_min + 1;      // tile grid covers the largest member map
+    p.meta = ctx->d_meta; p.order = ctx->d_order + g.first; p.count = g.count;
+    p.S = ctx->d_wS; p.rsD = ctx->d_wR; p.maps = ctx->d_maps;
+    p.C = im.C; p.mom_plane = ctx->moments_total;
+    if (ctx->cand_on) { p.cand = ctx->d_cand; p.cand_count = ctx->d_cand_count; p.cand_cap = MTM_CAND_CAP; p.cand_thr = ctx->cand_thr; }
+
+    // ---- persistent pipeline (two image tiles + slab ring in shared memory, two accumulators in TMEM)
+    static const bool persist_off = getenv("MTM_B200_PERSIST") && atoi(getenv("MTM_B200_PERSIST")) == 0;
+    if (!persist_off) {
+        const int xw_p = g.mode == 0 ? 16 : 128;
+        const int gx_p = (p.mw + xw_p - 1) / xw_p;
+        int ds_p = std::max(1, std::min(g.h, 24576 / g.slab_bytes));           // slabs (template rows) per ring stage
+        if (getenv("MTM_B200_DS")) ds_p = std::max(1, std::min(g.h, atoi(getenv("MTM_B200_DS"))));   // experiments
+        const size_t stage_b = (size_t)ds_p * g.slab_bytes;
+        const int force_n = getenv("MTM_B200_FORCE_N") ? atoi(getenv("MTM_B200_FORCE_N")) : 0;
+        // Cost model (clocks per CTA).  Per MMA: tensor pipe n/2, shared-memory traffic (A 4 KB read + 4 KB slab write +
+        // 32*n B read at 128 B/clk) 64 + n/4.  The epilogue of a tile (~TCP_EPI_CLK_PER_ROW clocks per row with 8 warps)
+        // overlaps the MMAs of the next one; the first image tile and the last epilogue are exposed.
+        int bestN = 0, best_stages = 0, best_ew = 8;
+        double best_cost = 1e300;
+        int force_ew = 0;
+        if (getenv("MTM_B200_EW")) { const int e = atoi(getenv("MTM_B200_EW")); force_ew = (e == 16 || e == 12) ? e : 8; }   // experiments
+        for (int n = 256; n >= 32; n -= 16) {
+            if (force_n && n != force_n) continue;
+            const size_t tile_b = ((size_t)2 * g.nk * (n + g.h - 1) * 16 + 127) & ~(size_t)127;
+            if (256 + 2 * tile_b + 3 * stage_b > 227 * 1024) continue;
+            const int stages = (int)std::min<size_t>(TCP_MAX_STAGES, (227 * 1024 - 256 - 2 * tile_b) / stage_b);
+            const long long tiles = (long long)gx_p * ((p.mh + n - 1) / n);
+            const long long per_cta = (tiles + ctx->sm_count - 1) / ctx->sm_count;
+            const double mma_tile = (double)g.h * g.nk * std::max(0.5 * n, 64.0 + 0.25 * n);
+            for (int ew = 8; ew <= 16; ew += 4) {
+                if (force_ew && ew != force_ew) continue;
+                const double epi_tile = n * TCP_EPI_CLK_PER_ROW * 8.0 / ew * (ew == 16 ? 1.1 : 1.0);   // 96-register build of EW = 16
+                const double cost = (double)per_cta * std::max(mma_tile, epi_tile) * (ew == 8 ? 1.0 : 1.02) + epi_tile + 40.0 * (n + g.h);
+                if (cost < best_cost - 1e-9) { best_cost = cost; bestN = n; best_stages = stages; best_ew = ew; }
+            }
+        }
+        if (bestN) {
+            const size_t tile_b = ((size_t)2 * g.nk * (bestN + g.h - 1) * 16 + 127) & ~(size_t)127;
+            p.N = bestN; p.R = bestN + g.h - 1; p.stages = best_stages; p.ds = ds_p;
+            p.tiles_x = gx_p; p.tiles_total = gx_p * ((p.mh + bestN - 1) / bestN);
+            const size_t smem_bytes = 256 + 2 * tile_b + (size_t)best_stages * stage_b;
+            if (!ctx->tcp_attr_set) {
+                MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_kernel<false, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_kernel<true, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                ctx->tcp_attr_set = true;
+            }
+            const int grid_p = std::min(p.tiles_total, ctx->sm_count);
+            static const bool prof = getenv("MTM_B200_PROF") != nullptr;       // debug: per-CTA role clocks to stderr
+            static const int pdbg = getenv("MTM_B200_PDBG") ? atoi(getenv("MTM_B200_PDBG")) : 0;
+            long long* d_prof = nullptr;
+            if (prof) {
+                MTM_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&d_prof), (size_t)grid_p * 16 * sizeof(long long)));
+                MTM_CUDA(ctx, cudaMemsetAsync(d_prof, 0, (size_t)grid_p * 16 * sizeof(long long), ctx->stream));
+                p.prof = d_prof;
+            }
+            p.dbg = pdbg;
+            const int ew = best_ew;
+            if (ew == 12) {
+                if (prof) ncc_tc_persist_kernel<true, 12><<<grid_p, 32 * 16, smem_bytes, ctx->stream>>>(p);
+                else ncc_tc_persist_kernel<false, 12><<<grid_p, 32 * 16, smem_bytes, ctx->stream>>>(p);
+            } else if (ew == 16) {
+                if (prof) ncc_tc_persist_kernel<true, 16><<<grid_p, 32 * 20, smem_bytes, ctx->stream>>>(p);
+                else ncc_tc_persist_kernel<false, 16><<<grid_p, 32 * 20, smem_bytes, ctx->stream>>>(p);
+            } else {
+                if (prof) ncc_tc_persist_kernel<true, 8><<<grid_p, 32 * 12, smem_bytes, ctx->stream>>>(p);
+                else ncc_tc_persist_kernel<false, 8><<<grid_p, 32 * 12, smem_bytes, ctx->stream>>>(p);
+            }
+            MTM_LAUNCH_CHECK(ctx);
+            if (prof) {
+                std::vector<long long> hp((size_t)grid_p * 16);
+                MTM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                MTM_CUDA(ctx, cudaMemcpy(hp.data(), d_prof, hp.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+                cudaFree(d_prof);
+                double a[16] = {0};
+                for (int c = 0; c < grid_p; ++c) for (int k = 0; k < 16; ++k) a[k] += (double)hp[16 * c + k] / grid_p;
+                fprintf(stderr, "[mtm prof] persist: %d CTAs x %.2f tiles N=%d stages=%d ew=%d smem=%zu | mma: wait tile %.0f acc %.0f slabs %.0f total %.0f | "
+                        "epilogue: wait %.0f work %.0f | stager: wait %.0f work %.0f | producer wait %.0f\n",
+                        grid_p, (double)p.tiles_total / grid_p, p.N, p.stages, ew, smem_bytes, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8]);
+            }
+            return MTM_OK;
+        }
+    }
+
+    // ---- one tile per CTA (tiles too large for two buffers, e.g. 256 x 256 templates)
     // Tile height: the planned g.N is the largest that fits; a smaller multiple of 16 can cut the number
     // of CTA waves (e.g. C2: 468 tiles of 256 rows = 1.58 waves of 296 slots -> 585 tiles of 208 rows =
     // 1.98 waves).  Cost model: waves x (rows + fixed per-tile work expressed in rows).
@@ -802,10 +1165,6 @@ int launch_ncc_tc(mtm_ctx* ctx, const TcGroup& g)
     if (getenv("MTM_B200_FORCE_N")) bestN = g.N;
     p.N = bestN; p.R = bestN + g.h - 1;
     const size_t smem_bytes = smem_for(bestN);
-    p.meta = ctx->d_meta; p.order = ctx->d_order + g.first; p.count = g.count;
-    p.S = ctx->d_wS; p.rsD = ctx->d_wR; p.maps = ctx->d_maps;
-    p.C = im.C; p.mom_plane = ctx->moments_total;
-    if (ctx->cand_on) { p.cand = ctx->d_cand; p.cand_count = ctx->d_cand_count; p.cand_cap = MTM_CAND_CAP; p.cand_thr = ctx->cand_thr; }
     if (!ctx->tc_attr_set) {
         MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         ctx->tc_attr_set = true;
