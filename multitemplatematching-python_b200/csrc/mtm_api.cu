@@ -108,6 +108,12 @@ static int reserve_hits(mtm_ctx* ctx, int cap)
     MTM_CUDA(ctx, cudaMemsetAsync(ctx->d_blockB, 0, bytes, ctx->stream));
     ctx->hit_cap = cap;
     MTM_TRY(reserve_pinned(ctx, ctx->h_stage, ctx->h_stage_cap, bytes));
+    if (!ctx->h_mirror) {
+        const size_t mb = MTM_HIT_HEADER + (size_t)MTM_MIRROR_HITS * sizeof(DevHit);
+        MTM_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_mirror), mb, cudaHostAllocMapped));
+        memset(ctx->h_mirror, 0, mb);
+        MTM_CUDA(ctx, cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx->d_mirror), ctx->h_mirror, 0));
+    }
     return MTM_OK;
 }
 
@@ -171,7 +177,7 @@ int mtm_destroy(mtm_ctx* ctx)
     cudaFree(ctx->img.pixf); cudaFree(ctx->img.satf_s); cudaFree(ctx->img.satf_q); cudaFree(ctx->d_tmpl_centred);
     cudaFree(ctx->d_slabs); cudaFree(ctx->d_wS); cudaFree(ctx->d_wR); cudaFree(ctx->d_sizes);
     for (int k = 0; k < MTM_MAX_INFLIGHT; ++k) { cudaFree(ctx->d_slot[k]); cudaFreeHost(ctx->h_slot[k]); if (ctx->ev_slot[k]) cudaEventDestroy(ctx->ev_slot[k]); }
-    cudaFreeHost(ctx->h_tmpl_stage); cudaFreeHost(ctx->h_stage); cudaFreeHost(ctx->h_geom);
+    cudaFreeHost(ctx->h_tmpl_stage); cudaFreeHost(ctx->h_stage); cudaFreeHost(ctx->h_geom); cudaFreeHost(ctx->h_mirror);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (int k = 0; k < MTM_NCC_RING; ++k)
@@ -256,6 +262,7 @@ static int set_image_impl(mtm_ctx* ctx, const void* pixels, int H, int W, int C,
         if (C == 2) return mtm_fail(ctx, MTM_ERR_UNSUPPORTED, "mtm_set_image: 2-channel float32 images");
         im.pitch_e = ((int64_t)W * C + 3) / 4 * 4;
         MTM_TRY(mtm_reserve(ctx, im.pixf, ctx->imgf_cap, (size_t)(H * im.pitch_e + 64)));
+        const bool same_shape_f = (im.H == H && im.W == W && im.C == C && ctx->img_dtype == dtype);
         im.H = H; im.W = W; im.C = C;
         im.sat_pitch = ((int64_t)W + 1 + 3) / 4 * 4;
         g_marks.mark(ctx, "begin");
@@ -266,7 +273,7 @@ static int set_image_impl(mtm_ctx* ctx, const void* pixels, int H, int W, int C,
         MTM_TRY(mtm_reserve(ctx, im.satf_q, ctx->satf_q_cap, (size_t)(H + 1) * im.sat_pitch));
         MTM_TRY(mtm_reserve(ctx, ctx->scratch, ctx->scratch_cap, (size_t)2 * (C + 1) * H * W + 16));
         ctx->img_dtype = dtype;
-        ctx->geometry_valid = false;
+        if (!same_shape_f) ctx->geometry_valid = false;     // map offsets depend on the image shape only
         ctx->moments_valid = false;
         ctx->masked_image_valid = false;
         MTM_TRY(launch_build_sat_f32(ctx));
@@ -274,6 +281,7 @@ static int set_image_impl(mtm_ctx* ctx, const void* pixels, int H, int W, int C,
     }
     const int64_t pitch = (((int64_t)W * C + 64 * C + 64) + 127) / 128 * 128;
     const bool reshape = (im.H != H || im.W != W || im.C != C);
+    const bool same_shape = !reshape && ctx->img_dtype == dtype;
     MTM_TRY(mtm_reserve(ctx, im.pix, ctx->img_cap, (size_t)(H * pitch + 256)));
     if (reshape) MTM_CUDA(ctx, cudaMemsetAsync(im.pix, 0, ctx->img_cap, ctx->stream));
     im.pitch = pitch; im.H = H; im.W = W; im.C = C;
@@ -288,7 +296,8 @@ static int set_image_impl(mtm_ctx* ctx, const void* pixels, int H, int W, int C,
     MTM_TRY(mtm_reserve(ctx, im.sat_q32, ctx->sat_q32_cap, (size_t)(H + 1) * im.sat_pitch));
     MTM_TRY(mtm_reserve(ctx, ctx->scratch, ctx->scratch_cap, (size_t)(C + 1) * H * ((W + 3) / 4 * 4)));
     ctx->img_dtype = dtype;
-    ctx->geometry_valid = false;
+    if (!same_shape) ctx->geometry_valid = false;           // map offsets depend on the image shape only: a stream of
+                                                            // equal-sized images keeps them (and skips the sync in ensure_geometry)
     ctx->moments_valid = false;
     ctx->masked_image_valid = false;
     MTM_TRY(launch_build_sat(ctx));
@@ -555,6 +564,29 @@ static int download_block(mtm_ctx* ctx, const uint8_t* d_block, int* n_raw, int*
     return MTM_OK;
 }
 
+// Same contract as download_block for a result that finalize_small_kernel also stored in the mapped mirror:
+// one stream synchronise, no copy engine round trip.  Results longer than the mirror fetch the rest from the block.
+static int download_mirror(mtm_ctx* ctx, const uint8_t* d_block, int* n_raw, int* n_valid, int* declined)
+{
+    MTM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int32_t* hdr = reinterpret_cast<const int32_t*>(ctx->h_mirror);
+    const int n = hdr[0];
+    *n_valid = n;
+    *n_raw = std::max(hdr[0], hdr[1]);
+    *declined = hdr[2];
+    const int have = std::min(std::max(n, 0), MTM_MIRROR_HITS);
+    memcpy(ctx->h_stage, ctx->h_mirror, MTM_HIT_HEADER + (size_t)have * sizeof(DevHit));
+    ctx->ctr.d2h_bytes += (int64_t)(MTM_HIT_HEADER + (size_t)have * sizeof(DevHit));
+    if (hdr[2]) return MTM_OK;
+    if (n > have && n <= ctx->hit_cap) {
+        const size_t first = MTM_HIT_HEADER + (size_t)have * sizeof(DevHit), rest = (size_t)(n - have) * sizeof(DevHit);
+        MTM_CUDA(ctx, cudaMemcpyAsync(ctx->h_stage + first, d_block + first, rest, cudaMemcpyDeviceToHost, ctx->stream));
+        MTM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->ctr.d2h_bytes += (int64_t)rest;
+    }
+    return MTM_OK;
+}
+
 static void copy_out(const mtm_ctx* ctx, mtm_hit* hits, int n)
 {
     const DevHit* src = reinterpret_cast<const DevHit*>(ctx->h_stage + MTM_HIT_HEADER);
@@ -782,9 +814,9 @@ int mtm_match_templates(mtm_ctx* ctx, int method, int64_t n_object, double score
         g_marks.mark(ctx, "peaks");
         int n_raw = 0, n = 0, declined = 0;
         MTM_TRY(launch_finalize_small(ctx, minimize, n_object != 1, n_object == 1, 1, thr_nms, ascending, n_object,
-                                      (float)max_overlap));
+                                      (float)max_overlap, nullptr, true));
         g_marks.mark(ctx, "finalize");
-        MTM_TRY(download_block(ctx, ctx->d_blockB, &n_raw, &n, &declined));
+        MTM_TRY(download_mirror(ctx, ctx->d_blockB, &n_raw, &n, &declined));
         g_marks.mark(ctx, "download");
         g_marks.report(ctx);
         if (declined == 2) { ctx->cand_valid = false; continue; }          // candidate list overflowed: stream the maps

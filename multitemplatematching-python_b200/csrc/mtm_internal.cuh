@@ -143,6 +143,7 @@ struct mtm_ctx {
     int32_t* d_keep = nullptr;           // kept indices (capacity hit_cap)
     size_t per_tmpl_cap = 0, best_cap = 0;
     uint8_t* h_stage = nullptr; size_t h_stage_cap = 0;   // pinned up/download buffer
+    uint8_t* h_mirror = nullptr; uint8_t* d_mirror = nullptr;   // mapped pinned result mirror (header + MTM_MIRROR_HITS hits) and its device alias
 
     // candidate list written by the tcgen05 epilogue (pixels above the threshold), consumed by verify_candidates
     DevHit* d_cand = nullptr; int32_t* d_cand_count = nullptr;
@@ -204,8 +205,9 @@ int launch_peaks(mtm_ctx* ctx, int method, int64_t n_object, float thr32, double
 // in-place sort of block A (mode 0: findMatches order, mode 1: NMSBoxes order)
 int launch_sort_hits(mtm_ctx* ctx, int mode, int minimize, int ascending_key, int check_trivial);
 // fast path (raw count <= 1024): sort(s) [+ NMS] in one launch; sets header[2] = 1 when it declines
+constexpr int MTM_MIRROR_HITS = 256;
 int launch_finalize_small(mtm_ctx* ctx, int minimize, int check_trivial, int presorted, int do_nms, float thr32,
-                          int ascending, int64_t n_object, float max_overlap, uint8_t* out_block = nullptr);
+                          int ascending, int64_t n_object, float max_overlap, uint8_t* out_block = nullptr, bool mirror = false);
 // block A (sorted mode 1) -> block B
 int launch_nms(mtm_ctx* ctx, float thr32, int ascending, int64_t n_object, float max_overlap);
 

@@ -447,11 +447,11 @@ ncc_tc_kernel(const TcParams p)
 // accumulators in TMEM turn the three phases of a tile (stage the image rows / MMA / epilogue) into
 // a pipeline, so the tensor pipe works on tile i+1 while tile i is normalised and stored and the
 // rows of tile i+2 are fetched.
-//   warps 0 .. EW-1   epilogue (TMEM -> registers -> score map), warp%4 = TMEM lane quarter; EW = 8 or 16
+//   warps 0 .. EW-1   epilogue (TMEM -> registers -> score map), warp%4 = TMEM lane quarter; EW = 8 or 12
 //   warp  EW          Toeplitz slab producer (cp.async.bulk into the ring, continuous over tiles)
 //   warp  EW+1        MMA issuer (one elected lane)
 //   warps EW+2, EW+3  image tile stagers (global -> registers -> shared memory, [k-block][row][16 B])
-// EW = 16 serves small templates, whose tiles spend longer in the epilogue than in the MMAs.
+// EW = 12 serves small templates, whose tiles spend longer in the epilogue than in the MMAs.
 constexpr int TCP_MAX_STAGES = 8;
 constexpr double TCP_EPI_CLK_PER_ROW = 100.0;   // measured: epilogue clocks per output row of a tile with 8 epilogue warps
 constexpr int TCP_STAGERS = 64;
@@ -499,7 +499,7 @@ __device__ __forceinline__ void issue_rows_any(int nk, uint32_t tmem_d, uint32_t
 }
 
 template <bool PROF, int EW>
-__global__ void __launch_bounds__(EW == 16 ? 640 : 512, 1)   // 512 caps the kernel at 128 registers: with EW = 8 (384 threads) other streams' small kernels still fit
+__global__ void __launch_bounds__(512, 1)   // 128 registers; with EW = 8 (384 threads) a quarter of the register file stays free for other streams' small kernels
 ncc_tc_persist_kernel(const TcParams p)
 {
     constexpr int TCP_THREADS = 32 * (EW + 4);
@@ -1078,7 +1078,7 @@ int launch_ncc_tc(mtm_ctx* ctx, const TcGroup& g)
         int bestN = 0, best_stages = 0, best_ew = 8;
         double best_cost = 1e300;
         int force_ew = 0;
-        if (getenv("MTM_B200_EW")) { const int e = atoi(getenv("MTM_B200_EW")); force_ew = (e == 16 || e == 12) ? e : 8; }   // experiments
+        if (getenv("MTM_B200_EW")) { const int e = atoi(getenv("MTM_B200_EW")); force_ew = e == 12 ? 12 : 8; }   // experiments
         for (int n = 256; n >= 32; n -= 16) {
             if (force_n && n != force_n) continue;
             const size_t tile_b = ((size_t)2 * g.nk * (n + g.h - 1) * 16 + 127) & ~(size_t)127;
@@ -1087,10 +1087,11 @@ int launch_ncc_tc(mtm_ctx* ctx, const TcGroup& g)
             const long long tiles = (long long)gx_p * ((p.mh + n - 1) / n);
             const long long per_cta = (tiles + ctx->sm_count - 1) / ctx->sm_count;
             const double mma_tile = (double)g.h * g.nk * std::max(0.5 * n, 64.0 + 0.25 * n);
-            for (int ew = 8; ew <= 16; ew += 4) {
+            for (int ew = 8; ew <= 12; ew += 4) {
                 if (force_ew && ew != force_ew) continue;
-                const double epi_tile = n * TCP_EPI_CLK_PER_ROW * 8.0 / ew * (ew == 16 ? 1.1 : 1.0);   // 96-register build of EW = 16
-                const double cost = (double)per_cta * std::max(mma_tile, epi_tile) * (ew == 8 ? 1.0 : 1.02) + epi_tile + 40.0 * (n + g.h);
+                const double epi_tile = n * TCP_EPI_CLK_PER_ROW * 8.0 / ew;
+                // EW = 12 fills the register file (no co-resident kernels of other streams): it has to win by 10 %
+                const double cost = ((double)per_cta * std::max(mma_tile, epi_tile) + epi_tile + 40.0 * (n + g.h)) * (ew == 8 ? 1.0 : 1.1);
                 if (cost < best_cost - 1e-9) { best_cost = cost; bestN = n; best_stages = stages; best_ew = ew; }
             }
         }
@@ -1104,8 +1105,6 @@ int launch_ncc_tc(mtm_ctx* ctx, const TcGroup& g)
                 MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
                 MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_kernel<false, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
                 MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_kernel<true, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-                MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-                MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
                 ctx->tcp_attr_set = true;
             }
             const int grid_p = std::min(p.tiles_total, ctx->sm_count);
@@ -1122,9 +1121,6 @@ int launch_ncc_tc(mtm_ctx* ctx, const TcGroup& g)
             if (ew == 12) {
                 if (prof) ncc_tc_persist_kernel<true, 12><<<grid_p, 32 * 16, smem_bytes, ctx->stream>>>(p);
                 else ncc_tc_persist_kernel<false, 12><<<grid_p, 32 * 16, smem_bytes, ctx->stream>>>(p);
-            } else if (ew == 16) {
-                if (prof) ncc_tc_persist_kernel<true, 16><<<grid_p, 32 * 20, smem_bytes, ctx->stream>>>(p);
-                else ncc_tc_persist_kernel<false, 16><<<grid_p, 32 * 20, smem_bytes, ctx->stream>>>(p);
             } else {
                 if (prof) ncc_tc_persist_kernel<true, 8><<<grid_p, 32 * 12, smem_bytes, ctx->stream>>>(p);
                 else ncc_tc_persist_kernel<false, 8><<<grid_p, 32 * 12, smem_bytes, ctx->stream>>>(p);

@@ -213,11 +213,11 @@ __device__ void smem_bitonic(DevHit* sh, int npad, const SortCtx& sc)
 
 // do_nms == 0: findMatches order -> written back to `hits` (block A), count[0]/[1] updated.
 // do_nms == 1: ... then MTM.NMS -> `out` (block B), out_count[0] = kept, out_count[1] = raw count.
-__global__ void __launch_bounds__(256, 1)
-finalize_small_kernel(DevHit* __restrict__ hits, int cap, int32_t* __restrict__ count, const TmplMeta* __restrict__ meta,
-                      const int32_t* __restrict__ nontrivial, int minimize, int check_trivial, int presorted, int do_nms,
-                      DevHit* __restrict__ out, int32_t* __restrict__ out_count, float thr32, int ascending,
-                      long long n_object, float max_overlap)
+__device__ __forceinline__ void
+finalize_small_body(DevHit* __restrict__ hits, int cap, int32_t* __restrict__ count, const TmplMeta* __restrict__ meta,
+                    const int32_t* __restrict__ nontrivial, int minimize, int check_trivial, int presorted, int do_nms,
+                    DevHit* __restrict__ out, int32_t* __restrict__ out_count, float thr32, int ascending,
+                    long long n_object, float max_overlap)
 {
     __shared__ DevHit sh[FIN_CAP];
     __shared__ int s_live, s_kept;
@@ -326,17 +326,40 @@ finalize_small_kernel(DevHit* __restrict__ hits, int cap, int32_t* __restrict__ 
     if (tid == 0) out_count[0] = kept;
 }
 
+// `mirror` (optional): mapped pinned host memory.  The header and the first MTM_MIRROR_HITS hits of the result are
+// stored there as well, so the synchronous API reads them after a stream synchronise instead of a D2H copy + synchronise.
+__global__ void __launch_bounds__(256, 1)
+finalize_small_kernel(DevHit* __restrict__ hits, int cap, int32_t* __restrict__ count, const TmplMeta* __restrict__ meta,
+                      const int32_t* __restrict__ nontrivial, int minimize, int check_trivial, int presorted, int do_nms,
+                      DevHit* __restrict__ out, int32_t* __restrict__ out_count, float thr32, int ascending,
+                      long long n_object, float max_overlap, uint8_t* __restrict__ mirror)
+{
+    finalize_small_body(hits, cap, count, meta, nontrivial, minimize, check_trivial, presorted, do_nms, out, out_count, thr32,
+                        ascending, n_object, max_overlap);
+    if (!mirror) return;
+    __syncthreads();                                           // the block's own global writes are visible to all its threads
+    const int32_t* hdr = do_nms ? out_count : count;
+    const uint4* src = reinterpret_cast<const uint4*>(do_nms ? out : hits);
+    const int n = min(max(hdr[0], 0), MTM_MIRROR_HITS);
+    uint4* dst = reinterpret_cast<uint4*>(mirror);
+    const int tid = threadIdx.x;
+    if (tid < 2) dst[tid] = reinterpret_cast<const uint4*>(hdr)[tid];          // 32-byte header
+    for (int i = tid; i < 2 * n; i += blockDim.x) dst[2 + i] = src[i];         // 32-byte hits
+    __threadfence_system();
+}
+
 }  // namespace
 
 int launch_finalize_small(mtm_ctx* ctx, int minimize, int check_trivial, int presorted, int do_nms, float thr32,
-                          int ascending, int64_t n_object, float max_overlap, uint8_t* out_block)
+                          int ascending, int64_t n_object, float max_overlap, uint8_t* out_block, bool mirror)
 {
     uint8_t* ob = out_block ? out_block : ctx->d_blockB;
+    static_assert(MTM_HIT_HEADER == 32 && sizeof(DevHit) == 32, "mirror layout");
     finalize_small_kernel<<<1, 256, 0, ctx->stream>>>(ctx->hitsA(), ctx->hit_cap, ctx->countA(), ctx->d_meta,
                                                        ctx->d_nontrivial, minimize, check_trivial, presorted, do_nms,
                                                        reinterpret_cast<DevHit*>(ob + MTM_HIT_HEADER),
                                                        reinterpret_cast<int32_t*>(ob), thr32, ascending, (long long)n_object,
-                                                       max_overlap);
+                                                       max_overlap, mirror ? ctx->d_mirror : nullptr);
     MTM_LAUNCH_CHECK(ctx);
     return MTM_OK;
 }

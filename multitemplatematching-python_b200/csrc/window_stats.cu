@@ -131,7 +131,7 @@ sat_cols_kernel(const uint32_t* __restrict__ scratch, int H, int W, int C, int S
     const uint32_t* src = scratch + table * plane + (live ? sx - 1 : 0);
     unsigned long long tot = 0;
     if (live) {
-#pragma unroll 8
+#pragma unroll 16
         for (int y = y0; y < y1; ++y) tot += __ldg(src + (int64_t)y * SP);
     }
     part[ry][cx] = tot;
@@ -145,7 +145,7 @@ sat_cols_kernel(const uint32_t* __restrict__ scratch, int H, int W, int C, int S
     if (ry == 0) {                                 // SAT row 0 is all zeros
         if (is_q) { sat_q[sx] = 0ull; sat_q32[sx] = 0u; } else ds[sx] = 0u;
     }
-#pragma unroll 8
+#pragma unroll 16
     for (int y = y0; y < y1; ++y) {
         if (live) run += __ldg(src + (int64_t)y * SP);
         const int64_t o = (int64_t)(y + 1) * sat_pitch + sx;
