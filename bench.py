@@ -140,7 +140,7 @@ def main():
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--path", default="auto", choices=["auto", "direct", "tensor"])
     ap.add_argument("--cpu-steps", type=int, default=None, help="steps of the cpu_baseline sample (default: ~15 s)")
-    ap.add_argument("--contexts", type=int, default=3,
+    ap.add_argument("--contexts", type=int, default=4,
                     help="library contexts (CUDA streams) the resident-throughput loop alternates between")
     args = ap.parse_args()
 

@@ -455,6 +455,7 @@ ncc_tc_kernel(const TcParams p)
 constexpr int TCP_MAX_STAGES = 8;
 constexpr double TCP_EPI_CLK_PER_ROW = 100.0;   // measured: epilogue clocks per output row of a tile with 8 epilogue warps
 constexpr int TCP_STAGERS = 64;
+constexpr size_t TCP_SMEM_SOFT = 188 * 1024;     // preferred ceiling of the persistent kernel's shared memory (see launch_ncc_tc)
 
 // MMAs of `rows` consecutive template rows: NK K-chunks each.  Only the low descriptor words move
 // (one 16-byte unit per image row, one slab per template row); they live in uniform registers.
@@ -1075,6 +1076,7 @@ int launch_ncc_tc(mtm_ctx* ctx, const TcGroup& g)
         // Cost model (clocks per CTA).  Per MMA: tensor pipe n/2, shared-memory traffic (A 4 KB read + 4 KB slab write +
         // 32*n B read at 128 B/clk) 64 + n/4.  The epilogue of a tile (~TCP_EPI_CLK_PER_ROW clocks per row with 8 warps)
         // overlaps the MMAs of the next one; the first image tile and the last epilogue are exposed.
+        const size_t smem_soft = getenv("MTM_B200_SMEM_SOFT") ? (size_t)atoi(getenv("MTM_B200_SMEM_SOFT")) * 1024 : TCP_SMEM_SOFT;
         int bestN = 0, best_stages = 0, best_ew = 8;
         double best_cost = 1e300;
         int force_ew = 0;
@@ -1083,7 +1085,11 @@ int launch_ncc_tc(mtm_ctx* ctx, const TcGroup& g)
             if (force_n && n != force_n) continue;
             const size_t tile_b = ((size_t)2 * g.nk * (n + g.h - 1) * 16 + 127) & ~(size_t)127;
             if (256 + 2 * tile_b + 3 * stage_b > 227 * 1024) continue;
-            const int stages = (int)std::min<size_t>(TCP_MAX_STAGES, (227 * 1024 - 256 - 2 * tile_b) / stage_b);
+            // Ring depth: as deep as shared memory allows, but when 4 stages fit under TCP_SMEM_SOFT the rest is left
+            // to the small kernels of other streams (the sort/NMS kernel needs 35 KB) so that they can run beside this one.
+            int stages = (int)std::min<size_t>(TCP_MAX_STAGES, (227 * 1024 - 256 - 2 * tile_b) / stage_b);
+            const size_t soft = smem_soft > 256 + 2 * tile_b ? (smem_soft - 256 - 2 * tile_b) / stage_b : 0;
+            if (soft >= 4) stages = (int)std::min<size_t>(stages, soft);
             const long long tiles = (long long)gx_p * ((p.mh + n - 1) / n);
             const long long per_cta = (tiles + ctx->sm_count - 1) / ctx->sm_count;
             const double mma_tile = (double)g.h * g.nk * std::max(0.5 * n, 64.0 + 0.25 * n);

@@ -100,8 +100,11 @@ sort_hits_kernel(DevHit* __restrict__ hits, int cap, int32_t* __restrict__ count
     }
     __syncthreads();
     SortCtx sc{meta, mode, minimize};
+#pragma unroll 1
     for (int k = 2; k <= npad; k <<= 1) {
+#pragma unroll 1
         for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll 1
             for (int i = tid; i < npad; i += nth) {
                 const int l = i ^ j;
                 if (l > i) {
@@ -195,8 +198,11 @@ constexpr int FIN_CAP = 1024;
 __device__ void smem_bitonic(DevHit* sh, int npad, const SortCtx& sc)
 {
     const int tid = threadIdx.x, nth = blockDim.x;
+#pragma unroll 1
     for (int k = 2; k <= npad; k <<= 1) {
+#pragma unroll 1
         for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll 1
             for (int i = tid; i < npad; i += nth) {
                 const int l = i ^ j;
                 if (l > i) {
@@ -213,12 +219,16 @@ __device__ void smem_bitonic(DevHit* sh, int npad, const SortCtx& sc)
 
 // do_nms == 0: findMatches order -> written back to `hits` (block A), count[0]/[1] updated.
 // do_nms == 1: ... then MTM.NMS -> `out` (block B), out_count[0] = kept, out_count[1] = raw count.
+// PRESORTED / DO_NMS are compile-time: the launch-latency-bound single CTA then walks ~8 KB of code instead of 32 KB
+// (instruction fetch of a cold kernel is a visible part of its ~15 us).
+template <bool PRESORTED, bool DO_NMS>
 __device__ __forceinline__ void
 finalize_small_body(DevHit* __restrict__ hits, int cap, int32_t* __restrict__ count, const TmplMeta* __restrict__ meta,
-                    const int32_t* __restrict__ nontrivial, int minimize, int check_trivial, int presorted, int do_nms,
+                    const int32_t* __restrict__ nontrivial, int minimize, int check_trivial,
                     DevHit* __restrict__ out, int32_t* __restrict__ out_count, float thr32, int ascending,
                     long long n_object, float max_overlap)
 {
+    constexpr bool presorted = PRESORTED, do_nms = DO_NMS;
     __shared__ DevHit sh[FIN_CAP];
     __shared__ int s_live, s_kept;
     __shared__ unsigned long long s_best;
@@ -232,6 +242,7 @@ finalize_small_body(DevHit* __restrict__ hits, int cap, int32_t* __restrict__ co
     int npad = 1;
     while (npad < n_raw) npad <<= 1;
     int dead_local = 0;
+#pragma unroll 1
     for (int i = tid; i < npad; i += nth) {
         DevHit h;
         if (i < n_raw) {
@@ -250,7 +261,9 @@ finalize_small_body(DevHit* __restrict__ hits, int cap, int32_t* __restrict__ co
     if (!presorted && !do_nms) {                                // findMatches order
         SortCtx sc0{meta, 0, minimize};
         smem_bitonic(sh, npad, sc0);
+#pragma unroll 1
         for (int i = tid; i < n; i += nth) store_hit(hits + i, sh[i]);
+#pragma unroll 1
         for (int i = tid; i < n; i += nth) hits[i].seq = i;
         if (tid == 0) { count[0] = n; count[1] = n; }
         return;
@@ -261,6 +274,7 @@ finalize_small_body(DevHit* __restrict__ hits, int cap, int32_t* __restrict__ co
     // ONE sort by (key desc, template asc, row-major index asc): mode 2.  Presorted input
     // (standalone mtm_nms, N_object == 1) keeps its own seq: mode 1.
     if (!presorted) {
+#pragma unroll 1
         for (int i = tid; i < npad; i += nth)
             if (sh[i].tmpl != 0x7fffffff) sh[i].key = ascending ? 1.0f - sh[i].score : sh[i].score;   // seq = row-major index (prep_mode0)
         __syncthreads();
@@ -273,6 +287,7 @@ finalize_small_body(DevHit* __restrict__ hits, int cap, int32_t* __restrict__ co
     }
     if (n_object == 1) {
         unsigned long long kbest = 0ull;
+#pragma unroll 1
         for (int i = tid; i < n; i += nth) {
             const float v = ascending ? -sh[i].score : sh[i].score;
             const unsigned long long key = ((unsigned long long)ordered_f32(v) << 32) |
@@ -281,6 +296,7 @@ finalize_small_body(DevHit* __restrict__ hits, int cap, int32_t* __restrict__ co
         }
         atomicMax(&s_best, kbest);
         __syncthreads();
+#pragma unroll 1
         for (int i = tid; i < n; i += nth) {
             const float v = ascending ? -sh[i].score : sh[i].score;
             const unsigned long long key = ((unsigned long long)ordered_f32(v) << 32) |
@@ -290,6 +306,7 @@ finalize_small_body(DevHit* __restrict__ hits, int cap, int32_t* __restrict__ co
         return;
     }
     if (presorted) {
+#pragma unroll 1
         for (int i = tid; i < npad; i += nth)
             if (i < n) sh[i].key = ascending ? 1.0f - sh[i].score : sh[i].score;
         __syncthreads();
@@ -301,10 +318,12 @@ finalize_small_body(DevHit* __restrict__ hits, int cap, int32_t* __restrict__ co
     const long long limit = n_object < 0 ? (long long)n : n_object;
     if (tid < 32) {
         int kept = 0;
+#pragma unroll 1
         for (int i = 0; i < n && kept < limit; ++i) {
             const DevHit cand = sh[i];
             if (!(cand.key > thr32)) break;
             int sup = 0;
+#pragma unroll 1
             for (int k = tid; k < kept; k += 32) {
                 const DevHit& o = sh[kept_idx[k]];
                 // disjoint boxes have overlap 1.f - (float)1.0 == 0 <= max_overlap: skip the fp64 division
@@ -322,20 +341,23 @@ finalize_small_body(DevHit* __restrict__ hits, int cap, int32_t* __restrict__ co
     }
     __syncthreads();
     const int kept = s_kept;
+#pragma unroll 1
     for (int k = tid; k < kept; k += nth) store_hit(out + k, sh[kept_idx[k]]);
     if (tid == 0) out_count[0] = kept;
 }
 
 // `mirror` (optional): mapped pinned host memory.  The header and the first MTM_MIRROR_HITS hits of the result are
 // stored there as well, so the synchronous API reads them after a stream synchronise instead of a D2H copy + synchronise.
+template <bool PRESORTED, bool DO_NMS>
 __global__ void __launch_bounds__(256, 1)
 finalize_small_kernel(DevHit* __restrict__ hits, int cap, int32_t* __restrict__ count, const TmplMeta* __restrict__ meta,
-                      const int32_t* __restrict__ nontrivial, int minimize, int check_trivial, int presorted, int do_nms,
+                      const int32_t* __restrict__ nontrivial, int minimize, int check_trivial,
                       DevHit* __restrict__ out, int32_t* __restrict__ out_count, float thr32, int ascending,
                       long long n_object, float max_overlap, uint8_t* __restrict__ mirror)
 {
-    finalize_small_body(hits, cap, count, meta, nontrivial, minimize, check_trivial, presorted, do_nms, out, out_count, thr32,
-                        ascending, n_object, max_overlap);
+    constexpr bool do_nms = DO_NMS;
+    finalize_small_body<PRESORTED, DO_NMS>(hits, cap, count, meta, nontrivial, minimize, check_trivial, out, out_count, thr32,
+                                           ascending, n_object, max_overlap);
     if (!mirror) return;
     __syncthreads();                                           // the block's own global writes are visible to all its threads
     const int32_t* hdr = do_nms ? out_count : count;
@@ -355,11 +377,14 @@ int launch_finalize_small(mtm_ctx* ctx, int minimize, int check_trivial, int pre
 {
     uint8_t* ob = out_block ? out_block : ctx->d_blockB;
     static_assert(MTM_HIT_HEADER == 32 && sizeof(DevHit) == 32, "mirror layout");
-    finalize_small_kernel<<<1, 256, 0, ctx->stream>>>(ctx->hitsA(), ctx->hit_cap, ctx->countA(), ctx->d_meta,
-                                                       ctx->d_nontrivial, minimize, check_trivial, presorted, do_nms,
-                                                       reinterpret_cast<DevHit*>(ob + MTM_HIT_HEADER),
-                                                       reinterpret_cast<int32_t*>(ob), thr32, ascending, (long long)n_object,
-                                                       max_overlap, mirror ? ctx->d_mirror : nullptr);
+    DevHit* oh = reinterpret_cast<DevHit*>(ob + MTM_HIT_HEADER);
+    int32_t* oc = reinterpret_cast<int32_t*>(ob);
+    uint8_t* mr = mirror ? ctx->d_mirror : nullptr;
+#define MTM_FIN(P, N) finalize_small_kernel<P, N><<<1, 256, 0, ctx->stream>>>(ctx->hitsA(), ctx->hit_cap, ctx->countA(), ctx->d_meta, \
+        ctx->d_nontrivial, minimize, check_trivial, oh, oc, thr32, ascending, (long long)n_object, max_overlap, mr)
+    if (presorted) { if (do_nms) MTM_FIN(true, true); else MTM_FIN(true, false); }
+    else { if (do_nms) MTM_FIN(false, true); else MTM_FIN(false, false); }
+#undef MTM_FIN
     MTM_LAUNCH_CHECK(ctx);
     return MTM_OK;
 }

@@ -174,6 +174,22 @@ def test_baseline_configs_full_size(mtm, cfg):
     assert_hits_equal(got, want)
 
 
+def test_baseline_config_c5_one_image(mtm):
+    """C5 (one 3840x2160 image of the batch, 64 templates of 64 different sizes 32..128, N_object=50): the
+    mixed-size tensor-core groups and the 12-warp epilogue variant against the CPU port; a second image of the
+    batch through the pipelined entry point must equal its own synchronous call."""
+    from oracle import mtm_port, synth
+    image, temps, params = synth.config("C5")
+    got = mtm.matchTemplates(temps, image, **params)
+    want = mtm_port.match_templates(temps, image, **params)
+    assert len(want) == 50
+    assert_hits_equal(got, want)
+    image1, _, _ = synth.config("C5", image_index=1)
+    batch = mtm.matchTemplatesBatch(temps, [image, image1], **params)
+    assert_hits_equal(batch[0], got, tol=0.0)
+    assert_hits_equal(batch[1], mtm.matchTemplates(temps, image1, **params), tol=0.0)
+
+
 def test_c3_large_template_properties(mtm):
     """C3 (4096^2, 256^2 template): too large for the direct oracle -> FFT-exact oracle on the map."""
     from oracle import ncc_exact, synth
