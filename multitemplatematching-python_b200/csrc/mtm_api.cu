@@ -497,7 +497,7 @@ static int compute_maps(mtm_ctx* ctx, int method, int tmpl)
     const bool tensor = use_tensor_path(ctx, method);
     if (!tensor && ctx->path == MTM_PATH_TENSOR)
         return mtm_fail(ctx, MTM_ERR_UNSUPPORTED, "tensor-core path requested but not available for these inputs/method");
-    if (tensor) MTM_TRY(ensure_moments(ctx));
+    if (tensor && method == MTM_TM_CCOEFF_NORMED) MTM_TRY(ensure_moments(ctx));   // the other methods read the summed-area tables directly
     const int64_t launches_before = ctx->ctr.kernel_launches;
     if (ctx->time_ncc) {
         MTM_TRY(harvest_ncc_time(ctx, false));
@@ -513,7 +513,7 @@ static int compute_maps(mtm_ctx* ctx, int method, int tmpl)
                 for (int k = 0; k < g.count; ++k) has = has || ctx->h_order[g.first + k] == tmpl;
                 if (!has) continue;
             }
-            MTM_TRY(launch_ncc_tc(ctx, g));
+            MTM_TRY(launch_ncc_tc(ctx, g, method));
         }
         i = n;
         ctx->cand_valid = ctx->cand_on;

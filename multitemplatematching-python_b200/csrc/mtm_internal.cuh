@@ -199,7 +199,7 @@ bool tc_path_supported(const mtm_ctx* ctx, int method, int h, int w);
 bool tc_plan_group(int mode, int h, int w, int C, TcGroup& g);
 int launch_toeplitz_prep(mtm_ctx* ctx, const TcGroup& g);
 int launch_window_moments(mtm_ctx* ctx);
-int launch_ncc_tc(mtm_ctx* ctx, const TcGroup& g);
+int launch_ncc_tc(mtm_ctx* ctx, const TcGroup& g, int method);
 // raw (unsorted) peaks of every template -> block A
 int launch_peaks(mtm_ctx* ctx, int method, int64_t n_object, float thr32, double thr64, bool allow_candidates = true);
 // in-place sort of block A (mode 0: findMatches order, mode 1: NMSBoxes order)

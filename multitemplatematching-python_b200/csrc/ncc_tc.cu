@@ -202,6 +202,25 @@ __device__ __forceinline__ void epilogue16_fast(const uint32_t (&v)[16], int y_f
     }
 }
 
+// Any method (cv2.TM_* 0..5): OpenCV's float64 epilogue (ncc_epilogue.cuh) on the exact tensor-core numerator and
+// the exact window sums from the summed-area tables; four pixels' table loads are in flight at a time.
+template <int C>
+__device__ __forceinline__ void epilogue16_generic(const uint32_t (&v)[16], int y_first, int mh, int mw, int x, int method,
+                                                   const TmplMeta& tm, const SatView& sat, float* __restrict__ out)
+{
+#pragma unroll 4
+    for (int k = 0; k < 16; ++k) {
+        const int y = y_first + k;
+        if (y < mh) {
+            uint32_t S[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) S[c] = sat_window_s(sat.s + c * sat.plane, sat.pitch, y, x, tm.h, tm.w);
+            const unsigned long long Q = sat_window_q(sat.q, sat.pitch, y, x, tm.h, tm.w);
+            out[(int64_t)y * mw + x] = ncc_epilogue<C>(method, (double)v[k], S, Q, tm);
+        }
+    }
+}
+
 // Multi-channel (interleaved RGB / RGBA) form: per-channel window sums, the squared sums share one table.
 //   N1 = A*CC - sum_c S_c*sumT_c ;  rsD already holds rsqrt(A*Q - sum_c S_c^2).
 template <int C>
@@ -292,9 +311,12 @@ struct TcParams {
     int C; int64_t mom_plane;         // channels (1, 3, 4) and the element stride between the per-channel S planes
     int stages, tiles_x, tiles_total; // persistent kernel: slab ring depth, tile grid width, number of tiles
     long long* prof; int dbg;         // debug only (MTM_B200_PROF / MTM_B200_PDBG): per-CTA role clocks, phase knock-outs
+    int method;                       // cv2 method id; != TM_CCOEFF_NORMED takes the float64 epilogue on the summed-area tables
+    SatView sat;
 };
 
 // Epilogue of one tile for one of 8 epilogue warps: warp%4 selects the TMEM lane quarter, warp/4 the column half.
+template <bool GEN>
 __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_d, int x0, int y0, int warp, int lane, int parts = 2)
 {
     const int m = 32 * (warp & 3) + lane;
@@ -325,6 +347,12 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_d
         uint32_t v[16];
         tmem_ld16(tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c0, v);
         if (!live || y0 + c0 >= t_mh) continue;
+        if (GEN) {                                             // compile-time: the default kernel carries none of the float64 code
+            if (p.C == 1) epilogue16_generic<1>(v, y0 + c0, t_mh, t_mw, x, p.method, *tm, p.sat, out);
+            else if (p.C == 3) epilogue16_generic<3>(v, y0 + c0, t_mh, t_mw, x, p.method, *tm, p.sat, out);
+            else epilogue16_generic<4>(v, y0 + c0, t_mh, t_mw, x, p.method, *tm, p.sat, out);
+            continue;
+        }
         if (p.C == 1) {
             // the prefetched rows of the next batch must exist: +32
             if (!is_const && y0 + c0 + 32 <= t_mh) epilogue16_fast(v, y0 + c0, t_mw, x, (uint32_t)area, (uint32_t)sumT, ct, SRm, out, sink, thr_eff, c0 + 16 < c_end);
@@ -338,7 +366,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_d
 // Pulls the window moments of a warp's first batch of the tile into L1 while the accumulator is still being computed.
 __device__ __forceinline__ void epilogue_prefetch_first(const TcParams& p, int x0, int y0, int warp, int lane, int parts)
 {
-    if (p.C != 1) return;
+    if (p.C != 1 || p.method != MTM_TM_CCOEFF_NORMED) return;
     const int m = 32 * (warp & 3) + lane;
     int x, tsel;
     if (p.mode == 0) { tsel = m >> 4; x = x0 + (m & 15); }
@@ -353,6 +381,7 @@ __device__ __forceinline__ void epilogue_prefetch_first(const TcParams& p, int x
 }
 
 // One CTA = one output tile.  Warp 0: slab producer, warp 1: MMA issuer, then all 8 warps: epilogue.
+template <bool GEN>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 ncc_tc_kernel(const TcParams p)
 {
@@ -435,7 +464,7 @@ ncc_tc_kernel(const TcParams p)
     if (warp == 1) { if (lane == 0) mbar_wait(accum, 0); __syncwarp(); }
     __syncthreads();
     tc_fence_after();
-    epilogue_tile(p, tmem_d, x0, y0, warp, lane);
+    epilogue_tile<GEN>(p, tmem_d, x0, y0, warp, lane);
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc(tmem_d, tmem_cols);
@@ -499,7 +528,7 @@ __device__ __forceinline__ void issue_rows_any(int nk, uint32_t tmem_d, uint32_t
     }
 }
 
-template <bool PROF, int EW>
+template <bool PROF, int EW, bool GEN>
 __global__ void __launch_bounds__(512, 1)   // 128 registers; with EW = 8 (384 threads) a quarter of the register file stays free for other streams' small kernels
 ncc_tc_persist_kernel(const TcParams p)
 {
@@ -648,7 +677,7 @@ ncc_tc_persist_kernel(const TcParams p)
             mbar_wait(&acc_full[b], u & 1);
             const long long c1 = PROF ? clock64() : 0;
             tc_fence_after();
-            if (!PROF || !(p.dbg & 1)) epilogue_tile(p, tmem_base + (uint32_t)b * acc_stride, x0, y0, warp, lane, EW / 4);
+            if (!PROF || !(p.dbg & 1)) epilogue_tile<GEN>(p, tmem_base + (uint32_t)b * acc_stride, x0, y0, warp, lane, EW / 4);
             tc_fence_before();
             mbar_arrive(&acc_empty[b]);
             if (PROF) { w_af += c1 - c0; w_epi += clock64() - c1; }
@@ -945,7 +974,8 @@ __global__ void window_moments_kernel(SatView sat, const uint32_t* __restrict__ 
 bool tc_path_supported(const mtm_ctx* ctx, int method, int h, int w)
 {
     const int C = ctx->img.C;
-    if ((C != 1 && C != 3 && C != 4) || method != MTM_TM_CCOEFF_NORMED) return false;
+    if ((C != 1 && C != 3 && C != 4) || method < 0 || method > 5) return false;
+    if (method != MTM_TM_CCOEFF_NORMED && getenv("MTM_B200_TS")) return false;    // the experimental TS kernel only has the default epilogue
     if ((long long)h * w < 16 || (double)h * w * C * 65025.0 >= 4294967296.0) return false;   // 32-bit exact range; tiny windows -> fp64 path
     return true;
 }
@@ -1050,11 +1080,13 @@ static int launch_ncc_tc_ts(mtm_ctx* ctx, const TcGroup& g)
     return MTM_OK;
 }
 
-int launch_ncc_tc(mtm_ctx* ctx, const TcGroup& g)
+int launch_ncc_tc(mtm_ctx* ctx, const TcGroup& g, int method)
 {
     if (g.variant == 1) return launch_ncc_tc_ts(ctx, g);
     const ImageDev& im = ctx->img;
     TcParams p{};
+    p.method = method;
+    p.sat = SatView{im.sat_s, im.sat_q, im.sat_pitch, (int64_t)(im.H + 1) * im.sat_pitch};
     p.img = im.pix; p.pitch = im.pitch; p.H = im.H; p.W = im.W;
     p.slabs = ctx->d_slabs + g.arena_off; p.slab_bytes = g.slab_bytes; p.a_kblk = g.a_kblk; p.nk = g.nk; p.ds = g.ds;
     p.mode = g.mode; p.h = g.h; p.w = g.w;
@@ -1107,10 +1139,13 @@ int launch_ncc_tc(mtm_ctx* ctx, const TcGroup& g)
             p.tiles_x = gx_p; p.tiles_total = gx_p * ((p.mh + bestN - 1) / bestN);
             const size_t smem_bytes = 256 + 2 * tile_b + (size_t)best_stages * stage_b;
             if (!ctx->tcp_attr_set) {
-                MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-                MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-                MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_kernel<false, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-                MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_kernel<true, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                const int big = 227 * 1024;
+                MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_kernel<false, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+                MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_kernel<true, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+                MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_kernel<false, 12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+                MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_kernel<true, 12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+                MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_kernel<false, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+                MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_kernel<false, 12, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
                 ctx->tcp_attr_set = true;
             }
             const int grid_p = std::min(p.tiles_total, ctx->sm_count);
@@ -1124,12 +1159,16 @@ int launch_ncc_tc(mtm_ctx* ctx, const TcGroup& g)
             }
             p.dbg = pdbg;
             const int ew = best_ew;
-            if (ew == 12) {
-                if (prof) ncc_tc_persist_kernel<true, 12><<<grid_p, 32 * 16, smem_bytes, ctx->stream>>>(p);
-                else ncc_tc_persist_kernel<false, 12><<<grid_p, 32 * 16, smem_bytes, ctx->stream>>>(p);
+            const bool gen = method != MTM_TM_CCOEFF_NORMED;
+            if (gen) {
+                if (ew == 12) ncc_tc_persist_kernel<false, 12, true><<<grid_p, 32 * 16, smem_bytes, ctx->stream>>>(p);
+                else ncc_tc_persist_kernel<false, 8, true><<<grid_p, 32 * 12, smem_bytes, ctx->stream>>>(p);
+            } else if (ew == 12) {
+                if (prof) ncc_tc_persist_kernel<true, 12, false><<<grid_p, 32 * 16, smem_bytes, ctx->stream>>>(p);
+                else ncc_tc_persist_kernel<false, 12, false><<<grid_p, 32 * 16, smem_bytes, ctx->stream>>>(p);
             } else {
-                if (prof) ncc_tc_persist_kernel<true, 8><<<grid_p, 32 * 12, smem_bytes, ctx->stream>>>(p);
-                else ncc_tc_persist_kernel<false, 8><<<grid_p, 32 * 12, smem_bytes, ctx->stream>>>(p);
+                if (prof) ncc_tc_persist_kernel<true, 8, false><<<grid_p, 32 * 12, smem_bytes, ctx->stream>>>(p);
+                else ncc_tc_persist_kernel<false, 8, false><<<grid_p, 32 * 12, smem_bytes, ctx->stream>>>(p);
             }
             MTM_LAUNCH_CHECK(ctx);
             if (prof) {
@@ -1168,12 +1207,14 @@ int launch_ncc_tc(mtm_ctx* ctx, const TcGroup& g)
     p.N = bestN; p.R = bestN + g.h - 1;
     const size_t smem_bytes = smem_for(bestN);
     if (!ctx->tc_attr_set) {
-        MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         ctx->tc_attr_set = true;
     }
     const int xw = g.mode == 0 ? 16 : 128;
     dim3 grid((p.mw + xw - 1) / xw, (p.mh + p.N - 1) / p.N);
-    ncc_tc_kernel<<<grid, TC_THREADS, smem_bytes, ctx->stream>>>(p);
+    if (method != MTM_TM_CCOEFF_NORMED) ncc_tc_kernel<true><<<grid, TC_THREADS, smem_bytes, ctx->stream>>>(p);
+    else ncc_tc_kernel<false><<<grid, TC_THREADS, smem_bytes, ctx->stream>>>(p);
     MTM_LAUNCH_CHECK(ctx);
     return MTM_OK;
 }

@@ -107,6 +107,34 @@ def test_tensor_path_rgb(mtm, ctxs, C, n_t, tshape, seed):
                       mtm.matchTemplates(labelled, img, score_threshold=0.5, context=cd), tol=2e-6)
 
 
+@pytest.mark.parametrize("C", [1, 3])
+@pytest.mark.parametrize("method", [0, 1, 2, 3, 4])
+def test_tensor_path_other_methods(mtm, ctxs, method, C):
+    """cv2 methods 0..4 on the tcgen05 numerator (float64 OpenCV epilogue on the summed-area tables) against
+    the exact oracle and the dp4a kernel, which shares the epilogue: identical numerators -> identical maps."""
+    from oracle import ncc_exact
+    ct, cd = ctxs                                           # ct is forced onto the tensor path: unsupported -> error
+    rng = np.random.default_rng(40 + method)
+    shape = (120, 170) if C == 1 else (120, 170, C)
+    img = rng.integers(0, 256, shape, dtype=np.uint8)
+    temps = []
+    for k in range(3):
+        y, x = int(rng.integers(0, 90)), int(rng.integers(0, 130))
+        t = img[y:y + 24, x:x + 31].astype(np.int32) + rng.integers(-30, 30, (24, 31) + shape[2:])
+        temps.append(np.clip(t, 0, 255).astype(np.uint8))
+    for t in temps:
+        got_t = mtm.computeScoreMap(t, img, method=method, context=ct)
+        got_d = mtm.computeScoreMap(t, img, method=method, context=cd)
+        exact = ncc_exact.match_template_exact(img, t, method=method, use_fft=False)
+        assert_map_close(got_t, exact)
+        assert np.array_equal(got_t, got_d)
+    if method != 0:                                         # matchTemplates rejects TM_SQDIFF like the reference
+        labelled = [("t%d" % i, t) for i, t in enumerate(temps)]
+        thr = {1: 0.3, 2: 0.0, 3: 0.9, 4: 0.0}[method]
+        kw = dict(method=method, score_threshold=thr, N_object=5)
+        assert_hits_equal(mtm.matchTemplates(labelled, img, context=ct, **kw), mtm.matchTemplates(labelled, img, context=cd, **kw), tol=0.0)
+
+
 def test_tensor_path_uniform_noise_and_bright(mtm, ctxs):
     """Saturated inputs: 255*255*h*w up to 4.26e9 needs the full unsigned 32-bit accumulator range."""
     from oracle import ncc_exact
