@@ -30,7 +30,11 @@ typedef enum mtm_status {
     MTM_ERR_UNSUPPORTED = -4   /* valid for the reference, not implemented on the GPU yet   */
 } mtm_status;
 
-typedef enum mtm_dtype { MTM_U8 = 0, MTM_F32 = 1 } mtm_dtype;
+/* MTM_U16: 16-bit unsigned pixels (image AND templates).  The reference casts them to float32 before
+ * cv2.matchTemplate (MTM/__init__.py:71-74); here the same float32 semantics are kept for the window statistics and the
+ * OpenCV epilogue, while the numerator is computed EXACTLY on the tensor cores from the high/low byte planes
+ * (single-channel images; other shapes take the float32 kernels). */
+typedef enum mtm_dtype { MTM_U8 = 0, MTM_F32 = 1, MTM_U16 = 2 } mtm_dtype;
 
 /* cv2.TM_* codes, MTM/__init__.py:56 `method` */
 typedef enum mtm_method {

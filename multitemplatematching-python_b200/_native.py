@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmtm_b200.so")
 
 MTM_OK, MTM_ERR_INVALID, MTM_ERR_CUDA, MTM_ERR_CAPACITY, MTM_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
-MTM_U8, MTM_F32 = 0, 1
+MTM_U8, MTM_F32, MTM_U16 = 0, 1, 2
 PATH_AUTO, PATH_DIRECT, PATH_TENSOR = 0, 1, 2
 OPT_PATH, OPT_TIME_NCC = 0, 1
 
@@ -96,6 +96,8 @@ def _dtype_code(arr):
         return MTM_U8
     if arr.dtype == np.float32:
         return MTM_F32
+    if arr.dtype == np.uint16:
+        return MTM_U16
     raise TypeError("unsupported dtype %s" % arr.dtype)
 
 

@@ -61,12 +61,15 @@ def computeScoreMap(template, image, method=TM_CCOEFF_NORMED, mask=None, *, cont
     Note the argument order (template, image), the reverse of ``cv2.matchTemplate``.
     Returns a float32 array of shape (H-h+1, W-w+1).
     """
+    template16, image16 = template, image
     template, image, mask = _dtype_policy(template, image, mask)
     mask = _mask_policy(template, mask, method)
     if template.ndim != image.ndim or any(t > i for t, i in zip(template.shape, image.shape)) \
             or template.shape[2:] != image.shape[2:]:
         raise _cv_error("matchTemplate: template must not be larger than the image and must have the same channels")
     _require_gpu_support(image, [template], mask)
+    if mask is None and _all_uint16(image16, [template16]):
+        image, template = image16, template16              # MTM_U16: see _prepare
     ctx = context or _native.default_context()
     with ctx.lock:
         ctx.set_image(image)
@@ -135,7 +138,16 @@ def _prepare(listTemplates, image, method):
         names.append(name)
         arrays.append(template)
         masks.append(mask)
+    if _all_uint16(image, [t[1] for t in listTemplates]) and all(m is None for m in masks):
+        # 16-bit grayscale: hand the integers over as they are (MTM_U16).  The library keeps the reference's float32
+        # semantics for the statistics and computes the numerator exactly from the byte planes on the tensor cores.
+        return names, [t[1] for t in listTemplates], image, masks
     return names, arrays, img, masks
+
+
+def _all_uint16(image, templates):
+    return (isinstance(image, np.ndarray) and image.dtype == np.uint16 and image.ndim == 2 and
+            all(isinstance(t, np.ndarray) and t.dtype == np.uint16 and t.ndim == 2 for t in templates))
 
 
 def _native_n_object(N_object):

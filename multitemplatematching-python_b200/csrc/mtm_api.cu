@@ -175,6 +175,7 @@ int mtm_destroy(mtm_ctx* ctx)
     cudaFree(ctx->d_nontrivial); cudaFree(ctx->d_best); cudaFree(ctx->d_cand); cudaFree(ctx->d_cand_count);
     cudaFree(ctx->img.pixf2); cudaFree(ctx->d_raw_t); cudaFree(ctx->d_raw_m); cudaFree(ctx->d_maps2);
     cudaFree(ctx->img.pixf); cudaFree(ctx->img.satf_s); cudaFree(ctx->img.satf_q); cudaFree(ctx->d_tmpl_centred);
+    cudaFree(ctx->d_raw16); cudaFree(ctx->img.pix_lo); cudaFree(ctx->d_tmpl8); cudaFree(ctx->d_pix8); cudaFree(ctx->d_acc);
     cudaFree(ctx->d_slabs); cudaFree(ctx->d_wS); cudaFree(ctx->d_wR); cudaFree(ctx->d_sizes);
     for (int k = 0; k < MTM_MAX_INFLIGHT; ++k) { cudaFree(ctx->d_slot[k]); cudaFreeHost(ctx->h_slot[k]); if (ctx->ev_slot[k]) cudaEventDestroy(ctx->ev_slot[k]); }
     cudaFreeHost(ctx->h_tmpl_stage); cudaFreeHost(ctx->h_stage); cudaFreeHost(ctx->h_geom); cudaFreeHost(ctx->h_mirror);
@@ -253,22 +254,50 @@ static int set_image_impl(mtm_ctx* ctx, const void* pixels, int H, int W, int C,
     MTM_ENTER(ctx);
     if (!pixels || H <= 0 || W <= 0) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_image: empty image (%d x %d)", H, W);
     if (C < 1 || C > MTM_MAX_CH) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_image: %d channels (1..4 supported)", C);
-    if (dtype != MTM_U8 && dtype != MTM_F32) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_image: unknown dtype %d", dtype);
+    if (dtype != MTM_U8 && dtype != MTM_F32 && dtype != MTM_U16) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_image: unknown dtype %d", dtype);
     if ((int64_t)W * C > 66000) return mtm_fail(ctx, MTM_ERR_UNSUPPORTED, "mtm_set_image: rows wider than 66000 elements");
-    const int64_t esz = dtype == MTM_F32 ? 4 : 1;
+    if (dtype == MTM_U16 && C != 1) return mtm_fail(ctx, MTM_ERR_UNSUPPORTED, "mtm_set_image: 16-bit images must be single channel (cast to float32 otherwise)");
+    const int64_t esz = dtype == MTM_F32 ? 4 : (dtype == MTM_U16 ? 2 : 1);
     if (row_stride < (int64_t)W * C * esz) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_image: row stride %lld < %lld", (long long)row_stride, (long long)W * C * esz);
     ImageDev& im = ctx->img;
-    if (dtype == MTM_F32) {
+    if (dtype == MTM_F32 || dtype == MTM_U16) {
+        // MTM_U16 = the reference's uint16 -> float32 cast done on the device, plus the byte planes of the exact numerator
+        const bool u16 = dtype == MTM_U16;
         if (C == 2) return mtm_fail(ctx, MTM_ERR_UNSUPPORTED, "mtm_set_image: 2-channel float32 images");
         im.pitch_e = ((int64_t)W * C + 3) / 4 * 4;
         MTM_TRY(mtm_reserve(ctx, im.pixf, ctx->imgf_cap, (size_t)(H * im.pitch_e + 64)));
-        const bool same_shape_f = (im.H == H && im.W == W && im.C == C && ctx->img_dtype == dtype);
+        const bool same_shape_f = (im.H == H && im.W == W && im.C == C && ctx->img_dtype == MTM_F32 && ctx->img_u16 == u16);
         im.H = H; im.W = W; im.C = C;
         im.sat_pitch = ((int64_t)W + 1 + 3) / 4 * 4;
         g_marks.mark(ctx, "begin");
-        MTM_CUDA(ctx, cudaMemcpy2DAsync(im.pixf, (size_t)im.pitch_e * 4, pixels, (size_t)row_stride, (size_t)W * C * 4, (size_t)H,
-                                        on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
-        if (!on_device) ctx->ctr.h2d_bytes += (int64_t)H * W * C * 4;
+        if (u16) {
+            const int64_t pitch = (((int64_t)W + 64 + 64) + 127) / 128 * 128;      // u8 tile layout of the tensor-core kernel
+            const size_t plane_bytes = (size_t)(H * pitch + 256);
+            const bool fresh = ctx->img_cap < plane_bytes || ctx->pix_lo_cap < plane_bytes || im.pitch != pitch || !same_shape_f;
+            MTM_TRY(mtm_reserve(ctx, im.pix, ctx->img_cap, plane_bytes));
+            MTM_TRY(mtm_reserve(ctx, im.pix_lo, ctx->pix_lo_cap, plane_bytes));
+            if (fresh) {                                           // the padding beyond W must read as zero
+                MTM_CUDA(ctx, cudaMemsetAsync(im.pix, 0, ctx->img_cap, ctx->stream));
+                MTM_CUDA(ctx, cudaMemsetAsync(im.pix_lo, 0, ctx->pix_lo_cap, ctx->stream));
+            }
+            im.pitch = pitch;
+            const uint16_t* src16 = static_cast<const uint16_t*>(pixels);
+            int64_t src_stride = row_stride;
+            if (!on_device) {
+                MTM_TRY(mtm_reserve(ctx, ctx->d_raw16, ctx->raw16_cap, (size_t)H * W + 8));
+                MTM_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_raw16, (size_t)W * 2, pixels, (size_t)row_stride, (size_t)W * 2, (size_t)H,
+                                                cudaMemcpyHostToDevice, ctx->stream));
+                ctx->ctr.h2d_bytes += (int64_t)H * W * 2;
+                src16 = ctx->d_raw16; src_stride = (int64_t)W * 2;
+            }
+            MTM_TRY(launch_u16_split_image(ctx, src16, src_stride));
+        } else {
+            MTM_CUDA(ctx, cudaMemcpy2DAsync(im.pixf, (size_t)im.pitch_e * 4, pixels, (size_t)row_stride, (size_t)W * C * 4, (size_t)H,
+                                            on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+            if (!on_device) ctx->ctr.h2d_bytes += (int64_t)H * W * C * 4;
+        }
+        ctx->img_u16 = u16;
+        dtype = MTM_F32;
         MTM_TRY(mtm_reserve(ctx, im.satf_s, ctx->satf_s_cap, (size_t)C * (H + 1) * im.sat_pitch));
         MTM_TRY(mtm_reserve(ctx, im.satf_q, ctx->satf_q_cap, (size_t)(H + 1) * im.sat_pitch));
         MTM_TRY(mtm_reserve(ctx, ctx->scratch, ctx->scratch_cap, (size_t)2 * (C + 1) * H * W + 16));
@@ -281,9 +310,10 @@ static int set_image_impl(mtm_ctx* ctx, const void* pixels, int H, int W, int C,
     }
     const int64_t pitch = (((int64_t)W * C + 64 * C + 64) + 127) / 128 * 128;
     const bool reshape = (im.H != H || im.W != W || im.C != C);
-    const bool same_shape = !reshape && ctx->img_dtype == dtype;
+    const bool same_shape = !reshape && ctx->img_dtype == dtype && !ctx->img_u16;
+    ctx->img_u16 = false;
     MTM_TRY(mtm_reserve(ctx, im.pix, ctx->img_cap, (size_t)(H * pitch + 256)));
-    if (reshape) MTM_CUDA(ctx, cudaMemsetAsync(im.pix, 0, ctx->img_cap, ctx->stream));
+    if (reshape || !same_shape || im.pitch != pitch) MTM_CUDA(ctx, cudaMemsetAsync(im.pix, 0, ctx->img_cap, ctx->stream));
     im.pitch = pitch; im.H = H; im.W = W; im.C = C;
     im.sat_pitch = ((int64_t)W + 1 + 3) / 4 * 4;
     g_marks.mark(ctx, "begin");
@@ -358,7 +388,8 @@ static int plan_tensor_path(mtm_ctx* ctx)
     ctx->tc_groups.clear();
     ctx->tc_ready = false;
     ctx->moments_valid = false;
-    if ((ctx->tmpl_C != 1 && ctx->tmpl_C != 3 && ctx->tmpl_C != 4) || ctx->tmpl_dtype != MTM_U8) return MTM_OK;
+    const bool planes16 = ctx->tmpl_u16 && ctx->tmpl_C == 1;      // 16-bit templates: slabs of the high- and the low-byte plane
+    if ((ctx->tmpl_C != 1 && ctx->tmpl_C != 3 && ctx->tmpl_C != 4) || (ctx->tmpl_dtype != MTM_U8 && !planes16)) return MTM_OK;
     const int n = ctx->n_tmpl;
     const int TC = ctx->tmpl_C;
     // Cost model (tensor-pipe clocks per output pixel, up to a constant): a mode-A launch serves up to
@@ -414,7 +445,8 @@ static int plan_tensor_path(mtm_ctx* ctx)
         }
         i = j;
     }
-    MTM_TRY(mtm_reserve(ctx, ctx->d_slabs, ctx->slabs_cap, (size_t)arena + 128));
+    ctx->slab_plane = (arena + 127) / 128 * 128;
+    MTM_TRY(mtm_reserve(ctx, ctx->d_slabs, ctx->slabs_cap, (size_t)(planes16 ? 2 : 1) * ctx->slab_plane + 128));
     for (const TcGroup& g : ctx->tc_groups) MTM_TRY(launch_toeplitz_prep(ctx, g));
     ctx->tc_ready = true;
     return MTM_OK;
@@ -437,6 +469,7 @@ static int ensure_moments(mtm_ctx* ctx)
 static bool use_tensor_path(const mtm_ctx* ctx, int method)
 {
     if (ctx->path == MTM_PATH_DIRECT || !ctx->tc_ready) return false;
+    if (ctx->img_dtype == MTM_F32 && !(ctx->img_u16 && ctx->tmpl_u16 && ctx->img.C == 1)) return false;   // float32 data: byte planes needed
     for (const TcGroup& g : ctx->tc_groups)
         if (!tc_path_supported(ctx, method, g.h, g.w)) return false;
     return true;
@@ -497,7 +530,9 @@ static int compute_maps(mtm_ctx* ctx, int method, int tmpl)
     const bool tensor = use_tensor_path(ctx, method);
     if (!tensor && ctx->path == MTM_PATH_TENSOR)
         return mtm_fail(ctx, MTM_ERR_UNSUPPORTED, "tensor-core path requested but not available for these inputs/method");
-    if (tensor && method == MTM_TM_CCOEFF_NORMED) MTM_TRY(ensure_moments(ctx));   // the other methods read the summed-area tables directly
+    const bool tensor16 = tensor && ctx->img_dtype == MTM_F32;     // 16-bit byte-plane path
+    if (tensor && !tensor16 && method == MTM_TM_CCOEFF_NORMED) MTM_TRY(ensure_moments(ctx));   // the other methods read the summed-area tables directly
+    if (tensor16) { MTM_TRY(mtm_reserve(ctx, ctx->d_acc, ctx->acc_cap, (size_t)ctx->maps_total)); ctx->cand_on = false; }
     const int64_t launches_before = ctx->ctr.kernel_launches;
     if (ctx->time_ncc) {
         MTM_TRY(harvest_ncc_time(ctx, false));
@@ -513,8 +548,17 @@ static int compute_maps(mtm_ctx* ctx, int method, int tmpl)
                 for (int k = 0; k < g.count; ++k) has = has || ctx->h_order[g.first + k] == tmpl;
                 if (!has) continue;
             }
-            MTM_TRY(launch_ncc_tc(ctx, g, method));
+            if (tensor16) {
+                // CC = 65536 Ih*Th + 256 (Ih*Tl + Il*Th) + Il*Tl: four exact u8 x u8 correlations into the double map
+                MTM_TRY(launch_ncc_tc_accum(ctx, g, 0, 0, 65536.0, true));
+                MTM_TRY(launch_ncc_tc_accum(ctx, g, 0, 1, 256.0, false));
+                MTM_TRY(launch_ncc_tc_accum(ctx, g, 1, 0, 256.0, false));
+                MTM_TRY(launch_ncc_tc_accum(ctx, g, 1, 1, 1.0, false));
+            } else {
+                MTM_TRY(launch_ncc_tc(ctx, g, method));
+            }
         }
+        if (tensor16) MTM_TRY(launch_cc16_epilogue(ctx, method, tmpl));
         i = n;
         ctx->cand_valid = ctx->cand_on;
     }
@@ -613,8 +657,11 @@ int mtm_set_templates(mtm_ctx* ctx, int n, const void* const* pixels, const int3
     MTM_ENTER(ctx);
     if (n <= 0 || !pixels || !h || !w) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_templates: empty template list");
     if (C < 1 || C > MTM_MAX_CH) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_templates: %d channels (1..4 supported)", C);
-    if (dtype != MTM_U8 && dtype != MTM_F32) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_templates: unknown dtype %d", dtype);
-    const int esz = dtype == MTM_F32 ? 4 : 1;
+    if (dtype != MTM_U8 && dtype != MTM_F32 && dtype != MTM_U16) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_templates: unknown dtype %d", dtype);
+    if (dtype == MTM_U16 && C != 1) return mtm_fail(ctx, MTM_ERR_UNSUPPORTED, "mtm_set_templates: 16-bit templates must be single channel (cast to float32 otherwise)");
+    const bool u16 = dtype == MTM_U16;
+    const int in_esz = dtype == MTM_F32 ? 4 : (u16 ? 2 : 1);     // element size of the caller's arrays
+    const int esz = (dtype == MTM_F32 || u16) ? 4 : 1;           // element size of the device arena (16-bit -> float32)
     // Same template set as last time (content hash)?  Then everything derived from it -- packed pixels,
     // statistics, Toeplitz slabs, launch plan -- is still resident: nothing to upload or recompute.
     {
@@ -624,14 +671,16 @@ int mtm_set_templates(mtm_ctx* ctx, int n, const void* const* pixels, const int3
             if (!pixels[t] || h[t] <= 0 || w[t] <= 0)
                 return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_templates: template %d is empty", t);
             mix(((uint64_t)(uint32_t)h[t] << 32) | (uint32_t)w[t]);
-            const size_t bytes = (size_t)h[t] * w[t] * C * esz;
+            const size_t bytes = (size_t)h[t] * w[t] * C * in_esz;
             const uint8_t* b = static_cast<const uint8_t*>(pixels[t]);
             size_t k = 0;
             for (; k + 8 <= bytes; k += 8) { uint64_t v; memcpy(&v, b + k, 8); mix(v); }
             uint64_t tail = 0;
             if (k < bytes) { memcpy(&tail, b + k, bytes - k); mix(tail ^ ((uint64_t)(bytes - k) << 56)); }
         }
-        if (ctx->n_tmpl == n && ctx->tmpl_hash == hsh && ctx->tmpl_C == C && ctx->tmpl_dtype == dtype && ctx->tmpl_hash_valid) return MTM_OK;
+        const int dev_dtype = u16 ? MTM_F32 : dtype;
+        if (ctx->n_tmpl == n && ctx->tmpl_hash == hsh && ctx->tmpl_C == C && ctx->tmpl_dtype == dev_dtype && ctx->tmpl_u16 == u16 &&
+            ctx->tmpl_hash_valid) return MTM_OK;
         ctx->tmpl_hash = hsh;
         ctx->tmpl_hash_valid = false;           // set again once the upload below has been queued
     }
@@ -656,8 +705,44 @@ int mtm_set_templates(mtm_ctx* ctx, int n, const void* const* pixels, const int3
         const uint8_t* src = static_cast<const uint8_t*>(pixels[t]);
         uint8_t* dst = ctx->h_tmpl_stage + m.pix_off;
         const size_t row = (size_t)m.w * C * esz;
-        for (int y = 0; y < m.h; ++y) memcpy(dst + (size_t)y * m.wp, src + (size_t)y * row, row);
+        if (u16) {                                                 // the reference's uint16 -> float32 cast
+            for (int y = 0; y < m.h; ++y) {
+                const uint16_t* s16 = reinterpret_cast<const uint16_t*>(src) + (size_t)y * m.w;
+                float* d32 = reinterpret_cast<float*>(dst + (size_t)y * m.wp);
+                for (int x = 0; x < m.w; ++x) d32[x] = (float)s16[x];
+            }
+        } else {
+            for (int y = 0; y < m.h; ++y) memcpy(dst + (size_t)y * m.wp, src + (size_t)y * row, row);
+        }
     }
+    if (u16) {
+        // byte planes for the exact tensor-core numerator: [high-byte arena][low-byte arena], u8 packing (pitch w rounded up to 4)
+        std::vector<TmplPix8> pix8((size_t)n);
+        size_t total8 = 0;
+        for (int t = 0; t < n; ++t) {
+            pix8[t].off = (int64_t)total8; pix8[t].wp = (w[t] + 3) / 4 * 4; pix8[t].pad = 0;
+            total8 += ((size_t)pix8[t].wp * h[t] + 15) / 16 * 16;
+        }
+        std::vector<uint8_t> planes(2 * total8, 0);
+        for (int t = 0; t < n; ++t) {
+            const uint16_t* s16 = static_cast<const uint16_t*>(pixels[t]);
+            for (int y = 0; y < h[t]; ++y)
+                for (int x = 0; x < w[t]; ++x) {
+                    const uint16_t v = s16[(size_t)y * w[t] + x];
+                    planes[(size_t)pix8[t].off + (size_t)y * pix8[t].wp + x] = (uint8_t)(v >> 8);
+                    planes[total8 + (size_t)pix8[t].off + (size_t)y * pix8[t].wp + x] = (uint8_t)(v & 255u);
+                }
+        }
+        MTM_TRY(mtm_reserve(ctx, ctx->d_tmpl8, ctx->tmpl8_cap, 2 * total8 + 64));
+        MTM_TRY(mtm_reserve(ctx, ctx->d_pix8, ctx->pix8_cap, (size_t)n));
+        ctx->tmpl8_plane = (int64_t)total8;
+        // pageable sources: the runtime stages these copies before returning
+        MTM_CUDA(ctx, cudaMemcpyAsync(ctx->d_tmpl8, planes.data(), 2 * total8, cudaMemcpyHostToDevice, ctx->stream));
+        MTM_CUDA(ctx, cudaMemcpyAsync(ctx->d_pix8, pix8.data(), (size_t)n * sizeof(TmplPix8), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->ctr.h2d_bytes += (int64_t)(2 * total8);
+    }
+    ctx->tmpl_u16 = u16;
+    if (u16) dtype = MTM_F32;
     MTM_TRY(mtm_reserve(ctx, ctx->d_tmpl, ctx->tmpl_cap, total + 64));
     MTM_TRY(mtm_reserve(ctx, ctx->d_meta, ctx->meta_cap, (size_t)n));
     MTM_TRY(mtm_reserve(ctx, ctx->d_order, ctx->order_cap, (size_t)n));
@@ -738,7 +823,7 @@ int mtm_set_templates_masked(mtm_ctx* ctx, int n, const void* const* pixels, con
     });
     MTM_CUDA(ctx, cudaMemcpyAsync(ctx->d_order, ctx->h_order.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     ctx->ctr.h2d_bytes += (int64_t)2 * raw_total + (int64_t)n * (sizeof(TmplMeta) + sizeof(int32_t));
-    ctx->n_tmpl = n; ctx->tmpl_C = C; ctx->tmpl_dtype = MTM_F32;
+    ctx->n_tmpl = n; ctx->tmpl_C = C; ctx->tmpl_dtype = MTM_F32; ctx->tmpl_u16 = false;
     ctx->geometry_valid = false;
     ctx->masked = true;
     ctx->tc_groups.clear(); ctx->tc_ready = false;

@@ -45,6 +45,12 @@ struct TmplMeta {
     float pad_f;
 };
 
+// Where a template's packed u8 pixels live inside a byte-plane arena (MTM_U16 templates).
+struct TmplPix8 {
+    int64_t off;
+    int32_t wp, pad;
+};
+
 // One distinct template size: where its window-moment maps live (window_moments_kernel, batched).
 struct SizeDesc {
     int32_t h, w, mh, mw;
@@ -75,6 +81,7 @@ struct ImageDev {
     int64_t sat_pitch = 0;       // elements
     // float32 images (MTM/__init__.py:71-74): pixels + float64 summed-area tables
     float* pixf = nullptr; int64_t pitch_e = 0;
+    uint8_t* pix_lo = nullptr;           // MTM_U16 images: `pix` holds the high bytes, `pix_lo` the low bytes (same pitch)
     float* pixf2 = nullptr;              // image squared (masked matching)
     double* satf_s = nullptr; double* satf_q = nullptr;
 };
@@ -107,6 +114,15 @@ struct mtm_ctx {
     uint8_t* d_tmpl_centred = nullptr; size_t tmplc_cap = 0;   // float32 templates minus their mean
     uint8_t* h_tmpl_stage = nullptr; size_t tmpl_stage_cap = 0;   // pinned
     int tmpl_C = 0, tmpl_dtype = -1;
+    // MTM_U16 uploads: float32 everywhere (img_dtype / tmpl_dtype == MTM_F32) plus the byte planes for the exact tensor-core numerator
+    bool img_u16 = false, tmpl_u16 = false;
+    uint16_t* d_raw16 = nullptr; size_t raw16_cap = 0;         // staging of the raw 16-bit image
+    size_t pix_lo_cap = 0;
+    uint8_t* d_tmpl8 = nullptr; size_t tmpl8_cap = 0;          // packed u8 templates: high-byte arena, then low-byte arena
+    int64_t tmpl8_plane = 0;                                   // bytes between the two arenas
+    TmplPix8* d_pix8 = nullptr; size_t pix8_cap = 0;           // per-template offset / pitch inside an arena
+    int64_t slab_plane = 0;                                    // bytes between the high- and low-byte Toeplitz slabs in d_slabs
+    double* d_acc = nullptr; size_t acc_cap = 0;               // exact numerator maps (double) of the 16-bit path
     uint64_t tmpl_hash = 0; bool tmpl_hash_valid = false;   // content hash of the resident template set
     bool geometry_valid = false;         // map offsets computed for (image, templates)
     bool masked = false;                 // templates carry masks (methods 0 / 3): d_tmpl = T*M^2, d_tmpl_centred = M^2
@@ -200,6 +216,10 @@ bool tc_plan_group(int mode, int h, int w, int C, TcGroup& g);
 int launch_toeplitz_prep(mtm_ctx* ctx, const TcGroup& g);
 int launch_window_moments(mtm_ctx* ctx);
 int launch_ncc_tc(mtm_ctx* ctx, const TcGroup& g, int method);
+// 16-bit path: one byte-plane product of the group accumulated into ctx->d_acc (img_plane / tmpl_plane: 0 = high, 1 = low bytes)
+int launch_ncc_tc_accum(mtm_ctx* ctx, const TcGroup& g, int img_plane, int tmpl_plane, double weight, bool first);
+int launch_u16_split_image(mtm_ctx* ctx, const uint16_t* src, int64_t src_stride_bytes);
+int launch_cc16_epilogue(mtm_ctx* ctx, int method, int tmpl);
 // raw (unsorted) peaks of every template -> block A
 int launch_peaks(mtm_ctx* ctx, int method, int64_t n_object, float thr32, double thr64, bool allow_candidates = true);
 // in-place sort of block A (mode 0: findMatches order, mode 1: NMSBoxes order)

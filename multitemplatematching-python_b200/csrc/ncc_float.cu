@@ -424,6 +424,66 @@ int launch_masked_combine(mtm_ctx* ctx, int method, const float* mapsB)
     return MTM_OK;
 }
 
+// ------------------------------------------------------------------ 16-bit images (MTM_U16)
+namespace {
+
+// raw u16 rows -> float32 image (statistics, fallback kernels) + high / low byte planes in the u8 tile layout of the
+// tensor-core kernel (zero padded pitch).
+__global__ void u16_split_image_kernel(const uint16_t* __restrict__ src, int64_t src_stride_e, int H, int W,
+                                       float* __restrict__ pixf, int64_t pitch_e, uint8_t* __restrict__ hi,
+                                       uint8_t* __restrict__ lo, int64_t pitch)
+{
+    const int y = blockIdx.y;
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < W; x += gridDim.x * blockDim.x) {
+        const uint32_t v = src[(int64_t)y * src_stride_e + x];
+        pixf[(int64_t)y * pitch_e + x] = (float)v;
+        hi[(int64_t)y * pitch + x] = (uint8_t)(v >> 8);
+        lo[(int64_t)y * pitch + x] = (uint8_t)(v & 255u);
+    }
+}
+
+// exact numerator (double) + float64 window statistics -> OpenCV's epilogue, any method.  blockIdx.y = template.
+__global__ void cc16_epilogue_kernel(const double* __restrict__ acc, float* __restrict__ maps, const TmplMeta* __restrict__ meta,
+                                     int tmpl_first, int method, const double* __restrict__ sat_s, const double* __restrict__ sat_q,
+                                     int64_t sat_pitch)
+{
+    const TmplMeta& tm = meta[tmpl_first + blockIdx.y];
+    const int64_t n = (int64_t)tm.mh * tm.mw;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int y = (int)(idx / tm.mw), x = (int)(idx - (int64_t)y * tm.mw);
+        double S[1] = {0.0}, Q = 0.0;
+        if (method != MTM_TM_CCORR) {
+            S[0] = satf_window(sat_s, sat_pitch, y, x, tm.h, tm.w);
+            Q = satf_window(sat_q, sat_pitch, y, x, tm.h, tm.w);
+        }
+        maps[tm.map_off + idx] = ncc_epilogue_f64<1>(method, acc[tm.map_off + idx], S, Q, tm);
+    }
+}
+
+}  // namespace
+
+int launch_u16_split_image(mtm_ctx* ctx, const uint16_t* src, int64_t src_stride_bytes)
+{
+    ImageDev& im = ctx->img;
+    dim3 grid((unsigned)std::min(8, (im.W + 255) / 256), (unsigned)im.H);
+    u16_split_image_kernel<<<grid, 256, 0, ctx->stream>>>(src, src_stride_bytes / 2, im.H, im.W, im.pixf, im.pitch_e, im.pix, im.pix_lo, im.pitch);
+    MTM_LAUNCH_CHECK(ctx);
+    return MTM_OK;
+}
+
+int launch_cc16_epilogue(mtm_ctx* ctx, int method, int tmpl)
+{
+    const ImageDev& im = ctx->img;
+    int64_t n = 0;
+    const int first = tmpl < 0 ? 0 : tmpl, count = tmpl < 0 ? ctx->n_tmpl : 1;
+    for (int t = first; t < first + count; ++t) n = std::max<int64_t>(n, (int64_t)ctx->h_meta[t].mh * ctx->h_meta[t].mw);
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 8));
+    cc16_epilogue_kernel<<<dim3(blocks, count), 256, 0, ctx->stream>>>(ctx->d_acc, ctx->d_maps, ctx->d_meta, first, method, im.satf_s,
+                                                                       im.satf_q, im.sat_pitch);
+    MTM_LAUNCH_CHECK(ctx);
+    return MTM_OK;
+}
+
 int launch_build_sat_f32(mtm_ctx* ctx)
 {
     ImageDev& im = ctx->img;

@@ -221,6 +221,23 @@ __device__ __forceinline__ void epilogue16_generic(const uint32_t (&v)[16], int 
     }
 }
 
+// 16-bit path: one byte-plane product (exact u32) joins the exact numerator map, CC = 65536 hh + 256 (hl + lh) + ll.
+__device__ __forceinline__ void epilogue16_accum(const uint32_t (&v)[16], int y_first, int mh, int mw, int x, double weight,
+                                                 bool first, double* __restrict__ acc)
+{
+    double old[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int y = min(y_first + k, mh - 1);
+        old[k] = first ? 0.0 : acc[(int64_t)y * mw + x];
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int y = y_first + k;
+        if (y < mh) acc[(int64_t)y * mw + x] = fma(weight, (double)v[k], old[k]);
+    }
+}
+
 // Multi-channel (interleaved RGB / RGBA) form: per-channel window sums, the squared sums share one table.
 //   N1 = A*CC - sum_c S_c*sumT_c ;  rsD already holds rsqrt(A*Q - sum_c S_c^2).
 template <int C>
@@ -313,10 +330,11 @@ struct TcParams {
     long long* prof; int dbg;         // debug only (MTM_B200_PROF / MTM_B200_PDBG): per-CTA role clocks, phase knock-outs
     int method;                       // cv2 method id; != TM_CCOEFF_NORMED takes the float64 epilogue on the summed-area tables
     SatView sat;
+    double* acc; double acc_weight; int acc_first;   // MODE 2 (16-bit byte planes): acc = (first ? 0 : acc) + weight * CC
 };
 
 // Epilogue of one tile for one of 8 epilogue warps: warp%4 selects the TMEM lane quarter, warp/4 the column half.
-template <bool GEN>
+template <int MODE>
 __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_d, int x0, int y0, int warp, int lane, int parts = 2)
 {
     const int m = 32 * (warp & 3) + lane;
@@ -347,7 +365,11 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_d
         uint32_t v[16];
         tmem_ld16(tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c0, v);
         if (!live || y0 + c0 >= t_mh) continue;
-        if (GEN) {                                             // compile-time: the default kernel carries none of the float64 code
+        if (MODE == 2) {                                       // 16-bit path: weighted byte-plane product into the exact map
+            epilogue16_accum(v, y0 + c0, t_mh, t_mw, x, p.acc_weight, p.acc_first != 0, p.acc + tm->map_off);
+            continue;
+        }
+        if (MODE == 1) {                                       // compile-time: the default kernel carries none of the float64 code
             if (p.C == 1) epilogue16_generic<1>(v, y0 + c0, t_mh, t_mw, x, p.method, *tm, p.sat, out);
             else if (p.C == 3) epilogue16_generic<3>(v, y0 + c0, t_mh, t_mw, x, p.method, *tm, p.sat, out);
             else epilogue16_generic<4>(v, y0 + c0, t_mh, t_mw, x, p.method, *tm, p.sat, out);
@@ -381,7 +403,7 @@ __device__ __forceinline__ void epilogue_prefetch_first(const TcParams& p, int x
 }
 
 // One CTA = one output tile.  Warp 0: slab producer, warp 1: MMA issuer, then all 8 warps: epilogue.
-template <bool GEN>
+template <int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 ncc_tc_kernel(const TcParams p)
 {
@@ -464,7 +486,7 @@ ncc_tc_kernel(const TcParams p)
     if (warp == 1) { if (lane == 0) mbar_wait(accum, 0); __syncwarp(); }
     __syncthreads();
     tc_fence_after();
-    epilogue_tile<GEN>(p, tmem_d, x0, y0, warp, lane);
+    epilogue_tile<MODE>(p, tmem_d, x0, y0, warp, lane);
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc(tmem_d, tmem_cols);
@@ -528,7 +550,7 @@ __device__ __forceinline__ void issue_rows_any(int nk, uint32_t tmem_d, uint32_t
     }
 }
 
-template <bool PROF, int EW, bool GEN>
+template <bool PROF, int EW, int MODE>
 __global__ void __launch_bounds__(512, 1)   // 128 registers; with EW = 8 (384 threads) a quarter of the register file stays free for other streams' small kernels
 ncc_tc_persist_kernel(const TcParams p)
 {
@@ -672,12 +694,12 @@ ncc_tc_persist_kernel(const TcParams p)
             const int b = i & 1, u = i >> 1;
             const int ti = (int)blockIdx.x + i * (int)gridDim.x;
             const int x0 = (ti % p.tiles_x) * xw, y0 = (ti / p.tiles_x) * p.N;
-            epilogue_prefetch_first(p, x0, y0, warp, lane, EW / 4);
+            if (MODE == 0) epilogue_prefetch_first(p, x0, y0, warp, lane, EW / 4);
             const long long c0 = PROF ? clock64() : 0;
             mbar_wait(&acc_full[b], u & 1);
             const long long c1 = PROF ? clock64() : 0;
             tc_fence_after();
-            if (!PROF || !(p.dbg & 1)) epilogue_tile<GEN>(p, tmem_base + (uint32_t)b * acc_stride, x0, y0, warp, lane, EW / 4);
+            if (!PROF || !(p.dbg & 1)) epilogue_tile<MODE>(p, tmem_base + (uint32_t)b * acc_stride, x0, y0, warp, lane, EW / 4);
             tc_fence_before();
             mbar_arrive(&acc_empty[b]);
             if (PROF) { w_af += c1 - c0; w_epi += clock64() - c1; }
@@ -914,7 +936,8 @@ ncc_tc_ts_kernel(const TsParams p)
 // Expands the templates of one group into Toeplitz slabs (see the header comment).
 __global__ void toeplitz_prep_kernel(const uint8_t* __restrict__ tmpl, const TmplMeta* __restrict__ meta,
                                      const int32_t* __restrict__ order, int count, int mode, int h, int w,
-                                     int nk, int slab_bytes, int C, uint8_t* __restrict__ slabs)
+                                     int nk, int slab_bytes, int C, uint8_t* __restrict__ slabs,
+                                     const TmplPix8* __restrict__ pix8)      // optional: byte-plane arena geometry (16-bit templates)
 {
     const int pieces_per_slab = slab_bytes / 16;
     const int64_t total = (int64_t)h * pieces_per_slab;
@@ -929,7 +952,9 @@ __global__ void toeplitz_prep_kernel(const uint8_t* __restrict__ tmpl, const Tmp
         for (int k = 0; k < 16; ++k) bytes[k] = 0;
         if (t < count) {
             const TmplMeta& tm = meta[order[t]];                 // members smaller than the group are zero padded
-            const uint8_t* row = tmpl + tm.pix_off + (int64_t)dy * tm.wp;
+            const int64_t t_off = pix8 ? pix8[order[t]].off : tm.pix_off;
+            const int t_wp = pix8 ? pix8[order[t]].wp : tm.wp;
+            const uint8_t* row = tmpl + t_off + (int64_t)dy * t_wp;
             if (dy < tm.h) {
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
@@ -1028,8 +1053,17 @@ int launch_toeplitz_prep(mtm_ctx* ctx, const TcGroup& g)
     if (g.variant == 1) return MTM_OK;                      // the TS variant builds A on the fly
     const int64_t pieces = (int64_t)g.h * (g.slab_bytes / 16);
     const int blocks = (int)std::min<int64_t>((pieces + 255) / 256, 4096);
+    if (ctx->tmpl_u16) {                                   // high- and low-byte planes of 16-bit templates
+        for (int plane = 0; plane < 2; ++plane) {
+            toeplitz_prep_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_tmpl8 + plane * ctx->tmpl8_plane, ctx->d_meta, ctx->d_order + g.first,
+                                                                 g.count, g.mode, g.h, g.w, g.nk, g.slab_bytes, 1,
+                                                                 ctx->d_slabs + plane * ctx->slab_plane + g.arena_off, ctx->d_pix8);
+            MTM_LAUNCH_CHECK(ctx);
+        }
+        return MTM_OK;
+    }
     toeplitz_prep_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_tmpl, ctx->d_meta, ctx->d_order + g.first, g.count, g.mode,
-                                                         g.h, g.w, g.nk, g.slab_bytes, ctx->tmpl_C, ctx->d_slabs + g.arena_off);
+                                                         g.h, g.w, g.nk, g.slab_bytes, ctx->tmpl_C, ctx->d_slabs + g.arena_off, nullptr);
     MTM_LAUNCH_CHECK(ctx);
     return MTM_OK;
 }
@@ -1080,7 +1114,9 @@ static int launch_ncc_tc_ts(mtm_ctx* ctx, const TcGroup& g)
     return MTM_OK;
 }
 
-int launch_ncc_tc(mtm_ctx* ctx, const TcGroup& g, int method)
+struct AccumArgs { int img_plane, tmpl_plane; double weight; bool first; };
+
+static int launch_ncc_tc_impl(mtm_ctx* ctx, const TcGroup& g, int method, const AccumArgs* accum)
 {
     if (g.variant == 1) return launch_ncc_tc_ts(ctx, g);
     const ImageDev& im = ctx->img;
@@ -1088,13 +1124,20 @@ int launch_ncc_tc(mtm_ctx* ctx, const TcGroup& g, int method)
     p.method = method;
     p.sat = SatView{im.sat_s, im.sat_q, im.sat_pitch, (int64_t)(im.H + 1) * im.sat_pitch};
     p.img = im.pix; p.pitch = im.pitch; p.H = im.H; p.W = im.W;
-    p.slabs = ctx->d_slabs + g.arena_off; p.slab_bytes = g.slab_bytes; p.a_kblk = g.a_kblk; p.nk = g.nk; p.ds = g.ds;
+    const int kmode = accum ? 2 : (method != MTM_TM_CCOEFF_NORMED ? 1 : 0);      // epilogue flavour = kernel instantiation
+    p.slabs = ctx->d_slabs + g.arena_off;
+    if (accum) {
+        if (accum->img_plane) p.img = im.pix_lo;
+        p.slabs += accum->tmpl_plane * ctx->slab_plane;
+        p.acc = ctx->d_acc; p.acc_weight = accum->weight; p.acc_first = accum->first ? 1 : 0;
+    }
+    p.slab_bytes = g.slab_bytes; p.a_kblk = g.a_kblk; p.nk = g.nk; p.ds = g.ds;
     p.mode = g.mode; p.h = g.h; p.w = g.w;
     p.mh = im.H - g.h_min + 1; p.mw = im.W - g.w_min + 1;      // tile grid covers the largest member map
     p.meta = ctx->d_meta; p.order = ctx->d_order + g.first; p.count = g.count;
     p.S = ctx->d_wS; p.rsD = ctx->d_wR; p.maps = ctx->d_maps;
     p.C = im.C; p.mom_plane = ctx->moments_total;
-    if (ctx->cand_on) { p.cand = ctx->d_cand; p.cand_count = ctx->d_cand_count; p.cand_cap = MTM_CAND_CAP; p.cand_thr = ctx->cand_thr; }
+    if (ctx->cand_on && kmode == 0) { p.cand = ctx->d_cand; p.cand_count = ctx->d_cand_count; p.cand_cap = MTM_CAND_CAP; p.cand_thr = ctx->cand_thr; }
 
     // ---- persistent pipeline (two image tiles + slab ring in shared memory, two accumulators in TMEM)
     static const bool persist_off = getenv("MTM_B200_PERSIST") && atoi(getenv("MTM_B200_PERSIST")) == 0;
@@ -1140,16 +1183,18 @@ int launch_ncc_tc(mtm_ctx* ctx, const TcGroup& g, int method)
             const size_t smem_bytes = 256 + 2 * tile_b + (size_t)best_stages * stage_b;
             if (!ctx->tcp_attr_set) {
                 const int big = 227 * 1024;
-                MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_kernel<false, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-                MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_kernel<true, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-                MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_kernel<false, 12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-                MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_kernel<true, 12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-                MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_kernel<false, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-                MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_kernel<false, 12, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+                MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_kernel<false, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+                MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_kernel<true, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+                MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_kernel<false, 12, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+                MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_kernel<true, 12, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+                MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_kernel<false, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+                MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_kernel<false, 12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+                MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_kernel<false, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+                MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_kernel<false, 12, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
                 ctx->tcp_attr_set = true;
             }
             const int grid_p = std::min(p.tiles_total, ctx->sm_count);
-            static const bool prof = getenv("MTM_B200_PROF") != nullptr;       // debug: per-CTA role clocks to stderr
+            const bool prof = getenv("MTM_B200_PROF") != nullptr && kmode == 0;   // debug: per-CTA role clocks to stderr
             static const int pdbg = getenv("MTM_B200_PDBG") ? atoi(getenv("MTM_B200_PDBG")) : 0;
             long long* d_prof = nullptr;
             if (prof) {
@@ -1159,16 +1204,18 @@ int launch_ncc_tc(mtm_ctx* ctx, const TcGroup& g, int method)
             }
             p.dbg = pdbg;
             const int ew = best_ew;
-            const bool gen = method != MTM_TM_CCOEFF_NORMED;
-            if (gen) {
-                if (ew == 12) ncc_tc_persist_kernel<false, 12, true><<<grid_p, 32 * 16, smem_bytes, ctx->stream>>>(p);
-                else ncc_tc_persist_kernel<false, 8, true><<<grid_p, 32 * 12, smem_bytes, ctx->stream>>>(p);
+            if (kmode == 2) {
+                if (ew == 12) ncc_tc_persist_kernel<false, 12, 2><<<grid_p, 32 * 16, smem_bytes, ctx->stream>>>(p);
+                else ncc_tc_persist_kernel<false, 8, 2><<<grid_p, 32 * 12, smem_bytes, ctx->stream>>>(p);
+            } else if (kmode == 1) {
+                if (ew == 12) ncc_tc_persist_kernel<false, 12, 1><<<grid_p, 32 * 16, smem_bytes, ctx->stream>>>(p);
+                else ncc_tc_persist_kernel<false, 8, 1><<<grid_p, 32 * 12, smem_bytes, ctx->stream>>>(p);
             } else if (ew == 12) {
-                if (prof) ncc_tc_persist_kernel<true, 12, false><<<grid_p, 32 * 16, smem_bytes, ctx->stream>>>(p);
-                else ncc_tc_persist_kernel<false, 12, false><<<grid_p, 32 * 16, smem_bytes, ctx->stream>>>(p);
+                if (prof) ncc_tc_persist_kernel<true, 12, 0><<<grid_p, 32 * 16, smem_bytes, ctx->stream>>>(p);
+                else ncc_tc_persist_kernel<false, 12, 0><<<grid_p, 32 * 16, smem_bytes, ctx->stream>>>(p);
             } else {
-                if (prof) ncc_tc_persist_kernel<true, 8, false><<<grid_p, 32 * 12, smem_bytes, ctx->stream>>>(p);
-                else ncc_tc_persist_kernel<false, 8, false><<<grid_p, 32 * 12, smem_bytes, ctx->stream>>>(p);
+                if (prof) ncc_tc_persist_kernel<true, 8, 0><<<grid_p, 32 * 12, smem_bytes, ctx->stream>>>(p);
+                else ncc_tc_persist_kernel<false, 8, 0><<<grid_p, 32 * 12, smem_bytes, ctx->stream>>>(p);
             }
             MTM_LAUNCH_CHECK(ctx);
             if (prof) {
@@ -1207,14 +1254,24 @@ int launch_ncc_tc(mtm_ctx* ctx, const TcGroup& g, int method)
     p.N = bestN; p.R = bestN + g.h - 1;
     const size_t smem_bytes = smem_for(bestN);
     if (!ctx->tc_attr_set) {
-        MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         ctx->tc_attr_set = true;
     }
     const int xw = g.mode == 0 ? 16 : 128;
     dim3 grid((p.mw + xw - 1) / xw, (p.mh + p.N - 1) / p.N);
-    if (method != MTM_TM_CCOEFF_NORMED) ncc_tc_kernel<true><<<grid, TC_THREADS, smem_bytes, ctx->stream>>>(p);
-    else ncc_tc_kernel<false><<<grid, TC_THREADS, smem_bytes, ctx->stream>>>(p);
+    if (kmode == 2) ncc_tc_kernel<2><<<grid, TC_THREADS, smem_bytes, ctx->stream>>>(p);
+    else if (kmode == 1) ncc_tc_kernel<1><<<grid, TC_THREADS, smem_bytes, ctx->stream>>>(p);
+    else ncc_tc_kernel<0><<<grid, TC_THREADS, smem_bytes, ctx->stream>>>(p);
     MTM_LAUNCH_CHECK(ctx);
     return MTM_OK;
+}
+
+int launch_ncc_tc(mtm_ctx* ctx, const TcGroup& g, int method) { return launch_ncc_tc_impl(ctx, g, method, nullptr); }
+
+int launch_ncc_tc_accum(mtm_ctx* ctx, const TcGroup& g, int img_plane, int tmpl_plane, double weight, bool first)
+{
+    const AccumArgs a{img_plane, tmpl_plane, weight, first};
+    return launch_ncc_tc_impl(ctx, g, MTM_TM_CCORR, &a);
 }
