@@ -121,15 +121,37 @@ def _prepare(listTemplates, image, method):
     (MTM/__init__.py:207-222, 67-88) applied to the whole list."""
     names, arrays, masks = [], [], []
     img = image
+    img_f32 = None                     # the image is cast at most once (the reference casts it once per template)
+    # 16-bit grayscale without usable masks: hand the integers over as they are (MTM_U16).  The library keeps the reference's
+    # float32 semantics for the statistics and computes the numerator exactly from the byte planes on the tensor cores.
+    route16 = _all_uint16(image, [t[1] for t in listTemplates]) and \
+        not any(len(t) >= 3 and t[2] is not None and method in (0, 3) for t in listTemplates)
     for tempTuple in listTemplates:
         name, template = tempTuple[:2]
+        if route16:
+            if len(tempTuple) >= 3 and method not in (0, 3):
+                warnings.warn("Template matching method not supporting the use of Mask. Use 0/TM_SQDIFF or 3/TM_CCORR_NORMED.")
+            names.append(name)
+            arrays.append(template)
+            masks.append(None)
+            continue
         mask = None
         if len(tempTuple) >= 3:
             if method in (0, 3):
                 mask = tempTuple[2]
             else:
                 warnings.warn("Template matching method not supporting the use of Mask. Use 0/TM_SQDIFF or 3/TM_CCORR_NORMED.")
-        template, img_t, mask = _dtype_policy(template, image, mask)
+        if template.dtype == "float64" or image.dtype == "float64":
+            raise ValueError("64-bit images not supported, max 32-bit")
+        if template.dtype == "uint8" and image.dtype == "uint8":
+            img_t = image
+        else:                          # MTM/__init__.py:71-74
+            template = np.float32(template)
+            if img_f32 is None:
+                img_f32 = image if image.dtype == np.float32 else np.float32(image)
+            img_t = img_f32
+            if mask is not None:
+                mask = np.float32(mask)
         mask = _mask_policy(template, mask, method)
         if template.ndim != img_t.ndim or template.shape[2:] != img_t.shape[2:]:
             raise _cv_error("matchTemplate: image and template must have the same number of dimensions/channels")
@@ -138,10 +160,6 @@ def _prepare(listTemplates, image, method):
         names.append(name)
         arrays.append(template)
         masks.append(mask)
-    if _all_uint16(image, [t[1] for t in listTemplates]) and all(m is None for m in masks):
-        # 16-bit grayscale: hand the integers over as they are (MTM_U16).  The library keeps the reference's float32
-        # semantics for the statistics and computes the numerator exactly from the byte planes on the tensor cores.
-        return names, [t[1] for t in listTemplates], image, masks
     return names, arrays, img, masks
 
 
