@@ -426,7 +426,6 @@ static int plan_tensor_path(mtm_ctx* ctx)
             if (!alone(mj.h, mj.w, sj)) return MTM_OK;
             const int hg2 = std::max(hg, mj.h), wg2 = std::max(wg, mj.w);
             if (!tc_plan_group(0, hg2, wg2, TC, grown)) break;
-            if (grown.variant == 1 && (mj.h != m0.h || mj.w != m0.w)) break;   // TS variant: same-size groups only
             if (cost(grown) > cost(open) + cost(sj)) break;          // cheaper to start a new group
             open = grown; hg = hg2; wg = wg2;
             h_min = std::min(h_min, mj.h); w_min = std::min(w_min, mj.w);

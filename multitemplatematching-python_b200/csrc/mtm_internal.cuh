@@ -62,9 +62,7 @@ struct SizeDesc {
 struct TcGroup {
     int mode;                  // 0: 8 templates x 16 x-offsets, 1: 1 template x 128 x-offsets
     int first, count;
-    int variant;               // 0: SS (Toeplitz slabs streamed from HBM/L2), 1: TS (A built into TMEM on the fly)
     int h, w, nk, a_kblk, slab_bytes, ds, N, R;
-    int row_stride, slots;     // TS variant
     size_t smem;
     int64_t arena_off;         // byte offset of the group's Toeplitz slabs in d_slabs
     int h_min, w_min;          // smallest member (largest score map): the tile grid covers its map

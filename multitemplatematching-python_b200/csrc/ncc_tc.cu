@@ -711,228 +711,6 @@ ncc_tc_persist_kernel(const TcParams p)
     if (warp == EW) tmem_dealloc(tmem_base, tmem_cols);
 }
 
-// ---------------------------------------------------------------------------------------------
-// Variant "TS" (mode A): the Toeplitz operand never exists in memory.  Four producer warps
-// build each thread's A row (lane m = 16*t + r holds T_t[dy][u - r], u = 0 .. 32*nk) in
-// registers from the compact template rows staged in shared memory, and write it straight
-// into TMEM with tcgen05.st; the MMA takes A from TMEM ([a_tmem] operand) and B (image rows)
-// from shared memory.  Per dy the CTA reads 8*w template bytes instead of a 2*nk*2048-byte slab,
-// so neither L2 nor shared-memory bandwidth sits between the templates and the tensor pipe.
-// TMEM budget per CTA: 128 accumulator columns (N = 128 output rows) + 128 columns of A ring.
-struct TsParams {
-    const uint8_t* img; int64_t pitch; int H, W;
-    const uint8_t* tmpl;
-    int nk, N, R, h, w, wp, mh, mw;
-    int row_stride;                   // bytes between staged template rows in shared memory
-    int tmpl_stride;                  // bytes between staged templates (h*row_stride + 16: bank skew)
-    long long pix_off[8];             // byte offsets of the group's templates in the template arena
-    int slots;                        // A ring depth (TMEM slots of 8*nk columns)
-    const TmplMeta* meta; const int32_t* order; int count;
-    const uint32_t* S; const float* rsD;
-    float* maps;
-    long long* prof;                  // optional: per-CTA phase clocks
-    int dbg;                          // debug: 1 = skip tcgen05.st, 2 = skip the LDS (timing experiments only)
-};
-
-__device__ __forceinline__ void umma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}"
-                 ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v)
-{
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
-}
-
-// One lane's A row for one dy: output word j = funnel(W[j-A-1], W[j-A], 8s) with W[k] = template word k
-// (row word k + 4 behind the 16-byte zero border).  Every 8 output words consume exactly two 16-byte
-// chunks, so the chunk alignment (4 - A) % 4 is a compile-time constant of the producer warp.
-template <int A>
-__device__ __forceinline__ void ts_build_row(const uint4* __restrict__ row, int sh, int nk, uint32_t taddr, int dbg)
-{
-    constexpr int C0 = (A == 0) ? 1 : 0;                    // chunk of row word 4 - A
-    constexpr int P0 = (A == 0) ? 0 : 4 - A;                // its position inside the chunk
-    uint32_t lo = 0u;                                       // W[-A-1] lies in the zero border
-    for (int i = 0; i < nk; ++i) {
-        uint4 q0 = make_uint4(1u, 2u, 3u, 4u), q1 = q0, q2 = make_uint4(0u, 0u, 0u, 0u);
-        if (!(dbg & 2)) {
-            q0 = row[C0 + 2 * i]; q1 = row[C0 + 2 * i + 1];
-            if (P0 != 0) q2 = row[C0 + 2 * i + 2];
-        }
-        const uint32_t w[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
-        uint32_t v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const uint32_t hi = w[P0 + j];
-            v[j] = __funnelshift_l(lo, hi, sh);
-            lo = hi;
-        }
-        if (!(dbg & 1)) tmem_st8(taddr + (uint32_t)(8 * i), v);
-        else if (v[0] == 0xdeadbeefu && v[7] == 0x12345u) asm volatile("trap;");   // keep v alive
-    }
-}
-
-constexpr int TS_MAX_SLOTS = 8;
-
-// TMEM lane m <-> (a, t, s) = (m >> 5, (m >> 2) & 7, m & 3): template t, x-offset r = 4a + s.  The word
-// part `a` of the shift is uniform per producer warp, so every lane of a template reads the SAME
-// 16-byte chunks of the (zero-bordered) template row -- broadcast LDS.128 -- and only the byte part
-// `s` is a per-lane funnel shift.
-__global__ void __launch_bounds__(TC_THREADS, 2)
-ncc_tc_ts_kernel(const TsParams p)
-{
-    extern __shared__ __align__(1024) uint8_t smem[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int kb_img = 2 * p.nk;
-    const uint32_t tile_bytes = ((uint32_t)kb_img * p.R * 16 + 127) & ~127u;
-    const uint32_t rows_bytes = ((uint32_t)8 * p.tmpl_stride + 127) & ~127u;
-    uint8_t* tile = smem;
-    uint8_t* trows = smem + tile_bytes;                         // [t][dy][row_stride], 16 zero bytes before each row
-    uint64_t* bars = reinterpret_cast<uint64_t*>(trows + rows_bytes);
-    uint64_t* a_full = bars;                                    // [slots]  4 producer-warp arrivals
-    uint64_t* a_empty = bars + TS_MAX_SLOTS;                    // [slots]  tcgen05.commit
-    uint64_t* accum = bars + 2 * TS_MAX_SLOTS;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TS_MAX_SLOTS + 1);
-
-    const int x0 = blockIdx.x * 16, y0 = blockIdx.y * p.N;
-    long long t_begin = 0, t_loaded = 0, t_main = 0;
-    if (p.prof && tid == 0) t_begin = clock64();
-
-    if (tid == 0) {
-        for (int s = 0; s < p.slots; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1); }
-        mbar_init(accum, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    const uint32_t tmem_total = p.N <= 128 ? 256u : 512u;        // N accumulator columns + the A ring
-    if (warp == 4) tmem_alloc(tmem_slot, tmem_total);
-
-    // ---- stage the image tile [k-block][row][16 B] and the zero-bordered template rows
-    {
-        const int pieces = kb_img * p.R;
-        for (int idx = tid; idx < pieces; idx += TC_THREADS) {
-            const int c = idx / p.R, r = idx - c * p.R;
-            const int gy = y0 + r;
-            const int64_t gb = (int64_t)x0 + 16 * c;
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (gy < p.H && gb + 16 <= p.pitch) v = *reinterpret_cast<const uint4*>(p.img + (int64_t)gy * p.pitch + gb);
-            *reinterpret_cast<uint4*>(tile + (size_t)idx * 16) = v;
-        }
-        // row = [16 B zeros][wp template bytes][zeros ...] ; row_stride/4 words, all written here
-        const int rsq = p.row_stride >> 2, wq = p.wp >> 2;
-        const int total = 8 * p.h * rsq;
-        for (int idx = tid; idx < total; idx += TC_THREADS) {
-            const int rw = idx / rsq, g = idx - rw * rsq;              // rw = t*h + dy
-            const int t = rw / p.h, dy = rw - t * p.h;
-            uint32_t v = 0u;
-            if (t < p.count && g >= 4 && g - 4 < wq)
-                v = __ldg(reinterpret_cast<const uint32_t*>(p.tmpl + p.pix_off[t] + (int64_t)dy * p.wp) + (g - 4));
-            reinterpret_cast<uint32_t*>(trows + (size_t)t * p.tmpl_stride + (size_t)dy * p.row_stride)[g] = v;
-        }
-    }
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_d = tmem_base;                           // columns [0, N)
-    const uint32_t tmem_a = tmem_base + (p.N <= 128 ? 128u : 256u); // A ring behind the accumulator columns
-    const int slot_cols = 8 * p.nk;
-    if (p.prof && tid == 0) t_loaded = clock64();
-
-    if (warp < 4) {
-        // ===== A producers: warp a = word shift; lane = (t, s) =====
-        const int a = warp, t = lane >> 2, sh = 8 * (lane & 3);
-        // A word j of lane (a, t, s) = bytes T[4(j - a) - s ..]; with the 16-byte zero border the needed
-        // words start at row word index 3 - a.  Read aligned 16-byte chunks starting at chunk 0.
-        const uint8_t* rows_t = trows + (size_t)t * p.tmpl_stride;
-        const uint32_t lane_addr = tmem_a + ((uint32_t)(32 * warp) << 16);
-        const bool pf = p.prof && warp == 0 && lane == 0;
-        long long c_wait = 0, c_build = 0, c_store = 0;
-        for (int dy = 0; dy < p.h; ++dy) {
-            const int s = dy % p.slots;
-            long long c0 = pf ? clock64() : 0;
-            if (dy >= p.slots) {
-                if (lane == 0) mbar_wait(&a_empty[s], ((dy / p.slots) - 1) & 1);
-                __syncwarp();
-            }
-            tc_fence_after();
-            long long c1 = pf ? clock64() : 0;
-            const uint4* row = reinterpret_cast<const uint4*>(rows_t + (size_t)dy * p.row_stride);
-            const uint32_t slot_addr = lane_addr + (uint32_t)(s * slot_cols);
-            switch (a) {                                            // warp-uniform: compile-time word alignment
-                case 0: ts_build_row<0>(row, sh, p.nk, slot_addr, p.dbg); break;
-                case 1: ts_build_row<1>(row, sh, p.nk, slot_addr, p.dbg); break;
-                case 2: ts_build_row<2>(row, sh, p.nk, slot_addr, p.dbg); break;
-                default: ts_build_row<3>(row, sh, p.nk, slot_addr, p.dbg); break;
-            }
-            long long c2 = pf ? clock64() : 0;
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&a_full[s]);
-            if (pf) { const long long c3 = clock64(); c_wait += c1 - c0; c_build += c2 - c1; c_store += c3 - c2; }
-        }
-        if (pf) { long long* q = p.prof + 8 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x); q[4] = c_wait; q[5] = c_build; q[6] = c_store; }
-    } else if (warp == 4) {
-        if (lane == 0) {
-            const uint32_t idesc = (2u << 4) | ((uint32_t)(p.N >> 3) << 17) | ((128u >> 4) << 24);
-            const uint32_t tile_addr = smem_u32(tile);
-            const uint32_t lbo_b = (uint32_t)p.R * 16;
-            long long m_wait = 0;
-            for (int dy = 0; dy < p.h; ++dy) {
-                const int s = dy % p.slots;
-                const long long c0 = p.prof ? clock64() : 0;
-                mbar_wait(&a_full[s], (dy / p.slots) & 1);
-                tc_fence_after();
-                if (p.prof) m_wait += clock64() - c0;
-                for (int i = 0; i < p.nk; ++i) {
-                    const uint64_t bd = umma_desc(tile_addr + dy * 16 + 2 * i * lbo_b, lbo_b, 128);
-                    umma_i8_ts(tmem_d, tmem_a + (uint32_t)(s * slot_cols + 8 * i), bd, idesc, (dy | i) != 0);
-                }
-                umma_commit(&a_empty[s]);
-            }
-            umma_commit(accum);
-            if (p.prof) p.prof[8 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x) + 7] = m_wait;
-        }
-        __syncwarp();
-    }
-
-    // ===== epilogue: all 8 warps (only the MMA warp polls; the rest blocks in bar.sync) =====
-    if (warp == 4) { if (lane == 0) mbar_wait(accum, 0); __syncwarp(); }
-    __syncthreads();
-    tc_fence_after();
-    if (p.prof && tid == 0) t_main = clock64();
-    {
-        const int m = 32 * (warp & 3) + lane;
-        const int tsel = (m >> 2) & 7, x = x0 + 4 * (m >> 5) + (m & 3);
-        const bool live = (tsel < p.count) && (x < p.mw);
-        const TmplMeta* tm = live ? &p.meta[p.order[tsel]] : nullptr;
-        const long long area = (long long)p.h * p.w;
-        const long long sumT = live ? tm->isum[0] : 0;
-        const float ct = live ? tm->inv_sqrt_d2 : 0.f;
-        const bool is_const = live ? (tm->is_const != 0) : false;
-        float* out = live ? p.maps + tm->map_off : nullptr;
-        const int half = p.N >> 1;
-        const int c_begin = (warp >> 2) * half, c_end = c_begin + half;
-        for (int c0 = c_begin; c0 < c_end; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c0, v);
-            if (!live || y0 + c0 >= p.mh) continue;
-            epilogue16(v, y0 + c0, p.mh, p.mw, x, area, sumT, ct, is_const, reinterpret_cast<const uint2*>(p.S) + tm->mom_off, out,
-                       CandSink{nullptr, nullptr, 0, 0.f, 0, 0, 0}, false);
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem_base, tmem_total);
-    if (p.prof && tid == 0) {
-        long long* q = p.prof + 8 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x);
-        q[0] = t_loaded - t_begin; q[1] = t_main - t_loaded; q[2] = clock64() - t_main; q[3] = t_begin;
-    }
-}
-
 // Expands the templates of one group into Toeplitz slabs (see the header comment).
 __global__ void toeplitz_prep_kernel(const uint8_t* __restrict__ tmpl, const TmplMeta* __restrict__ meta,
                                      const int32_t* __restrict__ order, int count, int mode, int h, int w,
@@ -1000,7 +778,6 @@ bool tc_path_supported(const mtm_ctx* ctx, int method, int h, int w)
 {
     const int C = ctx->img.C;
     if ((C != 1 && C != 3 && C != 4) || method < 0 || method > 5) return false;
-    if (method != MTM_TM_CCOEFF_NORMED && getenv("MTM_B200_TS")) return false;    // the experimental TS kernel only has the default epilogue
     if ((long long)h * w < 16 || (double)h * w * C * 65025.0 >= 4294967296.0) return false;   // 32-bit exact range; tiny windows -> fp64 path
     return true;
 }
@@ -1008,24 +785,10 @@ bool tc_path_supported(const mtm_ctx* ctx, int method, int h, int w)
 // Plans a group of `count` same-size templates.  Returns false when the tile does not fit shared memory.
 bool tc_plan_group(int mode, int h, int w, int C, TcGroup& g)
 {
-    g.mode = mode; g.h = h; g.w = w; g.variant = 0;
+    g.mode = mode; g.h = h; g.w = w;
     if (mode == 1 && C != 1) return false;                 // the aliased 128-offset layout needs a 1-byte x-step
     const int nx = mode == 0 ? 16 : 128;
     g.nk = (w * C + (nx - 1) * C + 31) / 32;               // band: template row bytes + the largest x-shift
-    if (mode == 0 && C == 1 && g.nk <= 5 && getenv("MTM_B200_TS")) {      // experimental: off by default (SS is faster today)
-        // TS variant: A generated into TMEM, N = 128 output rows, compact template rows resident in smem
-        int rs = 16 + 32 * g.nk + 16;
-        g.row_stride = rs;
-        g.N = getenv("MTM_B200_TS_N256") ? 256 : 128; g.R = g.N + h - 1;
-        g.slots = std::min(TS_MAX_SLOTS, g.N / (8 * g.nk));
-        const size_t tile = ((size_t)2 * g.nk * g.R * 16 + 127) & ~(size_t)127;
-        const size_t rows = ((size_t)8 * ((size_t)h * g.row_stride + 16) + 127) & ~(size_t)127;   // +16: bank skew between templates
-        if (tile + rows + 256 <= 224 * 1024 && g.R * 16 < (1 << 18)) {
-            g.variant = 1; g.smem = tile + rows + 256; g.slab_bytes = 0; g.ds = 0; g.a_kblk = 0;
-            g.eff = (double)w / (32.0 * g.nk);
-            return true;
-        }
-    }
     g.a_kblk = mode == 0 ? 2048 : 256;
     g.slab_bytes = mode == 0 ? 2 * g.nk * 2048 : (7 + 2 * g.nk) * 256;
     g.ds = 1;
@@ -1050,7 +813,6 @@ bool tc_plan_group(int mode, int h, int w, int C, TcGroup& g)
 
 int launch_toeplitz_prep(mtm_ctx* ctx, const TcGroup& g)
 {
-    if (g.variant == 1) return MTM_OK;                      // the TS variant builds A on the fly
     const int64_t pieces = (int64_t)g.h * (g.slab_bytes / 16);
     const int blocks = (int)std::min<int64_t>((pieces + 255) / 256, 4096);
     if (ctx->tmpl_u16) {                                   // high- and low-byte planes of 16-bit templates
@@ -1080,45 +842,10 @@ int launch_window_moments(mtm_ctx* ctx)
     return MTM_OK;
 }
 
-static int launch_ncc_tc_ts(mtm_ctx* ctx, const TcGroup& g)
-{
-    const ImageDev& im = ctx->img;
-    TsParams p{};
-    p.img = im.pix; p.pitch = im.pitch; p.H = im.H; p.W = im.W;
-    p.tmpl = ctx->d_tmpl;
-    p.nk = g.nk; p.N = g.N; p.R = g.R; p.h = g.h; p.w = g.w; p.wp = (g.w + 3) / 4 * 4;
-    p.mh = im.H - g.h + 1; p.mw = im.W - g.w + 1;
-    p.row_stride = g.row_stride; p.slots = g.slots; p.tmpl_stride = g.h * g.row_stride + 16;
-    for (int t = 0; t < 8; ++t) p.pix_off[t] = t < g.count ? ctx->h_meta[ctx->h_order[g.first + t]].pix_off : 0;
-    p.meta = ctx->d_meta; p.order = ctx->d_order + g.first; p.count = g.count;
-    p.S = ctx->d_wS; p.rsD = ctx->d_wR; p.maps = ctx->d_maps;
-    MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    dim3 grid((p.mw + 15) / 16, (p.mh + g.N - 1) / g.N);
-    static const bool prof = getenv("MTM_B200_PROF") != nullptr;       // debug: per-CTA phase clocks to stderr
-    long long* d_prof = nullptr;
-    const size_t n_cta = (size_t)grid.x * grid.y;
-    if (prof) { MTM_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&d_prof), n_cta * 8 * sizeof(long long))); p.prof = d_prof; }
-    p.dbg = getenv("MTM_B200_TS_DBG") ? atoi(getenv("MTM_B200_TS_DBG")) : 0;
-    ncc_tc_ts_kernel<<<grid, TC_THREADS, g.smem, ctx->stream>>>(p);
-    MTM_LAUNCH_CHECK(ctx);
-    if (prof) {
-        std::vector<long long> hp(n_cta * 8);
-        MTM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        MTM_CUDA(ctx, cudaMemcpy(hp.data(), d_prof, hp.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-        cudaFree(d_prof);
-        double a = 0, b = 0, c = 0, pw = 0, pb = 0, ps = 0, mw = 0;
-        for (size_t i = 0; i < n_cta; ++i) { a += hp[8*i]; b += hp[8*i+1]; c += hp[8*i+2]; pw += hp[8*i+4]; pb += hp[8*i+5]; ps += hp[8*i+6]; mw += hp[8*i+7]; }
-        fprintf(stderr, "[mtm prof] ts kernel: %zu CTAs, mean clocks load=%.0f main=%.0f epilogue=%.0f | producer wait=%.0f build=%.0f store=%.0f | mma wait=%.0f (smem %zu B, nk=%d, h=%d)\n",
-                n_cta, a / n_cta, b / n_cta, c / n_cta, pw / n_cta, pb / n_cta, ps / n_cta, mw / n_cta, g.smem, g.nk, g.h);
-    }
-    return MTM_OK;
-}
-
 struct AccumArgs { int img_plane, tmpl_plane; double weight; bool first; };
 
 static int launch_ncc_tc_impl(mtm_ctx* ctx, const TcGroup& g, int method, const AccumArgs* accum)
 {
-    if (g.variant == 1) return launch_ncc_tc_ts(ctx, g);
     const ImageDev& im = ctx->img;
     TcParams p{};
     p.method = method;
