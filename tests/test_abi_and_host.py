@@ -77,3 +77,33 @@ def test_api_surface_matches_reference(mtm):
     from MTM.NMS import NMS
     assert NMS is mtm.NMS
     assert callable(mtm.drawBoxesOnRGB) and callable(mtm.drawBoxesOnGray)
+
+
+def test_dtype_routing_of_the_host_layer(mtm):
+    """The dtype / mask policy (MTM/__init__.py:67-88, 207-222) without a device: which arrays reach the C ABI."""
+    import warnings
+    from mtm_b200 import _native, api
+    img8, t8 = np.zeros((20, 30), np.uint8), np.zeros((5, 6), np.uint8)
+    img16, t16 = img8.astype(np.uint16), t8.astype(np.uint16)
+    # uint8 stays uint8; anything else becomes float32, the image cast once and shared
+    _, arrs, img, _ = api._prepare([("a", t8), ("b", t8)], img8, 5)
+    assert img is img8 and all(a.dtype == np.uint8 for a in arrs)
+    _, arrs, img, _ = api._prepare([("a", t8.astype(np.float32)), ("b", t16)], img16, 5)
+    assert img.dtype == np.float32 and all(a.dtype == np.float32 for a in arrs)
+    # all-uint16 grayscale: handed over untouched (MTM_U16), unless a usable mask forces the float32 route
+    _, arrs, img, masks = api._prepare([("a", t16), ("b", t16)], img16, 5)
+    assert img is img16 and arrs[0] is t16 and masks == [None, None]
+    assert _native._dtype_code(img16) == _native.MTM_U16 == 2
+    _, arrs, img, masks = api._prepare([("a", t16, np.ones_like(t16))], img16, 3)
+    assert img.dtype == np.float32 and arrs[0].dtype == np.float32 and masks[0].dtype == np.float32
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        _, arrs, img, masks = api._prepare([("a", t16, np.ones_like(t16))], img16, 5)     # mask unusable with method 5
+    assert img is img16 and masks == [None] and len(w) == 1
+    rgb16 = np.zeros((20, 30, 3), np.uint16)
+    _, arrs, img, _ = api._prepare([("a", rgb16[:5, :6])], rgb16, 5)                         # 16-bit RGB: float32 route
+    assert img.dtype == np.float32
+    with pytest.raises(ValueError, match="64-bit"):
+        api._prepare([("a", t8.astype(np.float64))], img8, 5)
+    with pytest.raises(TypeError):
+        _native._dtype_code(np.zeros(3, np.int32))
