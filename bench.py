@@ -14,8 +14,8 @@ rot90), score_threshold 0.5, maxOverlap 0.25.
 * ``e2e``    : the same metric through the public Python API ``MTM.matchTemplates``
                with HOST (pinned) image/template arrays: H2D of image + templates
                and D2H of the hit list inside the timed region.
-* ``roofline``: the numerator kernel (ncc_direct / ncc_tc), bracketed by CUDA events
-               inside the same timed region (MTM_OPT_TIME_NCC).
+* ``roofline``: the numerator kernel (ncc_tc_persist / ncc_tc / ncc_direct), bracketed by CUDA events
+               (MTM_OPT_TIME_NCC) in a second, single-stream synchronous region of the same run.
 * ``cpu_baseline`` / ``--impl reference``: the CPU port of the reference on live
                OpenCV (oracle/mtm_port.py; /root/reference cannot travel to the GPU
                box), its own thread pool + cv2's threads, same workload.

@@ -10,8 +10,8 @@
 // so the image tile is loaded ONCE into shared memory and every dy just moves the B
 // descriptor's start address by one 16-byte row (no-swizzle K-major layout
 // [k-block][row][16 B], SBO = 128 B, LBO = rows*16 B).  The Toeplitz A slabs are
-// expanded once per template set (toeplitz_prep_kernel) and streamed per dy with
-// cp.async.bulk + mbarrier into a 4-stage ring.
+// expanded once per template set (toeplitz_prep_kernel) and streamed with
+// cp.async.bulk + mbarrier through a shared-memory ring.
 //   mode A: m = (t, r):  8 templates x 16 x-offsets     slab [k-block][t][r][16 B]
 //   mode B: m = (q', r): 1 template x 128 x-offsets, x = x0 + 16*(7-q') + r; slab
 //           [block b][r][16 B] with LBO = 256 B so that consecutive K blocks alias the next
@@ -20,6 +20,10 @@
 // tcgen05.ld and applies OpenCV's normalisation in exact-integer + fp32 form:
 //     score = (A*CC - S*sumT) * rsqrt(A*Q - S^2) * rsqrt(A*sumT2 - sumT^2),  clamped to [-1, 1],
 // with S and rsqrt(A*Q - S^2) precomputed per window size (window_moments_kernel).
+// Kernels: ncc_tc_persist_kernel<PROF, EW, MODE> (default: persistent, warp-specialised, two image tiles
+// and two accumulators in flight) and ncc_tc_kernel<MODE> (one tile per CTA, for tiles too large to
+// double-buffer).  MODE selects the epilogue: 0 the default above, 1 OpenCV's float64 rules for the
+// other five methods, 2 weighted accumulation of a byte-plane product (16-bit images).
 // Roofline: tensor pipe (kind::i8, 8192 MAC/clk/SM); useful fraction w / (32*nk).
 #include "mtm_internal.cuh"
 #include "ncc_epilogue.cuh"
