@@ -510,7 +510,8 @@ static int compute_maps_masked(mtm_ctx* ctx, int method)
 static void request_candidates(mtm_ctx* ctx, int method, int64_t n_object, double thr)
 {
     ctx->cand_on = false;
-    if (method != MTM_TM_CCOEFF_NORMED || n_object == 1 || getenv("MTM_B200_NO_CAND")) return;
+    static const bool no_cand = getenv("MTM_B200_NO_CAND") != nullptr;     // experiments: always stream the maps for peaks
+    if (method != MTM_TM_CCOEFF_NORMED || n_object == 1 || no_cand) return;
     for (int t = 0; t < ctx->n_tmpl; ++t) {
         const TmplMeta& m = ctx->h_meta[t];
         if (m.mh == 1 || m.mw == 1 || (int64_t)m.mh * m.mw <= MTM_CAND_CAP) return;

@@ -778,6 +778,31 @@ __global__ void window_moments_kernel(SatView sat, const uint32_t* __restrict__ 
 }  // namespace
 
 // ------------------------------------------------------------------------------ host side
+// Experiment knobs (environment, read once).  None of them is needed in production; they exist so that the
+// measurements under profiles/ can be repeated: tile height, ring stage size, epilogue warps, shared-memory ceiling,
+// the one-tile-per-CTA kernel, per-role clocks and phase knock-outs of the persistent kernel.
+struct TcEnv {
+    int force_n = 0, ds = 0, ew = 0, pdbg = 0;
+    size_t smem_soft = 0;
+    bool persist_off = false, prof = false;
+    TcEnv()
+    {
+        auto num = [](const char* name) { const char* v = getenv(name); return v ? atoi(v) : 0; };
+        force_n = num("MTM_B200_FORCE_N");
+        ds = num("MTM_B200_DS");
+        ew = getenv("MTM_B200_EW") ? (num("MTM_B200_EW") == 12 ? 12 : 8) : 0;
+        pdbg = num("MTM_B200_PDBG");
+        smem_soft = getenv("MTM_B200_SMEM_SOFT") ? (size_t)num("MTM_B200_SMEM_SOFT") * 1024 : 0;
+        persist_off = getenv("MTM_B200_PERSIST") && num("MTM_B200_PERSIST") == 0;
+        prof = getenv("MTM_B200_PROF") != nullptr;
+    }
+};
+static const TcEnv& tc_env()
+{
+    static const TcEnv e;
+    return e;
+}
+
 bool tc_path_supported(const mtm_ctx* ctx, int method, int h, int w)
 {
     const int C = ctx->img.C;
@@ -798,7 +823,7 @@ bool tc_plan_group(int mode, int h, int w, int C, TcGroup& g)
     g.ds = 1;
     while ((g.ds + 1) * g.slab_bytes <= 16384 && g.ds < h) ++g.ds;
     const size_t ring = (size_t)TC_STAGES * g.ds * g.slab_bytes;
-    const int force_n = getenv("MTM_B200_FORCE_N") ? atoi(getenv("MTM_B200_FORCE_N")) : 0;   // experiments
+    const int force_n = tc_env().force_n;
     const int candidates[4] = {force_n ? force_n : 256, force_n ? force_n : 128, force_n ? force_n : 64, force_n ? force_n : 32};
     g.N = 0;
     for (int pass = 0; pass < 2 && !g.N; ++pass) {
@@ -871,22 +896,20 @@ static int launch_ncc_tc_impl(mtm_ctx* ctx, const TcGroup& g, int method, const 
     if (ctx->cand_on && kmode == 0) { p.cand = ctx->d_cand; p.cand_count = ctx->d_cand_count; p.cand_cap = MTM_CAND_CAP; p.cand_thr = ctx->cand_thr; }
 
     // ---- persistent pipeline (two image tiles + slab ring in shared memory, two accumulators in TMEM)
-    static const bool persist_off = getenv("MTM_B200_PERSIST") && atoi(getenv("MTM_B200_PERSIST")) == 0;
-    if (!persist_off) {
+    if (!tc_env().persist_off) {
         const int xw_p = g.mode == 0 ? 16 : 128;
         const int gx_p = (p.mw + xw_p - 1) / xw_p;
         int ds_p = std::max(1, std::min(g.h, 24576 / g.slab_bytes));           // slabs (template rows) per ring stage
-        if (getenv("MTM_B200_DS")) ds_p = std::max(1, std::min(g.h, atoi(getenv("MTM_B200_DS"))));   // experiments
+        if (tc_env().ds) ds_p = std::max(1, std::min(g.h, tc_env().ds));
         const size_t stage_b = (size_t)ds_p * g.slab_bytes;
-        const int force_n = getenv("MTM_B200_FORCE_N") ? atoi(getenv("MTM_B200_FORCE_N")) : 0;
+        const int force_n = tc_env().force_n;
         // Cost model (clocks per CTA).  Per MMA: tensor pipe n/2, shared-memory traffic (A 4 KB read + 4 KB slab write +
         // 32*n B read at 128 B/clk) 64 + n/4.  The epilogue of a tile (~TCP_EPI_CLK_PER_ROW clocks per row with 8 warps)
         // overlaps the MMAs of the next one; the first image tile and the last epilogue are exposed.
-        const size_t smem_soft = getenv("MTM_B200_SMEM_SOFT") ? (size_t)atoi(getenv("MTM_B200_SMEM_SOFT")) * 1024 : TCP_SMEM_SOFT;
+        const size_t smem_soft = tc_env().smem_soft ? tc_env().smem_soft : TCP_SMEM_SOFT;
         int bestN = 0, best_stages = 0, best_ew = 8;
         double best_cost = 1e300;
-        int force_ew = 0;
-        if (getenv("MTM_B200_EW")) { const int e = atoi(getenv("MTM_B200_EW")); force_ew = e == 12 ? 12 : 8; }   // experiments
+        const int force_ew = tc_env().ew;
         for (int n = 256; n >= 32; n -= 16) {
             if (force_n && n != force_n) continue;
             const size_t tile_b = ((size_t)2 * g.nk * (n + g.h - 1) * 16 + 127) & ~(size_t)127;
@@ -925,8 +948,8 @@ static int launch_ncc_tc_impl(mtm_ctx* ctx, const TcGroup& g, int method, const 
                 ctx->tcp_attr_set = true;
             }
             const int grid_p = std::min(p.tiles_total, ctx->sm_count);
-            const bool prof = getenv("MTM_B200_PROF") != nullptr && kmode == 0;   // debug: per-CTA role clocks to stderr
-            static const int pdbg = getenv("MTM_B200_PDBG") ? atoi(getenv("MTM_B200_PDBG")) : 0;
+            const bool prof = tc_env().prof && kmode == 0;            // debug: per-CTA role clocks to stderr
+            const int pdbg = tc_env().pdbg;
             long long* d_prof = nullptr;
             if (prof) {
                 MTM_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&d_prof), (size_t)grid_p * 16 * sizeof(long long)));
@@ -981,7 +1004,7 @@ static int launch_ncc_tc_impl(mtm_ctx* ctx, const TcGroup& g, int method, const 
         const double cost = (double)waves * (n + 0.25 * g.h + 16.0) / per_sm;
         if (cost < best_cost - 1e-9) { best_cost = cost; bestN = n; }
     }
-    if (getenv("MTM_B200_FORCE_N")) bestN = g.N;
+    if (tc_env().force_n) bestN = g.N;
     p.N = bestN; p.R = bestN + g.h - 1;
     const size_t smem_bytes = smem_for(bestN);
     if (!ctx->tc_attr_set) {
