@@ -20,8 +20,9 @@ def _load():
 
 
 _impl = _load()
-from mtm_b200 import (BBox, TemplateTuple, __version__, computeScoreMap, drawBoxesOnGray,  # noqa: E402,F401
-                      drawBoxesOnRGB, findMatches, matchTemplates, matchTemplatesBatch)
+from mtm_b200 import (TRANSFORMS, BBox, TemplateTuple, __version__, computeScoreMap, drawBoxesOnGray,  # noqa: E402,F401
+                      drawBoxesOnRGB, expandTemplates, findMatches, matchTemplates, matchTemplatesAugmented,
+                      matchTemplatesBatch, matchTemplatesPyramid)
 # as in the reference (MTM/__init__.py:13): importing the submodule first, then rebinding the
 # name, leaves ``MTM.NMS`` bound to the FUNCTION while ``from MTM.NMS import NMS`` also works
 from .NMS import NMS, Hit  # noqa: E402,F401

@@ -44,6 +44,21 @@ typedef enum mtm_method {
 
 /* Numerator kernel selection (mtm_set_option MTM_OPT_PATH). */
 typedef enum mtm_path { MTM_PATH_AUTO = 0, MTM_PATH_DIRECT = 1, MTM_PATH_TENSOR = 2 } mtm_path;
+/* The 8 symmetries of the square applied to a template on the device (mtm_set_templates_transformed): what the
+ * tutorials of the reference do with numpy before calling matchTemplates (Tutorial2-Template_Augmentation.ipynb
+ * cell 15: np.rot90(template, k), "We could also do some flipping with np.fliplr, flipud"). */
+typedef enum mtm_transform {
+    MTM_XF_IDENTITY = 0,
+    MTM_XF_ROT90 = 1,          /* np.rot90(t, 1): counter-clockwise, (h, w) -> (w, h) */
+    MTM_XF_ROT180 = 2,         /* np.rot90(t, 2) */
+    MTM_XF_ROT270 = 3,         /* np.rot90(t, 3) */
+    MTM_XF_FLIPLR = 4,         /* np.fliplr(t) */
+    MTM_XF_FLIPUD = 5,         /* np.flipud(t) */
+    MTM_XF_TRANSPOSE = 6,      /* t.swapaxes(0, 1) */
+    MTM_XF_ANTITRANSPOSE = 7   /* np.rot90(t, 2).swapaxes(0, 1) */
+} mtm_transform;
+#define MTM_MAX_DOWNSCALE 16
+
 typedef enum mtm_option {
     MTM_OPT_PATH = 0,          /* mtm_path */
     MTM_OPT_TIME_NCC = 1       /* 1: bracket the numerator kernels with CUDA events (roofline timing) */
@@ -105,6 +120,28 @@ int mtm_set_templates(mtm_ctx* ctx, int n, const void* const* pixels,
  * dtype of pixels[i]; uint8 masks are binary (non-zero = use), float32 masks are weights (OpenCV). */
 int mtm_set_templates_masked(mtm_ctx* ctx, int n, const void* const* pixels, const void* const* masks,
                              const int32_t* h, const int32_t* w, int C, int dtype);
+
+/* ---- on-device augmentation and search-region / pyramid helpers ----------------------------
+ * The reference leaves these to user code in its tutorials; here they run on the device so that only the base
+ * pixels cross PCIe once.
+ *
+ * mtm_set_templates_transformed: the template list becomes, for every base template b (in order) and every
+ * ops[k] (in order), transform ops[k] of the `downscale`-times reduced base: index b*n_ops + k.  The reduction is
+ * cv2.resize(t[:h/f*f, :w/f*f], (w/f, h/f), interpolation=cv2.INTER_AREA) (Tutorial3-SpeedingUp.ipynb cells
+ * 17-19; bit-identical for integer pixels), downscale == 1 keeps the pixels.  MTM_U8 and MTM_F32 templates. */
+int mtm_set_templates_transformed(mtm_ctx* ctx, int n, const void* const* pixels, const int32_t* h, const int32_t* w,
+                                  int C, int dtype, int n_ops, const int32_t* ops, int downscale);
+
+/* mtm_set_image_scaled: uploads the full-resolution image (kept resident for mtm_set_image_roi) and searches its
+ * `downscale`-times reduced copy: cv2.resize(image[:H/f*f, :W/f*f], (W/f, H/f), interpolation=cv2.INTER_AREA),
+ * Tutorial3-SpeedingUp.ipynb cell 17.  downscale in [1, MTM_MAX_DOWNSCALE]. */
+int mtm_set_image_scaled(mtm_ctx* ctx, const void* pixels, int H, int W, int C, int dtype, int64_t row_stride_bytes,
+                         int downscale);
+
+/* mtm_set_image_roi: the searchBox crop of MTM.findMatches (MTM/__init__.py:140-144) taken from the resident
+ * full-resolution image of the last mtm_set_image_scaled: no host copy, no upload.  Hit coordinates of the
+ * following searches are relative to (x, y), as with a host-side crop. */
+int mtm_set_image_roi(mtm_ctx* ctx, int x, int y, int w, int h);
 
 /* ---- the hot path ---------------------------------------------------------
  * mtm_score_map: cv2.matchTemplate(image, template, method) at

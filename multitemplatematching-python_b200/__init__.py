@@ -5,6 +5,7 @@ reference's signatures (MTM/__init__.py:56,95,247; MTM/NMS.py:20) and run on
 hand-written sm_100a kernels behind the C ABI of ``libmtm_b200.so``.
 """
 from .api import NMS, computeScoreMap, findMatches, matchTemplates, matchTemplatesBatch
+from .augment import TRANSFORMS, expandTemplates, matchTemplatesAugmented, matchTemplatesPyramid
 from .draw import drawBoxesOnGray, drawBoxesOnRGB
 from ._native import Context, default_context
 

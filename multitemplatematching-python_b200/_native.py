@@ -14,6 +14,9 @@ MTM_OK, MTM_ERR_INVALID, MTM_ERR_CUDA, MTM_ERR_CAPACITY, MTM_ERR_UNSUPPORTED = 0
 MTM_U8, MTM_F32, MTM_U16 = 0, 1, 2
 PATH_AUTO, PATH_DIRECT, PATH_TENSOR = 0, 1, 2
 OPT_PATH, OPT_TIME_NCC = 0, 1
+# mtm_transform (include/mtm_b200.h)
+XF_IDENTITY, XF_ROT90, XF_ROT180, XF_ROT270, XF_FLIPLR, XF_FLIPUD, XF_TRANSPOSE, XF_ANTITRANSPOSE = range(8)
+MAX_DOWNSCALE = 16
 
 HIT_DTYPE = np.dtype([("tmpl", "<i4"), ("x", "<i4"), ("y", "<i4"), ("w", "<i4"), ("h", "<i4"), ("score", "<f4")])
 assert HIT_DTYPE.itemsize == 24
@@ -45,6 +48,12 @@ _SIGNATURES = {
     "mtm_set_templates_masked": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(_P), ctypes.POINTER(_P),
                                                 ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
                                                 ctypes.c_int, ctypes.c_int]),
+    "mtm_set_templates_transformed": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(_P), ctypes.POINTER(ctypes.c_int32),
+                                                     ctypes.POINTER(ctypes.c_int32), ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                     ctypes.POINTER(ctypes.c_int32), ctypes.c_int]),
+    "mtm_set_image_scaled": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64,
+                                            ctypes.c_int]),
+    "mtm_set_image_roi": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "mtm_score_map": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, _P, ctypes.c_int64]),
     "mtm_find_matches": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int64, ctypes.c_double, _P, ctypes.c_int,
                                         ctypes.POINTER(ctypes.c_int)]),
@@ -114,6 +123,9 @@ class Context:
         self.device = int(device)
         self.lock = threading.RLock()
         self._keep = None
+        self._hit_buf = None
+
+    _hit_buf = None                       # reusable host buffer of the hit-list calls (guarded by `lock`)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -211,22 +223,54 @@ class Context:
         ws = (ctypes.c_int32 * n)(*[a.shape[1] for a in arrs])
         self._check(self._lib.mtm_set_templates_masked(self._h, n, tp, mp, hs, ws, C, code))
 
+    # -- on-device augmentation / pyramid helpers ------------------
+    def set_templates_transformed(self, templates, ops, downscale=1):
+        """Template list := [transform op of the downscaled base for base in templates for op in ops]."""
+        arrs = [np.ascontiguousarray(t) for t in templates]
+        n = len(arrs)
+        if n == 0:
+            raise ValueError("empty template list")
+        C = 1 if arrs[0].ndim == 2 else arrs[0].shape[2]
+        code = _dtype_code(arrs[0])
+        for a in arrs:
+            if (1 if a.ndim == 2 else a.shape[2]) != C or _dtype_code(a) != code:
+                raise ValueError("templates must share dtype and channel count")
+        ops = [int(o) for o in ops]
+        ptrs = (_P * n)(*[a.ctypes.data for a in arrs])
+        hs = (ctypes.c_int32 * n)(*[a.shape[0] for a in arrs])
+        ws = (ctypes.c_int32 * n)(*[a.shape[1] for a in arrs])
+        op_arr = (ctypes.c_int32 * len(ops))(*ops)
+        self._check(self._lib.mtm_set_templates_transformed(self._h, n, ptrs, hs, ws, C, code, len(ops), op_arr, int(downscale)))
+
+    def set_image_scaled(self, image, downscale):
+        """Upload the full-resolution image (kept resident) and search its INTER_AREA reduction."""
+        arr, H, W, C, stride = self._image_view(image)
+        self._check(self._lib.mtm_set_image_scaled(self._h, _P(arr.ctypes.data), H, W, C, _dtype_code(arr), stride, int(downscale)))
+
+    def set_image_roi(self, x, y, w, h):
+        """Current image := region of the resident full-resolution image (device-side searchBox)."""
+        self._check(self._lib.mtm_set_image_roi(self._h, int(x), int(y), int(w), int(h)))
+
     # -- hot path ---------------------------------------------------------------
     def score_map(self, tmpl, method, map_shape):
         out = np.empty(map_shape, np.float32)
         self._check(self._lib.mtm_score_map(self._h, int(tmpl), int(method), _P(out.ctypes.data), out.size))
         return out
 
-    def _hits_call(self, fn, args, capacity=4096):
+    def _hits_call(self, fn, args):
+        """Calls a hit-list entry point with the context's reusable output buffer (grown on MTM_ERR_CAPACITY);
+        returns a private copy of the hits."""
         while True:
-            buf = np.empty(capacity, HIT_DTYPE)
+            buf = self._hit_buf
+            if buf is None:
+                buf = self._hit_buf = np.empty(4096, HIT_DTYPE)
             n = ctypes.c_int(0)
-            rc = fn(self._h, *args, _P(buf.ctypes.data), capacity, ctypes.byref(n))
+            rc = fn(self._h, *args, _P(buf.ctypes.data), buf.shape[0], ctypes.byref(n))
             if rc == MTM_ERR_CAPACITY:
-                capacity = max(2 * capacity, int(n.value))
+                self._hit_buf = np.empty(max(2 * buf.shape[0], int(n.value)), HIT_DTYPE)
                 continue
             self._check(rc)
-            return buf[: n.value]
+            return buf[: n.value].copy()
 
     def find_matches(self, method, n_object, score_threshold):
         return self._hits_call(self._lib.mtm_find_matches, (int(method), int(n_object), float(score_threshold)))

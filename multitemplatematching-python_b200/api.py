@@ -16,6 +16,7 @@ __all__ = ["computeScoreMap", "findMatches", "matchTemplates", "matchTemplatesBa
 
 TM_SQDIFF, TM_SQDIFF_NORMED, TM_CCORR, TM_CCORR_NORMED, TM_CCOEFF, TM_CCOEFF_NORMED = range(6)
 _INF = float("inf")
+_U8 = np.dtype(np.uint8)
 
 
 def _cv_error(msg):
@@ -102,23 +103,40 @@ def _validate_search(listTemplates, image, N_object, searchBox):
     if searchBox is not None:
         xOffset, yOffset, searchWidth, searchHeight = searchBox
         image = image[yOffset:yOffset + searchHeight, xOffset:xOffset + searchWidth]
+    ishape = image.shape
     for index, tempTuple in enumerate(listTemplates):
         if not isinstance(tempTuple, tuple) or len(tempTuple) < 2:
             raise ValueError("listTemplates should be a list of tuples as ('name','array') or ('name', 'array', 'mask')")
-        tempName, tempImage = tempTuple[0], tempTuple[1]
-        if tempImage.shape[0] == 0:
-            raise ValueError(f"Template '{tempName}' has a height of 0.")
-        if tempImage.shape[1] == 0:
-            raise ValueError(f"Template '{tempName}' has a width of 0.")
-        if not all(t <= i for t, i in zip(tempImage.shape, image.shape)):
+        tshape = tempTuple[1].shape
+        if tshape[0] == 0:
+            raise ValueError(f"Template '{tempTuple[0]}' has a height of 0.")
+        if tshape[1] == 0:
+            raise ValueError(f"Template '{tempTuple[0]}' has a width of 0.")
+        # `all(t <= i for t, i in zip(template.shape, image.shape))` of the reference, unrolled for the first two axes
+        if tshape[0] > ishape[0] or tshape[1] > ishape[1] or \
+                (len(tshape) > 2 and len(ishape) > 2 and not all(t <= i for t, i in zip(tshape[2:], ishape[2:]))):
             fitIn = "searchBox" if (searchBox is not None) else "image"
-            raise ValueError("Template '{}' at index {} in the list of templates is larger than {}.".format(tempName, index, fitIn))
+            raise ValueError("Template '{}' at index {} in the list of templates is larger than {}.".format(tempTuple[0], index, fitIn))
     return image, xOffset, yOffset
 
 
 def _prepare(listTemplates, image, method):
     """Per-template mask / dtype policy of _multi_compute + computeScoreMap
     (MTM/__init__.py:207-222, 67-88) applied to the whole list."""
+    if image.dtype == _U8:
+        # the common case in one pass: uint8 image, uint8 templates, no mask entries -> nothing is cast or dropped
+        names, arrays = [], []
+        ndim, chans = image.ndim, image.shape[2:]
+        for tempTuple in listTemplates:
+            template = tempTuple[1]
+            if len(tempTuple) != 2 or template.dtype != _U8:
+                break
+            if template.ndim != ndim or template.shape[2:] != chans:
+                raise _cv_error("matchTemplate: image and template must have the same number of dimensions/channels")
+            names.append(tempTuple[0])
+            arrays.append(template)
+        else:
+            return names, arrays, image, [None] * len(arrays)
     names, arrays, masks = [], [], []
     img = image
     img_f32 = None                     # the image is cast at most once (the reference casts it once per template)
@@ -175,8 +193,13 @@ def _native_n_object(N_object):
 
 
 def _to_hits(raw, names, xOffset, yOffset):
-    return [(names[int(r["tmpl"])], (int(r["x"]) + xOffset, int(r["y"]) + yOffset, int(r["w"]), int(r["h"])), r["score"])
-            for r in raw]
+    """Raw device records -> the reference's hit tuples (label, (x, y, w, h), np.float32 score), MTM/__init__.py:238-241."""
+    if len(raw) == 0:
+        return []
+    # column-wise conversion: per-record field access on a structured array costs microseconds per hit
+    return [(names[t], (x + xOffset, y + yOffset, w, h), s)
+            for t, x, y, w, h, s in zip(raw["tmpl"].tolist(), raw["x"].tolist(), raw["y"].tolist(), raw["w"].tolist(),
+                                        raw["h"].tolist(), list(raw["score"]))]
 
 
 def findMatches(listTemplates, image, method=TM_CCOEFF_NORMED, N_object=_INF, score_threshold=0.5,

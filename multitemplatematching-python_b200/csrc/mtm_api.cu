@@ -176,6 +176,7 @@ int mtm_destroy(mtm_ctx* ctx)
     cudaFree(ctx->img.pixf2); cudaFree(ctx->d_raw_t); cudaFree(ctx->d_raw_m); cudaFree(ctx->d_maps2);
     cudaFree(ctx->img.pixf); cudaFree(ctx->img.satf_s); cudaFree(ctx->img.satf_q); cudaFree(ctx->d_tmpl_centred);
     cudaFree(ctx->d_raw16); cudaFree(ctx->img.pix_lo); cudaFree(ctx->d_tmpl8); cudaFree(ctx->d_pix8); cudaFree(ctx->d_acc);
+    cudaFree(ctx->d_full); cudaFree(ctx->d_small); cudaFree(ctx->d_xform);
     cudaFree(ctx->d_slabs); cudaFree(ctx->d_wS); cudaFree(ctx->d_wR); cudaFree(ctx->d_sizes);
     for (int k = 0; k < MTM_MAX_INFLIGHT; ++k) { cudaFree(ctx->d_slot[k]); cudaFreeHost(ctx->h_slot[k]); if (ctx->ev_slot[k]) cudaEventDestroy(ctx->ev_slot[k]); }
     cudaFreeHost(ctx->h_tmpl_stage); cudaFreeHost(ctx->h_stage); cudaFreeHost(ctx->h_geom); cudaFreeHost(ctx->h_mirror);
@@ -585,6 +586,54 @@ static int compute_maps(mtm_ctx* ctx, int method, int tmpl)
     return MTM_OK;
 }
 
+// Second half of every plain template upload: ctx->h_meta holds sizes / pitches / arena offsets of the n templates and
+// the packed pixels are (queued to be) in ctx->d_tmpl.  Uploads the metadata and the (h, w) order, computes the
+// template statistics and plans the tensor-core launches.
+static int finish_templates(mtm_ctx* ctx, int n, int C, int dtype, size_t total)
+{
+    MTM_TRY(mtm_reserve(ctx, ctx->d_meta, ctx->meta_cap, (size_t)n));
+    MTM_TRY(mtm_reserve(ctx, ctx->d_order, ctx->order_cap, (size_t)n));
+    MTM_TRY(mtm_reserve(ctx, ctx->d_nontrivial, ctx->per_tmpl_cap, (size_t)n));
+    MTM_TRY(mtm_reserve(ctx, ctx->d_best, ctx->best_cap, (size_t)n));
+    MTM_CUDA(ctx, cudaMemcpyAsync(ctx->d_meta, ctx->h_meta.data(), (size_t)n * sizeof(TmplMeta), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h_order.resize(n);
+    for (int t = 0; t < n; ++t) ctx->h_order[t] = t;
+    std::stable_sort(ctx->h_order.begin(), ctx->h_order.end(), [&](int a, int b) {
+        const TmplMeta &x = ctx->h_meta[a], &y = ctx->h_meta[b];
+        return x.h != y.h ? x.h < y.h : x.w < y.w;
+    });
+    MTM_CUDA(ctx, cudaMemcpyAsync(ctx->d_order, ctx->h_order.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    // h_meta / h_order are pageable: the copies above are staged synchronously by the runtime.
+    ctx->ctr.h2d_bytes += (int64_t)n * (sizeof(TmplMeta) + sizeof(int32_t));
+    ctx->n_tmpl = n; ctx->tmpl_C = C; ctx->tmpl_dtype = dtype;
+    ctx->geometry_valid = false;
+    ctx->masked = false;
+    if (dtype == MTM_F32) {
+        MTM_TRY(mtm_reserve(ctx, ctx->d_tmpl_centred, ctx->tmplc_cap, total + 64));
+        MTM_TRY(launch_tmpl_stats_f32(ctx));
+    } else {
+        MTM_TRY(launch_tmpl_stats(ctx));
+    }
+    MTM_TRY(plan_tensor_path(ctx));
+    ctx->tmpl_hash_valid = true;
+    return MTM_OK;
+}
+
+// Content hash of a template upload (pixels, sizes, channel count, dtype and, for transformed uploads, the
+// transform list): an identical re-submission keeps everything derived from it resident.
+struct TmplHasher {
+    uint64_t h;
+    explicit TmplHasher(uint64_t seed) : h(0x9E3779B97F4A7C15ull ^ seed) {}
+    void mix(uint64_t v) { h ^= v; h *= 0x100000001B3ull; h ^= h >> 29; }
+    void bytes(const void* p, size_t n) {
+        const uint8_t* b = static_cast<const uint8_t*>(p);
+        size_t k = 0;
+        for (; k + 8 <= n; k += 8) { uint64_t v; memcpy(&v, b + k, 8); mix(v); }
+        uint64_t tail = 0;
+        if (k < n) { memcpy(&tail, b + k, n - k); mix(tail ^ ((uint64_t)(n - k) << 56)); }
+    }
+};
+
 // Downloads header + hits of a block into h_stage.  Returns the raw count in *n_raw.
 static int download_block(mtm_ctx* ctx, const uint8_t* d_block, int* n_raw, int* n_valid, int* declined = nullptr)
 {
@@ -665,23 +714,17 @@ int mtm_set_templates(mtm_ctx* ctx, int n, const void* const* pixels, const int3
     // Same template set as last time (content hash)?  Then everything derived from it -- packed pixels,
     // statistics, Toeplitz slabs, launch plan -- is still resident: nothing to upload or recompute.
     {
-        uint64_t hsh = 0x9E3779B97F4A7C15ull ^ ((uint64_t)n << 32) ^ ((uint64_t)C << 8) ^ (uint64_t)dtype;
-        auto mix = [&](uint64_t v) { hsh ^= v; hsh *= 0x100000001B3ull; hsh ^= hsh >> 29; };
+        TmplHasher hasher(((uint64_t)n << 32) ^ ((uint64_t)C << 8) ^ (uint64_t)dtype);
         for (int t = 0; t < n; ++t) {
             if (!pixels[t] || h[t] <= 0 || w[t] <= 0)
                 return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_templates: template %d is empty", t);
-            mix(((uint64_t)(uint32_t)h[t] << 32) | (uint32_t)w[t]);
-            const size_t bytes = (size_t)h[t] * w[t] * C * in_esz;
-            const uint8_t* b = static_cast<const uint8_t*>(pixels[t]);
-            size_t k = 0;
-            for (; k + 8 <= bytes; k += 8) { uint64_t v; memcpy(&v, b + k, 8); mix(v); }
-            uint64_t tail = 0;
-            if (k < bytes) { memcpy(&tail, b + k, bytes - k); mix(tail ^ ((uint64_t)(bytes - k) << 56)); }
+            hasher.mix(((uint64_t)(uint32_t)h[t] << 32) | (uint32_t)w[t]);
+            hasher.bytes(pixels[t], (size_t)h[t] * w[t] * C * in_esz);
         }
         const int dev_dtype = u16 ? MTM_F32 : dtype;
-        if (ctx->n_tmpl == n && ctx->tmpl_hash == hsh && ctx->tmpl_C == C && ctx->tmpl_dtype == dev_dtype && ctx->tmpl_u16 == u16 &&
+        if (ctx->n_tmpl == n && ctx->tmpl_hash == hasher.h && ctx->tmpl_C == C && ctx->tmpl_dtype == dev_dtype && ctx->tmpl_u16 == u16 &&
             ctx->tmpl_hash_valid) return MTM_OK;
-        ctx->tmpl_hash = hsh;
+        ctx->tmpl_hash = hasher.h;
         ctx->tmpl_hash_valid = false;           // set again once the upload below has been queued
     }
     // the previous upload may still be reading the pinned staging buffers
@@ -744,33 +787,9 @@ int mtm_set_templates(mtm_ctx* ctx, int n, const void* const* pixels, const int3
     ctx->tmpl_u16 = u16;
     if (u16) dtype = MTM_F32;
     MTM_TRY(mtm_reserve(ctx, ctx->d_tmpl, ctx->tmpl_cap, total + 64));
-    MTM_TRY(mtm_reserve(ctx, ctx->d_meta, ctx->meta_cap, (size_t)n));
-    MTM_TRY(mtm_reserve(ctx, ctx->d_order, ctx->order_cap, (size_t)n));
-    MTM_TRY(mtm_reserve(ctx, ctx->d_nontrivial, ctx->per_tmpl_cap, (size_t)n));
-    MTM_TRY(mtm_reserve(ctx, ctx->d_best, ctx->best_cap, (size_t)n));
     MTM_CUDA(ctx, cudaMemcpyAsync(ctx->d_tmpl, ctx->h_tmpl_stage, total, cudaMemcpyHostToDevice, ctx->stream));
-    MTM_CUDA(ctx, cudaMemcpyAsync(ctx->d_meta, ctx->h_meta.data(), (size_t)n * sizeof(TmplMeta), cudaMemcpyHostToDevice, ctx->stream));
-    ctx->h_order.resize(n);
-    for (int t = 0; t < n; ++t) ctx->h_order[t] = t;
-    std::stable_sort(ctx->h_order.begin(), ctx->h_order.end(), [&](int a, int b) {
-        const TmplMeta &x = ctx->h_meta[a], &y = ctx->h_meta[b];
-        return x.h != y.h ? x.h < y.h : x.w < y.w;
-    });
-    MTM_CUDA(ctx, cudaMemcpyAsync(ctx->d_order, ctx->h_order.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-    // h_meta / h_order are pageable: the copies above are staged synchronously by the runtime.
-    ctx->ctr.h2d_bytes += (int64_t)total + (int64_t)n * (sizeof(TmplMeta) + sizeof(int32_t));
-    ctx->n_tmpl = n; ctx->tmpl_C = C; ctx->tmpl_dtype = dtype;
-    ctx->geometry_valid = false;
-    ctx->masked = false;
-    if (dtype == MTM_F32) {
-        MTM_TRY(mtm_reserve(ctx, ctx->d_tmpl_centred, ctx->tmplc_cap, total + 64));
-        MTM_TRY(launch_tmpl_stats_f32(ctx));
-    } else {
-        MTM_TRY(launch_tmpl_stats(ctx));
-    }
-    MTM_TRY(plan_tensor_path(ctx));
-    ctx->tmpl_hash_valid = true;
-    return MTM_OK;
+    ctx->ctr.h2d_bytes += (int64_t)total;
+    return finish_templates(ctx, n, C, dtype, total);
 }
 
 int mtm_set_templates_masked(mtm_ctx* ctx, int n, const void* const* pixels, const void* const* masks,
@@ -829,6 +848,125 @@ int mtm_set_templates_masked(mtm_ctx* ctx, int n, const void* const* pixels, con
     ctx->tc_groups.clear(); ctx->tc_ready = false;
     MTM_TRY(launch_masked_prep(ctx, ctx->d_raw_t, ctx->d_raw_m, dtype == MTM_F32));
     return MTM_OK;
+}
+
+int mtm_set_templates_transformed(mtm_ctx* ctx, int n, const void* const* pixels, const int32_t* h, const int32_t* w,
+                                  int C, int dtype, int n_ops, const int32_t* ops, int downscale)
+{
+    MTM_ENTER(ctx);
+    if (n <= 0 || !pixels || !h || !w) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_templates_transformed: empty template list");
+    if (n_ops <= 0 || !ops) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_templates_transformed: empty transform list");
+    if (C < 1 || C > MTM_MAX_CH) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_templates_transformed: %d channels (1..4 supported)", C);
+    if (dtype != MTM_U8 && dtype != MTM_F32)
+        return mtm_fail(ctx, MTM_ERR_UNSUPPORTED, "mtm_set_templates_transformed: dtype %d (uint8 and float32 templates only)", dtype);
+    if (downscale < 1 || downscale > MTM_MAX_DOWNSCALE)
+        return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_templates_transformed: downscale %d outside [1, %d]", downscale, MTM_MAX_DOWNSCALE);
+    for (int k = 0; k < n_ops; ++k)
+        if (ops[k] < MTM_XF_IDENTITY || ops[k] > MTM_XF_ANTITRANSPOSE)
+            return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_templates_transformed: unknown transform %d", ops[k]);
+    const int esz = dtype == MTM_F32 ? 4 : 1;
+    const int f = downscale;
+    const int n_out = n * n_ops;
+    TmplHasher hasher(((uint64_t)n_out << 32) ^ ((uint64_t)C << 8) ^ (uint64_t)dtype ^ 0x7466000000000000ull ^ ((uint64_t)f << 16));
+    for (int k = 0; k < n_ops; ++k) hasher.mix((uint64_t)ops[k] + 1);
+    size_t raw_total = 0;
+    for (int t = 0; t < n; ++t) {
+        if (!pixels[t] || h[t] <= 0 || w[t] <= 0)
+            return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_templates_transformed: template %d is empty", t);
+        if (h[t] / f < 1 || w[t] / f < 1)
+            return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_templates_transformed: template %d (%d x %d) vanishes at downscale %d", t, h[t], w[t], f);
+        hasher.mix(((uint64_t)(uint32_t)h[t] << 32) | (uint32_t)w[t]);
+        hasher.bytes(pixels[t], (size_t)h[t] * w[t] * C * esz);
+        raw_total += ((size_t)h[t] * w[t] * C * esz + 15) / 16 * 16;
+    }
+    if (ctx->n_tmpl == n_out && ctx->tmpl_hash == hasher.h && ctx->tmpl_C == C && ctx->tmpl_dtype == dtype && !ctx->tmpl_u16 &&
+        !ctx->masked && ctx->tmpl_hash_valid) return MTM_OK;
+    ctx->tmpl_hash = hasher.h;
+    ctx->tmpl_hash_valid = false;
+    // the previous upload may still be reading the pinned staging buffer
+    MTM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    MTM_TRY(reserve_pinned(ctx, ctx->h_tmpl_stage, ctx->tmpl_stage_cap, raw_total + 64));
+    MTM_TRY(reserve_pinned(ctx, ctx->h_geom, ctx->geom_cap, (size_t)n_out));
+    ctx->h_meta.assign(n_out, TmplMeta{});
+    std::vector<XformDesc> descs((size_t)n_out);
+    size_t src_off = 0, total = 0;
+    int64_t max_pixels = 0;
+    for (int t = 0; t < n; ++t) {
+        const size_t bytes = (size_t)h[t] * w[t] * C * esz;
+        memcpy(ctx->h_tmpl_stage + src_off, pixels[t], bytes);
+        const int dh = h[t] / f, dw = w[t] / f;
+        for (int k = 0; k < n_ops; ++k) {
+            const int op = ops[k];
+            const bool swap = (op == MTM_XF_ROT90 || op == MTM_XF_ROT270 || op == MTM_XF_TRANSPOSE || op == MTM_XF_ANTITRANSPOSE);
+            TmplMeta& m = ctx->h_meta[(size_t)t * n_ops + k];
+            m.h = swap ? dw : dh; m.w = swap ? dh : dw;
+            m.wp = (m.w * C * esz + 3) / 4 * 4;
+            m.pix_off = (int64_t)total;
+            total += ((size_t)m.wp * m.h + 15) / 16 * 16;
+            XformDesc& d = descs[(size_t)t * n_ops + k];
+            d.src_off = (int64_t)src_off; d.src_pitch = (int64_t)w[t] * C * esz;
+            d.dst_off = m.pix_off; d.dst_pitch = m.wp;
+            d.dh = dh; d.dw = dw; d.oh = m.h; d.ow = m.w; d.op = op; d.pad = 0;
+            max_pixels = std::max(max_pixels, (int64_t)m.h * m.w);
+        }
+        src_off += (bytes + 15) / 16 * 16;
+    }
+    MTM_TRY(mtm_reserve(ctx, ctx->d_raw_t, ctx->raw_t_cap, raw_total + 64));
+    MTM_TRY(mtm_reserve(ctx, ctx->d_tmpl, ctx->tmpl_cap, total + 64));
+    MTM_TRY(mtm_reserve(ctx, ctx->d_xform, ctx->xform_cap, (size_t)n_out));
+    MTM_CUDA(ctx, cudaMemcpyAsync(ctx->d_raw_t, ctx->h_tmpl_stage, raw_total, cudaMemcpyHostToDevice, ctx->stream));
+    MTM_CUDA(ctx, cudaMemcpyAsync(ctx->d_xform, descs.data(), (size_t)n_out * sizeof(XformDesc), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->ctr.h2d_bytes += (int64_t)raw_total + (int64_t)n_out * (int64_t)sizeof(XformDesc);
+    MTM_CUDA(ctx, cudaMemsetAsync(ctx->d_tmpl, 0, total, ctx->stream));        // row padding must read as zero
+    MTM_TRY(launch_transform(ctx, ctx->d_raw_t, ctx->d_tmpl, ctx->d_xform, n_out, max_pixels, C, dtype, f));
+    ctx->tmpl_u16 = false;
+    return finish_templates(ctx, n_out, C, dtype, total);
+}
+
+int mtm_set_image_scaled(mtm_ctx* ctx, const void* pixels, int H, int W, int C, int dtype, int64_t row_stride_bytes,
+                         int downscale)
+{
+    MTM_ENTER(ctx);
+    if (!pixels || H <= 0 || W <= 0) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_image_scaled: empty image (%d x %d)", H, W);
+    if (C < 1 || C > MTM_MAX_CH) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_image_scaled: %d channels (1..4 supported)", C);
+    if (dtype != MTM_U8 && dtype != MTM_F32 && dtype != MTM_U16) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_image_scaled: unknown dtype %d", dtype);
+    if (downscale < 1 || downscale > MTM_MAX_DOWNSCALE)
+        return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_image_scaled: downscale %d outside [1, %d]", downscale, MTM_MAX_DOWNSCALE);
+    const int f = downscale;
+    if (H / f < 1 || W / f < 1) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_image_scaled: image %d x %d vanishes at downscale %d", H, W, f);
+    const int64_t esz = dtype == MTM_F32 ? 4 : (dtype == MTM_U16 ? 2 : 1);
+    const int64_t row = (int64_t)W * C * esz;
+    if (row_stride_bytes < row) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_image_scaled: row stride %lld < %lld", (long long)row_stride_bytes, (long long)row);
+    ctx->full_dtype = -1;                                        // invalid until the upload below is queued
+    MTM_TRY(mtm_reserve(ctx, ctx->d_full, ctx->full_cap, (size_t)(row * H + 64)));
+    MTM_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_full, (size_t)row, pixels, (size_t)row_stride_bytes, (size_t)row, (size_t)H,
+                                    cudaMemcpyHostToDevice, ctx->stream));
+    ctx->ctr.h2d_bytes += row * H;
+    ctx->full_H = H; ctx->full_W = W; ctx->full_C = C; ctx->full_dtype = dtype;
+    if (f == 1) return set_image_impl(ctx, ctx->d_full, H, W, C, dtype, row, true);
+    const int sh = H / f, sw = W / f;
+    const int64_t srow = (int64_t)sw * C * esz;
+    MTM_TRY(mtm_reserve(ctx, ctx->d_small, ctx->small_cap, (size_t)(srow * sh + 64)));
+    MTM_TRY(mtm_reserve(ctx, ctx->d_xform, ctx->xform_cap, (size_t)1));
+    XformDesc d{};
+    d.src_off = 0; d.src_pitch = row; d.dst_off = 0; d.dst_pitch = srow;
+    d.dh = sh; d.dw = sw; d.oh = sh; d.ow = sw; d.op = MTM_XF_IDENTITY;
+    MTM_CUDA(ctx, cudaMemcpyAsync(ctx->d_xform, &d, sizeof d, cudaMemcpyHostToDevice, ctx->stream));   // pageable: staged before returning
+    MTM_TRY(launch_transform(ctx, ctx->d_full, ctx->d_small, ctx->d_xform, 1, (int64_t)sh * sw, C, dtype, f));
+    return set_image_impl(ctx, ctx->d_small, sh, sw, C, dtype, srow, true);
+}
+
+int mtm_set_image_roi(mtm_ctx* ctx, int x, int y, int w, int h)
+{
+    MTM_ENTER(ctx);
+    if (ctx->full_dtype < 0) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_image_roi: no full-resolution image resident (call mtm_set_image_scaled first)");
+    if (x < 0 || y < 0 || w <= 0 || h <= 0 || (int64_t)x + w > ctx->full_W || (int64_t)y + h > ctx->full_H)
+        return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_image_roi: region (%d, %d, %d, %d) outside the %d x %d image", x, y, w, h,
+                        ctx->full_W, ctx->full_H);
+    const int64_t esz = ctx->full_dtype == MTM_F32 ? 4 : (ctx->full_dtype == MTM_U16 ? 2 : 1);
+    const int64_t row = (int64_t)ctx->full_W * ctx->full_C * esz;
+    const uint8_t* origin = ctx->d_full + (int64_t)y * row + (int64_t)x * ctx->full_C * esz;
+    return set_image_impl(ctx, origin, h, w, ctx->full_C, ctx->full_dtype, row, true);
 }
 
 int mtm_score_map(mtm_ctx* ctx, int tmpl, int method, float* out_host, int64_t out_elems)

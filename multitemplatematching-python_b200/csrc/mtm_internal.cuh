@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <algorithm>
 #include <string>
 #include <vector>
 #include "../../include/mtm_b200.h"
@@ -49,6 +50,17 @@ struct TmplMeta {
 struct TmplPix8 {
     int64_t off;
     int32_t wp, pad;
+};
+
+// One output of transform_kernel (transform.cu): `op` of the f-times area-reduced source array.
+struct XformDesc {
+    int64_t src_off;      // byte offset of the source array in the source buffer
+    int64_t src_pitch;    // bytes between source rows
+    int64_t dst_off;      // byte offset of the output in the destination buffer
+    int64_t dst_pitch;    // bytes between output rows
+    int32_t dh, dw;       // size of the reduced source (source size / f, rounded down)
+    int32_t oh, ow;       // output size: (dh, dw), swapped by the transposing symmetries
+    int32_t op, pad;      // mtm_transform
 };
 
 // One distinct template size: where its window-moment maps live (window_moments_kernel, batched).
@@ -103,6 +115,12 @@ struct mtm_ctx {
     size_t img_cap = 0, sat_s_cap = 0, sat_q_cap = 0, sat_q32_cap = 0, scratch_cap = 0, imgf_cap = 0, satf_s_cap = 0, satf_q_cap = 0;
     uint32_t* scratch = nullptr;         // row-prefix scratch for the SAT build
     int img_dtype = -1;
+
+    // full-resolution image of mtm_set_image_scaled (source of the reduced image and of mtm_set_image_roi)
+    uint8_t* d_full = nullptr; size_t full_cap = 0;
+    int full_H = 0, full_W = 0, full_C = 0, full_dtype = -1;
+    uint8_t* d_small = nullptr; size_t small_cap = 0;          // its reduced copy (contiguous), handed to set_image
+    XformDesc* d_xform = nullptr; size_t xform_cap = 0;        // descriptors of the transform launches
 
     // templates
     int n_tmpl = 0;
@@ -218,6 +236,9 @@ int launch_ncc_tc(mtm_ctx* ctx, const TcGroup& g, int method);
 int launch_ncc_tc_accum(mtm_ctx* ctx, const TcGroup& g, int img_plane, int tmpl_plane, double weight, bool first);
 int launch_u16_split_image(mtm_ctx* ctx, const uint16_t* src, int64_t src_stride_bytes);
 int launch_cc16_epilogue(mtm_ctx* ctx, int method, int tmpl);
+// augmentation / area downscale (transform.cu)
+int launch_transform(mtm_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, const XformDesc* d_descs, int n_out,
+                     int64_t max_pixels, int C, int dtype, int factor);
 // raw (unsorted) peaks of every template -> block A
 int launch_peaks(mtm_ctx* ctx, int method, int64_t n_object, float thr32, double thr64, bool allow_candidates = true);
 // in-place sort of block A (mode 0: findMatches order, mode 1: NMSBoxes order)

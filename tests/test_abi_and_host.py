@@ -107,3 +107,31 @@ def test_dtype_routing_of_the_host_layer(mtm):
         api._prepare([("a", t8.astype(np.float64))], img8, 5)
     with pytest.raises(TypeError):
         _native._dtype_code(np.zeros(3, np.int32))
+
+
+def test_augmented_and_pyramid_validate_before_device_work(mtm):
+    """SURVEY §8 f3 front ends: the reference's checks (on the EXPANDED list) and the extra ones, without a GPU."""
+    img = np.zeros((40, 100), np.uint8)
+    wide = np.zeros((10, 60), np.uint8)                      # fits, but its 90-degree rotations (60 x 10) do not
+    with pytest.raises(ValueError, match="'w_rot90' at index 1 in the list of templates is larger than image"):
+        mtm.matchTemplatesAugmented([("w", wide)], img)
+    with pytest.raises(ValueError, match="unknown transform"):
+        mtm.matchTemplatesAugmented([("w", wide)], img, transforms=("identity", "rot45"))
+    with pytest.raises(ValueError, match="Maximal overlap"):
+        mtm.matchTemplatesAugmented([("w", wide)], img, transforms=("identity",), maxOverlap=2)
+    with pytest.raises(NotImplementedError, match="masks"):
+        mtm.matchTemplatesAugmented([("w", wide, np.ones_like(wide))], img, transforms=("identity", "fliplr"))
+    with pytest.raises(NotImplementedError, match="all be uint8 or all be float32"):
+        mtm.matchTemplatesAugmented([("w", wide.astype(np.uint16))], img, transforms=("identity", "fliplr"))
+    with pytest.raises(ValueError, match="64-bit images not supported"):
+        mtm.matchTemplatesPyramid([("w", wide.astype(np.float64))], img, downscale=2)
+    with pytest.raises(ValueError, match="downscale must be an integer"):
+        mtm.matchTemplatesPyramid([("w", wide)], img, downscale=17)
+    with pytest.raises(ValueError, match="vanishes at downscale 16"):
+        mtm.matchTemplatesPyramid([("w", wide)], img, downscale=16)
+    with pytest.raises(ValueError, match="TM_SQDIFF is not supported"):
+        mtm.matchTemplatesPyramid([("w", wide)], img, downscale=2, method=0)
+    with pytest.raises(TypeError, match="N_object must be an integer"):
+        mtm.matchTemplatesPyramid([("w", wide)], img, downscale=2, N_object=1.5)
+    assert mtm.matchTemplatesAugmented([], img) == [] and mtm.matchTemplatesPyramid([], img) == []
+    assert set(mtm.TRANSFORMS) == {"identity", "rot90", "rot180", "rot270", "fliplr", "flipud", "transpose", "antitranspose"}

@@ -1,0 +1,55 @@
+"""CPU tests of the host layer above the C ABI for SURVEY §8 f3 (augment.py) with the oracle-backed test double of
+tests/mock_device.py in place of the GPU context.  They run the BODIES of the -m gpu tests of test_gpu_xform.py, so
+what those tests expect from the device is checked against the restated semantics before it reaches the GPU box."""
+import numpy as np
+import pytest
+
+import test_gpu_xform as gx
+from mock_device import MockContext
+
+
+@pytest.fixture()
+def mock_mtm(mtm, monkeypatch):
+    from mtm_b200 import _native
+    shared = MockContext()
+    monkeypatch.setattr(_native, "Context", MockContext)
+    monkeypatch.setattr(_native, "default_context", lambda device=None: shared)
+    mtm._mock = shared
+    return mtm
+
+
+@pytest.mark.parametrize("dtype,channels", [(np.uint8, 1), (np.uint8, 3), (np.uint16, 1), (np.float32, 3)])
+def test_downscale_read_back(mock_mtm, dtype, channels):
+    gx.test_device_downscale_equals_inter_area(mock_mtm, dtype, channels)
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.float32])
+def test_transform_read_back(mock_mtm, dtype):
+    gx.test_device_transforms_equal_numpy(mock_mtm, dtype)
+
+
+@pytest.mark.parametrize("case", ["gray", "rgb", "float32", "flips_n3"])
+def test_augmented_front_end(mock_mtm, case):
+    gx.test_match_templates_augmented(mock_mtm, case)
+    assert "set_templates_transformed" in mock_mtm._mock.calls
+
+
+def test_search_region(mock_mtm):
+    gx.test_device_search_region_equals_host_crop(mock_mtm)
+
+
+def test_pyramid_notebook_answers(mock_mtm):
+    gx.test_pyramid_reproduces_notebook_answers(mock_mtm)
+    calls = mock_mtm._mock.calls
+    assert "set_image_scaled" in calls and "set_image_roi" in calls and "set_image" not in calls   # one upload per search
+
+
+@pytest.mark.parametrize("f,refine,kw", [
+    (2, True, dict(score_threshold=0.5, maxOverlap=0.25)),
+    (4, False, dict(score_threshold=0.4, maxOverlap=0.25)),
+    (3, True, dict(score_threshold=0.5, maxOverlap=0.1, N_object=5)),
+    (4, True, dict(score_threshold=0.5, maxOverlap=0.25, searchBox=(40, 30, 700, 520), coarse_threshold=0.35)),
+    (2, True, dict(score_threshold=0.3, maxOverlap=0.25, method=1, N_object=1)),
+])
+def test_pyramid_front_end(mock_mtm, f, refine, kw):
+    gx.test_pyramid_equals_specification(mock_mtm, f, refine, kw)

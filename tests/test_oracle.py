@@ -153,3 +153,80 @@ def test_peak_finders_restated():
     got = peaks.peak_local_max(m, 0.4).tolist()
     assert got == [[0, 0], [2, 3], [2, 4], [4, 5]]
     assert peaks.peak_local_max(m, 0.5).tolist() == [[0, 0], [2, 3], [2, 4]]   # strict threshold
+
+
+# ---- augmentation / pyramid restatements ---------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16])
+@pytest.mark.parametrize("channels", [1, 3, 4])
+def test_area_downscale_restatement_equals_live_cv2(dtype, channels):
+    """oracle.augment_port.area_downscale == cv2.resize(..., INTER_AREA) bit for bit (integer factors 2..16,
+    odd output sizes, ties included) -- the rule transform.cu implements."""
+    from oracle import augment_port as ap
+    rng = np.random.default_rng(5)
+    top = 255 if dtype == np.uint8 else 65535
+    for f in range(2, 17):
+        h, w = 23, 37
+        shape = (h * f + f - 1, w * f + 1) + ((channels,) if channels > 1 else ())      # remainders are cropped
+        img = rng.integers(0, top + 1, shape).astype(dtype)
+        img[:f, :f] = top                                                                # saturated box
+        got = ap.area_downscale(img, f)
+        want = ap.cv_area_downscale(img, f)
+        assert got.dtype == want.dtype and got.shape == want.shape
+        assert np.array_equal(got, want), "factor %d: %d pixels differ" % (f, int((got != want).sum()))
+    # narrow images take OpenCV's scalar tail: same rule
+    for ow in range(1, 20):
+        img = rng.integers(0, top + 1, (6, 2 * ow) + ((channels,) if channels > 1 else ())).astype(dtype)
+        assert np.array_equal(ap.area_downscale(img, 2), ap.cv_area_downscale(img, 2))
+
+
+def test_area_downscale_float32_close_to_live_cv2():
+    from oracle import augment_port as ap
+    rng = np.random.default_rng(6)
+    for f in (2, 3, 4, 7, 8):
+        img = (rng.random((f * 31, f * 45)) * 255).astype(np.float32)
+        assert np.max(np.abs(ap.area_downscale(img, f) - ap.cv_area_downscale(img, f))) <= 1e-6 * 255
+
+
+def test_expand_templates_equals_product_host_expansion(mtm):
+    from oracle import augment_port as ap
+    rng = np.random.default_rng(8)
+    temps = [("a", rng.integers(0, 256, (5, 9), dtype=np.uint8)), ("b", rng.integers(0, 256, (7, 4, 3), dtype=np.uint8))]
+    names = list(ap.HOST_TRANSFORMS)
+    assert sorted(names) == sorted(mtm.TRANSFORMS)
+    got = mtm.expandTemplates(temps, names)
+    want = ap.expand_templates(temps, names)
+    assert [g[0] for g in got] == [w[0] for w in want]
+    assert all(np.array_equal(g[1], w[1]) for g, w in zip(got, want))
+    assert [g[0] for g in got[:3]] == ["a", "a_rot90", "a_rot180"]
+    # Tutorial2 cell 15: rotated = np.rot90(temp0, k=i+1)
+    assert np.array_equal(got[1][1], np.rot90(temps[0][1], 1)) and np.array_equal(got[2][1], np.rot90(temps[0][1], 2))
+
+
+def test_pyramid_port_reproduces_notebook_answers():
+    """The coarse-to-fine specification gives the full-resolution answer stored in Tutorial3 cell 10, and its
+    unrefined form on the notebook's own small pair gives cell 21."""
+    from oracle import augment_port as ap, golden_cases as gc
+    fish = gc.fish()
+    head = [("head", fish[842:842 + 184, 528:528 + 196])]
+    for f in (2, 4, 8):
+        got = ap.match_templates_pyramid(head, fish, downscale=f, N_object=1)
+        assert [(h[0], h[1]) for h in got] == [(h[0], h[1]) for h in gc.NOTEBOOK_ANSWERS["t3_full"]]
+        assert abs(float(got[0][2]) - 1.0) <= 1e-5
+    small = ap.cv_area_downscale(fish, 4)
+    assert np.array_equal(small, gc.area_downscale(fish, 4))
+    got = ap.match_templates_pyramid([("downsampled", small[210:210 + 46, 131:131 + 49])], small, downscale=1, N_object=1,
+                                     refine=False)
+    want = gc.NOTEBOOK_ANSWERS["t3_downscaled"]
+    assert (got[0][0], got[0][1]) == (want[0][0], want[0][1]) and abs(float(got[0][2]) - want[0][2]) <= 1e-5
+
+
+def test_pyramid_port_equals_full_search_on_planted_scenes():
+    from oracle import augment_port as ap, mtm_port, synth
+    rng = np.random.default_rng(3)
+    temps = [synth.make_template(rng, 64, 64), synth.make_template(rng, 48, 80)]
+    img, _ = synth.make_scene(600, 800, temps, 4, seed=3)
+    labelled = [("a", temps[0]), ("b", temps[1])]
+    full = mtm_port.match_templates(labelled, img, score_threshold=0.5, maxOverlap=0.25)
+    for f in (2, 4):
+        pyr = ap.match_templates_pyramid(labelled, img, downscale=f, score_threshold=0.5, maxOverlap=0.25)
+        assert [(h[0], h[1]) for h in pyr] == [(h[0], h[1]) for h in full]
