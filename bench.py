@@ -31,6 +31,7 @@ import os
 import subprocess
 import sys
 import tempfile
+import threading
 import time
 
 import numpy as np
@@ -72,21 +73,78 @@ def build_workload(name, n_images):
 
 
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed regions.  NVML is polled from a thread of this process every
+    10 ms (three driver calls per sample, the GIL is released inside them); samples carry perf_counter time stamps and
+    only those inside a marked window count.  Falls back to an `nvidia-smi -lms` child when pynvml is unusable."""
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        self.windows = []                 # [t_begin, t_end] of the timed regions
+        self.samples = []                 # (t, sm_mhz, reason bitmask)
+        self.sm_max = None
+        self.thread = self.p = self.f = None
+        self._stop = threading.Event()
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.FIELDS,
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
-                                      stderr=subprocess.DEVNULL)
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            index = gpu_index
+            if visible:
+                try:
+                    index = int(visible.split(",")[gpu_index])
+                except (ValueError, IndexError):
+                    index = gpu_index
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
         except Exception:
-            self.p = None
+            self.thread = None
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            try:
+                self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.FIELDS,
+                                           "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
+                                          stderr=subprocess.DEVNULL)
+            except Exception:
+                self.p = None
+
+    def _poll(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)),
+                                     int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))))
+            except Exception:
+                pass
+            self._stop.wait(0.010)
+
+    def begin(self):
+        self.windows.append([time.perf_counter(), None])
+
+    def end(self):
+        self.windows[-1][1] = time.perf_counter()
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        out = {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": [], "samples": 0}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        if self.thread is not None:
+            self._stop.set()
+            self.thread.join(timeout=2)
+            nv = self.nv
+            masks = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+            inside = [smp for smp in self.samples if any(a <= smp[0] <= (b if b is not None else smp[0]) for a, b in self.windows)]
+            if inside:
+                bits = 0
+                for smp in inside:
+                    bits |= smp[2]
+                out.update(sm_mhz=float(np.median([smp[1] for smp in inside])), samples=len(inside),
+                           reasons=[nm for nm in names if bits & masks[nm]],
+                           how="NVML polled every 10 ms; samples inside the timed regions (%.0f ms in total)"
+                               % (1e3 * sum((b or a) - a for a, b in self.windows)))
+            return out
         if self.p is None:
             return out
         self.p.terminate()
@@ -97,7 +155,6 @@ class ClockSampler:
         self.f.flush()
         self.f.seek(0)
         sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.f.read().splitlines():
             parts = [x.strip() for x in line.split(",")]
             if len(parts) < 6:
@@ -112,7 +169,8 @@ class ClockSampler:
         self.f.close()
         os.unlink(self.f.name)
         if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm),
+                       how="nvidia-smi -lms 20 over the whole run")
         return out
 
 
@@ -179,7 +237,7 @@ def main():
     # ------------------------------------------------------------------ our arm
     import torch
     import torch.distributed as dist
-    steps = args.steps if args.steps is not None else 300
+    steps = args.steps if args.steps is not None else 1000
     warmup = args.warmup if args.warmup is not None else 10
     warmup = max(warmup, 3)
     torch.cuda.set_device(local_rank)
@@ -257,6 +315,9 @@ def main():
         return n_hits
 
     # ---------------- value: inputs resident in HBM ----------------
+    sampler = ClockSampler(local_rank) if rank == 0 else None     # polls throughout; only samples inside the timed regions count
+    mark_begin = sampler.begin if sampler else (lambda: None)
+    mark_end = sampler.end if sampler else (lambda: None)
     for c in ctxs:
         c.set_templates(tmpl_arrays)
     for i in range(warmup):
@@ -266,10 +327,10 @@ def main():
     barrier()
     for c in ctxs:
         c.synchronize()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     for c in ctxs:
         c.reset_counters()
         c.set_time_ncc(True)
+    mark_begin()
     ctx.timer_begin()
     resident_stream(warmup, steps)
     for c in ctxs:
@@ -281,8 +342,8 @@ def main():
         cc = c.counters()
         for k in ctr:
             ctr[k] += cc[k]
+    mark_end()
     barrier()
-    clocks = sampler.stop() if sampler else None
     # Second timed region, single stream, one synchronous call per step (submit, wait, read the hits):
     # the per-step latency, and the region in which the numerator kernel is bracketed by CUDA events on
     # its own stream WITHOUT another stream sharing the SMs (with several contexts the kernels of two
@@ -290,10 +351,12 @@ def main():
     lat_steps = max(20, steps // 3)
     ctx.reset_counters()
     ctx.set_time_ncc(True)
+    mark_begin()
     ctx.timer_begin()
     for i in range(lat_steps):
         resident_step(warmup + steps + i)
     lat_ms = ctx.timer_end() / lat_steps
+    mark_end()
     ctx.set_time_ncc(False)
     lat_ctr = ctx.counters()
     barrier()
@@ -310,17 +373,40 @@ def main():
                            N_object=params["N_object"], context=ctx)
     barrier()
     ctx.reset_counters()
+    mark_begin()
     ctx.timer_begin()
     for i in range(e2e_steps):
         MTM.matchTemplates(templates, h_np[(3 + i) % pool_n], score_threshold=thr, maxOverlap=ov,
                            N_object=params["N_object"], context=ctx)
     e_ms = ctx.timer_end()
+    mark_end()
     ectr = ctx.counters()
     barrier()
     e_t = torch.tensor([e_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(e_t, op=dist.ReduceOp.MAX)
     e2e_value = world * n_t * e2e_steps / (float(e_t.item()) * 1e-3)
+    # the same host arrays through the batch entry point (one pipelined submission: the upload of image k+1 overlaps
+    # the search of image k; every image's hit list is still read back on the host inside the timed region)
+    batch_imgs = [h_np[(3 + i) % pool_n] for i in range(e2e_steps)]
+    MTM.matchTemplatesBatch(templates, batch_imgs[:8], score_threshold=thr, maxOverlap=ov, N_object=params["N_object"], context=ctx)
+    barrier()
+    batch_ctxs = [ctx] + _native.helper_contexts(local_rank, 1)       # the two streams matchTemplatesBatch alternates between
+    for c in batch_ctxs:
+        c.synchronize()
+        c.reset_counters()
+    mark_begin()
+    ctx.timer_begin()
+    MTM.matchTemplatesBatch(templates, batch_imgs, score_threshold=thr, maxOverlap=ov, N_object=params["N_object"], context=ctx)
+    b_ms = ctx.timer_end()                                            # every slot has been collected: both streams are drained
+    mark_end()
+    clocks = sampler.stop() if sampler else None
+    bctr = {k: sum(c.counters()[k] for c in batch_ctxs) for k in ("h2d_bytes", "d2h_bytes")}
+    barrier()
+    b_t = torch.tensor([b_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(b_t, op=dist.ReduceOp.MAX)
+    batch_value = world * n_t * e2e_steps / (float(b_t.item()) * 1e-3)
 
     if rank != 0:
         if world > 1:
@@ -378,7 +464,11 @@ def main():
             "e2e": {"value": e2e_value, "unit": "matches/s", "steps": e2e_steps,
                     "ms_per_step": float(e_t.item()) / e2e_steps,
                     "h2d_bytes_per_step": ectr["h2d_bytes"] / e2e_steps, "d2h_bytes_per_step": ectr["d2h_bytes"] / e2e_steps,
-                    "api": "MTM.matchTemplates(listTemplates, image) with pinned host arrays"},
+                    "api": "MTM.matchTemplates(listTemplates, image) with pinned host arrays",
+                    "batch": {"value": batch_value, "unit": "matches/s", "ms_per_step": float(b_t.item()) / e2e_steps,
+                              "h2d_bytes_per_step": bctr["h2d_bytes"] / e2e_steps, "d2h_bytes_per_step": bctr["d2h_bytes"] / e2e_steps,
+                              "api": "MTM.matchTemplatesBatch(listTemplates, images): the same %d pinned host images as one "
+                                     "pipelined submission" % e2e_steps}},
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks}
     print(json.dumps(line))
     if world > 1:

@@ -305,6 +305,7 @@ class Context:
 
 
 _default = {}
+_helpers = {}
 _default_lock = threading.Lock()
 
 
@@ -317,3 +318,13 @@ def default_context(device=None):
         if ctx is None:
             ctx = _default[device] = Context(device)
     return ctx
+
+
+def helper_contexts(device, n):
+    """``n`` additional lazily created contexts (= CUDA streams with their own workspaces) on ``device``, used next
+    to the caller's context by the batch entry point so that uploads overlap the searches of another stream."""
+    with _default_lock:
+        have = _helpers.setdefault(int(device), [])
+        while len(have) < n:
+            have.append(Context(device))
+        return have[:n]

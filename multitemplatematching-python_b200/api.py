@@ -6,6 +6,7 @@ operation is executed by libmtm_b200.so on a B200 (see include/mtm_b200.h).
 There is no CPU fallback: input combinations whose GPU kernel is not written yet
 raise ``NotImplementedError``.
 """
+import contextlib
 import warnings
 
 import numpy as np
@@ -256,12 +257,14 @@ def matchTemplates(listTemplates, image, method=TM_CCOEFF_NORMED, N_object=_INF,
 
 
 def matchTemplatesBatch(listTemplates, images, method=TM_CCOEFF_NORMED, N_object=_INF, score_threshold=0.5,
-                        maxOverlap=0.25, searchBox=None, *, context=None):
+                        maxOverlap=0.25, searchBox=None, *, context=None, streams=2):
     """``[matchTemplates(listTemplates, im, ...) for im in images]`` as one pipelined submission.
 
     The reference has no batch entry point (users loop over images, e.g. the 16-image batch of
-    BASELINE.json configs[4]); here the templates are uploaded once and the images stream through the
+    BASELINE.json configs[4]); here the templates are uploaded once per stream and the images go through the
     GPU back to back (``mtm_match_templates_async`` / ``_collect``): no per-image host synchronisation.
+    ``streams`` contexts of the device (the given / default one plus helpers, one CUDA stream each) take the
+    images in turn, so the upload of one image overlaps the search of the previous one.
     Results are identical to the per-image calls.
     """
     images = list(images)
@@ -273,32 +276,43 @@ def matchTemplatesBatch(listTemplates, images, method=TM_CCOEFF_NORMED, N_object
         return [matchTemplates(listTemplates, im, method, N_object, score_threshold, maxOverlap, searchBox,
                                context=context) for im in images]
     ctx = context or _native.default_context()
+    n_streams = max(1, min(int(streams), len(images)))
+    ctxs = [ctx] + _native.helper_contexts(ctx.device, n_streams - 1)
     n_dev = int(N_object) if finite else -1
     depth = _native.MAX_INFLIGHT
     results = [None] * len(images)
-    pending = {}                                   # slot -> (image index, names, offsets, keep-alive)
-    names = None
+    pending = {}                                   # (stream, slot) -> (image index, names, offsets, keep-alive)
+    uploaded = [None] * n_streams                  # per stream: (signature, arrays kept alive) of its resident template set
 
-    def collect(slot):
-        i, nm, xo, yo, _keep = pending.pop(slot)
-        raw = ctx.match_templates_collect(slot)
+    def collect(key):
+        i, nm, xo, yo, _keep = pending.pop(key)
+        raw = ctxs[key[0]].match_templates_collect(key[1])
         results[i] = None if raw is None else _to_hits(raw, nm, xo, yo)
 
-    with ctx.lock:
-        for i, image in enumerate(images):
-            crop, xOffset, yOffset = _validate_search(listTemplates, image, N_object, searchBox)
-            nm, arrays, img, masks = _prepare(listTemplates, crop, method)
-            if names is None:
-                _upload_templates(ctx, arrays, masks)   # templates are the same objects for every image
-                names = nm
-            slot = i % depth
-            if slot in pending:
-                collect(slot)
-            ctx.set_image(img)
-            ctx.match_templates_async(method, n_dev, score_threshold, maxOverlap, slot)
-            pending[slot] = (i, nm, xOffset, yOffset, img)
-        for slot in sorted(pending, key=lambda s: pending[s][0]):
-            collect(slot)
+    with contextlib.ExitStack() as stack:
+        for c in ctxs:
+            stack.enter_context(c.lock)
+        try:
+            for i, image in enumerate(images):
+                crop, xOffset, yOffset = _validate_search(listTemplates, image, N_object, searchBox)
+                nm, arrays, img, masks = _prepare(listTemplates, crop, method)
+                k = i % n_streams
+                key = (k, (i // n_streams) % depth)
+                if key in pending:
+                    collect(key)
+                c = ctxs[k]
+                c.set_image(img)
+                # the routed template arrays are the caller's own objects unless the dtype policy had to cast them
+                sig = (img.dtype, img.ndim, tuple(map(id, arrays)), tuple(map(id, masks)))
+                if uploaded[k] is None or uploaded[k][0] != sig:
+                    _upload_templates(c, arrays, masks)
+                    uploaded[k] = (sig, arrays, masks)
+                c.match_templates_async(method, n_dev, score_threshold, maxOverlap, key[1])
+                pending[key] = (i, nm, xOffset, yOffset, img)
+        finally:
+            # in submission order; also drains the slots when an image of the batch was rejected
+            for key in sorted(pending, key=lambda q: pending[q][0]):
+                collect(key)
     for i, r in enumerate(results):                # images that exceeded the fused fast path
         if r is None:
             results[i] = matchTemplates(listTemplates, images[i], method, N_object, score_threshold, maxOverlap,

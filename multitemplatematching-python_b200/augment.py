@@ -176,13 +176,41 @@ def matchTemplatesPyramid(listTemplates, image, downscale=4, method=TM_CCOEFF_NO
         coarse = _fused_or_split(ctx, method, N_object, coarse_threshold, maxOverlap, list(range(len(names))), 0, 0)
         if not refine:
             return [(names[t], (x * f + xOffset, y * f + yOffset, w * f, h * f), score) for t, (x, y, w, h), score in coarse]
-        refined = []
-        for t, (x, y, _w, _h), _score in coarse:
+        # Re-localisation: one small search per coarse hit, pipelined through the asynchronous entry points (no host
+        # synchronisation per hit); hits are visited template by template so that the template upload is reused.
+        refined = [None] * len(coarse)
+        depth = _native.MAX_INFLIGHT
+        pending = {}                                   # slot -> (position in `coarse`, template, x0, y0)
+
+        def region(k):
+            t, (x, y, _w, _h), _score = coarse[k]
             th, tw = arrays[t].shape[:2]
             x0, y0 = max(0, x * f - f), max(0, y * f - f)
-            x1, y1 = min(W, x * f + tw + f), min(H, y * f + th + f)
-            ctx.set_image_roi(x0, y0, x1 - x0, y1 - y0)
-            ctx.set_templates([arrays[t]])
-            raw = ctx.match_templates(method, 1, score_threshold, maxOverlap)
-            refined.extend(_to_hits(raw, [names[t]], x0 + xOffset, y0 + yOffset))
-    return NMS(refined, score_threshold, method == 1, N_object, maxOverlap, context=ctx)
+            return t, x0, y0, min(W, x * f + tw + f) - x0, min(H, y * f + th + f) - y0
+
+        def collect(slot):
+            k, t, x0, y0 = pending.pop(slot)
+            raw = ctx.match_templates_collect(slot)
+            refined[k] = None if raw is None else _to_hits(raw, [names[t]], x0 + xOffset, y0 + yOffset)
+
+        try:
+            for n, k in enumerate(sorted(range(len(coarse)), key=lambda q: coarse[q][0])):
+                slot = n % depth
+                if slot in pending:
+                    collect(slot)
+                t, x0, y0, bw, bh = region(k)
+                ctx.set_image_roi(x0, y0, bw, bh)
+                ctx.set_templates([arrays[t]])
+                ctx.match_templates_async(method, 1, score_threshold, maxOverlap, slot)
+                pending[slot] = (k, t, x0, y0)
+        finally:
+            for slot in sorted(pending, key=lambda q: pending[q][0]):
+                collect(slot)
+        for k, hits in enumerate(refined):             # a submission the fused fast path declined: synchronous call
+            if hits is None:
+                t, x0, y0, bw, bh = region(k)
+                ctx.set_image_roi(x0, y0, bw, bh)
+                ctx.set_templates([arrays[t]])
+                refined[k] = _to_hits(ctx.match_templates(method, 1, score_threshold, maxOverlap), [names[t]],
+                                      x0 + xOffset, y0 + yOffset)
+    return NMS([hit for hits in refined for hit in hits], score_threshold, method == 1, N_object, maxOverlap, context=ctx)

@@ -24,8 +24,12 @@ class MockContext:
         self.full = None
         self.templates = []
         self.calls = []                      # names of the entry points used, in order
+        self.slots = {}
 
     def close(self):
+        pass
+
+    def synchronize(self):
         pass
 
     # -- inputs ---------------------------------------------------------------------
@@ -84,6 +88,16 @@ class MockContext:
         labelled = [(i, t) for i, t in enumerate(self.templates)]
         n = mtm_port.INF if n_object < 0 else int(n_object)
         return self._raw(mtm_port.match_templates(labelled, self.image, method, n, score_threshold, max_overlap, workers=1))
+
+    def match_templates_async(self, method, n_object, score_threshold, max_overlap, slot):
+        self.calls.append("match_templates_async")
+        assert slot not in self.slots, "slot %d not collected yet" % slot
+        self.slots[slot] = self.match_templates(method, n_object, score_threshold, max_overlap)
+
+    def match_templates_collect(self, slot):
+        self.calls.append("match_templates_collect")
+        raw = self.slots.pop(slot)
+        return None if len(raw) > 1024 else raw
 
     def nms(self, hits, score_threshold, sort_ascending, n_object, max_overlap):
         self.calls.append("nms")

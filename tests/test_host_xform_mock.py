@@ -14,6 +14,9 @@ def mock_mtm(mtm, monkeypatch):
     shared = MockContext()
     monkeypatch.setattr(_native, "Context", MockContext)
     monkeypatch.setattr(_native, "default_context", lambda device=None: shared)
+    helpers = [MockContext() for _ in range(4)]
+    monkeypatch.setattr(_native, "helper_contexts", lambda device, n: helpers[:n])
+    mtm._mock_helpers = helpers
     mtm._mock = shared
     return mtm
 
@@ -53,3 +56,23 @@ def test_pyramid_notebook_answers(mock_mtm):
 ])
 def test_pyramid_front_end(mock_mtm, f, refine, kw):
     gx.test_pyramid_equals_specification(mock_mtm, f, refine, kw)
+
+
+def test_batch_front_end_equals_loop(mock_mtm):
+    """matchTemplatesBatch over 1..3 streams == the per-image calls (offsets, labels, order; mixed image dtypes)."""
+    from oracle import synth
+    rng = np.random.default_rng(77)
+    temps = [("t%d" % i, synth.make_template(rng, 24 + 4 * i, 30)) for i in range(3)]
+    images = [synth.make_scene(160, 200, [t[1] for t in temps], 2, seed=100 + k)[0] for k in range(7)]
+    images[3] = images[3].astype(np.float32)                   # dtype policy differs for this image: templates are re-routed
+    for streams in (1, 2, 3):
+        for kw in (dict(score_threshold=0.5, maxOverlap=0.25), dict(N_object=1), dict(score_threshold=0.5, searchBox=(10, 20, 150, 120))):
+            want = [mock_mtm.matchTemplates(temps, im, **kw) for im in images]
+            got = mock_mtm.matchTemplatesBatch(temps, images, streams=streams, **kw)
+            assert len(got) == len(want) == 7
+            for g, w in zip(got, want):
+                assert [(a[0], a[1], float(a[2])) for a in g] == [(b[0], b[1], float(b[2])) for b in w]
+    assert "match_templates_async" in mock_mtm._mock_helpers[0].calls and not mock_mtm._mock_helpers[3].calls
+    with pytest.raises(ValueError, match="larger than image"):     # a bad image in the middle: slots are drained, error propagates
+        mock_mtm.matchTemplatesBatch(temps, images[:2] + [images[0][:10, :10]] + images[2:], streams=2)
+    assert not mock_mtm._mock.slots and not mock_mtm._mock_helpers[0].slots
