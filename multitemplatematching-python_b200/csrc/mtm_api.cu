@@ -555,6 +555,8 @@ static int compute_maps(mtm_ctx* ctx, int method, int tmpl)
                 MTM_TRY(launch_ncc_tc_accum(ctx, g, 0, 1, 256.0, false));
                 MTM_TRY(launch_ncc_tc_accum(ctx, g, 1, 0, 256.0, false));
                 MTM_TRY(launch_ncc_tc_accum(ctx, g, 1, 1, 1.0, false));
+            } else if (points_path_preferred(ctx, g.first, g.count)) {
+                MTM_TRY(launch_ncc_points(ctx, method, g.first, g.count));          // tiny maps of large templates
             } else {
                 MTM_TRY(launch_ncc_tc(ctx, g, method));
             }
@@ -569,11 +571,16 @@ static int compute_maps(mtm_ctx* ctx, int method, int tmpl)
         int j = i + 1;
         while (j < n && ctx->h_meta[ctx->h_order[j]].h == a.h && ctx->h_meta[ctx->h_order[j]].w == a.w) ++j;
         const bool f32 = (ctx->img_dtype == MTM_F32);
+        const bool points = !f32 && points_path_preferred(ctx, i, j - i);
+        auto direct = [&](int first, int count) {
+            return f32 ? launch_ncc_direct_f32(ctx, method, first, count)
+                       : (points ? launch_ncc_points(ctx, method, first, count) : launch_ncc_direct(ctx, method, first, count));
+        };
         if (tmpl < 0) {
-            MTM_TRY(f32 ? launch_ncc_direct_f32(ctx, method, i, j - i) : launch_ncc_direct(ctx, method, i, j - i));
+            MTM_TRY(direct(i, j - i));
         } else {
             for (int k = i; k < j; ++k)
-                if (ctx->h_order[k] == tmpl) MTM_TRY(f32 ? launch_ncc_direct_f32(ctx, method, k, 1) : launch_ncc_direct(ctx, method, k, 1));
+                if (ctx->h_order[k] == tmpl) MTM_TRY(direct(k, 1));
         }
         i = j;
     }

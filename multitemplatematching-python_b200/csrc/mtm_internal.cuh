@@ -217,6 +217,9 @@ int launch_build_sat(mtm_ctx* ctx);
 int launch_tmpl_stats(mtm_ctx* ctx);
 // templates d_order[first .. first+count) share (h, w)
 int launch_ncc_direct(mtm_ctx* ctx, int method, int first, int count);
+// small score maps of large uint8 templates (ncc_points.cu); same group convention
+bool points_path_preferred(const mtm_ctx* ctx, int first, int count);
+int launch_ncc_points(mtm_ctx* ctx, int method, int first, int count);
 // float32 branch (ncc_float.cu)
 int launch_build_sat_f32(mtm_ctx* ctx);
 int launch_tmpl_stats_f32(mtm_ctx* ctx);
