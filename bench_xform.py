@@ -38,6 +38,8 @@ def timed(fn, reps, ctx):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=30)
+    ap.add_argument("--once", action="store_true",
+                    help="one cold-template call of each front end and exit (the launch list under ncu: profiles/README.md)")
     args = ap.parse_args()
     import MTM
     from mtm_b200 import _native
@@ -54,6 +56,13 @@ def main():
     images = [np.ascontiguousarray(np.roll(image, (13 * s, 29 * s), axis=(0, 1))) for s in range(8)]
     sets = [[("a", bases_a[0]), ("b", bases_a[1])], [("a", bases_b[0]), ("b", bases_b[1])]]
     kw = dict(score_threshold=0.5, maxOverlap=0.25)
+    if args.once:
+        MTM.matchTemplatesAugmented(sets[0], images[0], transforms, **kw)
+        big_t = synth.make_template(rng, 256, 256)
+        big, _ = synth.make_scene(4096, 4096, [big_t], 3, seed=0)
+        hits = MTM.matchTemplatesPyramid([("big", big_t)], big, downscale=4, **kw)
+        print(json.dumps({"bench": "once", "pyramid_hits": len(hits)}), flush=True)
+        return
     ref = MTM.matchTemplates(MTM.expandTemplates(sets[0], transforms), images[0], **kw)
     got = MTM.matchTemplatesAugmented(sets[0], images[0], transforms, **kw)
     same = [(h[0], h[1], float(h[2])) for h in ref] == [(h[0], h[1], float(h[2])) for h in got]

@@ -5,7 +5,7 @@
 // thousands of products per pixel.  The tiled kernels parallelise over output pixels: the tcgen05 kernel would run
 // all template rows of its single tile as one serial chain of MMAs (0.2 ms for a 256 x 256 template), the dp4a
 // kernel would leave most threads idle.  Here the parallelism is over the TEMPLATE: one CTA per output pixel,
-// its 256 threads stride over the template's 32-bit words (dp4a against the unaligned image word rebuilt with a
+// its 1024 threads stride over the template's 32-bit words (dp4a against the unaligned image word rebuilt with a
 // funnel shift), block reduction, then the same float64 OpenCV epilogue as ncc_direct.cu on the exact integer
 // sums -- maps are bit-identical to the dp4a kernel's.
 // Bound: L2 bandwidth (every CTA reads the template and its window once: 2*h*w*C bytes per output pixel).
@@ -15,7 +15,7 @@
 
 namespace {
 
-constexpr int PT_THREADS = 256;
+constexpr int PT_THREADS = 1024;
 constexpr int PT_MAX_PIXELS = 1024;        // largest score map this kernel is chosen for
 constexpr int PT_MIN_BYTES = 16384;        // smallest template (h*w*C bytes) it is chosen for
 
@@ -41,18 +41,15 @@ ncc_points_kernel(const PointsParams p)
     for (int pos = blockIdx.x; pos < npos; pos += gridDim.x) {
         const int y = pos / tm.mw, x = pos - y * tm.mw;
         unsigned long long total = 0ull;
-        uint32_t acc = 0u;
-        int since = 0;
+#pragma unroll 4
         for (int k = tid; k < nwords; k += PT_THREADS) {
             const int r = k / wq, g = k - r * wq;
-            const uint32_t tw = *reinterpret_cast<const uint32_t*>(tp + (int64_t)r * tm.wp + 4 * g);   // zero padded beyond w*C
+            const uint32_t tw = __ldg(reinterpret_cast<const uint32_t*>(tp + (int64_t)r * tm.wp + 4 * g));   // zero padded beyond w*C
             const int64_t a = (int64_t)(y + r) * p.pitch + (int64_t)x * C + 4 * g;
             const uint32_t* iw = reinterpret_cast<const uint32_t*>(p.img + (a & ~(int64_t)3));
-            const uint32_t s = __funnelshift_r(iw[0], iw[1], 8 * (int)(a & 3));                       // 4 image bytes from offset a
-            acc = __dp4a(s, tw, acc);
-            if (++since == 8192) { total += acc; acc = 0u; since = 0; }                                // 8192 * 4 * 255^2 < 2^32
+            const uint32_t s = __funnelshift_r(__ldg(iw), __ldg(iw + 1), 8 * (int)(a & 3));                    // 4 image bytes from offset a
+            total += __dp4a(s, tw, 0u);
         }
-        total += acc;
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) total += __shfl_down_sync(0xffffffffu, total, d);
         if (lane == 0) part[wid] = total;

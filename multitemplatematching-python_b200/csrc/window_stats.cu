@@ -153,19 +153,33 @@ sat_cols_kernel(const uint32_t* __restrict__ scratch, int H, int W, int C, int S
     }
 }
 
-// One block per template: integer sums -> OpenCV's meanStdDev-derived constants.
-__global__ void tmpl_stats_kernel(const uint8_t* __restrict__ tmpl, TmplMeta* __restrict__ meta, int C)
+// One block per template: integer sums -> OpenCV's meanStdDev-derived constants.  The packed rows (pitch wp, a
+// multiple of 4, zero padded beyond w*C bytes) are read as 32-bit words; byte b of a row belongs to channel b % C,
+// which a 0/1 byte mask selects for dp4a (sum) and a 0/255 mask for the squares.
+__global__ void __launch_bounds__(1024)
+tmpl_stats_kernel(const uint8_t* __restrict__ tmpl, TmplMeta* __restrict__ meta, int C)
 {
     TmplMeta& m = meta[blockIdx.x];
-    const uint8_t* p = tmpl + m.pix_off;
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(tmpl + m.pix_off);      // pix_off is a multiple of 16
     long long s[MTM_MAX_CH] = {0, 0, 0, 0}, q[MTM_MAX_CH] = {0, 0, 0, 0};
-    const int n = m.h * m.w;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int y = i / m.w, x = i - y * m.w;
-        for (int c = 0; c < C; ++c) {
-            long long v = p[(int64_t)y * m.wp + x * C + c];
-            s[c] += v;
-            q[c] += v * v;
+    const int wq = m.wp >> 2, nwords = m.h * wq;
+#pragma unroll 4
+    for (int k = threadIdx.x; k < nwords; k += blockDim.x) {
+        const uint32_t v = __ldg(p + k);
+        const int g = k % wq;                      // word index inside its row
+        int ch = (4 * g) % C;                      // channel of the word's first byte
+        uint32_t ones[MTM_MAX_CH] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+#pragma unroll
+            for (int c = 0; c < MTM_MAX_CH; ++c)
+                if (c == ch) ones[c] |= 1u << (8 * b);
+            ch = (ch + 1 == C) ? 0 : ch + 1;
+        }
+#pragma unroll
+        for (int c = 0; c < MTM_MAX_CH; ++c) {
+            s[c] += __dp4a(v, ones[c], 0u);
+            q[c] += __dp4a(v & (ones[c] * 255u), v, 0u);
         }
     }
     __shared__ long long red[2 * MTM_MAX_CH][32];
@@ -228,7 +242,7 @@ int launch_build_sat(mtm_ctx* ctx)
 
 int launch_tmpl_stats(mtm_ctx* ctx)
 {
-    tmpl_stats_kernel<<<ctx->n_tmpl, 256, 0, ctx->stream>>>(ctx->d_tmpl, ctx->d_meta, ctx->tmpl_C);
+    tmpl_stats_kernel<<<ctx->n_tmpl, 1024, 0, ctx->stream>>>(ctx->d_tmpl, ctx->d_meta, ctx->tmpl_C);
     MTM_LAUNCH_CHECK(ctx);
     return MTM_OK;
 }
