@@ -13,7 +13,11 @@ rot90), score_threshold 0.5, maxOverlap 0.25.
                CUDA events on the library's stream, max over ranks.
 * ``e2e``    : the same metric through the public Python API ``MTM.matchTemplates``
                with HOST (pinned) image/template arrays: H2D of image + templates
-               and D2H of the hit list inside the timed region.
+               and D2H of the hit list inside the timed region, one synchronous call per
+               step.  ``e2e.batch``: the same host images through ``MTM.matchTemplatesBatch``
+               (one pipelined submission over two streams; same copies, same read-backs).
+* ``clocks`` : NVML polled every 10 ms by a thread of this process; only samples that fall
+               inside the timed regions count (median SM clock, throttle reasons seen).
 * ``roofline``: the numerator kernel (ncc_tc_persist / ncc_tc / ncc_direct), bracketed by CUDA events
                (MTM_OPT_TIME_NCC) in a second, single-stream synchronous region of the same run.
 * ``cpu_baseline`` / ``--impl reference``: the CPU port of the reference on live
