@@ -135,3 +135,30 @@ def test_augmented_and_pyramid_validate_before_device_work(mtm):
         mtm.matchTemplatesPyramid([("w", wide)], img, downscale=2, N_object=1.5)
     assert mtm.matchTemplatesAugmented([], img) == [] and mtm.matchTemplatesPyramid([], img) == []
     assert set(mtm.TRANSFORMS) == {"identity", "rot90", "rot180", "rot270", "fliplr", "flipud", "transpose", "antitranspose"}
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/mtm_b200.h must compile as C (the boundary is a C ABI, not a C++ one) and link against the library."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "abi.c"
+    src.write_text('#include "mtm_b200.h"\n'
+                   'int main(void) {\n'
+                   '    mtm_hit h = {0, 1, 2, 3, 4, 0.5f};\n'
+                   '    mtm_counters c = {0};\n'
+                   '    mtm_ctx* ctx = 0;\n'
+                   '    int ok = sizeof(mtm_hit) == 24 && MTM_MAX_INFLIGHT == 8 && MTM_XF_ANTITRANSPOSE == 7 && MTM_U16 == 2;\n'
+                   '    (void)h; (void)c;\n'
+                   '    /* without a GPU mtm_create must fail loudly; with one it must succeed */\n'
+                   '    int rc = mtm_create(0, &ctx);\n'
+                   '    if (rc == MTM_OK) mtm_destroy(ctx); else if (!mtm_last_error(0)[0]) return 3;\n'
+                   '    return ok && mtm_abi_version() == MTM_ABI_VERSION ? 0 : 2;\n'
+                   '}\n')
+    lib_dir = os.path.join(ROOT, "multitemplatematching-python_b200")
+    exe = tmp_path / "abi"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", lib_dir, "-lmtm_b200", "-Wl,-rpath," + lib_dir], check=True, capture_output=True)
+    assert subprocess.run([str(exe)]).returncode == 0
