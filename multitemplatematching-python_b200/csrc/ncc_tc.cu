@@ -751,6 +751,9 @@ __global__ void toeplitz_prep_kernel(const uint8_t* __restrict__ tmpl, const Tmp
 
 // S = window sum, rsD = rsqrt(A*Q - S^2) (0 for an exactly flat window), per window position, for
 // every distinct template size in one launch (blockIdx.y = size).
+// STREAM (experiment knob): write the maps with the evict-first hint (st.global.cs) so that a many-size sweep (C5: 4 GB of
+// moments) cannot push the summed-area tables it keeps re-reading out of L2.
+template <bool STREAM>
 __global__ void window_moments_kernel(SatView sat, const uint32_t* __restrict__ sat_q32, const SizeDesc* __restrict__ sizes,
                                       uint32_t* __restrict__ S, float* __restrict__ rsD, int C, int64_t mom_plane)
 {
@@ -766,11 +769,12 @@ __global__ void window_moments_kernel(SatView sat, const uint32_t* __restrict__ 
         for (int c = 0; c < C; ++c) {
             const uint32_t s = sat_window_s(sat.s + c * sat.plane, sat.pitch, y, x, sd.h, sd.w);
             d1 -= (unsigned long long)s * s;
-            if (C > 1) S[c * mom_plane + sd.off + idx] = s;
+            if (C > 1) { if (STREAM) __stcs(S + c * mom_plane + sd.off + idx, s); else S[c * mom_plane + sd.off + idx] = s; }
             s0 = s;
         }
         const float rs = d1 ? rsqrtf((float)d1) : 0.0f;
-        if (C > 1) rsD[sd.off + idx] = rs;
+        if (C > 1) { if (STREAM) __stcs(rsD + sd.off + idx, rs); else rsD[sd.off + idx] = rs; }
+        else if (STREAM) __stcs(reinterpret_cast<uint2*>(S) + sd.off + idx, make_uint2(s0, __float_as_uint(rs)));
         else reinterpret_cast<uint2*>(S)[sd.off + idx] = make_uint2(s0, __float_as_uint(rs));   // one 8-byte load per pixel in the epilogue
     }
 }
@@ -782,7 +786,7 @@ __global__ void window_moments_kernel(SatView sat, const uint32_t* __restrict__ 
 // measurements under profiles/ can be repeated: tile height, ring stage size, epilogue warps, shared-memory ceiling,
 // the one-tile-per-CTA kernel, per-role clocks and phase knock-outs of the persistent kernel.
 struct TcEnv {
-    int force_n = 0, ds = 0, ew = 0, pdbg = 0;
+    int force_n = 0, ds = 0, ew = 0, pdbg = 0, mom_cs = -1;
     size_t smem_soft = 0;
     bool persist_off = false, prof = false;
     TcEnv()
@@ -795,6 +799,7 @@ struct TcEnv {
         smem_soft = getenv("MTM_B200_SMEM_SOFT") ? (size_t)num("MTM_B200_SMEM_SOFT") * 1024 : 0;
         persist_off = getenv("MTM_B200_PERSIST") && num("MTM_B200_PERSIST") == 0;
         prof = getenv("MTM_B200_PROF") != nullptr;
+        mom_cs = getenv("MTM_B200_MOM_CS") ? num("MTM_B200_MOM_CS") : -1;
     }
 };
 static const TcEnv& tc_env()
@@ -866,7 +871,14 @@ int launch_window_moments(mtm_ctx* ctx)
     int64_t n = 0;
     for (const SizeDesc& sd : ctx->h_sizes) n = std::max<int64_t>(n, (int64_t)sd.mh * sd.mw);
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 16));
-    window_moments_kernel<<<dim3(blocks, (unsigned)ctx->h_sizes.size()), 256, 0, ctx->stream>>>(sv, im.sat_q32, ctx->d_sizes, ctx->d_wS, ctx->d_wR, im.C, ctx->moments_total);
+    const dim3 grid(blocks, (unsigned)ctx->h_sizes.size());
+    // MTM_B200_MOM_CS=1 (experiment): evict-first stores.  Measured neutral on C5 (7.35 against 7.42 ms per step,
+    // profiles/README.md): the 64-size sweep is not limited by the moment maps evicting the tables, so the default stays off.
+    const bool stream_stores = tc_env().mom_cs > 0;
+    if (stream_stores)
+        window_moments_kernel<true><<<grid, 256, 0, ctx->stream>>>(sv, im.sat_q32, ctx->d_sizes, ctx->d_wS, ctx->d_wR, im.C, ctx->moments_total);
+    else
+        window_moments_kernel<false><<<grid, 256, 0, ctx->stream>>>(sv, im.sat_q32, ctx->d_sizes, ctx->d_wS, ctx->d_wR, im.C, ctx->moments_total);
     MTM_LAUNCH_CHECK(ctx);
     return MTM_OK;
 }
