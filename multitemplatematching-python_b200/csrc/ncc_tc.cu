@@ -779,6 +779,46 @@ __global__ void window_moments_kernel(SatView sat, const uint32_t* __restrict__ 
     }
 }
 
+// Row-walking form of window_moments_kernel (experiment knob MTM_B200_MOM_ROWS=1; same arithmetic per position, hence
+// bit-identical maps): blockIdx.z = size, blockIdx.y walks the rows, threads walk x -- no 64-bit division per position and
+// the eight corner addresses are a row pointer plus x.  The grid-stride kernel above executes ~110 instructions per
+// position and runs at ~0.75 positions per clock per SM (C5: 506 M positions in 2.4 ms), which is an issue-rate bound,
+// not a memory one (evict-first stores changed nothing, profiles/README.md).  NOT YET MEASURED ON THE GPU.
+template <int C>
+__global__ void __launch_bounds__(256)
+window_moments_rows_kernel(SatView sat, const uint32_t* __restrict__ sat_q32, const SizeDesc* __restrict__ sizes,
+                           uint32_t* __restrict__ S, float* __restrict__ rsD, int64_t mom_plane)
+{
+    const SizeDesc sd = sizes[blockIdx.z];
+    const uint32_t area = (uint32_t)sd.h * (uint32_t)sd.w;                 // <= 66051 on the tensor path
+    const int x_first = blockIdx.x * blockDim.x + threadIdx.x, x_step = gridDim.x * blockDim.x;
+    const int64_t down = (int64_t)sd.h * sat.pitch;                         // from the window's top SAT row to its bottom one
+    for (int y = blockIdx.y; y < sd.mh; y += gridDim.y) {
+        const uint32_t* qa = sat_q32 + (int64_t)y * sat.pitch;
+        const uint32_t* sa = sat.s + (int64_t)y * sat.pitch;
+        uint32_t* out_s = S + sd.off + (int64_t)y * sd.mw;
+        float* out_r = rsD + sd.off + (int64_t)y * sd.mw;
+        uint2* out_sr = reinterpret_cast<uint2*>(S) + sd.off + (int64_t)y * sd.mw;
+        for (int x = x_first; x < sd.mw; x += x_step) {
+            const uint32_t* q0 = qa + x;
+            const uint32_t q = q0[down + sd.w] - q0[sd.w] - q0[down] + q0[0];      // modulo 2^32, exact (window sums < 2^32)
+            unsigned long long d1 = (unsigned long long)area * q;
+            uint32_t s0 = 0;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const uint32_t* p0 = sa + c * sat.plane + x;
+                const uint32_t s = p0[down + sd.w] - p0[sd.w] - p0[down] + p0[0];
+                d1 -= (unsigned long long)s * s;
+                if (C > 1) out_s[c * mom_plane + x] = s;
+                s0 = s;
+            }
+            const float rs = d1 ? rsqrtf((float)d1) : 0.0f;
+            if (C > 1) out_r[x] = rs;
+            else out_sr[x] = make_uint2(s0, __float_as_uint(rs));
+        }
+    }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------ host side
@@ -788,7 +828,7 @@ __global__ void window_moments_kernel(SatView sat, const uint32_t* __restrict__ 
 struct TcEnv {
     int force_n = 0, ds = 0, ew = 0, pdbg = 0, mom_cs = -1;
     size_t smem_soft = 0;
-    bool persist_off = false, prof = false;
+    bool persist_off = false, prof = false, mom_rows = false;
     TcEnv()
     {
         auto num = [](const char* name) { const char* v = getenv(name); return v ? atoi(v) : 0; };
@@ -800,6 +840,7 @@ struct TcEnv {
         persist_off = getenv("MTM_B200_PERSIST") && num("MTM_B200_PERSIST") == 0;
         prof = getenv("MTM_B200_PROF") != nullptr;
         mom_cs = getenv("MTM_B200_MOM_CS") ? num("MTM_B200_MOM_CS") : -1;
+        mom_rows = num("MTM_B200_MOM_ROWS") != 0;
     }
 };
 static const TcEnv& tc_env()
@@ -871,6 +912,18 @@ int launch_window_moments(mtm_ctx* ctx)
     int64_t n = 0;
     for (const SizeDesc& sd : ctx->h_sizes) n = std::max<int64_t>(n, (int64_t)sd.mh * sd.mw);
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 16));
+    if (tc_env().mom_rows) {
+        int mh = 1, mw = 1;
+        for (const SizeDesc& sd : ctx->h_sizes) { mh = std::max(mh, sd.mh); mw = std::max(mw, sd.mw); }
+        const dim3 rgrid((unsigned)std::min((mw + 255) / 256, 8), (unsigned)std::min(mh, ctx->sm_count), (unsigned)ctx->h_sizes.size());
+        switch (im.C) {
+            case 1: window_moments_rows_kernel<1><<<rgrid, 256, 0, ctx->stream>>>(sv, im.sat_q32, ctx->d_sizes, ctx->d_wS, ctx->d_wR, ctx->moments_total); break;
+            case 3: window_moments_rows_kernel<3><<<rgrid, 256, 0, ctx->stream>>>(sv, im.sat_q32, ctx->d_sizes, ctx->d_wS, ctx->d_wR, ctx->moments_total); break;
+            default: window_moments_rows_kernel<4><<<rgrid, 256, 0, ctx->stream>>>(sv, im.sat_q32, ctx->d_sizes, ctx->d_wS, ctx->d_wR, ctx->moments_total); break;
+        }
+        MTM_LAUNCH_CHECK(ctx);
+        return MTM_OK;
+    }
     const dim3 grid(blocks, (unsigned)ctx->h_sizes.size());
     // MTM_B200_MOM_CS=1 (experiment): evict-first stores.  Measured neutral on C5 (7.35 against 7.42 ms per step,
     // profiles/README.md): the 64-size sweep is not limited by the moment maps evicting the tables, so the default stays off.
