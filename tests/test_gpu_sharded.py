@@ -18,6 +18,18 @@ def test_sharded_world1_equals_match_templates(mtm):
         assert_hits_equal(sharded.matchTemplatesSharded(temps, img, **kw), mtm.matchTemplates(temps, img, **kw), tol=0)
 
 
+def test_batch_sharded_world1_equals_per_image_calls(mtm):
+    """The image-sharded cut (SURVEY 8e, configs[4]) without a process group: == the per-image calls."""
+    import numpy as np
+    from mtm_b200 import sharded
+    from oracle import golden_cases as gc
+    kind, temps, img, kw = gc.build("synth_mixed")
+    images = [img, np.ascontiguousarray(img[::-1]), np.ascontiguousarray(img[:, ::-1])]
+    got = sharded.matchTemplatesBatchSharded(temps, images, **kw)
+    for g, im in zip(got, images):
+        assert_hits_equal(g, mtm.matchTemplates(temps, im, **kw), tol=0)
+
+
 def _worker(rank, world, port, out_dir):
     import pickle
     import sys

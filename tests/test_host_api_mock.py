@@ -71,3 +71,10 @@ def test_rare_corners_split_find_and_nms(mock_mtm):
         got = mock_mtm.matchTemplates(ts, im, score_threshold=0.5)
         want = mtm_port.match_templates(ts, im, score_threshold=0.5)
         assert [(h[0], h[1]) for h in got] == [(h[0], h[1]) for h in want] and len(want) >= 4
+
+
+def test_sharded_entry_points_without_a_process_group(mock_mtm):
+    """world size 1: the sharded wrappers reduce to the plain calls (bodies of tests/test_gpu_sharded.py)."""
+    import test_gpu_sharded as gs
+    gs.test_sharded_world1_equals_match_templates(mock_mtm)
+    gs.test_batch_sharded_world1_equals_per_image_calls(mock_mtm)

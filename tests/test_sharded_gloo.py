@@ -38,6 +38,14 @@ def _worker(rank, world, port, out_dir):
     kind, temps, img, kw = gc.build("c1_fish256_inf")
     got = sharded.matchTemplatesSharded(temps, img, find_fn=mtm_port.find_matches, nms_fn=mtm_port.nms, **kw)
     results["c1_fish256_inf"] = [(h[0], tuple(h[1]), float(h[2])) for h in got]
+    # the other cut (SURVEY 8e, configs[4]): images sharded, templates whole, one all-gather of the final lists
+    def batch_fn(temps, images, method, N_object, thr, overlap, box):
+        return [mtm_port.match_templates(temps, im, method, N_object, thr, overlap, box) for im in images]
+    kind, temps, img, kw = gc.build("synth_mixed")
+    images = [img, np.ascontiguousarray(img[::-1]), np.ascontiguousarray(img[:, ::-1])]
+    for name, ims in (("batch3", images), ("batch1", images[:1])):          # 3 images / 2 ranks; 1 image -> rank 1 idle
+        got = sharded.matchTemplatesBatchSharded(temps, ims, batch_fn=batch_fn, **kw)
+        results[name] = [[(h[0], tuple(h[1]), float(h[2])) for h in hits] for hits in got]
     with open(os.path.join(out_dir, "rank%d.pkl" % rank), "wb") as f:
         pickle.dump(results, f)
     dist.destroy_process_group()
@@ -55,6 +63,23 @@ def test_shard_bounds_cover_everything():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_mac_balanced_template_slices():
+    """Mixed template sizes (configs[4]: 64 templates of 32..128 px): slices balanced by work, not by count."""
+    import MTM  # noqa: F401
+    from mtm_b200.sharded import template_macs, weighted_bounds
+    sides = np.linspace(32, 128, 64).round().astype(int)
+    temps = [("t%d" % i, np.zeros((s, s), np.uint8)) for i, s in enumerate(sides)]
+    macs = template_macs(temps, (2160, 3840))
+    assert macs[0] == 32 * 32 * (2160 - 31) * (3840 - 31)
+    for world in (1, 2, 4, 8):
+        spans = weighted_bounds(macs, world)
+        assert spans[0][0] == 0 and spans[-1][1] == 64 and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        loads = [sum(macs[a:b]) for a, b in spans]
+        assert max(loads) <= 1.1 * sum(macs) / world                      # the count split reaches 2.05x at world 8
+    assert weighted_bounds([], 3) == [(0, 0)] * 3 and weighted_bounds([5.0], 2) in ([(0, 0), (0, 1)], [(0, 1), (1, 1)])
+    assert template_macs([("a", np.zeros((10, 20, 3), np.uint8))], (100, 200, 3), searchBox=(5, 5, 50, 40)) == [3.0 * 200 * 31 * 31]
+
+
 def test_sharded_match_templates_world2(tmp_path, golden):
     import pickle
     import torch.multiprocessing as mp
@@ -62,6 +87,15 @@ def test_sharded_match_templates_world2(tmp_path, golden):
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     res = [pickle.load(open(tmp_path / ("rank%d.pkl" % r), "rb")) for r in range(2)]
     assert res[0] == res[1]                                    # replicated NMS -> identical on every rank
+    from oracle import golden_cases as gc, mtm_port
+    kind, temps, img, kw = gc.build("synth_mixed")
+    images = [img, np.ascontiguousarray(img[::-1]), np.ascontiguousarray(img[:, ::-1])]
+    for name, ims in (("batch3", images), ("batch1", images[:1])):
+        got = res[0].pop(name)
+        want = [mtm_port.match_templates(temps, im, **kw) for im in ims]
+        assert len(got) == len(want)
+        for g, w in zip(got, want):
+            assert [(a[0], a[1], a[2]) for a in g] == [(b[0], tuple(b[1]), float(b[2])) for b in w]
     for name, got in res[0].items():
         want = [(r[0], tuple(r[1]), r[2]) for r in golden[name]]
         assert [(g[0], g[1]) for g in got] == [(w[0], w[1]) for w in want], name
