@@ -193,6 +193,7 @@ def matchTemplatesPyramid(listTemplates, image, downscale=4, method=TM_CCOEFF_NO
             raw = ctx.match_templates_collect(slot)
             refined[k] = None if raw is None else _to_hits(raw, [names[t]], x0 + xOffset, y0 + yOffset)
 
+        resident = None                                # template whose full-resolution pixels are the context's current set
         try:
             for n, k in enumerate(sorted(range(len(coarse)), key=lambda q: coarse[q][0])):
                 slot = n % depth
@@ -200,7 +201,9 @@ def matchTemplatesPyramid(listTemplates, image, downscale=4, method=TM_CCOEFF_NO
                     collect(slot)
                 t, x0, y0, bw, bh = region(k)
                 ctx.set_image_roi(x0, y0, bw, bh)
-                ctx.set_templates([arrays[t]])
+                if t != resident:
+                    ctx.set_templates([arrays[t]])
+                    resident = t
                 ctx.match_templates_async(method, 1, score_threshold, maxOverlap, slot)
                 pending[slot] = (k, t, x0, y0)
         finally:
