@@ -79,11 +79,43 @@ def match_templates_augmented(templates, image, transforms, **kw):
     return mtm_port.match_templates(expand_templates(templates, transforms), image, **kw)
 
 
+def reference_augmented(ref, templates, image, transforms, **kw):
+    """Tutorial2 cell 15 + cell 17 with the unmodified reference: numpy builds the list, ``MTM.matchTemplates`` searches it."""
+    return ref.matchTemplates(expand_templates(templates, transforms), image, **kw)
+
+
+class _PortImpl:
+    """The two reference entry points the specification is written in, served by the CPU port."""
+
+    @staticmethod
+    def matchTemplates(templates, image, method, N_object, score_threshold, maxOverlap, searchBox=None, workers=None):
+        return mtm_port.match_templates(templates, image, method=method, N_object=N_object, score_threshold=score_threshold,
+                                        maxOverlap=maxOverlap, searchBox=searchBox, workers=workers)
+
+    NMS = staticmethod(mtm_port.nms)
+
+
+class ReferenceImpl:
+    """Adapter over the UNMODIFIED reference package (``oracle/ref_loader.py``; build container only):
+    ``MTM.matchTemplates`` (MTM/__init__.py:247) and ``MTM.NMS`` (MTM/NMS.py:20)."""
+
+    def __init__(self, ref):
+        self.ref = ref
+
+    def matchTemplates(self, templates, image, method, N_object, score_threshold, maxOverlap, searchBox=None, workers=None):
+        return self.ref.matchTemplates(templates, image, method=method, N_object=N_object, score_threshold=score_threshold,
+                                       maxOverlap=maxOverlap, searchBox=searchBox)
+
+    def NMS(self, hits, scoreThreshold, sortAscending, N_object, maxOverlap):
+        return self.ref.NMS(hits, scoreThreshold, sortAscending, N_object, maxOverlap)
+
+
 def match_templates_pyramid(templates, image, downscale=4, method=cv2.TM_CCOEFF_NORMED, N_object=INF,
                             score_threshold=0.5, maxOverlap=0.25, searchBox=None, refine=True,
-                            coarse_threshold=None, workers=None):
+                            coarse_threshold=None, workers=None, impl=_PortImpl):
     """Coarse search on the INTER_AREA-reduced pair, then full-resolution re-localisation of every coarse hit
-    inside a search box of +-downscale pixels (``N_object=1``), then ``NMS``.  See the product docstring."""
+    inside a search box of +-downscale pixels (``N_object=1``), then ``NMS``.  See the product docstring.
+    ``impl`` supplies ``matchTemplates`` / ``NMS``: the CPU port (default) or the unmodified reference."""
     f = int(downscale)
     if method == 0:
         raise ValueError("The method TM_SQDIFF is not supported. Use TM_SQDIFF_NORMED instead.")
@@ -96,8 +128,7 @@ def match_templates_pyramid(templates, image, downscale=4, method=cv2.TM_CCOEFF_
     H, W = image.shape[:2]
     small_image = cv_area_downscale(image, f)
     small_templates = [(i, cv_area_downscale(entry[1], f)) for i, entry in enumerate(templates)]
-    coarse = mtm_port.match_templates(small_templates, small_image, method=method, N_object=N_object,
-                                      score_threshold=coarse_threshold, maxOverlap=maxOverlap, workers=workers)
+    coarse = impl.matchTemplates(small_templates, small_image, method, N_object, coarse_threshold, maxOverlap, workers=workers)
     if not refine:
         return [(templates[t][0], (x * f + x_off, y * f + y_off, w * f, h * f), s) for t, (x, y, w, h), s in coarse]
     refined = []
@@ -106,7 +137,7 @@ def match_templates_pyramid(templates, image, downscale=4, method=cv2.TM_CCOEFF_
         th, tw = full.shape[:2]
         x0, y0 = max(0, x * f - f), max(0, y * f - f)
         x1, y1 = min(W, x * f + tw + f), min(H, y * f + th + f)
-        hit = mtm_port.match_templates([(name, full)], image, method=method, N_object=1, score_threshold=score_threshold,
-                                       maxOverlap=maxOverlap, searchBox=(x0, y0, x1 - x0, y1 - y0), workers=1)
+        hit = impl.matchTemplates([(name, full)], image, method, 1, score_threshold, maxOverlap,
+                                  searchBox=(x0, y0, x1 - x0, y1 - y0), workers=1)
         refined.extend((lbl, (bx + x_off, by + y_off, bw_, bh_), sc) for lbl, (bx, by, bw_, bh_), sc in hit)
-    return mtm_port.nms(refined, score_threshold, method == 1, N_object, maxOverlap)
+    return impl.NMS(refined, score_threshold, method == 1, N_object, maxOverlap)

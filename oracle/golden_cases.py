@@ -113,6 +113,43 @@ def build(name):
     raise KeyError(name)
 
 
+def build_f3(name):
+    """Recipes of the SURVEY 8 f3 golden cases (tutorial user code run with the unmodified reference).
+    Returns ("aug", templates, transforms, image, kwargs) or ("pyr", templates, image, downscale, refine, kwargs)."""
+    from . import synth
+    inf = float("inf")
+    if name in ("aug_rot4", "aug_flips_n3"):
+        rng = np.random.default_rng(31)
+        base = [synth.make_template(rng, 24, 40), synth.make_template(rng, 32, 32)]
+        planted = [np.ascontiguousarray(np.rot90(base[0], 1)), base[1], np.ascontiguousarray(np.rot90(base[1], 2)), base[0]]
+        img, _ = synth.make_scene(300, 420, planted, 2, seed=31)
+        temps = [("a", base[0]), ("b", base[1])]
+        if name == "aug_rot4":
+            return "aug", temps, ("identity", "rot90", "rot180", "rot270"), img, dict(
+                method=5, N_object=inf, score_threshold=0.5, maxOverlap=0.25)
+        return "aug", temps, ("fliplr", "identity", "flipud", "transpose", "antitranspose"), img, dict(
+            method=5, N_object=3, score_threshold=0.4, maxOverlap=0.1)
+    if name in ("pyr_f4_refined", "pyr_f4_coarse", "pyr_f3_n5", "pyr_f2_sqdiff_n1"):
+        rng = np.random.default_rng(3)
+        ts = [synth.make_template(rng, 64, 64), synth.make_template(rng, 48, 80)]
+        img, _ = synth.make_scene(600, 800, ts, 4, seed=3)
+        temps = [("a", ts[0]), ("b", ts[1])]
+        if name == "pyr_f4_refined":
+            return "pyr", temps, img, 4, True, dict(method=5, N_object=inf, score_threshold=0.5, maxOverlap=0.25)
+        if name == "pyr_f4_coarse":
+            return "pyr", temps, img, 4, False, dict(method=5, N_object=inf, score_threshold=0.4, maxOverlap=0.25)
+        if name == "pyr_f3_n5":
+            return "pyr", temps, img, 3, True, dict(method=5, N_object=5, score_threshold=0.5, maxOverlap=0.1)
+        return "pyr", temps, img, 2, True, dict(method=1, N_object=1, score_threshold=0.3, maxOverlap=0.25)
+    if name == "pyr_fish_f4":
+        img = fish()
+        return "pyr", [("head", img[842:842 + 184, 528:528 + 196])], img, 4, True, dict(
+            method=5, N_object=1, score_threshold=0.5, maxOverlap=0.25)
+    raise KeyError(name)
+
+
+F3_CASES = ["aug_rot4", "aug_flips_n3", "pyr_f4_refined", "pyr_f4_coarse", "pyr_f3_n5", "pyr_f2_sqdiff_n1", "pyr_fish_f4"]
+
 CASES = ["t3_full", "t3_searchbox", "t3_downscaled",
          "c1_fish256_n1", "c1_fish256_inf", "c1_fish256_find", "c1_fish256_map",
          "fish512_multi", "fish512_multi_n3", "fish512_find",

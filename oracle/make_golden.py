@@ -7,6 +7,9 @@ Writes
 * ``tests/golden/ref_outputs.json`` -- reference outputs for every recipe in
   ``oracle/golden_cases.py`` (hit lists; for "map" cases the float32 map goes to
   ``tests/golden/<case>.npy``);
+* ``tests/golden/ref_outputs_f3.json`` -- the tutorials' augmentation / downscaling user code
+  (``oracle/augment_port.py``) run with the UNMODIFIED reference's ``matchTemplates`` / ``NMS`` on the
+  recipes of ``golden_cases.F3_CASES`` (``python -m oracle.make_golden --f3`` writes only this file);
 * records cv2/scipy/numpy versions used.
 TEST INFRASTRUCTURE; never imported by product code.
 """
@@ -21,11 +24,35 @@ def _plain(hits):
     return [[str(l), [int(v) for v in b], float(np.float32(s))] for (l, b, s) in hits]
 
 
+def make_f3():
+    import cv2
+    from . import augment_port as ap, golden_cases as gc, ref_loader
+    ref = ref_loader.load()
+    out = {"_meta": {"reference_version": ref.__version__, "cv2": cv2.__version__, "numpy": np.__version__,
+                     "note": "tutorial user code (oracle/augment_port.py) on top of the unmodified reference's matchTemplates / NMS; "
+                             "peak_local_max inside the reference run is oracle/peaks.py (scikit-image absent)"}}
+    for name in gc.F3_CASES:
+        case = gc.build_f3(name)
+        if case[0] == "aug":
+            _, temps, transforms, img, kw = case
+            res = _plain(ap.reference_augmented(ref, temps, img, transforms, **kw))
+        else:
+            _, temps, img, f, refine, kw = case
+            res = _plain(ap.match_templates_pyramid(temps, img, downscale=f, refine=refine, impl=ap.ReferenceImpl(ref), **kw))
+        out[name] = res
+        print(name, len(res), file=sys.stderr)
+    with open(os.path.join(gc.GOLDEN_DIR, "ref_outputs_f3.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
 def main():
     import cv2
     import scipy
     from . import golden_cases as gc, ref_loader
     os.makedirs(gc.GOLDEN_DIR, exist_ok=True)
+    if "--f3" in sys.argv:
+        make_f3()
+        return
     fish_path = os.path.join(gc.GOLDEN_DIR, "fish_2048.npz")
     if not os.path.exists(fish_path):
         fish = cv2.imread(os.path.join(ref_loader.REF_ROOT, "images", "Fish.tif"), -1)

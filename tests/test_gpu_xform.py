@@ -182,3 +182,27 @@ def test_pyramid_equals_specification(mtm, f, refine, kw):
     if refine and kw.get("method", 5) == 5 and "N_object" not in kw:
         full = mtm_port.match_templates(labelled, img, **{k: v for k, v in kw.items() if k != "coarse_threshold"})
         assert_hits_equal(got, full)                        # and the full-resolution search finds the same objects
+
+
+def _f3_golden():
+    import json
+    import os
+    from oracle import golden_cases as gc
+    with open(os.path.join(gc.GOLDEN_DIR, "ref_outputs_f3.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("name", ["aug_rot4", "aug_flips_n3", "pyr_f4_refined", "pyr_f4_coarse", "pyr_f3_n5",
+                                  "pyr_f2_sqdiff_n1", "pyr_fish_f4"])
+def test_f3_front_ends_against_the_unmodified_reference(mtm, name):
+    """Golden vectors made by running the tutorials' user code on the UNMODIFIED reference (oracle/make_golden.py --f3)."""
+    from oracle import golden_cases as gc
+    case = gc.build_f3(name)
+    if case[0] == "aug":
+        _, temps, transforms, img, kw = case
+        got = mtm.matchTemplatesAugmented(temps, img, transforms, **kw)
+    else:
+        _, temps, img, f, refine, kw = case
+        got = mtm.matchTemplatesPyramid(temps, img, downscale=f, refine=refine, **kw)
+    want = [(w[0], tuple(w[1]), w[2]) for w in _f3_golden()[name]]
+    assert_hits_equal(got, want)

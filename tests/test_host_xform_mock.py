@@ -76,3 +76,9 @@ def test_batch_front_end_equals_loop(mock_mtm):
     with pytest.raises(ValueError, match="larger than image"):     # a bad image in the middle: slots are drained, error propagates
         mock_mtm.matchTemplatesBatch(temps, images[:2] + [images[0][:10, :10]] + images[2:], streams=2)
     assert not mock_mtm._mock.slots and not mock_mtm._mock_helpers[0].slots
+
+
+@pytest.mark.parametrize("name", ["aug_rot4", "aug_flips_n3", "pyr_f4_refined", "pyr_f4_coarse", "pyr_f3_n5",
+                                  "pyr_f2_sqdiff_n1", "pyr_fish_f4"])
+def test_f3_front_ends_against_reference_goldens(mock_mtm, name):
+    gx.test_f3_front_ends_against_the_unmodified_reference(mock_mtm, name)

@@ -1,5 +1,7 @@
 """CPU tests: pin the oracle (restated algorithms) against the golden vectors made by
 the unmodified reference, the reference's own known answers, and live cv2/scipy."""
+import os
+
 import cv2
 import numpy as np
 import pytest
@@ -230,3 +232,29 @@ def test_pyramid_port_equals_full_search_on_planted_scenes():
     for f in (2, 4):
         pyr = ap.match_templates_pyramid(labelled, img, downscale=f, score_threshold=0.5, maxOverlap=0.25)
         assert [(h[0], h[1]) for h in pyr] == [(h[0], h[1]) for h in full]
+
+
+def _f3_golden():
+    import json
+    from oracle import golden_cases as gc
+    with open(os.path.join(gc.GOLDEN_DIR, "ref_outputs_f3.json")) as f:
+        return json.load(f)
+
+
+def test_f3_port_reproduces_the_unmodified_reference():
+    """oracle/augment_port.py on the CPU port == the same tutorial user code on the UNMODIFIED reference's
+    matchTemplates / NMS (tests/golden/ref_outputs_f3.json, made by `python -m oracle.make_golden --f3`)."""
+    from oracle import augment_port as ap, golden_cases as gc
+    golden = _f3_golden()
+    for name in gc.F3_CASES:
+        case = gc.build_f3(name)
+        if case[0] == "aug":
+            _, temps, transforms, img, kw = case
+            got = ap.match_templates_augmented(temps, img, transforms, **kw)
+        else:
+            _, temps, img, f, refine, kw = case
+            got = ap.match_templates_pyramid(temps, img, downscale=f, refine=refine, **kw)
+        want = golden[name]
+        assert [(g[0], tuple(int(v) for v in g[1])) for g in got] == [(w[0], tuple(w[1])) for w in want], name
+        assert max(abs(float(g[2]) - w[2]) for g, w in zip(got, want)) <= 1e-6, name
+    assert golden["pyr_fish_f4"][0][:2] == ["head", [528, 842, 196, 184]]          # Tutorial3 cell 10, through the reference itself
