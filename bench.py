@@ -139,15 +139,20 @@ class ClockSampler:
             nv = self.nv
             masks = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
                      "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
-            inside = [smp for smp in self.samples if any(a <= smp[0] <= (b if b is not None else smp[0]) for a, b in self.windows)]
+            def within(slack):
+                return [smp for smp in self.samples
+                        if any(a - slack <= smp[0] <= (b if b is not None else smp[0]) + slack for a, b in self.windows)]
+            inside, note = within(0.0), "inside the timed regions"
+            if not inside:                     # timed regions shorter than the polling period (very small --steps)
+                inside, note = within(0.03), "within 30 ms of the timed regions (the regions are shorter than the polling period)"
             if inside:
                 bits = 0
                 for smp in inside:
                     bits |= smp[2]
                 out.update(sm_mhz=float(np.median([smp[1] for smp in inside])), samples=len(inside),
                            reasons=[nm for nm in names if bits & masks[nm]],
-                           how="NVML polled every 10 ms; samples inside the timed regions (%.0f ms in total)"
-                               % (1e3 * sum((b or a) - a for a, b in self.windows)))
+                           how="NVML polled every 10 ms; samples %s (%.0f ms in total)"
+                               % (note, 1e3 * sum((b or a) - a for a, b in self.windows)))
             return out
         if self.p is None:
             return out
