@@ -80,6 +80,25 @@ def test_mac_balanced_template_slices():
     assert template_macs([("a", np.zeros((10, 20, 3), np.uint8))], (100, 200, 3), searchBox=(5, 5, 50, 40)) == [3.0 * 200 * 31 * 31]
 
 
+def test_weighted_bounds_is_optimal_on_small_lists():
+    import itertools
+    import random
+    import MTM  # noqa: F401
+    from mtm_b200.sharded import weighted_bounds
+    random.seed(0)
+    for _ in range(150):
+        n, world = random.randint(0, 8), random.randint(1, 4)
+        w = [random.randint(1, 50) for _ in range(n)]
+        spans = weighted_bounds(w, world)
+        assert len(spans) == world and spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] and a[0] <= a[1] for a, b in zip(spans, spans[1:] + [(n, n)]))
+        cost = max(sum(w[a:b]) for a, b in spans)
+        best = min(max(sum(w[b[i]:b[i + 1]]) for i in range(world))
+                   for cuts in itertools.combinations_with_replacement(range(n + 1), world - 1)
+                   for b in [[0] + list(cuts) + [n]])
+        assert cost == best, (w, world, spans)
+
+
 def test_sharded_match_templates_world2(tmp_path, golden):
     import pickle
     import torch.multiprocessing as mp
