@@ -162,3 +162,31 @@ def test_header_is_plain_c(tmp_path):
     subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
                     "-L", lib_dir, "-lmtm_b200", "-Wl,-rpath," + lib_dir], check=True, capture_output=True)
     assert subprocess.run([str(exe)]).returncode == 0
+
+
+def test_draw_helpers_equal_the_reference(mtm):
+    """drawBoxesOnRGB / drawBoxesOnGray (MTM/__init__.py:299-391): pixel-identical to the unmodified reference when it is
+    present (build container), and to the cv2 primitives it calls otherwise."""
+    import cv2
+    from oracle import ref_loader
+    rng = np.random.default_rng(2)
+    gray = rng.integers(0, 256, (120, 160), dtype=np.uint8)
+    rgb = rng.integers(0, 256, (120, 160, 3), dtype=np.uint8)
+    hits = [("head", (10, 20, 40, 30), np.float32(0.9)), ("tail", (90, 50, 50, 60), np.float32(0.7))]
+    ref = ref_loader.load() if ref_loader.available() else None
+    for image in (gray, rgb):
+        for kw in (dict(), dict(boxThickness=3, showLabel=True, labelScale=0.7)):
+            ours_rgb, ours_gray = mtm.drawBoxesOnRGB(image, hits, **kw), mtm.drawBoxesOnGray(image, hits, **kw)
+            assert ours_rgb.shape == (120, 160, 3) and ours_gray.shape == (120, 160)
+            assert not np.shares_memory(ours_rgb, image) and not np.shares_memory(ours_gray, image)
+            if ref is not None:
+                assert np.array_equal(ours_rgb, ref.drawBoxesOnRGB(image, hits, **kw))
+                assert np.array_equal(ours_gray, ref.drawBoxesOnGray(image, hits, **kw))
+            else:
+                want = cv2.cvtColor(image, cv2.COLOR_GRAY2RGB) if image.ndim == 2 else image.copy()
+                for label, (x, y, w, h), _ in hits:
+                    cv2.rectangle(want, (x, y), (x + w, y + h), color=(255, 255, 0), thickness=kw.get("boxThickness", 2))
+                    if kw.get("showLabel"):
+                        cv2.putText(want, text=label, org=(x, y), fontFace=cv2.FONT_HERSHEY_SIMPLEX, fontScale=kw["labelScale"],
+                                    color=(255, 255, 0), lineType=cv2.LINE_AA)
+                assert np.array_equal(ours_rgb, want)
