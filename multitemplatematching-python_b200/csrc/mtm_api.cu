@@ -736,6 +736,7 @@ int mtm_set_templates(mtm_ctx* ctx, int n, const void* const* pixels, const int3
     }
     // the previous upload may still be reading the pinned staging buffers
     MTM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->n_tmpl = 0; ctx->geometry_valid = false;          // a failed upload leaves "no templates set", not a half-updated list
     ctx->h_meta.assign(n, TmplMeta{});
     size_t total = 0;
     for (int t = 0; t < n; ++t) {
@@ -809,6 +810,7 @@ int mtm_set_templates_masked(mtm_ctx* ctx, int n, const void* const* pixels, con
     const int esz = dtype == MTM_F32 ? 4 : 1;
     MTM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->tmpl_hash_valid = false;
+    ctx->n_tmpl = 0; ctx->geometry_valid = false;          // a failed upload leaves "no templates set", not a half-updated list
     ctx->h_meta.assign(n, TmplMeta{});
     size_t total = 0;                                        // bytes of the float32 arenas (T*M^2 and M^2)
     for (int t = 0; t < n; ++t) {
@@ -894,6 +896,7 @@ int mtm_set_templates_transformed(mtm_ctx* ctx, int n, const void* const* pixels
     MTM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     MTM_TRY(reserve_pinned(ctx, ctx->h_tmpl_stage, ctx->tmpl_stage_cap, raw_total + 64));
     MTM_TRY(reserve_pinned(ctx, ctx->h_geom, ctx->geom_cap, (size_t)n_out));
+    ctx->n_tmpl = 0; ctx->geometry_valid = false;          // a failed upload leaves "no templates set", not a half-updated list
     ctx->h_meta.assign(n_out, TmplMeta{});
     std::vector<XformDesc> descs((size_t)n_out);
     size_t src_off = 0, total = 0;
