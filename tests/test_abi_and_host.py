@@ -190,3 +190,55 @@ def test_draw_helpers_equal_the_reference(mtm):
                         cv2.putText(want, text=label, org=(x, y), fontFace=cv2.FONT_HERSHEY_SIMPLEX, fontScale=kw["labelScale"],
                                     color=(255, 255, 0), lineType=cv2.LINE_AA)
                 assert np.array_equal(ours_rgb, want)
+
+
+def test_hit_buffer_growth_and_strided_inputs_without_a_device(mtm):
+    """Host plumbing of the ctypes layer with a stub library: MTM_ERR_CAPACITY grows the reusable hit buffer and the call
+    is repeated; the returned hits are a private copy; strided image views are passed without a host copy when their
+    rows are contiguous (the searchBox crop of MTM/__init__.py:140-144) and copied otherwise."""
+    import ctypes
+    import threading
+    from mtm_b200 import _native
+
+    class Stub:
+        def __init__(self):
+            self.calls = []
+
+        def mtm_find_matches(self, h, method, n_object, thr, buf, cap, n_ptr):
+            self.calls.append(cap)
+            need = 10000
+            n_ptr._obj.value = need
+            if cap < need:
+                return _native.MTM_ERR_CAPACITY
+            arr = np.ctypeslib.as_array(ctypes.cast(buf, ctypes.POINTER(ctypes.c_uint8)), shape=(cap * 24,)).view(_native.HIT_DTYPE)
+            arr[:need]["x"] = np.arange(need)
+            return _native.MTM_OK
+
+        def mtm_set_image(self, h, ptr, H, W, C, code, stride):
+            self.calls.append(("image", ptr.value, H, W, C, code, stride))
+            return _native.MTM_OK
+
+        def mtm_last_error(self, h):
+            return b"stub"
+
+    ctx = _native.Context.__new__(_native.Context)
+    ctx._lib, ctx._h, ctx.device, ctx.lock = Stub(), ctypes.c_void_p(1), 0, threading.RLock()
+    ctx.close = lambda: None
+    first = ctx.find_matches(5, -1, 0.5)
+    assert ctx._lib.calls == [4096, 10000] and len(first) == 10000 and first["x"][-1] == 9999
+    second = ctx.find_matches(5, -1, 0.5)
+    assert ctx._lib.calls == [4096, 10000, 10000]                      # the grown buffer is kept
+    second["x"][0] = -7
+    assert first["x"][0] == 0 and not np.shares_memory(first, second)     # results are private copies
+    ctx._lib.calls.clear()
+    img = np.zeros((50, 64), np.uint8)
+    ctx.set_image(img[5:25, 8:40])                                        # rows contiguous inside: no copy, row stride 64
+    tag, ptr, H, W, C, code, stride = ctx._lib.calls[-1]
+    assert (H, W, C, code, stride) == (20, 32, 1, _native.MTM_U8, 64) and ptr == img[5:25, 8:40].ctypes.data
+    ctx.set_image(img[:, ::2])                                            # strided inside a row: compact copy
+    tag, ptr, H, W, C, code, stride = ctx._lib.calls[-1]
+    assert (H, W, stride) == (50, 32, 32)
+    rgb = np.zeros((30, 40, 3), np.float32)
+    ctx.set_image(rgb[2:12, 3:13])
+    tag, ptr, H, W, C, code, stride = ctx._lib.calls[-1]
+    assert (H, W, C, code, stride) == (10, 10, 3, _native.MTM_F32, 40 * 3 * 4)
