@@ -110,6 +110,48 @@ def _dtype_code(arr):
     raise TypeError("unsupported dtype %s" % arr.dtype)
 
 
+class DeviceArray:
+    """An image that already lives in HBM, seen through ``__cuda_array_interface__`` (PyTorch CUDA tensors, CuPy
+    arrays, ...).  Exposes just what the host layer reads from an image (``shape``, ``dtype``, ``ndim``, ``strides``) and
+    the 2-D slicing of the searchBox crop (MTM/__init__.py:140-144); the pixels are never touched on the host.
+    The producer's work on the array must be complete before it is handed over (synchronise its stream)."""
+
+    def __init__(self, ptr, shape, dtype, strides, owner):
+        self.ptr, self.shape, self.dtype, self.owner = int(ptr), tuple(int(v) for v in shape), np.dtype(dtype), owner
+        if strides is None:                          # C-contiguous
+            strides, step = [], self.dtype.itemsize
+            for extent in reversed(self.shape):
+                strides.append(step)
+                step *= extent
+            strides = strides[::-1]
+        self.strides = tuple(int(v) for v in strides)
+        self.ndim = len(self.shape)
+
+    @classmethod
+    def wrap(cls, obj):
+        cai = obj.__cuda_array_interface__
+        if cai.get("mask") is not None:
+            raise ValueError("masked device arrays are not supported")
+        ptr, read_only = cai["data"]
+        return cls(ptr, cai["shape"], np.dtype(cai["typestr"]), cai.get("strides"), obj)
+
+    def __getitem__(self, key):
+        if not (isinstance(key, tuple) and len(key) == 2 and all(isinstance(k, slice) for k in key)) or self.ndim < 2:
+            raise TypeError("device images support only image[y0:y1, x0:x1] slicing")
+        (y0, y1, ys), (x0, x1, xs) = key[0].indices(self.shape[0]), key[1].indices(self.shape[1])
+        if ys != 1 or xs != 1:
+            raise TypeError("device images support only unit-step slices")
+        shape = (max(y1 - y0, 0), max(x1 - x0, 0)) + self.shape[2:]
+        return DeviceArray(self.ptr + y0 * self.strides[0] + x0 * self.strides[1], shape, self.dtype, self.strides, self.owner)
+
+
+def as_image(image):
+    """numpy arrays pass through; objects exposing ``__cuda_array_interface__`` become a ``DeviceArray`` view."""
+    if isinstance(image, (np.ndarray, DeviceArray)) or not hasattr(image, "__cuda_array_interface__"):
+        return image
+    return DeviceArray.wrap(image)
+
+
 class Context:
     """One CUDA stream + device workspaces on one GPU.  Not re-entrant (guarded by a lock)."""
 
@@ -186,6 +228,16 @@ class Context:
         return image, image.shape[0], image.shape[1], C, image.strides[0]
 
     def set_image(self, image):
+        if isinstance(image, DeviceArray):           # pixels already in HBM: device-to-device copy into the tile layout, no PCIe traffic
+            if image.ndim not in (2, 3):
+                raise ValueError("image must be 2-D (grayscale) or 3-D (H, W, C)")
+            C = 1 if image.ndim == 2 else image.shape[2]
+            item = image.dtype.itemsize
+            if image.strides[1] != item * C or (image.ndim == 3 and image.strides[2] != item) or image.strides[0] < image.shape[1] * C * item:
+                raise ValueError("device images must have contiguous rows (strides %r)" % (image.strides,))
+            self._keep = image
+            self.set_image_device(image.ptr, image.shape[0], image.shape[1], C, image.strides[0], _dtype_code(image))
+            return
         arr, H, W, C, stride = self._image_view(image)
         self._check(self._lib.mtm_set_image(self._h, _P(arr.ctypes.data), H, W, C, _dtype_code(arr), stride))
 

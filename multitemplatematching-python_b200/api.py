@@ -34,10 +34,27 @@ def _dtype_policy(template, image, mask):
         raise ValueError("64-bit images not supported, max 32-bit")
     if not (template.dtype == "uint8" and image.dtype == "uint8"):
         template = np.float32(template)
-        image = np.float32(image)
+        if not isinstance(image, _native.DeviceArray):            # device images: checked by _device_image_dtypes
+            image = np.float32(image)
         if mask is not None:
             mask = np.float32(mask)
     return template, image, mask
+
+
+def _device_image_dtypes(image, templates, usable_mask):
+    """An image that is already in HBM (``_native.DeviceArray``) is never cast on the host: the combinations the
+    reference would cast (MTM/__init__.py:71-74) or mask are only accepted when no cast of the IMAGE is needed."""
+    if not isinstance(image, _native.DeviceArray):
+        return
+    if image.dtype == "float64":
+        raise ValueError("64-bit images not supported, max 32-bit")
+    all_u8 = image.dtype == np.uint8 and all(t.dtype == np.uint8 for t in templates)
+    all_u16 = image.dtype == np.uint16 and image.ndim == 2 and not usable_mask and \
+        all(t.dtype == np.uint16 and t.ndim == 2 for t in templates)
+    if not (all_u8 or all_u16 or image.dtype == np.float32):
+        raise NotImplementedError("device-resident %s image with %s templates: the reference's float32 cast of the image is not done "
+                                  "on the host; pass a float32 (or matching uint8 / 2-D uint16) device image"
+                                  % (image.dtype, sorted({str(t.dtype) for t in templates})))
 
 
 def _mask_policy(template, mask, method):
@@ -63,15 +80,18 @@ def computeScoreMap(template, image, method=TM_CCOEFF_NORMED, mask=None, *, cont
     Note the argument order (template, image), the reverse of ``cv2.matchTemplate``.
     Returns a float32 array of shape (H-h+1, W-w+1).
     """
+    image = _native.as_image(image)
+    _device_image_dtypes(image, [template], mask is not None and method in (0, 3))
     template16, image16 = template, image
     template, image, mask = _dtype_policy(template, image, mask)
     mask = _mask_policy(template, mask, method)
     if template.ndim != image.ndim or any(t > i for t, i in zip(template.shape, image.shape)) \
             or template.shape[2:] != image.shape[2:]:
         raise _cv_error("matchTemplate: template must not be larger than the image and must have the same channels")
-    _require_gpu_support(image, [template], mask)
     if mask is None and _all_uint16(image16, [template16]):
         image, template = image16, template16              # MTM_U16: see _prepare
+    else:
+        _require_gpu_support(image, [template], mask)
     ctx = context or _native.default_context()
     with ctx.lock:
         ctx.set_image(image)
@@ -138,6 +158,8 @@ def _prepare(listTemplates, image, method):
             arrays.append(template)
         else:
             return names, arrays, image, [None] * len(arrays)
+    _device_image_dtypes(image, [t[1] for t in listTemplates],
+                         method in (0, 3) and any(len(t) >= 3 and t[2] is not None for t in listTemplates))
     names, arrays, masks = [], [], []
     img = image
     img_f32 = None                     # the image is cast at most once (the reference casts it once per template)
@@ -183,7 +205,7 @@ def _prepare(listTemplates, image, method):
 
 
 def _all_uint16(image, templates):
-    return (isinstance(image, np.ndarray) and image.dtype == np.uint16 and image.ndim == 2 and
+    return (isinstance(image, (np.ndarray, _native.DeviceArray)) and image.dtype == np.uint16 and image.ndim == 2 and
             all(isinstance(t, np.ndarray) and t.dtype == np.uint16 and t.ndim == 2 for t in templates))
 
 
@@ -211,7 +233,7 @@ def findMatches(listTemplates, image, method=TM_CCOEFF_NORMED, N_object=_INF, sc
     thread-completion order, so any order it can produce is a permutation of this
     one), each template's hits in the order its peak finder yields them.
     """
-    image, xOffset, yOffset = _validate_search(listTemplates, image, N_object, searchBox)
+    image, xOffset, yOffset = _validate_search(listTemplates, _native.as_image(image), N_object, searchBox)
     if len(listTemplates) == 0:
         return []
     names, arrays, img, masks = _prepare(listTemplates, image, method)
@@ -236,6 +258,7 @@ def matchTemplates(listTemplates, image, method=TM_CCOEFF_NORMED, N_object=_INF,
         # the reference searches first and rejects TM_SQDIFF afterwards (MTM/__init__.py:289-292)
         findMatches(listTemplates, image, method, N_object, score_threshold, searchBox, context=context)
         raise ValueError("The method TM_SQDIFF is not supported. Use TM_SQDIFF_NORMED instead.")
+    image = _native.as_image(image)
     crop, xOffset, yOffset = _validate_search(listTemplates, image, N_object, searchBox)
     if len(listTemplates) == 0:
         return []
@@ -294,7 +317,7 @@ def matchTemplatesBatch(listTemplates, images, method=TM_CCOEFF_NORMED, N_object
             stack.enter_context(c.lock)
         try:
             for i, image in enumerate(images):
-                crop, xOffset, yOffset = _validate_search(listTemplates, image, N_object, searchBox)
+                crop, xOffset, yOffset = _validate_search(listTemplates, _native.as_image(image), N_object, searchBox)
                 nm, arrays, img, masks = _prepare(listTemplates, crop, method)
                 k = i % n_streams
                 key = (k, (i // n_streams) % depth)

@@ -117,7 +117,7 @@ def matchTemplatesAugmented(listTemplates, image, transforms=("identity", "rot90
                 expanded_shapes.append((_label(entry[0], t), _ShapeOnly((shp[1], shp[0]) + shp[2:] if t in _SWAPS else shp)))
         else:
             expanded_shapes.append(entry)              # rejected by the reference's check below
-    crop, xOffset, yOffset = _validate_search(expanded_shapes, image, N_object, searchBox)
+    crop, xOffset, yOffset = _validate_search(expanded_shapes, _native.as_image(image), N_object, searchBox)
     if len(listTemplates) == 0:
         return []
     arrays = _device_template_set(listTemplates, crop, "matchTemplatesAugmented")
@@ -158,6 +158,8 @@ def matchTemplatesPyramid(listTemplates, image, downscale=4, method=TM_CCOEFF_NO
         raise ValueError("Maximal overlap between bounding box is in range [0-1]")
     if method == 0:
         raise ValueError("The method TM_SQDIFF is not supported. Use TM_SQDIFF_NORMED instead.")
+    if not isinstance(image, np.ndarray) and hasattr(image, "__cuda_array_interface__"):
+        raise NotImplementedError("matchTemplatesPyramid takes host images (the reduction starts from the uploaded full-resolution pixels)")
     crop, xOffset, yOffset = _validate_search(listTemplates, image, N_object, searchBox)
     if len(listTemplates) == 0:
         return []

@@ -34,6 +34,18 @@ class MockContext:
 
     # -- inputs ---------------------------------------------------------------------
     def set_image(self, image):
+        from mtm_b200._native import DeviceArray
+        if isinstance(image, DeviceArray):           # CPU tests hand over HOST pointers dressed as device arrays
+            self.calls.append("set_image_device")
+            import ctypes
+            C = 1 if image.ndim == 2 else image.shape[2]
+            item = image.dtype.itemsize
+            assert image.strides[1] == item * C and image.strides[0] >= image.shape[1] * C * item
+            rows = image.shape[0]
+            raw = np.ctypeslib.as_array(ctypes.cast(image.ptr, ctypes.POINTER(ctypes.c_uint8)), shape=((rows - 1) * image.strides[0] + image.shape[1] * C * item,))
+            self.image = np.stack([raw[r * image.strides[0]: r * image.strides[0] + image.shape[1] * C * item].view(image.dtype).reshape(image.shape[1:])
+                                   for r in range(rows)]).copy()
+            return
         self.calls.append("set_image")
         self.image = np.ascontiguousarray(image)
 

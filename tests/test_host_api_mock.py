@@ -78,3 +78,55 @@ def test_sharded_entry_points_without_a_process_group(mock_mtm):
     import test_gpu_sharded as gs
     gs.test_sharded_world1_equals_match_templates(mock_mtm)
     gs.test_batch_sharded_world1_equals_per_image_calls(mock_mtm)
+
+
+class _FakeDeviceArray:
+    """A numpy array dressed as a CUDA array (host pointer in ``__cuda_array_interface__``): lets the CPU tests drive the
+    device-image route of the host layer; the test double reads the pixels back through the pointer."""
+
+    def __init__(self, arr):
+        self._arr = arr
+        self.__cuda_array_interface__ = {"shape": arr.shape, "typestr": arr.dtype.str, "data": (arr.ctypes.data, False),
+                                         "strides": None if arr.flags.c_contiguous else arr.strides, "version": 3}
+
+
+def test_device_resident_images_take_the_device_route(mock_mtm):
+    """Objects exposing __cuda_array_interface__ (PyTorch / CuPy arrays) are searched where they are: same results as
+    the numpy image, searchBox crops are pointer arithmetic, and nothing is cast on the host."""
+    from mtm_b200 import _native
+    from oracle import synth
+    rng = np.random.default_rng(41)
+    temps = [("a", synth.make_template(rng, 20, 24)), ("b", synth.make_template(rng, 16, 30))]
+    img, _ = synth.make_scene(150, 200, [t[1] for t in temps], 3, seed=41)
+    shared = _native.default_context()
+    for image, ts in ((img, temps), (img.astype(np.float32), [(n, t.astype(np.float32)) for n, t in temps]),
+                      (img.astype(np.uint16) * 100, [(n, t.astype(np.uint16) * 100) for n, t in temps]),
+                      (np.stack([img, 255 - img, img[::-1]], axis=2), [(n, np.stack([t, 255 - t, t[::-1]], axis=2)) for n, t in temps])):
+        image = np.ascontiguousarray(image)
+        dev = _FakeDeviceArray(image)
+        for kw in (dict(score_threshold=0.5), dict(N_object=1), dict(score_threshold=0.5, searchBox=(13, 7, 150, 120))):
+            shared.calls.clear()
+            got = mock_mtm.matchTemplates(ts, dev, **kw)
+            assert "set_image_device" in shared.calls and "set_image" not in shared.calls
+            want = mock_mtm.matchTemplates(ts, image, **kw)
+            assert [(h[0], h[1], float(h[2])) for h in got] == [(h[0], h[1], float(h[2])) for h in want] and len(want) >= 1
+        assert np.array_equal(mock_mtm.computeScoreMap(ts[0][1], dev), mock_mtm.computeScoreMap(ts[0][1], image))
+        assert [(h[0], h[1]) for h in mock_mtm.findMatches(ts, dev)] == [(h[0], h[1]) for h in mock_mtm.findMatches(ts, image)]
+    batch = mock_mtm.matchTemplatesBatch(temps, [_FakeDeviceArray(img), img, _FakeDeviceArray(np.ascontiguousarray(img[::-1]))])
+    assert [[(h[0], h[1]) for h in hits] for hits in batch] == \
+        [[(h[0], h[1]) for h in mock_mtm.matchTemplates(temps, im)] for im in (img, img, np.ascontiguousarray(img[::-1]))]
+    aug = mock_mtm.matchTemplatesAugmented(temps, _FakeDeviceArray(img), ("identity", "rot180"))
+    assert [(h[0], h[1]) for h in aug] == [(h[0], h[1]) for h in mock_mtm.matchTemplatesAugmented(temps, img, ("identity", "rot180"))]
+    # combinations that would need the reference's float32 cast of the IMAGE are refused, not cast on the host
+    with pytest.raises(NotImplementedError, match="device-resident"):
+        mock_mtm.matchTemplates([("a", temps[0][1].astype(np.float32))], _FakeDeviceArray(img))
+    with pytest.raises(NotImplementedError, match="host images"):
+        mock_mtm.matchTemplatesPyramid(temps, _FakeDeviceArray(img), downscale=2)
+    with pytest.raises(ValueError, match="64-bit"):
+        mock_mtm.matchTemplates(temps, _FakeDeviceArray(img.astype(np.float64)))
+    with pytest.raises(ValueError, match="larger than searchBox"):
+        mock_mtm.matchTemplates(temps, _FakeDeviceArray(img), searchBox=(0, 0, 10, 10))
+    view = _native.as_image(_FakeDeviceArray(img))
+    assert view[5:25, 8:40].shape == (20, 32) and view[5:25, 8:40].ptr == img[5:25, 8:40].ctypes.data and view.strides == img.strides
+    with pytest.raises(TypeError):
+        view[::2, :]
