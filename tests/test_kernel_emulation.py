@@ -1,6 +1,6 @@
 """CPU tests of device code: the SIMPLE kernels of csrc/ (no shared memory, no warp intrinsics, no PTX) are compiled
-for the host behind tests/emu/cuda_shim.h -- their source text is taken verbatim from the .cu files -- and run thread by
-thread.  Checks, bit for bit and without a GPU:
+for the host behind tests/emu/cuda_runtime.h -- their source text is taken verbatim from the .cu files -- and run on the
+CPU (serially, or one OS thread per CUDA thread when the kernel uses barriers / shuffles / shared memory).  Checks, bit for bit and without a GPU:
   * transform.cu: the 8 symmetries and the integer-factor INTER_AREA rounding against numpy / the restated OpenCV rule
     (which tests/test_oracle.py pins to the live cv2.resize);
   * ncc_tc.cu: the row-walking window-moment kernel (experiment knob MTM_B200_MOM_ROWS) writes exactly what the default
@@ -36,22 +36,22 @@ def emu(tmp_path_factory):
         pytest.skip("no g++")
     xf = open(os.path.join(CSRC, "transform.cu")).read()
     tc = open(os.path.join(CSRC, "ncc_tc.cu")).read()
-    epi = open(os.path.join(CSRC, "ncc_epilogue.cuh")).read()
-    internal = open(os.path.join(CSRC, "mtm_internal.cuh")).read()
-    parts = ['#include "cuda_shim.h"', '#include "mtm_b200.h"',
-             "struct SatView { const uint32_t* s; const unsigned long long* q; int64_t pitch; int64_t plane; };",
-             _function(internal, "struct XformDesc {") + ";", _function(internal, "struct SizeDesc {") + ";",
-             _function(epi, "__device__ __forceinline__ uint32_t sat_window_s("),
+    ws = open(os.path.join(CSRC, "window_stats.cu")).read()
+    pt = open(os.path.join(CSRC, "ncc_points.cu")).read()
+    parts = ['#include "cuda_runtime.h"', '#include "mtm_internal.cuh"', '#include "ncc_epilogue.cuh"',
              xf[xf.index("namespace {"):xf.index("}  // namespace") + 1],          # all device code of transform.cu
+             ws[ws.index("namespace {"):ws.index("}  // namespace") + 1],          # ... of window_stats.cu
+             pt[pt.index("namespace {"):pt.index("}  // namespace") + 1],          # ... of ncc_points.cu
              "namespace {",
              _function(tc, "template <bool STREAM>\n__global__ void window_moments_kernel("),
              _function(tc, "template <int C>\n__global__ void __launch_bounds__(256)\nwindow_moments_rows_kernel("),
              "}",
              r'''
+extern "C" int emu_sizeof_tmplmeta() { return (int)sizeof(TmplMeta); }
 extern "C" void emu_transform(const uint8_t* src, uint8_t* dst, const XformDesc* descs, int n_out, int C, int dtype, int f, int grid_x)
 {
     const float scale = 1.f / (float)(f * f);
-    dim3 g; g.x = grid_x; g.y = n_out; dim3 b; b.x = 256;
+    dim3 g(grid_x, n_out), b(256);
     if (dtype == MTM_U8) emu_launch(g, b, [&] { transform_kernel<uint8_t>(src, dst, descs, C, f, scale); });
     else if (dtype == MTM_U16) emu_launch(g, b, [&] { transform_kernel<uint16_t>(src, dst, descs, C, f, scale); });
     else emu_launch(g, b, [&] { transform_kernel<float>(src, dst, descs, C, f, scale); });
@@ -60,24 +60,54 @@ extern "C" void emu_moments(int rows_form, const uint32_t* sat_s, const uint32_t
                             int n_sizes, int C, uint32_t* S, float* rsD, int64_t mom_plane, int gx, int gy)
 {
     SatView sv{sat_s, nullptr, pitch, plane};
-    dim3 b; b.x = 256;
+    dim3 b(256);
     if (!rows_form) {
-        dim3 g; g.x = gx; g.y = n_sizes;
-        emu_launch(g, b, [&] { window_moments_kernel<false>(sv, sat_q32, sizes, S, rsD, C, mom_plane); });
+        emu_launch(dim3(gx, n_sizes), b, [&] { window_moments_kernel<false>(sv, sat_q32, sizes, S, rsD, C, mom_plane); });
         return;
     }
-    dim3 g; g.x = gx; g.y = gy; g.z = n_sizes;
+    dim3 g(gx, gy, n_sizes);
     if (C == 1) emu_launch(g, b, [&] { window_moments_rows_kernel<1>(sv, sat_q32, sizes, S, rsD, mom_plane); });
     else if (C == 3) emu_launch(g, b, [&] { window_moments_rows_kernel<3>(sv, sat_q32, sizes, S, rsD, mom_plane); });
     else emu_launch(g, b, [&] { window_moments_rows_kernel<4>(sv, sat_q32, sizes, S, rsD, mom_plane); });
+}
+// launch_build_sat (window_stats.cu) with the same grids
+extern "C" void emu_build_sat(const uint8_t* img, int64_t pitch, int H, int W, int C, uint32_t* scratch, uint32_t* sat_s,
+                              unsigned long long* sat_q, uint32_t* sat_q32, int64_t sat_pitch)
+{
+    const int SP = (W + 3) / 4 * 4;
+    dim3 g1(H), b1(256);
+    switch (C) {
+        case 1: emu_launch_coop(g1, b1, [&] { sat_rows_c1_kernel(img, pitch, H, W, SP, scratch); }); break;
+        case 2: emu_launch_coop(g1, b1, [&] { sat_rows_kernel<2>(img, pitch, H, W, SP, scratch); }); break;
+        case 3: emu_launch_coop(g1, b1, [&] { sat_rows_kernel<3>(img, pitch, H, W, SP, scratch); }); break;
+        default: emu_launch_coop(g1, b1, [&] { sat_rows_kernel<4>(img, pitch, H, W, SP, scratch); }); break;
+    }
+    emu_launch_coop(dim3((W + 1 + 31) / 32, C + 1), dim3(32, 32), [&] { sat_cols_kernel(scratch, H, W, C, SP, sat_s, sat_q, sat_q32, sat_pitch); });
+}
+extern "C" void emu_tmpl_stats(const uint8_t* tmpl, TmplMeta* meta, int n, int C)
+{
+    emu_launch_coop(dim3(n), dim3(1024), [&] { tmpl_stats_kernel(tmpl, meta, C); });
+}
+extern "C" void emu_ncc_points(const uint8_t* img, int64_t pitch, int H, int C, const uint32_t* sat_s, const unsigned long long* sat_q,
+                               int64_t sat_pitch, const uint8_t* tmpl, const TmplMeta* meta, const int32_t* order, int count,
+                               int npos, float* maps, int method)
+{
+    PointsParams p{};
+    p.img = img; p.pitch = pitch;
+    p.sat.s = sat_s; p.sat.q = sat_q; p.sat.pitch = sat_pitch; p.sat.plane = (int64_t)(H + 1) * sat_pitch;
+    p.tmpl = tmpl; p.meta = meta; p.order = order; p.maps = maps; p.method = method;
+    dim3 g(npos, count), b(PT_THREADS);
+    if (C == 1) emu_launch_coop(g, b, [&] { ncc_points_kernel<1>(p); });
+    else if (C == 3) emu_launch_coop(g, b, [&] { ncc_points_kernel<3>(p); });
+    else emu_launch_coop(g, b, [&] { ncc_points_kernel<4>(p); });
 }
 ''']
     d = tmp_path_factory.mktemp("emu")
     (d / "emu.cpp").write_text("\n".join(parts))
     lib = d / "libemu.so"
-    r = subprocess.run([gxx, "-O1", "-std=c++17", "-shared", "-fPIC", "-I", os.path.join(ROOT, "tests", "emu"), "-I", os.path.join(ROOT, "include"),
-                        str(d / "emu.cpp"), "-o", str(lib)], capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr[-4000:]
+    r = subprocess.run([gxx, "-O1", "-std=c++20", "-shared", "-fPIC", "-pthread", "-I", os.path.join(ROOT, "tests", "emu"), "-I", CSRC,
+                        "-I", os.path.join(ROOT, "include"), str(d / "emu.cpp"), "-o", str(lib)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-6000:]
     return ctypes.CDLL(str(lib))
 
 
@@ -157,3 +187,140 @@ def test_row_walking_moment_kernel_equals_the_default_one(emu, channels):
     idx = y * (W - w + 1) + x
     rs = outs[0][1][idx] if channels > 1 else outs[0][0].view(np.float32)[2 * idx + 1]
     assert rs == 0.0
+
+
+TMPL_META_DTYPE = np.dtype([("map_off", "<i8"), ("mh", "<i4"), ("mw", "<i4"), ("mom_off", "<i8"), ("pix_off", "<i8"),
+                            ("h", "<i4"), ("w", "<i4"), ("wp", "<i4"), ("is_const", "<i4"), ("mean", "<f8", 4), ("sum2", "<f8"),
+                            ("norm_ccoeff", "<f8"), ("norm_plain", "<f8"), ("inv_area", "<f8"), ("isum", "<i8", 4),
+                            ("inv_sqrt_d2", "<f4"), ("pad_f", "<f4")])
+
+
+def _ptr(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def _host_sat(emu, img):
+    """launch_build_sat's two kernels on the host: (sat_s [C][H+1][pitch] u32, sat_q [H+1][pitch] u64, sat_q32, pitch)."""
+    H, W = img.shape[:2]
+    C = 1 if img.ndim == 2 else img.shape[2]
+    ipitch = (W * C + 3) // 4 * 4
+    buf = np.full(H * ipitch + 16, 0xEE, np.uint8)                           # padding bytes are garbage on purpose
+    rows = buf[:H * ipitch].reshape(H, ipitch)
+    rows[:, :W * C] = img.reshape(H, W * C)
+    SP = (W + 3) // 4 * 4
+    pitch = (W + 1 + 3) // 4 * 4
+    scratch = np.full((C + 1) * H * SP, 0xDEADBEEF, np.uint32)
+    sat_s = np.full((C, H + 1, pitch), 0xDEADBEEF, np.uint32)
+    sat_q = np.full((H + 1, pitch), 0xDEADBEEFDEADBEEF, np.uint64)
+    sat_q32 = np.full((H + 1, pitch), 0xDEADBEEF, np.uint32)
+    emu.emu_build_sat(_ptr(buf), ctypes.c_int64(ipitch), H, W, C, _ptr(scratch), _ptr(sat_s), _ptr(sat_q), _ptr(sat_q32),
+                      ctypes.c_int64(pitch))
+    return buf, ipitch, sat_s, sat_q, sat_q32, pitch
+
+
+@pytest.mark.parametrize("channels", [1, 2, 3, 4])
+@pytest.mark.parametrize("shape", [(37, 45), (64, 64), (5, 301), (70, 3)])
+def test_summed_area_kernels_on_the_host(emu, channels, shape):
+    """sat_rows_*_kernel + sat_cols_kernel (window_stats.cu) == numpy cumulative sums: u32 tables modulo 2^32, u64 table of
+    squares, zero first row and column, the low words in sat_q32."""
+    rng = np.random.default_rng(5)
+    H, W = shape
+    img = rng.integers(0, 256, (H, W, channels)).astype(np.uint8)
+    img[:H // 2] = 255                                                       # large sums early
+    _, _, sat_s, sat_q, sat_q32, _ = _host_sat(emu, img if channels > 1 else img[:, :, 0])
+    wide = img.astype(np.uint64)
+    for c in range(channels):
+        want = np.zeros((H + 1, W + 1), np.uint64)
+        want[1:, 1:] = wide[:, :, c].cumsum(0).cumsum(1)
+        assert np.array_equal(sat_s[c, :, :W + 1], (want & 0xFFFFFFFF).astype(np.uint32)), c
+    wq = np.zeros((H + 1, W + 1), np.uint64)
+    wq[1:, 1:] = (wide * wide).sum(2).cumsum(0).cumsum(1)
+    assert np.array_equal(sat_q[:, :W + 1], wq)
+    assert np.array_equal(sat_q32[:, :W + 1], (wq & 0xFFFFFFFF).astype(np.uint32))
+
+
+def _pack_templates(templates, channels):
+    """The template arena of mtm_set_templates: rows padded with zeros to a multiple of 4 bytes, 16-byte aligned starts."""
+    meta = np.zeros(len(templates), TMPL_META_DTYPE)
+    chunks, off = [], 0
+    for k, t in enumerate(templates):
+        h, w = t.shape[:2]
+        wp = (w * channels + 3) // 4 * 4
+        rows = np.zeros((h, wp), np.uint8)
+        rows[:, :w * channels] = t.reshape(h, w * channels)
+        meta[k]["pix_off"], meta[k]["h"], meta[k]["w"], meta[k]["wp"] = off, h, w, wp
+        size = (h * wp + 15) // 16 * 16
+        chunks.append(np.concatenate([rows.ravel(), np.zeros(size - h * wp, np.uint8)]))
+        off += size
+    return np.concatenate(chunks + [np.zeros(16, np.uint8)]), meta
+
+
+@pytest.mark.parametrize("channels", [1, 3, 4])
+def test_template_statistics_kernel_on_the_host(emu, channels):
+    """tmpl_stats_kernel (window_stats.cu): the word/byte-mask sums give OpenCV's meanStdDev-derived constants exactly as
+    the oracle's epilogue derives them, and flag constant templates."""
+    assert emu.emu_sizeof_tmplmeta() == TMPL_META_DTYPE.itemsize
+    rng = np.random.default_rng(9)
+    tmpls = [rng.integers(0, 256, (h, w, channels)).astype(np.uint8) for h, w in [(7, 5), (33, 41), (1, 1), (64, 130)]]
+    tmpls.append(np.full((9, 11, channels), 200, np.uint8))                  # constant: is_const, inv_sqrt_d2 = 0
+    arena, meta = _pack_templates(tmpls, channels)
+    emu.emu_tmpl_stats(_ptr(arena), _ptr(meta), len(tmpls), channels)
+    for k, t in enumerate(tmpls):
+        m = meta[k]
+        T = t.reshape(-1, channels).astype(np.int64)
+        area = t.shape[0] * t.shape[1]
+        s, q = T.sum(0), (T * T).sum(0)
+        assert list(m["isum"][:channels]) == list(s) and not m["isum"][channels:].any()
+        inv_area = 1.0 / float(area)
+        mean = s.astype(np.float64) * inv_area
+        var = np.maximum(q.astype(np.float64) * inv_area - mean * mean, 0.0)
+        norm = 0.0
+        mean2 = 0.0
+        for c in range(channels):                                            # same summation order as the kernel
+            norm += var[c]
+            mean2 += mean[c] * mean[c]
+        sum2 = norm + mean2
+        assert m["inv_area"] == inv_area and np.array_equal(m["mean"][:channels], mean)
+        assert m["is_const"] == (1 if norm < np.finfo(np.float64).eps else 0)
+        assert m["sum2"] == sum2 / inv_area
+        assert m["norm_ccoeff"] == np.sqrt(norm) / np.sqrt(inv_area)
+        assert m["norm_plain"] == np.sqrt(sum2) / np.sqrt(inv_area)
+        d2 = int((area * q - s * s).sum())
+        assert m["inv_sqrt_d2"] == (np.float32(1.0 / np.sqrt(float(d2))) if d2 > 0 else np.float32(0))
+    assert meta[-1]["is_const"] == 1 and meta[-1]["inv_sqrt_d2"] == 0 and meta[0]["is_const"] == 0
+
+
+@pytest.mark.parametrize("channels", [1, 3, 4])
+def test_small_map_kernel_on_the_host(emu, channels):
+    """ncc_points_kernel (ncc_points.cu) end to end on the host -- summed-area tables and template statistics from their
+    own kernels, then one CTA per output pixel -- against the oracle's exact score maps, all six methods.  Covers the
+    funnel-shift rebuild of unaligned image words (every x offset modulo 4) and rows that are not a whole number of
+    words (zero-padded template words against live image bytes)."""
+    from oracle import ncc_exact
+    rng = np.random.default_rng(21)
+    H, W = 23, 30
+    img = rng.integers(0, 256, (H, W, channels)).astype(np.uint8)
+    image = img if channels > 1 else img[:, :, 0]
+    shapes = [(21, 25), (20, 27), (23, 30)]                                  # maps of 3x6, 4x4 and 1x1 positions
+    tmpls = []
+    for h, w in shapes:
+        y0, x0 = int(rng.integers(0, H - h + 1)), int(rng.integers(0, W - w + 1))
+        t = img[y0:y0 + h, x0:x0 + w].astype(np.int64) + rng.integers(-20, 21, (h, w, channels))   # a noisy crop: scores near 1
+        tmpls.append(np.clip(t, 0, 255).astype(np.uint8))
+    buf, ipitch, sat_s, sat_q, _, pitch = _host_sat(emu, image)
+    arena, meta = _pack_templates(tmpls, channels)
+    off = 0
+    for k, (h, w) in enumerate(shapes):
+        meta[k]["mh"], meta[k]["mw"], meta[k]["map_off"] = H - h + 1, W - w + 1, off
+        off += ((H - h + 1) * (W - w + 1) + 31) // 32 * 32
+    emu.emu_tmpl_stats(_ptr(arena), _ptr(meta), len(tmpls), channels)
+    order = np.array([2, 0, 1], np.int32)
+    for method in range(6):
+        maps = np.full(off, np.nan, np.float32)
+        emu.emu_ncc_points(_ptr(buf), ctypes.c_int64(ipitch), H, channels, _ptr(sat_s), _ptr(sat_q), ctypes.c_int64(pitch),
+                           _ptr(arena), _ptr(meta), _ptr(order), 3, 7, _ptr(maps), method)      # 7 CTAs stride over 18 positions
+        for k, t in enumerate(tmpls):
+            mh, mw = int(meta[k]["mh"]), int(meta[k]["mw"])
+            got = maps[int(meta[k]["map_off"]):int(meta[k]["map_off"]) + mh * mw].reshape(mh, mw)
+            want = ncc_exact.match_template_exact(image, t if channels > 1 else t[:, :, 0], method)
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (method, k, np.abs(got - want).max())
