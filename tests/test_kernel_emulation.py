@@ -38,10 +38,14 @@ def emu(tmp_path_factory):
     tc = open(os.path.join(CSRC, "ncc_tc.cu")).read()
     ws = open(os.path.join(CSRC, "window_stats.cu")).read()
     pt = open(os.path.join(CSRC, "ncc_points.cu")).read()
+    pk = open(os.path.join(CSRC, "peaks.cu")).read()
+    nm = open(os.path.join(CSRC, "nms.cu")).read()
     parts = ['#include "cuda_runtime.h"', '#include "mtm_internal.cuh"', '#include "ncc_epilogue.cuh"',
              xf[xf.index("namespace {"):xf.index("}  // namespace") + 1],          # all device code of transform.cu
              ws[ws.index("namespace {"):ws.index("}  // namespace") + 1],          # ... of window_stats.cu
              pt[pt.index("namespace {"):pt.index("}  // namespace") + 1],          # ... of ncc_points.cu
+             pk[pk.index("namespace {"):pk.index("}  // namespace") + 1],          # ... of peaks.cu
+             nm[nm.index("namespace {"):nm.index("}  // namespace") + 1],          # ... of nms.cu
              "namespace {",
              _function(tc, "template <bool STREAM>\n__global__ void window_moments_kernel("),
              _function(tc, "template <int C>\n__global__ void __launch_bounds__(256)\nwindow_moments_rows_kernel("),
@@ -100,6 +104,72 @@ extern "C" void emu_ncc_points(const uint8_t* img, int64_t pitch, int H, int C, 
     if (C == 1) emu_launch_coop(g, b, [&] { ncc_points_kernel<1>(p); });
     else if (C == 3) emu_launch_coop(g, b, [&] { ncc_points_kernel<3>(p); });
     else emu_launch_coop(g, b, [&] { ncc_points_kernel<4>(p); });
+}
+// The post-map half of mtm_find_matches / mtm_match_templates (mtm_api.cu) with launch_peaks' grids: raw peaks -> block A,
+// then the one-launch route (finalize_small_kernel) or, when it declines (> 1024 raw hits) or `force_general`, the
+// multi-launch route (sort_hits_kernel x2 + nms_kernel).  n_cand >= 0: the candidate-list route (verify_candidates_kernel).
+// Returns the hit count; *where = 0 -> hits in block A, 1 -> block B; *route = 0 one launch, 1 general.
+extern "C" int emu_postprocess(const TmplMeta* meta, int nt, const float* maps, int method, long long n_object, double thr,
+                               double max_overlap, int do_nms, int force_general, const DevHit* cand, int n_cand, int cand_cap,
+                               int cap, uint8_t* blockA, uint8_t* blockB, int32_t* nontrivial, unsigned long long* best,
+                               int32_t* keep, uint8_t* mirror, int* where, int* route)
+{
+    const int minimize = method_is_min(method) ? 1 : 0;
+    const int ascending = (method == MTM_TM_SQDIFF_NORMED) ? 1 : 0;
+    const float thr32 = (float)thr;
+    const float thr_nms = ascending ? (float)(1.0 - thr) : thr32;
+    int32_t* countA = reinterpret_cast<int32_t*>(blockA); DevHit* hitsA = reinterpret_cast<DevHit*>(blockA + MTM_HIT_HEADER);
+    int32_t* countB = reinterpret_cast<int32_t*>(blockB); DevHit* hitsB = reinterpret_cast<DevHit*>(blockB + MTM_HIT_HEADER);
+    memset(countA, 0, MTM_HIT_HEADER);
+    int64_t max_px = 0;
+    bool any2d = false, any1d = false;
+    for (int t = 0; t < nt; ++t) {
+        max_px = std::max<int64_t>(max_px, (int64_t)meta[t].mh * meta[t].mw);
+        if (meta[t].mh == 1 || meta[t].mw == 1) any1d = true; else any2d = true;
+    }
+    int bx = (int)((max_px + 4095) / 4096);
+    if (bx < 1) bx = 1;
+    if (n_object == 1) {
+        memset(best, 0, nt * sizeof(unsigned long long));
+        emu_launch_coop(dim3(bx, nt), dim3(256), [&] { argbest_kernel(meta, maps, minimize, best); });
+        emu_launch(dim3((nt + 127) / 128), dim3(128), [&] { emit_best_kernel(meta, nt, maps, best, hitsA, countA); });
+    } else if (n_cand >= 0) {
+        int32_t cc = n_cand;
+        emu_launch(dim3(4), dim3(64), [&] { verify_candidates_kernel(meta, nt, maps, cand, &cc, cand_cap, hitsA, cap, countA, nontrivial); });
+    } else {
+        memset(nontrivial, 0, nt * sizeof(int32_t));
+        const float t32 = minimize ? -thr32 : thr32;
+        const double t64 = minimize ? -thr : thr;
+        if (any2d) emu_launch_coop(dim3(bx, nt), dim3(256), [&] { peaks2d_kernel(meta, maps, t32, minimize, hitsA, cap, countA, nontrivial); });
+        if (any1d) emu_launch(dim3((nt + 63) / 64), dim3(64), [&] { peaks1d_kernel(meta, nt, maps, t32, t64, minimize, hitsA, cap, countA, nontrivial); });
+    }
+    *route = 0;
+    int declined = force_general;
+    if (!force_general) {
+        const int check_trivial = n_object != 1, presorted = n_object == 1;
+        if (do_nms) {
+            memset(countB, 0, MTM_HIT_HEADER);
+            const long long no = n_object; const float mo = (float)max_overlap;
+            if (presorted) emu_launch_coop(dim3(1), dim3(256), [&] { finalize_small_kernel<true, true>(hitsA, cap, countA, meta, nontrivial, minimize, check_trivial, hitsB, countB, thr_nms, ascending, no, mo, mirror); });
+            else emu_launch_coop(dim3(1), dim3(256), [&] { finalize_small_kernel<false, true>(hitsA, cap, countA, meta, nontrivial, minimize, check_trivial, hitsB, countB, thr_nms, ascending, no, mo, mirror); });
+            declined = countB[2];
+        } else if (n_object != 1) {
+            emu_launch_coop(dim3(1), dim3(256), [&] { finalize_small_kernel<false, false>(hitsA, cap, countA, meta, nontrivial, minimize, 1, hitsB, countB, 0.f, 0, -1ll, 0.f, mirror); });
+            declined = countA[2];
+        }
+    }
+    if (declined == 2) return -2;                               // candidate list overflow: the caller streams the maps instead
+    if (declined) {
+        *route = 1;
+        if (countA[0] > cap) return -1;                         // the library grows the hit blocks and starts over
+        if (n_object != 1) {
+            emu_launch_coop(dim3(1), dim3(1024), [&] { sort_hits_kernel(hitsA, cap, countA, meta, nontrivial, 0, minimize, 0, 1); });
+            if (do_nms) emu_launch_coop(dim3(1), dim3(1024), [&] { sort_hits_kernel(hitsA, cap, countA, meta, nontrivial, 1, minimize, ascending, 0); });
+        }
+        if (do_nms) emu_launch_coop(dim3(1), dim3(1024), [&] { nms_kernel(hitsA, cap, countA, hitsB, countB, keep, thr_nms, ascending, (long long)n_object, (float)max_overlap); });
+    }
+    *where = do_nms ? 1 : 0;
+    return do_nms ? countB[0] : countA[0];
 }
 ''']
     d = tmp_path_factory.mktemp("emu")
@@ -324,3 +394,134 @@ def test_small_map_kernel_on_the_host(emu, channels):
             got = maps[int(meta[k]["map_off"]):int(meta[k]["map_off"]) + mh * mw].reshape(mh, mw)
             want = ncc_exact.match_template_exact(image, t if channels > 1 else t[:, :, 0], method)
             assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (method, k, np.abs(got - want).max())
+
+
+DEVHIT_DTYPE = np.dtype([("tmpl", "<i4"), ("x", "<i4"), ("y", "<i4"), ("w", "<i4"), ("h", "<i4"), ("score", "<f4"), ("seq", "<i4"),
+                         ("key", "<f4")])
+
+
+def _host_postprocess(emu, maps, sizes, method, n_object, thr, max_overlap, do_nms, force_general=False, candidates=None,
+                      cand_cap=32768, cap=4096):
+    """Peak extraction [+ sort + NMS] kernels on the host for a list of score maps; returns ([(tmpl, (x, y, w, h), score)], route)."""
+    meta = np.zeros(len(maps), TMPL_META_DTYPE)
+    off = 0
+    for k, (m, (h, w)) in enumerate(zip(maps, sizes)):
+        meta[k]["mh"], meta[k]["mw"], meta[k]["map_off"], meta[k]["h"], meta[k]["w"] = m.shape[0], m.shape[1], off, h, w
+        off += (m.size + 31) // 32 * 32
+    flat = np.full(off + 32, np.nan, np.float32)
+    for k, m in enumerate(maps):
+        flat[int(meta[k]["map_off"]):int(meta[k]["map_off"]) + m.size] = m.ravel()
+    block_a = np.zeros(32 + 32 * cap, np.uint8)
+    block_b = np.zeros(32 + 32 * cap, np.uint8)
+    nontrivial = np.zeros(len(maps), np.int32)
+    best = np.zeros(len(maps), np.uint64)
+    keep = np.zeros(cap, np.int32)
+    mirror = np.zeros(32 + 32 * 256, np.uint8)
+    where, route = ctypes.c_int(0), ctypes.c_int(0)
+    cand = np.zeros(1, DEVHIT_DTYPE) if candidates is None else candidates
+    n = emu.emu_postprocess(_ptr(meta), len(maps), _ptr(flat), method, ctypes.c_longlong(-1 if n_object == float("inf") else n_object),
+                            ctypes.c_double(thr), ctypes.c_double(max_overlap), int(do_nms), int(force_general), _ptr(cand),
+                            -1 if candidates is None else len(candidates), cand_cap, cap, _ptr(block_a), _ptr(block_b),
+                            _ptr(nontrivial), _ptr(best), _ptr(keep), _ptr(mirror), ctypes.byref(where), ctypes.byref(route))
+    assert n >= 0, n
+    hits = (block_b if where.value else block_a)[32:32 + 32 * n].view(DEVHIT_DTYPE)
+    out = [(int(r["tmpl"]), (int(r["x"]), int(r["y"]), int(r["w"]), int(r["h"])), float(r["score"])) for r in hits]
+    if route.value == 0 and (do_nms or n_object != 1):                         # the mapped mirror carries the same header + first 256 hits
+        assert int(mirror[:4].view(np.int32)[0]) == n
+        m = min(n, 256)
+        assert np.array_equal(mirror[32:32 + 32 * m], (block_b if where.value else block_a)[32:32 + 32 * m])
+    return out, route.value
+
+
+def _port_postprocess(maps, sizes, method, n_object, thr, max_overlap, do_nms):
+    """The same list through oracle/mtm_port.py (MTM/__init__.py:22-53, 222-241 and MTM/NMS.py on live cv2.dnn.NMSBoxes)."""
+    import cv2
+    from oracle import mtm_port
+    hits = []
+    for t, (m, (h, w)) in enumerate(zip(maps, sizes)):
+        if n_object == 1:
+            _, _, lo, hi = cv2.minMaxLoc(m)
+            peaks = [(lo if method in (0, 1) else hi)[::-1]]
+        elif method in (0, 1):
+            peaks = mtm_port.find_local_min(m, thr)
+        else:
+            peaks = mtm_port.find_local_max(m, thr)
+        hits += [(t, (int(p[1]), int(p[0]), w, h), float(m[tuple(p)])) for p in peaks]
+    return mtm_port.nms(hits, thr, method == 1, n_object, max_overlap) if do_nms else hits
+
+
+def _score_maps(rng, levels):
+    """A mix of every shape class of MTM._findLocalMax_: 2-D maps with ties and plateaus (few score levels), a constant 2-D map
+    above the threshold (peak_local_max: no peaks), a 1 x n row, an n x 1 column and a 1 x 1 map."""
+    q = lambda a: (np.round(a * levels) / levels).astype(np.float32)
+    maps = [q(rng.random((20, 30))), np.full((6, 7), 0.9, np.float32), q(rng.random((1, 40))), q(rng.random((33, 1))),
+            np.array([[0.75]], np.float32), q(rng.random((17, 9))), np.array([[0.25]], np.float32)]
+    maps[0][3:6, 10:13] = 1.0                                                 # a 3 x 3 plateau of the maximum
+    sizes = [(12, 9), (30, 30), (8, 8), (5, 20), (64, 64), (10, 10), (3, 3)]
+    return maps, sizes
+
+
+@pytest.mark.parametrize("method", [1, 3, 5])
+@pytest.mark.parametrize("n_object", [float("inf"), 1, 4])
+def test_peak_sort_nms_kernels_on_the_host(emu, method, n_object):
+    """peaks.cu + nms.cu from their source on the CPU: the findMatches list (order included) and the post-NMS list of
+    MTM.matchTemplates equal the port's on maps full of ties, for the one-launch route and the general multi-launch route."""
+    rng = np.random.default_rng(100 * method + (0 if n_object == float("inf") else n_object))
+    for levels in (8, 1000):
+        maps, sizes = _score_maps(rng, levels)
+        if method == 1:
+            maps = [(1.0 - m).astype(np.float32) for m in maps]
+        thr = 0.5
+        want_list = _port_postprocess(maps, sizes, method, n_object, thr, 0.3, False)
+        got_list, _ = _host_postprocess(emu, maps, sizes, method, n_object, thr, 0.3, False)
+        assert got_list == want_list
+        want = _port_postprocess(maps, sizes, method, n_object, thr, 0.3, True)
+        for force_general in (False, True):
+            got, route = _host_postprocess(emu, maps, sizes, method, n_object, thr, 0.3, True, force_general)
+            assert route == int(force_general)
+            assert got == want, (levels, force_general)
+        if n_object != 1:
+            got_list_g, _ = _host_postprocess(emu, maps, sizes, method, n_object, thr, 0.3, False, True)
+            assert got_list_g == want_list
+
+
+def test_candidate_list_route_on_the_host(emu):
+    """verify_candidates_kernel: the pixels above the threshold that the tcgen05 epilogue lists (any order) give the same hit lists as
+    the streaming pass; a list that overflowed (a constant map above the threshold always does: the route needs maps larger than the
+    list) is reported with header[2] = 2 so that the library streams the maps instead."""
+    rng = np.random.default_rng(77)
+    maps = [(np.round(rng.random((24, 30)) * 16) / 16).astype(np.float32), rng.random((26, 31)).astype(np.float32)]
+    sizes = [(9, 9), (14, 6)]
+    thr = 0.6
+    cand = []
+    for t, m in enumerate(maps):
+        ys, xs = np.nonzero(m > np.float32(thr))
+        cand += [(t, int(x), int(y), sizes[t][1], sizes[t][0], float(m[y, x]), 0, 0.0) for y, x in zip(ys, xs)]
+    cand = np.array([cand[i] for i in rng.permutation(len(cand))], DEVHIT_DTYPE)          # epilogue warps append in any order
+    assert 0 < len(cand) < 700
+    for do_nms in (False, True):
+        want = _port_postprocess(maps, sizes, 5, float("inf"), thr, 0.25, do_nms)
+        got, _ = _host_postprocess(emu, maps, sizes, 5, float("inf"), thr, 0.25, do_nms, candidates=cand, cand_cap=700)
+        assert got == want and len(want) > 5
+    flat = [np.full((24, 30), 0.9, np.float32)]
+    every = np.array([(0, x, y, 9, 9, 0.9, 0, 0.0) for y in range(24) for x in range(30)], DEVHIT_DTYPE)
+    with pytest.raises(AssertionError, match="-2"):
+        _host_postprocess(emu, flat, [(9, 9)], 5, float("inf"), thr, 0.25, True, candidates=every, cand_cap=700)
+    assert _port_postprocess(flat, [(9, 9)], 5, float("inf"), thr, 0.25, True) == []
+    assert _host_postprocess(emu, flat, [(9, 9)], 5, float("inf"), thr, 0.25, True)[0] == []          # ... and the streaming pass agrees
+
+
+def test_more_than_1024_raw_hits_take_the_general_route_on_the_host(emu):
+    """finalize_small_kernel declines lists above 1024 raw hits; sort_hits_kernel (global-memory bitonic sorts, padding to a power of
+    two) + nms_kernel then give the port's lists, including the [:N_object] cut."""
+    rng = np.random.default_rng(5)
+    maps = [rng.random((110, 120)).astype(np.float32), (np.round(rng.random((40, 50)) * 32) / 32).astype(np.float32)]
+    sizes = [(4, 5), (7, 3)]
+    want_list = _port_postprocess(maps, sizes, 5, float("inf"), 0.2, 0.0, False)
+    assert len(want_list) > 1024
+    got_list, route = _host_postprocess(emu, maps, sizes, 5, float("inf"), 0.2, 0.0, False)
+    assert route == 1 and got_list == want_list
+    for n_object in (60, 1):
+        want = _port_postprocess(maps, sizes, 5, n_object, 0.2, 0.1, True)
+        got, route = _host_postprocess(emu, maps, sizes, 5, n_object, 0.2, 0.1, True)
+        assert got == want and route == (1 if n_object != 1 else 0)
