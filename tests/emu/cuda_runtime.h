@@ -108,6 +108,7 @@ struct EmuBlock {
     std::atomic<int> vote{0};
 };
 static EmuBlock* emu_block = nullptr;
+static uint8_t* emu_dyn_smem = nullptr;          // dynamic shared memory of the running block (`extern __shared__` is rewritten to it)
 static thread_local int emu_lane = 0, emu_warp = 0;
 static thread_local bool emu_coop = false;
 
@@ -171,33 +172,43 @@ template <typename F> static void emu_launch(dim3 grid, dim3 block, F body)
                         }
 }
 
-// one OS thread per CUDA thread; a thread that returns early leaves the block barrier like an exited CUDA thread
+// one OS thread per CUDA thread (created once per launch, walking the blocks together); a thread that returns early leaves the
+// block barrier like an exited CUDA thread
 template <typename F> static void emu_launch_coop(dim3 grid, dim3 block, F body)
 {
     gridDim = grid; blockDim = block;
     const int nthreads = (int)(block.x * block.y * block.z);
-    for (unsigned bz = 0; bz < grid.z; ++bz)
-        for (unsigned by = 0; by < grid.y; ++by)
-            for (unsigned bx = 0; bx < grid.x; ++bx) {
-                blockIdx = dim3(bx, by, bz);
-                EmuBlock blk;
-                blk.bar = std::make_unique<std::barrier<>>(nthreads);
-                blk.warps.resize((nthreads + 31) / 32);
-                for (size_t w = 0; w < blk.warps.size(); ++w) {
-                    blk.warps[w].lanes = std::min(32, nthreads - 32 * (int)w);
-                    blk.warps[w].bar = std::make_unique<std::barrier<>>(blk.warps[w].lanes);
+    const long long nblocks = (long long)grid.x * grid.y * grid.z;
+    std::barrier<> between(nthreads);                      // separates the blocks of the launch
+    std::unique_ptr<EmuBlock> blk;
+    auto next_block = [&](long long b) {
+        blockIdx = dim3((unsigned)(b % grid.x), (unsigned)((b / grid.x) % grid.y), (unsigned)(b / ((long long)grid.x * grid.y)));
+        blk = std::make_unique<EmuBlock>();
+        blk->bar = std::make_unique<std::barrier<>>(nthreads);
+        blk->warps.resize((nthreads + 31) / 32);
+        for (size_t w = 0; w < blk->warps.size(); ++w) {
+            blk->warps[w].lanes = std::min(32, nthreads - 32 * (int)w);
+            blk->warps[w].bar = std::make_unique<std::barrier<>>(blk->warps[w].lanes);
+        }
+        emu_block = blk.get();
+    };
+    next_block(0);
+    std::vector<std::thread> pool;
+    pool.reserve(nthreads);
+    for (int t = 0; t < nthreads; ++t)
+        pool.emplace_back([&, t] {
+            threadIdx = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
+            emu_lane = t & 31; emu_warp = t >> 5; emu_coop = true;
+            for (long long b = 0; b < nblocks; ++b) {
+                body();
+                emu_block->bar->arrive_and_drop();
+                between.arrive_and_wait();                 // every thread has left block b
+                if (b + 1 < nblocks) {
+                    if (t == 0) next_block(b + 1);
+                    between.arrive_and_wait();
                 }
-                emu_block = &blk;
-                std::vector<std::thread> pool;
-                pool.reserve(nthreads);
-                for (int t = 0; t < nthreads; ++t)
-                    pool.emplace_back([&, t] {
-                        threadIdx = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
-                        emu_lane = t & 31; emu_warp = t >> 5; emu_coop = true;
-                        body();
-                        emu_block->bar->arrive_and_drop();
-                    });
-                for (auto& th : pool) th.join();
-                emu_block = nullptr;
             }
+        });
+    for (auto& th : pool) th.join();
+    emu_block = nullptr;
 }

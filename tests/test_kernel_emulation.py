@@ -39,12 +39,17 @@ def emu(tmp_path_factory):
     ws = open(os.path.join(CSRC, "window_stats.cu")).read()
     pt = open(os.path.join(CSRC, "ncc_points.cu")).read()
     pk = open(os.path.join(CSRC, "peaks.cu")).read()
+    dr = open(os.path.join(CSRC, "ncc_direct.cu")).read()
+    dyn = "extern __shared__ uint32_t smem[];"                                # the one edit: dynamic shared memory comes from the launcher
+    assert dr.count(dyn) == 1
+    dr = dr.replace(dyn, "uint32_t* smem = reinterpret_cast<uint32_t*>(emu_dyn_smem);")
     nm = open(os.path.join(CSRC, "nms.cu")).read()
     parts = ['#include "cuda_runtime.h"', '#include "mtm_internal.cuh"', '#include "ncc_epilogue.cuh"',
              xf[xf.index("namespace {"):xf.index("}  // namespace") + 1],          # all device code of transform.cu
              ws[ws.index("namespace {"):ws.index("}  // namespace") + 1],          # ... of window_stats.cu
              pt[pt.index("namespace {"):pt.index("}  // namespace") + 1],          # ... of ncc_points.cu
              pk[pk.index("namespace {"):pk.index("}  // namespace") + 1],          # ... of peaks.cu
+             dr[dr.index("namespace {"):dr.index("template <int C, int TT>\nint launch_one(")] + "}",   # ... of ncc_direct.cu
              nm[nm.index("namespace {"):nm.index("}  // namespace") + 1],          # ... of nms.cu
              "namespace {",
              _function(tc, "template <bool STREAM>\n__global__ void window_moments_kernel("),
@@ -170,6 +175,40 @@ extern "C" int emu_postprocess(const TmplMeta* meta, int nt, const float* maps, 
     }
     *where = do_nms ? 1 : 0;
     return do_nms ? countB[0] : countA[0];
+}
+// launch_ncc_direct (ncc_direct.cu) restated: same template tile / chunk / shared-memory pitch choices and grid.
+extern "C" int emu_ncc_direct(const uint8_t* img, int64_t pitch, int H, int W, int C, const uint32_t* sat_s, const unsigned long long* sat_q,
+                              int64_t sat_pitch, const uint8_t* tmpl, const TmplMeta* meta, const int32_t* order, int count,
+                              float* maps, int method, int force_wide)
+{
+    const TmplMeta& m0 = meta[order[0]];
+    DirectParams p{};
+    p.img = img; p.pitch = pitch; p.H = H; p.W = W;
+    p.sat.s = sat_s; p.sat.q = sat_q; p.sat.pitch = sat_pitch; p.sat.plane = (int64_t)(H + 1) * sat_pitch;
+    p.tmpl = tmpl; p.meta = meta; p.order = order; p.maps = maps;
+    p.count = count; p.h = m0.h; p.w = m0.w; p.wp = m0.wp; p.mh = m0.mh; p.mw = m0.mw; p.method = method;
+    int TT = count >= 8 ? 8 : count >= 4 ? 4 : count >= 2 ? 2 : 1;
+    if (C > 1 && TT > 4) TT = 4;
+    int TW = (BX * C + p.wp) / 4 + 4;
+    TW = ((TW + 15) / 16) * 16 + 8;
+    const int CH = p.h < 16 ? p.h : 16;
+    p.CH = CH; p.TW = TW;
+    p.wide = (force_wide || (double)p.h * p.w * C * 65025.0 >= 4294967296.0) ? 1 : 0;
+    const size_t smem = (size_t)(BY + CH) * TW * 4 + (size_t)TT * CH * p.wp;
+    std::vector<uint8_t> dyn(smem + 64, 0xCD);
+    emu_dyn_smem = dyn.data();
+    dim3 grid((p.mw + BX - 1) / BX, (p.mh + BY - 1) / BY, (count + TT - 1) / TT), block(NTHREADS);
+#define EMU_DIRECT(CC) \
+    switch (TT) { \
+        case 1: emu_launch_coop(grid, block, [&] { ncc_direct_u8_kernel<CC, 1>(p); }); break; \
+        case 2: emu_launch_coop(grid, block, [&] { ncc_direct_u8_kernel<CC, 2>(p); }); break; \
+        case 4: emu_launch_coop(grid, block, [&] { ncc_direct_u8_kernel<CC, 4>(p); }); break; \
+        default: emu_launch_coop(grid, block, [&] { ncc_direct_u8_kernel<CC, 8>(p); }); break; \
+    }
+    if (C == 1) { EMU_DIRECT(1) } else if (C == 3) { EMU_DIRECT(3) } else if (C == 4) { EMU_DIRECT(4) } else return -1;
+#undef EMU_DIRECT
+    emu_dyn_smem = nullptr;
+    return TT;
 }
 ''']
     d = tmp_path_factory.mktemp("emu")
@@ -525,3 +564,56 @@ def test_more_than_1024_raw_hits_take_the_general_route_on_the_host(emu):
         want = _port_postprocess(maps, sizes, 5, n_object, 0.2, 0.1, True)
         got, route = _host_postprocess(emu, maps, sizes, 5, n_object, 0.2, 0.1, True)
         assert got == want and route == (1 if n_object != 1 else 0)
+
+
+def _host_direct_maps(emu, image, tmpls, methods, force_wide=False):
+    """K1 + K2 of the library on the host: summed-area tables, template statistics (once) and ncc_direct_u8_kernel per method for a
+    list of equal-sized uint8 templates; returns {method: score maps} and the template-tile width the launch chose."""
+    H, W = image.shape[:2]
+    C = 1 if image.ndim == 2 else image.shape[2]
+    buf, ipitch, sat_s, sat_q, _, pitch = _host_sat(emu, image)
+    arena, meta = _pack_templates([t.reshape(t.shape[0], t.shape[1], C) for t in tmpls], C)
+    h, w = tmpls[0].shape[:2]
+    mh, mw = H - h + 1, W - w + 1
+    per = (mh * mw + 31) // 32 * 32
+    for k in range(len(tmpls)):
+        meta[k]["mh"], meta[k]["mw"], meta[k]["map_off"] = mh, mw, k * per
+    emu.emu_tmpl_stats(_ptr(arena), _ptr(meta), len(tmpls), C)
+    order = np.arange(len(tmpls), dtype=np.int32)
+    out = {}
+    for method in methods:
+        maps = np.full(per * len(tmpls), np.nan, np.float32)
+        tt = emu.emu_ncc_direct(_ptr(buf), ctypes.c_int64(ipitch), H, W, C, _ptr(sat_s), _ptr(sat_q), ctypes.c_int64(pitch), _ptr(arena),
+                                _ptr(meta), _ptr(order), len(tmpls), _ptr(maps), method, int(force_wide))
+        assert tt > 0
+        out[method] = [maps[k * per:k * per + mh * mw].reshape(mh, mw) for k in range(len(tmpls))]
+    return out, tt
+
+
+@pytest.mark.parametrize("channels,count", [(1, 1), (1, 3), (1, 9), (3, 2), (3, 5), (4, 4)])
+def test_direct_kernel_on_the_host(emu, channels, count):
+    """ncc_direct_u8_kernel (register tile of dp4a accumulators over byte-shifted image words, chunked template rows, fused float64
+    epilogue) for every template-tile width TT and channel count: score maps bit-identical to the oracle's exact maps, all six
+    methods; the 64-bit accumulation route gives the same bits."""
+    from oracle import ncc_exact
+    rng = np.random.default_rng(40 + channels * 10 + count)
+    H, W, h, w = 45, 83, 19, 13                                              # 27 x 71 maps: two tiles in x, a second chunk of 3 rows
+    img = rng.integers(0, 256, (H, W, channels)).astype(np.uint8)
+    img[5:30, 40:70] = 128                                                   # flat windows (the epilogue's zero-variance rule)
+    image = img if channels > 1 else img[:, :, 0]
+    tmpls = []
+    for k in range(count):
+        y0, x0 = int(rng.integers(0, H - h + 1)), int(rng.integers(0, W - w + 1))
+        t = np.clip(img[y0:y0 + h, x0:x0 + w].astype(np.int64) + rng.integers(-30, 31, (h, w, channels)), 0, 255).astype(np.uint8)
+        tmpls.append(t if channels > 1 else t[:, :, 0])
+    if count >= 3:
+        tmpls[1] = np.full_like(tmpls[1], 99)                                # a constant template (TM_CCOEFF_NORMED map := 1)
+    got, tt = _host_direct_maps(emu, image, tmpls, range(6))
+    assert tt == (1 if count == 1 else 2 if count < 4 else 4 if (count < 8 or channels > 1) else 8)
+    for method in range(6):
+        for k, t in enumerate(tmpls):
+            want = ncc_exact.match_template_exact(image, t, method)
+            assert np.array_equal(got[method][k].view(np.uint32), want.view(np.uint32)), (method, k, np.abs(got[method][k] - want).max())
+    wide, _ = _host_direct_maps(emu, image, tmpls, [5], force_wide=True)
+    for a, b in zip(wide[5], got[5]):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
