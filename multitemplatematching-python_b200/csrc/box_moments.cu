@@ -1,0 +1,172 @@
+// box_moments.cu -- window moments of a template set with ONE window size, straight from the image.
+//
+// Same outputs, bit for bit, as window_moments_kernel (ncc_tc.cu): per window position the per-channel sums S_c and
+// rsD = rsqrt(A*Q - sum_c S_c^2) (0 for an exactly flat window) -- the denominator statistics that OpenCV's
+// common_matchTemplate takes from integral(img, sum, sqsum) (third-party; reached from MTM/__init__.py:92).  The
+// summed-area route costs three launches per image (row prefixes, column prefixes, moment sweep: 27 + 15 us at
+// BASELINE configs[1]) and ~100 MB of table traffic; when every template has the same size the tables are not needed:
+//
+//   vertical running sums   V_c(y, x') = sum_{dy < h} I_c[y+dy][x'],  VQ(y, x') = sum_c sum_{dy < h} I_c[y+dy][x']^2
+//                           kept in registers, one add (row y+h-1) and one subtract (row y-1) per output row;
+//   horizontal window sums  block-wide exclusive prefix P of V along x (warp shuffles + one shared-memory hop),
+//                           S_c(y, x) = P_c[x+w] - P_c[x]  -- modulo 2^32, exact because window sums stay below 2^32
+//                           on the tensor path (h*w*C <= 66051).
+//
+// A CTA owns a strip of 1024 image columns (4 per thread, aligned 32-bit loads) and a band of output rows; it first
+// accumulates the h-1 rows above its band (adds only).  HBM-bound by design: the image is read from L2 (each row
+// (band overlap) times), the moment maps are written once: 8 B (C = 1) or 4(C+1) B per window position.
+//
+// Experiment knob MTM_B200_MOM_BOX=1 (mtm_api.cu: the summed-area tables are then built on demand only).  Checked on the
+// CPU against window_moments_kernel (tests/test_kernel_emulation.py); NOT YET MEASURED ON THE GPU.
+#include "mtm_internal.cuh"
+#include <cstdlib>
+
+namespace {
+
+constexpr int BM_THREADS = 256;
+constexpr int BM_PX = 4;                               // image columns per thread
+constexpr int BM_COLS = BM_THREADS * BM_PX;            // image columns per strip
+constexpr int BM_ROW = BM_COLS + 4;                    // prefix row in shared memory (16-byte aligned rows, entry BM_COLS used)
+
+struct BoxParams {
+    const uint8_t* img; int64_t pitch;                 // zero-padded u8 rows, interleaved channels
+    int h, w, mh, mw;
+    uint32_t* S; float* rsD;                           // window_moments_kernel's layout
+    int64_t off, mom_plane;
+    int strip_out;                                     // window positions per strip: a multiple of 4, <= BM_COLS - (w - 1)
+    int band;                                          // output rows per CTA
+};
+
+template <int C>
+__global__ void __launch_bounds__(BM_THREADS)
+box_moments_kernel(const BoxParams p)
+{
+    __shared__ __align__(16) uint32_t P[2][C + 1][BM_ROW];
+    __shared__ uint32_t wtot[2][C + 1][BM_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int x0 = blockIdx.x * p.strip_out;           // first image column of the strip == its first window position
+    const int y0 = blockIdx.y * p.band, y1 = min(p.mh, y0 + p.band);
+    if (y0 >= p.mh) return;
+    const int64_t col_byte = ((int64_t)x0 + BM_PX * tid) * C;      // a multiple of 4: strip_out and BM_PX are
+    uint32_t V[C + 1][BM_PX];
+#pragma unroll
+    for (int q = 0; q <= C; ++q)
+#pragma unroll
+        for (int j = 0; j < BM_PX; ++j) V[q][j] = 0u;
+
+    // adds (SUB = false) or subtracts image row r to / from the running column sums of this thread's 4 pixels
+    auto row_update = [&](int r, bool sub) {
+        const uint8_t* row = p.img + (int64_t)r * p.pitch + col_byte;
+        uint32_t wd[C];
+#pragma unroll
+        for (int k = 0; k < C; ++k)
+            wd[k] = (col_byte + 4 * k + 4 <= p.pitch) ? __ldg(reinterpret_cast<const uint32_t*>(row) + k) : 0u;   // beyond the row: no pixels
+#pragma unroll
+        for (int j = 0; j < BM_PX; ++j) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const int b = j * C + c;
+                const uint32_t v = (wd[b >> 2] >> (8 * (b & 3))) & 255u;
+                if (sub) { V[c][j] -= v; V[C][j] -= v * v; } else { V[c][j] += v; V[C][j] += v * v; }
+            }
+        }
+    };
+
+    for (int r = y0; r < y0 + p.h - 1; ++r) row_update(r, false);
+    const uint32_t area = (uint32_t)p.h * (uint32_t)p.w;
+    for (int y = y0; y < y1; ++y) {
+        const int buf = (y - y0) & 1;
+        row_update(y + p.h - 1, false);
+        // block-wide exclusive prefix of every quantity along x
+        uint32_t incl[C + 1];
+#pragma unroll
+        for (int q = 0; q <= C; ++q) {
+            uint32_t s = V[q][0] + V[q][1] + V[q][2] + V[q][3];
+            const uint32_t own = s;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t n = __shfl_up_sync(0xffffffffu, s, d);
+                if (lane >= d) s += n;
+            }
+            if (lane == 31) wtot[buf][q][wid] = s;
+            incl[q] = s - own;                         // exclusive inside the warp
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q <= C; ++q) {
+            uint32_t e = incl[q];
+            for (int k = 0; k < wid; ++k) e += wtot[buf][q][k];
+            uint4 v;
+            v.x = e; v.y = v.x + V[q][0]; v.z = v.y + V[q][1]; v.w = v.z + V[q][2];
+            *reinterpret_cast<uint4*>(&P[buf][q][BM_PX * tid]) = v;
+            if (tid == BM_THREADS - 1) P[buf][q][BM_COLS] = v.w + V[q][3];
+        }
+        __syncthreads();
+        // window positions tid, tid + 256, ... of the strip: conflict-free shared-memory reads, coalesced stores
+        const int64_t out_row = p.off + (int64_t)y * p.mw;
+#pragma unroll
+        for (int j = 0; j < BM_PX; ++j) {
+            const int xl = tid + j * BM_THREADS;
+            const int x = x0 + xl;
+            if (xl >= p.strip_out || x >= p.mw) continue;
+            const uint32_t qs = P[buf][C][xl + p.w] - P[buf][C][xl];
+            unsigned long long d1 = (unsigned long long)area * qs;
+            uint32_t s0 = 0;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const uint32_t s = P[buf][c][xl + p.w] - P[buf][c][xl];
+                d1 -= (unsigned long long)s * s;
+                if (C > 1) p.S[c * p.mom_plane + out_row + x] = s;
+                s0 = s;
+            }
+            const float rs = d1 ? rsqrtf((float)d1) : 0.0f;
+            if (C > 1) p.rsD[out_row + x] = rs;
+            else reinterpret_cast<uint2*>(p.S)[out_row + x] = make_uint2(s0, __float_as_uint(rs));
+        }
+        row_update(y, true);
+    }
+}
+
+}  // namespace
+
+bool box_moments_enabled()
+{
+    static const bool on = getenv("MTM_B200_MOM_BOX") != nullptr && atoi(getenv("MTM_B200_MOM_BOX")) != 0;
+    return on;
+}
+
+// Can the resident (image, template set) take the box-sum route?  One window size, plain uint8, a window narrower than a strip.
+bool box_moments_applicable(const mtm_ctx* ctx)
+{
+    if (ctx->img_dtype != MTM_U8 || ctx->masked || ctx->h_sizes.size() != 1) return false;
+    const int C = ctx->img.C;
+    if (C != 1 && C != 3 && C != 4) return false;
+    const SizeDesc& sd = ctx->h_sizes[0];
+    if ((double)sd.h * sd.w * C * 65025.0 >= 4294967296.0) return false;     // window sums of squares must stay below 2^32
+    return sd.w <= BM_COLS / 2;
+}
+
+int launch_box_moments(mtm_ctx* ctx)
+{
+    const ImageDev& im = ctx->img;
+    const SizeDesc& sd = ctx->h_sizes[0];
+    BoxParams p{};
+    p.img = im.pix; p.pitch = im.pitch;
+    p.h = sd.h; p.w = sd.w; p.mh = sd.mh; p.mw = sd.mw;
+    p.S = ctx->d_wS; p.rsD = ctx->d_wR; p.off = sd.off; p.mom_plane = ctx->moments_total;
+    p.strip_out = (BM_COLS - (sd.w - 1)) & ~3;
+    const int strips = (sd.mw + p.strip_out - 1) / p.strip_out;
+    // about two CTAs per SM; a band re-reads the h-1 rows above it, so bands stay as tall as that allows
+    int bands = std::max(1, std::min(sd.mh, (2 * ctx->sm_count + strips - 1) / strips));
+    p.band = (sd.mh + bands - 1) / bands;
+    bands = (sd.mh + p.band - 1) / p.band;
+    const dim3 grid((unsigned)strips, (unsigned)bands);
+    switch (im.C) {
+        case 1: box_moments_kernel<1><<<grid, BM_THREADS, 0, ctx->stream>>>(p); break;
+        case 3: box_moments_kernel<3><<<grid, BM_THREADS, 0, ctx->stream>>>(p); break;
+        case 4: box_moments_kernel<4><<<grid, BM_THREADS, 0, ctx->stream>>>(p); break;
+        default: return mtm_fail(ctx, MTM_ERR_INVALID, "unsupported channel count %d", im.C);
+    }
+    MTM_LAUNCH_CHECK(ctx);
+    return MTM_OK;
+}

@@ -249,6 +249,15 @@ int mtm_timer_end(mtm_ctx* ctx, float* elapsed_ms)
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------
+// Summed-area tables of the resident uint8 image (window_stats.cu).
+static int ensure_sat(mtm_ctx* ctx)
+{
+    if (ctx->sat_valid) return MTM_OK;
+    MTM_TRY(launch_build_sat(ctx));
+    ctx->sat_valid = true;
+    return MTM_OK;
+}
+
 static int set_image_impl(mtm_ctx* ctx, const void* pixels, int H, int W, int C, int dtype,
                           int64_t row_stride, bool on_device)
 {
@@ -331,7 +340,8 @@ static int set_image_impl(mtm_ctx* ctx, const void* pixels, int H, int W, int C,
                                                             // equal-sized images keeps them (and skips the sync in ensure_geometry)
     ctx->moments_valid = false;
     ctx->masked_image_valid = false;
-    MTM_TRY(launch_build_sat(ctx));
+    ctx->sat_valid = false;
+    if (!box_moments_enabled()) MTM_TRY(ensure_sat(ctx));   // knob: compute_maps builds the tables when a kernel of the call reads them
     g_marks.mark(ctx, "sat");
     return MTM_OK;
 }
@@ -453,7 +463,7 @@ static int plan_tensor_path(mtm_ctx* ctx)
 }
 
 // Window moments (S, rsqrt(A*Q - S^2)) for every distinct template size; image-dependent.
-static int ensure_moments(mtm_ctx* ctx)
+static int ensure_moments(mtm_ctx* ctx, bool box)
 {
     if (ctx->moments_valid) return MTM_OK;
     MTM_TRY(mtm_reserve(ctx, ctx->d_wS, ctx->wS_cap, (size_t)ctx->moments_total * std::max(2, ctx->img.C)));   // C == 1: interleaved {S, rsD}
@@ -461,7 +471,8 @@ static int ensure_moments(mtm_ctx* ctx)
     MTM_TRY(mtm_reserve(ctx, ctx->d_sizes, ctx->sizes_cap, ctx->h_sizes.size()));
     MTM_CUDA(ctx, cudaMemcpyAsync(ctx->d_sizes, ctx->h_sizes.data(), ctx->h_sizes.size() * sizeof(SizeDesc),
                                   cudaMemcpyHostToDevice, ctx->stream));
-    MTM_TRY(launch_window_moments(ctx));
+    if (box) MTM_TRY(launch_box_moments(ctx));             // one window size: straight from the image, same bits
+    else MTM_TRY(launch_window_moments(ctx));
     ctx->moments_valid = true;
     return MTM_OK;
 }
@@ -532,7 +543,14 @@ static int compute_maps(mtm_ctx* ctx, int method, int tmpl)
     if (!tensor && ctx->path == MTM_PATH_TENSOR)
         return mtm_fail(ctx, MTM_ERR_UNSUPPORTED, "tensor-core path requested but not available for these inputs/method");
     const bool tensor16 = tensor && ctx->img_dtype == MTM_F32;     // 16-bit byte-plane path
-    if (tensor && !tensor16 && method == MTM_TM_CCOEFF_NORMED) MTM_TRY(ensure_moments(ctx));   // the other methods read the summed-area tables directly
+    if (ctx->img_dtype == MTM_U8) {
+        // Everything but the default method's tensor-core epilogue reads the summed-area tables; under MTM_B200_MOM_BOX a
+        // one-size template set gets its window moments from the image instead and the tables are never built.
+        bool box = box_moments_enabled() && tensor && method == MTM_TM_CCOEFF_NORMED && box_moments_applicable(ctx);
+        for (const TcGroup& g : ctx->tc_groups) box = box && !points_path_preferred(ctx, g.first, g.count);
+        if (!box) MTM_TRY(ensure_sat(ctx));
+        if (tensor && method == MTM_TM_CCOEFF_NORMED) MTM_TRY(ensure_moments(ctx, box));   // the other methods read the tables directly
+    }
     if (tensor16) { MTM_TRY(mtm_reserve(ctx, ctx->d_acc, ctx->acc_cap, (size_t)ctx->maps_total)); ctx->cand_on = false; }
     const int64_t launches_before = ctx->ctr.kernel_launches;
     if (ctx->time_ncc) {

@@ -114,6 +114,7 @@ struct mtm_ctx {
     ImageDev img;
     size_t img_cap = 0, sat_s_cap = 0, sat_q_cap = 0, sat_q32_cap = 0, scratch_cap = 0, imgf_cap = 0, satf_s_cap = 0, satf_q_cap = 0;
     uint32_t* scratch = nullptr;         // row-prefix scratch for the SAT build
+    bool sat_valid = false;              // the u8 summed-area tables belong to the resident image (built on demand under MTM_B200_MOM_BOX)
     int img_dtype = -1;
 
     // full-resolution image of mtm_set_image_scaled (source of the reduced image and of mtm_set_image_roi)
@@ -234,6 +235,10 @@ bool tc_path_supported(const mtm_ctx* ctx, int method, int h, int w);
 bool tc_plan_group(int mode, int h, int w, int C, TcGroup& g);
 int launch_toeplitz_prep(mtm_ctx* ctx, const TcGroup& g);
 int launch_window_moments(mtm_ctx* ctx);
+// one-size template sets, experiment knob MTM_B200_MOM_BOX (box_moments.cu): the same maps without summed-area tables
+bool box_moments_enabled();
+bool box_moments_applicable(const mtm_ctx* ctx);
+int launch_box_moments(mtm_ctx* ctx);
 int launch_ncc_tc(mtm_ctx* ctx, const TcGroup& g, int method);
 // 16-bit path: one byte-plane product of the group accumulated into ctx->d_acc (img_plane / tmpl_plane: 0 = high, 1 = low bytes)
 int launch_ncc_tc_accum(mtm_ctx* ctx, const TcGroup& g, int img_plane, int tmpl_plane, double weight, bool first);

@@ -35,7 +35,7 @@ static dim3 blockIdx, blockDim, gridDim;
 #define __restrict__
 #define __launch_bounds__(...)
 #define __shared__ static
-#define __align__(n) alignas(n)
+#define __align__(n) __attribute__((aligned(n)))
 
 typedef void* cudaStream_t;
 typedef void* cudaEvent_t;

@@ -1,10 +1,10 @@
 """-m gpu, opt-in (MTM_B200_TEST_KNOBS=1): parity of the experiment knobs of the library.
 
-Every knob (environment variable read once per process, see TcEnv in csrc/ncc_tc.cu and ncc_points.cu) selects an
+Every knob (environment variable read once per process, see TcEnv in csrc/ncc_tc.cu, ncc_points.cu and box_moments.cu) selects an
 alternative kernel or launch plan that must produce the same results as the default; they exist so that the
 measurements under profiles/ can be repeated and so that a variant can be validated before it becomes the default.
 Each case runs a small parity script in a subprocess with the variable set.  Skipped unless MTM_B200_TEST_KNOBS=1:
-variants that have not been measured yet (MTM_B200_MOM_ROWS) must not gate the default suite.
+variants that have not been measured yet (MTM_B200_MOM_ROWS, MTM_B200_MOM_BOX) must not gate the default suite.
 """
 import os
 import subprocess
@@ -34,6 +34,13 @@ got = MTM.matchTemplates(temps, img, score_threshold=0.5, maxOverlap=0.25)
 want = mtm_port.match_templates(temps, img, score_threshold=0.5, maxOverlap=0.25)
 assert [(h[0], h[1]) for h in got] == [(h[0], h[1]) for h in want] and len(want) >= 6, (got, want)
 assert max(abs(float(a[2]) - float(b[2])) for a, b in zip(got, want)) <= 1e-4
+# a one-size template set (the box-sum moment route under MTM_B200_MOM_BOX), then another method on the same resident image
+# (summed-area tables built on demand) and the default method again
+same = [temps[0], temps[2]]
+for method, thr in ((5, 0.5), (3, 0.97), (5, 0.6)):
+    got = MTM.matchTemplates(same, img, method=method, score_threshold=thr, maxOverlap=0.25)
+    want = mtm_port.match_templates(same, img, method=method, score_threshold=thr, maxOverlap=0.25)
+    assert [(h[0], h[1]) for h in got] == [(h[0], h[1]) for h in want] and len(want) >= 2, (method, got, want)
 # RGB (per-channel moments) and a small map of a large template (small-map kernel)
 rgb = np.stack([img, img[::-1], 255 - img], axis=2)
 t3 = np.ascontiguousarray(rgb[100:140, 200:260])
@@ -44,7 +51,7 @@ assert np.max(np.abs(MTM.computeScoreMap(big, scene) - ncc_exact.match_template_
 print("knob parity ok")
 """
 
-KNOBS = [{"MTM_B200_MOM_ROWS": "1"}, {"MTM_B200_MOM_CS": "1"}, {"MTM_B200_NO_POINTS": "1"}, {"MTM_B200_NO_CAND": "1"},
+KNOBS = [{"MTM_B200_MOM_BOX": "1"}, {"MTM_B200_MOM_ROWS": "1"}, {"MTM_B200_MOM_CS": "1"}, {"MTM_B200_NO_POINTS": "1"}, {"MTM_B200_NO_CAND": "1"},
          {"MTM_B200_PERSIST": "0"}, {"MTM_B200_EW": "12"}, {"MTM_B200_EW": "8"}, {}]
 
 

@@ -44,6 +44,7 @@ def emu(tmp_path_factory):
     assert dr.count(dyn) == 1
     dr = dr.replace(dyn, "uint32_t* smem = reinterpret_cast<uint32_t*>(emu_dyn_smem);")
     nm = open(os.path.join(CSRC, "nms.cu")).read()
+    bm = open(os.path.join(CSRC, "box_moments.cu")).read()
     parts = ['#include "cuda_runtime.h"', '#include "mtm_internal.cuh"', '#include "ncc_epilogue.cuh"',
              xf[xf.index("namespace {"):xf.index("}  // namespace") + 1],          # all device code of transform.cu
              ws[ws.index("namespace {"):ws.index("}  // namespace") + 1],          # ... of window_stats.cu
@@ -51,6 +52,7 @@ def emu(tmp_path_factory):
              pk[pk.index("namespace {"):pk.index("}  // namespace") + 1],          # ... of peaks.cu
              dr[dr.index("namespace {"):dr.index("template <int C, int TT>\nint launch_one(")] + "}",   # ... of ncc_direct.cu
              nm[nm.index("namespace {"):nm.index("}  // namespace") + 1],          # ... of nms.cu
+             bm[bm.index("namespace {"):bm.index("}  // namespace") + 1],          # ... of box_moments.cu
              "namespace {",
              _function(tc, "template <bool STREAM>\n__global__ void window_moments_kernel("),
              _function(tc, "template <int C>\n__global__ void __launch_bounds__(256)\nwindow_moments_rows_kernel("),
@@ -209,6 +211,23 @@ extern "C" int emu_ncc_direct(const uint8_t* img, int64_t pitch, int H, int W, i
 #undef EMU_DIRECT
     emu_dyn_smem = nullptr;
     return TT;
+}
+// launch_box_moments (box_moments.cu) with the strip width it derives; the band height is the caller's (the library picks
+// it from the SM count).
+extern "C" int emu_box_moments(const uint8_t* img, int64_t pitch, int C, int h, int w, int mh, int mw, uint32_t* S, float* rsD,
+                               int64_t off, int64_t mom_plane, int band)
+{
+    BoxParams p{};
+    p.img = img; p.pitch = pitch; p.h = h; p.w = w; p.mh = mh; p.mw = mw;
+    p.S = S; p.rsD = rsD; p.off = off; p.mom_plane = mom_plane;
+    p.strip_out = (BM_COLS - (w - 1)) & ~3;
+    p.band = band;
+    const dim3 grid((mw + p.strip_out - 1) / p.strip_out, (mh + band - 1) / band), block(BM_THREADS);
+    if (C == 1) emu_launch_coop(grid, block, [&] { box_moments_kernel<1>(p); });
+    else if (C == 3) emu_launch_coop(grid, block, [&] { box_moments_kernel<3>(p); });
+    else if (C == 4) emu_launch_coop(grid, block, [&] { box_moments_kernel<4>(p); });
+    else return -1;
+    return (int)(grid.x * grid.y);
 }
 ''']
     d = tmp_path_factory.mktemp("emu")
@@ -717,3 +736,46 @@ def test_device_code_on_the_host_gives_the_reference_score_map(emu_mtm):
     want = np.load(os.path.join(gc.GOLDEN_DIR, "c1_fish256_map.npy"))
     assert got.shape == want.shape and got.dtype == np.float32
     assert np.max(np.abs(got - want)) <= 1e-4
+
+
+@pytest.mark.parametrize("channels", [1, 3, 4])
+@pytest.mark.parametrize("shape,window,band", [((41, 1100), (17, 40), 9), ((30, 333), (30, 5), 1), ((64, 70), (8, 64), 57), ((25, 2100), (3, 512), 4)])
+def test_box_sum_moment_kernel_equals_the_summed_area_one(emu, channels, shape, window, band):
+    """box_moments_kernel (experiment knob MTM_B200_MOM_BOX: one-size template sets, no summed-area tables) writes exactly what
+    window_moments_kernel writes from the tables: several strips and bands, a one-row map, a window as wide as half a strip,
+    flat windows (rsD = 0), garbage in the row padding."""
+    rng = np.random.default_rng(13)
+    (H, W), (h, w) = shape, window
+    mh, mw = H - h + 1, W - w + 1
+    img = rng.integers(0, 256, (H, W, channels)).astype(np.uint8)
+    img[H // 3:, W // 4:W // 4 + 3 * w] = 201                                 # flat windows
+    ipitch = (W * channels + 64 * channels + 64 + 127) // 128 * 128          # the library's row pitch
+    buf = rng.integers(0, 256, H * ipitch + 256).astype(np.uint8)            # (the library pads with zeros; any bytes do)
+    buf[:H * ipitch].reshape(H, ipitch)[:, :W * channels] = img.reshape(H, W * channels)
+    wide = img.astype(np.int64)
+    pitch = (W + 1 + 3) // 4 * 4
+    plane = (H + 1) * pitch
+    sat_s = np.zeros((channels, H + 1, pitch), np.uint32)
+    for c in range(channels):
+        sat_s[c, 1:, 1:W + 1] = np.cumsum(np.cumsum(wide[:, :, c], axis=0), axis=1).astype(np.uint32)
+    sat_q = np.zeros((H + 1, pitch), np.uint32)
+    sat_q[1:, 1:W + 1] = (np.cumsum(np.cumsum((wide ** 2).sum(axis=2), axis=0), axis=1) & 0xFFFFFFFF).astype(np.uint32)
+    sizes = np.zeros(1, SIZE_DTYPE)
+    off = 64                                                                  # the maps do not start at element 0
+    sizes[0] = (h, w, mh, mw, off)
+    total = off + (mh * mw + 31) // 32 * 32
+    outs = []
+    for box in (0, 1):
+        S = np.full(total * max(2, channels), 0xDEADBEEF, np.uint32)
+        R = np.full(total, -1.0, np.float32)
+        if box:
+            assert emu.emu_box_moments(_ptr(buf), ctypes.c_int64(ipitch), channels, h, w, mh, mw, _ptr(S), _ptr(R), ctypes.c_int64(off),
+                                       ctypes.c_int64(total), band) >= 1
+        else:
+            emu.emu_moments(0, _ptr(sat_s), _ptr(sat_q), ctypes.c_int64(pitch), ctypes.c_int64(plane), _ptr(sizes), 1, channels, _ptr(S),
+                            _ptr(R), ctypes.c_int64(total), 3, 1)
+        outs.append((S, R))
+    assert np.array_equal(outs[0][0], outs[1][0])
+    assert np.array_equal(outs[0][1].view(np.uint32), outs[1][1].view(np.uint32))
+    first = outs[1][0][off] if channels > 1 else outs[1][0][2 * off]
+    assert int(first) == int(wide[:h, :w, 0].sum())
