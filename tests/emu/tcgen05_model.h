@@ -1,0 +1,160 @@
+// tcgen05_model.h -- TEST INFRASTRUCTURE: a FUNCTIONAL host model of the Blackwell pieces that csrc/ncc_tc.cu reaches
+// through its PTX wrappers (the section "PTX wrappers" of that file is left out when the kernels are compiled for the
+// host and these definitions take its place, name for name):
+//   * shared-memory addresses   offsets into the block's dynamic shared memory (emu_dyn_smem);
+//   * mbarriers                 arrival count + transaction bytes + phase parity, blocking try_wait;
+//   * cp.async.bulk             memcpy, then complete_tx on the barrier;
+//   * tensor memory             128 lanes x 512 columns of 32 bits per CTA; tcgen05.ld.32x32b.x16;
+//   * tcgen05.mma kind::i8      D[m][n] (+)= sum_k A[m][k] * B[n][k], u8 x u8 -> 32 bit, K = 32, operands fetched through
+//                               K-major no-swizzle descriptors (8 x 16-byte core matrices; LBO between K blocks, SBO
+//                               between 8-row groups) exactly as addressed -- aliased layouts included;
+//   * tcgen05.commit            arrives at once: the model executes an MMA when it is issued, which is one of the orders
+//                               the hardware may take.
+// It checks the LOGIC of the kernels (tile geometry, Toeplitz slabs, descriptor arithmetic, barrier protocol, epilogue
+// index maps), not timing, and not whether the real hardware reads a descriptor the way this file does: that is what the
+// -m gpu parity tests are for.
+#pragma once
+#include <chrono>
+#include <condition_variable>
+#include <cstdio>
+#include <map>
+#include <mutex>
+
+static inline uint32_t smem_u32(const void* p) { return (uint32_t)(static_cast<const uint8_t*>(p) - emu_dyn_smem); }
+static inline uint8_t* emu_smem_ptr(uint32_t a) { return emu_dyn_smem + a; }
+
+// ---- mbarrier ---------------------------------------------------------------------------------------------------
+struct EmuMbar { uint32_t expected = 0; int64_t pending = 0, tx = 0; uint32_t phase = 0; };
+static std::mutex emu_mbar_mu;
+static std::condition_variable emu_mbar_cv;
+static std::map<uint32_t, EmuMbar> emu_mbars;
+static long long emu_mma_count = 0, emu_bulk_bytes = 0;
+
+static inline void emu_mbar_settle(EmuMbar& b)
+{
+    if (b.pending == 0 && b.tx == 0) { b.phase ^= 1u; b.pending = b.expected; emu_mbar_cv.notify_all(); }
+}
+static inline void mbar_init(uint64_t* bar, uint32_t count)
+{
+    std::lock_guard<std::mutex> g(emu_mbar_mu);
+    EmuMbar b; b.expected = count; b.pending = count;
+    emu_mbars[smem_u32(bar)] = b;
+}
+static inline EmuMbar& emu_mbar_at(uint64_t* bar)
+{
+    auto it = emu_mbars.find(smem_u32(bar));
+    if (it == emu_mbars.end()) { fprintf(stderr, "mbarrier at %u used before mbarrier.init\n", smem_u32(bar)); abort(); }
+    return it->second;
+}
+static inline void mbar_arrive(uint64_t* bar)
+{
+    std::lock_guard<std::mutex> g(emu_mbar_mu);
+    EmuMbar& b = emu_mbar_at(bar);
+    if (b.pending <= 0) { fprintf(stderr, "mbarrier at %u: more arrivals than its count\n", smem_u32(bar)); abort(); }
+    b.pending--; emu_mbar_settle(b);
+}
+static inline void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    std::lock_guard<std::mutex> g(emu_mbar_mu);
+    EmuMbar& b = emu_mbar_at(bar);
+    b.tx += bytes; b.pending--; emu_mbar_settle(b);
+}
+static inline void emu_mbar_complete_tx(uint64_t* bar, uint32_t bytes)
+{
+    std::lock_guard<std::mutex> g(emu_mbar_mu);
+    EmuMbar& b = emu_mbar_at(bar);
+    b.tx -= bytes; emu_mbar_settle(b);
+}
+static inline bool mbar_try_wait(uint64_t* bar, uint32_t parity)
+{
+    std::unique_lock<std::mutex> g(emu_mbar_mu);
+    EmuMbar& b = emu_mbar_at(bar);
+    if (b.phase == (parity & 1u)) emu_mbar_cv.wait_for(g, std::chrono::milliseconds(20));
+    return b.phase != (parity & 1u);                       // the phase with this parity has completed
+}
+static inline void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
+        if (spins > 500) {
+            fprintf(stderr, "mbarrier at %u never completed (parity %u; thread %u of block %u): deadlock in the kernel's protocol\n", smem_u32(bar), parity, threadIdx.x, blockIdx.x);
+            for (auto& kv : emu_mbars) fprintf(stderr, "  mbarrier %u: count %u pending %lld tx %lld phase %u\n", kv.first, kv.second.expected, (long long)kv.second.pending, (long long)kv.second.tx, kv.second.phase);
+            fprintf(stderr, "  %lld MMAs issued, %lld bytes bulk-copied\n", emu_mma_count, emu_bulk_bytes);
+            abort();
+        }
+}
+// elect.sync: the lanes of the warp meet here before one of them is chosen.  The kernels' warp-uniform loops (every lane
+// polls the same barriers, one elected lane issues) rely on that: a lane may not fall a whole barrier phase behind.
+static inline bool elect_one()
+{
+    if (emu_coop) emu_block->warps[emu_warp].bar->arrive_and_wait();
+    return emu_lane == 0;
+}
+static inline void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
+{
+    if ((bytes & 15u) || (smem_u32(dst_smem) & 15u) || (reinterpret_cast<uintptr_t>(src_gmem) & 15u)) {
+        fprintf(stderr, "cp.async.bulk: size / addresses must be multiples of 16\n"); abort();
+    }
+    if (getenv("EMU_TC_TRACE")) fprintf(stderr, "[block %u] bulk copy %u bytes -> smem %u, barrier %u\n", blockIdx.x, bytes, smem_u32(dst_smem), smem_u32(bar));
+    memcpy(dst_smem, src_gmem, bytes);
+    { std::lock_guard<std::mutex> g(emu_mbar_mu); emu_bulk_bytes += bytes; }
+    emu_mbar_complete_tx(bar, bytes);
+}
+
+// ---- tensor memory ------------------------------------------------------------------------------------------------
+static uint32_t emu_tmem[128][512];
+static uint32_t emu_tmem_cols = 0;
+static inline void tmem_alloc(uint32_t* dst_smem, uint32_t ncols)
+{
+    if (ncols < 32 || ncols > 512 || (ncols & (ncols - 1))) { fprintf(stderr, "tcgen05.alloc: %u columns\n", ncols); abort(); }
+    if (emu_lane == 0) { emu_tmem_cols = ncols; memset(emu_tmem, 0xA5, sizeof(emu_tmem)); *dst_smem = 0u; }
+}
+static inline void tmem_dealloc(uint32_t, uint32_t ncols) { if (emu_lane == 0 && ncols != emu_tmem_cols) { fprintf(stderr, "tcgen05.dealloc: column count differs from the allocation\n"); abort(); } }
+static inline void tc_fence_before() {}
+static inline void tc_fence_after() {}
+static inline void fence_async_smem() {}
+static inline void prefetch_l1(const void*) {}
+static inline long long clock64() { return 0; }
+static inline void __trap() { fprintf(stderr, "__trap()\n"); abort(); }
+
+static inline uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// byte (row, k) of a K-major no-swizzle operand: 8 rows x 16 bytes per core matrix
+static inline uint8_t emu_operand_byte(uint64_t desc, int row, int k)
+{
+    const uint32_t start = (uint32_t)(desc & 0x3FFFu) << 4, lbo = (uint32_t)((desc >> 16) & 0x3FFFu) << 4, sbo = (uint32_t)((desc >> 32) & 0x3FFFu) << 4;
+    return *emu_smem_ptr(start + (uint32_t)(row >> 3) * sbo + (uint32_t)(row & 7) * 16u + (uint32_t)(k >> 4) * lbo + (uint32_t)(k & 15));
+}
+static inline void umma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    const int N = (int)((idesc >> 17) & 0x3Fu) << 3, M = (int)((idesc >> 24) & 0x1Fu) << 4;
+    const uint32_t lane0 = d_tmem >> 16, col0 = d_tmem & 0xFFFFu;
+    if (M != 128 || N < 16 || N > 256 || (N & 15) || lane0 != 0 || col0 + (uint32_t)N > emu_tmem_cols || ((idesc >> 4) & 3u) != 2u) {
+        fprintf(stderr, "tcgen05.mma: bad instruction descriptor / accumulator (M %d N %d lane %u col %u of %u)\n", M, N, lane0, col0, emu_tmem_cols); abort();
+    }
+    uint8_t A[128][32], B[256][32];
+    for (int m = 0; m < M; ++m) for (int k = 0; k < 32; ++k) A[m][k] = emu_operand_byte(a_desc, m, k);
+    for (int n = 0; n < N; ++n) for (int k = 0; k < 32; ++k) B[n][k] = emu_operand_byte(b_desc, n, k);
+    for (int m = 0; m < M; ++m)
+        for (int n = 0; n < N; ++n) {
+            uint32_t s = accumulate ? emu_tmem[m][col0 + n] : 0u;
+            for (int k = 0; k < 32; ++k) s += (uint32_t)A[m][k] * (uint32_t)B[n][k];
+            emu_tmem[m][col0 + n] = s;
+        }
+    { std::lock_guard<std::mutex> g(emu_mbar_mu); emu_mma_count++; }
+}
+static inline void umma_commit(uint64_t* bar)
+{
+    if (getenv("EMU_TC_TRACE")) fprintf(stderr, "[block %u] commit -> barrier %u after %lld MMAs\n", blockIdx.x, smem_u32(bar), emu_mma_count);
+    mbar_arrive(bar);
+}        // every MMA issued so far has already executed
+static inline void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
+{
+    const uint32_t lane = (taddr >> 16) + (uint32_t)emu_lane, col = taddr & 0xFFFFu;
+    if (lane >= 128 || col + 16 > 512) { fprintf(stderr, "tcgen05.ld outside tensor memory\n"); abort(); }
+    if ((taddr >> 16) != 32u * (uint32_t)(emu_warp & 3)) { fprintf(stderr, "tcgen05.ld: warp %d may only read lanes %d..%d\n", emu_warp, 32 * (emu_warp & 3), 32 * (emu_warp & 3) + 31); abort(); }
+    for (int j = 0; j < 16; ++j) v[j] = emu_tmem[lane][col + j];
+}
+static void emu_tc_reset() { std::lock_guard<std::mutex> g(emu_mbar_mu); emu_mbars.clear(); emu_mma_count = 0; emu_bulk_bytes = 0; }

@@ -45,7 +45,17 @@ def emu(tmp_path_factory):
     dr = dr.replace(dyn, "uint32_t* smem = reinterpret_cast<uint32_t*>(emu_dyn_smem);")
     nm = open(os.path.join(CSRC, "nms.cu")).read()
     bm = open(os.path.join(CSRC, "box_moments.cu")).read()
-    parts = ['#include "cuda_runtime.h"', '#include "mtm_internal.cuh"', '#include "ncc_epilogue.cuh"',
+    tcn = tc[tc.index("namespace {"):tc.index("}  // namespace") + 1]         # all device code of ncc_tc.cu ...
+    a, b = tcn.index("// ---------------------------------------------------------------- PTX wrappers"), tcn.index("// Normalise 16 consecutive")
+    tcn = tcn[:a] + tcn[b:]                                                   # ... minus its PTX wrappers: tests/emu/tcgen05_model.h stands in
+    for text, count, repl in (('__device__ __forceinline__ void prefetch_l1(const void* ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }', 1, ""),
+                              ('asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");', 2, ""),
+                              ("extern __shared__ __align__(1024) uint8_t smem[];", 2, "uint8_t* smem = emu_dyn_smem;")):
+        assert tcn.count(text) == count, text
+        tcn = tcn.replace(text, repl)
+    assert "asm" not in tcn
+    tc_host = tc[tc.index("struct TcEnv {"):tc.index("int launch_toeplitz_prep(")]       # experiment knobs + tc_plan_group (plain host code)
+    parts = ['#include "cuda_runtime.h"', '#include "tcgen05_model.h"', '#include "mtm_internal.cuh"', '#include "ncc_epilogue.cuh"',
              xf[xf.index("namespace {"):xf.index("}  // namespace") + 1],          # all device code of transform.cu
              ws[ws.index("namespace {"):ws.index("}  // namespace") + 1],          # ... of window_stats.cu
              pt[pt.index("namespace {"):pt.index("}  // namespace") + 1],          # ... of ncc_points.cu
@@ -53,10 +63,7 @@ def emu(tmp_path_factory):
              dr[dr.index("namespace {"):dr.index("template <int C, int TT>\nint launch_one(")] + "}",   # ... of ncc_direct.cu
              nm[nm.index("namespace {"):nm.index("}  // namespace") + 1],          # ... of nms.cu
              bm[bm.index("namespace {"):bm.index("}  // namespace") + 1],          # ... of box_moments.cu
-             "namespace {",
-             _function(tc, "template <bool STREAM>\n__global__ void window_moments_kernel("),
-             _function(tc, "template <int C>\n__global__ void __launch_bounds__(256)\nwindow_moments_rows_kernel("),
-             "}",
+             tcn, tc_host,
              r'''
 extern "C" int emu_sizeof_tmplmeta() { return (int)sizeof(TmplMeta); }
 extern "C" void emu_transform(const uint8_t* src, uint8_t* dst, const XformDesc* descs, int n_out, int C, int dtype, int f, int grid_x)
@@ -228,6 +235,55 @@ extern "C" int emu_box_moments(const uint8_t* img, int64_t pitch, int C, int h, 
     else if (C == 4) emu_launch_coop(grid, block, [&] { box_moments_kernel<4>(p); });
     else return -1;
     return (int)(grid.x * grid.y);
+}
+// One tcgen05 launch of a template group, as launch_toeplitz_prep + launch_ncc_tc_impl (ncc_tc.cu) set it up; the tile height N,
+// the ring (ds, stages), the number of epilogue warps and the number of persistent CTAs are the caller's (the library derives
+// them from a clock model; every valid choice must give the same maps).  persist = 0: the one-tile-per-CTA kernel.
+// method 5 -> MODE 0 (integer / fp32 epilogue on the window moments), else MODE 1 (float64 epilogue on the tables).
+extern "C" long long emu_ncc_tc(const uint8_t* img, int64_t pitch, int H, int W, int C, const uint8_t* tmpl, const TmplMeta* meta,
+                                const int32_t* order, int count, int mode, int h, int w, int h_min, int w_min,
+                                const uint32_t* S, const float* rsD, int64_t mom_plane, const uint32_t* sat_s,
+                                const unsigned long long* sat_q, int64_t sat_pitch, float* maps, int method, int N, int stages, int ds,
+                                int EW, int persist, int ctas, DevHit* cand, int32_t* cand_count, int cand_cap, float cand_thr)
+{
+    TcGroup g{};
+    if (!tc_plan_group(mode, h, w, C, g)) return -1;
+    std::vector<uint8_t> slab_store((size_t)h * g.slab_bytes + 64);
+    uint8_t* slabs = slab_store.data() + ((64 - (reinterpret_cast<uintptr_t>(slab_store.data()) & 63)) & 63);
+    const int64_t pieces = (int64_t)h * (g.slab_bytes / 16);
+    emu_launch(dim3((unsigned)std::min<int64_t>((pieces + 255) / 256, 4096)), dim3(256),
+               [&] { toeplitz_prep_kernel(tmpl, meta, order, count, mode, h, w, g.nk, g.slab_bytes, C, slabs, nullptr); });
+    TcParams p{};
+    p.method = method;
+    p.sat = SatView{sat_s, sat_q, sat_pitch, (int64_t)(H + 1) * sat_pitch};
+    p.img = img; p.pitch = pitch; p.H = H; p.W = W;
+    p.slabs = slabs; p.slab_bytes = g.slab_bytes; p.a_kblk = g.a_kblk; p.nk = g.nk;
+    p.mode = mode; p.h = h; p.w = w; p.mh = H - h_min + 1; p.mw = W - w_min + 1;
+    p.meta = meta; p.order = order; p.count = count; p.S = S; p.rsD = rsD; p.maps = maps; p.C = C; p.mom_plane = mom_plane;
+    if (cand) { p.cand = cand; p.cand_count = cand_count; p.cand_cap = cand_cap; p.cand_thr = cand_thr; }
+    const int xw = mode == 0 ? 16 : 128, gx = (p.mw + xw - 1) / xw;
+    p.N = N; p.R = N + h - 1;
+    static uint8_t smem_store[227 * 1024 + 1024];
+    emu_dyn_smem = smem_store + ((1024 - (reinterpret_cast<uintptr_t>(smem_store) & 1023)) & 1023);
+    memset(emu_dyn_smem, 0xCD, 227 * 1024);
+    emu_tc_reset();
+    const size_t tile_b = ((size_t)2 * g.nk * p.R * 16 + 127) & ~(size_t)127;
+    const int kmode = method != MTM_TM_CCOEFF_NORMED ? 1 : 0;
+    if (persist) {
+        p.ds = std::max(1, std::min(h, ds)); p.stages = stages;
+        if (stages < 2 || stages > TCP_MAX_STAGES || 256 + 2 * tile_b + (size_t)stages * p.ds * g.slab_bytes > 227 * 1024) return -2;
+        p.tiles_x = gx; p.tiles_total = gx * ((p.mh + N - 1) / N);
+        const dim3 grid((unsigned)std::min(p.tiles_total, ctas)), block(32 * (EW + 4));
+        if (EW == 12) { if (kmode) emu_launch_coop(grid, block, [&] { ncc_tc_persist_kernel<false, 12, 1>(p); }); else emu_launch_coop(grid, block, [&] { ncc_tc_persist_kernel<false, 12, 0>(p); }); }
+        else { if (kmode) emu_launch_coop(grid, block, [&] { ncc_tc_persist_kernel<false, 8, 1>(p); }); else emu_launch_coop(grid, block, [&] { ncc_tc_persist_kernel<false, 8, 0>(p); }); }
+    } else {
+        p.ds = g.ds;
+        if (tile_b + (size_t)TC_STAGES * g.ds * g.slab_bytes + 256 > 227 * 1024) return -2;
+        const dim3 grid(gx, (p.mh + N - 1) / N), block(TC_THREADS);
+        if (kmode) emu_launch_coop(grid, block, [&] { ncc_tc_kernel<1>(p); }); else emu_launch_coop(grid, block, [&] { ncc_tc_kernel<0>(p); });
+    }
+    emu_dyn_smem = nullptr;
+    return emu_mma_count;
 }
 ''']
     d = tmp_path_factory.mktemp("emu")
@@ -779,3 +835,130 @@ def test_box_sum_moment_kernel_equals_the_summed_area_one(emu, channels, shape, 
     assert np.array_equal(outs[0][1].view(np.uint32), outs[1][1].view(np.uint32))
     first = outs[1][0][off] if channels > 1 else outs[1][0][2 * off]
     assert int(first) == int(wide[:h, :w, 0].sum())
+
+
+# ---- the tcgen05 kernels on the functional model of tests/emu/tcgen05_model.h -----------------------------------------------
+
+def _host_tensor_maps(emu, image, tmpls, method, mode, N, stages=3, ds=4, EW=8, persist=True, ctas=2, cand_thr=None, box=False):
+    """ncc_tc.cu on the host for ONE template group (mode A: up to 8 templates of mixed sizes, zero padded to the largest; mode B:
+    one grayscale template x 128 x-offsets): summed-area tables, template statistics, window moments, Toeplitz slabs, then the
+    persistent (or the one-tile-per-CTA) kernel.  Returns (maps, number of MMAs issued, candidate records or None)."""
+    H, W = image.shape[:2]
+    C = 1 if image.ndim == 2 else image.shape[2]
+    ipitch = (W * C + 64 * C + 64 + 127) // 128 * 128                        # mtm_set_image's tile layout: zero padded rows
+    buf = np.zeros(H * ipitch + 256, np.uint8)
+    buf[:H * ipitch].reshape(H, ipitch)[:, :W * C] = image.reshape(H, W * C)
+    _, _, sat_s, sat_q, sat_q32, spitch = _host_sat(emu, image)
+    arena, meta = _pack_templates([t.reshape(t.shape[0], t.shape[1], C) for t in tmpls], C)
+    order = np.asarray(sorted(range(len(tmpls)), key=lambda k: tmpls[k].shape[:2]), np.int32)      # (h, w) order of finish_templates
+    sizes, moff, off = [], 0, 0
+    for k in range(len(tmpls)):
+        h, w = tmpls[k].shape[:2]
+        meta[k]["mh"], meta[k]["mw"], meta[k]["map_off"] = H - h + 1, W - w + 1, off
+        off += ((H - h + 1) * (W - w + 1) + 31) // 32 * 32
+    for k in order:
+        h, w = tmpls[k].shape[:2]
+        if not sizes or (sizes[-1][0], sizes[-1][1]) != (h, w):
+            sizes.append((h, w, H - h + 1, W - w + 1, moff))
+            moff += ((H - h + 1) * (W - w + 1) + 31) // 32 * 32
+        meta[k]["mom_off"] = sizes[-1][4]
+    emu.emu_tmpl_stats(_ptr(arena), _ptr(meta), len(tmpls), C)
+    sd = np.zeros(len(sizes), SIZE_DTYPE)
+    for k, v in enumerate(sizes):
+        sd[k] = v
+    S = np.full(moff * max(2, C), 0xDEADBEEF, np.uint32)
+    R = np.full(moff, np.nan, np.float32)
+    if box:
+        assert len(sizes) == 1
+        emu.emu_box_moments(_ptr(buf), ctypes.c_int64(ipitch), C, sizes[0][0], sizes[0][1], sizes[0][2], sizes[0][3], _ptr(S), _ptr(R),
+                            ctypes.c_int64(0), ctypes.c_int64(moff), 7)
+    else:
+        emu.emu_moments(0, _ptr(sat_s), _ptr(sat_q32), ctypes.c_int64(spitch), ctypes.c_int64((H + 1) * spitch), _ptr(sd), len(sizes), C,
+                        _ptr(S), _ptr(R), ctypes.c_int64(moff), 2, 1)
+    maps = np.full(off + 32, np.nan, np.float32)
+    hs, ws = [t.shape[0] for t in tmpls], [t.shape[1] for t in tmpls]
+    cand = np.zeros(4096, DEVHIT_DTYPE)
+    cand_count = np.zeros(1, np.int32)
+    emu.emu_ncc_tc.restype = ctypes.c_longlong
+    n_mma = emu.emu_ncc_tc(_ptr(buf), ctypes.c_int64(ipitch), H, W, C, _ptr(arena), _ptr(meta), _ptr(order), len(tmpls), mode,
+                           max(hs), max(ws), min(hs), min(ws), _ptr(S), _ptr(R), ctypes.c_int64(moff), _ptr(sat_s), _ptr(sat_q),
+                           ctypes.c_int64(spitch), _ptr(maps), method, N, stages, ds, EW, int(persist), ctas,
+                           _ptr(cand) if cand_thr is not None else None, _ptr(cand_count), len(cand),
+                           ctypes.c_float(cand_thr if cand_thr is not None else 0.0))
+    assert n_mma > 0, n_mma
+    out = [maps[int(m["map_off"]):int(m["map_off"]) + int(m["mh"]) * int(m["mw"])].reshape(int(m["mh"]), int(m["mw"])) for m in meta]
+    return out, n_mma, (cand[:int(cand_count[0])] if cand_thr is not None else None)
+
+
+def _planted(rng, H, W, C, shapes):
+    img = rng.integers(0, 256, (H, W, C)).astype(np.uint8)
+    img[H // 2:H // 2 + 14, W // 3:W // 3 + 40] = 90                          # a flat patch: zero-variance windows for the small templates
+    tmpls = []
+    for h, w in shapes:
+        y0, x0 = int(rng.integers(0, H - h + 1)), int(rng.integers(0, W - w + 1))
+        t = np.clip(img[y0:y0 + h, x0:x0 + w].astype(np.int64) + rng.integers(-25, 26, (h, w, C)), 0, 255).astype(np.uint8)
+        tmpls.append(t)
+    if C == 1:
+        return img[:, :, 0], [t[:, :, 0] for t in tmpls]
+    return img, tmpls
+
+
+@pytest.mark.parametrize("channels,shapes,N,opts", [
+    (1, [(17, 20), (12, 9), (17, 20)], 32, dict()),                            # mixed sizes in one mode-A group, 12 tiles over 2 CTAs
+    (1, [(17, 20), (12, 9), (17, 20)], 48, dict(EW=12, stages=2, ds=1, ctas=3)),
+    (1, [(17, 20), (12, 9), (17, 20)], 32, dict(persist=False)),              # the one-tile-per-CTA kernel
+    (3, [(10, 13), (10, 13)], 32, dict(stages=4, ds=3)),                      # RGB: C-byte x-step of the band, per-channel moments
+    (4, [(9, 6)], 16, dict(ctas=5)),
+    (1, [(8, 8)] * 8, 64, dict(ctas=1)),                                      # a full group of eight, one CTA walks every tile
+])
+def test_tensor_core_kernel_on_the_functional_model(emu, channels, shapes, N, opts):
+    """ncc_tc_persist_kernel / ncc_tc_kernel, mode A, from their source on the CPU with tests/emu/tcgen05_model.h in place of the PTX
+    wrappers: Toeplitz slabs through the bulk-copy ring, descriptor arithmetic of the row shift, double-buffered image tiles and
+    accumulators, epilogue index maps.  TM_CCOEFF_NORMED maps within 2e-6 of the oracle (fp32 epilogue on exact integers); the
+    float64-epilogue instantiation gives the oracle's bits for TM_CCORR (the raw numerator) and TM_CCORR_NORMED."""
+    from oracle import ncc_exact
+    rng = np.random.default_rng(17 + channels)
+    image, tmpls = _planted(rng, 70, 90, channels, shapes)
+    if len(tmpls) >= 3:
+        tmpls[2] = np.full_like(tmpls[2], 140)                               # a constant template: the map := 1 rule
+    got, n_mma, _ = _host_tensor_maps(emu, image, tmpls, 5, 0, N, **opts)
+    for k, t in enumerate(tmpls):
+        want = ncc_exact.match_template_exact(image, t, 5)
+        assert got[k].shape == want.shape and np.max(np.abs(got[k] - want)) <= 2e-6, (k, float(np.nanmax(np.abs(got[k] - want))))
+    for method in (2, 3):
+        got, _, _ = _host_tensor_maps(emu, image, tmpls, method, 0, N, **opts)
+        for k, t in enumerate(tmpls):
+            want = ncc_exact.match_template_exact(image, t, method)
+            assert np.array_equal(got[k].view(np.uint32), want.view(np.uint32)), (method, k)
+
+
+@pytest.mark.parametrize("N,opts", [(48, dict(ctas=2)), (32, dict(persist=False)), (64, dict(EW=12, stages=5, ds=2, ctas=4))])
+def test_tensor_core_kernel_mode_b_on_the_functional_model(emu, N, opts):
+    """Mode B (one grayscale template x 128 x-offsets): the aliased Toeplitz slab (K blocks 256 bytes apart over 128-byte row groups,
+    so consecutive K blocks re-read the next row groups) and the reversed x-offset order of the accumulator lanes."""
+    from oracle import ncc_exact
+    rng = np.random.default_rng(23)
+    image, tmpls = _planted(rng, 60, 300, 1, [(14, 33)])                     # 268 window columns: three x tiles, the last one partial
+    got, n_mma, _ = _host_tensor_maps(emu, image, tmpls, 5, 1, N, **opts)
+    want = ncc_exact.match_template_exact(image, tmpls[0], 5)
+    assert np.max(np.abs(got[0] - want)) <= 2e-6
+    nk = (33 + 127 + 31) // 32
+    assert n_mma == 3 * ((47 + N - 1) // N) * 14 * nk                        # tiles x template rows x K chunks: nothing issued twice
+    got, _, _ = _host_tensor_maps(emu, image, tmpls, 2, 1, N, **opts)
+    assert np.array_equal(got[0].view(np.uint32), ncc_exact.match_template_exact(image, tmpls[0], 2).view(np.uint32))
+
+
+def test_tensor_core_epilogue_lists_the_candidates_and_takes_box_sum_moments(emu):
+    """The default epilogue appends every pixel above the threshold to the candidate list (the peak pass then visits only those);
+    with the window moments coming from box_moments_kernel instead of the summed-area tables the maps do not change by a bit."""
+    rng = np.random.default_rng(29)
+    image, tmpls = _planted(rng, 70, 90, 1, [(16, 16), (16, 16)])
+    ref, _, _ = _host_tensor_maps(emu, image, tmpls, 5, 0, 32)
+    got, _, cand = _host_tensor_maps(emu, image, tmpls, 5, 0, 32, cand_thr=0.25, box=True)
+    listed = set()
+    for k in range(2):
+        assert np.array_equal(got[k].view(np.uint32), ref[k].view(np.uint32))
+        ys, xs = np.nonzero(got[k] > np.float32(0.25))
+        listed |= {(k, int(x), int(y), 16, 16, float(got[k][y, x])) for y, x in zip(ys, xs)}
+    assert len(listed) >= 2
+    assert sorted((int(c["tmpl"]), int(c["x"]), int(c["y"]), int(c["w"]), int(c["h"]), float(c["score"])) for c in cand) == sorted(listed)
