@@ -1,11 +1,15 @@
-"""CPU tests of device code: the SIMPLE kernels of csrc/ (no shared memory, no warp intrinsics, no PTX) are compiled
-for the host behind tests/emu/cuda_runtime.h -- their source text is taken verbatim from the .cu files -- and run on the
-CPU (serially, or one OS thread per CUDA thread when the kernel uses barriers / shuffles / shared memory).  Checks, bit for bit and without a GPU:
-  * transform.cu: the 8 symmetries and the integer-factor INTER_AREA rounding against numpy / the restated OpenCV rule
-    (which tests/test_oracle.py pins to the live cv2.resize);
-  * ncc_tc.cu: the row-walking window-moment kernel (experiment knob MTM_B200_MOM_ROWS) writes exactly what the default
-    grid-stride kernel writes.
-TEST INFRASTRUCTURE: the emulation is a checker of kernel logic, not a CPU path of the product."""
+"""CPU tests of device code: every kernel of csrc/ is compiled for the host -- source text taken from the .cu files as it is, apart
+from `extern __shared__` declarations (a pointer handed over by the launcher) and two `fence.mbarrier_init` lines -- behind
+tests/emu/cuda_runtime.h (one OS thread per CUDA thread of a block: barriers, shuffles, votes, shared memory, atomics) and, for the
+tcgen05 kernels of ncc_tc.cu, tests/emu/tcgen05_model.h (a functional model of mbarriers, bulk copies, tensor memory and tcgen05.mma
+kind::i8 that takes the place of the file's PTX wrappers).  Without a GPU this checks, mostly bit for bit:
+  * transform.cu, window_stats.cu, ncc_direct.cu, ncc_points.cu, peaks.cu, nms.cu against numpy / oracle/ and, behind
+    MTM.matchTemplates, against the golden vectors of the unmodified reference;
+  * ncc_tc.cu (persistent and one-tile kernels, modes A / B, both epilogues, the 16-bit accumulate flavour), ncc_float.cu (float32 and
+    masked matching) against the oracle;
+  * the experiment-knob kernels (row-walking and box-sum window moments) against the default moment kernel.
+TEST INFRASTRUCTURE: the emulation is a checker of kernel LOGIC (one legal order of execution, no timing), not a CPU path of the
+product; whether sm_100a hardware agrees with the model is what the -m gpu tests establish."""
 import ctypes
 import os
 import shutil
@@ -54,6 +58,14 @@ def emu(tmp_path_factory):
         assert tcn.count(text) == count, text
         tcn = tcn.replace(text, repl)
     assert "asm" not in tcn
+    fl = open(os.path.join(CSRC, "ncc_float.cu")).read()
+    dynf = "extern __shared__ float smemf[];"
+    assert fl.count(dynf) == 1
+    fl = fl.replace(dynf, "float* smemf = reinterpret_cast<float*>(emu_dyn_smem);")
+    a, b = fl.index("template <int C, int TT>\nint launch_f("), fl.index("// ------------------------------------------------------------------ masked matching")
+    fl_dev = fl[fl.index("namespace {"):a] + fl[b:fl.index("}  // namespace") + 1]            # device code of ncc_float.cu without its launchers
+    a = fl.index("namespace {", fl.index("// ------------------------------------------------------------------ 16-bit images"))
+    fl_dev += "\n" + fl[a:fl.index("}  // namespace", a) + 1]                                 # ... and the 16-bit kernels
     tc_host = tc[tc.index("struct TcEnv {"):tc.index("int launch_toeplitz_prep(")]       # experiment knobs + tc_plan_group (plain host code)
     parts = ['#include "cuda_runtime.h"', '#include "tcgen05_model.h"', '#include "mtm_internal.cuh"', '#include "ncc_epilogue.cuh"',
              xf[xf.index("namespace {"):xf.index("}  // namespace") + 1],          # all device code of transform.cu
@@ -63,7 +75,7 @@ def emu(tmp_path_factory):
              dr[dr.index("namespace {"):dr.index("template <int C, int TT>\nint launch_one(")] + "}",   # ... of ncc_direct.cu
              nm[nm.index("namespace {"):nm.index("}  // namespace") + 1],          # ... of nms.cu
              bm[bm.index("namespace {"):bm.index("}  // namespace") + 1],          # ... of box_moments.cu
-             tcn, tc_host,
+             tcn, tc_host, fl_dev,
              r'''
 extern "C" int emu_sizeof_tmplmeta() { return (int)sizeof(TmplMeta); }
 extern "C" void emu_transform(const uint8_t* src, uint8_t* dst, const XformDesc* descs, int n_out, int C, int dtype, int f, int grid_x)
@@ -284,6 +296,132 @@ extern "C" long long emu_ncc_tc(const uint8_t* img, int64_t pitch, int H, int W,
     }
     emu_dyn_smem = nullptr;
     return emu_mma_count;
+}
+// float32 branch (ncc_float.cu): launch_build_sat_f32 + launch_tmpl_stats_f32 + launch_ncc_direct_f32 restated for one group of
+// equal-sized templates.  `arena` holds the packed float32 templates, `centred` receives their mean-centred copies.
+static int emu_f32_launch(const FloatParams& p0, int C, int count, int we4)
+{
+    FloatParams p = p0;
+    const int BXf = (C == 1) ? FBX : 16;
+    int TT = count >= 4 ? 4 : count >= 2 ? 2 : 1;
+    int TW = BXf * C + we4 + 8;
+    TW = ((TW + 31) / 32) * 32 + 8;
+    const int CH = p.h < 8 ? p.h : 8;
+    p.CH = CH; p.TW = TW;
+    const size_t smem = ((size_t)(FBY + CH) * TW + (size_t)TT * CH * we4) * sizeof(float);
+    if (smem > 200 * 1024) return -1;
+    std::vector<uint8_t> dyn(smem + 64, 0xCD);
+    emu_dyn_smem = dyn.data();
+    dim3 grid((p.mw + BXf - 1) / BXf, (p.mh + FBY - 1) / FBY, (count + TT - 1) / TT), block(FTHREADS);
+#define EMU_F32(CC) \
+    switch (TT) { \
+        case 1: emu_launch_coop(grid, block, [&] { ncc_direct_f32_kernel<CC, 1>(p); }); break; \
+        case 2: emu_launch_coop(grid, block, [&] { ncc_direct_f32_kernel<CC, 2>(p); }); break; \
+        default: emu_launch_coop(grid, block, [&] { ncc_direct_f32_kernel<CC, 4>(p); }); break; \
+    }
+    if (C == 1) { EMU_F32(1) } else if (C == 3) { EMU_F32(3) } else if (C == 4) { EMU_F32(4) } else return -1;
+#undef EMU_F32
+    emu_dyn_smem = nullptr;
+    return TT;
+}
+extern "C" void emu_satf(const float* img, int64_t pitch_e, int H, int W, int C, double* scratch, double* sat_s, double* sat_q, int64_t sat_pitch)
+{
+    if (C == 1) emu_launch_coop(dim3(H), dim3(256), [&] { satf_rows_kernel<1>(img, pitch_e, H, W, scratch); });
+    else if (C == 3) emu_launch_coop(dim3(H), dim3(256), [&] { satf_rows_kernel<3>(img, pitch_e, H, W, scratch); });
+    else emu_launch_coop(dim3(H), dim3(256), [&] { satf_rows_kernel<4>(img, pitch_e, H, W, scratch); });
+    emu_launch_coop(dim3((W + 1 + 31) / 32, C + 1), dim3(32, 32), [&] { satf_cols_kernel(scratch, H, W, C, sat_s, sat_q, sat_pitch); });
+}
+extern "C" int emu_ncc_f32(const float* img, int64_t pitch_e, int H, int W, int C, const double* sat_s, const double* sat_q, int64_t sat_pitch,
+                           const float* arena, float* centred, TmplMeta* meta, int n_tmpl, int stats, const int32_t* order, int count,
+                           float* maps, int method)
+{
+    if (stats) emu_launch_coop(dim3(n_tmpl), dim3(256), [&] { tmplf_stats_kernel(arena, centred, meta, C); });
+    const TmplMeta& m0 = meta[order[0]];
+    FloatParams p{};
+    p.img = img; p.pitch_e = pitch_e; p.H = H; p.W = W;
+    p.sat_s = sat_s; p.sat_q = sat_q; p.sat_pitch = sat_pitch; p.sat_plane = (int64_t)(H + 1) * sat_pitch;
+    p.centred = (method == MTM_TM_CCOEFF || method == MTM_TM_CCOEFF_NORMED) ? 1 : 0;
+    p.tmpl = p.centred ? centred : arena;
+    p.meta = meta; p.order = order; p.maps = maps;
+    p.count = count; p.h = m0.h; p.w = m0.w; p.mh = m0.mh; p.mw = m0.mw; p.method = method;
+    return emu_f32_launch(p, C, count, (m0.w * C + 3) & ~3);
+}
+// masked matching, methods 0 / 3 (compute_maps_masked in mtm_api.cu): T*M^2 and M^2 arenas, image and image^2 in float32, two plain
+// correlations, the combine kernel.  `img8` != nullptr: uint8 image (pitch in bytes), else the float image already in `imgf`.
+extern "C" int emu_masked(const uint8_t* img8, int64_t pitch8, float* imgf, float* imgf2, int64_t pitch_e, int H, int W, int C,
+                          const uint8_t* raw_t, const uint8_t* raw_m, int is_f32, float* tm2, float* m2, TmplMeta* meta, int n_tmpl,
+                          const int32_t* order, int count, float* mapsA, float* mapsB, int method)
+{
+    emu_launch_coop(dim3(n_tmpl), dim3(256), [&] { masked_prep_kernel(raw_t, raw_m, is_f32, tm2, m2, meta, C); });
+    emu_launch(dim3(4), dim3(256), [&] { u8_to_f32_sq_kernel(img8, pitch8, imgf, imgf, imgf2, pitch_e, H, W * C); });
+    const TmplMeta& m0 = meta[order[0]];
+    FloatParams p{};
+    p.pitch_e = pitch_e; p.H = H; p.W = W; p.centred = 0;
+    p.meta = meta; p.order = order; p.count = count; p.h = m0.h; p.w = m0.w; p.mh = m0.mh; p.mw = m0.mw; p.method = MTM_TM_CCORR;
+    const int we4 = (m0.w * C + 3) & ~3;
+    p.img = imgf; p.tmpl = tm2; p.maps = mapsA;
+    if (emu_f32_launch(p, C, count, we4) < 0) return -1;
+    p.img = imgf2; p.tmpl = m2; p.maps = mapsB;
+    if (emu_f32_launch(p, C, count, we4) < 0) return -1;
+    emu_launch(dim3(2, n_tmpl), dim3(256), [&] { masked_combine_kernel(mapsA, mapsB, meta, method); });
+    return 0;
+}
+// The 16-bit grayscale route (compute_maps with tensor16 in mtm_api.cu): u16_split_image_kernel -> float32 image + high / low byte
+// planes; float64 tables; float32 template statistics; Toeplitz slabs of both template byte planes; four accumulate launches
+// (MODE = 2) CC = 65536 hh + 256 (hl + lh) + ll into the float64 map; cc16_epilogue_kernel.  One template group.
+extern "C" long long emu_ncc_tc16(const uint16_t* src, int H, int W, float* pixf, int64_t pitch_e, uint8_t* hi, uint8_t* lo, int64_t pitch,
+                                  double* scratch, double* sat_s, double* sat_q, int64_t sat_pitch, const float* arena, float* centred,
+                                  TmplMeta* meta, const uint8_t* tmpl8, int64_t tmpl8_plane, const TmplPix8* pix8, const int32_t* order,
+                                  int count, int mode, int h, int w, int h_min, int w_min, double* acc, float* maps, int method,
+                                  int N, int stages, int ds, int ctas, int epilogue_only)
+{
+    int64_t n_px = 0;
+    for (int t = 0; t < count; ++t) n_px = std::max<int64_t>(n_px, (int64_t)meta[t].mh * meta[t].mw);
+    if (epilogue_only) {                                    // the numerator map does not depend on the method
+        emu_launch(dim3((unsigned)std::max<int64_t>(1, (n_px + 255) / 256), (unsigned)count), dim3(256),
+                   [&] { cc16_epilogue_kernel(acc, maps, meta, 0, method, sat_s, sat_q, sat_pitch); });
+        return 1;
+    }
+    emu_launch(dim3((unsigned)std::min(8, (W + 255) / 256), (unsigned)H), dim3(256),
+               [&] { u16_split_image_kernel(src, (int64_t)W, H, W, pixf, pitch_e, hi, lo, pitch); });
+    emu_satf(pixf, pitch_e, H, W, 1, scratch, sat_s, sat_q, sat_pitch);
+    emu_launch_coop(dim3(count), dim3(256), [&] { tmplf_stats_kernel(arena, centred, meta, 1); });
+    TcGroup g{};
+    if (!tc_plan_group(mode, h, w, 1, g)) return -1;
+    std::vector<uint8_t> slab_store((size_t)2 * h * g.slab_bytes + 64);
+    uint8_t* slabs = slab_store.data() + ((64 - (reinterpret_cast<uintptr_t>(slab_store.data()) & 63)) & 63);
+    const int64_t slab_plane = (int64_t)h * g.slab_bytes;
+    const int64_t pieces = (int64_t)h * (g.slab_bytes / 16);
+    for (int plane = 0; plane < 2; ++plane)
+        emu_launch(dim3((unsigned)std::min<int64_t>((pieces + 255) / 256, 4096)), dim3(256),
+                   [&] { toeplitz_prep_kernel(tmpl8 + plane * tmpl8_plane, meta, order, count, mode, h, w, g.nk, g.slab_bytes, 1, slabs + plane * slab_plane, pix8); });
+    static uint8_t smem_store[227 * 1024 + 1024];
+    long long mmas = 0;
+    const int planes[4][2] = {{0, 0}, {0, 1}, {1, 0}, {1, 1}};
+    const double weights[4] = {65536.0, 256.0, 256.0, 1.0};
+    for (int k = 0; k < 4; ++k) {
+        TcParams p{};
+        p.method = MTM_TM_CCORR;
+        p.img = planes[k][0] ? lo : hi; p.pitch = pitch; p.H = H; p.W = W;
+        p.slabs = slabs + planes[k][1] * slab_plane; p.slab_bytes = g.slab_bytes; p.a_kblk = g.a_kblk; p.nk = g.nk;
+        p.mode = mode; p.h = h; p.w = w; p.mh = H - h_min + 1; p.mw = W - w_min + 1;
+        p.meta = meta; p.order = order; p.count = count; p.maps = maps; p.C = 1;
+        p.acc = acc; p.acc_weight = weights[k]; p.acc_first = k == 0 ? 1 : 0;
+        const int xw = mode == 0 ? 16 : 128, gx = (p.mw + xw - 1) / xw;
+        p.N = N; p.R = N + h - 1; p.ds = std::max(1, std::min(h, ds)); p.stages = stages;
+        p.tiles_x = gx; p.tiles_total = gx * ((p.mh + N - 1) / N);
+        const size_t tile_b = ((size_t)2 * g.nk * p.R * 16 + 127) & ~(size_t)127;
+        if (256 + 2 * tile_b + (size_t)stages * p.ds * g.slab_bytes > 227 * 1024) return -2;
+        emu_dyn_smem = smem_store + ((1024 - (reinterpret_cast<uintptr_t>(smem_store) & 1023)) & 1023);
+        memset(emu_dyn_smem, 0xCD, 227 * 1024);
+        emu_tc_reset();
+        emu_launch_coop(dim3((unsigned)std::min(p.tiles_total, ctas)), dim3(32 * 12), [&] { ncc_tc_persist_kernel<false, 8, 2>(p); });
+        mmas += emu_mma_count;
+    }
+    emu_dyn_smem = nullptr;
+    emu_launch(dim3((unsigned)std::max<int64_t>(1, (n_px + 255) / 256), (unsigned)count), dim3(256),
+               [&] { cc16_epilogue_kernel(acc, maps, meta, 0, method, sat_s, sat_q, sat_pitch); });
+    return mmas;
 }
 ''']
     d = tmp_path_factory.mktemp("emu")
@@ -962,3 +1100,187 @@ def test_tensor_core_epilogue_lists_the_candidates_and_takes_box_sum_moments(emu
         listed |= {(k, int(x), int(y), 16, 16, float(got[k][y, x])) for y, x in zip(ys, xs)}
     assert len(listed) >= 2
     assert sorted((int(c["tmpl"]), int(c["x"]), int(c["y"]), int(c["w"]), int(c["h"]), float(c["score"])) for c in cand) == sorted(listed)
+
+
+# ---- float32 branch and masked matching (ncc_float.cu) --------------------------------------------------------------------
+
+def _f32_arena(tmpls, C):
+    """mtm_set_templates for float32: rows of w*C floats, 16-byte aligned template starts."""
+    meta = np.zeros(len(tmpls), TMPL_META_DTYPE)
+    off = 0
+    for k, t in enumerate(tmpls):
+        h, w = t.shape[:2]
+        meta[k]["pix_off"], meta[k]["h"], meta[k]["w"], meta[k]["wp"] = off, h, w, w * C * 4
+        off += (h * w * C * 4 + 15) // 16 * 16
+    arena = np.zeros(off // 4 + 16, np.float32)
+    for k, t in enumerate(tmpls):
+        o = int(meta[k]["pix_off"]) // 4
+        arena[o:o + t.size] = t.astype(np.float32).ravel()
+    return arena, meta
+
+
+def _geometry(meta, tmpls, H, W):
+    off = 0
+    for k, t in enumerate(tmpls):
+        mh, mw = H - t.shape[0] + 1, W - t.shape[1] + 1
+        meta[k]["mh"], meta[k]["mw"], meta[k]["map_off"] = mh, mw, off
+        off += (mh * mw + 31) // 32 * 32
+    return off
+
+
+def _maps_of(flat, meta):
+    return [flat[int(m["map_off"]):int(m["map_off"]) + int(m["mh"]) * int(m["mw"])].reshape(int(m["mh"]), int(m["mw"])) for m in meta]
+
+
+@pytest.mark.parametrize("channels,count", [(1, 1), (1, 5), (3, 2), (4, 1)])
+def test_float32_kernels_on_the_host(emu, channels, count):
+    """satf_rows / satf_cols (float64 tables), tmplf_stats_kernel (OpenCV constants + mean-centred copy) and ncc_direct_f32_kernel for
+    equal-sized float32 templates: all six methods within the GPU parity bar (1e-4 of max(1, max |exact|)) of the oracle's
+    exact maps; 16-bit-valued data as the reference's uint16 -> float32 cast produces it."""
+    from oracle import ncc_exact
+    rng = np.random.default_rng(60 + channels)
+    H, W, h, w = 50, 77, 11, 14
+    image8, tmpls8 = _planted(rng, H, W, channels, [(h, w)] * count)
+    scale = np.float32(97.0)                                                  # 16-bit range
+    image = image8.astype(np.float32) * scale
+    tmpls = [t.astype(np.float32) * scale for t in tmpls8]
+    if count >= 3:
+        tmpls[1] = np.full_like(tmpls[1], 1234.0)                            # constant template
+    pitch_e = (W * channels + 3) // 4 * 4
+    img = np.zeros(H * pitch_e + 64, np.float32)
+    img[:H * pitch_e].reshape(H, pitch_e)[:, :W * channels] = image.reshape(H, W * channels)
+    spitch = (W + 1 + 3) // 4 * 4
+    scratch = np.zeros(2 * (channels + 1) * H * W + 16, np.float64)
+    sat_s = np.full((channels, H + 1, spitch), np.nan)
+    sat_q = np.full((H + 1, spitch), np.nan)
+    emu.emu_satf(_ptr(img), ctypes.c_int64(pitch_e), H, W, channels, _ptr(scratch), _ptr(sat_s), _ptr(sat_q), ctypes.c_int64(spitch))
+    wide = image.reshape(H, W, channels).astype(np.float64)
+    for c in range(channels):                                                 # the tables themselves: float64 prefix sums (exact here: integers)
+        want = np.zeros((H + 1, W + 1))
+        want[1:, 1:] = wide[:, :, c].cumsum(0).cumsum(1)
+        assert np.array_equal(sat_s[c, :, :W + 1], want)
+    arena, meta = _f32_arena(tmpls, channels)
+    total = _geometry(meta, tmpls, H, W)
+    centred = np.full_like(arena, np.nan)
+    order = np.arange(count, dtype=np.int32)
+    for method in range(6):
+        maps = np.full(total + 32, np.nan, np.float32)
+        tt = emu.emu_ncc_f32(_ptr(img), ctypes.c_int64(pitch_e), H, W, channels, _ptr(sat_s), _ptr(sat_q), ctypes.c_int64(spitch), _ptr(arena),
+                             _ptr(centred), _ptr(meta), count, int(method == 0), _ptr(order), count, _ptr(maps), method)
+        assert tt == (4 if count >= 4 else 2 if count >= 2 else 1)
+        for k, got in enumerate(_maps_of(maps, meta)):
+            want = ncc_exact.match_template_exact(image, tmpls[k], method)
+            scale = max(1.0, float(np.abs(want).max()))                       # the bar of tests/test_gpu_float.py
+            assert np.max(np.abs(got.astype(np.float64) - want)) <= 1e-4 * scale, (method, k, float(np.max(np.abs(got - want))), scale)
+    for k, t in enumerate(tmpls):                                             # the mean-centred copies
+        o = int(meta[k]["pix_off"]) // 4
+        mean = t.reshape(-1, channels).astype(np.float64).mean(0)
+        assert np.allclose(centred[o:o + t.size].reshape(-1, channels), t.reshape(-1, channels) - mean, rtol=0, atol=1e-2)
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.float32])
+@pytest.mark.parametrize("channels", [1, 3])
+def test_masked_kernels_on_the_host(emu, dtype, channels):
+    """Masked matching (methods 0 / 3; the optional third element of MTM's template tuples): masked_prep_kernel, the float image and
+    its square, two plain correlations and masked_combine_kernel against the oracle's restatement of OpenCV's matchTemplateMask --
+    binary uint8 masks and weighted float32 masks."""
+    from oracle import ncc_exact
+    rng = np.random.default_rng(80 + channels)
+    H, W, h, w = 40, 61, 9, 12
+    image8, tmpls8 = _planted(rng, H, W, channels, [(h, w), (h, w)])
+    if dtype == np.uint8:
+        image, tmpls = image8, tmpls8
+        masks = [(rng.random(t.shape) > 0.3).astype(np.uint8) * rng.integers(1, 255, t.shape).astype(np.uint8) for t in tmpls]   # non-zero -> 1
+    else:
+        image, tmpls = image8.astype(np.float32), [t.astype(np.float32) for t in tmpls8]
+        masks = [rng.random(t.shape).astype(np.float32) for t in tmpls]
+    arena, meta = _f32_arena(tmpls, channels)                                  # geometry of the float arenas (T*M^2, M^2)
+    total = _geometry(meta, tmpls, H, W)
+    esz = np.dtype(dtype).itemsize
+    raw_t = np.zeros(arena.size * esz + 64, np.uint8)
+    raw_m = np.zeros(arena.size * esz + 64, np.uint8)
+    for k, (t, m) in enumerate(zip(tmpls, masks)):
+        o = int(meta[k]["pix_off"]) // 4 * esz
+        raw_t[o:o + t.nbytes] = np.ascontiguousarray(t).view(np.uint8).ravel()
+        raw_m[o:o + m.nbytes] = np.ascontiguousarray(m).view(np.uint8).ravel()
+    pitch_e = (W * channels + 3) // 4 * 4
+    imgf = np.zeros(H * pitch_e + 64, np.float32)
+    imgf2 = np.zeros(H * pitch_e + 64, np.float32)
+    if dtype == np.uint8:
+        pitch8 = (W * channels + 3) // 4 * 4
+        img8 = np.zeros(H * pitch8 + 16, np.uint8)
+        img8[:H * pitch8].reshape(H, pitch8)[:, :W * channels] = image.reshape(H, W * channels)
+    else:
+        pitch8, img8 = 0, None
+        imgf[:H * pitch_e].reshape(H, pitch_e)[:, :W * channels] = image.reshape(H, W * channels)
+    order = np.arange(2, dtype=np.int32)
+    for method in (0, 3):
+        tm2, m2 = np.full_like(arena, np.nan), np.full_like(arena, np.nan)
+        maps_a, maps_b = np.full(total + 32, np.nan, np.float32), np.full(total + 32, np.nan, np.float32)
+        rc = emu.emu_masked(_ptr(img8) if img8 is not None else None, ctypes.c_int64(pitch8), _ptr(imgf), _ptr(imgf2), ctypes.c_int64(pitch_e),
+                            H, W, channels, _ptr(raw_t), _ptr(raw_m), int(dtype == np.float32), _ptr(tm2), _ptr(m2), _ptr(meta), 2,
+                            _ptr(order), 2, _ptr(maps_a), _ptr(maps_b), method)
+        assert rc == 0
+        for k, got in enumerate(_maps_of(maps_a, meta)):
+            want = ncc_exact.match_template_masked_exact(image, tmpls[k], masks[k], method)
+            scale = max(1.0, float(np.abs(want).max()))
+            assert np.max(np.abs(got.astype(np.float64) - want)) <= 1e-4 * scale, (method, k, float(np.max(np.abs(got - want))), scale)
+
+
+@pytest.mark.parametrize("mode,shapes", [(0, [(13, 18), (10, 9)]), (1, [(12, 30)])])
+def test_sixteen_bit_route_on_the_functional_model(emu, mode, shapes):
+    """uint16 grayscale images and templates: the integers are split into byte planes on the device, the numerator is assembled
+    EXACTLY from four u8 x u8 tensor-core correlations (accumulate flavour of the persistent kernel), then OpenCV's float64 epilogue --
+    all six methods within the float32 bar of the oracle (the reference casts uint16 to float32, MTM/__init__.py:71-74), and the
+    raw numerator (TM_CCORR) equal to the exact integer correlation rounded once to float32."""
+    from oracle import ncc_exact
+    rng = np.random.default_rng(91 + mode)
+    H, W = 52, 170 if mode else 64
+    image = rng.integers(0, 65536, (H, W)).astype(np.uint16)
+    tmpls = []
+    for h, w in shapes:
+        y0, x0 = int(rng.integers(0, H - h + 1)), int(rng.integers(0, W - w + 1))
+        tmpls.append(np.clip(image[y0:y0 + h, x0:x0 + w].astype(np.int64) + rng.integers(-3000, 3001, (h, w)), 0, 65535).astype(np.uint16))
+    count = len(tmpls)
+    arena, meta = _f32_arena(tmpls, 1)
+    total = _geometry(meta, tmpls, H, W)
+    order = np.asarray(sorted(range(count), key=lambda k: tmpls[k].shape), np.int32)
+    pix8 = np.zeros(count, np.dtype([("off", "<i8"), ("wp", "<i4"), ("pad", "<i4")]))
+    total8 = 0
+    for k, t in enumerate(tmpls):
+        pix8[k] = (total8, (t.shape[1] + 3) // 4 * 4, 0)
+        total8 += (int(pix8[k]["wp"]) * t.shape[0] + 15) // 16 * 16
+    planes = np.zeros(2 * total8 + 64, np.uint8)
+    for k, t in enumerate(tmpls):
+        for y in range(t.shape[0]):
+            o = int(pix8[k]["off"]) + y * int(pix8[k]["wp"])
+            planes[o:o + t.shape[1]] = t[y] >> 8
+            planes[total8 + o:total8 + o + t.shape[1]] = t[y] & 255
+    pitch_e = (W + 3) // 4 * 4
+    pitch = (W + 64 + 64 + 127) // 128 * 128
+    pixf = np.zeros(H * pitch_e + 64, np.float32)
+    hi, lo = np.zeros(H * pitch + 256, np.uint8), np.zeros(H * pitch + 256, np.uint8)
+    spitch = (W + 1 + 3) // 4 * 4
+    scratch = np.zeros(4 * H * W + 16, np.float64)
+    sat_s, sat_q = np.full((H + 1, spitch), np.nan), np.full((H + 1, spitch), np.nan)
+    centred = np.full_like(arena, np.nan)
+    src = np.ascontiguousarray(image)
+    hs, ws = [t.shape[0] for t in tmpls], [t.shape[1] for t in tmpls]
+    emu.emu_ncc_tc16.restype = ctypes.c_longlong
+    imagef = image.astype(np.float32)
+    acc = np.full(total + 32, np.nan, np.float64)
+    for method in range(6):
+        maps = np.full(total + 32, np.nan, np.float32)
+        n_mma = emu.emu_ncc_tc16(_ptr(src), H, W, _ptr(pixf), ctypes.c_int64(pitch_e), _ptr(hi), _ptr(lo), ctypes.c_int64(pitch), _ptr(scratch),
+                                 _ptr(sat_s), _ptr(sat_q), ctypes.c_int64(spitch), _ptr(arena), _ptr(centred), _ptr(meta), _ptr(planes),
+                                 ctypes.c_int64(total8), _ptr(pix8), _ptr(order), count, mode, max(hs), max(ws), min(hs), min(ws), _ptr(acc),
+                                 _ptr(maps), method, 32, 3, 4, 2, int(method > 0))
+        assert n_mma > 0, n_mma
+        for k, got in enumerate(_maps_of(maps, meta)):
+            want = ncc_exact.match_template_exact(imagef, tmpls[k].astype(np.float32), method)
+            scale = max(1.0, float(np.abs(want).max()))
+            assert np.max(np.abs(got.astype(np.float64) - want)) <= 1e-4 * scale, (method, k)
+            if method == 2:                                                   # the exact integer numerator, rounded once
+                exact = ncc_exact.cc_direct(image.astype(np.float32), tmpls[k].astype(np.float32))     # float64 sums of integers: exact
+                assert np.array_equal(got, exact.astype(np.float32))
+    assert np.array_equal(hi[:H * pitch].reshape(H, pitch)[:, :W], image >> 8) and np.array_equal(lo[:H * pitch].reshape(H, pitch)[:, :W], image & 255)
