@@ -1,10 +1,11 @@
-// box_moments.cu -- window moments of a template set with ONE window size, straight from the image.
+// box_moments.cu -- window moments of every distinct template size, straight from the image (no summed-area tables).
 //
 // Same outputs, bit for bit, as window_moments_kernel (ncc_tc.cu): per window position the per-channel sums S_c and
 // rsD = rsqrt(A*Q - sum_c S_c^2) (0 for an exactly flat window) -- the denominator statistics that OpenCV's
 // common_matchTemplate takes from integral(img, sum, sqsum) (third-party; reached from MTM/__init__.py:92).  The
 // summed-area route costs three launches per image (row prefixes, column prefixes, moment sweep: 27 + 15 us at
-// BASELINE configs[1]) and ~100 MB of table traffic; when every template has the same size the tables are not needed:
+// BASELINE configs[1]) and, per window position and size, eight table corners through L2 (~24 B with the 8 B written;
+// configs[4]: 64 sizes, 2.4 ms).  Box sums need ~2 image bytes per position instead:
 //
 //   vertical running sums   V_c(y, x') = sum_{dy < h} I_c[y+dy][x'],  VQ(y, x') = sum_c sum_{dy < h} I_c[y+dy][x']^2
 //                           kept in registers, one add (row y+h-1) and one subtract (row y-1) per output row;
@@ -12,8 +13,8 @@
 //                           S_c(y, x) = P_c[x+w] - P_c[x]  -- modulo 2^32, exact because window sums stay below 2^32
 //                           on the tensor path (h*w*C <= 66051).
 //
-// A CTA owns a strip of 1024 image columns (4 per thread, aligned 32-bit loads) and a band of output rows; it first
-// accumulates the h-1 rows above its band (adds only).  HBM-bound by design: the image is read from L2 (each row
+// A CTA owns one size (blockIdx.z), a strip of 1024 image columns (4 per thread, aligned 32-bit loads) and a band of
+// output rows; it first accumulates the h-1 rows above its band (adds only).  HBM-bound by design: the image is read from L2 (each row
 // (band overlap) times), the moment maps are written once: 8 B (C = 1) or 4(C+1) B per window position.
 //
 // Experiment knob MTM_B200_MOM_BOX=1 (mtm_api.cu: the summed-area tables are then built on demand only).  Checked on the
@@ -30,11 +31,9 @@ constexpr int BM_ROW = BM_COLS + 4;                    // prefix row in shared m
 
 struct BoxParams {
     const uint8_t* img; int64_t pitch;                 // zero-padded u8 rows, interleaved channels
-    int h, w, mh, mw;
+    const SizeDesc* sizes;                             // blockIdx.z -> (h, w, mh, mw, offset of its maps)
     uint32_t* S; float* rsD;                           // window_moments_kernel's layout
-    int64_t off, mom_plane;
-    int strip_out;                                     // window positions per strip: a multiple of 4, <= BM_COLS - (w - 1)
-    int band;                                          // output rows per CTA
+    int64_t mom_plane;
 };
 
 template <int C>
@@ -44,9 +43,12 @@ box_moments_kernel(const BoxParams p)
     __shared__ __align__(16) uint32_t P[2][C + 1][BM_ROW];
     __shared__ uint32_t wtot[2][C + 1][BM_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int x0 = blockIdx.x * p.strip_out;           // first image column of the strip == its first window position
-    const int y0 = blockIdx.y * p.band, y1 = min(p.mh, y0 + p.band);
-    if (y0 >= p.mh) return;
+    const SizeDesc sd = p.sizes[blockIdx.z];
+    const int strip_out = (BM_COLS - (sd.w - 1)) & ~3; // window positions per strip: a multiple of 4 (aligned loads)
+    const int band = (sd.mh + (int)gridDim.y - 1) / (int)gridDim.y;
+    const int x0 = blockIdx.x * strip_out;             // first image column of the strip == its first window position
+    const int y0 = blockIdx.y * band, y1 = min(sd.mh, y0 + band);
+    if (x0 >= sd.mw || y0 >= sd.mh) return;            // the grid is sized for the largest map of the launch
     const int64_t col_byte = ((int64_t)x0 + BM_PX * tid) * C;      // a multiple of 4: strip_out and BM_PX are
     uint32_t V[C + 1][BM_PX];
 #pragma unroll
@@ -72,11 +74,11 @@ box_moments_kernel(const BoxParams p)
         }
     };
 
-    for (int r = y0; r < y0 + p.h - 1; ++r) row_update(r, false);
-    const uint32_t area = (uint32_t)p.h * (uint32_t)p.w;
+    for (int r = y0; r < y0 + sd.h - 1; ++r) row_update(r, false);
+    const uint32_t area = (uint32_t)sd.h * (uint32_t)sd.w;
     for (int y = y0; y < y1; ++y) {
         const int buf = (y - y0) & 1;
-        row_update(y + p.h - 1, false);
+        row_update(y + sd.h - 1, false);
         // block-wide exclusive prefix of every quantity along x
         uint32_t incl[C + 1];
 #pragma unroll
@@ -103,18 +105,18 @@ box_moments_kernel(const BoxParams p)
         }
         __syncthreads();
         // window positions tid, tid + 256, ... of the strip: conflict-free shared-memory reads, coalesced stores
-        const int64_t out_row = p.off + (int64_t)y * p.mw;
+        const int64_t out_row = sd.off + (int64_t)y * sd.mw;
 #pragma unroll
         for (int j = 0; j < BM_PX; ++j) {
             const int xl = tid + j * BM_THREADS;
             const int x = x0 + xl;
-            if (xl >= p.strip_out || x >= p.mw) continue;
-            const uint32_t qs = P[buf][C][xl + p.w] - P[buf][C][xl];
+            if (xl >= strip_out || x >= sd.mw) continue;
+            const uint32_t qs = P[buf][C][xl + sd.w] - P[buf][C][xl];
             unsigned long long d1 = (unsigned long long)area * qs;
             uint32_t s0 = 0;
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-                const uint32_t s = P[buf][c][xl + p.w] - P[buf][c][xl];
+                const uint32_t s = P[buf][c][xl + sd.w] - P[buf][c][xl];
                 d1 -= (unsigned long long)s * s;
                 if (C > 1) p.S[c * p.mom_plane + out_row + x] = s;
                 s0 = s;
@@ -135,32 +137,36 @@ bool box_moments_enabled()
     return on;
 }
 
-// Can the resident (image, template set) take the box-sum route?  One window size, plain uint8, a window narrower than a strip.
+// Can the resident (image, template set) take the box-sum route?  Plain uint8, every window narrower than half a strip.
 bool box_moments_applicable(const mtm_ctx* ctx)
 {
-    if (ctx->img_dtype != MTM_U8 || ctx->masked || ctx->h_sizes.size() != 1) return false;
+    if (ctx->img_dtype != MTM_U8 || ctx->masked || ctx->h_sizes.empty()) return false;
     const int C = ctx->img.C;
     if (C != 1 && C != 3 && C != 4) return false;
-    const SizeDesc& sd = ctx->h_sizes[0];
-    if ((double)sd.h * sd.w * C * 65025.0 >= 4294967296.0) return false;     // window sums of squares must stay below 2^32
-    return sd.w <= BM_COLS / 2;
+    for (const SizeDesc& sd : ctx->h_sizes) {
+        if ((double)sd.h * sd.w * C * 65025.0 >= 4294967296.0) return false;     // window sums of squares must stay below 2^32
+        if (sd.w > BM_COLS / 2) return false;
+    }
+    return true;
 }
 
+// ctx->d_sizes holds ctx->h_sizes (ensure_moments).
 int launch_box_moments(mtm_ctx* ctx)
 {
     const ImageDev& im = ctx->img;
-    const SizeDesc& sd = ctx->h_sizes[0];
     BoxParams p{};
-    p.img = im.pix; p.pitch = im.pitch;
-    p.h = sd.h; p.w = sd.w; p.mh = sd.mh; p.mw = sd.mw;
-    p.S = ctx->d_wS; p.rsD = ctx->d_wR; p.off = sd.off; p.mom_plane = ctx->moments_total;
-    p.strip_out = (BM_COLS - (sd.w - 1)) & ~3;
-    const int strips = (sd.mw + p.strip_out - 1) / p.strip_out;
-    // about two CTAs per SM; a band re-reads the h-1 rows above it, so bands stay as tall as that allows
-    int bands = std::max(1, std::min(sd.mh, (2 * ctx->sm_count + strips - 1) / strips));
-    p.band = (sd.mh + bands - 1) / bands;
-    bands = (sd.mh + p.band - 1) / p.band;
-    const dim3 grid((unsigned)strips, (unsigned)bands);
+    p.img = im.pix; p.pitch = im.pitch; p.sizes = ctx->d_sizes;
+    p.S = ctx->d_wS; p.rsD = ctx->d_wR; p.mom_plane = ctx->moments_total;
+    int strips = 1, mh = 1;
+    for (const SizeDesc& sd : ctx->h_sizes) {
+        const int strip_out = (BM_COLS - (sd.w - 1)) & ~3;
+        strips = std::max(strips, (sd.mw + strip_out - 1) / strip_out);
+        mh = std::max(mh, sd.mh);
+    }
+    // about two CTAs per SM over all sizes; a band re-reads the h-1 rows above it, so bands stay as tall as that allows
+    const int n_sizes = (int)ctx->h_sizes.size();
+    const int bands = std::max(1, std::min(mh, (2 * ctx->sm_count + strips * n_sizes - 1) / (strips * n_sizes)));
+    const dim3 grid((unsigned)strips, (unsigned)bands, (unsigned)n_sizes);
     switch (im.C) {
         case 1: box_moments_kernel<1><<<grid, BM_THREADS, 0, ctx->stream>>>(p); break;
         case 3: box_moments_kernel<3><<<grid, BM_THREADS, 0, ctx->stream>>>(p); break;

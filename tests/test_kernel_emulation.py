@@ -231,22 +231,24 @@ extern "C" int emu_ncc_direct(const uint8_t* img, int64_t pitch, int H, int W, i
     emu_dyn_smem = nullptr;
     return TT;
 }
-// launch_box_moments (box_moments.cu) with the strip width it derives; the band height is the caller's (the library picks
-// it from the SM count).
-extern "C" int emu_box_moments(const uint8_t* img, int64_t pitch, int C, int h, int w, int mh, int mw, uint32_t* S, float* rsD,
-                               int64_t off, int64_t mom_plane, int band)
+// launch_box_moments (box_moments.cu): grid = (strips of the widest map, bands, sizes); the number of bands is the caller's (the
+// library picks it from the SM count).
+extern "C" int emu_box_moments(const uint8_t* img, int64_t pitch, int C, const SizeDesc* sizes, int n_sizes, uint32_t* S, float* rsD,
+                               int64_t mom_plane, int bands)
 {
     BoxParams p{};
-    p.img = img; p.pitch = pitch; p.h = h; p.w = w; p.mh = mh; p.mw = mw;
-    p.S = S; p.rsD = rsD; p.off = off; p.mom_plane = mom_plane;
-    p.strip_out = (BM_COLS - (w - 1)) & ~3;
-    p.band = band;
-    const dim3 grid((mw + p.strip_out - 1) / p.strip_out, (mh + band - 1) / band), block(BM_THREADS);
+    p.img = img; p.pitch = pitch; p.sizes = sizes; p.S = S; p.rsD = rsD; p.mom_plane = mom_plane;
+    int strips = 1;
+    for (int k = 0; k < n_sizes; ++k) {
+        const int strip_out = (BM_COLS - (sizes[k].w - 1)) & ~3;
+        strips = std::max(strips, (sizes[k].mw + strip_out - 1) / strip_out);
+    }
+    const dim3 grid(strips, bands, n_sizes), block(BM_THREADS);
     if (C == 1) emu_launch_coop(grid, block, [&] { box_moments_kernel<1>(p); });
     else if (C == 3) emu_launch_coop(grid, block, [&] { box_moments_kernel<3>(p); });
     else if (C == 4) emu_launch_coop(grid, block, [&] { box_moments_kernel<4>(p); });
     else return -1;
-    return (int)(grid.x * grid.y);
+    return strips;
 }
 // One tcgen05 launch of a template group, as launch_toeplitz_prep + launch_ncc_tc_impl (ncc_tc.cu) set it up; the tile height N,
 // the ring (ds, stages), the number of epilogue warps and the number of persistent CTAs are the caller's (the library derives
@@ -933,16 +935,16 @@ def test_device_code_on_the_host_gives_the_reference_score_map(emu_mtm):
 
 
 @pytest.mark.parametrize("channels", [1, 3, 4])
-@pytest.mark.parametrize("shape,window,band", [((41, 1100), (17, 40), 9), ((30, 333), (30, 5), 1), ((64, 70), (8, 64), 57), ((25, 2100), (3, 512), 4)])
-def test_box_sum_moment_kernel_equals_the_summed_area_one(emu, channels, shape, window, band):
-    """box_moments_kernel (experiment knob MTM_B200_MOM_BOX: one-size template sets, no summed-area tables) writes exactly what
-    window_moments_kernel writes from the tables: several strips and bands, a one-row map, a window as wide as half a strip,
-    flat windows (rsD = 0), garbage in the row padding."""
+@pytest.mark.parametrize("shape,windows,bands", [((41, 1100), [(17, 40)], 3), ((30, 333), [(30, 5)], 1), ((64, 70), [(8, 64)], 57),
+                                                 ((25, 2100), [(3, 512)], 6), ((48, 1150), [(5, 9), (17, 16), (32, 200), (48, 1)], 4)])
+def test_box_sum_moment_kernel_equals_the_summed_area_one(emu, channels, shape, windows, bands):
+    """box_moments_kernel (experiment knob MTM_B200_MOM_BOX: window moments from running box sums, no summed-area tables) writes
+    exactly what window_moments_kernel writes from the tables: several strips and bands, a one-row map, a window as wide as half a
+    strip, four sizes in one launch (grid sized for the largest map), flat windows (rsD = 0), garbage in the row padding."""
     rng = np.random.default_rng(13)
-    (H, W), (h, w) = shape, window
-    mh, mw = H - h + 1, W - w + 1
+    H, W = shape
     img = rng.integers(0, 256, (H, W, channels)).astype(np.uint8)
-    img[H // 3:, W // 4:W // 4 + 3 * w] = 201                                 # flat windows
+    img[H // 3:, W // 4:W // 4 + 3 * windows[0][1]] = 201                     # flat windows
     ipitch = (W * channels + 64 * channels + 64 + 127) // 128 * 128          # the library's row pitch
     buf = rng.integers(0, 256, H * ipitch + 256).astype(np.uint8)            # (the library pads with zeros; any bytes do)
     buf[:H * ipitch].reshape(H, ipitch)[:, :W * channels] = img.reshape(H, W * channels)
@@ -954,24 +956,26 @@ def test_box_sum_moment_kernel_equals_the_summed_area_one(emu, channels, shape, 
         sat_s[c, 1:, 1:W + 1] = np.cumsum(np.cumsum(wide[:, :, c], axis=0), axis=1).astype(np.uint32)
     sat_q = np.zeros((H + 1, pitch), np.uint32)
     sat_q[1:, 1:W + 1] = (np.cumsum(np.cumsum((wide ** 2).sum(axis=2), axis=0), axis=1) & 0xFFFFFFFF).astype(np.uint32)
-    sizes = np.zeros(1, SIZE_DTYPE)
-    off = 64                                                                  # the maps do not start at element 0
-    sizes[0] = (h, w, mh, mw, off)
-    total = off + (mh * mw + 31) // 32 * 32
+    sizes = np.zeros(len(windows), SIZE_DTYPE)
+    total = 64                                                                # the maps do not start at element 0
+    for k, (h, w) in enumerate(windows):
+        sizes[k] = (h, w, H - h + 1, W - w + 1, total)
+        total += ((H - h + 1) * (W - w + 1) + 31) // 32 * 32
     outs = []
     for box in (0, 1):
         S = np.full(total * max(2, channels), 0xDEADBEEF, np.uint32)
         R = np.full(total, -1.0, np.float32)
         if box:
-            assert emu.emu_box_moments(_ptr(buf), ctypes.c_int64(ipitch), channels, h, w, mh, mw, _ptr(S), _ptr(R), ctypes.c_int64(off),
-                                       ctypes.c_int64(total), band) >= 1
+            assert emu.emu_box_moments(_ptr(buf), ctypes.c_int64(ipitch), channels, _ptr(sizes), len(sizes), _ptr(S), _ptr(R),
+                                       ctypes.c_int64(total), bands) >= 1
         else:
-            emu.emu_moments(0, _ptr(sat_s), _ptr(sat_q), ctypes.c_int64(pitch), ctypes.c_int64(plane), _ptr(sizes), 1, channels, _ptr(S),
-                            _ptr(R), ctypes.c_int64(total), 3, 1)
+            emu.emu_moments(0, _ptr(sat_s), _ptr(sat_q), ctypes.c_int64(pitch), ctypes.c_int64(plane), _ptr(sizes), len(sizes), channels,
+                            _ptr(S), _ptr(R), ctypes.c_int64(total), 3, 1)
         outs.append((S, R))
     assert np.array_equal(outs[0][0], outs[1][0])
     assert np.array_equal(outs[0][1].view(np.uint32), outs[1][1].view(np.uint32))
-    first = outs[1][0][off] if channels > 1 else outs[1][0][2 * off]
+    h, w = windows[0]
+    first = outs[1][0][64] if channels > 1 else outs[1][0][2 * 64]
     assert int(first) == int(wide[:h, :w, 0].sum())
 
 
@@ -1007,9 +1011,7 @@ def _host_tensor_maps(emu, image, tmpls, method, mode, N, stages=3, ds=4, EW=8, 
     S = np.full(moff * max(2, C), 0xDEADBEEF, np.uint32)
     R = np.full(moff, np.nan, np.float32)
     if box:
-        assert len(sizes) == 1
-        emu.emu_box_moments(_ptr(buf), ctypes.c_int64(ipitch), C, sizes[0][0], sizes[0][1], sizes[0][2], sizes[0][3], _ptr(S), _ptr(R),
-                            ctypes.c_int64(0), ctypes.c_int64(moff), 7)
+        emu.emu_box_moments(_ptr(buf), ctypes.c_int64(ipitch), C, _ptr(sd), len(sizes), _ptr(S), _ptr(R), ctypes.c_int64(moff), 5)
     else:
         emu.emu_moments(0, _ptr(sat_s), _ptr(sat_q32), ctypes.c_int64(spitch), ctypes.c_int64((H + 1) * spitch), _ptr(sd), len(sizes), C,
                         _ptr(S), _ptr(R), ctypes.c_int64(moff), 2, 1)
