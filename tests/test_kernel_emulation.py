@@ -1134,6 +1134,34 @@ def _maps_of(flat, meta):
     return [flat[int(m["map_off"]):int(m["map_off"]) + int(m["mh"]) * int(m["mw"])].reshape(int(m["mh"]), int(m["mw"])) for m in meta]
 
 
+def _host_f32_maps(emu, image, tmpls, methods):
+    """ncc_float.cu on the host for equal-sized float32 templates: float64 tables, template statistics (+ mean-centred copies), then
+    ncc_direct_f32_kernel per method.  Returns ({method: maps}, template-tile width, tables, centred arena, meta)."""
+    H, W = image.shape[:2]
+    C = 1 if image.ndim == 2 else image.shape[2]
+    count = len(tmpls)
+    pitch_e = (W * C + 3) // 4 * 4
+    img = np.zeros(H * pitch_e + 64, np.float32)
+    img[:H * pitch_e].reshape(H, pitch_e)[:, :W * C] = image.reshape(H, W * C)
+    spitch = (W + 1 + 3) // 4 * 4
+    scratch = np.zeros(2 * (C + 1) * H * W + 16, np.float64)
+    sat_s = np.full((C, H + 1, spitch), np.nan)
+    sat_q = np.full((H + 1, spitch), np.nan)
+    emu.emu_satf(_ptr(img), ctypes.c_int64(pitch_e), H, W, C, _ptr(scratch), _ptr(sat_s), _ptr(sat_q), ctypes.c_int64(spitch))
+    arena, meta = _f32_arena(tmpls, C)
+    total = _geometry(meta, tmpls, H, W)
+    centred = np.full_like(arena, np.nan)
+    order = np.arange(count, dtype=np.int32)
+    out, tt = {}, 0
+    for n, method in enumerate(methods):
+        maps = np.full(total + 32, np.nan, np.float32)
+        tt = emu.emu_ncc_f32(_ptr(img), ctypes.c_int64(pitch_e), H, W, C, _ptr(sat_s), _ptr(sat_q), ctypes.c_int64(spitch), _ptr(arena),
+                             _ptr(centred), _ptr(meta), count, int(n == 0), _ptr(order), count, _ptr(maps), method)
+        assert tt > 0, tt
+        out[method] = _maps_of(maps, meta)
+    return out, tt, sat_s, centred, meta
+
+
 @pytest.mark.parametrize("channels,count", [(1, 1), (1, 5), (3, 2), (4, 1)])
 def test_float32_kernels_on_the_host(emu, channels, count):
     """satf_rows / satf_cols (float64 tables), tmplf_stats_kernel (OpenCV constants + mean-centred copy) and ncc_direct_f32_kernel for
@@ -1148,32 +1176,18 @@ def test_float32_kernels_on_the_host(emu, channels, count):
     tmpls = [t.astype(np.float32) * scale for t in tmpls8]
     if count >= 3:
         tmpls[1] = np.full_like(tmpls[1], 1234.0)                            # constant template
-    pitch_e = (W * channels + 3) // 4 * 4
-    img = np.zeros(H * pitch_e + 64, np.float32)
-    img[:H * pitch_e].reshape(H, pitch_e)[:, :W * channels] = image.reshape(H, W * channels)
-    spitch = (W + 1 + 3) // 4 * 4
-    scratch = np.zeros(2 * (channels + 1) * H * W + 16, np.float64)
-    sat_s = np.full((channels, H + 1, spitch), np.nan)
-    sat_q = np.full((H + 1, spitch), np.nan)
-    emu.emu_satf(_ptr(img), ctypes.c_int64(pitch_e), H, W, channels, _ptr(scratch), _ptr(sat_s), _ptr(sat_q), ctypes.c_int64(spitch))
+    got, tt, sat_s, centred, meta = _host_f32_maps(emu, image, tmpls, range(6))
+    assert tt == (4 if count >= 4 else 2 if count >= 2 else 1)
     wide = image.reshape(H, W, channels).astype(np.float64)
     for c in range(channels):                                                 # the tables themselves: float64 prefix sums (exact here: integers)
         want = np.zeros((H + 1, W + 1))
         want[1:, 1:] = wide[:, :, c].cumsum(0).cumsum(1)
         assert np.array_equal(sat_s[c, :, :W + 1], want)
-    arena, meta = _f32_arena(tmpls, channels)
-    total = _geometry(meta, tmpls, H, W)
-    centred = np.full_like(arena, np.nan)
-    order = np.arange(count, dtype=np.int32)
     for method in range(6):
-        maps = np.full(total + 32, np.nan, np.float32)
-        tt = emu.emu_ncc_f32(_ptr(img), ctypes.c_int64(pitch_e), H, W, channels, _ptr(sat_s), _ptr(sat_q), ctypes.c_int64(spitch), _ptr(arena),
-                             _ptr(centred), _ptr(meta), count, int(method == 0), _ptr(order), count, _ptr(maps), method)
-        assert tt == (4 if count >= 4 else 2 if count >= 2 else 1)
-        for k, got in enumerate(_maps_of(maps, meta)):
-            want = ncc_exact.match_template_exact(image, tmpls[k], method)
-            scale = max(1.0, float(np.abs(want).max()))                       # the bar of tests/test_gpu_float.py
-            assert np.max(np.abs(got.astype(np.float64) - want)) <= 1e-4 * scale, (method, k, float(np.max(np.abs(got - want))), scale)
+        for k, t in enumerate(tmpls):
+            want = ncc_exact.match_template_exact(image, t, method)
+            scale_m = max(1.0, float(np.abs(want).max()))                     # the bar of tests/test_gpu_float.py
+            assert np.max(np.abs(got[method][k].astype(np.float64) - want)) <= 1e-4 * scale_m, (method, k)
     for k, t in enumerate(tmpls):                                             # the mean-centred copies
         o = int(meta[k]["pix_off"]) // 4
         mean = t.reshape(-1, channels).astype(np.float64).mean(0)
