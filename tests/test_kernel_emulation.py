@@ -1300,3 +1300,62 @@ def test_sixteen_bit_route_on_the_functional_model(emu, mode, shapes):
                 exact = ncc_exact.cc_direct(image.astype(np.float32), tmpls[k].astype(np.float32))     # float64 sums of integers: exact
                 assert np.array_equal(got, exact.astype(np.float32))
     assert np.array_equal(hi[:H * pitch].reshape(H, pitch)[:, :W], image >> 8) and np.array_equal(lo[:H * pitch].reshape(H, pitch)[:, :W], image & 255)
+
+
+# ---- seeded random sweeps (a few cases each; the same generators ran hundreds of cases while the emulation was written) ---------
+
+@pytest.mark.parametrize("seed", [111, 137, 166, 203])
+def test_tensor_core_kernel_random_geometries(emu, seed):
+    """Random image / template-group geometry, tile height, ring shape, epilogue-warp count, kernel flavour and CTA count on the
+    tcgen05 model: the raw numerator and TM_CCORR_NORMED bit-identical to the oracle, TM_CCOEFF_NORMED within 2e-6."""
+    from oracle import ncc_exact
+    rng = np.random.default_rng(seed)
+    C = int(rng.choice([1, 1, 3, 4]))
+    mode = int(rng.integers(0, 2)) if C == 1 else 0
+    H, W = int(rng.integers(12, 90)), int(rng.integers(20, 200 if mode == 0 else 400))
+    hmax, wmax = int(rng.integers(4, min(H, 40) + 1)), int(rng.integers(4, min(W, 60) + 1))
+    shapes = [(hmax, wmax)]
+    for _ in range(0 if mode == 1 else int(rng.integers(0, 8))):
+        shapes.append((hmax, wmax) if rng.random() < 0.5 else
+                      (int(rng.integers(max(1, hmax // 2), hmax + 1)), int(rng.integers(max(1, wmax // 2), wmax + 1))))
+    shapes = [(h, w) for h, w in shapes if h * w >= 16]
+    N = int(rng.choice([16, 32, 48, 64, 96]))
+    opts = dict(stages=int(rng.integers(2, 6)), ds=int(rng.integers(1, 3)), EW=int(rng.choice([8, 12])), persist=bool(rng.random() < 0.8),
+                ctas=int(rng.integers(1, 5)))
+    image, tmpls = _planted(rng, H, W, C, shapes)
+    for method in (2, 3, 5):
+        got, _, _ = _host_tensor_maps(emu, image, tmpls, method, mode, N, **opts)
+        for k, t in enumerate(tmpls):
+            want = ncc_exact.match_template_exact(image, t, method)
+            if method == 5:
+                assert np.max(np.abs(got[k] - want)) <= 2e-6, (k, shapes, N, opts)
+            else:
+                assert np.array_equal(got[k].view(np.uint32), want.view(np.uint32)), (method, k, shapes, N, opts)
+
+
+@pytest.mark.parametrize("seed", [1001, 1002, 1003, 1004, 1005, 1006, 1008, 1009])
+def test_peak_sort_nms_kernels_random_maps(emu, seed):
+    """Random score maps (few levels: ties and plateaus; constant maps; 1 x n, n x 1 and 1 x 1 shapes), method, N_object, thresholds and
+    route: the device lists equal the port's, order included."""
+    rng = np.random.default_rng(seed)
+    levels = int(rng.choice([2, 4, 16, 1000]))
+    maps, sizes = [], []
+    for _ in range(int(rng.integers(1, 7))):
+        kind = rng.integers(0, 6)
+        shp = (1, int(rng.integers(1, 50))) if kind == 0 else (int(rng.integers(1, 50)), 1) if kind == 1 else \
+            (int(rng.integers(2, 40)), int(rng.integers(2, 60)))
+        m = (np.round(rng.random(shp) * levels) / levels).astype(np.float32)
+        if rng.random() < 0.15:
+            m[:] = m.flat[0]
+        maps.append(m)
+        sizes.append((int(rng.integers(1, 40)), int(rng.integers(1, 40))))
+    method = int(rng.choice([1, 3, 5]))
+    n_object = [float("inf"), 1, int(rng.integers(2, 30))][int(rng.integers(0, 3))]
+    thr, overlap = float(rng.choice([0.0, 0.25, 0.5, 0.75, 0.9])), float(rng.choice([0.0, 0.1, 0.25, 0.5, 1.0]))
+    for do_nms in (False, True):
+        want = _port_postprocess(maps, sizes, method, n_object, thr, overlap, do_nms)
+        for force_general in (False, True):
+            if force_general and not do_nms and n_object == 1:
+                continue
+            got, _ = _host_postprocess(emu, maps, sizes, method, n_object, thr, overlap, do_nms, force_general)
+            assert got == want, (do_nms, force_general, method, n_object, thr, overlap)
