@@ -4,20 +4,21 @@
 //
 // Two launchers:
 //   emu_launch       every thread of every block one after the other (kernels whose threads do not communicate);
-//   emu_launch_coop  one OS thread per CUDA thread of a block, blocks one after the other: __syncthreads(), warp
-//                    shuffles / votes (full-warp, all lanes converged), shared memory (`__shared__` becomes `static`)
-//                    and atomics behave as on the device.
+//   emu_launch_coop  one FIBER (user-level context, ucontext) per CUDA thread of a block, blocks one after the other, all on
+//                    the calling OS thread: __syncthreads(), warp shuffles / votes (full-warp, all lanes converged), shared
+//                    memory (`__shared__` becomes `static`) and atomics behave as on the device.  A fiber that waits (block /
+//                    warp barrier, mbarrier) is parked until its condition holds; when no fiber can run, the kernel has
+//                    deadlocked and the process aborts with a message.  Scheduling is round-robin and deterministic.
 // The emulation checks kernel LOGIC (index arithmetic, reductions, rounding) bit for bit; it says nothing about speed.
 #pragma once
 #include <algorithm>
-#include <atomic>
-#include <barrier>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
-#include <thread>
+#include <ucontext.h>
 #include <vector>
 
 struct dim3 {
@@ -25,8 +26,7 @@ struct dim3 {
     dim3() = default;
     dim3(unsigned a, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
 };
-static thread_local dim3 threadIdx;
-static dim3 blockIdx, blockDim, gridDim;
+static dim3 threadIdx, blockIdx, blockDim, gridDim;      // threadIdx follows the running fiber
 
 #define __global__
 #define __device__
@@ -96,35 +96,68 @@ static inline int atomicMax(int* p, int v)
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 
-// ---- cooperative block emulation ------------------------------------------------------------------------------------
-struct EmuWarp {
-    std::unique_ptr<std::barrier<>> bar;
-    uint64_t slot[32];
-    int lanes = 0;
+// ---- cooperative block emulation: fibers ------------------------------------------------------------------------------
+struct EmuFiber {
+    ucontext_t ctx;
+    dim3 tid;
+    int lane = 0, warp = 0;
+    bool done = false;
+    const volatile uint32_t* wait_ptr = nullptr;      // parked until *wait_ptr != wait_val
+    uint32_t wait_val = 0;
 };
+struct EmuGate { volatile uint32_t gen = 0; int arrived = 0, expected = 0; };   // a re-usable barrier
+struct EmuWarp { EmuGate gate; uint64_t slot[32]; int lanes = 0; };
 struct EmuBlock {
-    std::unique_ptr<std::barrier<>> bar;
+    EmuGate gate;
     std::vector<EmuWarp> warps;
-    std::atomic<int> vote{0};
+    int vote[2] = {0, 0};
+    uint32_t vote_round = 0;
 };
+static constexpr size_t EMU_STACK = 256 * 1024;
+static std::vector<std::unique_ptr<char[]>> emu_stacks;      // kept across launches
+static std::vector<EmuFiber> emu_fibers;
+static ucontext_t emu_sched_ctx;
+static int emu_cur = -1;
 static EmuBlock* emu_block = nullptr;
 static uint8_t* emu_dyn_smem = nullptr;          // dynamic shared memory of the running block (`extern __shared__` is rewritten to it)
-static thread_local int emu_lane = 0, emu_warp = 0;
-static thread_local bool emu_coop = false;
+static int emu_lane = 0, emu_warp = 0;
+static bool emu_coop = false;
+static void (*emu_body_call)(void*) = nullptr;
+static void* emu_body_ptr = nullptr;
 
-static inline void __syncthreads() { if (emu_coop) emu_block->bar->arrive_and_wait(); }
+// parks the running fiber until *ptr != val
+static inline void emu_wait_change(const volatile uint32_t* ptr, uint32_t val)
+{
+    if (*ptr != val) return;
+    EmuFiber& f = emu_fibers[emu_cur];
+    f.wait_ptr = ptr; f.wait_val = val;
+    swapcontext(&f.ctx, &emu_sched_ctx);
+}
+static inline void emu_gate_release(EmuGate& g) { g.arrived = 0; g.gen = g.gen + 1; }
+static inline void emu_gate_arrive_and_wait(EmuGate& g)
+{
+    const uint32_t gen = g.gen;
+    if (++g.arrived == g.expected) emu_gate_release(g);
+    else emu_wait_change(&g.gen, gen);
+}
+// an exiting thread no longer takes part in the barrier (like an exited CUDA thread)
+static inline void emu_gate_drop(EmuGate& g)
+{
+    if (--g.expected > 0 && g.arrived == g.expected) emu_gate_release(g);
+}
+
+static inline void __syncthreads() { if (emu_coop) emu_gate_arrive_and_wait(emu_block->gate); }
 static inline int __syncthreads_or(int pred)
 {
     if (!emu_coop) return pred != 0;
-    if (pred) emu_block->vote.store(1);
-    emu_block->bar->arrive_and_wait();
-    const int r = emu_block->vote.load();
-    emu_block->bar->arrive_and_wait();
-    if (threadIdx.x == 0 && threadIdx.y == 0) emu_block->vote.store(0);
-    emu_block->bar->arrive_and_wait();
-    return r;
+    EmuBlock& b = *emu_block;
+    const uint32_t round = b.vote_round;                    // changes only when the barrier of this vote releases
+    if (pred) b.vote[round & 1] = 1;
+    if (b.gate.arrived + 1 == b.gate.expected) { b.vote[(round + 1) & 1] = 0; b.vote_round = round + 1; }   // last arrival: next vote's slot
+    emu_gate_arrive_and_wait(b.gate);
+    return b.vote[round & 1];
 }
-static inline void __syncwarp(unsigned = 0xffffffffu) { if (emu_coop) emu_block->warps[emu_warp].bar->arrive_and_wait(); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { if (emu_coop) emu_gate_arrive_and_wait(emu_block->warps[emu_warp].gate); }
 
 template <typename T> static inline T emu_exchange(T v, int src_lane)
 {
@@ -133,10 +166,10 @@ template <typename T> static inline T emu_exchange(T v, int src_lane)
     uint64_t bits = 0;
     memcpy(&bits, &v, sizeof(T));
     w.slot[emu_lane] = bits;
-    w.bar->arrive_and_wait();
+    emu_gate_arrive_and_wait(w.gate);
     T out = v;
     if (src_lane >= 0 && src_lane < w.lanes) memcpy(&out, &w.slot[src_lane], sizeof(T));
-    w.bar->arrive_and_wait();
+    emu_gate_arrive_and_wait(w.gate);
     return out;
 }
 template <typename T> static inline T __shfl_down_sync(unsigned, T v, int d) { return emu_exchange(v, emu_lane + d < 32 ? emu_lane + d : -1); }
@@ -146,10 +179,10 @@ static inline unsigned __ballot_sync(unsigned, int pred)
 {
     EmuWarp& w = emu_block->warps[emu_warp];
     w.slot[emu_lane] = pred ? 1u : 0u;
-    w.bar->arrive_and_wait();
+    emu_gate_arrive_and_wait(w.gate);
     unsigned m = 0;
     for (int l = 0; l < w.lanes; ++l) m |= (unsigned)(w.slot[l] != 0) << l;
-    w.bar->arrive_and_wait();
+    emu_gate_arrive_and_wait(w.gate);
     return m;
 }
 static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
@@ -172,43 +205,70 @@ template <typename F> static void emu_launch(dim3 grid, dim3 block, F body)
                         }
 }
 
-// one OS thread per CUDA thread (created once per launch, walking the blocks together); a thread that returns early leaves the
-// block barrier like an exited CUDA thread
+static void emu_fiber_main()
+{
+    emu_body_call(emu_body_ptr);
+    EmuFiber& f = emu_fibers[emu_cur];
+    f.done = true;
+    emu_gate_drop(emu_block->gate);
+    emu_gate_drop(emu_block->warps[f.warp].gate);
+    swapcontext(&f.ctx, &emu_sched_ctx);                   // never resumed
+}
+
+// one fiber per CUDA thread, the blocks of the grid one after the other
 template <typename F> static void emu_launch_coop(dim3 grid, dim3 block, F body)
 {
     gridDim = grid; blockDim = block;
     const int nthreads = (int)(block.x * block.y * block.z);
-    const long long nblocks = (long long)grid.x * grid.y * grid.z;
-    std::barrier<> between(nthreads);                      // separates the blocks of the launch
-    std::unique_ptr<EmuBlock> blk;
-    auto next_block = [&](long long b) {
-        blockIdx = dim3((unsigned)(b % grid.x), (unsigned)((b / grid.x) % grid.y), (unsigned)(b / ((long long)grid.x * grid.y)));
-        blk = std::make_unique<EmuBlock>();
-        blk->bar = std::make_unique<std::barrier<>>(nthreads);
-        blk->warps.resize((nthreads + 31) / 32);
-        for (size_t w = 0; w < blk->warps.size(); ++w) {
-            blk->warps[w].lanes = std::min(32, nthreads - 32 * (int)w);
-            blk->warps[w].bar = std::make_unique<std::barrier<>>(blk->warps[w].lanes);
-        }
-        emu_block = blk.get();
-    };
-    next_block(0);
-    std::vector<std::thread> pool;
-    pool.reserve(nthreads);
-    for (int t = 0; t < nthreads; ++t)
-        pool.emplace_back([&, t] {
-            threadIdx = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
-            emu_lane = t & 31; emu_warp = t >> 5; emu_coop = true;
-            for (long long b = 0; b < nblocks; ++b) {
-                body();
-                emu_block->bar->arrive_and_drop();
-                between.arrive_and_wait();                 // every thread has left block b
-                if (b + 1 < nblocks) {
-                    if (t == 0) next_block(b + 1);
-                    between.arrive_and_wait();
+    while ((int)emu_stacks.size() < nthreads) emu_stacks.emplace_back(new char[EMU_STACK]);
+    emu_body_call = [](void* p) { (*static_cast<F*>(p))(); };
+    emu_body_ptr = &body;
+    emu_coop = true;
+    for (unsigned bz = 0; bz < grid.z; ++bz)
+        for (unsigned by = 0; by < grid.y; ++by)
+            for (unsigned bx = 0; bx < grid.x; ++bx) {
+                blockIdx = dim3(bx, by, bz);
+                EmuBlock blk;
+                blk.gate.expected = nthreads;
+                blk.warps.resize((nthreads + 31) / 32);
+                for (size_t w = 0; w < blk.warps.size(); ++w)
+                    blk.warps[w].lanes = blk.warps[w].gate.expected = std::min(32, nthreads - 32 * (int)w);
+                emu_block = &blk;
+                emu_fibers.assign(nthreads, EmuFiber());
+                for (int t = 0; t < nthreads; ++t) {
+                    EmuFiber& f = emu_fibers[t];
+                    f.tid = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
+                    f.lane = t & 31; f.warp = t >> 5;
+                    getcontext(&f.ctx);
+                    f.ctx.uc_stack.ss_sp = emu_stacks[t].get();
+                    f.ctx.uc_stack.ss_size = EMU_STACK;
+                    f.ctx.uc_link = nullptr;
+                    makecontext(&f.ctx, emu_fiber_main, 0);
                 }
+                int live = nthreads;
+                while (live > 0) {
+                    bool ran = false;
+                    for (int t = 0; t < nthreads; ++t) {
+                        EmuFiber& f = emu_fibers[t];
+                        if (f.done) continue;
+                        if (f.wait_ptr) {
+                            if (*f.wait_ptr == f.wait_val) continue;          // still parked
+                            f.wait_ptr = nullptr;
+                        }
+                        emu_cur = t; threadIdx = f.tid; emu_lane = f.lane; emu_warp = f.warp;
+                        swapcontext(&emu_sched_ctx, &f.ctx);
+                        ran = true;
+                        if (f.done) --live;
+                    }
+                    if (!ran) {
+                        fprintf(stderr, "emulated kernel deadlocked in block (%u, %u, %u): %d threads wait for something that cannot happen "
+                                "(first of them: thread %d)\n", bx, by, bz, live,
+                                (int)(std::find_if(emu_fibers.begin(), emu_fibers.end(), [](const EmuFiber& f) { return !f.done; }) - emu_fibers.begin()));
+                        abort();
+                    }
+                }
+                emu_block = nullptr;
             }
-        });
-    for (auto& th : pool) th.join();
-    emu_block = nullptr;
+    emu_coop = false;
+    emu_cur = -1;
 }

