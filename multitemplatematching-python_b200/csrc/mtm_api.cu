@@ -471,7 +471,7 @@ static int ensure_moments(mtm_ctx* ctx, bool box)
     MTM_TRY(mtm_reserve(ctx, ctx->d_sizes, ctx->sizes_cap, ctx->h_sizes.size()));
     MTM_CUDA(ctx, cudaMemcpyAsync(ctx->d_sizes, ctx->h_sizes.data(), ctx->h_sizes.size() * sizeof(SizeDesc),
                                   cudaMemcpyHostToDevice, ctx->stream));
-    if (box) MTM_TRY(launch_box_moments(ctx));             // one window size: straight from the image, same bits
+    if (box) MTM_TRY(launch_box_moments(ctx));             // straight from the image, same bits
     else MTM_TRY(launch_window_moments(ctx));
     ctx->moments_valid = true;
     return MTM_OK;
@@ -544,8 +544,8 @@ static int compute_maps(mtm_ctx* ctx, int method, int tmpl)
         return mtm_fail(ctx, MTM_ERR_UNSUPPORTED, "tensor-core path requested but not available for these inputs/method");
     const bool tensor16 = tensor && ctx->img_dtype == MTM_F32;     // 16-bit byte-plane path
     if (ctx->img_dtype == MTM_U8) {
-        // Everything but the default method's tensor-core epilogue reads the summed-area tables; under MTM_B200_MOM_BOX a
-        // one-size template set gets its window moments from the image instead and the tables are never built.
+        // Everything but the default method's tensor-core epilogue reads the summed-area tables; under MTM_B200_MOM_BOX the
+        // window moments come from the image instead (box_moments.cu) and the tables are not built for such a call.
         bool box = box_moments_enabled() && tensor && method == MTM_TM_CCOEFF_NORMED && box_moments_applicable(ctx);
         for (const TcGroup& g : ctx->tc_groups) box = box && !points_path_preferred(ctx, g.first, g.count);
         if (!box) MTM_TRY(ensure_sat(ctx));

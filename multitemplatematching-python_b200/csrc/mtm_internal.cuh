@@ -235,7 +235,7 @@ bool tc_path_supported(const mtm_ctx* ctx, int method, int h, int w);
 bool tc_plan_group(int mode, int h, int w, int C, TcGroup& g);
 int launch_toeplitz_prep(mtm_ctx* ctx, const TcGroup& g);
 int launch_window_moments(mtm_ctx* ctx);
-// one-size template sets, experiment knob MTM_B200_MOM_BOX (box_moments.cu): the same maps without summed-area tables
+// experiment knob MTM_B200_MOM_BOX (box_moments.cu): the same moment maps from running box sums, without summed-area tables
 bool box_moments_enabled();
 bool box_moments_applicable(const mtm_ctx* ctx);
 int launch_box_moments(mtm_ctx* ctx);
