@@ -272,3 +272,56 @@ template <typename F> static void emu_launch_coop(dim3 grid, dim3 block, F body)
     emu_coop = false;
     emu_cur = -1;
 }
+
+// ---- a stand-in for the CUDA runtime API (whole-library host build, tests/emu_library.py) -----------------------------------
+// Everything is synchronous and "device memory" is host memory; one emulated device that reports compute capability 10.0.
+// EMU_SM_COUNT keeps persistent / capped grids small so that the emulation stays fast.
+#ifndef EMU_SM_COUNT
+#define EMU_SM_COUNT 4
+#endif
+enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
+enum { cudaErrorNotReady = 600, cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaHostAllocMapped = 2,
+       cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+struct cudaDeviceProp { int major = 10, minor = 0, multiProcessorCount = EMU_SM_COUNT; char name[64] = "emulated sm_100a"; };
+static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { *p = cudaDeviceProp(); return cudaSuccess; }
+static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+static inline cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = reinterpret_cast<cudaStream_t>(new int(0)); return cudaSuccess; }
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { return cudaStreamCreate(s); }
+static inline cudaError_t cudaStreamDestroy(cudaStream_t s) { delete reinterpret_cast<int*>(s); return cudaSuccess; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = reinterpret_cast<cudaEvent_t>(new int(0)); return cudaSuccess; }
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { return cudaEventCreate(e); }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete reinterpret_cast<int*>(e); return cudaSuccess; }
+static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) { return cudaSuccess; }
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventQuery(cudaEvent_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
+template <typename T> static inline cudaError_t cudaMalloc(T** p, size_t n) { *p = static_cast<T*>(aligned_alloc(256, (n + 255) / 256 * 256 + 256)); return cudaSuccess; }
+static inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+template <typename T> static inline cudaError_t cudaMallocHost(T** p, size_t n) { return cudaMalloc(p, n); }
+template <typename T> static inline cudaError_t cudaHostAlloc(T** p, size_t n, unsigned) { return cudaMalloc(p, n); }
+static inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
+template <typename T> static inline cudaError_t cudaHostGetDevicePointer(T** d, void* h, unsigned) { *d = static_cast<T*>(h); return cudaSuccess; }
+static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { memcpy(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, cudaMemcpyKind, cudaStream_t = nullptr)
+{
+    for (size_t y = 0; y < h; ++y) memcpy(static_cast<char*>(d) + y * dp, static_cast<const char*>(s) + y * sp, w);
+    return cudaSuccess;
+}
+static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = nullptr) { memset(d, v, n); return cudaSuccess; }
+template <typename K> static inline cudaError_t cudaFuncSetAttribute(K, int, int) { return cudaSuccess; }
+
+// kernel<<<grid, block, smem, stream>>>(args) of the library's host code is rewritten to this (tests/emu_library.py)
+static long long emu_launch_count = 0;
+template <typename F> static void emu_launch_dyn(dim3 grid, dim3 block, size_t smem, F body)
+{
+    std::unique_ptr<uint8_t[]> store(new uint8_t[smem + 2048]);
+    uint8_t* base = store.get() + ((1024 - (reinterpret_cast<uintptr_t>(store.get()) & 1023)) & 1023);
+    memset(base, 0xCD, smem);
+    emu_dyn_smem = base;
+    ++emu_launch_count;
+    emu_launch_coop(grid, block, body);
+    emu_dyn_smem = nullptr;
+}

@@ -21,6 +21,7 @@ import sys
 sys.path.insert(0, %(root)r)
 import numpy as np
 import MTM
+%(preamble)s
 from oracle import mtm_port, ncc_exact, synth
 rng = np.random.default_rng(5)
 # grayscale, two sizes (window moments of several sizes), a map large enough for the candidate list
@@ -60,5 +61,9 @@ KNOBS = [{"MTM_B200_MOM_BOX": "1"}, {"MTM_B200_MOM_ROWS": "1"}, {"MTM_B200_MOM_C
 def test_knob_keeps_parity(knob):
     env = dict(os.environ)
     env.update(knob)
-    r = subprocess.run([sys.executable, "-c", SCRIPT % {"root": ROOT}], env=env, capture_output=True, text=True, timeout=300)
+    # MTM_B200_EMULATE=1 (tests/conftest.py): the subprocess loads the host build of the library instead (CPU, slow)
+    emulated = os.environ.get("MTM_B200_EMULATED_LIB")
+    preamble = "from mtm_b200 import _native; _native.LIB_PATH = %r" % emulated if emulated else ""
+    r = subprocess.run([sys.executable, "-c", SCRIPT % {"root": ROOT, "preamble": preamble}], env=env, capture_output=True, text=True,
+                       timeout=3600 if emulated else 300)
     assert r.returncode == 0 and "knob parity ok" in r.stdout, (knob, r.stdout[-2000:], r.stderr[-4000:])

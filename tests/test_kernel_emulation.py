@@ -3,8 +3,8 @@ from `extern __shared__` declarations (a pointer handed over by the launcher) an
 tests/emu/cuda_runtime.h (one fiber per CUDA thread of a block: barriers, shuffles, votes, shared memory, atomics) and, for the
 tcgen05 kernels of ncc_tc.cu, tests/emu/tcgen05_model.h (a functional model of mbarriers, bulk copies, tensor memory and tcgen05.mma
 kind::i8 that takes the place of the file's PTX wrappers).  Without a GPU this checks, mostly bit for bit:
-  * transform.cu, window_stats.cu, ncc_direct.cu, ncc_points.cu, peaks.cu, nms.cu against numpy / oracle/ and, behind
-    MTM.matchTemplates, against the golden vectors of the unmodified reference;
+  * transform.cu, window_stats.cu, ncc_direct.cu, ncc_points.cu, peaks.cu, nms.cu against numpy / oracle/ (the golden vectors of
+    the unmodified reference are checked through the whole-library host build, tests/test_library_emulation.py);
   * ncc_tc.cu (persistent and one-tile kernels, modes A / B, both epilogues, the 16-bit accumulate flavour), ncc_float.cu (float32 and
     masked matching) against the oracle;
   * the experiment-knob kernels (row-walking and box-sum window moments) against the default moment kernel.
@@ -832,106 +832,6 @@ def test_direct_kernel_on_the_host(emu, channels, count):
     wide, _ = _host_direct_maps(emu, image, tmpls, [5], force_wide=True)
     for a, b in zip(wide[5], got[5]):
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
-
-
-# ---- the uint8 dp4a route of the library, kernel by kernel on the host, behind the product's Python API ---------------------
-
-def _emu_context_class(emu):
-    from mock_device import MockContext, HIT_DTYPE
-
-    class EmuContext(MockContext):
-        """tests/mock_device.py's context with the HOT PATH replaced by the library's own device code run on the CPU
-        (uint8 inputs, `MTM_OPT_PATH = direct` route): K1 summed-area tables + template statistics, K2 dp4a kernel per template
-        size, K5/K6 peak passes, K7 sort + NMS.  Inputs, label mapping and search boxes come through api.py unchanged."""
-
-        def _maps(self, method, only=None):
-            image = self.image
-            assert image.dtype == np.uint8 and all(t.dtype == np.uint8 for t in self.templates)
-            H, W = image.shape[:2]
-            C = 1 if image.ndim == 2 else image.shape[2]
-            buf, ipitch, sat_s, sat_q, _, pitch = _host_sat(emu, image)
-            arena, meta = _pack_templates([t.reshape(t.shape[0], t.shape[1], C) for t in self.templates], C)
-            off = 0
-            for k, t in enumerate(self.templates):
-                mh, mw = H - t.shape[0] + 1, W - t.shape[1] + 1
-                meta[k]["mh"], meta[k]["mw"], meta[k]["map_off"] = mh, mw, off
-                off += (mh * mw + 31) // 32 * 32
-            emu.emu_tmpl_stats(_ptr(arena), _ptr(meta), len(self.templates), C)
-            maps = np.full(off + 32, np.nan, np.float32)
-            groups = {}
-            for k, t in enumerate(self.templates):
-                if only is None or k == only:
-                    groups.setdefault(t.shape[:2], []).append(k)
-            for members in groups.values():                                   # compute_maps: one launch per template size
-                order = np.asarray(members, np.int32)
-                assert emu.emu_ncc_direct(_ptr(buf), ctypes.c_int64(ipitch), H, W, C, _ptr(sat_s), _ptr(sat_q), ctypes.c_int64(pitch),
-                                          _ptr(arena), _ptr(meta), _ptr(order), len(members), _ptr(maps), method, 0) > 0
-            return [maps[int(m["map_off"]):int(m["map_off"]) + int(m["mh"]) * int(m["mw"])].reshape(int(m["mh"]), int(m["mw"]))
-                    for m in meta]
-
-        def score_map(self, tmpl, method, map_shape):
-            self.calls.append("score_map")
-            out = self._maps(method, only=tmpl)[tmpl]
-            assert out.shape == tuple(map_shape)
-            return out.copy()
-
-        def _post(self, method, n_object, thr, max_overlap, do_nms):
-            maps = self._maps(method)
-            sizes = [t.shape[:2] for t in self.templates]
-            hits, _ = _host_postprocess(emu, maps, sizes, method, float("inf") if n_object < 0 else int(n_object), thr, max_overlap,
-                                        do_nms, cap=16384)
-            raw = np.zeros(len(hits), HIT_DTYPE)
-            for k, (t, (x, y, w, h), s) in enumerate(hits):
-                raw[k] = (t, x, y, w, h, np.float32(s))
-            return raw
-
-        def find_matches(self, method, n_object, score_threshold):
-            self.calls.append("find_matches")
-            return self._post(method, 1 if n_object == 1 else -1, score_threshold, 0.0, False)
-
-        def match_templates(self, method, n_object, score_threshold, max_overlap):
-            self.calls.append("match_templates")
-            return self._post(method, n_object, score_threshold, max_overlap, True)
-
-    return EmuContext
-
-
-@pytest.fixture()
-def emu_mtm(emu, mtm, monkeypatch):
-    from mtm_b200 import _native
-    cls = _emu_context_class(emu)
-    shared = cls()
-    monkeypatch.setattr(_native, "Context", cls)
-    monkeypatch.setattr(_native, "default_context", lambda device=None: shared)
-    monkeypatch.setattr(_native, "helper_contexts", lambda device, n: [cls() for _ in range(n)])
-    return mtm
-
-
-@pytest.mark.parametrize("name", ["t3_downscaled", "c1_fish256_n1", "c1_fish256_inf", "fish512_multi", "synth_rot8", "synth_mixed_n5",
-                                  "synth_searchbox", "synth_exact_fit"])
-def test_device_code_on_the_host_gives_the_reference_hit_lists(emu_mtm, golden, name):
-    """MTM.matchTemplates -> api.py -> the library's kernels run on the CPU == outputs of the UNMODIFIED reference
-    (tests/golden/ref_outputs.json), eight of the golden matchTemplates cases (the 2048 x 2048 ones are too large for the emulation): Fish 256 x 256 (BASELINE
-    configs[0]) and 512 x 512 with three templates, rotated template sets, five template sizes with N_object = 5, a search box, a
-    template as large as the search box (1 x 1 map)."""
-    import test_gpu_parity as gp
-    gp.test_match_templates_golden(emu_mtm, golden, name)
-
-
-@pytest.mark.parametrize("name", ["c1_fish256_find", "synth_row_map", "synth_col_map"])
-def test_device_code_on_the_host_gives_the_reference_raw_lists(emu_mtm, golden, name):
-    import test_gpu_parity as gp
-    gp.test_find_matches_golden(emu_mtm, golden, name)
-
-
-def test_device_code_on_the_host_gives_the_reference_score_map(emu_mtm):
-    """computeScoreMap against the reference's own map of the Fish example (tests/golden/c1_fish256_map.npy)."""
-    from oracle import golden_cases as gc
-    kind, temps, img, kw = gc.build("c1_fish256_map")
-    got = emu_mtm.computeScoreMap(temps[0][1], img, **kw)
-    want = np.load(os.path.join(gc.GOLDEN_DIR, "c1_fish256_map.npy"))
-    assert got.shape == want.shape and got.dtype == np.float32
-    assert np.max(np.abs(got - want)) <= 1e-4
 
 
 @pytest.mark.parametrize("channels", [1, 3, 4])
