@@ -91,3 +91,36 @@ def test_direct_and_tensor_routes_agree(lib_mtm):
     finally:
         ct.close()
         cd.close()
+
+
+def test_device_resident_images_through_the_real_host_code(lib_mtm):
+    """The body of tests/test_gpu_zz_device_inputs.py with host pointers dressed as CUDA arrays (the emulated device's memory IS host
+    memory): mtm_set_image_device for uint8 / float32 / uint16 / RGB, searchBox crops as pointer arithmetic, no upload of the image,
+    same results as the numpy route; the batch entry point with mixed device / host images and a strided view."""
+    from mtm_b200 import _native
+    from oracle import synth
+    from test_host_api_mock import _FakeDeviceArray
+    rng = np.random.default_rng(43)
+    temps = [("a", synth.make_template(rng, 16, 24)), ("b", synth.make_template(rng, 20, 20))]
+    img, _ = synth.make_scene(110, 150, [t[1] for t in temps], 3, seed=43)
+    cases = [(img, temps),
+             (img.astype(np.float32), [(n, t.astype(np.float32)) for n, t in temps]),
+             (img.astype(np.uint16) * 100, [(n, t.astype(np.uint16) * 100) for n, t in temps]),
+             (np.stack([img, 255 - img, img[::-1]], axis=2), [(n, np.ascontiguousarray(np.stack([t, 255 - t, t[::-1]], axis=2))) for n, t in temps])]
+    ctx = _native.default_context()
+    for image, ts in cases:
+        image = np.ascontiguousarray(image)
+        dev = _FakeDeviceArray(image)
+        all_kw = (dict(score_threshold=0.5, maxOverlap=0.25), dict(N_object=1), dict(score_threshold=0.5, searchBox=(13, 7, 120, 90)))
+        for kw in (all_kw if image is cases[0][0] or image.dtype == np.uint8 and image.ndim == 2 else all_kw[2:]):
+            before = ctx.counters()["h2d_bytes"]
+            got = lib_mtm.matchTemplates(ts, dev, **kw)
+            moved = ctx.counters()["h2d_bytes"] - before
+            assert moved < image.nbytes // 4, "the image must not be uploaded again (%d bytes moved)" % moved
+            want = lib_mtm.matchTemplates(ts, image, **kw)
+            assert [(h[0], h[1], float(h[2])) for h in got] == [(h[0], h[1], float(h[2])) for h in want] and len(want) >= 1
+        assert np.array_equal(lib_mtm.computeScoreMap(ts[0][1], dev), lib_mtm.computeScoreMap(ts[0][1], image))
+    view = np.ascontiguousarray(img)[10:100, 20:140]                         # a strided view, as torch slicing gives
+    batch = lib_mtm.matchTemplatesBatch(temps, [_FakeDeviceArray(img), img, _FakeDeviceArray(view)], score_threshold=0.5)
+    want = [lib_mtm.matchTemplates(temps, im, score_threshold=0.5) for im in (img, img, np.ascontiguousarray(view))]
+    assert [[(h[0], h[1], float(h[2])) for h in hits] for hits in batch] == [[(h[0], h[1], float(h[2])) for h in hits] for hits in want]
