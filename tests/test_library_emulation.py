@@ -124,3 +124,67 @@ def test_device_resident_images_through_the_real_host_code(lib_mtm):
     batch = lib_mtm.matchTemplatesBatch(temps, [_FakeDeviceArray(img), img, _FakeDeviceArray(view)], score_threshold=0.5)
     want = [lib_mtm.matchTemplates(temps, im, score_threshold=0.5) for im in (img, img, np.ascontiguousarray(view))]
     assert [[(h[0], h[1], float(h[2])) for h in hits] for hits in batch] == [[(h[0], h[1], float(h[2])) for h in hits] for hits in want]
+
+
+@pytest.mark.parametrize("seed", [203, 231])
+def test_call_sequences_keep_no_stale_state(lib_mtm, monkeypatch, seed):
+    """One context, a random sequence of calls that change image size, dtype, channel count, template set, method, threshold, N_object
+    and search box between them: everything the library keeps between calls (map geometry of equal-sized images, the hashed template
+    set, window moments, the candidate list, the result mirror) must never leak into the next answer.  Expected results: the port
+    on EXACT maps (live cv2's own fp32 noise moves near-threshold peaks of methods 1 / 3)."""
+    import warnings
+    from oracle import mtm_port, ncc_exact, synth
+
+    def exact_map(template, image, method=5, mask=None):
+        if not (template.dtype == np.uint8 and image.dtype == np.uint8):
+            template, image = np.float32(template), np.float32(image)
+        return ncc_exact.match_template_exact(image, template, method)
+
+    monkeypatch.setattr(mtm_port, "compute_score_map", exact_map)
+    rng = np.random.default_rng(seed)
+    sets, scenes = {}, {}
+    for step in range(8):
+        C = int(rng.choice([1, 1, 3]))
+        kind = int(rng.integers(0, 2))
+        if (kind, C) not in sets:
+            k = int(rng.integers(1, 5))
+            shapes = [(int(rng.integers(8, 25)), int(rng.integers(8, 30)))] * k if kind == 0 else \
+                [(int(rng.integers(6, 25)), int(rng.integers(6, 30))) for _ in range(k)]
+            ts = [synth.make_template(rng, h, w) for h, w in shapes]
+            if C == 3:
+                ts = [np.ascontiguousarray(np.stack([t, 255 - t, t[::-1, ::-1]], axis=2)) for t in ts]
+            sets[kind, C] = [("t%d" % i, t) for i, t in enumerate(ts)]
+        temps = sets[kind, C]
+        idx = int(rng.integers(0, 3))
+        if (idx, kind, C) not in scenes:
+            H, W = [(90, 130), (90, 130), (70, 101)][idx]
+            img, _ = synth.make_scene(H, W, [t[1] if C == 1 else t[1][:, :, 0] for t in temps], 2, seed=seed * 10 + idx)
+            scenes[idx, kind, C] = img if C == 1 else np.ascontiguousarray(np.stack([img, 255 - img, img[::-1, ::-1]], axis=2))
+        img = scenes[idx, kind, C]
+        dt = rng.choice(["u8", "u8", "u8", "f32", "u16"]) if C == 1 else rng.choice(["u8", "u8", "f32"])
+        if dt == "f32":
+            im, ts = img.astype(np.float32), [(n, t.astype(np.float32)) for n, t in temps]
+        elif dt == "u16":
+            im, ts = img.astype(np.uint16) * 150, [(n, t.astype(np.uint16) * 150) for n, t in temps]
+        else:
+            im, ts = img, temps
+        method = int(rng.choice([5, 5, 5, 1, 3]))
+        thr = 0.9 if method == 3 else float(rng.choice([0.3, 0.4])) if method == 1 else float(rng.choice([0.4, 0.5, 0.7]))
+        n_object = [float("inf"), 1, int(rng.integers(2, 6))][int(rng.integers(0, 3))]
+        box = (int(rng.integers(0, 10)), int(rng.integers(0, 10)), im.shape[1] - 12, im.shape[0] - 12) if rng.random() < 0.3 else None
+        kw = dict(method=method, N_object=n_object, score_threshold=thr, maxOverlap=float(rng.choice([0.0, 0.25, 0.5])), searchBox=box)
+        op = int(rng.integers(0, 3))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            if op == 0:
+                got, want = lib_mtm.matchTemplates(ts, im, **kw), mtm_port.match_templates(ts, im, **kw)
+                assert [(h[0], h[1]) for h in got] == [(h[0], h[1]) for h in want], (step, kw)
+                assert all(abs(float(a[2]) - float(b[2])) <= 1e-4 for a, b in zip(got, want))
+            elif op == 1:
+                kw.pop("maxOverlap")
+                got, want = lib_mtm.findMatches(ts, im, **kw), mtm_port.find_matches(ts, im, **kw)
+                assert sorted((h[0], h[1]) for h in got) == sorted((h[0], h[1]) for h in want), (step, kw)
+            else:
+                t = ts[int(rng.integers(0, len(ts)))][1]
+                got, want = lib_mtm.computeScoreMap(t, im, method=method), exact_map(t, im, method)
+                assert got.shape == want.shape and float(np.max(np.abs(got - want))) <= 1e-4 * max(1.0, float(np.abs(want).max())), (step, method)
