@@ -14,7 +14,8 @@
 //                           on the tensor path (h*w*C <= 66051).
 //
 // A CTA owns one size (blockIdx.z), a strip of 1024 image columns (4 per thread, aligned 32-bit loads) and a band of
-// output rows; it first accumulates the h-1 rows above its band (adds only).  HBM-bound by design: the image is read from L2 (each row
+// output rows; it first accumulates the h-1 rows above its band (adds only, eight row loads in flight); the two rows that enter
+// and leave the window are fetched one output row ahead.  HBM-bound by design: the image is read from L2 (each row
 // (band overlap) times), the moment maps are written once: 8 B (C = 1) or 4(C+1) B per window position.
 //
 // Experiment knob MTM_B200_MOM_BOX=1 (mtm_api.cu: the summed-area tables are then built on demand only).  Checked on the
@@ -56,13 +57,15 @@ box_moments_kernel(const BoxParams p)
 #pragma unroll
         for (int j = 0; j < BM_PX; ++j) V[q][j] = 0u;
 
-    // adds (SUB = false) or subtracts image row r to / from the running column sums of this thread's 4 pixels
-    auto row_update = [&](int r, bool sub) {
+    // the C 32-bit words holding this thread's 4 pixels of image row r
+    auto load_row = [&](int r, uint32_t (&wd)[C]) {
         const uint8_t* row = p.img + (int64_t)r * p.pitch + col_byte;
-        uint32_t wd[C];
 #pragma unroll
         for (int k = 0; k < C; ++k)
             wd[k] = (col_byte + 4 * k + 4 <= p.pitch) ? __ldg(reinterpret_cast<const uint32_t*>(row) + k) : 0u;   // beyond the row: no pixels
+    };
+    // adds or subtracts those words to / from the running column sums
+    auto accumulate = [&](const uint32_t (&wd)[C], bool sub) {
 #pragma unroll
         for (int j = 0; j < BM_PX; ++j) {
 #pragma unroll
@@ -74,11 +77,33 @@ box_moments_kernel(const BoxParams p)
         }
     };
 
-    for (int r = y0; r < y0 + sd.h - 1; ++r) row_update(r, false);
+    // the h-1 rows above the band: eight independent loads in flight (one L2 round trip per eight rows, not per row)
+    constexpr int WARM = 8;
+    int r = y0;
+    const int r_end = y0 + sd.h - 1;
+    for (; r + WARM <= r_end; r += WARM) {
+        uint32_t wd[WARM][C];
+#pragma unroll
+        for (int u = 0; u < WARM; ++u) load_row(r + u, wd[u]);
+#pragma unroll
+        for (int u = 0; u < WARM; ++u) accumulate(wd[u], false);
+    }
+    for (; r < r_end; ++r) {
+        uint32_t wd[C];
+        load_row(r, wd);
+        accumulate(wd, false);
+    }
     const uint32_t area = (uint32_t)sd.h * (uint32_t)sd.w;
+    // the rows entering and leaving the window are fetched one output row ahead, behind the scan and the stores of the current one
+    uint32_t w_in[C], w_out[C];
+    load_row(y0 + sd.h - 1, w_in);
+    load_row(y0, w_out);
     for (int y = y0; y < y1; ++y) {
         const int buf = (y - y0) & 1;
-        row_update(y + sd.h - 1, false);
+        accumulate(w_in, false);
+        uint32_t n_in[C], n_out[C];
+        const bool more = y + 1 < y1;
+        if (more) { load_row(y + sd.h, n_in); load_row(y + 1, n_out); }
         // block-wide exclusive prefix of every quantity along x
         uint32_t incl[C + 1];
 #pragma unroll
@@ -125,7 +150,11 @@ box_moments_kernel(const BoxParams p)
             if (C > 1) p.rsD[out_row + x] = rs;
             else reinterpret_cast<uint2*>(p.S)[out_row + x] = make_uint2(s0, __float_as_uint(rs));
         }
-        row_update(y, true);
+        accumulate(w_out, true);
+        if (more) {
+#pragma unroll
+            for (int k = 0; k < C; ++k) { w_in[k] = n_in[k]; w_out[k] = n_out[k]; }
+        }
     }
 }
 
