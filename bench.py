@@ -61,7 +61,7 @@ def load_peaks():
 def build_workload(name, n_images):
     """Seeded synthetic inputs of SURVEY.md 8(d); the image pool is made of circular
     shifts of a few generated scenes (distinct memory, same statistics)."""
-    from oracle import synth
+    import workloads as synth
     base_imgs = []
     image0, templates, params = synth.config(name, seed=0)
     base_imgs.append(image0)
@@ -216,7 +216,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world != args.gpus and world > 1:
         args.gpus = world
-    from oracle import synth
+    import workloads as synth
 
     # ------------------------------------------------------------------ reference arm
     if args.impl == "reference":

@@ -42,7 +42,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     import MTM
     from mtm_b200 import sharded
-    from oracle import synth
+    import workloads as synth
     if args.mode == "images":
         return bench_images(args, MTM, sharded, synth, torch, dist, rank, world)
     image, temps, params = synth.config(args.workload)

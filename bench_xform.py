@@ -9,7 +9,7 @@ back on the host every call; a synchronize on both sides of every timed loop):
     with a different set every call ("cold": upload + statistics + Toeplitz slabs every call);
   * C3-shaped pyramid: 4096x4096 image, one 256x256 template -- `matchTemplatesPyramid(downscale=2, 4, 8)` against
     the full-resolution `matchTemplates`, checking that the hit lists agree.
-Nothing under oracle/ is timed; oracle.synth only generates the inputs.
+Nothing under oracle/ is imported; workloads.py generates the inputs.
 """
 import argparse
 import json
@@ -43,7 +43,7 @@ def main():
     args = ap.parse_args()
     import MTM
     from mtm_b200 import _native
-    from oracle import synth
+    import workloads as synth
     ctx = _native.default_context()
     rng = np.random.default_rng(0)
 

@@ -27,7 +27,8 @@ Modules
 ``nms_port``       restated ``cv2.dnn.NMSBoxes`` (NMSFast_ + jaccardDistance).
 ``mtm_port``       restated MTM orchestration (``MTM/__init__.py:22-296``,
                    ``MTM/NMS.py:20-84``) on top of live cv2 + ``peaks``.
-``synth``          seeded synthetic inputs of SURVEY.md section 8(d).
+``synth``          re-export of the repo-level ``workloads`` module (seeded synthetic inputs of
+                   SURVEY.md section 8(d); the benches import ``workloads`` directly).
 ``ref_loader``     imports the UNMODIFIED reference from /root/reference (build
                    container only) to pin the restatement and make fixtures.
 
