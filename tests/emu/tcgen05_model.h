@@ -112,6 +112,11 @@ static inline uint8_t emu_operand_byte(uint64_t desc, int row, int k)
     const uint32_t start = (uint32_t)(desc & 0x3FFFu) << 4, lbo = (uint32_t)((desc >> 16) & 0x3FFFu) << 4, sbo = (uint32_t)((desc >> 32) & 0x3FFFu) << 4;
     return *emu_smem_ptr(start + (uint32_t)(row >> 3) * sbo + (uint32_t)(row & 7) * 16u + (uint32_t)(k >> 4) * lbo + (uint32_t)(k & 15));
 }
+static inline const uint8_t* emu_operand_row16(uint64_t desc, int row, int k)
+{
+    const uint32_t start = (uint32_t)(desc & 0x3FFFu) << 4, lbo = (uint32_t)((desc >> 16) & 0x3FFFu) << 4, sbo = (uint32_t)((desc >> 32) & 0x3FFFu) << 4;
+    return emu_smem_ptr(start + (uint32_t)(row >> 3) * sbo + (uint32_t)(row & 7) * 16u + (uint32_t)(k >> 4) * lbo);
+}
 static inline void umma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
 {
     const int N = (int)((idesc >> 17) & 0x3Fu) << 3, M = (int)((idesc >> 24) & 0x1Fu) << 4;
@@ -119,15 +124,18 @@ static inline void umma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, ui
     if (M != 128 || N < 16 || N > 256 || (N & 15) || lane0 != 0 || col0 + (uint32_t)N > emu_tmem_cols || ((idesc >> 4) & 3u) != 2u) {
         fprintf(stderr, "tcgen05.mma: bad instruction descriptor / accumulator (M %d N %d lane %u col %u of %u)\n", M, N, lane0, col0, emu_tmem_cols); abort();
     }
-    uint8_t A[128][32], B[256][32];
-    for (int m = 0; m < M; ++m) for (int k = 0; k < 32; ++k) A[m][k] = emu_operand_byte(a_desc, m, k);
-    for (int n = 0; n < N; ++n) for (int k = 0; k < 32; ++k) B[n][k] = emu_operand_byte(b_desc, n, k);
-    for (int m = 0; m < M; ++m)
+    alignas(32) uint8_t A[128][32], B[256][32];
+    for (int m = 0; m < M; ++m) for (int k = 0; k < 32; k += 16) memcpy(&A[m][k], emu_operand_row16(a_desc, m, k), 16);   // a core-matrix row is 16 contiguous bytes
+    for (int n = 0; n < N; ++n) for (int k = 0; k < 32; k += 16) memcpy(&B[n][k], emu_operand_row16(b_desc, n, k), 16);
+    for (int m = 0; m < M; ++m) {
+        uint16_t a16[32];
+        for (int k = 0; k < 32; ++k) a16[k] = A[m][k];
         for (int n = 0; n < N; ++n) {
-            uint32_t s = accumulate ? emu_tmem[m][col0 + n] : 0u;
-            for (int k = 0; k < 32; ++k) s += (uint32_t)A[m][k] * (uint32_t)B[n][k];
-            emu_tmem[m][col0 + n] = s;
+            uint32_t s = 0;
+            for (int k = 0; k < 32; ++k) s += (uint32_t)a16[k] * (uint32_t)B[n][k];
+            emu_tmem[m][col0 + n] = (accumulate ? emu_tmem[m][col0 + n] : 0u) + s;
         }
+    }
     emu_mma_count++;
 }
 static inline void umma_commit(uint64_t* bar)

@@ -125,7 +125,8 @@ def build(out_dir, sm_count=4):
             f.write(host_source(name))
         obj = cpp[:-4] + ".o"
         objs.append(obj)
-        jobs.append([gxx, "-O1", "-std=c++20", "-fPIC", "-w", "-DEMU_SM_COUNT=%d" % sm_count, "-I", EMU, "-I", CSRC, "-I", os.path.join(ROOT, "include"),
+        opt = ["-O3", "-march=native"] if name == "ncc_tc.cu" else ["-O1"]       # the tcgen05.mma model is the hot loop of the emulation
+        jobs.append([gxx] + opt + ["-std=c++20", "-fPIC", "-w", "-DEMU_SM_COUNT=%d" % sm_count, "-I", EMU, "-I", CSRC, "-I", os.path.join(ROOT, "include"),
                      "-c", cpp, "-o", obj])
 
     def run(cmd):
