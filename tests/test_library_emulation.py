@@ -188,3 +188,10 @@ def test_call_sequences_keep_no_stale_state(lib_mtm, monkeypatch, seed):
                 t = ts[int(rng.integers(0, len(ts)))][1]
                 got, want = lib_mtm.computeScoreMap(t, im, method=method), exact_map(t, im, method)
                 assert got.shape == want.shape and float(np.max(np.abs(got - want))) <= 1e-4 * max(1.0, float(np.abs(want).max())), (step, method)
+
+
+def test_baseline_config_c2_at_full_size(lib_mtm):
+    """BASELINE configs[1] -- 1920 x 1080, 8 templates 64 x 64 (two bases x four rotations), threshold 0.5 -- through the host build at
+    FULL size: 585 tiles and 112 320 tcgen05.mma on the functional model, candidate list, one-launch sort + NMS; the hit list equals the
+    port's (the body of tests/test_gpu_parity.py::test_baseline_configs_full_size[C2])."""
+    gp.test_baseline_configs_full_size(lib_mtm, "C2")
