@@ -125,6 +125,32 @@ static bool emu_coop = false;
 static void (*emu_body_call)(void*) = nullptr;
 static void* emu_body_ptr = nullptr;
 
+// EMU_SCHED_SEED=<n> (environment): instead of round-robin, the scheduler visits the runnable fibers in a pseudo-random order and the
+// modelled hardware operations (tests/emu/tcgen05_model.h) become preemption points -- other legal interleavings of the same kernel,
+// to look for races in its synchronisation.  Deterministic for a given seed.
+static uint64_t emu_rng_state = 0;
+static bool emu_random_sched = false;
+static inline uint32_t emu_rand()
+{
+    emu_rng_state = emu_rng_state * 6364136223846793005ull + 1442695040888963407ull;
+    return (uint32_t)(emu_rng_state >> 33);
+}
+static inline void emu_sched_init()
+{
+    const char* v = getenv("EMU_SCHED_SEED");
+    emu_random_sched = v != nullptr;
+    if (v) emu_rng_state = 0x9E3779B97F4A7C15ull ^ (uint64_t)atoll(v);
+}
+static const volatile uint32_t emu_always_ready = 1;
+// a point where the running fiber may be preempted (random scheduling only)
+static inline void emu_preempt_point()
+{
+    if (!emu_random_sched || emu_cur < 0 || (emu_rand() & 3u) != 0) return;
+    EmuFiber& f = emu_fibers[emu_cur];
+    f.wait_ptr = &emu_always_ready; f.wait_val = 0;         // runnable again at once
+    swapcontext(&f.ctx, &emu_sched_ctx);
+}
+
 // parks the running fiber until *ptr != val
 static inline void emu_wait_change(const volatile uint32_t* ptr, uint32_t val)
 {
@@ -221,6 +247,7 @@ template <typename F> static void emu_launch_coop(dim3 grid, dim3 block, F body)
     gridDim = grid; blockDim = block;
     const int nthreads = (int)(block.x * block.y * block.z);
     while ((int)emu_stacks.size() < nthreads) emu_stacks.emplace_back(new char[EMU_STACK]);
+    emu_sched_init();
     emu_body_call = [](void* p) { (*static_cast<F*>(p))(); };
     emu_body_ptr = &body;
     emu_coop = true;
@@ -246,9 +273,14 @@ template <typename F> static void emu_launch_coop(dim3 grid, dim3 block, F body)
                     makecontext(&f.ctx, emu_fiber_main, 0);
                 }
                 int live = nthreads;
+                std::vector<int> visit(nthreads);
+                for (int t = 0; t < nthreads; ++t) visit[t] = t;
                 while (live > 0) {
                     bool ran = false;
-                    for (int t = 0; t < nthreads; ++t) {
+                    if (emu_random_sched)
+                        for (int t = nthreads - 1; t > 0; --t) std::swap(visit[t], visit[emu_rand() % (uint32_t)(t + 1)]);
+                    for (int v = 0; v < nthreads; ++v) {
+                        const int t = visit[v];
                         EmuFiber& f = emu_fibers[t];
                         if (f.done) continue;
                         if (f.wait_ptr) {

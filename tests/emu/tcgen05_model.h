@@ -42,6 +42,7 @@ static inline EmuMbar& emu_mbar_at(uint64_t* bar)
 }
 static inline void mbar_arrive(uint64_t* bar)
 {
+    emu_preempt_point();
     EmuMbar& b = emu_mbar_at(bar);
     if (b.pending <= 0) { fprintf(stderr, "mbarrier at %u: more arrivals than its count\n", smem_u32(bar)); abort(); }
     b.pending--; emu_mbar_settle(b);
@@ -79,6 +80,7 @@ static inline void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes
     if ((bytes & 15u) || (smem_u32(dst_smem) & 15u) || (reinterpret_cast<uintptr_t>(src_gmem) & 15u)) {
         fprintf(stderr, "cp.async.bulk: size / addresses must be multiples of 16\n"); abort();
     }
+    emu_preempt_point();
     if (getenv("EMU_TC_TRACE")) fprintf(stderr, "[block %u] bulk copy %u bytes -> smem %u, barrier %u\n", blockIdx.x, bytes, smem_u32(dst_smem), smem_u32(bar));
     memcpy(dst_smem, src_gmem, bytes);
     emu_bulk_bytes += bytes;
@@ -119,6 +121,7 @@ static inline const uint8_t* emu_operand_row16(uint64_t desc, int row, int k)
 }
 static inline void umma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
 {
+    emu_preempt_point();
     const int N = (int)((idesc >> 17) & 0x3Fu) << 3, M = (int)((idesc >> 24) & 0x1Fu) << 4;
     const uint32_t lane0 = d_tmem >> 16, col0 = d_tmem & 0xFFFFu;
     if (M != 128 || N < 16 || N > 256 || (N & 15) || lane0 != 0 || col0 + (uint32_t)N > emu_tmem_cols || ((idesc >> 4) & 3u) != 2u) {
@@ -145,6 +148,7 @@ static inline void umma_commit(uint64_t* bar)
 }        // every MMA issued so far has already executed
 static inline void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
 {
+    emu_preempt_point();
     const uint32_t lane = (taddr >> 16) + (uint32_t)emu_lane, col = taddr & 0xFFFFu;
     if (lane >= 128 || col + 16 > 512) { fprintf(stderr, "tcgen05.ld outside tensor memory\n"); abort(); }
     if ((taddr >> 16) != 32u * (uint32_t)(emu_warp & 3)) { fprintf(stderr, "tcgen05.ld: warp %d may only read lanes %d..%d\n", emu_warp, 32 * (emu_warp & 3), 32 * (emu_warp & 3) + 31); abort(); }
