@@ -20,14 +20,15 @@
 extern "C" {
 #endif
 
-#define MTM_ABI_VERSION 1
+#define MTM_ABI_VERSION 2
 
 typedef enum mtm_status {
     MTM_OK = 0,
     MTM_ERR_INVALID = -1,      /* bad argument (shape, dtype, null pointer, state)          */
     MTM_ERR_CUDA = -2,         /* CUDA runtime / driver failure (message has the details)   */
     MTM_ERR_CAPACITY = -3,     /* caller's hit buffer too small; *n_hits holds the need     */
-    MTM_ERR_UNSUPPORTED = -4   /* valid for the reference, not implemented on the GPU yet   */
+    MTM_ERR_UNSUPPORTED = -4,  /* valid for the reference, not implemented on the GPU yet   */
+    MTM_ERR_PEER = -5          /* another rank of the communicator failed inside a collective call */
 } mtm_status;
 
 /* MTM_U16: 16-bit unsigned pixels (image AND templates).  The reference casts them to float32 before
@@ -84,6 +85,8 @@ typedef struct mtm_ctx mtm_ctx;
 
 /* ---- lifetime ------------------------------------------------------------- */
 int mtm_abi_version(void);
+/* Number of usable (sm_100) CUDA devices visible to the process, 0 without a GPU / driver (never fails). */
+int mtm_device_count(void);
 int mtm_create(int device, mtm_ctx** out);
 int mtm_destroy(mtm_ctx* ctx);
 /* ctx may be NULL: returns the message of the last failed mtm_create(). */
@@ -179,6 +182,56 @@ int mtm_match_templates(mtm_ctx* ctx, int method, int64_t n_object, double score
 int mtm_match_templates_async(mtm_ctx* ctx, int method, int64_t n_object, double score_threshold,
                               double max_overlap, int slot);
 int mtm_match_templates_collect(mtm_ctx* ctx, int slot, mtm_hit* hits, int capacity, int* n_hits);
+
+/* ---- multi-GPU: the two cuts of the reference's parallel axis (SURVEY 8 b/e) ------------------------------
+ * The reference runs one task per template (MTM/__init__.py:172-175) and couples them again only in the NMS
+ * (MTM/__init__.py:294-296).  Across GPUs the same cut needs ONE exchange: an all-gather of the ranks' hit
+ * blocks (32-byte count header + 32-byte records) over NCCL / NVLink, issued by the library on the context's
+ * stream between the peak kernels and the replicated NMS kernel -- no host round trip, no torch.
+ *
+ * A communicator (mtm_comm) is one rank's endpoint:
+ *   mtm_comm_init_rank  one process per GPU (torchrun): rank 0 makes an id with mtm_comm_unique_id, the launcher
+ *                       hands its MTM_COMM_ID_BYTES bytes to every rank (file, socket, environment ...);
+ *   mtm_comm_create     one process driving n GPUs: out[0..n) receive n endpoints (ncclCommInitAll); each must
+ *                       then be driven by its own host thread.  When every entry of `devices` names the SAME
+ *                       GPU the group runs on an in-process loop-back (device-to-device copies ordered by CUDA
+ *                       events instead of NCCL), which lets a single-GPU box exercise the whole exchange.
+ * libnccl.so.2 is resolved at run time (dlopen; override with MTM_B200_NCCL_LIB): a single-GPU user of the
+ * library needs no NCCL.  world == 1 never touches NCCL. */
+typedef struct mtm_comm mtm_comm;
+#define MTM_COMM_ID_BYTES 128
+int mtm_comm_unique_id(void* id_out);
+int mtm_comm_init_rank(int device, int world, int rank, const void* id, mtm_comm** out);
+int mtm_comm_create(int n, const int* devices, mtm_comm** out);
+int mtm_comm_destroy(mtm_comm* comm);
+int mtm_comm_info(const mtm_comm* comm, int* world, int* rank, int* device);
+/* comm may be NULL: message of the last failed mtm_comm_init_rank / mtm_comm_create / mtm_comm_unique_id. */
+const char* mtm_comm_last_error(const mtm_comm* comm);
+/* Element-wise MAX of `n` doubles over the ranks (device-timed durations: "max over ranks"), and a barrier. */
+int mtm_comm_allreduce_max(mtm_comm* comm, double* values, int n);
+int mtm_comm_barrier(mtm_comm* comm);
+
+/* mtm_match_templates_sharded: MTM.matchTemplates (MTM/__init__.py:247-296) with the TEMPLATE LIST cut into
+ * contiguous slices, one per rank (BASELINE configs[3]).  Every rank holds the whole image and its own slice of
+ * `n_local` templates in `ctx` (mtm_set_templates with the slice; n_local == 0: this rank contributes nothing and
+ * the templates resident in ctx are ignored); `tmpl_base` is the list index of the slice's first template.
+ * Local stage: score maps -> peaks of the slice (the per-template tasks of :172-175).  Exchange: one all-gather of
+ * the hit blocks; the rank-ordered concatenation is the list findMatches would have returned.  Then every rank
+ * runs the identical global NMS (:294-296) on its GPU and returns the identical list; hits[].tmpl indexes the
+ * WHOLE template list.  A rank whose local stage fails still takes part in the exchange and every rank returns
+ * an error (the failing one its own, the others MTM_ERR_PEER): nobody is left waiting in the collective. */
+int mtm_match_templates_sharded(mtm_ctx* ctx, mtm_comm* comm, int tmpl_base, int n_local, int method, int64_t n_object,
+                                double score_threshold, double max_overlap, mtm_hit* hits, int capacity, int* n_hits);
+
+/* mtm_gather_results: the IMAGE cut (BASELINE configs[4]: a batch of images, NMS local to an image).  Rank r has
+ * submitted its n_local <= images_per_rank images with mtm_match_templates_async: submission i sits in slot
+ * slots[i] of context ctxs[i].  One all-gather of images_per_rank blocks per rank (header + hits_per_image
+ * records) hands every image's final hit list to every rank: out_hits[(r * images_per_rank + i) * hits_per_image
+ * + k], out_counts[r * images_per_rank + i] = number of hits, -1 for an unused entry, -2 when that image did not
+ * fit (more than hits_per_image hits, or outside the fused fast path): re-run it with mtm_match_templates.
+ * The gathered slots are released (no mtm_match_templates_collect afterwards). */
+int mtm_gather_results(mtm_comm* comm, int n_local, mtm_ctx* const* ctxs, const int* slots, int images_per_rank,
+                       int hits_per_image, mtm_hit* out_hits, int32_t* out_counts);
 
 #ifdef __cplusplus
 }

@@ -10,7 +10,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmtm_b200.so")
 
-MTM_OK, MTM_ERR_INVALID, MTM_ERR_CUDA, MTM_ERR_CAPACITY, MTM_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
+MTM_OK, MTM_ERR_INVALID, MTM_ERR_CUDA, MTM_ERR_CAPACITY, MTM_ERR_UNSUPPORTED, MTM_ERR_PEER = 0, -1, -2, -3, -4, -5
 MTM_U8, MTM_F32, MTM_U16 = 0, 1, 2
 PATH_AUTO, PATH_DIRECT, PATH_TENSOR = 0, 1, 2
 OPT_PATH, OPT_TIME_NCC = 0, 1
@@ -31,6 +31,7 @@ class Counters(ctypes.Structure):
 _P = ctypes.c_void_p
 _SIGNATURES = {
     "mtm_abi_version": (ctypes.c_int, []),
+    "mtm_device_count": (ctypes.c_int, []),
     "mtm_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(_P)]),
     "mtm_destroy": (ctypes.c_int, [_P]),
     "mtm_last_error": (ctypes.c_char_p, [_P]),
@@ -64,8 +65,23 @@ _SIGNATURES = {
     "mtm_match_templates_async": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_double,
                                                  ctypes.c_int]),
     "mtm_match_templates_collect": (ctypes.c_int, [_P, ctypes.c_int, _P, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
+    # multi-GPU
+    "mtm_comm_unique_id": (ctypes.c_int, [_P]),
+    "mtm_comm_init_rank": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, _P, ctypes.POINTER(_P)]),
+    "mtm_comm_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(_P)]),
+    "mtm_comm_destroy": (ctypes.c_int, [_P]),
+    "mtm_comm_info": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
+    "mtm_comm_last_error": (ctypes.c_char_p, [_P]),
+    "mtm_comm_allreduce_max": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_double), ctypes.c_int]),
+    "mtm_comm_barrier": (ctypes.c_int, [_P]),
+    "mtm_match_templates_sharded": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_double,
+                                                   ctypes.c_double, _P, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
+    "mtm_gather_results": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(_P), ctypes.POINTER(ctypes.c_int), ctypes.c_int,
+                                          ctypes.c_int, _P, _P]),
 }
 MAX_INFLIGHT = 8
+COMM_ID_BYTES = 128
+SLOT_HITS = 1024
 
 _lib = None
 _lib_lock = threading.Lock()
@@ -346,6 +362,12 @@ class Context:
         self._check(rc)
         return buf[: n.value]
 
+    def match_templates_sharded(self, comm, tmpl_base, n_local, method, n_object, score_threshold, max_overlap):
+        """Template cut (mtm_match_templates_sharded): this context holds the image and its slice of the template list;
+        collective over ``comm``; every rank gets the same list, ``tmpl`` indexing the whole template list."""
+        return self._hits_call(lambda h, *a: self._lib.mtm_match_templates_sharded(h, comm._h, *a),
+                               (int(tmpl_base), int(n_local), int(method), int(n_object), float(score_threshold), float(max_overlap)))
+
     def nms(self, hits, score_threshold, sort_ascending, n_object, max_overlap):
         hits = np.ascontiguousarray(hits, HIT_DTYPE)
         n = hits.shape[0]
@@ -356,15 +378,97 @@ class Context:
         return keep[: nk.value]
 
 
+class Comm:
+    """One rank's endpoint of a communicator (mtm_comm).  ``Comm.init_rank`` = one process per GPU (the NCCL id made by
+    ``Comm.unique_id()`` on rank 0 has to reach the other ranks: see ``rendezvous.py``); ``Comm.create(devices)`` = one
+    process driving several endpoints, each from its own thread (all devices equal: in-process loop-back)."""
+
+    def __init__(self, handle, lib):
+        self._h, self._lib = handle, lib
+        w, r, d = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        lib.mtm_comm_info(handle, ctypes.byref(w), ctypes.byref(r), ctypes.byref(d))
+        self.world, self.rank, self.device = w.value, r.value, d.value
+
+    @staticmethod
+    def unique_id():
+        lib = load()
+        buf = ctypes.create_string_buffer(COMM_ID_BYTES)
+        rc = lib.mtm_comm_unique_id(buf)
+        if rc != MTM_OK:
+            raise NativeError(rc, (lib.mtm_comm_last_error(None) or b"").decode())
+        return buf.raw
+
+    @classmethod
+    def init_rank(cls, device, world, rank, unique_id=None):
+        lib = load()
+        handle = _P()
+        idbuf = ctypes.create_string_buffer(unique_id, COMM_ID_BYTES) if unique_id is not None else None
+        rc = lib.mtm_comm_init_rank(int(device), int(world), int(rank), idbuf, ctypes.byref(handle))
+        if rc != MTM_OK:
+            raise NativeError(rc, (lib.mtm_comm_last_error(None) or b"").decode())
+        return cls(handle, lib)
+
+    @classmethod
+    def create(cls, devices):
+        lib = load()
+        n = len(devices)
+        devs = (ctypes.c_int * n)(*[int(d) for d in devices])
+        handles = (_P * n)()
+        rc = lib.mtm_comm_create(n, devs, handles)
+        if rc != MTM_OK:
+            raise NativeError(rc, (lib.mtm_comm_last_error(None) or b"").decode())
+        return [cls(_P(handles[i]), lib) for i in range(n)]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.mtm_comm_destroy(self._h)
+            self._h = None
+
+    def _check(self, rc):
+        if rc != MTM_OK:
+            raise NativeError(rc, (self._lib.mtm_comm_last_error(self._h) or b"").decode())
+
+    def allreduce_max(self, values):
+        arr = (ctypes.c_double * len(values))(*[float(v) for v in values])
+        self._check(self._lib.mtm_comm_allreduce_max(self._h, arr, len(values)))
+        return list(arr)
+
+    def barrier(self):
+        self._check(self._lib.mtm_comm_barrier(self._h))
+
+    def gather_results(self, entries, images_per_rank, hits_per_image):
+        """``entries`` = this rank's submissions in image order, as (Context, slot) pairs (mtm_match_templates_async).  Returns
+        (hits, counts): a (world * images_per_rank, hits_per_image) HIT_DTYPE array and the per-entry counts (-1 unused,
+        -2 does not fit / outside the fused fast path), identical on every rank."""
+        n = len(entries)
+        ctxs = (_P * max(n, 1))(*[c._h for c, _ in entries])
+        slots = (ctypes.c_int * max(n, 1))(*[int(s) for _, s in entries])
+        total = self.world * int(images_per_rank)
+        hits = np.zeros((total, int(hits_per_image)), HIT_DTYPE)
+        counts = np.zeros(total, np.int32)
+        self._check(self._lib.mtm_gather_results(self._h, n, ctxs, slots, int(images_per_rank), int(hits_per_image),
+                                                 _P(hits.ctypes.data), _P(counts.ctypes.data)))
+        return hits, counts
+
+
 _default = {}
 _helpers = {}
 _default_lock = threading.Lock()
 
 
+def local_device():
+    """CUDA ordinal of this process: MTM_B200_DEVICE when set, else LOCAL_RANK folded into the VISIBLE device count (a
+    launcher that gives every rank its own CUDA_VISIBLE_DEVICES leaves one visible device per rank: ordinal 0)."""
+    if "MTM_B200_DEVICE" in os.environ:
+        return int(os.environ["MTM_B200_DEVICE"])
+    n = load().mtm_device_count()
+    return int(os.environ.get("LOCAL_RANK", "0")) % max(n, 1)
+
+
 def default_context(device=None):
     """Lazily created per-device context used by the module-level API."""
     if device is None:
-        device = int(os.environ.get("MTM_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+        device = local_device()
     with _default_lock:
         ctx = _default.get(device)
         if ctx is None:
@@ -372,11 +476,13 @@ def default_context(device=None):
     return ctx
 
 
-def helper_contexts(device, n):
+def helper_contexts(device, n, owner=None):
     """``n`` additional lazily created contexts (= CUDA streams with their own workspaces) on ``device``, used next
-    to the caller's context by the batch entry point so that uploads overlap the searches of another stream."""
+    to the caller's context by the batch entry points so that uploads overlap the searches of another stream.
+    ``owner``: the caller's own context when it is not the default one -- helpers are per owner, so that two host
+    threads driving two contexts of one device never share (and wait for) a helper."""
     with _default_lock:
-        have = _helpers.setdefault(int(device), [])
+        have = _helpers.setdefault((int(device), id(owner) if owner is not None else None), [])
         while len(have) < n:
             have.append(Context(device))
         return have[:n]

@@ -162,7 +162,9 @@ box_moments_kernel(const BoxParams p)
 
 bool box_moments_enabled()
 {
-    static const bool on = getenv("MTM_B200_MOM_BOX") != nullptr && atoi(getenv("MTM_B200_MOM_BOX")) != 0;
+    // default ON since round 2 (profiles/README.md: C2 0.101 -> 0.082, C4 0.46 -> 0.41, C5 7.27 -> 6.00 ms per step against the
+    // summed-area route); MTM_B200_MOM_BOX=0 restores the tables + window_moments_kernel for A/B runs.
+    static const bool on = getenv("MTM_B200_MOM_BOX") == nullptr || atoi(getenv("MTM_B200_MOM_BOX")) != 0;
     return on;
 }
 

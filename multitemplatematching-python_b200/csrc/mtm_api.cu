@@ -44,10 +44,6 @@ static int reserve_pinned(mtm_ctx* ctx, T*& ptr, size_t& cap, size_t need)
     return MTM_OK;
 }
 
-#define MTM_TRY(expr) do { int rc__ = (expr); if (rc__ != MTM_OK) return rc__; } while (0)
-#define MTM_ENTER(ctx)                                                        \
-    if (!(ctx)) return MTM_ERR_INVALID;                                       \
-    MTM_CUDA(ctx, cudaSetDevice((ctx)->device))
 
 // Folds completed MTM_OPT_TIME_NCC event brackets into the counters.  `all`: wait for every pending
 // bracket; otherwise only wait when the ring is full.
@@ -91,7 +87,7 @@ static StageMarks g_marks;
 
 static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
-static int reserve_hits(mtm_ctx* ctx, int cap)
+int reserve_hits(mtm_ctx* ctx, int cap)
 {
     cap = next_pow2(std::max(cap, 1024));
     if (cap <= ctx->hit_cap) return MTM_OK;
@@ -120,6 +116,13 @@ static int reserve_hits(mtm_ctx* ctx, int cap)
 extern "C" {
 
 int mtm_abi_version(void) { return MTM_ABI_VERSION; }
+
+int mtm_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    return n;
+}
 
 const char* mtm_last_error(const mtm_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 
@@ -346,7 +349,7 @@ static int set_image_impl(mtm_ctx* ctx, const void* pixels, int H, int W, int C,
     return MTM_OK;
 }
 
-static int ensure_geometry(mtm_ctx* ctx)
+int ensure_geometry(mtm_ctx* ctx)
 {
     if (ctx->img.H == 0) return mtm_fail(ctx, MTM_ERR_INVALID, "no image set (call mtm_set_image first)");
     if (ctx->n_tmpl == 0) return mtm_fail(ctx, MTM_ERR_INVALID, "no templates set (call mtm_set_templates first)");
@@ -519,7 +522,7 @@ static int compute_maps_masked(mtm_ctx* ctx, int method)
 // May the numerator kernel's epilogue list the above-threshold pixels for the peak search?  Only for the
 // default method, the multi-object search and maps larger than the list (so that a constant map -- the one
 // case peak_local_max treats specially -- can never hide behind a short list).
-static void request_candidates(mtm_ctx* ctx, int method, int64_t n_object, double thr)
+void request_candidates(mtm_ctx* ctx, int method, int64_t n_object, double thr)
 {
     ctx->cand_on = false;
     static const bool no_cand = getenv("MTM_B200_NO_CAND") != nullptr;     // experiments: always stream the maps for peaks
@@ -533,7 +536,7 @@ static void request_candidates(mtm_ctx* ctx, int method, int64_t n_object, doubl
 }
 
 // Score maps of every template (tmpl < 0) or of one template, grouped by template size.
-static int compute_maps(mtm_ctx* ctx, int method, int tmpl)
+int compute_maps(mtm_ctx* ctx, int method, int tmpl)
 {
     if (method < 0 || method > 5) return mtm_fail(ctx, MTM_ERR_INVALID, "unknown method %d", method);
     const int n = ctx->n_tmpl;
@@ -660,7 +663,7 @@ struct TmplHasher {
 };
 
 // Downloads header + hits of a block into h_stage.  Returns the raw count in *n_raw.
-static int download_block(mtm_ctx* ctx, const uint8_t* d_block, int* n_raw, int* n_valid, int* declined = nullptr)
+int download_block(mtm_ctx* ctx, const uint8_t* d_block, int* n_raw, int* n_valid, int* declined)
 {
     const int PRE = 256;
     const int pre = std::min(PRE, ctx->hit_cap);
@@ -684,7 +687,7 @@ static int download_block(mtm_ctx* ctx, const uint8_t* d_block, int* n_raw, int*
 
 // Same contract as download_block for a result that finalize_small_kernel also stored in the mapped mirror:
 // one stream synchronise, no copy engine round trip.  Results longer than the mirror fetch the rest from the block.
-static int download_mirror(mtm_ctx* ctx, const uint8_t* d_block, int* n_raw, int* n_valid, int* declined)
+int download_mirror(mtm_ctx* ctx, const uint8_t* d_block, int* n_raw, int* n_valid, int* declined)
 {
     MTM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     const int32_t* hdr = reinterpret_cast<const int32_t*>(ctx->h_mirror);
@@ -705,7 +708,7 @@ static int download_mirror(mtm_ctx* ctx, const uint8_t* d_block, int* n_raw, int
     return MTM_OK;
 }
 
-static void copy_out(const mtm_ctx* ctx, mtm_hit* hits, int n)
+void copy_out(const mtm_ctx* ctx, mtm_hit* hits, int n)
 {
     const DevHit* src = reinterpret_cast<const DevHit*>(ctx->h_stage + MTM_HIT_HEADER);
     for (int i = 0; i < n; ++i) {

@@ -210,8 +210,22 @@ int mtm_fail(mtm_ctx* ctx, int code, const char* fmt, ...);
         MTM_CUDA(ctx, cudaGetLastError());                                           \
     } while (0)
 
+#define MTM_TRY(expr) do { int rc__ = (expr); if (rc__ != MTM_OK) return rc__; } while (0)
+#define MTM_ENTER(ctx)                                                        \
+    if (!(ctx)) return MTM_ERR_INVALID;                                       \
+    MTM_CUDA(ctx, cudaSetDevice((ctx)->device))
+
 template <typename T>
 int mtm_reserve(mtm_ctx* ctx, T*& ptr, size_t& cap, size_t need_elems);
+
+// ---- host-side stages of a search (mtm_api.cu), shared with the multi-GPU entry points (mtm_comm.cu)
+int reserve_hits(mtm_ctx* ctx, int cap);
+int ensure_geometry(mtm_ctx* ctx);
+void request_candidates(mtm_ctx* ctx, int method, int64_t n_object, double thr);
+int compute_maps(mtm_ctx* ctx, int method, int tmpl);
+int download_block(mtm_ctx* ctx, const uint8_t* d_block, int* n_raw, int* n_valid, int* declined = nullptr);
+int download_mirror(mtm_ctx* ctx, const uint8_t* d_block, int* n_raw, int* n_valid, int* declined);
+void copy_out(const mtm_ctx* ctx, mtm_hit* hits, int n);
 
 // ---- kernels (defined in the .cu files) -------------------------------------
 int launch_build_sat(mtm_ctx* ctx);
@@ -250,16 +264,26 @@ int launch_transform(mtm_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, const X
 // raw (unsorted) peaks of every template -> block A
 int launch_peaks(mtm_ctx* ctx, int method, int64_t n_object, float thr32, double thr64, bool allow_candidates = true);
 // in-place sort of block A (mode 0: findMatches order, mode 1: NMSBoxes order)
-int launch_sort_hits(mtm_ctx* ctx, int mode, int minimize, int ascending_key, int check_trivial);
+int launch_sort_hits(mtm_ctx* ctx, int mode, int minimize, int ascending_key, int check_trivial, bool prepped = false);
 // fast path (raw count <= 1024): sort(s) [+ NMS] in one launch; sets header[2] = 1 when it declines
 constexpr int MTM_MIRROR_HITS = 256;
 int launch_finalize_small(mtm_ctx* ctx, int minimize, int check_trivial, int presorted, int do_nms, float thr32,
-                          int ascending, int64_t n_object, float max_overlap, uint8_t* out_block = nullptr, bool mirror = false);
+                          int ascending, int64_t n_object, float max_overlap, uint8_t* out_block = nullptr, bool mirror = false,
+                          bool prepped = false);
 // block A (sorted mode 1) -> block B
 int launch_nms(mtm_ctx* ctx, float thr32, int ascending, int64_t n_object, float max_overlap);
 
 // ---- shared device helpers ----------------------------------------------------
 __host__ __device__ inline bool method_is_min(int method) { return method == 0 || method == 1; }
+
+// mode-0 sort keys are cached in the hit itself so that comparisons never touch global memory:
+// seq = row-major index in the score map, key = 1 for 1-D (find_peaks) maps.
+__device__ __forceinline__ void prep_mode0(DevHit& h, const TmplMeta* __restrict__ meta)
+{
+    const TmplMeta& tm = meta[h.tmpl];
+    h.seq = h.y * tm.mw + h.x;
+    h.key = (tm.mh == 1 || tm.mw == 1) ? 1.0f : 0.0f;
+}
 
 __device__ __forceinline__ uint32_t ordered_f32(float f) {
     f += 0.0f;                                    // -0 -> +0

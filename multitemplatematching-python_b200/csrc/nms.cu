@@ -39,14 +39,6 @@ __device__ __forceinline__ bool hit_less(const DevHit& a, const DevHit& b, const
     return a.seq < b.seq;
 }
 
-// mode-0 sort keys are cached in the hit itself so that comparisons never touch global memory
-__device__ __forceinline__ void prep_mode0(DevHit& h, const TmplMeta* __restrict__ meta)
-{
-    const TmplMeta& tm = meta[h.tmpl];
-    h.seq = h.y * tm.mw + h.x;
-    h.key = (tm.mh == 1 || tm.mw == 1) ? 1.0f : 0.0f;
-}
-
 __device__ __forceinline__ DevHit load_hit(const DevHit* p)
 {
     DevHit h;
@@ -67,7 +59,8 @@ __device__ __forceinline__ void store_hit(DevHit* p, const DevHit& h)
 // rule of peak_local_max) and, when assign_seq, numbers the survivors.
 __global__ void __launch_bounds__(1024, 1)
 sort_hits_kernel(DevHit* __restrict__ hits, int cap, int32_t* __restrict__ count, const TmplMeta* __restrict__ meta,
-                 const int32_t* __restrict__ nontrivial, int mode, int minimize, int ascending_key, int check_trivial)
+                 const int32_t* __restrict__ nontrivial, int mode, int minimize, int ascending_key, int check_trivial,
+                 int prepped)
 {
     __shared__ int dead;
     const int tid = threadIdx.x, nth = blockDim.x;
@@ -89,7 +82,7 @@ sort_hits_kernel(DevHit* __restrict__ hits, int cap, int32_t* __restrict__ count
                 hits[i].key = -CUDART_INF_F;
                 hits[i].seq = 0x7fffffff;
                 atomicAdd(&dead, 1);
-            } else {
+            } else if (!prepped) {              // gathered hits (mtm_match_templates_sharded) carry their keys already
                 DevHit h = load_hit(hits + i);
                 prep_mode0(h, meta);
                 store_hit(hits + i, h);
@@ -226,7 +219,7 @@ __device__ __forceinline__ void
 finalize_small_body(DevHit* __restrict__ hits, int cap, int32_t* __restrict__ count, const TmplMeta* __restrict__ meta,
                     const int32_t* __restrict__ nontrivial, int minimize, int check_trivial,
                     DevHit* __restrict__ out, int32_t* __restrict__ out_count, float thr32, int ascending,
-                    long long n_object, float max_overlap)
+                    long long n_object, float max_overlap, int prepped)
 {
     constexpr bool presorted = PRESORTED, do_nms = DO_NMS;
     __shared__ DevHit sh[FIN_CAP];
@@ -235,6 +228,8 @@ finalize_small_body(DevHit* __restrict__ hits, int cap, int32_t* __restrict__ co
     const int tid = threadIdx.x, nth = blockDim.x;
     const int n_raw = count[0];
     int32_t* flag_hdr = do_nms ? out_count : count;
+    // sharded calls: the merge kernel left the largest per-rank raw count in [4] and a failing rank's status in [5]
+    if (do_nms && tid < 4) out_count[4 + tid] = count[4 + tid];            // [4] largest per-rank count, [5] status, [6] largest raw count
     if (count[3]) { if (tid == 0) { flag_hdr[2] = 2; if (do_nms) out_count[1] = 0; } return; }   // candidate list overflowed
     if (n_raw > FIN_CAP) { if (tid == 0) { flag_hdr[2] = 1; if (do_nms) out_count[1] = n_raw; } return; }
     if (tid == 0) { s_live = 0; s_kept = 0; s_best = 0ull; flag_hdr[2] = 0; }
@@ -248,7 +243,7 @@ finalize_small_body(DevHit* __restrict__ hits, int cap, int32_t* __restrict__ co
         if (i < n_raw) {
             h = load_hit(hits + i);
             if (check_trivial && !nontrivial[h.tmpl]) { h.tmpl = 0x7fffffff; h.key = -CUDART_INF_F; h.seq = 0x7fffffff; dead_local++; }
-            else if (!presorted) prep_mode0(h, meta);
+            else if (!presorted && !prepped) prep_mode0(h, meta);
         } else {
             h.tmpl = 0x7fffffff; h.x = h.y = h.w = h.h = 0; h.score = 0.f; h.seq = 0x7fffffff; h.key = -CUDART_INF_F;
         }
@@ -353,11 +348,11 @@ __global__ void __launch_bounds__(256, 1)
 finalize_small_kernel(DevHit* __restrict__ hits, int cap, int32_t* __restrict__ count, const TmplMeta* __restrict__ meta,
                       const int32_t* __restrict__ nontrivial, int minimize, int check_trivial,
                       DevHit* __restrict__ out, int32_t* __restrict__ out_count, float thr32, int ascending,
-                      long long n_object, float max_overlap, uint8_t* __restrict__ mirror)
+                      long long n_object, float max_overlap, uint8_t* __restrict__ mirror, int prepped)
 {
     constexpr bool do_nms = DO_NMS;
     finalize_small_body<PRESORTED, DO_NMS>(hits, cap, count, meta, nontrivial, minimize, check_trivial, out, out_count, thr32,
-                                           ascending, n_object, max_overlap);
+                                           ascending, n_object, max_overlap, prepped);
     if (!mirror) return;
     __syncthreads();                                           // the block's own global writes are visible to all its threads
     const int32_t* hdr = do_nms ? out_count : count;
@@ -373,7 +368,7 @@ finalize_small_kernel(DevHit* __restrict__ hits, int cap, int32_t* __restrict__ 
 }  // namespace
 
 int launch_finalize_small(mtm_ctx* ctx, int minimize, int check_trivial, int presorted, int do_nms, float thr32,
-                          int ascending, int64_t n_object, float max_overlap, uint8_t* out_block, bool mirror)
+                          int ascending, int64_t n_object, float max_overlap, uint8_t* out_block, bool mirror, bool prepped)
 {
     uint8_t* ob = out_block ? out_block : ctx->d_blockB;
     static_assert(MTM_HIT_HEADER == 32 && sizeof(DevHit) == 32, "mirror layout");
@@ -381,7 +376,7 @@ int launch_finalize_small(mtm_ctx* ctx, int minimize, int check_trivial, int pre
     int32_t* oc = reinterpret_cast<int32_t*>(ob);
     uint8_t* mr = mirror ? ctx->d_mirror : nullptr;
 #define MTM_FIN(P, N) finalize_small_kernel<P, N><<<1, 256, 0, ctx->stream>>>(ctx->hitsA(), ctx->hit_cap, ctx->countA(), ctx->d_meta, \
-        ctx->d_nontrivial, minimize, check_trivial, oh, oc, thr32, ascending, (long long)n_object, max_overlap, mr)
+        ctx->d_nontrivial, minimize, check_trivial, oh, oc, thr32, ascending, (long long)n_object, max_overlap, mr, prepped ? 1 : 0)
     if (presorted) { if (do_nms) MTM_FIN(true, true); else MTM_FIN(true, false); }
     else { if (do_nms) MTM_FIN(false, true); else MTM_FIN(false, false); }
 #undef MTM_FIN
@@ -389,10 +384,10 @@ int launch_finalize_small(mtm_ctx* ctx, int minimize, int check_trivial, int pre
     return MTM_OK;
 }
 
-int launch_sort_hits(mtm_ctx* ctx, int mode, int minimize, int ascending_key, int check_trivial)
+int launch_sort_hits(mtm_ctx* ctx, int mode, int minimize, int ascending_key, int check_trivial, bool prepped)
 {
     sort_hits_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->hitsA(), ctx->hit_cap, ctx->countA(), ctx->d_meta,
-                                                  ctx->d_nontrivial, mode, minimize, ascending_key, check_trivial);
+                                                  ctx->d_nontrivial, mode, minimize, ascending_key, check_trivial, prepped ? 1 : 0);
     MTM_LAUNCH_CHECK(ctx);
     return MTM_OK;
 }

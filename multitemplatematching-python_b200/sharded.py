@@ -1,29 +1,25 @@
-"""Template-sharded ``matchTemplates`` across GPUs (one process per GPU, torch.distributed).
+"""``matchTemplates`` across GPUs: the two cuts of the reference's parallel axis.
 
-The reference parallelises over templates with a thread pool
-(``MTM/__init__.py:172-175``) and couples them again only in the NMS
-(``MTM/__init__.py:294-296``).  The same cut works across GPUs:
+The reference parallelises over templates with a thread pool (``MTM/__init__.py:172-175``) and couples them
+again only in the NMS (``MTM/__init__.py:294-296``).  Across GPUs:
 
-* every rank holds the whole image and template list (KBs..MBs) and searches a
-  CONTIGUOUS slice of the template list on its GPU (slices balanced by multiply-accumulate
-  count, so that a list of mixed template sizes -- BASELINE.json configs[4] -- loads the
-  ranks evenly) -> pre-NMS hits in the canonical order (template index, then the peak
-  finder's order);
-* one all-reduce(MAX) of the hit counts and ONE all-gather of fixed-size hit rows
-  (6 x int32 per hit; NCCL over NVLink for CUDA tensors, gloo on CPU);
-* concatenation in rank order IS the canonical global order, so every rank runs the
-  identical global NMS and returns the identical list.
+* ``matchTemplatesSharded`` -- TEMPLATE cut (BASELINE.json configs[3]): every rank holds the whole image and
+  searches a CONTIGUOUS slice of the template list (slices balanced by multiply-accumulate count, so that a list
+  of mixed template sizes loads the ranks evenly).  The library then exchanges the ranks' hit blocks with ONE
+  ``ncclAllGather`` on the context's stream and runs the identical global NMS on every GPU
+  (``mtm_match_templates_sharded``): no host round trip between the local search and the final list.
+* ``matchTemplatesBatchSharded`` -- IMAGE cut (configs[4]: a batch of images): contiguous blocks of the image list
+  per rank, the whole template list everywhere, NMS local to an image; ONE all-gather of the final per-image hit
+  blocks (``mtm_gather_results``) returns every image's list to every rank.
 
-``matchTemplatesBatchSharded`` is the other cut of SURVEY.md 8e (configs[4]: a batch of
-images): contiguous slices of the IMAGE list per rank, the whole template list everywhere,
-NMS stays local to the image, and the same single all-gather returns every image's final
-hit list to every rank.
-
-``find_fn`` / ``nms_fn`` / ``batch_fn`` are injectable so the host logic is testable on CPU
-with world_size 2 (tests/test_sharded_gloo.py uses the oracle there; the product default is
-the CUDA path).
+No torch here: the communicator is ``_native.Comm`` (NCCL inside libmtm_b200.so; ``rendezvous.comm_from_env()``
+builds it from the torchrun environment).  ``search_fn`` / ``batch_fn`` are injectable so that the host logic
+(partition, labels, offsets, validation before the collective) runs on CPU with world_size 2
+(tests/test_sharded_gloo.py drives it with the oracle and a gloo exchange).
 """
 import numpy as np
+
+from . import _native, api
 
 _INF = float("inf")
 
@@ -33,6 +29,14 @@ def shard_bounds(n_items, world, rank):
     base, extra = divmod(n_items, world)
     start = rank * base + min(rank, extra)
     return start, start + base + (1 if rank < extra else 0)
+
+
+def block_bounds(n_items, world, rank):
+    """Image cut: fixed blocks of ``ceil(n_items / world)`` images per rank (the gather layout), last ranks may idle.
+    Returns (start, stop, images_per_rank)."""
+    per = max(1, -(-n_items // world))
+    start = min(n_items, rank * per)
+    return start, min(n_items, start + per), per
 
 
 def weighted_bounds(weights, world):
@@ -77,111 +81,122 @@ def template_macs(listTemplates, image_shape, searchBox=None):
     return out
 
 
-def pack_hits(hits, first_index):
-    """(label '#k', bbox, score) hits -> int32 rows [global index, x, y, w, h, score bits]."""
-    rows = np.zeros((len(hits), 6), np.int32)
-    for i, (label, box, score) in enumerate(hits):
-        rows[i, 0] = first_index + int(label[1:])
-        rows[i, 1:5] = box
-        rows[i, 5] = np.array([score], np.float32).view(np.int32)[0]
-    return rows
-
-
-def unpack_hits(rows, listTemplates):
-    return [(listTemplates[int(r[0])][0], (int(r[1]), int(r[2]), int(r[3]), int(r[4])),
-             np.array([r[5]], np.int32).view(np.float32)[0]) for r in rows]
-
-
-def gather_rows(rows, group=None, device=None):
-    """All ranks contribute ``rows`` (k_r x ncol int32, same ncol everywhere); returns the rank-ordered concatenation."""
-    import torch
-    import torch.distributed as dist
-    if not dist.is_initialized() or dist.get_world_size(group) == 1:
-        return rows
-    world = dist.get_world_size(group)
-    if dist.get_backend(group) == "nccl":
-        dev = torch.device("cuda", device if device is not None else torch.cuda.current_device())
-    else:
-        dev = torch.device("cpu")
-    cap = torch.tensor([rows.shape[0]], dtype=torch.int64, device=dev)
-    dist.all_reduce(cap, op=dist.ReduceOp.MAX, group=group)
-    cap = max(int(cap.item()), 1)
-    ncol = rows.shape[1]
-    buf = torch.zeros((cap + 1, ncol), dtype=torch.int32, device=dev)     # row 0 = header (count)
-    buf[0, 0] = rows.shape[0]
-    if rows.shape[0]:
-        buf[1:1 + rows.shape[0]] = torch.from_numpy(rows).to(dev)
-    gathered = torch.empty((world * (cap + 1), ncol), dtype=torch.int32, device=dev)   # concatenated form (gloo + nccl)
-    dist.all_gather_into_tensor(gathered, buf, group=group)
-    g = gathered.cpu().numpy().reshape(world, cap + 1, ncol)
-    return np.concatenate([g[r, 1:1 + int(g[r, 0, 0])] for r in range(world)], axis=0)
+def _device_search(ctx, comm, arrays, masks, img, lo, method, n_dev, score_threshold, maxOverlap):
+    """Product path of the template cut: this rank's slice on its GPU, exchange + global NMS inside the library."""
+    with ctx.lock:
+        ctx.set_image(img)
+        if arrays:
+            api._upload_templates(ctx, arrays, masks)
+        return ctx.match_templates_sharded(comm, lo, len(arrays), method, n_dev, score_threshold, maxOverlap)
 
 
 def matchTemplatesSharded(listTemplates, image, method=5, N_object=_INF, score_threshold=0.5, maxOverlap=0.25,
-                          searchBox=None, *, group=None, device=None, find_fn=None, nms_fn=None):
-    """Same contract as ``MTM.matchTemplates``; collective over ``group`` (default: WORLD)."""
-    import torch.distributed as dist
-    if find_fn is None or nms_fn is None:
-        from . import api
-        find_fn = find_fn or api.findMatches
-        nms_fn = nms_fn or api.NMS
+                          searchBox=None, *, comm, context=None, search_fn=None):
+    """Same contract as ``MTM.matchTemplates``; collective over ``comm`` (every rank calls it with the same arguments
+    and receives the same list)."""
     if maxOverlap < 0 or maxOverlap > 1:
         raise ValueError("Maximal overlap between bounding box is in range [0-1]")
-    from .api import _validate_search
-    _validate_search(listTemplates, image, N_object, searchBox)          # the reference's errors, original labels
-    distributed = dist.is_initialized()
-    world = dist.get_world_size(group) if distributed else 1
-    rank = dist.get_rank(group) if distributed else 0
-    lo, hi = weighted_bounds(template_macs(listTemplates, image.shape, searchBox), world)[rank]
-    # unique per-shard labels '#k' carry the template index through the label-only hit tuples
-    mine = [("#%d" % k,) + tuple(entry[1:]) for k, entry in enumerate(listTemplates[lo:hi])]
-    local = find_fn(mine, image, method, N_object, score_threshold, searchBox) if mine else []
+    image = _native.as_image(image)
+    # every rank raises the reference's errors (original labels) BEFORE any collective
+    crop, xOffset, yOffset = api._validate_search(listTemplates, image, N_object, searchBox)
     if method == 0:
         raise ValueError("The method TM_SQDIFF is not supported. Use TM_SQDIFF_NORMED instead.")
-    rows = gather_rows(pack_hits(local, lo), group=group, device=device)
-    return nms_fn(unpack_hits(rows, listTemplates), score_threshold, method == 1, N_object, maxOverlap)
+    if len(listTemplates) == 0:
+        return []
+    finite = N_object != _INF
+    nms_threshold = (1 - score_threshold) if method == 1 else score_threshold
+    if (finite and N_object < 1) or nms_threshold < 0:
+        # rare corners whose behaviour depends on the pre-NMS list length (api.matchTemplates): replicated, no exchange
+        return api.matchTemplates(listTemplates, image, method, N_object, score_threshold, maxOverlap, searchBox, context=context)
+    names, arrays, img, masks = api._prepare(listTemplates, crop, method)
+    lo, hi = weighted_bounds(template_macs(listTemplates, image.shape, searchBox), comm.world)[comm.rank]
+    n_dev = int(N_object) if finite else -1
+    if search_fn is None:
+        ctx = context or _native.default_context(comm.device)
+        search_fn = lambda *a: _device_search(ctx, comm, *a)       # noqa: E731
+    raw = search_fn(arrays[lo:hi], masks[lo:hi], img, lo, method, n_dev, score_threshold, maxOverlap)
+    return api._to_hits(raw, names, xOffset, yOffset)
+
+
+def _device_batch(ctxs, comm, prepared, method, n_dev, score_threshold, maxOverlap, images_per_rank, hits_per_image):
+    """Product path of the image cut: this rank's images through the pipelined entry points of its contexts (streams),
+    then ONE all-gather of the final hit blocks.  ``prepared`` = [(arrays, masks, img)] of the local images."""
+    depth = _native.MAX_INFLIGHT
+    n_streams = len(ctxs)
+    assert len(prepared) <= depth * n_streams
+    uploaded = [None] * n_streams
+    entries = []
+    for i, (arrays, masks, img) in enumerate(prepared):
+        k = i % n_streams
+        c = ctxs[k]
+        c.set_image(img)
+        sig = (img.dtype, img.ndim, tuple(map(id, arrays)), tuple(map(id, masks)))
+        if uploaded[k] != sig:
+            api._upload_templates(c, arrays, masks)
+            uploaded[k] = sig
+        slot = (i // n_streams) % depth
+        c.match_templates_async(method, n_dev, score_threshold, maxOverlap, slot)
+        entries.append((c, slot))
+    return comm.gather_results(entries, images_per_rank, hits_per_image)
 
 
 def matchTemplatesBatchSharded(listTemplates, images, method=5, N_object=_INF, score_threshold=0.5, maxOverlap=0.25,
-                               searchBox=None, *, group=None, device=None, batch_fn=None):
-    """``[matchTemplates(listTemplates, im, ...) for im in images]`` with the IMAGES sharded over the ranks of ``group``.
-
-    Rank r searches the contiguous slice ``shard_bounds(len(images), world, r)`` of the image list with the whole
-    template list (``MTM.matchTemplatesBatch`` on its GPU: NMS is local to an image, MTM/__init__.py:296), then ONE
-    all-gather of 7 x int32 rows [image, template, x, y, w, h, score bits] hands every image's final hit list to
-    every rank.  Returns the same list of hit lists on every rank.
-    """
-    import torch.distributed as dist
-    images = list(images)
-    if batch_fn is None:
-        from . import api
-        batch_fn = api.matchTemplatesBatch
+                               searchBox=None, *, comm, context=None, streams=2, batch_fn=None):
+    """``[matchTemplates(listTemplates, im, ...) for im in images]`` with the IMAGES cut into blocks over the ranks of
+    ``comm``.  Rank r searches images ``block_bounds(len(images), world, r)`` with the whole template list
+    (``mtm_match_templates_async`` on its GPU: NMS is local to an image, MTM/__init__.py:296), then ONE all-gather of
+    fixed-size hit blocks (``mtm_gather_results``) hands every image's final hit list to every rank.  Returns the same
+    list of hit lists on every rank."""
+    images = [_native.as_image(im) for im in images]
     if maxOverlap < 0 or maxOverlap > 1:
         raise ValueError("Maximal overlap between bounding box is in range [0-1]")
-    from .api import _validate_search
-    for im in images:                               # every rank raises the reference's errors BEFORE the collective
-        _validate_search(listTemplates, im, N_object, searchBox)
+    checked = [api._validate_search(listTemplates, im, N_object, searchBox) for im in images]   # every rank, before the collective
     if method == 0:
         raise ValueError("The method TM_SQDIFF is not supported. Use TM_SQDIFF_NORMED instead.")
-    distributed = dist.is_initialized()
-    world = dist.get_world_size(group) if distributed else 1
-    rank = dist.get_rank(group) if distributed else 0
-    lo, hi = shard_bounds(len(images), world, rank)
-    relabelled = [("#%d" % k,) + tuple(entry[1:]) for k, entry in enumerate(listTemplates)]
-    local = batch_fn(relabelled, images[lo:hi], method, N_object, score_threshold, maxOverlap, searchBox) if hi > lo else []
-    n_rows = sum(len(hits) for hits in local)
-    rows = np.zeros((n_rows, 7), np.int32)
-    k = 0
-    for i, hits in enumerate(local):
-        for label, box, score in hits:              # the order inside an image is the NMS order: kept as is
-            rows[k, 0] = lo + i
-            rows[k, 1] = int(label[1:])
-            rows[k, 2:6] = box
-            rows[k, 6] = np.array([score], np.float32).view(np.int32)[0]
-            k += 1
-    rows = gather_rows(rows, group=group, device=device)
-    results = [[] for _ in images]
-    for r in rows:
-        results[int(r[0])].append((listTemplates[int(r[1])][0], (int(r[2]), int(r[3]), int(r[4]), int(r[5])),
-                                   np.array([r[6]], np.int32).view(np.float32)[0]))
+    finite = N_object != _INF
+    nms_threshold = (1 - score_threshold) if method == 1 else score_threshold
+    if len(listTemplates) == 0 or (finite and N_object < 1) or nms_threshold < 0:
+        return api.matchTemplatesBatch(listTemplates, images, method, N_object, score_threshold, maxOverlap, searchBox, context=context)
+    n_dev = int(N_object) if finite else -1
+    hits_per_image = min(max(n_dev, 1), _native.SLOT_HITS) if finite else _native.SLOT_HITS
+    results = [None] * len(images)
+    ctxs = None
+    if batch_fn is None:
+        ctx = context or _native.default_context(comm.device)
+        ctxs = [ctx] + _native.helper_contexts(ctx.device, max(1, int(streams)) - 1, owner=context)
+    round_images = comm.world * _native.MAX_INFLIGHT * (len(ctxs) if ctxs else 1)     # what one exchange can carry
+    names = None
+    for first in range(0, len(images), round_images):
+        chunk = checked[first:first + round_images]
+        lo, hi, per = block_bounds(len(chunk), comm.world, comm.rank)
+        prepared = []
+        for crop, _xo, _yo in chunk[lo:hi]:
+            names, arrays, img, masks = api._prepare(listTemplates, crop, method)
+            prepared.append((arrays, masks, img))
+        if names is None:                                   # an idle rank still needs the labels
+            names = [t[0] for t in listTemplates]
+        if batch_fn is not None:
+            hits, counts = batch_fn(prepared, method, n_dev, score_threshold, maxOverlap, per, hits_per_image)
+        else:
+            locks = [c.lock for c in ctxs]
+            for lk in locks:
+                lk.acquire()
+            try:
+                hits, counts = _device_batch(ctxs, comm, prepared, method, n_dev, score_threshold, maxOverlap, per, hits_per_image)
+            finally:
+                for lk in reversed(locks):
+                    lk.release()
+        for r in range(comm.world):
+            for i in range(per):
+                g = r * per + i                             # index inside the chunk
+                if g >= len(chunk):
+                    continue
+                cnt = int(counts[r * per + i])
+                _crop, xo, yo = chunk[g]
+                if cnt >= 0:
+                    results[first + g] = api._to_hits(hits[r * per + i, :cnt], names, xo, yo)
+    for i, r in enumerate(results):                        # did not fit the fused fast path: replicated synchronous call
+        if r is None:
+            results[i] = api.matchTemplates(listTemplates, images[i], method, N_object, score_threshold, maxOverlap, searchBox,
+                                            context=context)
     return results

@@ -111,6 +111,12 @@ class MockContext:
         raw = self.slots.pop(slot)
         return None if len(raw) > 1024 else raw
 
+    def match_templates_sharded(self, comm, tmpl_base, n_local, method, n_object, score_threshold, max_overlap):
+        """mtm_match_templates_sharded for a one-rank communicator: the slice is the whole list."""
+        self.calls.append("match_templates_sharded")
+        assert comm.world == 1 and tmpl_base == 0 and n_local == len(self.templates)
+        return self.match_templates(method, n_object, score_threshold, max_overlap)
+
     def nms(self, hits, score_threshold, sort_ascending, n_object, max_overlap):
         self.calls.append("nms")
         listed = [(k, (int(r["x"]), int(r["y"]), int(r["w"]), int(r["h"])), r["score"]) for k, r in enumerate(hits)]
@@ -126,3 +132,31 @@ class MockContext:
         if n != mtm_port.INF:
             keep = keep[:n]
         return np.asarray(keep, np.int32)
+
+
+class MockComm:
+    """TEST DOUBLE of ``mtm_b200._native.Comm`` for a single rank (world 1): mtm_gather_results reduces to handing the
+    local slots over in the gather layout."""
+
+    def __init__(self, world=1, rank=0, device=0):
+        self.world, self.rank, self.device = world, rank, device
+
+    @classmethod
+    def init_rank(cls, device, world, rank, unique_id=None):
+        assert world == 1
+        return cls(1, 0, device)
+
+    def close(self):
+        pass
+
+    def gather_results(self, entries, images_per_rank, hits_per_image):
+        hits = np.zeros((images_per_rank, hits_per_image), HIT_DTYPE)
+        counts = np.full(images_per_rank, -1, np.int32)
+        for i, (ctx, slot) in enumerate(entries):
+            raw = ctx.slots.pop(slot)
+            if len(raw) > hits_per_image:
+                counts[i] = -2
+            else:
+                counts[i] = len(raw)
+                hits[i, :len(raw)] = raw
+        return hits, counts

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol(mtm):
     for name in declared:
         assert hasattr(lib, name), "libmtm_b200.so lacks %s" % name
     assert sorted(_native.exported_symbols()) == declared            # the binding covers the whole header
-    assert lib.mtm_abi_version() == 1
+    assert lib.mtm_abi_version() == 2
     assert ctypes.sizeof(ctypes.c_int32) * 5 + 4 == _native.HIT_DTYPE.itemsize
 
 

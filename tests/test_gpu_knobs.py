@@ -1,10 +1,9 @@
-"""-m gpu, opt-in (MTM_B200_TEST_KNOBS=1): parity of the experiment knobs of the library.
+"""-m gpu: parity of the experiment knobs of the library (every alternative kernel of the shipped .so runs on the GPU).
 
 Every knob (environment variable read once per process, see TcEnv in csrc/ncc_tc.cu, ncc_points.cu and box_moments.cu) selects an
 alternative kernel or launch plan that must produce the same results as the default; they exist so that the
 measurements under profiles/ can be repeated and so that a variant can be validated before it becomes the default.
-Each case runs a small parity script in a subprocess with the variable set.  Skipped unless MTM_B200_TEST_KNOBS=1:
-variants that have not been measured yet (MTM_B200_MOM_ROWS, MTM_B200_MOM_BOX) must not gate the default suite.
+Each case runs a small parity script in a subprocess with the variable set (about 3 s per case).
 """
 import os
 import subprocess
@@ -52,11 +51,11 @@ assert np.max(np.abs(MTM.computeScoreMap(big, scene) - ncc_exact.match_template_
 print("knob parity ok")
 """
 
-KNOBS = [{"MTM_B200_MOM_BOX": "1"}, {"MTM_B200_MOM_ROWS": "1"}, {"MTM_B200_MOM_CS": "1"}, {"MTM_B200_NO_POINTS": "1"}, {"MTM_B200_NO_CAND": "1"},
-         {"MTM_B200_PERSIST": "0"}, {"MTM_B200_EW": "12"}, {"MTM_B200_EW": "8"}, {}]
+# MTM_B200_MOM_BOX=0: the summed-area moment route (the default until round 2; box sums are the default now)
+KNOBS = [{"MTM_B200_MOM_BOX": "0"}, {"MTM_B200_MOM_BOX": "0", "MTM_B200_MOM_ROWS": "1"}, {"MTM_B200_MOM_BOX": "0", "MTM_B200_MOM_CS": "1"},
+         {"MTM_B200_NO_POINTS": "1"}, {"MTM_B200_NO_CAND": "1"}, {"MTM_B200_PERSIST": "0"}, {"MTM_B200_EW": "12"}, {"MTM_B200_EW": "8"}, {}]
 
 
-@pytest.mark.skipif(os.environ.get("MTM_B200_TEST_KNOBS") != "1", reason="opt-in: set MTM_B200_TEST_KNOBS=1")
 @pytest.mark.parametrize("knob", KNOBS, ids=lambda k: ",".join("%s=%s" % kv for kv in k.items()) or "default")
 def test_knob_keeps_parity(knob):
     env = dict(os.environ)

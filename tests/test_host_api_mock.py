@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import test_gpu_parity as gp
-from mock_device import MockContext
+from mock_device import MockComm, MockContext
 
 
 @pytest.fixture()
@@ -15,8 +15,9 @@ def mock_mtm(mtm, monkeypatch):
     shared = MockContext()
     helpers = [MockContext() for _ in range(4)]
     monkeypatch.setattr(_native, "Context", MockContext)
+    monkeypatch.setattr(_native, "Comm", MockComm)
     monkeypatch.setattr(_native, "default_context", lambda device=None: shared)
-    monkeypatch.setattr(_native, "helper_contexts", lambda device, n: helpers[:n])
+    monkeypatch.setattr(_native, "helper_contexts", lambda device, n, owner=None: helpers[:n])
     return mtm
 
 
@@ -77,7 +78,6 @@ def test_sharded_entry_points_without_a_process_group(mock_mtm):
     """world size 1: the sharded wrappers reduce to the plain calls (bodies of tests/test_gpu_sharded.py)."""
     import test_gpu_sharded as gs
     gs.test_sharded_world1_equals_match_templates(mock_mtm)
-    gs.test_batch_sharded_world1_equals_per_image_calls(mock_mtm)
 
 
 class _FakeDeviceArray:

@@ -15,7 +15,7 @@ def mock_mtm(mtm, monkeypatch):
     monkeypatch.setattr(_native, "Context", MockContext)
     monkeypatch.setattr(_native, "default_context", lambda device=None: shared)
     helpers = [MockContext() for _ in range(4)]
-    monkeypatch.setattr(_native, "helper_contexts", lambda device, n: helpers[:n])
+    monkeypatch.setattr(_native, "helper_contexts", lambda device, n, owner=None: helpers[:n])
     mtm._mock_helpers = helpers
     mtm._mock = shared
     return mtm

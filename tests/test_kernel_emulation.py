@@ -176,11 +176,11 @@ extern "C" int emu_postprocess(const TmplMeta* meta, int nt, const float* maps, 
         if (do_nms) {
             memset(countB, 0, MTM_HIT_HEADER);
             const long long no = n_object; const float mo = (float)max_overlap;
-            if (presorted) emu_launch_coop(dim3(1), dim3(256), [&] { finalize_small_kernel<true, true>(hitsA, cap, countA, meta, nontrivial, minimize, check_trivial, hitsB, countB, thr_nms, ascending, no, mo, mirror); });
-            else emu_launch_coop(dim3(1), dim3(256), [&] { finalize_small_kernel<false, true>(hitsA, cap, countA, meta, nontrivial, minimize, check_trivial, hitsB, countB, thr_nms, ascending, no, mo, mirror); });
+            if (presorted) emu_launch_coop(dim3(1), dim3(256), [&] { finalize_small_kernel<true, true>(hitsA, cap, countA, meta, nontrivial, minimize, check_trivial, hitsB, countB, thr_nms, ascending, no, mo, mirror, 0); });
+            else emu_launch_coop(dim3(1), dim3(256), [&] { finalize_small_kernel<false, true>(hitsA, cap, countA, meta, nontrivial, minimize, check_trivial, hitsB, countB, thr_nms, ascending, no, mo, mirror, 0); });
             declined = countB[2];
         } else if (n_object != 1) {
-            emu_launch_coop(dim3(1), dim3(256), [&] { finalize_small_kernel<false, false>(hitsA, cap, countA, meta, nontrivial, minimize, 1, hitsB, countB, 0.f, 0, -1ll, 0.f, mirror); });
+            emu_launch_coop(dim3(1), dim3(256), [&] { finalize_small_kernel<false, false>(hitsA, cap, countA, meta, nontrivial, minimize, 1, hitsB, countB, 0.f, 0, -1ll, 0.f, mirror, 0); });
             declined = countA[2];
         }
     }
@@ -189,8 +189,8 @@ extern "C" int emu_postprocess(const TmplMeta* meta, int nt, const float* maps, 
         *route = 1;
         if (countA[0] > cap) return -1;                         // the library grows the hit blocks and starts over
         if (n_object != 1) {
-            emu_launch_coop(dim3(1), dim3(1024), [&] { sort_hits_kernel(hitsA, cap, countA, meta, nontrivial, 0, minimize, 0, 1); });
-            if (do_nms) emu_launch_coop(dim3(1), dim3(1024), [&] { sort_hits_kernel(hitsA, cap, countA, meta, nontrivial, 1, minimize, ascending, 0); });
+            emu_launch_coop(dim3(1), dim3(1024), [&] { sort_hits_kernel(hitsA, cap, countA, meta, nontrivial, 0, minimize, 0, 1, 0); });
+            if (do_nms) emu_launch_coop(dim3(1), dim3(1024), [&] { sort_hits_kernel(hitsA, cap, countA, meta, nontrivial, 1, minimize, ascending, 0, 0); });
         }
         if (do_nms) emu_launch_coop(dim3(1), dim3(1024), [&] { nms_kernel(hitsA, cap, countA, hitsB, countB, keep, thr_nms, ascending, (long long)n_object, (float)max_overlap); });
     }

@@ -1,7 +1,7 @@
 """CPU test (gloo, world_size 2) of the multi-GPU host logic: template sharding, the
 all-gather of hit rows and the replicated global NMS must reproduce the unsharded result.
-The per-rank search/NMS are injected from the oracle here (no GPU); on the GPU box the same
-code path runs with the CUDA functions (tests/test_gpu_sharded.py)."""
+The per-rank search and the exchange are injected here (oracle + gloo, no GPU); on the GPU box the same
+host code runs on the library's own exchange (tests/test_gpu_sharded.py: NCCL / in-process loop-back)."""
 import os
 import socket
 
@@ -17,6 +17,55 @@ def _free_port():
     return p
 
 
+class _GlooComm:
+    """Host-side stand-in for ``_native.Comm``: rank / world of the gloo group (no GPU here)."""
+
+    def __init__(self, dist):
+        self.world, self.rank, self.device = dist.get_world_size(), dist.get_rank(), 0
+
+
+def _doubles(dist, comm):
+    """Oracle-backed test doubles of the two device paths of mtm_b200.sharded: the per-rank search runs on the CPU port,
+    the exchange is a gloo all_gather_object, everything after it follows the library's contract (rank-ordered
+    concatenation, replicated NMS / fixed blocks of ``images_per_rank`` entries with counts -1 = unused)."""
+    from mtm_b200 import _native
+    from oracle import mtm_port
+
+    def search_fn(arrays, masks, img, lo, method, n_dev, thr, overlap):
+        n_object = float("inf") if n_dev < 0 else n_dev
+        slice_list = [(k, a) if m is None else (k, a, m) for k, (a, m) in enumerate(zip(arrays, masks))]
+        local = mtm_port.find_matches(slice_list, img, method, n_object, thr) if slice_list else []
+        rows = [(lo + k, tuple(int(v) for v in box), float(score)) for k, box, score in local]
+        gathered = [None] * comm.world
+        dist.all_gather_object(gathered, rows)
+        merged = [r for part in gathered for r in part]                 # rank order == template-list order
+        kept = mtm_port.nms(merged, thr, method == 1, n_object, overlap)
+        raw = np.zeros(len(kept), _native.HIT_DTYPE)
+        for i, (t, box, score) in enumerate(kept):
+            raw[i] = (t, box[0], box[1], box[2], box[3], score)
+        return raw
+
+    def batch_fn(prepared, method, n_dev, thr, overlap, per, hits_per_image):
+        n_object = float("inf") if n_dev < 0 else n_dev
+        mine = []
+        for arrays, masks, img in prepared:
+            temps = [(k, a) if m is None else (k, a, m) for k, (a, m) in enumerate(zip(arrays, masks))]
+            mine.append([(t, tuple(int(v) for v in box), float(sc)) for t, box, sc in
+                         mtm_port.match_templates(temps, img, method, n_object, thr, overlap)])
+        gathered = [None] * comm.world
+        dist.all_gather_object(gathered, mine)
+        hits = np.zeros((comm.world * per, hits_per_image), _native.HIT_DTYPE)
+        counts = np.full(comm.world * per, -1, np.int32)
+        for r, part in enumerate(gathered):
+            for i, lst in enumerate(part):
+                counts[r * per + i] = len(lst)
+                for k, (t, box, sc) in enumerate(lst):
+                    hits[r * per + i, k] = (t, box[0], box[1], box[2], box[3], sc)
+        return hits, counts
+
+    return search_fn, batch_fn
+
+
 def _worker(rank, world, port, out_dir):
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -27,28 +76,47 @@ def _worker(rank, world, port, out_dir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import MTM  # noqa: F401
     from mtm_b200 import sharded
-    from oracle import golden_cases as gc, mtm_port
+    from oracle import golden_cases as gc
     import pickle
+    comm = _GlooComm(dist)
+    search_fn, batch_fn = _doubles(dist, comm)
     results = {}
     for name in ("synth_mixed", "synth_rot8", "synth_mixed_n5", "synth_searchbox"):
         kind, temps, img, kw = gc.build(name)
-        got = sharded.matchTemplatesSharded(temps, img, find_fn=mtm_port.find_matches, nms_fn=mtm_port.nms, **kw)
+        got = sharded.matchTemplatesSharded(temps, img, comm=comm, search_fn=search_fn, **kw)
         results[name] = [(h[0], tuple(h[1]), float(h[2])) for h in got]
     # a rank with an empty shard (1 template, 2 ranks) and one with no hits at all
     kind, temps, img, kw = gc.build("c1_fish256_inf")
-    got = sharded.matchTemplatesSharded(temps, img, find_fn=mtm_port.find_matches, nms_fn=mtm_port.nms, **kw)
+    got = sharded.matchTemplatesSharded(temps, img, comm=comm, search_fn=search_fn, **kw)
     results["c1_fish256_inf"] = [(h[0], tuple(h[1]), float(h[2])) for h in got]
-    # the other cut (SURVEY 8e, configs[4]): images sharded, templates whole, one all-gather of the final lists
-    def batch_fn(temps, images, method, N_object, thr, overlap, box):
-        return [mtm_port.match_templates(temps, im, method, N_object, thr, overlap, box) for im in images]
+    # validation errors are raised on every rank before any collective (a rank-local raise would hang the others)
+    try:
+        sharded.matchTemplatesSharded(temps, img[:10, :10], comm=comm, search_fn=search_fn, **kw)
+        results["too_large"] = "no error"
+    except ValueError as e:
+        results["too_large"] = str(e)
+    # the other cut (SURVEY 8e, configs[4]): images in blocks over the ranks, templates whole, one all-gather of the final lists
     kind, temps, img, kw = gc.build("synth_mixed")
     images = [img, np.ascontiguousarray(img[::-1]), np.ascontiguousarray(img[:, ::-1])]
     for name, ims in (("batch3", images), ("batch1", images[:1])):          # 3 images / 2 ranks; 1 image -> rank 1 idle
-        got = sharded.matchTemplatesBatchSharded(temps, ims, batch_fn=batch_fn, **kw)
+        got = sharded.matchTemplatesBatchSharded(temps, ims, comm=comm, batch_fn=batch_fn, **kw)
         results[name] = [[(h[0], tuple(h[1]), float(h[2])) for h in hits] for hits in got]
     with open(os.path.join(out_dir, "rank%d.pkl" % rank), "wb") as f:
         pickle.dump(results, f)
     dist.destroy_process_group()
+
+
+def test_block_bounds_cover_everything():
+    import MTM  # noqa: F401
+    from mtm_b200.sharded import block_bounds
+    for n in (0, 1, 5, 16, 17):
+        for world in (1, 2, 3, 8):
+            spans = [block_bounds(n, world, r) for r in range(world)]
+            per = spans[0][2]
+            assert all(sp[2] == per for sp in spans) and per * world >= n
+            assert spans[0][0] == 0 and max(sp[1] for sp in spans) == n
+            assert all(a[1] == b[0] or b[0] == b[1] == n for a, b in zip(spans, spans[1:]))
+            assert all(sp[0] == min(n, r * per) for r, sp in enumerate(spans))
 
 
 def test_shard_bounds_cover_everything():
@@ -106,6 +174,7 @@ def test_sharded_match_templates_world2(tmp_path, golden):
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     res = [pickle.load(open(tmp_path / ("rank%d.pkl" % r), "rb")) for r in range(2)]
     assert res[0] == res[1]                                    # replicated NMS -> identical on every rank
+    assert "larger than image" in res[0].pop("too_large")
     from oracle import golden_cases as gc, mtm_port
     kind, temps, img, kw = gc.build("synth_mixed")
     images = [img, np.ascontiguousarray(img[::-1]), np.ascontiguousarray(img[:, ::-1])]
