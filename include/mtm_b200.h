@@ -79,6 +79,7 @@ typedef struct mtm_counters {
     int64_t d2h_bytes;
     int64_t ncc_launches;      /* numerator (K2/K3) kernel launches timed with MTM_OPT_TIME_NCC   */
     double ncc_ms;             /* their summed device time in ms (CUDA events on the ctx stream) */
+    int64_t tma_launches;      /* numerator launches whose image tiles went through the TMA unit (cp.async.bulk.tensor) */
 } mtm_counters;
 
 typedef struct mtm_ctx mtm_ctx;
@@ -101,6 +102,11 @@ int mtm_reset_counters(mtm_ctx* ctx);
 /* CUDA-event stopwatch on the context's stream (bench.py): begin, work, end -> ms. */
 int mtm_timer_begin(mtm_ctx* ctx);
 int mtm_timer_end(mtm_ctx* ctx, float* elapsed_ms);
+/* Measurement helper for the roofline bench.py reports: the dense rate of the tensor pipe the numerator kernels use.
+ * One CTA per SM issues `iters` back-to-back tcgen05.mma kind::i8 (u8 x u8 -> s32, M 128 x N n_cols x K 32) from
+ * operands resident in shared memory -- no loads, no epilogue; best of 5 launches timed with CUDA events.
+ * *tmacs_per_s = 1e-12 * MACs / s (x2 = TOP/s). */
+int mtm_measure_i8_peak(mtm_ctx* ctx, int n_cols, int iters, double* tmacs_per_s);
 
 /* ---- inputs ---------------------------------------------------------------
  * mtm_set_image: the `image` operand of cv2.matchTemplate (MTM/__init__.py:92)

@@ -24,7 +24,7 @@ assert HIT_DTYPE.itemsize == 24
 
 class Counters(ctypes.Structure):
     _fields_ = [("kernel_launches", ctypes.c_int64), ("h2d_bytes", ctypes.c_int64), ("d2h_bytes", ctypes.c_int64),
-                ("ncc_launches", ctypes.c_int64), ("ncc_ms", ctypes.c_double)]
+                ("ncc_launches", ctypes.c_int64), ("ncc_ms", ctypes.c_double), ("tma_launches", ctypes.c_int64)]
 
 
 # name -> (restype, argtypes); mirrors include/mtm_b200.h one to one
@@ -42,6 +42,7 @@ _SIGNATURES = {
     "mtm_reset_counters": (ctypes.c_int, [_P]),
     "mtm_timer_begin": (ctypes.c_int, [_P]),
     "mtm_timer_end": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_float)]),
+    "mtm_measure_i8_peak": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
     "mtm_set_image": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64]),
     "mtm_set_image_device": (ctypes.c_int, [_P, _P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64]),
     "mtm_set_templates": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(_P), ctypes.POINTER(ctypes.c_int32),
@@ -214,7 +215,7 @@ class Context:
         c = Counters()
         self._check(self._lib.mtm_get_counters(self._h, ctypes.byref(c)))
         return {"kernel_launches": c.kernel_launches, "h2d_bytes": c.h2d_bytes, "d2h_bytes": c.d2h_bytes,
-                "ncc_launches": c.ncc_launches, "ncc_ms": c.ncc_ms}
+                "ncc_launches": c.ncc_launches, "ncc_ms": c.ncc_ms, "tma_launches": c.tma_launches}
 
     def set_time_ncc(self, on):
         self._check(self._lib.mtm_set_option(self._h, OPT_TIME_NCC, 1 if on else 0))
@@ -229,6 +230,12 @@ class Context:
         ms = ctypes.c_float()
         self._check(self._lib.mtm_timer_end(self._h, ctypes.byref(ms)))
         return float(ms.value)
+
+    def measure_i8_peak(self, n_cols=256, iters=4000):
+        """Dense u8 x u8 MAC rate of the tensor pipe in TMAC/s (mtm_measure_i8_peak)."""
+        out = ctypes.c_double()
+        self._check(self._lib.mtm_measure_i8_peak(self._h, int(n_cols), int(iters), ctypes.byref(out)))
+        return float(out.value)
 
     # -- inputs -----------------------------------------------------------------
     @staticmethod

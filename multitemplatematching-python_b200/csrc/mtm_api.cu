@@ -232,6 +232,26 @@ int mtm_reset_counters(mtm_ctx* ctx)
     return MTM_OK;
 }
 
+int mtm_measure_i8_peak(mtm_ctx* ctx, int n_cols, int iters, double* tmacs_per_s)
+{
+    MTM_ENTER(ctx);
+    if (!tmacs_per_s || n_cols < 16 || n_cols > 256 || n_cols % 16 || iters < 1)
+        return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_measure_i8_peak: N in 16..256 (multiple of 16), iters >= 1");
+    MTM_TRY(launch_i8_peak(ctx, n_cols, 64));                  // warm-up: module load, clocks
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        MTM_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+        MTM_TRY(launch_i8_peak(ctx, n_cols, iters));
+        MTM_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        MTM_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+        float ms = 0.f;
+        MTM_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        best = std::min(best, ms);
+    }
+    *tmacs_per_s = (double)ctx->sm_count * iters * 128.0 * n_cols * 32.0 / (best * 1e-3) / 1e12;
+    return MTM_OK;
+}
+
 int mtm_timer_begin(mtm_ctx* ctx)
 {
     MTM_ENTER(ctx);

@@ -254,6 +254,7 @@ bool box_moments_enabled();
 bool box_moments_applicable(const mtm_ctx* ctx);
 int launch_box_moments(mtm_ctx* ctx);
 int launch_ncc_tc(mtm_ctx* ctx, const TcGroup& g, int method);
+int launch_i8_peak(mtm_ctx* ctx, int n, int iters);      // measurement helper: back-to-back kind::i8 MMAs, no loads, no epilogue
 // 16-bit path: one byte-plane product of the group accumulated into ctx->d_acc (img_plane / tmpl_plane: 0 = high, 1 = low bytes)
 int launch_ncc_tc_accum(mtm_ctx* ctx, const TcGroup& g, int img_plane, int tmpl_plane, double weight, bool first);
 int launch_u16_split_image(mtm_ctx* ctx, const uint16_t* src, int64_t src_stride_bytes);

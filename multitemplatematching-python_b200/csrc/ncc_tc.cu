@@ -27,9 +27,13 @@
 // Roofline: tensor pipe (kind::i8, 8192 MAC/clk/SM); useful fraction w / (32*nk).
 #include "mtm_internal.cuh"
 #include "ncc_epilogue.cuh"
+#if defined(__CUDACC__)
+#include <cuda.h>          // CUtensorMap + the encoder's prototype; cuTensorMapEncodeTiled itself is resolved at run time (no libcuda link)
+#endif
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 namespace {
@@ -79,6 +83,36 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// TMA: one box (16 bytes x box rows) of the image tensor map -> shared memory, completion on an mbarrier (bytes of the whole
+// box, zero-filled parts included).  `tmap` points at a __grid_constant__ kernel parameter.
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* tmap, int x, int y, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+// Tensor map of the padded u8 image (tile layout of mtm_set_image): dim0 = bytes of a row (pitch), dim1 = rows; box = 16 bytes x
+// `box_rows` rows, no swizzle, out-of-bounds elements read as zero (rows below the image, bytes beyond the pitch).
+static bool encode_tile_map(CUtensorMap* out, const uint8_t* base, int64_t pitch, int H, int box_rows)
+{
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static const EncodeFn encode = [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) fn = nullptr;
+        (void)cudaGetLastError();
+        return reinterpret_cast<EncodeFn>(fn);
+    }();
+    if (!encode || box_rows < 1 || box_rows > 256 || (pitch & 15) || (reinterpret_cast<uintptr_t>(base) & 15)) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)pitch, (cuuint64_t)H};
+    const cuuint64_t strides[1] = {(cuuint64_t)pitch};
+    const cuuint32_t box[2] = {16u, (cuuint32_t)box_rows};
+    const cuuint32_t elem_strides[2] = {1u, 1u};
+    return encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(base), dims, strides, box, elem_strides,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols)
 {
@@ -314,6 +348,20 @@ __device__ __forceinline__ void stage_image_tile(uint8_t* __restrict__ tile, con
     }
 }
 
+// The same tile through the TMA unit: per 16-byte k-block, `chunks` boxes of `rc` rows (a box holds at most 256 rows; the last
+// box is moved up so that it ends with the tile -- overlapping rows are written twice with the same bytes).  R and rc are
+// multiples of 8: every destination is 128-byte aligned.  Issued by ONE thread after mbar_expect_tx(bar, tma_tile_bytes(..)).
+__device__ __forceinline__ uint32_t tma_tile_bytes(int kb, int rc, int chunks) { return (uint32_t)(kb * chunks * rc * 16); }
+__device__ __forceinline__ void tma_stage_tile(uint8_t* tile, const CUtensorMap* tmap, int xb, int y0, int R, int kb, int rc, int chunks,
+                                               uint64_t* bar)
+{
+    for (int c = 0; c < kb; ++c)
+        for (int j = 0; j < chunks; ++j) {
+            const int r0 = min(j * rc, R - rc);
+            tma_load_2d(tile + ((size_t)c * R + r0) * 16, tmap, xb + 16 * c, y0 + r0, bar);
+        }
+}
+
 struct TcParams {
     const uint8_t* img; int64_t pitch; int H, W;
     const uint8_t* slabs;             // this group's Toeplitz slabs: h slabs of slab_bytes
@@ -323,7 +371,8 @@ struct TcParams {
     int ds;                           // slabs (dy values) per ring stage
     int mode;                         // 0 = A (8 templates x 16 x), 1 = B (1 template x 128 x)
     int N;                            // output rows per tile == MMA N == TMEM columns used
-    int R;                            // image tile rows = N + h - 1
+    int R;                            // image tile rows = N + h - 1 rounded up to 8 (tc_tile_rows)
+    int tma, tma_rc, tma_chunks;      // image tiles through the TMA unit (tensor map = second kernel parameter): rows per box, boxes per k-block
     int h, w, mh, mw;
     const TmplMeta* meta; const int32_t* order; int count;
     const uint32_t* S; const float* rsD;   // window moments of this (h, w): [mh][mw]
@@ -409,7 +458,7 @@ __device__ __forceinline__ void epilogue_prefetch_first(const TcParams& p, int x
 // One CTA = one output tile.  Warp 0: slab producer, warp 1: MMA issuer, then all 8 warps: epilogue.
 template <int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 2)
-ncc_tc_kernel(const TcParams p)
+ncc_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -422,7 +471,8 @@ ncc_tc_kernel(const TcParams p)
     uint64_t* full = bars;                                     // [TC_STAGES]
     uint64_t* empty = bars + TC_STAGES;                        // [TC_STAGES]
     uint64_t* accum = bars + 2 * TC_STAGES;                    // [1]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
+    uint64_t* tile_bar = accum + 1;                            // [1] image tile landed (TMA)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 2);
 
     const int xw = p.mode == 0 ? 16 : 128;
     const int x0 = blockIdx.x * xw, y0 = blockIdx.y * p.N;
@@ -432,13 +482,23 @@ ncc_tc_kernel(const TcParams p)
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(accum, 1);
+        mbar_init(tile_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
 
     // ---- stage the image tile: rows [y0, y0+R) x bytes [x0, x0 + 32*nk), layout [k-block][row][16 B]
-    stage_image_tile<TC_THREADS>(tile, p.img, p.pitch, p.H, x0 * p.C, y0, p.R, kb_img, tid);
-    fence_async_smem();                                        // generic-proxy writes -> visible to the MMA (async proxy)
+    if (p.tma) {                                               // TMA unit: one thread issues the boxes, everybody waits for the bytes
+        __syncthreads();                                       // tile_bar initialised
+        if (tid == 0) {
+            mbar_expect_tx(tile_bar, tma_tile_bytes(kb_img, p.tma_rc, p.tma_chunks));
+            tma_stage_tile(tile, &tmap, x0 * p.C, y0, p.R, kb_img, p.tma_rc, p.tma_chunks, tile_bar);
+        }
+        mbar_wait(tile_bar, 0);
+    } else {
+        stage_image_tile<TC_THREADS>(tile, p.img, p.pitch, p.H, x0 * p.C, y0, p.R, kb_img, tid);
+        fence_async_smem();                                    // generic-proxy writes -> visible to the MMA (async proxy)
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -556,7 +616,7 @@ __device__ __forceinline__ void issue_rows_any(int nk, uint32_t tmem_d, uint32_t
 
 template <bool PROF, int EW, int MODE>
 __global__ void __launch_bounds__(512, 1)   // 128 registers; with EW = 8 (384 threads) a quarter of the register file stays free for other streams' small kernels
-ncc_tc_persist_kernel(const TcParams p)
+ncc_tc_persist_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap)
 {
     constexpr int TCP_THREADS = 32 * (EW + 4);
     constexpr int TCP_EPI_THREADS = 32 * EW;
@@ -585,15 +645,16 @@ ncc_tc_persist_kernel(const TcParams p)
     if (tid == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(&tile_full[b], TCP_STAGERS); mbar_init(&tile_empty[b], 1);
+            mbar_init(&tile_full[b], p.tma ? 1 : TCP_STAGERS); mbar_init(&tile_empty[b], 1);
             mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], TCP_EPI_THREADS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == EW) tmem_alloc(tmem_slot, tmem_cols);
-    // the first image tile is staged by the whole CTA (nothing else to do yet); the stagers take over from the second
-    stage_image_tile<TCP_THREADS>(tiles, p.img, p.pitch, p.H, ((int)blockIdx.x % p.tiles_x) * xw * p.C, ((int)blockIdx.x / p.tiles_x) * p.N,
-                                  p.R, kb_img, tid);
+    // register staging (p.tma == 0): the first image tile is staged by the whole CTA (nothing else to do yet); the stagers
+    // take over from the second.  With the TMA unit the loader warp issues every tile, the first one included.
+    if (!p.tma) stage_image_tile<TCP_THREADS>(tiles, p.img, p.pitch, p.H, ((int)blockIdx.x % p.tiles_x) * xw * p.C, ((int)blockIdx.x / p.tiles_x) * p.N,
+                                              p.R, kb_img, tid);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -673,8 +734,24 @@ ncc_tc_persist_kernel(const TcParams p)
             q[0] = w_tile; q[1] = w_acc; q[2] = w_full; q[3] = clock64() - m_begin;
         }
         __syncwarp();
+    } else if (warp >= EW + 2 && p.tma) {
+        // ===== image tile loader: one warp, one elected lane per tile feeds the TMA unit (launched with EW + 3 warps)
+        if (warp == EW + 2) {
+            const uint32_t bytes = tma_tile_bytes(kb_img, p.tma_rc, p.tma_chunks);
+            for (int i = 0; i < my_tiles; ++i) {
+                const int b = i & 1, u = i >> 1;
+                const int ti = (int)blockIdx.x + i * (int)gridDim.x;
+                const int x0 = (ti % p.tiles_x) * xw, y0 = (ti / p.tiles_x) * p.N;
+                mbar_wait(&tile_empty[b], (u & 1) ^ 1);        // fresh barrier: parity 1 passes
+                if (elect_one()) {
+                    mbar_expect_tx(&tile_full[b], bytes);
+                    tma_stage_tile(tiles + (size_t)b * tile_bytes, &tmap, x0 * p.C, y0, p.R, kb_img, p.tma_rc, p.tma_chunks, &tile_full[b]);
+                }
+                __syncwarp();
+            }
+        }
     } else if (warp >= EW + 2) {
-        // ===== image tile stagers =====
+        // ===== image tile stagers (register staging) =====
         const int t = tid - 32 * (EW + 2);
         long long w_te = 0, w_work = 0;
         for (int i = 0; i < my_tiles; ++i) {
@@ -819,7 +896,50 @@ window_moments_rows_kernel(SatView sat, const uint32_t* __restrict__ sat_q32, co
     }
 }
 
+// Measurement helper (mtm_measure_i8_peak): the rate of the pipe the numerator kernels use.  One CTA per SM issues `iters`
+// back-to-back tcgen05.mma kind::i8 M128 x N x K32 from operands resident in shared memory (zeros; two accumulators in
+// turn), no loads, no epilogue: time / (grid * iters * 128 * N * 32) is the dense u8 MAC rate bench.py quotes rooflines against.
+__global__ void __launch_bounds__(128, 1)
+i8_peak_kernel(int iters, int n)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 16);
+    uint8_t* A = smem + 1024;                                   // [2 k-blocks][128 rows][16 B]
+    uint8_t* B = A + 4096;                                      // [2 k-blocks][n rows][16 B]
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < (4096 + 32 * n) / 16; i += blockDim.x) reinterpret_cast<uint4*>(A)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (tid == 0) mbar_init(bar, 1);
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (warp == 1) {
+        const uint32_t idesc = (2u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+        const uint64_t a_desc = umma_desc(smem_u32(A), 128 * 16, 128), b_desc = umma_desc(smem_u32(B), (uint32_t)n * 16, 128);
+        if (elect_one()) {
+            for (int i = 0; i < iters; ++i) umma_i8(tmem_base + (uint32_t)(i & 1) * 256u, a_desc, b_desc, idesc, i > 1);
+            umma_commit(bar);
+        }
+        __syncwarp();
+        mbar_wait(bar, 0);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
 }  // namespace
+
+int launch_i8_peak(mtm_ctx* ctx, int n, int iters)
+{
+    const size_t smem_bytes = 1024 + 4096 + (size_t)32 * n;
+    i8_peak_kernel<<<ctx->sm_count, 128, smem_bytes, ctx->stream>>>(iters, n);
+    MTM_LAUNCH_CHECK(ctx);
+    return MTM_OK;
+}
 
 // ------------------------------------------------------------------------------ host side
 // Experiment knobs (environment, read once).  None of them is needed in production; they exist so that the
@@ -828,7 +948,7 @@ window_moments_rows_kernel(SatView sat, const uint32_t* __restrict__ sat_q32, co
 struct TcEnv {
     int force_n = 0, ds = 0, ew = 0, pdbg = 0, mom_cs = -1;
     size_t smem_soft = 0;
-    bool persist_off = false, prof = false, mom_rows = false;
+    bool persist_off = false, prof = false, mom_rows = false, tma_off = false;
     TcEnv()
     {
         auto num = [](const char* name) { const char* v = getenv(name); return v ? atoi(v) : 0; };
@@ -841,6 +961,7 @@ struct TcEnv {
         prof = getenv("MTM_B200_PROF") != nullptr;
         mom_cs = getenv("MTM_B200_MOM_CS") ? num("MTM_B200_MOM_CS") : -1;
         mom_rows = num("MTM_B200_MOM_ROWS") != 0;
+        tma_off = getenv("MTM_B200_TMA") && num("MTM_B200_TMA") == 0;
     }
 };
 static const TcEnv& tc_env()
@@ -848,6 +969,10 @@ static const TcEnv& tc_env()
     static const TcEnv e;
     return e;
 }
+
+// Rows of an image tile that yields n output rows of an h-row template, rounded up to 8 so that every k-block of the
+// [k-block][row][16 B] layout starts on a 128-byte boundary (TMA destinations).
+static inline int tc_tile_rows(int n, int h) { return (n + h - 1 + 7) & ~7; }
 
 bool tc_path_supported(const mtm_ctx* ctx, int method, int h, int w)
 {
@@ -875,12 +1000,12 @@ bool tc_plan_group(int mode, int h, int w, int C, TcGroup& g)
     for (int pass = 0; pass < 2 && !g.N; ++pass) {
         const size_t budget = pass == 0 ? 110 * 1024 : 224 * 1024;       // first try 2 CTAs per SM
         for (int n : candidates) {
-            const size_t tile = ((size_t)2 * g.nk * (n + h - 1) * 16 + 127) & ~(size_t)127;
-            if (tile + ring + 256 <= budget && (n + h - 1) * 16 < (1 << 18)) { g.N = n; break; }
+            const size_t tile = ((size_t)2 * g.nk * tc_tile_rows(n, h) * 16 + 127) & ~(size_t)127;
+            if (tile + ring + 256 <= budget && tc_tile_rows(n, h) * 16 < (1 << 18)) { g.N = n; break; }
         }
     }
     if (!g.N) return false;
-    g.R = g.N + h - 1;
+    g.R = tc_tile_rows(g.N, h);
     g.smem = (((size_t)2 * g.nk * g.R * 16 + 127) & ~(size_t)127) + ring + 256;
     g.eff = (double)w * C / (32.0 * g.nk);
     return true;
@@ -959,6 +1084,16 @@ static int launch_ncc_tc_impl(mtm_ctx* ctx, const TcGroup& g, int method, const 
     p.S = ctx->d_wS; p.rsD = ctx->d_wR; p.maps = ctx->d_maps;
     p.C = im.C; p.mom_plane = ctx->moments_total;
     if (ctx->cand_on && kmode == 0) { p.cand = ctx->d_cand; p.cand_count = ctx->d_cand_count; p.cand_cap = MTM_CAND_CAP; p.cand_thr = ctx->cand_thr; }
+    // Image tiles through the TMA unit (default; MTM_B200_TMA=0 or a failing encoder: register staging by the stager warps).
+    // Called once p.R is final: a box holds at most 256 rows.
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof tmap);
+    auto plan_tma = [&]() {
+        p.tma_chunks = (p.R + 255) / 256;
+        p.tma_rc = ((p.R + p.tma_chunks - 1) / p.tma_chunks + 7) & ~7;
+        p.tma = (!tc_env().tma_off && encode_tile_map(&tmap, p.img, p.pitch, p.H, p.tma_rc)) ? 1 : 0;
+        if (p.tma) ctx->ctr.tma_launches++;
+    };
 
     // ---- persistent pipeline (two image tiles + slab ring in shared memory, two accumulators in TMEM)
     if (!tc_env().persist_off) {
@@ -977,7 +1112,7 @@ static int launch_ncc_tc_impl(mtm_ctx* ctx, const TcGroup& g, int method, const 
         const int force_ew = tc_env().ew;
         for (int n = 256; n >= 32; n -= 16) {
             if (force_n && n != force_n) continue;
-            const size_t tile_b = ((size_t)2 * g.nk * (n + g.h - 1) * 16 + 127) & ~(size_t)127;
+            const size_t tile_b = ((size_t)2 * g.nk * tc_tile_rows(n, g.h) * 16 + 127) & ~(size_t)127;
             if (256 + 2 * tile_b + 3 * stage_b > 227 * 1024) continue;
             // Ring depth: as deep as shared memory allows, but when 4 stages fit under TCP_SMEM_SOFT the rest is left
             // to the small kernels of other streams (the sort/NMS kernel needs 35 KB) so that they can run beside this one.
@@ -996,9 +1131,10 @@ static int launch_ncc_tc_impl(mtm_ctx* ctx, const TcGroup& g, int method, const 
             }
         }
         if (bestN) {
-            const size_t tile_b = ((size_t)2 * g.nk * (bestN + g.h - 1) * 16 + 127) & ~(size_t)127;
-            p.N = bestN; p.R = bestN + g.h - 1; p.stages = best_stages; p.ds = ds_p;
+            const size_t tile_b = ((size_t)2 * g.nk * tc_tile_rows(bestN, g.h) * 16 + 127) & ~(size_t)127;
+            p.N = bestN; p.R = tc_tile_rows(bestN, g.h); p.stages = best_stages; p.ds = ds_p;
             p.tiles_x = gx_p; p.tiles_total = gx_p * ((p.mh + bestN - 1) / bestN);
+            plan_tma();
             const size_t smem_bytes = 256 + 2 * tile_b + (size_t)best_stages * stage_b;
             if (!ctx->tcp_attr_set) {
                 const int big = 227 * 1024;
@@ -1024,17 +1160,17 @@ static int launch_ncc_tc_impl(mtm_ctx* ctx, const TcGroup& g, int method, const 
             p.dbg = pdbg;
             const int ew = best_ew;
             if (kmode == 2) {
-                if (ew == 12) ncc_tc_persist_kernel<false, 12, 2><<<grid_p, 32 * 16, smem_bytes, ctx->stream>>>(p);
-                else ncc_tc_persist_kernel<false, 8, 2><<<grid_p, 32 * 12, smem_bytes, ctx->stream>>>(p);
+                if (ew == 12) ncc_tc_persist_kernel<false, 12, 2><<<grid_p, 32 * (p.tma ? 15 : 16), smem_bytes, ctx->stream>>>(p, tmap);
+                else ncc_tc_persist_kernel<false, 8, 2><<<grid_p, 32 * (p.tma ? 11 : 12), smem_bytes, ctx->stream>>>(p, tmap);
             } else if (kmode == 1) {
-                if (ew == 12) ncc_tc_persist_kernel<false, 12, 1><<<grid_p, 32 * 16, smem_bytes, ctx->stream>>>(p);
-                else ncc_tc_persist_kernel<false, 8, 1><<<grid_p, 32 * 12, smem_bytes, ctx->stream>>>(p);
+                if (ew == 12) ncc_tc_persist_kernel<false, 12, 1><<<grid_p, 32 * (p.tma ? 15 : 16), smem_bytes, ctx->stream>>>(p, tmap);
+                else ncc_tc_persist_kernel<false, 8, 1><<<grid_p, 32 * (p.tma ? 11 : 12), smem_bytes, ctx->stream>>>(p, tmap);
             } else if (ew == 12) {
-                if (prof) ncc_tc_persist_kernel<true, 12, 0><<<grid_p, 32 * 16, smem_bytes, ctx->stream>>>(p);
-                else ncc_tc_persist_kernel<false, 12, 0><<<grid_p, 32 * 16, smem_bytes, ctx->stream>>>(p);
+                if (prof) ncc_tc_persist_kernel<true, 12, 0><<<grid_p, 32 * (p.tma ? 15 : 16), smem_bytes, ctx->stream>>>(p, tmap);
+                else ncc_tc_persist_kernel<false, 12, 0><<<grid_p, 32 * (p.tma ? 15 : 16), smem_bytes, ctx->stream>>>(p, tmap);
             } else {
-                if (prof) ncc_tc_persist_kernel<true, 8, 0><<<grid_p, 32 * 12, smem_bytes, ctx->stream>>>(p);
-                else ncc_tc_persist_kernel<false, 8, 0><<<grid_p, 32 * 12, smem_bytes, ctx->stream>>>(p);
+                if (prof) ncc_tc_persist_kernel<true, 8, 0><<<grid_p, 32 * (p.tma ? 11 : 12), smem_bytes, ctx->stream>>>(p, tmap);
+                else ncc_tc_persist_kernel<false, 8, 0><<<grid_p, 32 * (p.tma ? 11 : 12), smem_bytes, ctx->stream>>>(p, tmap);
             }
             MTM_LAUNCH_CHECK(ctx);
             if (prof) {
@@ -1059,7 +1195,7 @@ static int launch_ncc_tc_impl(mtm_ctx* ctx, const TcGroup& g, int method, const 
     const int xw_ = g.mode == 0 ? 16 : 128;
     const int gx = (p.mw + xw_ - 1) / xw_;
     const size_t ring = (size_t)TC_STAGES * g.ds * g.slab_bytes;
-    auto smem_for = [&](int n) { return (((size_t)2 * g.nk * (n + g.h - 1) * 16 + 127) & ~(size_t)127) + ring + 256; };
+    auto smem_for = [&](int n) { return (((size_t)2 * g.nk * tc_tile_rows(n, g.h) * 16 + 127) & ~(size_t)127) + ring + 256; };
     int bestN = g.N;
     double best_cost = 1e300;
     for (int n = g.N; n >= 32 && n >= g.N / 2; n -= 16) {
@@ -1070,7 +1206,8 @@ static int launch_ncc_tc_impl(mtm_ctx* ctx, const TcGroup& g, int method, const 
         if (cost < best_cost - 1e-9) { best_cost = cost; bestN = n; }
     }
     if (tc_env().force_n) bestN = g.N;
-    p.N = bestN; p.R = bestN + g.h - 1;
+    p.N = bestN; p.R = tc_tile_rows(bestN, g.h);
+    plan_tma();
     const size_t smem_bytes = smem_for(bestN);
     if (!ctx->tc_attr_set) {
         MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1080,9 +1217,9 @@ static int launch_ncc_tc_impl(mtm_ctx* ctx, const TcGroup& g, int method, const 
     }
     const int xw = g.mode == 0 ? 16 : 128;
     dim3 grid((p.mw + xw - 1) / xw, (p.mh + p.N - 1) / p.N);
-    if (kmode == 2) ncc_tc_kernel<2><<<grid, TC_THREADS, smem_bytes, ctx->stream>>>(p);
-    else if (kmode == 1) ncc_tc_kernel<1><<<grid, TC_THREADS, smem_bytes, ctx->stream>>>(p);
-    else ncc_tc_kernel<0><<<grid, TC_THREADS, smem_bytes, ctx->stream>>>(p);
+    if (kmode == 2) ncc_tc_kernel<2><<<grid, TC_THREADS, smem_bytes, ctx->stream>>>(p, tmap);
+    else if (kmode == 1) ncc_tc_kernel<1><<<grid, TC_THREADS, smem_bytes, ctx->stream>>>(p, tmap);
+    else ncc_tc_kernel<0><<<grid, TC_THREADS, smem_bytes, ctx->stream>>>(p, tmap);
     MTM_LAUNCH_CHECK(ctx);
     return MTM_OK;
 }

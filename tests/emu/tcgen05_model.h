@@ -87,6 +87,33 @@ static inline void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes
     emu_mbar_complete_tx(bar, bytes);
 }
 
+// ---- TMA tensor copies ---------------------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled / cp.async.bulk.tensor.2d for the one shape the library uses: a u8 image of `H` rows of `pitch`
+// bytes, box = 16 bytes x box_rows rows, no swizzle, out-of-bounds elements read as zero; the barrier receives the bytes
+// of the WHOLE box.  Destinations must be 128-byte aligned, coordinates are in elements (bytes, rows).
+struct CUtensorMap { const uint8_t* base; int64_t pitch; int H; int box_rows; };
+static long long emu_tma_boxes = 0;
+static bool encode_tile_map(CUtensorMap* out, const uint8_t* base, int64_t pitch, int H, int box_rows)
+{
+    if (getenv("EMU_NO_TMA")) return false;                  // lets a test drive the register-staging path
+    if (box_rows < 1 || box_rows > 256 || (pitch & 15) || (reinterpret_cast<uintptr_t>(base) & 15)) return false;
+    out->base = base; out->pitch = pitch; out->H = H; out->box_rows = box_rows;
+    return true;
+}
+static inline void tma_load_2d(void* dst_smem, const CUtensorMap* tmap, int x, int y, uint64_t* bar)
+{
+    if (smem_u32(dst_smem) & 127u) { fprintf(stderr, "cp.async.bulk.tensor: shared-memory destination %u is not 128-byte aligned\n", smem_u32(dst_smem)); abort(); }
+    emu_preempt_point();
+    uint8_t* d = static_cast<uint8_t*>(dst_smem);
+    for (int r = 0; r < tmap->box_rows; ++r)
+        for (int b = 0; b < 16; ++b) {
+            const int64_t gx = (int64_t)x + b, gy = (int64_t)y + r;
+            d[r * 16 + b] = (gx >= 0 && gx < tmap->pitch && gy >= 0 && gy < tmap->H) ? tmap->base[gy * tmap->pitch + gx] : (uint8_t)0;
+        }
+    emu_tma_boxes++;
+    emu_mbar_complete_tx(bar, (uint32_t)tmap->box_rows * 16u);
+}
+
 // ---- tensor memory ------------------------------------------------------------------------------------------------
 static uint32_t emu_tmem[128][512];
 static uint32_t emu_tmem_cols = 0;

@@ -54,7 +54,7 @@ def emu(tmp_path_factory):
     tcn = tcn[:a] + tcn[b:]                                                   # ... minus its PTX wrappers: tests/emu/tcgen05_model.h stands in
     for text, count, repl in (('__device__ __forceinline__ void prefetch_l1(const void* ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }', 1, ""),
                               ('asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");', 2, ""),
-                              ("extern __shared__ __align__(1024) uint8_t smem[];", 2, "uint8_t* smem = emu_dyn_smem;")):
+                              ("extern __shared__ __align__(1024) uint8_t smem[];", 3, "uint8_t* smem = emu_dyn_smem;")):
         assert tcn.count(text) == count, text
         tcn = tcn.replace(text, repl)
     assert "asm" not in tcn
@@ -276,7 +276,11 @@ extern "C" long long emu_ncc_tc(const uint8_t* img, int64_t pitch, int H, int W,
     p.meta = meta; p.order = order; p.count = count; p.S = S; p.rsD = rsD; p.maps = maps; p.C = C; p.mom_plane = mom_plane;
     if (cand) { p.cand = cand; p.cand_count = cand_count; p.cand_cap = cand_cap; p.cand_thr = cand_thr; }
     const int xw = mode == 0 ? 16 : 128, gx = (p.mw + xw - 1) / xw;
-    p.N = N; p.R = N + h - 1;
+    p.N = N; p.R = tc_tile_rows(N, h);
+    CUtensorMap tmap{};                                     // image tiles through the (modelled) TMA unit unless EMU_NO_TMA is set
+    p.tma_chunks = (p.R + 255) / 256;
+    p.tma_rc = ((p.R + p.tma_chunks - 1) / p.tma_chunks + 7) & ~7;
+    p.tma = encode_tile_map(&tmap, img, pitch, H, p.tma_rc) ? 1 : 0;
     static uint8_t smem_store[227 * 1024 + 1024];
     emu_dyn_smem = smem_store + ((1024 - (reinterpret_cast<uintptr_t>(smem_store) & 1023)) & 1023);
     memset(emu_dyn_smem, 0xCD, 227 * 1024);
@@ -287,14 +291,14 @@ extern "C" long long emu_ncc_tc(const uint8_t* img, int64_t pitch, int H, int W,
         p.ds = std::max(1, std::min(h, ds)); p.stages = stages;
         if (stages < 2 || stages > TCP_MAX_STAGES || 256 + 2 * tile_b + (size_t)stages * p.ds * g.slab_bytes > 227 * 1024) return -2;
         p.tiles_x = gx; p.tiles_total = gx * ((p.mh + N - 1) / N);
-        const dim3 grid((unsigned)std::min(p.tiles_total, ctas)), block(32 * (EW + 4));
-        if (EW == 12) { if (kmode) emu_launch_coop(grid, block, [&] { ncc_tc_persist_kernel<false, 12, 1>(p); }); else emu_launch_coop(grid, block, [&] { ncc_tc_persist_kernel<false, 12, 0>(p); }); }
-        else { if (kmode) emu_launch_coop(grid, block, [&] { ncc_tc_persist_kernel<false, 8, 1>(p); }); else emu_launch_coop(grid, block, [&] { ncc_tc_persist_kernel<false, 8, 0>(p); }); }
+        const dim3 grid((unsigned)std::min(p.tiles_total, ctas)), block(32 * (EW + (p.tma ? 3 : 4)));
+        if (EW == 12) { if (kmode) emu_launch_coop(grid, block, [&] { ncc_tc_persist_kernel<false, 12, 1>(p, tmap); }); else emu_launch_coop(grid, block, [&] { ncc_tc_persist_kernel<false, 12, 0>(p, tmap); }); }
+        else { if (kmode) emu_launch_coop(grid, block, [&] { ncc_tc_persist_kernel<false, 8, 1>(p, tmap); }); else emu_launch_coop(grid, block, [&] { ncc_tc_persist_kernel<false, 8, 0>(p, tmap); }); }
     } else {
         p.ds = g.ds;
         if (tile_b + (size_t)TC_STAGES * g.ds * g.slab_bytes + 256 > 227 * 1024) return -2;
         const dim3 grid(gx, (p.mh + N - 1) / N), block(TC_THREADS);
-        if (kmode) emu_launch_coop(grid, block, [&] { ncc_tc_kernel<1>(p); }); else emu_launch_coop(grid, block, [&] { ncc_tc_kernel<0>(p); });
+        if (kmode) emu_launch_coop(grid, block, [&] { ncc_tc_kernel<1>(p, tmap); }); else emu_launch_coop(grid, block, [&] { ncc_tc_kernel<0>(p, tmap); });
     }
     emu_dyn_smem = nullptr;
     return emu_mma_count;
@@ -410,14 +414,18 @@ extern "C" long long emu_ncc_tc16(const uint16_t* src, int H, int W, float* pixf
         p.meta = meta; p.order = order; p.count = count; p.maps = maps; p.C = 1;
         p.acc = acc; p.acc_weight = weights[k]; p.acc_first = k == 0 ? 1 : 0;
         const int xw = mode == 0 ? 16 : 128, gx = (p.mw + xw - 1) / xw;
-        p.N = N; p.R = N + h - 1; p.ds = std::max(1, std::min(h, ds)); p.stages = stages;
+        p.N = N; p.R = tc_tile_rows(N, h); p.ds = std::max(1, std::min(h, ds)); p.stages = stages;
+        CUtensorMap tmap{};
+        p.tma_chunks = (p.R + 255) / 256;
+        p.tma_rc = ((p.R + p.tma_chunks - 1) / p.tma_chunks + 7) & ~7;
+        p.tma = encode_tile_map(&tmap, p.img, pitch, H, p.tma_rc) ? 1 : 0;
         p.tiles_x = gx; p.tiles_total = gx * ((p.mh + N - 1) / N);
         const size_t tile_b = ((size_t)2 * g.nk * p.R * 16 + 127) & ~(size_t)127;
         if (256 + 2 * tile_b + (size_t)stages * p.ds * g.slab_bytes > 227 * 1024) return -2;
         emu_dyn_smem = smem_store + ((1024 - (reinterpret_cast<uintptr_t>(smem_store) & 1023)) & 1023);
         memset(emu_dyn_smem, 0xCD, 227 * 1024);
         emu_tc_reset();
-        emu_launch_coop(dim3((unsigned)std::min(p.tiles_total, ctas)), dim3(32 * 12), [&] { ncc_tc_persist_kernel<false, 8, 2>(p); });
+        emu_launch_coop(dim3((unsigned)std::min(p.tiles_total, ctas)), dim3(32 * (p.tma ? 11 : 12)), [&] { ncc_tc_persist_kernel<false, 8, 2>(p, tmap); });
         mmas += emu_mma_count;
     }
     emu_dyn_smem = nullptr;
@@ -970,6 +978,23 @@ def test_tensor_core_kernel_on_the_functional_model(emu, channels, shapes, N, op
         for k, t in enumerate(tmpls):
             want = ncc_exact.match_template_exact(image, t, method)
             assert np.array_equal(got[k].view(np.uint32), want.view(np.uint32)), (method, k)
+
+
+@pytest.mark.parametrize("opts", [dict(), dict(persist=False)])
+def test_tensor_core_kernel_register_staging_when_the_tensor_map_is_refused(emu, monkeypatch, opts):
+    """Image tiles normally arrive through the TMA unit (cp.async.bulk.tensor boxes of 16 bytes x up to 256 rows, modelled in
+    tests/emu/tcgen05_model.h: 128-byte aligned destinations, zero fill outside the image, whole-box transaction bytes).  When
+    cuTensorMapEncodeTiled is unavailable the stager warps copy the tile through registers: same maps."""
+    from oracle import ncc_exact
+    rng = np.random.default_rng(18)
+    image, tmpls = _planted(rng, 70, 90, 1, [(17, 20), (12, 9), (17, 20)])
+    with_tma, n_mma, _ = _host_tensor_maps(emu, image, tmpls, 5, 0, 32, **opts)
+    monkeypatch.setenv("EMU_NO_TMA", "1")
+    without, n_mma2, _ = _host_tensor_maps(emu, image, tmpls, 5, 0, 32, **opts)
+    assert n_mma == n_mma2
+    for k, t in enumerate(tmpls):
+        assert np.array_equal(with_tma[k].view(np.uint32), without[k].view(np.uint32))
+        assert np.max(np.abs(without[k] - ncc_exact.match_template_exact(image, t, 5))) <= 2e-6
 
 
 @pytest.mark.parametrize("N,opts", [(48, dict(ctas=2)), (32, dict(persist=False)), (64, dict(EW=12, stages=5, ds=2, ctas=4))])
