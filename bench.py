@@ -737,12 +737,13 @@ def traffic_child(names):
         pool, templates, params = build_workload(wl, 2)
         n_obj = -1 if params["N_object"] == float("inf") else int(params["N_object"])
         ctx.set_templates([t[1] for t in templates])
+        ctx.synchronize()
+        ctx.reset_counters()
         ctx.set_time_ncc(True)
         for k in range(2):
-            ctx.reset_counters()
             ctx.set_image(pool[k])
             ctx.match_templates(5, n_obj, params["score_threshold"], params["maxOverlap"])
-        plan.append((name, int(ctx.counters()["ncc_launches"])))
+        plan.append((name, int(ctx.counters()["ncc_launches"]) // 2))
         ctx.set_time_ncc(False)
     print("TRAFFIC_PLAN " + json.dumps(plan))
     return 0

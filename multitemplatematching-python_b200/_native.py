@@ -92,6 +92,25 @@ def exported_symbols():
     return sorted(_SIGNATURES)
 
 
+def _prefer_bundled_nccl():
+    """libmtm_b200.so resolves libnccl.so.2 with dlopen when a multi-GPU communicator is first made.  A process that also
+    imports PyTorch must end up with ONE NCCL: torch links the copy bundled in the ``nvidia.nccl`` wheel, so when that wheel
+    is installed (and MTM_B200_NCCL_LIB is not set) the library is pointed at the same file -- whichever of the two loads
+    first, the other finds it.  Without the wheel the system libnccl.so.2 is used."""
+    if "MTM_B200_NCCL_LIB" in os.environ:
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for base in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["MTM_B200_NCCL_LIB"] = cand
+                return
+    except Exception:
+        pass
+
+
 def load():
     """dlopen libmtm_b200.so and declare every entry point (no GPU needed for this)."""
     global _lib
@@ -101,6 +120,7 @@ def load():
                 raise RuntimeError(
                     "libmtm_b200.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'` "
                     "or `python multitemplatematching-python_b200/build.py`. There is no CPU fallback." % LIB_PATH)
+            _prefer_bundled_nccl()
             lib = ctypes.CDLL(LIB_PATH)
             for name, (res, args) in _SIGNATURES.items():
                 fn = getattr(lib, name)      # AttributeError if the library lacks a declared symbol

@@ -183,6 +183,7 @@ int mtm_destroy(mtm_ctx* ctx)
     cudaFree(ctx->d_slabs); cudaFree(ctx->d_wS); cudaFree(ctx->d_wR); cudaFree(ctx->d_sizes);
     for (int k = 0; k < MTM_MAX_INFLIGHT; ++k) { cudaFree(ctx->d_slot[k]); cudaFreeHost(ctx->h_slot[k]); if (ctx->ev_slot[k]) cudaEventDestroy(ctx->ev_slot[k]); }
     cudaFreeHost(ctx->h_tmpl_stage); cudaFreeHost(ctx->h_stage); cudaFreeHost(ctx->h_geom); cudaFreeHost(ctx->h_mirror);
+    for (int k = 0; k < MTM_STAGE_BUFS; ++k) { cudaFreeHost(ctx->h_chunk[k]); if (ctx->ev_chunk[k]) cudaEventDestroy(ctx->ev_chunk[k]); }
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (int k = 0; k < MTM_NCC_RING; ++k)
@@ -318,15 +319,17 @@ static int set_image_impl(mtm_ctx* ctx, const void* pixels, int H, int W, int C,
             int64_t src_stride = row_stride;
             if (!on_device) {
                 MTM_TRY(mtm_reserve(ctx, ctx->d_raw16, ctx->raw16_cap, (size_t)H * W + 8));
-                MTM_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_raw16, (size_t)W * 2, pixels, (size_t)row_stride, (size_t)W * 2, (size_t)H,
-                                                cudaMemcpyHostToDevice, ctx->stream));
+                MTM_TRY(mtm_upload_rows(ctx, ctx->d_raw16, (size_t)W * 2, pixels, (size_t)row_stride, (size_t)W * 2, H));
                 ctx->ctr.h2d_bytes += (int64_t)H * W * 2;
                 src16 = ctx->d_raw16; src_stride = (int64_t)W * 2;
             }
             MTM_TRY(launch_u16_split_image(ctx, src16, src_stride));
         } else {
-            MTM_CUDA(ctx, cudaMemcpy2DAsync(im.pixf, (size_t)im.pitch_e * 4, pixels, (size_t)row_stride, (size_t)W * C * 4, (size_t)H,
-                                            on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+            if (on_device)
+                MTM_CUDA(ctx, cudaMemcpy2DAsync(im.pixf, (size_t)im.pitch_e * 4, pixels, (size_t)row_stride, (size_t)W * C * 4, (size_t)H,
+                                                cudaMemcpyDeviceToDevice, ctx->stream));
+            else
+                MTM_TRY(mtm_upload_rows(ctx, im.pixf, (size_t)im.pitch_e * 4, pixels, (size_t)row_stride, (size_t)W * C * 4, H));
             if (!on_device) ctx->ctr.h2d_bytes += (int64_t)H * W * C * 4;
         }
         ctx->img_u16 = u16;
@@ -350,8 +353,11 @@ static int set_image_impl(mtm_ctx* ctx, const void* pixels, int H, int W, int C,
     im.pitch = pitch; im.H = H; im.W = W; im.C = C;
     im.sat_pitch = ((int64_t)W + 1 + 3) / 4 * 4;
     g_marks.mark(ctx, "begin");
-    MTM_CUDA(ctx, cudaMemcpy2DAsync(im.pix, (size_t)pitch, pixels, (size_t)row_stride, (size_t)W * C, (size_t)H,
-                                    on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+    if (on_device)
+        MTM_CUDA(ctx, cudaMemcpy2DAsync(im.pix, (size_t)pitch, pixels, (size_t)row_stride, (size_t)W * C, (size_t)H,
+                                        cudaMemcpyDeviceToDevice, ctx->stream));
+    else
+        MTM_TRY(mtm_upload_rows(ctx, im.pix, (size_t)pitch, pixels, (size_t)row_stride, (size_t)W * C, H));      // pageable sources: staged through pinned chunks
     g_marks.mark(ctx, "copy_image");
     if (!on_device) ctx->ctr.h2d_bytes += (int64_t)H * W * C;
     MTM_TRY(mtm_reserve(ctx, im.sat_s, ctx->sat_s_cap, (size_t)C * (H + 1) * im.sat_pitch));
@@ -990,8 +996,7 @@ int mtm_set_image_scaled(mtm_ctx* ctx, const void* pixels, int H, int W, int C, 
     if (row_stride_bytes < row) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_set_image_scaled: row stride %lld < %lld", (long long)row_stride_bytes, (long long)row);
     ctx->full_dtype = -1;                                        // invalid until the upload below is queued
     MTM_TRY(mtm_reserve(ctx, ctx->d_full, ctx->full_cap, (size_t)(row * H + 64)));
-    MTM_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_full, (size_t)row, pixels, (size_t)row_stride_bytes, (size_t)row, (size_t)H,
-                                    cudaMemcpyHostToDevice, ctx->stream));
+    MTM_TRY(mtm_upload_rows(ctx, ctx->d_full, (size_t)row, pixels, (size_t)row_stride_bytes, (size_t)row, H));
     ctx->ctr.h2d_bytes += row * H;
     ctx->full_H = H; ctx->full_W = W; ctx->full_C = C; ctx->full_dtype = dtype;
     if (f == 1) return set_image_impl(ctx, ctx->d_full, H, W, C, dtype, row, true);

@@ -51,7 +51,7 @@ const NcclApi& nccl_api()
         const char* names[3] = {override_path, "libnccl.so.2", "libnccl.so"};
         for (const char* nm : names) {
             if (!nm || !*nm) continue;
-            a.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            a.handle = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
             if (a.handle) break;
             a.err = dlerror();
         }

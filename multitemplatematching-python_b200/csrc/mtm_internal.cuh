@@ -11,6 +11,7 @@
 #define MTM_NCC_RING 16
 #define MTM_CAND_CAP 32768      // above-threshold pixels the tensor-core epilogue may list per call
 #define MTM_SLOT_HITS 1024      // hits a slot of the asynchronous API can return (== the fused fast path)
+#define MTM_STAGE_BUFS 4        // pinned chunks of the pageable-upload pipeline (host_staging.cu)
 #define MTM_HIT_HEADER 32      // bytes: int32 count[8]; count[0] = number of hits (may exceed capacity)
 
 // Device-side record of one hit (32 bytes); the public mtm_hit is its 24-byte prefix.
@@ -184,6 +185,12 @@ struct mtm_ctx {
     bool cand_valid = false;             // the list belongs to the resident score maps
     float cand_thr = 0.f;
 
+    // pageable-upload pipeline (host_staging.cu): pinned chunks + the event of each chunk's last DMA
+    uint8_t* h_chunk[MTM_STAGE_BUFS] = {};
+    cudaEvent_t ev_chunk[MTM_STAGE_BUFS] = {};
+    bool chunk_used[MTM_STAGE_BUFS] = {};
+    int chunk_next = 0;
+
     // asynchronous submissions (mtm_match_templates_async / _collect): per-slot result blocks
     uint8_t* d_slot[MTM_MAX_INFLIGHT] = {};        // header + DevHit[MTM_SLOT_HITS]
     uint8_t* h_slot[MTM_MAX_INFLIGHT] = {};        // pinned mirrors
@@ -217,6 +224,9 @@ int mtm_fail(mtm_ctx* ctx, int code, const char* fmt, ...);
 
 template <typename T>
 int mtm_reserve(mtm_ctx* ctx, T*& ptr, size_t& cap, size_t need_elems);
+
+// host rows -> device rows on the context's stream; pageable sources go through pinned chunks filled by a host thread pool
+int mtm_upload_rows(mtm_ctx* ctx, void* dst, size_t dst_pitch, const void* src, size_t src_stride, size_t row_bytes, int H);
 
 // ---- host-side stages of a search (mtm_api.cu), shared with the multi-GPU entry points (mtm_comm.cu)
 int reserve_hits(mtm_ctx* ctx, int cap);

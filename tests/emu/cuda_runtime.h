@@ -329,6 +329,10 @@ static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete reinterpret_c
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) { return cudaSuccess; }
 static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }   // launches are synchronous here
 static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2, cudaMemoryTypeManaged = 3 };
+struct cudaPointerAttributes { cudaMemoryType type = cudaMemoryTypeUnregistered; int device = 0; void* devicePointer = nullptr; void* hostPointer = nullptr; };
+// every host pointer reads as pageable: the CPU build then exercises the chunked staging pipeline of host_staging.cu
+static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void*) { *a = cudaPointerAttributes(); return cudaSuccess; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventQuery(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
