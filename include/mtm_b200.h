@@ -80,6 +80,7 @@ typedef struct mtm_counters {
     int64_t ncc_launches;      /* numerator (K2/K3) kernel launches timed with MTM_OPT_TIME_NCC   */
     double ncc_ms;             /* their summed device time in ms (CUDA events on the ctx stream) */
     int64_t tma_launches;      /* numerator launches whose image tiles went through the TMA unit (cp.async.bulk.tensor) */
+    int64_t hits_only_searches;/* searches that wrote no score map (candidate list / arg-max straight from the epilogue)  */
 } mtm_counters;
 
 typedef struct mtm_ctx mtm_ctx;

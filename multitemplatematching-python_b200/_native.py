@@ -24,7 +24,8 @@ assert HIT_DTYPE.itemsize == 24
 
 class Counters(ctypes.Structure):
     _fields_ = [("kernel_launches", ctypes.c_int64), ("h2d_bytes", ctypes.c_int64), ("d2h_bytes", ctypes.c_int64),
-                ("ncc_launches", ctypes.c_int64), ("ncc_ms", ctypes.c_double), ("tma_launches", ctypes.c_int64)]
+                ("ncc_launches", ctypes.c_int64), ("ncc_ms", ctypes.c_double), ("tma_launches", ctypes.c_int64),
+                ("hits_only_searches", ctypes.c_int64)]
 
 
 # name -> (restype, argtypes); mirrors include/mtm_b200.h one to one
@@ -235,7 +236,8 @@ class Context:
         c = Counters()
         self._check(self._lib.mtm_get_counters(self._h, ctypes.byref(c)))
         return {"kernel_launches": c.kernel_launches, "h2d_bytes": c.h2d_bytes, "d2h_bytes": c.d2h_bytes,
-                "ncc_launches": c.ncc_launches, "ncc_ms": c.ncc_ms, "tma_launches": c.tma_launches}
+                "ncc_launches": c.ncc_launches, "ncc_ms": c.ncc_ms, "tma_launches": c.tma_launches,
+                "hits_only_searches": c.hits_only_searches}
 
     def set_time_ncc(self, on):
         self._check(self._lib.mtm_set_option(self._h, OPT_TIME_NCC, 1 if on else 0))

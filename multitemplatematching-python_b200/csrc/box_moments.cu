@@ -158,6 +158,130 @@ box_moments_kernel(const BoxParams p)
     }
 }
 
+// ---- single channel, throughput form ------------------------------------------------------------------------------------
+// Same quantities, same bits; about a third of the instructions per window position (the generic kernel above spends ~84,
+// which made the 64-size sweep of BASELINE configs[4] issue-bound at 1.3 TB/s of moment stores):
+//   * 8 columns per thread (one aligned 8-byte load per image row), strips of 2048 columns: the block-wide scan is paid
+//     once per 8 window positions;
+//   * vertical sums of I as two 16-bit lanes per register (a column sum is at most 255 * h < 2^16 for h <= 257): the row
+//     entering / leaving the window is spread into the lanes with two byte permutes per word;
+//   * ONE barrier per output row: every warp publishes its own exclusive prefix and its total (double-buffered), the
+//     readers add the warp bases themselves;
+//   * {S prefix, Q prefix} interleaved in shared memory: one 8-byte read per window edge.
+constexpr int B1_THREADS = 256;
+constexpr int B1_PX = 8;
+constexpr int B1_COLS = B1_THREADS * B1_PX;           // 2048 image columns per strip
+constexpr int B1_WARPS = B1_THREADS / 32;
+
+__global__ void __launch_bounds__(B1_THREADS, 3)
+box_moments_c1_kernel(const BoxParams p)
+{
+    __shared__ __align__(16) uint2 P[2][B1_COLS + 8];  // exclusive prefix INSIDE the owning warp's 256 columns: {S, Q mod 2^32}
+    __shared__ uint2 wtot[2][B1_WARPS];                // the warps' totals
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const SizeDesc sd = p.sizes[blockIdx.z];
+    const int strip_out = (B1_COLS - (sd.w - 1)) & ~7;
+    const int band = (sd.mh + (int)gridDim.y - 1) / (int)gridDim.y;
+    const int x0 = blockIdx.x * strip_out;
+    const int y0 = blockIdx.y * band, y1 = min(sd.mh, y0 + band);
+    if (x0 >= sd.mw || y0 >= sd.mh) return;
+    const int64_t col_byte = (int64_t)x0 + B1_PX * tid;            // a multiple of 8
+    const bool in_row = col_byte + 8 <= p.pitch;                    // beyond the padded row: no pixels
+    const uint8_t* col = p.img + col_byte;
+    uint32_t VS[4] = {0u, 0u, 0u, 0u};                              // columns (0,1) (2,3) (4,5) (6,7) as 16-bit lanes
+    uint32_t VQ[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) VQ[j] = 0u;
+    if (tid == 0) { P[0][B1_COLS] = make_uint2(0u, 0u); P[1][B1_COLS] = make_uint2(0u, 0u); }
+
+    auto load_row = [&](int r) -> uint2 {
+        return in_row ? __ldg(reinterpret_cast<const uint2*>(col + (int64_t)r * p.pitch)) : make_uint2(0u, 0u);
+    };
+    auto add_row = [&](uint2 wd) {
+        VS[0] += __byte_perm(wd.x, 0u, 0x4140); VS[1] += __byte_perm(wd.x, 0u, 0x4342);
+        VS[2] += __byte_perm(wd.y, 0u, 0x4140); VS[3] += __byte_perm(wd.y, 0u, 0x4342);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t a = __byte_perm(wd.x, 0u, 0x4440 + j), b = __byte_perm(wd.y, 0u, 0x4440 + j);
+            VQ[j] += a * a; VQ[4 + j] += b * b;
+        }
+    };
+    auto sub_row = [&](uint2 wd) {                                  // lane-wise: a column sum contains the row being removed
+        VS[0] -= __byte_perm(wd.x, 0u, 0x4140); VS[1] -= __byte_perm(wd.x, 0u, 0x4342);
+        VS[2] -= __byte_perm(wd.y, 0u, 0x4140); VS[3] -= __byte_perm(wd.y, 0u, 0x4342);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t a = __byte_perm(wd.x, 0u, 0x4440 + j), b = __byte_perm(wd.y, 0u, 0x4440 + j);
+            VQ[j] -= a * a; VQ[4 + j] -= b * b;
+        }
+    };
+
+    // the h-1 rows above the band: adds only, eight loads in flight
+    constexpr int WARM = 8;
+    int r = y0;
+    const int r_end = y0 + sd.h - 1;
+    for (; r + WARM <= r_end; r += WARM) {
+        uint2 wd[WARM];
+#pragma unroll
+        for (int u = 0; u < WARM; ++u) wd[u] = load_row(r + u);
+#pragma unroll
+        for (int u = 0; u < WARM; ++u) add_row(wd[u]);
+    }
+    for (; r < r_end; ++r) add_row(load_row(r));
+
+    const uint32_t area = (uint32_t)sd.h * (uint32_t)sd.w;
+    uint2* out_base = reinterpret_cast<uint2*>(p.S) + sd.off;
+    uint2 w_in = load_row(y0 + sd.h - 1), w_out = load_row(y0);
+    for (int y = y0; y < y1; ++y) {
+        const int buf = (y - y0) & 1;
+        add_row(w_in);
+        const bool more = y + 1 < y1;
+        uint2 n_in = make_uint2(0u, 0u), n_out = make_uint2(0u, 0u);
+        if (more) { n_in = load_row(y + sd.h); n_out = load_row(y + 1); }      // one output row ahead
+        // exclusive prefix of this thread's 8 columns, then of the warp
+        uint32_t es[8], eq[8];
+        uint32_t ts = 0u, tq = 0u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            es[j] = ts; eq[j] = tq;
+            ts += (VS[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
+            tq += VQ[j];
+        }
+        uint32_t is = ts, iq = tq;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t ns = __shfl_up_sync(0xffffffffu, is, d), nq = __shfl_up_sync(0xffffffffu, iq, d);
+            if (lane >= d) { is += ns; iq += nq; }
+        }
+        if (lane == 31) wtot[buf][wid] = make_uint2(is, iq);
+        const uint32_t bs = is - ts, bq = iq - tq;                  // exclusive inside the warp
+        uint4* dst = reinterpret_cast<uint4*>(&P[buf][B1_PX * tid]);
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) dst[j >> 1] = make_uint4(bs + es[j], bq + eq[j], bs + es[j + 1], bq + eq[j + 1]);
+        __syncthreads();                                            // the only barrier of the row (buffers alternate)
+        uint2 wb[B1_WARPS + 1];                                     // base of every warp's segment; [B1_WARPS] = the strip total
+        wb[0] = make_uint2(0u, 0u);
+#pragma unroll
+        for (int k = 0; k < B1_WARPS; ++k) { const uint2 t = wtot[buf][k]; wb[k + 1] = make_uint2(wb[k].x + t.x, wb[k].y + t.y); }
+        uint2* out_row = out_base + (int64_t)y * sd.mw + x0;
+#pragma unroll
+        for (int j = 0; j < B1_PX; ++j) {
+            const int xl = tid + j * B1_THREADS;                    // segment j
+            if (xl >= strip_out || x0 + xl >= sd.mw) continue;
+            const int xr = xl + sd.w;                               // segment j or later (w may span several)
+            const uint2 lo = P[buf][xl], hi = P[buf][xr];
+            const uint2 hb = wb[xr >> 8];
+            const uint32_t s = (hi.x + hb.x) - (lo.x + wb[j].x);
+            const uint32_t qs = (hi.y + hb.y) - (lo.y + wb[j].y);
+            const unsigned long long d1 = (unsigned long long)area * qs - (unsigned long long)s * s;
+            const float rs = d1 ? rsqrtf((float)d1) : 0.0f;
+            out_row[xl] = make_uint2(s, __float_as_uint(rs));
+        }
+        sub_row(w_out);
+        w_in = n_in; w_out = n_out;
+    }
+}
+
 }  // namespace
 
 bool box_moments_enabled()
@@ -194,8 +318,25 @@ int launch_box_moments(mtm_ctx* ctx)
         strips = std::max(strips, (sd.mw + strip_out - 1) / strip_out);
         mh = std::max(mh, sd.mh);
     }
-    // about two CTAs per SM over all sizes; a band re-reads the h-1 rows above it, so bands stay as tall as that allows
     const int n_sizes = (int)ctx->h_sizes.size();
+    static const bool generic_only = getenv("MTM_B200_BOX_GENERIC") != nullptr;      // A/B runs
+    bool lanes16 = true;                               // the throughput form keeps column sums in 16-bit lanes: 255 * h < 2^16
+    for (const SizeDesc& sd : ctx->h_sizes) lanes16 = lanes16 && sd.h <= 257 && sd.w <= B1_COLS / 2;
+    if (im.C == 1 && !generic_only && lanes16) {
+        // throughput form: strips of 2048 columns, about three resident CTAs per SM in total
+        int strips1 = 1;
+        for (const SizeDesc& sd : ctx->h_sizes) {
+            const int strip_out = (B1_COLS - (sd.w - 1)) & ~7;
+            strips1 = std::max(strips1, (sd.mw + strip_out - 1) / strip_out);
+        }
+        const int want = 3 * ctx->sm_count;
+        const int bands1 = std::max(1, std::min(std::max(1, mh / 64), (want + strips1 * n_sizes - 1) / (strips1 * n_sizes)));
+        const dim3 grid1((unsigned)strips1, (unsigned)bands1, (unsigned)n_sizes);
+        box_moments_c1_kernel<<<grid1, B1_THREADS, 0, ctx->stream>>>(p);
+        MTM_LAUNCH_CHECK(ctx);
+        return MTM_OK;
+    }
+    // about two CTAs per SM over all sizes; a band re-reads the h-1 rows above it, so bands stay as tall as that allows
     const int bands = std::max(1, std::min(mh, (2 * ctx->sm_count + strips * n_sizes - 1) / (strips * n_sizes)));
     const dim3 grid((unsigned)strips, (unsigned)bands, (unsigned)n_sizes);
     switch (im.C) {

@@ -161,6 +161,9 @@ int mtm_create(int device, mtm_ctx** out)
             if ((e = cudaEventCreate(&ctx->ev_ncc[k][j])) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_cand), (size_t)MTM_CAND_CAP * sizeof(DevHit))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_cand_count), 64)) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_hkeys), (size_t)MTM_HASH_SLOTS * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_hvals), (size_t)MTM_HASH_SLOTS * sizeof(int32_t))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMemsetAsync(ctx->d_hkeys, 0xFF, (size_t)MTM_HASH_SLOTS * sizeof(unsigned long long), ctx->stream)) != cudaSuccess) return bail("cudaMemsetAsync", e);
     int rc = reserve_hits(ctx, 1 << 16);
     if (rc != MTM_OK) { g_create_err = ctx->err; mtm_destroy(ctx); return rc; }
     *out = ctx;
@@ -175,7 +178,7 @@ int mtm_destroy(mtm_ctx* ctx)
     cudaFree(ctx->img.pix); cudaFree(ctx->img.sat_s); cudaFree(ctx->img.sat_q); cudaFree(ctx->img.sat_q32); cudaFree(ctx->scratch);
     cudaFree(ctx->d_meta); cudaFree(ctx->d_tmpl); cudaFree(ctx->d_maps); cudaFree(ctx->d_order);
     cudaFree(ctx->d_blockA); cudaFree(ctx->d_blockB); cudaFree(ctx->d_keep);
-    cudaFree(ctx->d_nontrivial); cudaFree(ctx->d_best); cudaFree(ctx->d_cand); cudaFree(ctx->d_cand_count);
+    cudaFree(ctx->d_nontrivial); cudaFree(ctx->d_best); cudaFree(ctx->d_cand); cudaFree(ctx->d_cand_count); cudaFree(ctx->d_hkeys); cudaFree(ctx->d_hvals);
     cudaFree(ctx->img.pixf2); cudaFree(ctx->d_raw_t); cudaFree(ctx->d_raw_m); cudaFree(ctx->d_maps2);
     cudaFree(ctx->img.pixf); cudaFree(ctx->img.satf_s); cudaFree(ctx->img.satf_q); cudaFree(ctx->d_tmpl_centred);
     cudaFree(ctx->d_raw16); cudaFree(ctx->img.pix_lo); cudaFree(ctx->d_tmpl8); cudaFree(ctx->d_pix8); cudaFree(ctx->d_acc);
@@ -415,7 +418,7 @@ int ensure_geometry(mtm_ctx* ctx)
     }
     MTM_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_meta, sizeof(TmplMeta), ctx->h_geom, sizeof(TmplGeom), sizeof(TmplGeom),
                                     (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-    MTM_TRY(mtm_reserve(ctx, ctx->d_maps, ctx->maps_cap, (size_t)off));
+    ctx->maps_resident = false;                             // the map arena is reserved by compute_maps when a search needs it
     ctx->geometry_valid = true;
     return MTM_OK;
 }
@@ -551,6 +554,7 @@ static int compute_maps_masked(mtm_ctx* ctx, int method)
 void request_candidates(mtm_ctx* ctx, int method, int64_t n_object, double thr)
 {
     ctx->cand_on = false;
+    ctx->want_n1 = n_object == 1;
     static const bool no_cand = getenv("MTM_B200_NO_CAND") != nullptr;     // experiments: always stream the maps for peaks
     if (method != MTM_TM_CCOEFF_NORMED || n_object == 1 || no_cand) return;
     for (int t = 0; t < ctx->n_tmpl; ++t) {
@@ -562,16 +566,39 @@ void request_candidates(mtm_ctx* ctx, int method, int64_t n_object, double thr)
 }
 
 // Score maps of every template (tmpl < 0) or of one template, grouped by template size.
-int compute_maps(mtm_ctx* ctx, int method, int tmpl)
+int compute_maps(mtm_ctx* ctx, int method, int tmpl, bool hits_ok)
 {
     if (method < 0 || method > 5) return mtm_fail(ctx, MTM_ERR_INVALID, "unknown method %d", method);
     const int n = ctx->n_tmpl;
     int i = 0;
-    if (ctx->masked) { ctx->cand_on = false; ctx->cand_valid = false; return compute_maps_masked(ctx, method); }
+    ctx->hits_only = false; ctx->best_on = false; ctx->best_valid = false;
+    if (ctx->masked) {
+        ctx->cand_on = false; ctx->cand_valid = false;
+        MTM_TRY(mtm_reserve(ctx, ctx->d_maps, ctx->maps_cap, (size_t)ctx->maps_total));
+        ctx->maps_resident = true;
+        return compute_maps_masked(ctx, method);
+    }
     const bool tensor = use_tensor_path(ctx, method);
     if (!tensor && ctx->path == MTM_PATH_TENSOR)
         return mtm_fail(ctx, MTM_ERR_UNSUPPORTED, "tensor-core path requested but not available for these inputs/method");
     const bool tensor16 = tensor && ctx->img_dtype == MTM_F32;     // 16-bit byte-plane path
+    ctx->cand_on = ctx->cand_on && tensor && !tensor16 && tmpl < 0;
+    // Hits-only search: the caller reads no score map, every template runs the default-method tcgen05 kernel, and the peak
+    // search has what it needs without one (candidate list, or the per-template arg-max for N_object == 1): the numerator
+    // kernels then store no map at all (MODE 3) and the map arena is not even reserved.  MTM_B200_NO_HITS_ONLY=1: A/B runs.
+    static const bool no_hits = getenv("MTM_B200_NO_HITS_ONLY") != nullptr;
+    bool hits = hits_ok && !no_hits && tensor && !tensor16 && method == MTM_TM_CCOEFF_NORMED && tmpl < 0 && ctx->img_dtype == MTM_U8 &&
+                (ctx->cand_on || ctx->want_n1);
+    if (hits)
+        for (const TcGroup& g : ctx->tc_groups) hits = hits && !points_path_preferred(ctx, g.first, g.count);
+    if (!hits) MTM_TRY(mtm_reserve(ctx, ctx->d_maps, ctx->maps_cap, (size_t)ctx->maps_total));
+    ctx->hits_only = hits;
+    if (hits) ctx->ctr.hits_only_searches++;
+    ctx->maps_resident = false;
+    if (hits && ctx->want_n1 && !ctx->cand_on) {
+        ctx->best_on = true;
+        MTM_CUDA(ctx, cudaMemsetAsync(ctx->d_best, 0, (size_t)n * sizeof(unsigned long long), ctx->stream));
+    }
     if (ctx->img_dtype == MTM_U8) {
         // Everything but the default method's tensor-core epilogue reads the summed-area tables; under MTM_B200_MOM_BOX the
         // window moments come from the image instead (box_moments.cu) and the tables are not built for such a call.
@@ -586,7 +613,6 @@ int compute_maps(mtm_ctx* ctx, int method, int tmpl)
         MTM_TRY(harvest_ncc_time(ctx, false));
         MTM_CUDA(ctx, cudaEventRecord(ctx->ev_ncc[ctx->ncc_head % MTM_NCC_RING][0], ctx->stream));
     }
-    ctx->cand_on = ctx->cand_on && tensor && tmpl < 0;
     ctx->cand_valid = false;
     if (ctx->cand_on) MTM_CUDA(ctx, cudaMemsetAsync(ctx->d_cand_count, 0, sizeof(int32_t), ctx->stream));
     if (tensor) {
@@ -611,8 +637,11 @@ int compute_maps(mtm_ctx* ctx, int method, int tmpl)
         if (tensor16) MTM_TRY(launch_cc16_epilogue(ctx, method, tmpl));
         i = n;
         ctx->cand_valid = ctx->cand_on;
+        ctx->best_valid = ctx->best_on;
     }
     ctx->cand_on = false;
+    ctx->best_on = false;
+    ctx->maps_resident = !hits;
     while (i < n) {
         const TmplMeta& a = ctx->h_meta[ctx->h_order[i]];
         int j = i + 1;
@@ -687,6 +716,18 @@ struct TmplHasher {
         if (k < n) { memcpy(&tail, b + k, n - k); mix(tail ^ ((uint64_t)(n - k) << 56)); }
     }
 };
+
+// The candidate list of a search overflowed (more than MTM_CAND_CAP pixels above the threshold): the peak search must stream
+// the score maps.  A hits-only search has none: compute them (no list this time).
+int candidates_overflowed(mtm_ctx* ctx, int method)
+{
+    ctx->cand_valid = false;
+    if (!ctx->maps_resident) {
+        ctx->cand_on = false;
+        MTM_TRY(compute_maps(ctx, method, -1, false));
+    }
+    return MTM_OK;
+}
 
 // Downloads header + hits of a block into h_stage.  Returns the raw count in *n_raw.
 int download_block(mtm_ctx* ctx, const uint8_t* d_block, int* n_raw, int* n_valid, int* declined)
@@ -1048,7 +1089,7 @@ int mtm_find_matches(mtm_ctx* ctx, int method, int64_t n_object, double score_th
     if (!n_hits || (capacity > 0 && !hits)) return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_find_matches: null output");
     MTM_TRY(ensure_geometry(ctx));
     request_candidates(ctx, method, n_object, score_threshold);
-    MTM_TRY(compute_maps(ctx, method, -1));
+    MTM_TRY(compute_maps(ctx, method, -1, true));
     const int minimize = method_is_min(method) ? 1 : 0;
     for (int attempt = 0; attempt < 8; ++attempt) {
         MTM_TRY(launch_peaks(ctx, method, n_object, (float)score_threshold, score_threshold));
@@ -1056,7 +1097,7 @@ int mtm_find_matches(mtm_ctx* ctx, int method, int64_t n_object, double score_th
         if (n_object != 1) {
             MTM_TRY(launch_finalize_small(ctx, minimize, 1, 0, 0, 0.f, 0, -1, 0.f));
             MTM_TRY(download_block(ctx, ctx->d_blockA, &n_raw, &n, &declined));
-            if (declined == 2) { ctx->cand_valid = false; continue; }      // candidate list overflowed: stream the maps
+            if (declined == 2) { MTM_TRY(candidates_overflowed(ctx, method)); continue; }      // candidate list overflowed: stream the maps
             if (declined) {                                  // more than 1024 raw hits: general path
                 if (n_raw > ctx->hit_cap) { MTM_TRY(reserve_hits(ctx, n_raw)); continue; }
                 MTM_TRY(launch_sort_hits(ctx, 0, minimize, 0, 1));
@@ -1083,7 +1124,7 @@ int mtm_match_templates(mtm_ctx* ctx, int method, int64_t n_object, double score
     MTM_TRY(ensure_geometry(ctx));
     g_marks.mark(ctx, "geometry");
     request_candidates(ctx, method, n_object, score_threshold);
-    MTM_TRY(compute_maps(ctx, method, -1));
+    MTM_TRY(compute_maps(ctx, method, -1, true));
     g_marks.mark(ctx, "moments+ncc");
     const int minimize = method_is_min(method) ? 1 : 0;
     const int ascending = (method == MTM_TM_SQDIFF_NORMED) ? 1 : 0;
@@ -1098,7 +1139,7 @@ int mtm_match_templates(mtm_ctx* ctx, int method, int64_t n_object, double score
         MTM_TRY(download_mirror(ctx, ctx->d_blockB, &n_raw, &n, &declined));
         g_marks.mark(ctx, "download");
         g_marks.report(ctx);
-        if (declined == 2) { ctx->cand_valid = false; continue; }          // candidate list overflowed: stream the maps
+        if (declined == 2) { MTM_TRY(candidates_overflowed(ctx, method)); continue; }          // candidate list overflowed: stream the maps
         if (declined) {                                      // more than 1024 raw hits: general path
             if (n_raw > ctx->hit_cap) { MTM_TRY(reserve_hits(ctx, n_raw)); continue; }
             if (n_object != 1) {
@@ -1133,7 +1174,7 @@ int mtm_match_templates_async(mtm_ctx* ctx, int method, int64_t n_object, double
     }
     MTM_TRY(ensure_geometry(ctx));
     request_candidates(ctx, method, n_object, score_threshold);
-    MTM_TRY(compute_maps(ctx, method, -1));
+    MTM_TRY(compute_maps(ctx, method, -1, true));
     const int minimize = method_is_min(method) ? 1 : 0;
     const int ascending = (method == MTM_TM_SQDIFF_NORMED) ? 1 : 0;
     const float thr_nms = ascending ? (float)(1.0 - score_threshold) : (float)score_threshold;

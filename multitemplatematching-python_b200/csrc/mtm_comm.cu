@@ -467,7 +467,7 @@ int mtm_match_templates_sharded(mtm_ctx* ctx, mtm_comm* comm, int tmpl_base, int
             return mtm_fail(ctx, MTM_ERR_INVALID, "mtm_match_templates_sharded: slice of %d templates, %d resident in the context", n_local, ctx->n_tmpl);
         MTM_TRY(ensure_geometry(ctx));
         request_candidates(ctx, method, n_object, score_threshold);
-        MTM_TRY(compute_maps(ctx, method, -1));
+        MTM_TRY(compute_maps(ctx, method, -1, true));
         return MTM_OK;
     };
     int status = local_stage();
@@ -507,7 +507,7 @@ int mtm_match_templates_sharded(mtm_ctx* ctx, mtm_comm* comm, int tmpl_base, int
         // every rank reads the same header, so every rank takes the same branch below
         if (raw_max > ctx->hit_cap) { MTM_TRY(reserve_hits(ctx, raw_max)); continue; }
         if (need > cap_g) { comm->cap_g = next_pow2_i(need); continue; }
-        if (declined == 2) { ctx->cand_valid = false; continue; }          // a candidate list overflowed: stream the maps
+        if (declined == 2) { MTM_TRY(candidates_overflowed(ctx, method)); continue; }          // a candidate list overflowed: stream the maps
         if (declined) {                                                      // more than 1024 merged hits: general path
             if (n_raw > ctx->hit_cap) { MTM_TRY(reserve_hits(ctx, n_raw)); continue; }
             if (!presorted) {

@@ -10,6 +10,7 @@
 #define MTM_MAX_CH 4
 #define MTM_NCC_RING 16
 #define MTM_CAND_CAP 32768      // above-threshold pixels the tensor-core epilogue may list per call
+#define MTM_HASH_SLOTS (1 << 17) // slots of the candidate hash table (load factor <= 1/4)
 #define MTM_SLOT_HITS 1024      // hits a slot of the asynchronous API can return (== the fused fast path)
 #define MTM_STAGE_BUFS 4        // pinned chunks of the pageable-upload pipeline (host_staging.cu)
 #define MTM_HIT_HEADER 32      // bytes: int32 count[8]; count[0] = number of hits (may exceed capacity)
@@ -181,6 +182,14 @@ struct mtm_ctx {
 
     // candidate list written by the tcgen05 epilogue (pixels above the threshold), consumed by verify_candidates
     DevHit* d_cand = nullptr; int32_t* d_cand_count = nullptr;
+    // hits-only searches (MODE 3 of the tcgen05 kernels): no score map is written; the peak search works on the candidate list
+    // (3x3 maxima resolved inside the list, resolve_candidates_kernel) or on the per-template arg-max keys of the epilogue
+    bool want_n1 = false;                // the pending search is the N_object == 1 one (request_candidates)
+    bool hits_only = false;              // the current / last compute_maps call ran without score maps
+    bool best_on = false;                // ... and its epilogues raise d_best (N_object == 1)
+    bool best_valid = false;             // d_best holds the arg-max keys of the resident search
+    bool maps_resident = false;          // d_maps holds the score maps of the resident (image, templates, method)
+    unsigned long long* d_hkeys = nullptr; int32_t* d_hvals = nullptr;   // open-addressing table of resolve_candidates_kernel (kept empty between calls)
     bool cand_on = false;                // the current compute_maps call fills the list
     bool cand_valid = false;             // the list belongs to the resident score maps
     float cand_thr = 0.f;
@@ -232,7 +241,8 @@ int mtm_upload_rows(mtm_ctx* ctx, void* dst, size_t dst_pitch, const void* src, 
 int reserve_hits(mtm_ctx* ctx, int cap);
 int ensure_geometry(mtm_ctx* ctx);
 void request_candidates(mtm_ctx* ctx, int method, int64_t n_object, double thr);
-int compute_maps(mtm_ctx* ctx, int method, int tmpl);
+int candidates_overflowed(mtm_ctx* ctx, int method);
+int compute_maps(mtm_ctx* ctx, int method, int tmpl, bool hits_ok = false);   // hits_ok: the caller only needs the hit list (no score map read-back)
 int download_block(mtm_ctx* ctx, const uint8_t* d_block, int* n_raw, int* n_valid, int* declined = nullptr);
 int download_mirror(mtm_ctx* ctx, const uint8_t* d_block, int* n_raw, int* n_valid, int* declined);
 void copy_out(const mtm_ctx* ctx, mtm_hit* hits, int n);

@@ -176,9 +176,16 @@ __device__ __forceinline__ void prefetch_moments16(const uint2* __restrict__ SR,
     }
 }
 
+// Hits-only epilogues (STORE == false: MODE 3) write no score map: pixels above the threshold go to the candidate list as
+// before, and for the N_object == 1 search every lane keeps the best score it has seen with its row-major map index (the
+// first occurrence: a lane walks its column downwards, ties keep the earlier row).
+struct BestTrack { float r; uint32_t idx; };
+
+template <bool STORE>
 __device__ __forceinline__ void epilogue16(const uint32_t (&v)[16], int y_first, int mh, int mw, int x, long long area,
                                            long long sumT, float ct, bool is_const, const uint2* __restrict__ SR,
-                                           float* __restrict__ out, const CandSink& sink, bool prefetch_next)
+                                           float* __restrict__ out, const CandSink& sink, bool prefetch_next,
+                                           BestTrack& bt, bool track)
 {
     uint2 m[16];
 #pragma unroll
@@ -195,7 +202,8 @@ __device__ __forceinline__ void epilogue16(const uint32_t (&v)[16], int y_first,
         r = fminf(1.0f, fmaxf(-1.0f, r));
         if (is_const) r = 1.0f;
         if (y < mh) {
-            out[(int64_t)y * mw + x] = r;
+            if (STORE) out[(int64_t)y * mw + x] = r;
+            if (!STORE && track && r > bt.r) { bt.r = r; bt.idx = (uint32_t)(y * mw + x); }
             if (sink.list && r > sink.thr) {
                 const int slot = atomicAdd(sink.count, 1);
                 if (slot < sink.cap) {
@@ -210,12 +218,14 @@ __device__ __forceinline__ void epilogue16(const uint32_t (&v)[16], int y_first,
 
 // Fast form of epilogue16 for the common case (all 16 rows inside the map, template not constant): 32-bit operands,
 // one running offset, no per-pixel bounds tests.  A <= 66051 and sumT <= 255*66051 fit 32 bits on the tensor path.
+template <bool STORE>
 __device__ __forceinline__ void epilogue16_fast(const uint32_t (&v)[16], int y_first, int mw, int x, uint32_t area, uint32_t sumT,
                                                 float ct, const uint2* __restrict__ SR, float* __restrict__ out,
-                                                const CandSink& sink, float thr, bool prefetch_next)
+                                                const CandSink& sink, float thr, bool prefetch_next, BestTrack& bt, bool track)
 {
     const uint2* sr = SR + (int64_t)y_first * mw + x;
     float* o = out + (int64_t)y_first * mw + x;
+    const uint32_t idx0 = (uint32_t)(y_first * mw + x);
     uint2 m[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) m[k] = __ldg(sr + (uint32_t)(k * mw));
@@ -228,7 +238,8 @@ __device__ __forceinline__ void epilogue16_fast(const uint32_t (&v)[16], int y_f
         const long long n1 = (long long)((unsigned long long)area * v[k]) - (long long)((unsigned long long)m[k].x * sumT);
         float r = (float)n1 * __uint_as_float(m[k].y) * ct;
         r = fminf(1.0f, fmaxf(-1.0f, r));
-        o[(uint32_t)(k * mw)] = r;
+        if (STORE) o[(uint32_t)(k * mw)] = r;
+        if (!STORE && track) { const bool better = r > bt.r; bt.r = better ? r : bt.r; bt.idx = better ? idx0 + (uint32_t)(k * mw) : bt.idx; }
         if (r > thr) {
             const int slot = atomicAdd(sink.count, 1);
             if (slot < sink.cap) {
@@ -278,11 +289,11 @@ __device__ __forceinline__ void epilogue16_accum(const uint32_t (&v)[16], int y_
 
 // Multi-channel (interleaved RGB / RGBA) form: per-channel window sums, the squared sums share one table.
 //   N1 = A*CC - sum_c S_c*sumT_c ;  rsD already holds rsqrt(A*Q - sum_c S_c^2).
-template <int C>
+template <int C, bool STORE>
 __device__ __forceinline__ void epilogue16_mc(const uint32_t (&v)[16], int y_first, int mh, int mw, int x, long long area,
                                               const long long (&sumT)[MTM_MAX_CH], float ct, bool is_const,
                                               const uint32_t* __restrict__ S, int64_t plane, const float* __restrict__ rsD,
-                                              float* __restrict__ out, const CandSink& sink)
+                                              float* __restrict__ out, const CandSink& sink, BestTrack& bt, bool track)
 {
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
@@ -306,7 +317,8 @@ __device__ __forceinline__ void epilogue16_mc(const uint32_t (&v)[16], int y_fir
             r = fminf(1.0f, fmaxf(-1.0f, r));
             if (is_const) r = 1.0f;
             if (y < mh) {
-                out[(int64_t)y * mw + x] = r;
+                if (STORE) out[(int64_t)y * mw + x] = r;
+                if (!STORE && track && r > bt.r) { bt.r = r; bt.idx = (uint32_t)(y * mw + x); }
                 if (sink.list && r > sink.thr) {
                     const int slot = atomicAdd(sink.count, 1);
                     if (slot < sink.cap) {
@@ -378,6 +390,7 @@ struct TcParams {
     const uint32_t* S; const float* rsD;   // window moments of this (h, w): [mh][mw]
     float* maps;
     DevHit* cand; int32_t* cand_count; int cand_cap; float cand_thr;   // optional candidate list (nullptr: off)
+    unsigned long long* best;         // MODE 3, N_object == 1: per template arg-max key (ordered score << 32 | ~map index), nullptr: off
     int C; int64_t mom_plane;         // channels (1, 3, 4) and the element stride between the per-channel S planes
     int stages, tiles_x, tiles_total; // persistent kernel: slab ring depth, tile grid width, number of tiles
     long long* prof; int dbg;         // debug only (MTM_B200_PROF / MTM_B200_PDBG): per-CTA role clocks, phase knock-outs
@@ -388,8 +401,10 @@ struct TcParams {
 
 // Epilogue of one tile for one of 8 epilogue warps: warp%4 selects the TMEM lane quarter, warp/4 the column half.
 template <int MODE>
-__device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_d, int x0, int y0, int warp, int lane, int parts = 2)
+__device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_d, int x0, int y0, int warp, int lane, int parts, BestTrack& bt)
 {
+    constexpr bool STORE = MODE != 3;                          // MODE 3 = MODE 0 without the score map (hits only)
+    const bool track = MODE == 3 && p.best != nullptr;
     const int m = 32 * (warp & 3) + lane;
     int x, tsel;
     if (p.mode == 0) { tsel = m >> 4; x = x0 + (m & 15); }
@@ -430,11 +445,11 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_d
         }
         if (p.C == 1) {
             // the prefetched rows of the next batch must exist: +32
-            if (!is_const && y0 + c0 + 32 <= t_mh) epilogue16_fast(v, y0 + c0, t_mw, x, (uint32_t)area, (uint32_t)sumT, ct, SRm, out, sink, thr_eff, c0 + 16 < c_end);
-            else epilogue16(v, y0 + c0, t_mh, t_mw, x, area, sumT, ct, is_const, SRm, out, sink, c0 + 16 < c_end);
+            if (!is_const && y0 + c0 + 32 <= t_mh) epilogue16_fast<STORE>(v, y0 + c0, t_mw, x, (uint32_t)area, (uint32_t)sumT, ct, SRm, out, sink, thr_eff, c0 + 16 < c_end, bt, track);
+            else epilogue16<STORE>(v, y0 + c0, t_mh, t_mw, x, area, sumT, ct, is_const, SRm, out, sink, c0 + 16 < c_end, bt, track);
         }
-        else if (p.C == 3) epilogue16_mc<3>(v, y0 + c0, t_mh, t_mw, x, area, sumT_c, ct, is_const, Sm, p.mom_plane, Rm, out, sink);
-        else epilogue16_mc<4>(v, y0 + c0, t_mh, t_mw, x, area, sumT_c, ct, is_const, Sm, p.mom_plane, Rm, out, sink);
+        else if (p.C == 3) epilogue16_mc<3, STORE>(v, y0 + c0, t_mh, t_mw, x, area, sumT_c, ct, is_const, Sm, p.mom_plane, Rm, out, sink, bt, track);
+        else epilogue16_mc<4, STORE>(v, y0 + c0, t_mh, t_mw, x, area, sumT_c, ct, is_const, Sm, p.mom_plane, Rm, out, sink, bt, track);
     }
 }
 
@@ -453,6 +468,21 @@ __device__ __forceinline__ void epilogue_prefetch_first(const TcParams& p, int x
     const int c_begin = 16 * ((batches * (warp >> 2)) / parts);
     if (x >= t_mw || y0 + c_begin >= t_mh) return;
     prefetch_moments16(reinterpret_cast<const uint2*>(p.S) + tm->mom_off, y0 + c_begin, t_mh, t_mw, x);
+}
+
+// MODE 3, N_object == 1: the lanes of a warp that serve the same template (mode A: 16, mode B: 32) reduce their best pixel and
+// one of them raises the template's arg-max key (larger score wins, then the smaller map index = cv2.minMaxLoc's first occurrence).
+__device__ __forceinline__ void flush_best(const TcParams& p, const BestTrack& bt, int warp, int lane)
+{
+    const int m = 32 * (warp & 3) + lane;
+    const int tsel = p.mode == 0 ? (m >> 4) : 0;
+    unsigned long long key = bt.r > -2.0f ? (((unsigned long long)ordered_f32(bt.r) << 32) | (unsigned long long)(0xFFFFFFFFu - bt.idx)) : 0ull;
+    const int span = p.mode == 0 ? 8 : 16;
+    for (int d = span; d; d >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, key, d);
+        key = o > key ? o : key;
+    }
+    if (tsel < p.count && key && (lane & (p.mode == 0 ? 15 : 31)) == 0) atomicMax(&p.best[p.order[tsel]], key);
 }
 
 // One CTA = one output tile.  Warp 0: slab producer, warp 1: MMA issuer, then all 8 warps: epilogue.
@@ -550,7 +580,9 @@ ncc_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap)
     if (warp == 1) { if (lane == 0) mbar_wait(accum, 0); __syncwarp(); }
     __syncthreads();
     tc_fence_after();
-    epilogue_tile<MODE>(p, tmem_d, x0, y0, warp, lane);
+    BestTrack bt{-3.0e38f, 0u};
+    epilogue_tile<MODE>(p, tmem_d, x0, y0, warp, lane, 2, bt);
+    if (MODE == 3 && p.best) flush_best(p, bt, warp, lane);
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc(tmem_d, tmem_cols);
@@ -771,20 +803,22 @@ ncc_tc_persist_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap
     } else {
         // ===== epilogue warps =====
         long long w_af = 0, w_epi = 0;
+        BestTrack bt{-3.0e38f, 0u};
         for (int i = 0; i < my_tiles; ++i) {
             const int b = i & 1, u = i >> 1;
             const int ti = (int)blockIdx.x + i * (int)gridDim.x;
             const int x0 = (ti % p.tiles_x) * xw, y0 = (ti / p.tiles_x) * p.N;
-            if (MODE == 0) epilogue_prefetch_first(p, x0, y0, warp, lane, EW / 4);
+            if (MODE == 0 || MODE == 3) epilogue_prefetch_first(p, x0, y0, warp, lane, EW / 4);
             const long long c0 = PROF ? clock64() : 0;
             mbar_wait(&acc_full[b], u & 1);
             const long long c1 = PROF ? clock64() : 0;
             tc_fence_after();
-            if (!PROF || !(p.dbg & 1)) epilogue_tile<MODE>(p, tmem_base + (uint32_t)b * acc_stride, x0, y0, warp, lane, EW / 4);
+            if (!PROF || !(p.dbg & 1)) epilogue_tile<MODE>(p, tmem_base + (uint32_t)b * acc_stride, x0, y0, warp, lane, EW / 4, bt);
             tc_fence_before();
             mbar_arrive(&acc_empty[b]);
             if (PROF) { w_af += c1 - c0; w_epi += clock64() - c1; }
         }
+        if (MODE == 3 && p.best) flush_best(p, bt, warp, lane);
         if (PROF && tid == 0) { p.prof[16 * blockIdx.x + 4] = w_af; p.prof[16 * blockIdx.x + 5] = w_epi; }
     }
     tc_fence_before();
@@ -1070,7 +1104,9 @@ static int launch_ncc_tc_impl(mtm_ctx* ctx, const TcGroup& g, int method, const 
     p.method = method;
     p.sat = SatView{im.sat_s, im.sat_q, im.sat_pitch, (int64_t)(im.H + 1) * im.sat_pitch};
     p.img = im.pix; p.pitch = im.pitch; p.H = im.H; p.W = im.W;
-    const int kmode = accum ? 2 : (method != MTM_TM_CCOEFF_NORMED ? 1 : 0);      // epilogue flavour = kernel instantiation
+    // epilogue flavour = kernel instantiation: 0 default method, 1 float64 rules of the other methods, 2 byte-plane accumulation,
+    // 3 default method without the score map (hits only: candidate list and / or per-template arg-max)
+    const int kmode = accum ? 2 : (method != MTM_TM_CCOEFF_NORMED ? 1 : (ctx->hits_only ? 3 : 0));
     p.slabs = ctx->d_slabs + g.arena_off;
     if (accum) {
         if (accum->img_plane) p.img = im.pix_lo;
@@ -1083,7 +1119,8 @@ static int launch_ncc_tc_impl(mtm_ctx* ctx, const TcGroup& g, int method, const 
     p.meta = ctx->d_meta; p.order = ctx->d_order + g.first; p.count = g.count;
     p.S = ctx->d_wS; p.rsD = ctx->d_wR; p.maps = ctx->d_maps;
     p.C = im.C; p.mom_plane = ctx->moments_total;
-    if (ctx->cand_on && kmode == 0) { p.cand = ctx->d_cand; p.cand_count = ctx->d_cand_count; p.cand_cap = MTM_CAND_CAP; p.cand_thr = ctx->cand_thr; }
+    if (kmode == 3 && ctx->best_on) p.best = ctx->d_best;
+    if (ctx->cand_on && (kmode == 0 || kmode == 3)) { p.cand = ctx->d_cand; p.cand_count = ctx->d_cand_count; p.cand_cap = MTM_CAND_CAP; p.cand_thr = ctx->cand_thr; }
     // Image tiles through the TMA unit (default; MTM_B200_TMA=0 or a failing encoder: register staging by the stager warps).
     // Called once p.R is final: a box holds at most 256 rows.
     CUtensorMap tmap;
@@ -1146,6 +1183,8 @@ static int launch_ncc_tc_impl(mtm_ctx* ctx, const TcGroup& g, int method, const 
                 MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_kernel<false, 12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
                 MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_kernel<false, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
                 MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_kernel<false, 12, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+                MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_kernel<false, 8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+                MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_kernel<false, 12, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
                 ctx->tcp_attr_set = true;
             }
             const int grid_p = std::min(p.tiles_total, ctx->sm_count);
@@ -1165,6 +1204,9 @@ static int launch_ncc_tc_impl(mtm_ctx* ctx, const TcGroup& g, int method, const 
             } else if (kmode == 1) {
                 if (ew == 12) ncc_tc_persist_kernel<false, 12, 1><<<grid_p, 32 * (p.tma ? 15 : 16), smem_bytes, ctx->stream>>>(p, tmap);
                 else ncc_tc_persist_kernel<false, 8, 1><<<grid_p, 32 * (p.tma ? 11 : 12), smem_bytes, ctx->stream>>>(p, tmap);
+            } else if (kmode == 3) {
+                if (ew == 12) ncc_tc_persist_kernel<false, 12, 3><<<grid_p, 32 * (p.tma ? 15 : 16), smem_bytes, ctx->stream>>>(p, tmap);
+                else ncc_tc_persist_kernel<false, 8, 3><<<grid_p, 32 * (p.tma ? 11 : 12), smem_bytes, ctx->stream>>>(p, tmap);
             } else if (ew == 12) {
                 if (prof) ncc_tc_persist_kernel<true, 12, 0><<<grid_p, 32 * (p.tma ? 15 : 16), smem_bytes, ctx->stream>>>(p, tmap);
                 else ncc_tc_persist_kernel<false, 12, 0><<<grid_p, 32 * (p.tma ? 15 : 16), smem_bytes, ctx->stream>>>(p, tmap);
@@ -1213,12 +1255,14 @@ static int launch_ncc_tc_impl(mtm_ctx* ctx, const TcGroup& g, int method, const 
         MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         ctx->tc_attr_set = true;
     }
     const int xw = g.mode == 0 ? 16 : 128;
     dim3 grid((p.mw + xw - 1) / xw, (p.mh + p.N - 1) / p.N);
     if (kmode == 2) ncc_tc_kernel<2><<<grid, TC_THREADS, smem_bytes, ctx->stream>>>(p, tmap);
     else if (kmode == 1) ncc_tc_kernel<1><<<grid, TC_THREADS, smem_bytes, ctx->stream>>>(p, tmap);
+    else if (kmode == 3) ncc_tc_kernel<3><<<grid, TC_THREADS, smem_bytes, ctx->stream>>>(p, tmap);
     else ncc_tc_kernel<0><<<grid, TC_THREADS, smem_bytes, ctx->stream>>>(p, tmap);
     MTM_LAUNCH_CHECK(ctx);
     return MTM_OK;

@@ -162,6 +162,85 @@ __global__ void verify_candidates_kernel(const TmplMeta* __restrict__ meta, int 
     }
 }
 
+// Hits-only searches have no score map to look the neighbours up in.  They are not needed: a neighbour that beats a candidate
+// scores above the threshold itself, so it is in the list too.  ONE CTA: (1) every candidate enters an open-addressing table
+// keyed by (template, map index); (2) every candidate probes its (up to) eight neighbours and survives unless one of them is
+// listed with a larger score -- the same test as verify_candidates_kernel, '>' on the same float32 scores; (3) the used
+// slots are emptied again, so the table needs no memset between calls.  count[3] = 1 reports a list overflow.
+__device__ __forceinline__ uint32_t cand_hash(unsigned long long key)
+{
+    key ^= key >> 33; key *= 0xff51afd7ed558ccdull; key ^= key >> 29;
+    return (uint32_t)key & (MTM_HASH_SLOTS - 1);
+}
+
+__global__ void __launch_bounds__(1024, 1)
+resolve_candidates_kernel(const TmplMeta* __restrict__ meta, int n_tmpl, DevHit* __restrict__ cand, const int32_t* __restrict__ cand_count,
+                          int cand_cap, unsigned long long* __restrict__ hkeys, int32_t* __restrict__ hvals,
+                          DevHit* __restrict__ hits, int cap, int32_t* __restrict__ count, int32_t* __restrict__ nontrivial)
+{
+    constexpr unsigned long long EMPTY = ~0ull;
+    const int n = *cand_count;
+    const int tid = threadIdx.x;
+    for (int t = tid; t < n_tmpl; t += blockDim.x) nontrivial[t] = 1;     // only used for maps with more pixels than the list holds
+    if (n > cand_cap) { if (tid == 0) count[3] = 1; return; }
+    for (int i = tid; i < n; i += blockDim.x) {
+        const DevHit c = cand[i];
+        const unsigned long long key = ((unsigned long long)(uint32_t)c.tmpl << 32) | (uint32_t)(c.y * meta[c.tmpl].mw + c.x);
+        uint32_t h = cand_hash(key);
+        while (atomicCAS(&hkeys[h], EMPTY, key) != EMPTY) h = (h + 1) & (MTM_HASH_SLOTS - 1);     // keys are unique: a pixel is listed once
+        hvals[h] = i;
+        cand[i].seq = (int32_t)h;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) {
+        const DevHit c = cand[i];
+        const TmplMeta& tm = meta[c.tmpl];
+        bool is_max = true;
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+            const int yy = c.y + dy;
+            if (yy < 0 || yy >= tm.mh) continue;
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int xx = c.x + dx;
+                if (xx < 0 || xx >= tm.mw || (dx == 0 && dy == 0)) continue;
+                const unsigned long long key = ((unsigned long long)(uint32_t)c.tmpl << 32) | (uint32_t)(yy * tm.mw + xx);
+                uint32_t h = cand_hash(key);
+                for (;;) {
+                    const unsigned long long k = hkeys[h];
+                    if (k == EMPTY) break;                               // not listed: its score is at most the threshold
+                    if (k == key) { if (cand[hvals[h]].score > c.score) is_max = false; break; }
+                    h = (h + 1) & (MTM_HASH_SLOTS - 1);
+                }
+            }
+        }
+        if (is_max) {
+            const int slot = atomicAdd(count, 1);
+            if (slot < cap) { DevHit o = c; o.seq = 0; hits[slot] = o; }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) hkeys[cand[i].seq] = EMPTY;
+}
+
+// N_object == 1 of a hits-only search: the epilogues of the numerator kernels raised best[t] (flush_best, ncc_tc.cu).
+__global__ void emit_best_keys_kernel(const TmplMeta* __restrict__ meta, int n_tmpl, const unsigned long long* __restrict__ best,
+                                      DevHit* __restrict__ hits, int32_t* __restrict__ count)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0) count[0] = n_tmpl;
+    if (t >= n_tmpl) return;
+    const TmplMeta& tm = meta[t];
+    const unsigned long long key = best[t];
+    const uint32_t idx = 0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull);
+    const uint32_t o = (uint32_t)(key >> 32);
+    const uint32_t bits = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;    // inverse of ordered_f32
+    DevHit h;
+    h.tmpl = t; h.y = (int)(idx / (uint32_t)tm.mw); h.x = (int)(idx - (uint32_t)h.y * (uint32_t)tm.mw);
+    h.w = tm.w; h.h = tm.h; h.score = __uint_as_float(bits); h.seq = t; h.key = 0.f;
+    hits[t] = h;
+}
+
 __global__ void argbest_kernel(const TmplMeta* __restrict__ meta, const float* __restrict__ maps,
                                int minimize, unsigned long long* __restrict__ best)
 {
@@ -216,6 +295,14 @@ int launch_peaks(mtm_ctx* ctx, int method, int64_t n_object, float thr32, double
     const int bx_cap = ctx->sm_count * 8;
     if (bx > bx_cap) bx = bx_cap;
     if (bx < 1) bx = 1;
+    if (n_object == 1 && ctx->best_valid) {                  // hits-only search: the numerator kernels' epilogues found the arg-max
+        emit_best_keys_kernel<<<(nt + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_meta, nt, ctx->d_best, ctx->hitsA(), ctx->countA());
+        MTM_LAUNCH_CHECK(ctx);
+        return MTM_OK;
+    }
+    const bool listed = allow_candidates && ctx->cand_valid && ctx->cand_thr == thr32 && !minimize && n_object != 1;
+    if (!ctx->maps_resident && !listed)
+        return mtm_fail(ctx, MTM_ERR_INVALID, "internal: the peak search needs score maps that this search did not write");
     if (n_object == 1) {
         MTM_CUDA(ctx, cudaMemsetAsync(ctx->d_best, 0, nt * sizeof(unsigned long long), ctx->stream));
         argbest_kernel<<<dim3(bx, nt), 256, 0, ctx->stream>>>(ctx->d_meta, ctx->d_maps, minimize, ctx->d_best);
@@ -225,7 +312,14 @@ int launch_peaks(mtm_ctx* ctx, int method, int64_t n_object, float thr32, double
         MTM_LAUNCH_CHECK(ctx);
         return MTM_OK;
     }
-    if (allow_candidates && ctx->cand_valid && ctx->cand_thr == thr32 && !minimize) {
+    if (listed && !ctx->maps_resident) {
+        // hits-only search: 3x3 maxima resolved inside the list of above-threshold pixels
+        resolve_candidates_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_meta, nt, ctx->d_cand, ctx->d_cand_count, MTM_CAND_CAP, ctx->d_hkeys,
+                                                              ctx->d_hvals, ctx->hitsA(), ctx->hit_cap, ctx->countA(), ctx->d_nontrivial);
+        MTM_LAUNCH_CHECK(ctx);
+        return MTM_OK;
+    }
+    if (listed) {
         // the epilogue of the numerator kernel already listed every pixel above the threshold
         verify_candidates_kernel<<<64, 256, 0, ctx->stream>>>(ctx->d_meta, nt, ctx->d_maps, ctx->d_cand, ctx->d_cand_count,
                                                              MTM_CAND_CAP, ctx->hitsA(), ctx->hit_cap, ctx->countA(),

@@ -81,7 +81,25 @@ static inline long long max(long long a, int b) { return a > b ? a : (long long)
 static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+// __byte_perm(x, y, s): byte i of the result is byte (s >> 4i) & 7 of the 8-byte value {y, x}; selector bit 3 replicates its sign bit
+static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s)
+{
+    const unsigned long long v = ((unsigned long long)y << 32) | x;
+    unsigned out = 0;
+    for (int i = 0; i < 4; ++i) {
+        const unsigned sel = (s >> (4 * i)) & 15u;
+        unsigned b = (unsigned)(v >> (8 * (sel & 7u))) & 255u;
+        if (sel & 8u) b = (b & 128u) ? 255u : 0u;
+        out |= b << (8 * i);
+    }
+    return out;
+}
 static inline int atomicOr(int* p, int v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned long long atomicCAS(unsigned long long* p, unsigned long long expected, unsigned long long desired)
+{
+    __atomic_compare_exchange_n(p, &expected, desired, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+    return expected;                                                   // the value found, as CUDA's atomicCAS returns it
+}
 static inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v)
 {
     unsigned long long old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
@@ -201,6 +219,7 @@ template <typename T> static inline T emu_exchange(T v, int src_lane)
 }
 template <typename T> static inline T __shfl_down_sync(unsigned, T v, int d) { return emu_exchange(v, emu_lane + d < 32 ? emu_lane + d : -1); }
 template <typename T> static inline T __shfl_up_sync(unsigned, T v, int d) { return emu_exchange(v, emu_lane - d); }
+template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int d) { return emu_exchange(v, emu_lane ^ d); }
 template <typename T> static inline T __shfl_sync(unsigned, T v, int lane) { return emu_exchange(v, lane & 31); }
 static inline unsigned __ballot_sync(unsigned, int pred)
 {

@@ -243,6 +243,15 @@ extern "C" int emu_box_moments(const uint8_t* img, int64_t pitch, int C, const S
         const int strip_out = (BM_COLS - (sizes[k].w - 1)) & ~3;
         strips = std::max(strips, (sizes[k].mw + strip_out - 1) / strip_out);
     }
+    if (C == 1 && bands < 0) {                              // the throughput form of the single-channel kernel (strips of 2048 columns)
+        int strips1 = 1;
+        for (int k = 0; k < n_sizes; ++k) {
+            const int strip_out = (B1_COLS - (sizes[k].w - 1)) & ~7;
+            strips1 = std::max(strips1, (sizes[k].mw + strip_out - 1) / strip_out);
+        }
+        emu_launch_coop(dim3(strips1, -bands, n_sizes), dim3(B1_THREADS), [&] { box_moments_c1_kernel(p); });
+        return strips1;
+    }
     const dim3 grid(strips, bands, n_sizes), block(BM_THREADS);
     if (C == 1) emu_launch_coop(grid, block, [&] { box_moments_kernel<1>(p); });
     else if (C == 3) emu_launch_coop(grid, block, [&] { box_moments_kernel<3>(p); });
@@ -870,18 +879,21 @@ def test_box_sum_moment_kernel_equals_the_summed_area_one(emu, channels, shape, 
         sizes[k] = (h, w, H - h + 1, W - w + 1, total)
         total += ((H - h + 1) * (W - w + 1) + 31) // 32 * 32
     outs = []
-    for box in (0, 1):
+    for box in (0, 1, 2):                                                      # summed-area kernel, generic box kernel, throughput form (C == 1)
+        if box == 2 and channels != 1:
+            continue
         S = np.full(total * max(2, channels), 0xDEADBEEF, np.uint32)
         R = np.full(total, -1.0, np.float32)
         if box:
             assert emu.emu_box_moments(_ptr(buf), ctypes.c_int64(ipitch), channels, _ptr(sizes), len(sizes), _ptr(S), _ptr(R),
-                                       ctypes.c_int64(total), bands) >= 1
+                                       ctypes.c_int64(total), bands if box == 1 else -bands) >= 1
         else:
             emu.emu_moments(0, _ptr(sat_s), _ptr(sat_q), ctypes.c_int64(pitch), ctypes.c_int64(plane), _ptr(sizes), len(sizes), channels,
                             _ptr(S), _ptr(R), ctypes.c_int64(total), 3, 1)
         outs.append((S, R))
-    assert np.array_equal(outs[0][0], outs[1][0])
-    assert np.array_equal(outs[0][1].view(np.uint32), outs[1][1].view(np.uint32))
+    for other in outs[1:]:
+        assert np.array_equal(outs[0][0], other[0])
+        assert np.array_equal(outs[0][1].view(np.uint32), other[1].view(np.uint32))
     h, w = windows[0]
     first = outs[1][0][64] if channels > 1 else outs[1][0][2 * 64]
     assert int(first) == int(wide[:h, :w, 0].sum())
