@@ -270,7 +270,11 @@ box_moments_c1_kernel(const BoxParams p)
             if (xl >= strip_out || x0 + xl >= sd.mw) continue;
             const int xr = xl + sd.w;                               // segment j or later (w may span several)
             const uint2 lo = P[buf][xl], hi = P[buf][xr];
-            const uint2 hb = wb[xr >> 8];
+            uint2 hb = wb[j];                                       // xr lies in segment j .. j+4 (w <= 1024): selects, no indexed register array
+            const int seg = xr >> 8;
+#pragma unroll
+            for (int k = 1; k <= 4; ++k)
+                if (j + k <= B1_WARPS && seg == j + k) hb = wb[j + k];
             const uint32_t s = (hi.x + hb.x) - (lo.x + wb[j].x);
             const uint32_t qs = (hi.y + hb.y) - (lo.y + wb[j].y);
             const unsigned long long d1 = (unsigned long long)area * qs - (unsigned long long)s * s;
@@ -329,8 +333,9 @@ int launch_box_moments(mtm_ctx* ctx)
             const int strip_out = (B1_COLS - (sd.w - 1)) & ~7;
             strips1 = std::max(strips1, (sd.mw + strip_out - 1) / strip_out);
         }
+        // bands: enough CTAs for three per SM, but a band keeps at least 8 output rows (it first re-adds the h-1 rows above it)
         const int want = 3 * ctx->sm_count;
-        const int bands1 = std::max(1, std::min(std::max(1, mh / 64), (want + strips1 * n_sizes - 1) / (strips1 * n_sizes)));
+        const int bands1 = std::max(1, std::min(std::max(1, mh / 8), (want + strips1 * n_sizes - 1) / (strips1 * n_sizes)));
         const dim3 grid1((unsigned)strips1, (unsigned)bands1, (unsigned)n_sizes);
         box_moments_c1_kernel<<<grid1, B1_THREADS, 0, ctx->stream>>>(p);
         MTM_LAUNCH_CHECK(ctx);

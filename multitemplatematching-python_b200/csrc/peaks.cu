@@ -195,24 +195,26 @@ resolve_candidates_kernel(const TmplMeta* __restrict__ meta, int n_tmpl, DevHit*
     for (int i = tid; i < n; i += blockDim.x) {
         const DevHit c = cand[i];
         const TmplMeta& tm = meta[c.tmpl];
+        // the eight first probes are independent loads (one round trip); collisions continue one by one
+        unsigned long long want[8], found[8];
+        uint32_t slot_of[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int dy = (q < 3) ? -1 : (q < 5 ? 0 : 1);
+            const int dx = (q < 3) ? q - 1 : (q == 3 ? -1 : (q == 4 ? 1 : q - 6));
+            const int yy = c.y + dy, xx = c.x + dx;
+            const bool inside = yy >= 0 && yy < tm.mh && xx >= 0 && xx < tm.mw;
+            want[q] = inside ? (((unsigned long long)(uint32_t)c.tmpl << 32) | (uint32_t)(yy * tm.mw + xx)) : EMPTY;
+            slot_of[q] = cand_hash(want[q]);
+            found[q] = inside ? hkeys[slot_of[q]] : EMPTY;
+        }
         bool is_max = true;
 #pragma unroll
-        for (int dy = -1; dy <= 1; ++dy) {
-            const int yy = c.y + dy;
-            if (yy < 0 || yy >= tm.mh) continue;
-#pragma unroll
-            for (int dx = -1; dx <= 1; ++dx) {
-                const int xx = c.x + dx;
-                if (xx < 0 || xx >= tm.mw || (dx == 0 && dy == 0)) continue;
-                const unsigned long long key = ((unsigned long long)(uint32_t)c.tmpl << 32) | (uint32_t)(yy * tm.mw + xx);
-                uint32_t h = cand_hash(key);
-                for (;;) {
-                    const unsigned long long k = hkeys[h];
-                    if (k == EMPTY) break;                               // not listed: its score is at most the threshold
-                    if (k == key) { if (cand[hvals[h]].score > c.score) is_max = false; break; }
-                    h = (h + 1) & (MTM_HASH_SLOTS - 1);
-                }
-            }
+        for (int q = 0; q < 8; ++q) {
+            unsigned long long k = found[q];
+            uint32_t h = slot_of[q];
+            while (k != EMPTY && k != want[q]) { h = (h + 1) & (MTM_HASH_SLOTS - 1); k = hkeys[h]; }
+            if (k != EMPTY && cand[hvals[h]].score > c.score) is_max = false;      // an empty slot: not listed, its score is at most the threshold
         }
         if (is_max) {
             const int slot = atomicAdd(count, 1);

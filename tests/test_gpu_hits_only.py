@@ -46,7 +46,8 @@ def test_hits_only_equals_the_map_route(mtm, channels):
         before = ctx.counters()["hits_only_searches"]
         got_find = mtm.findMatches(temps, scene, score_threshold=thr, N_object=nobj)
         got = mtm.matchTemplates(temps, scene, score_threshold=thr, maxOverlap=overlap, N_object=nobj)
-        assert ctx.counters()["hits_only_searches"] == before + 2, "the search did not take the hits-only kernels"
+        # (>=: a hit list longer than the binding's buffer makes it repeat the call with a larger one)
+        assert ctx.counters()["hits_only_searches"] >= before + 2, "the search did not take the hits-only kernels"
         want_find, want = _from_own_maps(mtm, temps, scene, thr, overlap, nobj)
         assert [(g[0], g[1]) for g in got_find] == [(w[0], w[1]) for w in want_find], (thr, nobj)
         assert all(g[2] == w[2] for g, w in zip(got_find, want_find))
