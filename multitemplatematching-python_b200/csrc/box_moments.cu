@@ -32,9 +32,10 @@ constexpr int BM_ROW = BM_COLS + 4;                    // prefix row in shared m
 
 struct BoxParams {
     const uint8_t* img; int64_t pitch;                 // zero-padded u8 rows, interleaved channels
-    const SizeDesc* sizes;                             // blockIdx.z -> (h, w, mh, mw, offset of its maps)
-    uint32_t* S; float* rsD;                           // window_moments_kernel's layout
+    const SizeDesc* sizes;                             // blockIdx.z -> (h, w, mh, mw, ring segment, rows per band) of the launch's sizes
+    uint32_t* S; float* rsD;                           // the moment ring (tile-major segments, mtm_internal.cuh)
     int64_t mom_plane;
+    int y_begin, rows;                                 // output rows [y_begin, y_begin + rows) of every size (clipped to its map)
 };
 
 template <int C>
@@ -46,10 +47,11 @@ box_moments_kernel(const BoxParams p)
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const SizeDesc sd = p.sizes[blockIdx.z];
     const int strip_out = (BM_COLS - (sd.w - 1)) & ~3; // window positions per strip: a multiple of 4 (aligned loads)
-    const int band = (sd.mh + (int)gridDim.y - 1) / (int)gridDim.y;
+    const int y_end = min(sd.mh, p.y_begin + p.rows);  // rows of this launch that exist for this size
+    const int band = (max(y_end - p.y_begin, 0) + (int)gridDim.y - 1) / (int)gridDim.y;
     const int x0 = blockIdx.x * strip_out;             // first image column of the strip == its first window position
-    const int y0 = blockIdx.y * band, y1 = min(sd.mh, y0 + band);
-    if (x0 >= sd.mw || y0 >= sd.mh) return;            // the grid is sized for the largest map of the launch
+    const int y0 = p.y_begin + blockIdx.y * band, y1 = min(y_end, y0 + band);
+    if (x0 >= sd.mw || y0 >= y_end) return;            // the grid is sized for the largest map of the launch
     const int64_t col_byte = ((int64_t)x0 + BM_PX * tid) * C;      // a multiple of 4: strip_out and BM_PX are
     uint32_t V[C + 1][BM_PX];
 #pragma unroll
@@ -130,12 +132,12 @@ box_moments_kernel(const BoxParams p)
         }
         __syncthreads();
         // window positions tid, tid + 256, ... of the strip: conflict-free shared-memory reads, coalesced stores
-        const int64_t out_row = sd.off + (int64_t)y * sd.mw;
 #pragma unroll
         for (int j = 0; j < BM_PX; ++j) {
             const int xl = tid + j * BM_THREADS;
             const int x = x0 + xl;
             if (xl >= strip_out || x >= sd.mw) continue;
+            const int64_t out_idx = sd.off + mom_index(x, y - p.y_begin, sd.band);
             const uint32_t qs = P[buf][C][xl + sd.w] - P[buf][C][xl];
             unsigned long long d1 = (unsigned long long)area * qs;
             uint32_t s0 = 0;
@@ -143,12 +145,12 @@ box_moments_kernel(const BoxParams p)
             for (int c = 0; c < C; ++c) {
                 const uint32_t s = P[buf][c][xl + sd.w] - P[buf][c][xl];
                 d1 -= (unsigned long long)s * s;
-                if (C > 1) p.S[c * p.mom_plane + out_row + x] = s;
+                if (C > 1) p.S[c * p.mom_plane + out_idx] = s;
                 s0 = s;
             }
             const float rs = d1 ? rsqrtf((float)d1) : 0.0f;
-            if (C > 1) p.rsD[out_row + x] = rs;
-            else reinterpret_cast<uint2*>(p.S)[out_row + x] = make_uint2(s0, __float_as_uint(rs));
+            if (C > 1) p.rsD[out_idx] = rs;
+            else reinterpret_cast<uint2*>(p.S)[out_idx] = make_uint2(s0, __float_as_uint(rs));
         }
         accumulate(w_out, true);
         if (more) {
@@ -180,11 +182,12 @@ box_moments_c1_kernel(const BoxParams p)
     __shared__ uint2 wtot[2][B1_WARPS];                // the warps' totals
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const SizeDesc sd = p.sizes[blockIdx.z];
-    const int strip_out = (B1_COLS - (sd.w - 1)) & ~7;
-    const int band = (sd.mh + (int)gridDim.y - 1) / (int)gridDim.y;
+    const int strip_out = (B1_COLS - (sd.w - 1)) & ~15;             // a multiple of 16: strips start on a tile column of the ring
+    const int y_end = min(sd.mh, p.y_begin + p.rows);
+    const int band = (max(y_end - p.y_begin, 0) + (int)gridDim.y - 1) / (int)gridDim.y;
     const int x0 = blockIdx.x * strip_out;
-    const int y0 = blockIdx.y * band, y1 = min(sd.mh, y0 + band);
-    if (x0 >= sd.mw || y0 >= sd.mh) return;
+    const int y0 = p.y_begin + blockIdx.y * band, y1 = min(y_end, y0 + band);
+    if (x0 >= sd.mw || y0 >= y_end) return;
     const int64_t col_byte = (int64_t)x0 + B1_PX * tid;            // a multiple of 8
     const bool in_row = col_byte + 8 <= p.pitch;                    // beyond the padded row: no pixels
     const uint8_t* col = p.img + col_byte;
@@ -263,7 +266,8 @@ box_moments_c1_kernel(const BoxParams p)
         wb[0] = make_uint2(0u, 0u);
 #pragma unroll
         for (int k = 0; k < B1_WARPS; ++k) { const uint2 t = wtot[buf][k]; wb[k + 1] = make_uint2(wb[k].x + t.x, wb[k].y + t.y); }
-        uint2* out_row = out_base + (int64_t)y * sd.mw + x0;
+        // ring entry of (x0 + xl, y): ((x >> 4) * band + r) * 16 + (x & 15); x0 is a multiple of 16, so x & 15 == xl & 15
+        uint2* out_row = out_base + ((int64_t)(x0 >> 4) * sd.band + (y - p.y_begin)) * 16;
 #pragma unroll
         for (int j = 0; j < B1_PX; ++j) {
             const int xl = tid + j * B1_THREADS;                    // segment j
@@ -279,7 +283,7 @@ box_moments_c1_kernel(const BoxParams p)
             const uint32_t qs = (hi.y + hb.y) - (lo.y + wb[j].y);
             const unsigned long long d1 = (unsigned long long)area * qs - (unsigned long long)s * s;
             const float rs = d1 ? rsqrtf((float)d1) : 0.0f;
-            out_row[xl] = make_uint2(s, __float_as_uint(rs));
+            out_row[(int64_t)(xl >> 4) * sd.band * 16 + (xl & 15)] = make_uint2(s, __float_as_uint(rs));
         }
         sub_row(w_out);
         w_in = n_in; w_out = n_out;
@@ -309,29 +313,32 @@ bool box_moments_applicable(const mtm_ctx* ctx)
     return true;
 }
 
-// ctx->d_sizes holds ctx->h_sizes (ensure_moments).
-int launch_box_moments(mtm_ctx* ctx)
+// ctx->d_sizes holds ctx->h_sizes (ensure_geometry).  Sizes [size_first, size_first + size_count), output rows [y_begin, y_begin + rows).
+int launch_box_moments(mtm_ctx* ctx, int size_first, int size_count, int y_begin, int rows)
 {
     const ImageDev& im = ctx->img;
     BoxParams p{};
-    p.img = im.pix; p.pitch = im.pitch; p.sizes = ctx->d_sizes;
+    p.img = im.pix; p.pitch = im.pitch; p.sizes = ctx->d_sizes + size_first;
     p.S = ctx->d_wS; p.rsD = ctx->d_wR; p.mom_plane = ctx->moments_total;
+    p.y_begin = y_begin; p.rows = rows;
+    const SizeDesc* sizes = ctx->h_sizes.data() + size_first;
     int strips = 1, mh = 1;
-    for (const SizeDesc& sd : ctx->h_sizes) {
+    for (int q = 0; q < size_count; ++q) {
+        const SizeDesc& sd = sizes[q];
         const int strip_out = (BM_COLS - (sd.w - 1)) & ~3;
         strips = std::max(strips, (sd.mw + strip_out - 1) / strip_out);
-        mh = std::max(mh, sd.mh);
+        mh = std::max(mh, std::min(sd.mh, y_begin + rows) - y_begin);
     }
-    const int n_sizes = (int)ctx->h_sizes.size();
+    const int n_sizes = size_count;
     static const bool generic_only = getenv("MTM_B200_BOX_GENERIC") != nullptr;      // A/B runs
     bool lanes16 = true;                               // the throughput form keeps column sums in 16-bit lanes: 255 * h < 2^16
-    for (const SizeDesc& sd : ctx->h_sizes) lanes16 = lanes16 && sd.h <= 257 && sd.w <= B1_COLS / 2;
+    for (int q = 0; q < size_count; ++q) lanes16 = lanes16 && sizes[q].h <= 257 && sizes[q].w <= B1_COLS / 2;
     if (im.C == 1 && !generic_only && lanes16) {
         // throughput form: strips of 2048 columns, about three resident CTAs per SM in total
         int strips1 = 1;
-        for (const SizeDesc& sd : ctx->h_sizes) {
-            const int strip_out = (B1_COLS - (sd.w - 1)) & ~7;
-            strips1 = std::max(strips1, (sd.mw + strip_out - 1) / strip_out);
+        for (int q = 0; q < size_count; ++q) {
+            const int strip_out = (B1_COLS - (sizes[q].w - 1)) & ~15;
+            strips1 = std::max(strips1, (sizes[q].mw + strip_out - 1) / strip_out);
         }
         // bands: enough CTAs for three per SM, but a band keeps at least 8 output rows (it first re-adds the h-1 rows above it)
         const int want = 3 * ctx->sm_count;

@@ -64,6 +64,26 @@ static int harvest_ncc_time(mtm_ctx* ctx, bool all)
     return MTM_OK;
 }
 
+// MTM_OPT_TIME_NCC: an event bracket around a run of numerator launches (closed and reopened around anything else that is
+// queued in between, e.g. the window moments of the next band).
+static int ncc_bracket_open(mtm_ctx* ctx)
+{
+    if (!ctx->time_ncc) return MTM_OK;
+    MTM_TRY(harvest_ncc_time(ctx, false));
+    MTM_CUDA(ctx, cudaEventRecord(ctx->ev_ncc[ctx->ncc_head % MTM_NCC_RING][0], ctx->stream));
+    ctx->ncc_mark = ctx->ctr.kernel_launches;
+    return MTM_OK;
+}
+static int ncc_bracket_close(mtm_ctx* ctx)
+{
+    if (!ctx->time_ncc) return MTM_OK;
+    const int k = ctx->ncc_head % MTM_NCC_RING;
+    MTM_CUDA(ctx, cudaEventRecord(ctx->ev_ncc[k][1], ctx->stream));
+    ctx->ncc_launches_of[k] = (int)(ctx->ctr.kernel_launches - ctx->ncc_mark);
+    ctx->ncc_head++;
+    return MTM_OK;
+}
+
 // Debug aid (MTM_B200_STAGES=1): CUDA events between the stages of a call, printed at its end.
 struct StageMarks {
     std::vector<std::pair<const char*, cudaEvent_t>> ev;
@@ -400,18 +420,60 @@ int ensure_geometry(mtm_ctx* ctx)
     }
     ctx->maps_total = off;
     ctx->moments_valid = false;
-    // window-moment maps: one pair per distinct size, in (h, w)-sorted order
+    // Window moments: the distinct sizes in (h, w)-sorted order.  They are produced per template group and per band of
+    // output rows into a ring that every group and band reuses (mtm_internal.cuh, SizeDesc): offsets are per group.
     ctx->h_sizes.clear();
-    int64_t moff = 0;
+    std::vector<int> size_of((size_t)n, 0);
     for (int k = 0; k < n; ++k) {
-        TmplMeta& m = ctx->h_meta[ctx->h_order[k]];
-        if (ctx->h_sizes.empty() || ctx->h_sizes.back().h != m.h || ctx->h_sizes.back().w != m.w) {
-            ctx->h_sizes.push_back(SizeDesc{m.h, m.w, m.mh, m.mw, moff});
-            moff += ((int64_t)m.mh * m.mw + 31) / 32 * 32;
-        }
-        m.mom_off = ctx->h_sizes.back().off;
+        const TmplMeta& m = ctx->h_meta[ctx->h_order[k]];
+        if (ctx->h_sizes.empty() || ctx->h_sizes.back().h != m.h || ctx->h_sizes.back().w != m.w)
+            ctx->h_sizes.push_back(SizeDesc{m.h, m.w, m.mh, m.mw, 0, m.mh, 0});
+        size_of[k] = (int)ctx->h_sizes.size() - 1;
     }
-    ctx->moments_total = moff;
+    ctx->moments_total = 0;
+    ctx->box_ok = false;
+    if (ctx->tc_ready && ctx->img_dtype == MTM_U8) {
+        // box sums straight from the image (banded) unless some input rules them out: then the summed-area route, whole maps
+        bool box = box_moments_enabled() && box_moments_applicable(ctx);
+        for (const TcGroup& g : ctx->tc_groups) box = box && !points_path_preferred(ctx, g.first, g.count);
+        ctx->box_ok = box;
+        // ring budget: 48 MB (the 126 MB L2 also holds the image, the Toeplitz slabs and the candidate list); MTM_B200_RING_KB
+        // overrides it (read at every geometry change: the tests force many bands on small images with it)
+        const char* ring_env = getenv("MTM_B200_RING_KB");
+        const int64_t ring_bytes = ring_env ? (int64_t)std::max(1, atoi(ring_env)) << 10 : (int64_t)48 << 20;
+        const int64_t entry_bytes = ctx->img.C == 1 ? 8 : 4 * (ctx->img.C + 1);
+        for (TcGroup& g : ctx->tc_groups) {
+            g.size_first = size_of[g.first];
+            g.size_count = size_of[g.first + g.count - 1] - g.size_first + 1;
+            int mh_max = 1;
+            int64_t per_row = 0;
+            for (int q = 0; q < g.size_count; ++q) {
+                const SizeDesc& sd = ctx->h_sizes[g.size_first + q];
+                mh_max = std::max(mh_max, sd.mh);
+                per_row += (int64_t)((sd.mw + 15) >> 4) * 16;
+            }
+            int band = mh_max;
+            const int64_t rows_budget = std::max<int64_t>(16, ring_bytes / entry_bytes / per_row);
+            if (box && rows_budget < mh_max) {                  // several bands of (nearly) equal height, multiples of 16 rows
+                const int bands = (int)((mh_max + rows_budget - 1) / rows_budget);
+                band = (((mh_max + bands - 1) / bands) + 15) & ~15;
+            }
+            g.band_rows = band;
+            int64_t moff = 0;
+            for (int q = 0; q < g.size_count; ++q) {
+                SizeDesc& sd = ctx->h_sizes[g.size_first + q];
+                sd.off = moff; sd.band = band;
+                moff += mom_segment(sd.mw, band);
+            }
+            ctx->moments_total = std::max(ctx->moments_total, moff);
+        }
+        MTM_TRY(mtm_reserve(ctx, ctx->d_wS, ctx->wS_cap, (size_t)ctx->moments_total * std::max(2, ctx->img.C)));   // C == 1: interleaved {S, rsD}
+        MTM_TRY(mtm_reserve(ctx, ctx->d_wR, ctx->wR_cap, (size_t)ctx->moments_total));
+        MTM_TRY(mtm_reserve(ctx, ctx->d_sizes, ctx->sizes_cap, ctx->h_sizes.size()));
+        MTM_CUDA(ctx, cudaMemcpyAsync(ctx->d_sizes, ctx->h_sizes.data(), ctx->h_sizes.size() * sizeof(SizeDesc),
+                                      cudaMemcpyHostToDevice, ctx->stream));      // pageable source: staged before returning
+    }
+    for (int k = 0; k < n; ++k) ctx->h_meta[ctx->h_order[k]].mom_off = ctx->h_sizes[size_of[k]].off;
     for (int t = 0; t < n; ++t) {
         const TmplMeta& m = ctx->h_meta[t];
         ctx->h_geom[t].map_off = m.map_off; ctx->h_geom[t].mh = m.mh; ctx->h_geom[t].mw = m.mw; ctx->h_geom[t].mom_off = m.mom_off;
@@ -491,21 +553,6 @@ static int plan_tensor_path(mtm_ctx* ctx)
     MTM_TRY(mtm_reserve(ctx, ctx->d_slabs, ctx->slabs_cap, (size_t)(planes16 ? 2 : 1) * ctx->slab_plane + 128));
     for (const TcGroup& g : ctx->tc_groups) MTM_TRY(launch_toeplitz_prep(ctx, g));
     ctx->tc_ready = true;
-    return MTM_OK;
-}
-
-// Window moments (S, rsqrt(A*Q - S^2)) for every distinct template size; image-dependent.
-static int ensure_moments(mtm_ctx* ctx, bool box)
-{
-    if (ctx->moments_valid) return MTM_OK;
-    MTM_TRY(mtm_reserve(ctx, ctx->d_wS, ctx->wS_cap, (size_t)ctx->moments_total * std::max(2, ctx->img.C)));   // C == 1: interleaved {S, rsD}
-    MTM_TRY(mtm_reserve(ctx, ctx->d_wR, ctx->wR_cap, (size_t)ctx->moments_total));
-    MTM_TRY(mtm_reserve(ctx, ctx->d_sizes, ctx->sizes_cap, ctx->h_sizes.size()));
-    MTM_CUDA(ctx, cudaMemcpyAsync(ctx->d_sizes, ctx->h_sizes.data(), ctx->h_sizes.size() * sizeof(SizeDesc),
-                                  cudaMemcpyHostToDevice, ctx->stream));
-    if (box) MTM_TRY(launch_box_moments(ctx));             // straight from the image, same bits
-    else MTM_TRY(launch_window_moments(ctx));
-    ctx->moments_valid = true;
     return MTM_OK;
 }
 
@@ -602,17 +649,12 @@ int compute_maps(mtm_ctx* ctx, int method, int tmpl, bool hits_ok)
     if (ctx->img_dtype == MTM_U8) {
         // Everything but the default method's tensor-core epilogue reads the summed-area tables; under MTM_B200_MOM_BOX the
         // window moments come from the image instead (box_moments.cu) and the tables are not built for such a call.
-        bool box = box_moments_enabled() && tensor && method == MTM_TM_CCOEFF_NORMED && box_moments_applicable(ctx);
-        for (const TcGroup& g : ctx->tc_groups) box = box && !points_path_preferred(ctx, g.first, g.count);
+        // window moments: banded box sums (ctx->box_ok, ensure_geometry) or, when some input rules those out, the tables
+        const bool box = ctx->box_ok && tensor && method == MTM_TM_CCOEFF_NORMED;
         if (!box) MTM_TRY(ensure_sat(ctx));
-        if (tensor && method == MTM_TM_CCOEFF_NORMED) MTM_TRY(ensure_moments(ctx, box));   // the other methods read the tables directly
     }
     if (tensor16) { MTM_TRY(mtm_reserve(ctx, ctx->d_acc, ctx->acc_cap, (size_t)ctx->maps_total)); ctx->cand_on = false; }
-    const int64_t launches_before = ctx->ctr.kernel_launches;
-    if (ctx->time_ncc) {
-        MTM_TRY(harvest_ncc_time(ctx, false));
-        MTM_CUDA(ctx, cudaEventRecord(ctx->ev_ncc[ctx->ncc_head % MTM_NCC_RING][0], ctx->stream));
-    }
+    MTM_TRY(ncc_bracket_open(ctx));
     ctx->cand_valid = false;
     if (ctx->cand_on) MTM_CUDA(ctx, cudaMemsetAsync(ctx->d_cand_count, 0, sizeof(int32_t), ctx->stream));
     if (tensor) {
@@ -630,8 +672,19 @@ int compute_maps(mtm_ctx* ctx, int method, int tmpl, bool hits_ok)
                 MTM_TRY(launch_ncc_tc_accum(ctx, g, 1, 1, 1.0, false));
             } else if (points_path_preferred(ctx, g.first, g.count)) {
                 MTM_TRY(launch_ncc_points(ctx, method, g.first, g.count));          // tiny maps of large templates
+            } else if (method != MTM_TM_CCOEFF_NORMED) {
+                MTM_TRY(launch_ncc_tc(ctx, g, method, 0, ctx->img.H - g.h_min + 1));       // float64 epilogue on the tables: no moments
             } else {
-                MTM_TRY(launch_ncc_tc(ctx, g, method));
+                // default method: the group's window moments band by band (ring in L2), each band followed by its numerator launch
+                const int mh_max = ctx->img.H - g.h_min + 1;
+                for (int y_base = 0; y_base < mh_max; y_base += g.band_rows) {
+                    const int rows = std::min(g.band_rows, mh_max - y_base);
+                    MTM_TRY(ncc_bracket_close(ctx));               // the moments are not numerator time
+                    if (ctx->box_ok) MTM_TRY(launch_box_moments(ctx, g.size_first, g.size_count, y_base, rows));
+                    else MTM_TRY(launch_window_moments(ctx, g.size_first, g.size_count));
+                    MTM_TRY(ncc_bracket_open(ctx));
+                    MTM_TRY(launch_ncc_tc(ctx, g, method, y_base, rows));
+                }
             }
         }
         if (tensor16) MTM_TRY(launch_cc16_epilogue(ctx, method, tmpl));
@@ -660,12 +713,7 @@ int compute_maps(mtm_ctx* ctx, int method, int tmpl, bool hits_ok)
         }
         i = j;
     }
-    if (ctx->time_ncc) {
-        const int k = ctx->ncc_head % MTM_NCC_RING;
-        MTM_CUDA(ctx, cudaEventRecord(ctx->ev_ncc[k][1], ctx->stream));
-        ctx->ncc_launches_of[k] = (int)(ctx->ctr.kernel_launches - launches_before);
-        ctx->ncc_head++;
-    }
+    MTM_TRY(ncc_bracket_close(ctx));
     return MTM_OK;
 }
 

@@ -8,7 +8,7 @@
 #include "../../include/mtm_b200.h"
 
 #define MTM_MAX_CH 4
-#define MTM_NCC_RING 16
+#define MTM_NCC_RING 256     // event brackets of MTM_OPT_TIME_NCC in flight (a banded search opens one per band)
 #define MTM_CAND_CAP 32768      // above-threshold pixels the tensor-core epilogue may list per call
 #define MTM_HASH_SLOTS (1 << 17) // slots of the candidate hash table (load factor <= 1/4)
 #define MTM_SLOT_HITS 1024      // hits a slot of the asynchronous API can return (== the fused fast path)
@@ -65,11 +65,18 @@ struct XformDesc {
     int32_t op, pad;      // mtm_transform
 };
 
-// One distinct template size: where its window-moment maps live (window_moments_kernel, batched).
+// One distinct template size: where its window moments live.  Moments are produced per template group and per BAND of output
+// rows, into a ring the next band overwrites (it stays in L2: the moment stage writes to DRAM only what the cache evicts).  A
+// size's segment holds `band` rows in tile-major order, the order the tcgen05 epilogue reads them in:
+//     entry(x, r) = ((x >> 4) * band + r) * 16 + (x & 15),   r = y - first row of the band
+// i.e. the 16 x-offsets of a tile column are one 128-byte line and consecutive rows follow each other 128 bytes apart.
 struct SizeDesc {
     int32_t h, w, mh, mw;
-    int64_t off;
+    int64_t off;          // element offset of the segment in the ring
+    int32_t band, pad;    // rows per band of this size's group
 };
+__host__ __device__ inline int64_t mom_index(int x, int r, int band) { return ((int64_t)(x >> 4) * band + r) * 16 + (x & 15); }
+__host__ __device__ inline int64_t mom_segment(int mw, int band) { return (int64_t)((mw + 15) >> 4) * 16 * band; }
 
 // One launch of the tcgen05 kernel: `count` templates d_order[first .. first+count); (h, w) is the
 // group's padded size (mode A may mix sizes: smaller templates are zero padded in the Toeplitz slabs).
@@ -80,6 +87,8 @@ struct TcGroup {
     size_t smem;
     int64_t arena_off;         // byte offset of the group's Toeplitz slabs in d_slabs
     int h_min, w_min;          // smallest member (largest score map): the tile grid covers its map
+    int size_first, size_count;// its distinct sizes: ctx->h_sizes[size_first .. size_first + size_count)   (ensure_geometry)
+    int band_rows;             // output rows per band of window moments (>= the largest member map: one band)
     double eff;
 };
 
@@ -110,6 +119,7 @@ struct mtm_ctx {
     cudaEvent_t ev_ncc[MTM_NCC_RING][2] = {};
     int ncc_launches_of[MTM_NCC_RING] = {};
     int time_ncc = 0, ncc_head = 0, ncc_tail = 0;       // [tail, head) are recorded but not yet folded into ctr
+    int64_t ncc_mark = 0;                               // kernel_launches when the open bracket began
     int sm_count = 0;
 
     // image
@@ -162,7 +172,8 @@ struct mtm_ctx {
     SizeDesc* d_sizes = nullptr; size_t sizes_cap = 0;
     uint32_t* d_wS = nullptr; size_t wS_cap = 0;         // window sums S
     float* d_wR = nullptr; size_t wR_cap = 0;            // rsqrt(A*Q - S^2)
-    bool moments_valid = false;
+    bool moments_valid = false;                          // (unused since the moments are produced per group and band)
+    bool box_ok = false;                                 // window moments by box sums straight from the image (banded); else summed-area tables
     bool tc_attr_set = false;
     bool tcp_attr_set = false;
 
@@ -268,12 +279,14 @@ int launch_masked_combine(mtm_ctx* ctx, int method, const float* mapsB);
 bool tc_path_supported(const mtm_ctx* ctx, int method, int h, int w);
 bool tc_plan_group(int mode, int h, int w, int C, TcGroup& g);
 int launch_toeplitz_prep(mtm_ctx* ctx, const TcGroup& g);
-int launch_window_moments(mtm_ctx* ctx);
+// window moments of the sizes h_sizes[size_first .. +size_count) for output rows [y_begin, y_begin + rows) -> the ring
+int launch_window_moments(mtm_ctx* ctx, int size_first, int size_count);          // summed-area route: whole maps only (one band)
 // experiment knob MTM_B200_MOM_BOX (box_moments.cu): the same moment maps from running box sums, without summed-area tables
 bool box_moments_enabled();
 bool box_moments_applicable(const mtm_ctx* ctx);
-int launch_box_moments(mtm_ctx* ctx);
-int launch_ncc_tc(mtm_ctx* ctx, const TcGroup& g, int method);
+int launch_box_moments(mtm_ctx* ctx, int size_first, int size_count, int y_begin, int rows);
+// rows [y_base, y_base + rows) of the group's score maps (rows counted on its largest map)
+int launch_ncc_tc(mtm_ctx* ctx, const TcGroup& g, int method, int y_base, int rows);
 int launch_i8_peak(mtm_ctx* ctx, int n, int iters);      // measurement helper: back-to-back kind::i8 MMAs, no loads, no epilogue
 // 16-bit path: one byte-plane product of the group accumulated into ctx->d_acc (img_plane / tmpl_plane: 0 = high, 1 = low bytes)
 int launch_ncc_tc_accum(mtm_ctx* ctx, const TcGroup& g, int img_plane, int tmpl_plane, double weight, bool first);

@@ -167,12 +167,13 @@ __device__ __forceinline__ void prefetch_l1(const void* ptr) { asm volatile("pre
 
 // Single channel: the window moments are interleaved {S, bits of rsqrt(A*Q - S^2)} so that one 8-byte load serves
 // a pixel.  `ahead` > 0: also pull the batch `ahead` rows further down into L1 (the next batch of this warp).
-__device__ __forceinline__ void prefetch_moments16(const uint2* __restrict__ SR, int y_first, int mh, int mw, int x)
+// (r_first: row inside the band; rows_avail: rows of the band that exist for this template; band: rows of the ring segment)
+__device__ __forceinline__ void prefetch_moments16(const uint2* __restrict__ SR, int r_first, int rows_avail, int band, int x)
 {
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-        const int y = min(y_first + k, mh - 1);
-        prefetch_l1(SR + (int64_t)y * mw + x);
+        const int r = min(r_first + k, rows_avail - 1);
+        prefetch_l1(SR + mom_index(x, r, band));
     }
 }
 
@@ -185,15 +186,16 @@ template <bool STORE>
 __device__ __forceinline__ void epilogue16(const uint32_t (&v)[16], int y_first, int mh, int mw, int x, long long area,
                                            long long sumT, float ct, bool is_const, const uint2* __restrict__ SR,
                                            float* __restrict__ out, const CandSink& sink, bool prefetch_next,
-                                           BestTrack& bt, bool track)
+                                           BestTrack& bt, bool track, int y_base, int band)
 {
+    // mh: first row that is NOT computed for this template in this launch (end of its map or of the band)
     uint2 m[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
         const int y = min(y_first + k, mh - 1);
-        m[k] = __ldg(SR + (int64_t)y * mw + x);
+        m[k] = __ldg(SR + mom_index(x, y - y_base, band));
     }
-    if (prefetch_next) prefetch_moments16(SR, y_first + 16, mh, mw, x);
+    if (prefetch_next) prefetch_moments16(SR, y_first + 16 - y_base, mh - y_base, band, x);
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
         const int y = y_first + k;
@@ -221,17 +223,18 @@ __device__ __forceinline__ void epilogue16(const uint32_t (&v)[16], int y_first,
 template <bool STORE>
 __device__ __forceinline__ void epilogue16_fast(const uint32_t (&v)[16], int y_first, int mw, int x, uint32_t area, uint32_t sumT,
                                                 float ct, const uint2* __restrict__ SR, float* __restrict__ out,
-                                                const CandSink& sink, float thr, bool prefetch_next, BestTrack& bt, bool track)
+                                                const CandSink& sink, float thr, bool prefetch_next, BestTrack& bt, bool track,
+                                                int y_base, int band)
 {
-    const uint2* sr = SR + (int64_t)y_first * mw + x;
+    const uint2* sr = SR + mom_index(x, y_first - y_base, band);       // consecutive rows: 16 entries = 128 bytes apart (immediate offsets)
     float* o = out + (int64_t)y_first * mw + x;
     const uint32_t idx0 = (uint32_t)(y_first * mw + x);
     uint2 m[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) m[k] = __ldg(sr + (uint32_t)(k * mw));
+    for (int k = 0; k < 16; ++k) m[k] = __ldg(sr + 16 * k);
     if (prefetch_next) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) prefetch_l1(sr + (uint32_t)((16 + k) * mw));
+        for (int k = 0; k < 16; ++k) prefetch_l1(sr + 16 * (16 + k));
     }
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
@@ -293,7 +296,8 @@ template <int C, bool STORE>
 __device__ __forceinline__ void epilogue16_mc(const uint32_t (&v)[16], int y_first, int mh, int mw, int x, long long area,
                                               const long long (&sumT)[MTM_MAX_CH], float ct, bool is_const,
                                               const uint32_t* __restrict__ S, int64_t plane, const float* __restrict__ rsD,
-                                              float* __restrict__ out, const CandSink& sink, BestTrack& bt, bool track)
+                                              float* __restrict__ out, const CandSink& sink, BestTrack& bt, bool track,
+                                              int y_base, int band)
 {
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
@@ -302,7 +306,7 @@ __device__ __forceinline__ void epilogue16_mc(const uint32_t (&v)[16], int y_fir
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const int y = min(y_first + 8 * half + k, mh - 1);
-            const int64_t o = (int64_t)y * mw + x;
+            const int64_t o = mom_index(x, y - y_base, band);
             rs[k] = __ldg(rsD + o);
 #pragma unroll
             for (int c = 0; c < C; ++c) sw[k][c] = __ldg(S + c * plane + o);
@@ -386,6 +390,7 @@ struct TcParams {
     int R;                            // image tile rows = N + h - 1 rounded up to 8 (tc_tile_rows)
     int tma, tma_rc, tma_chunks;      // image tiles through the TMA unit (tensor map = second kernel parameter): rows per box, boxes per k-block
     int h, w, mh, mw;
+    int y_base, rows, band_rows;      // this launch covers output rows [y_base, y_base + rows); band_rows: rows of the moment ring's segments
     const TmplMeta* meta; const int32_t* order; int count;
     const uint32_t* S; const float* rsD;   // window moments of this (h, w): [mh][mw]
     float* maps;
@@ -411,7 +416,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_d
     else { tsel = 0; x = x0 + 16 * (7 - (m >> 4)) + (m & 15); }
     // per-lane template geometry: a mode-A group may mix template sizes
     const TmplMeta* tm = (tsel < p.count) ? &p.meta[p.order[tsel]] : nullptr;
-    const int t_mh = tm ? tm->mh : 0, t_mw = tm ? tm->mw : 0;
+    const int t_mh = tm ? min(tm->mh, p.y_base + p.rows) : 0, t_mw = tm ? tm->mw : 0;     // rows end with the map or with the band
     const bool live = tm && (x < t_mw);
     const long long area = tm ? (long long)tm->h * tm->w : 0;
     const long long sumT = tm ? tm->isum[0] : 0;
@@ -445,11 +450,115 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_d
         }
         if (p.C == 1) {
             // the prefetched rows of the next batch must exist: +32
-            if (!is_const && y0 + c0 + 32 <= t_mh) epilogue16_fast<STORE>(v, y0 + c0, t_mw, x, (uint32_t)area, (uint32_t)sumT, ct, SRm, out, sink, thr_eff, c0 + 16 < c_end, bt, track);
-            else epilogue16<STORE>(v, y0 + c0, t_mh, t_mw, x, area, sumT, ct, is_const, SRm, out, sink, c0 + 16 < c_end, bt, track);
+            if (!is_const && y0 + c0 + 32 <= t_mh) epilogue16_fast<STORE>(v, y0 + c0, t_mw, x, (uint32_t)area, (uint32_t)sumT, ct, SRm, out, sink, thr_eff, c0 + 16 < c_end, bt, track, p.y_base, p.band_rows);
+            else epilogue16<STORE>(v, y0 + c0, t_mh, t_mw, x, area, sumT, ct, is_const, SRm, out, sink, c0 + 16 < c_end, bt, track, p.y_base, p.band_rows);
         }
-        else if (p.C == 3) epilogue16_mc<3, STORE>(v, y0 + c0, t_mh, t_mw, x, area, sumT_c, ct, is_const, Sm, p.mom_plane, Rm, out, sink, bt, track);
-        else epilogue16_mc<4, STORE>(v, y0 + c0, t_mh, t_mw, x, area, sumT_c, ct, is_const, Sm, p.mom_plane, Rm, out, sink, bt, track);
+        else if (p.C == 3) epilogue16_mc<3, STORE>(v, y0 + c0, t_mh, t_mw, x, area, sumT_c, ct, is_const, Sm, p.mom_plane, Rm, out, sink, bt, track, p.y_base, p.band_rows);
+        else epilogue16_mc<4, STORE>(v, y0 + c0, t_mh, t_mw, x, area, sumT_c, ct, is_const, Sm, p.mom_plane, Rm, out, sink, bt, track, p.y_base, p.band_rows);
+    }
+}
+
+// ---- single channel, default method (MODE 0 / 3): the epilogue the configs spend their time in -----------------------------
+// One batch = 16 accumulator columns (output rows) of a lane.  The ring holds a lane's consecutive rows 128 bytes apart, so the 16
+// moment loads of a batch are immediate offsets from one pointer; they are issued one batch AHEAD (two register sets) and the
+// tcgen05.ld of the current batch is queued behind them.  Per output: exact 64-bit N1, one conversion, two multiplies; the
+// above-threshold test of the 16 outputs is one accumulated predicate -- the (rare) append runs in a separate loop, and MODE 3
+// clamps only there.
+__device__ __forceinline__ void load_moments16(uint2 (&m)[16], const uint2* __restrict__ sr)
+{
+#pragma unroll
+    for (int k = 0; k < 16; ++k) m[k] = __ldg(sr + 16 * k);
+}
+
+template <bool STORE>
+__device__ __forceinline__ void epilogue16_c1(const uint32_t (&v)[16], const uint2 (&m)[16], int y_first, int mw, int x, uint32_t area,
+                                              uint32_t sumT, float ct, float* __restrict__ out, const CandSink& sink, float thr_any,
+                                              BestTrack& bt, bool track)
+{
+    float r[16];
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const long long n1 = (long long)((unsigned long long)area * v[k]) - (long long)((unsigned long long)m[k].x * sumT);
+        float rk = (float)n1 * __uint_as_float(m[k].y) * ct;
+        if (STORE) rk = fminf(1.0f, fmaxf(-1.0f, rk));
+        r[k] = rk;
+        any = any || (rk > thr_any);
+    }
+    if (STORE) {
+        float* o = out + (int64_t)y_first * mw + x;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) o[(uint32_t)(k * mw)] = r[k];
+    } else if (track) {
+        const uint32_t idx0 = (uint32_t)(y_first * mw + x);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const float rc = fminf(1.0f, r[k]);                // ties are decided on the clamped score (first occurrence)
+            const bool better = rc > bt.r;
+            bt.r = better ? rc : bt.r;
+            bt.idx = better ? idx0 + (uint32_t)(k * mw) : bt.idx;
+        }
+    }
+    if (any) {
+#pragma unroll 1
+        for (int k = 0; k < 16; ++k) {
+            const float rc = fminf(1.0f, fmaxf(-1.0f, r[k]));
+            if (rc > sink.thr) {
+                const int slot = atomicAdd(sink.count, 1);
+                if (slot < sink.cap) {
+                    DevHit c;
+                    c.tmpl = sink.tmpl; c.x = x; c.y = y_first + k; c.w = sink.w; c.h = sink.h; c.score = rc; c.seq = 0; c.key = 0.f;
+                    sink.list[slot] = c;
+                }
+            }
+        }
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ void epilogue_tile_c1(const TcParams& p, uint32_t tmem_d, int x0, int y0, int warp, int lane, int parts, BestTrack& bt)
+{
+    constexpr bool STORE = MODE != 3;
+    const bool track = MODE == 3 && p.best != nullptr;
+    const int m_row = 32 * (warp & 3) + lane;
+    int x, tsel;
+    if (p.mode == 0) { tsel = m_row >> 4; x = x0 + (m_row & 15); }
+    else { tsel = 0; x = x0 + 16 * (7 - (m_row >> 4)) + (m_row & 15); }
+    const TmplMeta* tm = (tsel < p.count) ? &p.meta[p.order[tsel]] : nullptr;
+    const int t_mh = tm ? min(tm->mh, p.y_base + p.rows) : 0, t_mw = tm ? tm->mw : 0;
+    const bool live = tm && (x < t_mw);
+    const uint32_t area = tm ? (uint32_t)(tm->h * tm->w) : 0u;
+    const uint32_t sumT = tm ? (uint32_t)tm->isum[0] : 0u;          // <= 255 * 66051 on the tensor path
+    const float ct = tm ? tm->inv_sqrt_d2 : 0.f;
+    const bool is_const = tm ? (tm->is_const != 0) : false;
+    float* out = tm ? p.maps + tm->map_off : nullptr;
+    const uint2* SRm = tm ? reinterpret_cast<const uint2*>(p.S) + tm->mom_off : nullptr;
+    CandSink sink{p.cand, p.cand_count, p.cand_cap, p.cand_thr, tm ? p.order[tsel] : 0, tm ? tm->w : 0, tm ? tm->h : 0};
+    // the accumulated test runs on the UNclamped score in MODE 3: thresholds outside (-1, 1) are decided by the clamped re-test
+    float thr_any = 3.0e38f;                                          // no list: never
+    if (p.cand) thr_any = p.cand_thr >= 1.0f ? 3.0e38f : (p.cand_thr < -1.0f ? -3.0e38f : p.cand_thr);
+    const int batches = p.N >> 4, part = warp >> 2;
+    const int c_begin = 16 * ((batches * part) / parts), c_end = 16 * ((batches * (part + 1)) / parts);
+    const uint2* sr0 = live ? SRm + mom_index(x, y0 - p.y_base, p.band_rows) : nullptr;      // row c of the tile: sr0 + 16 * c
+    auto fast_at = [&](int c0) { return live && !is_const && y0 + c0 + 16 <= t_mh; };
+    uint2 m[16], mn[16];
+    bool fast = c_begin < c_end && fast_at(c_begin);
+    if (fast) load_moments16(m, sr0 + 16 * c_begin);
+    for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+        const bool fast_next = c0 + 16 < c_end && fast_at(c0 + 16);
+        if (fast_next) load_moments16(mn, sr0 + 16 * (c0 + 16));
+        uint32_t v[16];
+        tmem_ld16(tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c0, v);
+        if (live && y0 + c0 < t_mh) {
+            if (fast) epilogue16_c1<STORE>(v, m, y0 + c0, t_mw, x, area, sumT, ct, out, sink, thr_any, bt, track);
+            else epilogue16<STORE>(v, y0 + c0, t_mh, t_mw, x, (long long)area, (long long)sumT, ct, is_const, SRm, out, sink, false, bt, track,
+                                   p.y_base, p.band_rows);           // bottom rows of a map / constant template: bounds-tested form
+        }
+        fast = fast_next;
+        if (fast_next) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) m[k] = mn[k];
+        }
     }
 }
 
@@ -463,11 +572,11 @@ __device__ __forceinline__ void epilogue_prefetch_first(const TcParams& p, int x
     else { tsel = 0; x = x0 + 16 * (7 - (m >> 4)) + (m & 15); }
     if (tsel >= p.count) return;
     const TmplMeta* tm = &p.meta[p.order[tsel]];
-    const int t_mh = tm->mh, t_mw = tm->mw;
+    const int t_mh = min(tm->mh, p.y_base + p.rows), t_mw = tm->mw;
     const int batches = p.N >> 4;
     const int c_begin = 16 * ((batches * (warp >> 2)) / parts);
     if (x >= t_mw || y0 + c_begin >= t_mh) return;
-    prefetch_moments16(reinterpret_cast<const uint2*>(p.S) + tm->mom_off, y0 + c_begin, t_mh, t_mw, x);
+    prefetch_moments16(reinterpret_cast<const uint2*>(p.S) + tm->mom_off, y0 + c_begin - p.y_base, t_mh - p.y_base, p.band_rows, x);
 }
 
 // MODE 3, N_object == 1: the lanes of a warp that serve the same template (mode A: 16, mode B: 32) reduce their best pixel and
@@ -505,7 +614,7 @@ ncc_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 2);
 
     const int xw = p.mode == 0 ? 16 : 128;
-    const int x0 = blockIdx.x * xw, y0 = blockIdx.y * p.N;
+    const int x0 = blockIdx.x * xw, y0 = p.y_base + blockIdx.y * p.N;
     uint32_t tmem_cols = 32;                                    // tcgen05.alloc: power of two >= 32
     while (tmem_cols < (uint32_t)p.N) tmem_cols <<= 1;
 
@@ -581,7 +690,8 @@ ncc_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap)
     __syncthreads();
     tc_fence_after();
     BestTrack bt{-3.0e38f, 0u};
-    epilogue_tile<MODE>(p, tmem_d, x0, y0, warp, lane, 2, bt);
+    if ((MODE == 0 || MODE == 3) && p.C == 1) epilogue_tile_c1<(MODE == 3 ? 3 : 0)>(p, tmem_d, x0, y0, warp, lane, 2, bt);
+    else epilogue_tile<MODE>(p, tmem_d, x0, y0, warp, lane, 2, bt);
     if (MODE == 3 && p.best) flush_best(p, bt, warp, lane);
     tc_fence_before();
     __syncthreads();
@@ -601,7 +711,7 @@ ncc_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap)
 // EW = 12 serves small templates, whose tiles spend longer in the epilogue than in the MMAs.
 constexpr int TCP_MAX_STAGES = 8;
 constexpr double TCP_EPI_CLK_PER_ROW = 100.0;   // measured: epilogue clocks per output row of a tile with 8 epilogue warps
-constexpr int TCP_STAGERS = 64;
+constexpr int TCP_STAGERS = 32;                 // register staging (fallback when no tensor map can be made): one stager warp
 constexpr size_t TCP_SMEM_SOFT = 188 * 1024;     // preferred ceiling of the persistent kernel's shared memory (see launch_ncc_tc)
 
 // MMAs of `rows` consecutive template rows: NK K-chunks each.  Only the low descriptor words move
@@ -647,10 +757,10 @@ __device__ __forceinline__ void issue_rows_any(int nk, uint32_t tmem_d, uint32_t
 }
 
 template <bool PROF, int EW, int MODE>
-__global__ void __launch_bounds__(512, 1)   // 128 registers; with EW = 8 (384 threads) a quarter of the register file stays free for other streams' small kernels
+__global__ void __launch_bounds__(32 * (EW + 3), 1)   // EW = 8: 352 threads, up to 184 registers (the pipelined epilogue holds two batches of moments); EW = 12: 480 threads, 136
 ncc_tc_persist_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap)
 {
-    constexpr int TCP_THREADS = 32 * (EW + 4);
+    constexpr int TCP_THREADS = 32 * (EW + 3);
     constexpr int TCP_EPI_THREADS = 32 * EW;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -685,8 +795,8 @@ ncc_tc_persist_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap
     if (warp == EW) tmem_alloc(tmem_slot, tmem_cols);
     // register staging (p.tma == 0): the first image tile is staged by the whole CTA (nothing else to do yet); the stagers
     // take over from the second.  With the TMA unit the loader warp issues every tile, the first one included.
-    if (!p.tma) stage_image_tile<TCP_THREADS>(tiles, p.img, p.pitch, p.H, ((int)blockIdx.x % p.tiles_x) * xw * p.C, ((int)blockIdx.x / p.tiles_x) * p.N,
-                                              p.R, kb_img, tid);
+    if (!p.tma) stage_image_tile<TCP_THREADS>(tiles, p.img, p.pitch, p.H, ((int)blockIdx.x % p.tiles_x) * xw * p.C,
+                                              p.y_base + ((int)blockIdx.x / p.tiles_x) * p.N, p.R, kb_img, tid);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -773,7 +883,7 @@ ncc_tc_persist_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap
             for (int i = 0; i < my_tiles; ++i) {
                 const int b = i & 1, u = i >> 1;
                 const int ti = (int)blockIdx.x + i * (int)gridDim.x;
-                const int x0 = (ti % p.tiles_x) * xw, y0 = (ti / p.tiles_x) * p.N;
+                const int x0 = (ti % p.tiles_x) * xw, y0 = p.y_base + (ti / p.tiles_x) * p.N;
                 mbar_wait(&tile_empty[b], (u & 1) ^ 1);        // fresh barrier: parity 1 passes
                 if (elect_one()) {
                     mbar_expect_tx(&tile_full[b], bytes);
@@ -789,7 +899,7 @@ ncc_tc_persist_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap
         for (int i = 0; i < my_tiles; ++i) {
             const int b = i & 1, u = i >> 1;
             const int ti = (int)blockIdx.x + i * (int)gridDim.x;
-            const int x0 = (ti % p.tiles_x) * xw, y0 = (ti / p.tiles_x) * p.N;
+            const int x0 = (ti % p.tiles_x) * xw, y0 = p.y_base + (ti / p.tiles_x) * p.N;
             const long long c0 = PROF ? clock64() : 0;
             mbar_wait(&tile_empty[b], (u & 1) ^ 1);
             const long long c1 = PROF ? clock64() : 0;
@@ -807,13 +917,16 @@ ncc_tc_persist_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap
         for (int i = 0; i < my_tiles; ++i) {
             const int b = i & 1, u = i >> 1;
             const int ti = (int)blockIdx.x + i * (int)gridDim.x;
-            const int x0 = (ti % p.tiles_x) * xw, y0 = (ti / p.tiles_x) * p.N;
+            const int x0 = (ti % p.tiles_x) * xw, y0 = p.y_base + (ti / p.tiles_x) * p.N;
             if (MODE == 0 || MODE == 3) epilogue_prefetch_first(p, x0, y0, warp, lane, EW / 4);
             const long long c0 = PROF ? clock64() : 0;
             mbar_wait(&acc_full[b], u & 1);
             const long long c1 = PROF ? clock64() : 0;
             tc_fence_after();
-            if (!PROF || !(p.dbg & 1)) epilogue_tile<MODE>(p, tmem_base + (uint32_t)b * acc_stride, x0, y0, warp, lane, EW / 4, bt);
+            if (!PROF || !(p.dbg & 1)) {
+                if ((MODE == 0 || MODE == 3) && p.C == 1) epilogue_tile_c1<(MODE == 3 ? 3 : 0)>(p, tmem_base + (uint32_t)b * acc_stride, x0, y0, warp, lane, EW / 4, bt);
+                else epilogue_tile<MODE>(p, tmem_base + (uint32_t)b * acc_stride, x0, y0, warp, lane, EW / 4, bt);
+            }
             tc_fence_before();
             mbar_arrive(&acc_empty[b]);
             if (PROF) { w_af += c1 - c0; w_epi += clock64() - c1; }
@@ -871,8 +984,9 @@ __global__ void window_moments_kernel(SatView sat, const uint32_t* __restrict__ 
     const SizeDesc sd = sizes[blockIdx.y];
     const int64_t n = (int64_t)sd.mh * sd.mw;
     const unsigned long long area = (unsigned long long)sd.h * sd.w;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int y = (int)(idx / sd.mw), x = (int)(idx - (int64_t)y * sd.mw);
+    for (int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pos < n; pos += (int64_t)gridDim.x * blockDim.x) {
+        const int y = (int)(pos / sd.mw), x = (int)(pos - (int64_t)y * sd.mw);
+        const int64_t idx = mom_index(x, y, sd.band);          // whole maps: one band that starts at row 0
         // window sums of squares < 2^32 on the tensor path (h*w*C <= 66051): the 32-bit wrap-around table is exact
         const unsigned long long q = sat_window_s(sat_q32, sat.pitch, y, x, sd.h, sd.w);
         unsigned long long d1 = area * q;
@@ -907,10 +1021,11 @@ window_moments_rows_kernel(SatView sat, const uint32_t* __restrict__ sat_q32, co
     for (int y = blockIdx.y; y < sd.mh; y += gridDim.y) {
         const uint32_t* qa = sat_q32 + (int64_t)y * sat.pitch;
         const uint32_t* sa = sat.s + (int64_t)y * sat.pitch;
-        uint32_t* out_s = S + sd.off + (int64_t)y * sd.mw;
-        float* out_r = rsD + sd.off + (int64_t)y * sd.mw;
-        uint2* out_sr = reinterpret_cast<uint2*>(S) + sd.off + (int64_t)y * sd.mw;
+        uint32_t* out_s = S + sd.off;
+        float* out_r = rsD + sd.off;
+        uint2* out_sr = reinterpret_cast<uint2*>(S) + sd.off;
         for (int x = x_first; x < sd.mw; x += x_step) {
+            const int64_t idx = mom_index(x, y, sd.band);
             const uint32_t* q0 = qa + x;
             const uint32_t q = q0[down + sd.w] - q0[sd.w] - q0[down] + q0[0];      // modulo 2^32, exact (window sums < 2^32)
             unsigned long long d1 = (unsigned long long)area * q;
@@ -920,12 +1035,12 @@ window_moments_rows_kernel(SatView sat, const uint32_t* __restrict__ sat_q32, co
                 const uint32_t* p0 = sa + c * sat.plane + x;
                 const uint32_t s = p0[down + sd.w] - p0[sd.w] - p0[down] + p0[0];
                 d1 -= (unsigned long long)s * s;
-                if (C > 1) out_s[c * mom_plane + x] = s;
+                if (C > 1) out_s[c * mom_plane + idx] = s;
                 s0 = s;
             }
             const float rs = d1 ? rsqrtf((float)d1) : 0.0f;
-            if (C > 1) out_r[x] = rs;
-            else out_sr[x] = make_uint2(s0, __float_as_uint(rs));
+            if (C > 1) out_r[idx] = rs;
+            else out_sr[idx] = make_uint2(s0, __float_as_uint(rs));
         }
     }
 }
@@ -1064,40 +1179,42 @@ int launch_toeplitz_prep(mtm_ctx* ctx, const TcGroup& g)
     return MTM_OK;
 }
 
-int launch_window_moments(mtm_ctx* ctx)
+int launch_window_moments(mtm_ctx* ctx, int size_first, int size_count)
 {
     const ImageDev& im = ctx->img;
     SatView sv{im.sat_s, im.sat_q, im.sat_pitch, (int64_t)(im.H + 1) * im.sat_pitch};
     int64_t n = 0;
-    for (const SizeDesc& sd : ctx->h_sizes) n = std::max<int64_t>(n, (int64_t)sd.mh * sd.mw);
+    const SizeDesc* h_first = ctx->h_sizes.data() + size_first;
+    const SizeDesc* d_first = ctx->d_sizes + size_first;
+    for (int q = 0; q < size_count; ++q) n = std::max<int64_t>(n, (int64_t)h_first[q].mh * h_first[q].mw);
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 16));
     if (tc_env().mom_rows) {
         int mh = 1, mw = 1;
-        for (const SizeDesc& sd : ctx->h_sizes) { mh = std::max(mh, sd.mh); mw = std::max(mw, sd.mw); }
-        const dim3 rgrid((unsigned)std::min((mw + 255) / 256, 8), (unsigned)std::min(mh, ctx->sm_count), (unsigned)ctx->h_sizes.size());
+        for (int q = 0; q < size_count; ++q) { mh = std::max(mh, h_first[q].mh); mw = std::max(mw, h_first[q].mw); }
+        const dim3 rgrid((unsigned)std::min((mw + 255) / 256, 8), (unsigned)std::min(mh, ctx->sm_count), (unsigned)size_count);
         switch (im.C) {
-            case 1: window_moments_rows_kernel<1><<<rgrid, 256, 0, ctx->stream>>>(sv, im.sat_q32, ctx->d_sizes, ctx->d_wS, ctx->d_wR, ctx->moments_total); break;
-            case 3: window_moments_rows_kernel<3><<<rgrid, 256, 0, ctx->stream>>>(sv, im.sat_q32, ctx->d_sizes, ctx->d_wS, ctx->d_wR, ctx->moments_total); break;
-            default: window_moments_rows_kernel<4><<<rgrid, 256, 0, ctx->stream>>>(sv, im.sat_q32, ctx->d_sizes, ctx->d_wS, ctx->d_wR, ctx->moments_total); break;
+            case 1: window_moments_rows_kernel<1><<<rgrid, 256, 0, ctx->stream>>>(sv, im.sat_q32, d_first, ctx->d_wS, ctx->d_wR, ctx->moments_total); break;
+            case 3: window_moments_rows_kernel<3><<<rgrid, 256, 0, ctx->stream>>>(sv, im.sat_q32, d_first, ctx->d_wS, ctx->d_wR, ctx->moments_total); break;
+            default: window_moments_rows_kernel<4><<<rgrid, 256, 0, ctx->stream>>>(sv, im.sat_q32, d_first, ctx->d_wS, ctx->d_wR, ctx->moments_total); break;
         }
         MTM_LAUNCH_CHECK(ctx);
         return MTM_OK;
     }
-    const dim3 grid(blocks, (unsigned)ctx->h_sizes.size());
+    const dim3 grid(blocks, (unsigned)size_count);
     // MTM_B200_MOM_CS=1 (experiment): evict-first stores.  Measured neutral on C5 (7.35 against 7.42 ms per step,
     // profiles/README.md): the 64-size sweep is not limited by the moment maps evicting the tables, so the default stays off.
     const bool stream_stores = tc_env().mom_cs > 0;
     if (stream_stores)
-        window_moments_kernel<true><<<grid, 256, 0, ctx->stream>>>(sv, im.sat_q32, ctx->d_sizes, ctx->d_wS, ctx->d_wR, im.C, ctx->moments_total);
+        window_moments_kernel<true><<<grid, 256, 0, ctx->stream>>>(sv, im.sat_q32, d_first, ctx->d_wS, ctx->d_wR, im.C, ctx->moments_total);
     else
-        window_moments_kernel<false><<<grid, 256, 0, ctx->stream>>>(sv, im.sat_q32, ctx->d_sizes, ctx->d_wS, ctx->d_wR, im.C, ctx->moments_total);
+        window_moments_kernel<false><<<grid, 256, 0, ctx->stream>>>(sv, im.sat_q32, d_first, ctx->d_wS, ctx->d_wR, im.C, ctx->moments_total);
     MTM_LAUNCH_CHECK(ctx);
     return MTM_OK;
 }
 
 struct AccumArgs { int img_plane, tmpl_plane; double weight; bool first; };
 
-static int launch_ncc_tc_impl(mtm_ctx* ctx, const TcGroup& g, int method, const AccumArgs* accum)
+static int launch_ncc_tc_impl(mtm_ctx* ctx, const TcGroup& g, int method, const AccumArgs* accum, int y_base, int rows)
 {
     const ImageDev& im = ctx->img;
     TcParams p{};
@@ -1115,7 +1232,8 @@ static int launch_ncc_tc_impl(mtm_ctx* ctx, const TcGroup& g, int method, const 
     }
     p.slab_bytes = g.slab_bytes; p.a_kblk = g.a_kblk; p.nk = g.nk; p.ds = g.ds;
     p.mode = g.mode; p.h = g.h; p.w = g.w;
-    p.mh = im.H - g.h_min + 1; p.mw = im.W - g.w_min + 1;      // tile grid covers the largest member map
+    p.mh = im.H - g.h_min + 1; p.mw = im.W - g.w_min + 1;      // tile grid covers the largest member map ...
+    p.y_base = y_base; p.rows = std::min(rows, p.mh - y_base); p.band_rows = g.band_rows;      // ... rows [y_base, y_base + rows) of it in this launch
     p.meta = ctx->d_meta; p.order = ctx->d_order + g.first; p.count = g.count;
     p.S = ctx->d_wS; p.rsD = ctx->d_wR; p.maps = ctx->d_maps;
     p.C = im.C; p.mom_plane = ctx->moments_total;
@@ -1156,7 +1274,7 @@ static int launch_ncc_tc_impl(mtm_ctx* ctx, const TcGroup& g, int method, const 
             int stages = (int)std::min<size_t>(TCP_MAX_STAGES, (227 * 1024 - 256 - 2 * tile_b) / stage_b);
             const size_t soft = smem_soft > 256 + 2 * tile_b ? (smem_soft - 256 - 2 * tile_b) / stage_b : 0;
             if (soft >= 4) stages = (int)std::min<size_t>(stages, soft);
-            const long long tiles = (long long)gx_p * ((p.mh + n - 1) / n);
+            const long long tiles = (long long)gx_p * ((p.rows + n - 1) / n);
             const long long per_cta = (tiles + ctx->sm_count - 1) / ctx->sm_count;
             const double mma_tile = (double)g.h * g.nk * std::max(0.5 * n, 64.0 + 0.25 * n);
             for (int ew = 8; ew <= 12; ew += 4) {
@@ -1170,7 +1288,7 @@ static int launch_ncc_tc_impl(mtm_ctx* ctx, const TcGroup& g, int method, const 
         if (bestN) {
             const size_t tile_b = ((size_t)2 * g.nk * tc_tile_rows(bestN, g.h) * 16 + 127) & ~(size_t)127;
             p.N = bestN; p.R = tc_tile_rows(bestN, g.h); p.stages = best_stages; p.ds = ds_p;
-            p.tiles_x = gx_p; p.tiles_total = gx_p * ((p.mh + bestN - 1) / bestN);
+            p.tiles_x = gx_p; p.tiles_total = gx_p * ((p.rows + bestN - 1) / bestN);
             plan_tma();
             const size_t smem_bytes = 256 + 2 * tile_b + (size_t)best_stages * stage_b;
             if (!ctx->tcp_attr_set) {
@@ -1199,20 +1317,20 @@ static int launch_ncc_tc_impl(mtm_ctx* ctx, const TcGroup& g, int method, const 
             p.dbg = pdbg;
             const int ew = best_ew;
             if (kmode == 2) {
-                if (ew == 12) ncc_tc_persist_kernel<false, 12, 2><<<grid_p, 32 * (p.tma ? 15 : 16), smem_bytes, ctx->stream>>>(p, tmap);
-                else ncc_tc_persist_kernel<false, 8, 2><<<grid_p, 32 * (p.tma ? 11 : 12), smem_bytes, ctx->stream>>>(p, tmap);
+                if (ew == 12) ncc_tc_persist_kernel<false, 12, 2><<<grid_p, 32 * 15, smem_bytes, ctx->stream>>>(p, tmap);
+                else ncc_tc_persist_kernel<false, 8, 2><<<grid_p, 32 * 11, smem_bytes, ctx->stream>>>(p, tmap);
             } else if (kmode == 1) {
-                if (ew == 12) ncc_tc_persist_kernel<false, 12, 1><<<grid_p, 32 * (p.tma ? 15 : 16), smem_bytes, ctx->stream>>>(p, tmap);
-                else ncc_tc_persist_kernel<false, 8, 1><<<grid_p, 32 * (p.tma ? 11 : 12), smem_bytes, ctx->stream>>>(p, tmap);
+                if (ew == 12) ncc_tc_persist_kernel<false, 12, 1><<<grid_p, 32 * 15, smem_bytes, ctx->stream>>>(p, tmap);
+                else ncc_tc_persist_kernel<false, 8, 1><<<grid_p, 32 * 11, smem_bytes, ctx->stream>>>(p, tmap);
             } else if (kmode == 3) {
-                if (ew == 12) ncc_tc_persist_kernel<false, 12, 3><<<grid_p, 32 * (p.tma ? 15 : 16), smem_bytes, ctx->stream>>>(p, tmap);
-                else ncc_tc_persist_kernel<false, 8, 3><<<grid_p, 32 * (p.tma ? 11 : 12), smem_bytes, ctx->stream>>>(p, tmap);
+                if (ew == 12) ncc_tc_persist_kernel<false, 12, 3><<<grid_p, 32 * 15, smem_bytes, ctx->stream>>>(p, tmap);
+                else ncc_tc_persist_kernel<false, 8, 3><<<grid_p, 32 * 11, smem_bytes, ctx->stream>>>(p, tmap);
             } else if (ew == 12) {
-                if (prof) ncc_tc_persist_kernel<true, 12, 0><<<grid_p, 32 * (p.tma ? 15 : 16), smem_bytes, ctx->stream>>>(p, tmap);
-                else ncc_tc_persist_kernel<false, 12, 0><<<grid_p, 32 * (p.tma ? 15 : 16), smem_bytes, ctx->stream>>>(p, tmap);
+                if (prof) ncc_tc_persist_kernel<true, 12, 0><<<grid_p, 32 * 15, smem_bytes, ctx->stream>>>(p, tmap);
+                else ncc_tc_persist_kernel<false, 12, 0><<<grid_p, 32 * 15, smem_bytes, ctx->stream>>>(p, tmap);
             } else {
-                if (prof) ncc_tc_persist_kernel<true, 8, 0><<<grid_p, 32 * (p.tma ? 11 : 12), smem_bytes, ctx->stream>>>(p, tmap);
-                else ncc_tc_persist_kernel<false, 8, 0><<<grid_p, 32 * (p.tma ? 11 : 12), smem_bytes, ctx->stream>>>(p, tmap);
+                if (prof) ncc_tc_persist_kernel<true, 8, 0><<<grid_p, 32 * 11, smem_bytes, ctx->stream>>>(p, tmap);
+                else ncc_tc_persist_kernel<false, 8, 0><<<grid_p, 32 * 11, smem_bytes, ctx->stream>>>(p, tmap);
             }
             MTM_LAUNCH_CHECK(ctx);
             if (prof) {
@@ -1242,7 +1360,7 @@ static int launch_ncc_tc_impl(mtm_ctx* ctx, const TcGroup& g, int method, const 
     double best_cost = 1e300;
     for (int n = g.N; n >= 32 && n >= g.N / 2; n -= 16) {
         const int per_sm = (2 * smem_for(n) <= 226 * 1024) ? 2 : 1;          // TMEM (<= 256 columns) also allows 2
-        const long long tiles = (long long)gx * ((p.mh + n - 1) / n);
+        const long long tiles = (long long)gx * ((p.rows + n - 1) / n);
         const long long waves = (tiles + (long long)per_sm * ctx->sm_count - 1) / ((long long)per_sm * ctx->sm_count);
         const double cost = (double)waves * (n + 0.25 * g.h + 16.0) / per_sm;
         if (cost < best_cost - 1e-9) { best_cost = cost; bestN = n; }
@@ -1259,7 +1377,7 @@ static int launch_ncc_tc_impl(mtm_ctx* ctx, const TcGroup& g, int method, const 
         ctx->tc_attr_set = true;
     }
     const int xw = g.mode == 0 ? 16 : 128;
-    dim3 grid((p.mw + xw - 1) / xw, (p.mh + p.N - 1) / p.N);
+    dim3 grid((p.mw + xw - 1) / xw, (p.rows + p.N - 1) / p.N);
     if (kmode == 2) ncc_tc_kernel<2><<<grid, TC_THREADS, smem_bytes, ctx->stream>>>(p, tmap);
     else if (kmode == 1) ncc_tc_kernel<1><<<grid, TC_THREADS, smem_bytes, ctx->stream>>>(p, tmap);
     else if (kmode == 3) ncc_tc_kernel<3><<<grid, TC_THREADS, smem_bytes, ctx->stream>>>(p, tmap);
@@ -1268,10 +1386,10 @@ static int launch_ncc_tc_impl(mtm_ctx* ctx, const TcGroup& g, int method, const 
     return MTM_OK;
 }
 
-int launch_ncc_tc(mtm_ctx* ctx, const TcGroup& g, int method) { return launch_ncc_tc_impl(ctx, g, method, nullptr); }
+int launch_ncc_tc(mtm_ctx* ctx, const TcGroup& g, int method, int y_base, int rows) { return launch_ncc_tc_impl(ctx, g, method, nullptr, y_base, rows); }
 
 int launch_ncc_tc_accum(mtm_ctx* ctx, const TcGroup& g, int img_plane, int tmpl_plane, double weight, bool first)
 {
     const AccumArgs a{img_plane, tmpl_plane, weight, first};
-    return launch_ncc_tc_impl(ctx, g, MTM_TM_CCORR, &a);
+    return launch_ncc_tc_impl(ctx, g, MTM_TM_CCORR, &a, 0, ctx->img.H - g.h_min + 1);
 }

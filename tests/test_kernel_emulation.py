@@ -234,10 +234,11 @@ extern "C" int emu_ncc_direct(const uint8_t* img, int64_t pitch, int H, int W, i
 // launch_box_moments (box_moments.cu): grid = (strips of the widest map, bands, sizes); the number of bands is the caller's (the
 // library picks it from the SM count).
 extern "C" int emu_box_moments(const uint8_t* img, int64_t pitch, int C, const SizeDesc* sizes, int n_sizes, uint32_t* S, float* rsD,
-                               int64_t mom_plane, int bands)
+                               int64_t mom_plane, int bands, int y_begin, int rows)
 {
     BoxParams p{};
     p.img = img; p.pitch = pitch; p.sizes = sizes; p.S = S; p.rsD = rsD; p.mom_plane = mom_plane;
+    p.y_begin = y_begin; p.rows = rows;
     int strips = 1;
     for (int k = 0; k < n_sizes; ++k) {
         const int strip_out = (BM_COLS - (sizes[k].w - 1)) & ~3;
@@ -246,7 +247,7 @@ extern "C" int emu_box_moments(const uint8_t* img, int64_t pitch, int C, const S
     if (C == 1 && bands < 0) {                              // the throughput form of the single-channel kernel (strips of 2048 columns)
         int strips1 = 1;
         for (int k = 0; k < n_sizes; ++k) {
-            const int strip_out = (B1_COLS - (sizes[k].w - 1)) & ~7;
+            const int strip_out = (B1_COLS - (sizes[k].w - 1)) & ~15;
             strips1 = std::max(strips1, (sizes[k].mw + strip_out - 1) / strip_out);
         }
         emu_launch_coop(dim3(strips1, -bands, n_sizes), dim3(B1_THREADS), [&] { box_moments_c1_kernel(p); });
@@ -267,7 +268,8 @@ extern "C" long long emu_ncc_tc(const uint8_t* img, int64_t pitch, int H, int W,
                                 const int32_t* order, int count, int mode, int h, int w, int h_min, int w_min,
                                 const uint32_t* S, const float* rsD, int64_t mom_plane, const uint32_t* sat_s,
                                 const unsigned long long* sat_q, int64_t sat_pitch, float* maps, int method, int N, int stages, int ds,
-                                int EW, int persist, int ctas, DevHit* cand, int32_t* cand_count, int cand_cap, float cand_thr)
+                                int EW, int persist, int ctas, DevHit* cand, int32_t* cand_count, int cand_cap, float cand_thr,
+                                int y_base, int rows, int band_rows)
 {
     TcGroup g{};
     if (!tc_plan_group(mode, h, w, C, g)) return -1;
@@ -285,6 +287,7 @@ extern "C" long long emu_ncc_tc(const uint8_t* img, int64_t pitch, int H, int W,
     p.meta = meta; p.order = order; p.count = count; p.S = S; p.rsD = rsD; p.maps = maps; p.C = C; p.mom_plane = mom_plane;
     if (cand) { p.cand = cand; p.cand_count = cand_count; p.cand_cap = cand_cap; p.cand_thr = cand_thr; }
     const int xw = mode == 0 ? 16 : 128, gx = (p.mw + xw - 1) / xw;
+    p.y_base = y_base; p.rows = std::min(rows, p.mh - y_base); p.band_rows = band_rows;      // one band of output rows per launch
     p.N = N; p.R = tc_tile_rows(N, h);
     CUtensorMap tmap{};                                     // image tiles through the (modelled) TMA unit unless EMU_NO_TMA is set
     p.tma_chunks = (p.R + 255) / 256;
@@ -299,14 +302,14 @@ extern "C" long long emu_ncc_tc(const uint8_t* img, int64_t pitch, int H, int W,
     if (persist) {
         p.ds = std::max(1, std::min(h, ds)); p.stages = stages;
         if (stages < 2 || stages > TCP_MAX_STAGES || 256 + 2 * tile_b + (size_t)stages * p.ds * g.slab_bytes > 227 * 1024) return -2;
-        p.tiles_x = gx; p.tiles_total = gx * ((p.mh + N - 1) / N);
+        p.tiles_x = gx; p.tiles_total = gx * ((p.rows + N - 1) / N);
         const dim3 grid((unsigned)std::min(p.tiles_total, ctas)), block(32 * (EW + (p.tma ? 3 : 4)));
         if (EW == 12) { if (kmode) emu_launch_coop(grid, block, [&] { ncc_tc_persist_kernel<false, 12, 1>(p, tmap); }); else emu_launch_coop(grid, block, [&] { ncc_tc_persist_kernel<false, 12, 0>(p, tmap); }); }
         else { if (kmode) emu_launch_coop(grid, block, [&] { ncc_tc_persist_kernel<false, 8, 1>(p, tmap); }); else emu_launch_coop(grid, block, [&] { ncc_tc_persist_kernel<false, 8, 0>(p, tmap); }); }
     } else {
         p.ds = g.ds;
         if (tile_b + (size_t)TC_STAGES * g.ds * g.slab_bytes + 256 > 227 * 1024) return -2;
-        const dim3 grid(gx, (p.mh + N - 1) / N), block(TC_THREADS);
+        const dim3 grid(gx, (p.rows + N - 1) / N), block(TC_THREADS);
         if (kmode) emu_launch_coop(grid, block, [&] { ncc_tc_kernel<1>(p, tmap); }); else emu_launch_coop(grid, block, [&] { ncc_tc_kernel<0>(p, tmap); });
     }
     emu_dyn_smem = nullptr;
@@ -423,6 +426,7 @@ extern "C" long long emu_ncc_tc16(const uint16_t* src, int H, int W, float* pixf
         p.meta = meta; p.order = order; p.count = count; p.maps = maps; p.C = 1;
         p.acc = acc; p.acc_weight = weights[k]; p.acc_first = k == 0 ? 1 : 0;
         const int xw = mode == 0 ? 16 : 128, gx = (p.mw + xw - 1) / xw;
+        p.y_base = 0; p.rows = p.mh; p.band_rows = p.mh;
         p.N = N; p.R = tc_tile_rows(N, h); p.ds = std::max(1, std::min(h, ds)); p.stages = stages;
         CUtensorMap tmap{};
         p.tma_chunks = (p.R + 255) / 256;
@@ -454,7 +458,16 @@ extern "C" long long emu_ncc_tc16(const uint16_t* src, int H, int W, float* pixf
 
 XFORM_DTYPE = np.dtype([("src_off", "<i8"), ("src_pitch", "<i8"), ("dst_off", "<i8"), ("dst_pitch", "<i8"),
                         ("dh", "<i4"), ("dw", "<i4"), ("oh", "<i4"), ("ow", "<i4"), ("op", "<i4"), ("pad", "<i4")])
-SIZE_DTYPE = np.dtype([("h", "<i4"), ("w", "<i4"), ("mh", "<i4"), ("mw", "<i4"), ("off", "<i8")])
+SIZE_DTYPE = np.dtype([("h", "<i4"), ("w", "<i4"), ("mh", "<i4"), ("mw", "<i4"), ("off", "<i8"), ("band", "<i4"), ("pad", "<i4")])
+
+
+def _mom_segment(mw, band):
+    """Entries of a size's moment segment (csrc/mtm_internal.cuh, SizeDesc): tile-major, `band` rows."""
+    return (mw + 15) // 16 * 16 * band
+
+
+def _mom_index(x, r, band):
+    return ((x >> 4) * band + r) * 16 + (x & 15)
 OPS = ["identity", "rot90", "rot180", "rot270", "fliplr", "flipud", "transpose", "antitranspose"]
 
 
@@ -508,8 +521,8 @@ def test_row_walking_moment_kernel_equals_the_default_one(emu, channels):
     sizes = np.zeros(3, SIZE_DTYPE)
     off = 0
     for k, (h, w) in enumerate([(5, 9), (17, 16), (32, 40)]):
-        sizes[k] = (h, w, H - h + 1, W - w + 1, off)
-        off += ((H - h + 1) * (W - w + 1) + 31) // 32 * 32
+        sizes[k] = (h, w, H - h + 1, W - w + 1, off, H - h + 1, 0)              # whole maps: one band
+        off += _mom_segment(W - w + 1, H - h + 1)
     outs = []
     for rows_form in (0, 1):
         S = np.full(off * max(2, channels), 0xDEADBEEF, np.uint32)
@@ -525,7 +538,7 @@ def test_row_walking_moment_kernel_equals_the_default_one(emu, channels):
     first = outs[0][0][0] if channels > 1 else outs[0][0].view(np.uint32)[0]
     assert int(first) == int(win)
     y, x = 12, 25                                                             # a flat 5 x 9 window inside the constant patch
-    idx = y * (W - w + 1) + x
+    idx = _mom_index(x, y, H - h + 1)
     rs = outs[0][1][idx] if channels > 1 else outs[0][0].view(np.float32)[2 * idx + 1]
     assert rs == 0.0
 
@@ -876,8 +889,8 @@ def test_box_sum_moment_kernel_equals_the_summed_area_one(emu, channels, shape, 
     sizes = np.zeros(len(windows), SIZE_DTYPE)
     total = 64                                                                # the maps do not start at element 0
     for k, (h, w) in enumerate(windows):
-        sizes[k] = (h, w, H - h + 1, W - w + 1, total)
-        total += ((H - h + 1) * (W - w + 1) + 31) // 32 * 32
+        sizes[k] = (h, w, H - h + 1, W - w + 1, total, H - h + 1, 0)          # whole maps: one band each
+        total += _mom_segment(W - w + 1, H - h + 1)
     outs = []
     for box in (0, 1, 2):                                                      # summed-area kernel, generic box kernel, throughput form (C == 1)
         if box == 2 and channels != 1:
@@ -886,7 +899,7 @@ def test_box_sum_moment_kernel_equals_the_summed_area_one(emu, channels, shape, 
         R = np.full(total, -1.0, np.float32)
         if box:
             assert emu.emu_box_moments(_ptr(buf), ctypes.c_int64(ipitch), channels, _ptr(sizes), len(sizes), _ptr(S), _ptr(R),
-                                       ctypes.c_int64(total), bands if box == 1 else -bands) >= 1
+                                       ctypes.c_int64(total), bands if box == 1 else -bands, 0, H) >= 1
         else:
             emu.emu_moments(0, _ptr(sat_s), _ptr(sat_q), ctypes.c_int64(pitch), ctypes.c_int64(plane), _ptr(sizes), len(sizes), channels,
                             _ptr(S), _ptr(R), ctypes.c_int64(total), 3, 1)
@@ -897,11 +910,40 @@ def test_box_sum_moment_kernel_equals_the_summed_area_one(emu, channels, shape, 
     h, w = windows[0]
     first = outs[1][0][64] if channels > 1 else outs[1][0][2 * 64]
     assert int(first) == int(wide[:h, :w, 0].sum())
+    # the same rows band by band into a RING: every band overwrites the previous one (what the library does when the maps of a
+    # template group exceed the ring budget); entry (x, r) of a band = entry (x, y_begin + r) of the whole map
+    B = 16
+    ring = np.zeros(len(windows), SIZE_DTYPE)
+    rtotal = 32
+    for k, (h, w) in enumerate(windows):
+        ring[k] = (h, w, H - h + 1, W - w + 1, rtotal, B, 0)
+        rtotal += _mom_segment(W - w + 1, B)
+    full_S, full_R = outs[0]
+    for box in (1, 2):
+        if box == 2 and channels != 1:
+            continue
+        S = np.full(rtotal * max(2, channels), 0xDEADBEEF, np.uint32)
+        R = np.full(rtotal, -1.0, np.float32)
+        for y_begin in range(0, max(int(sz["mh"]) for sz in ring), B):
+            emu.emu_box_moments(_ptr(buf), ctypes.c_int64(ipitch), channels, _ptr(ring), len(ring), _ptr(S), _ptr(R),
+                                ctypes.c_int64(rtotal), 2 if box == 1 else -2, y_begin, B)
+            for k, (h, w) in enumerate(windows):
+                mh_, mw_ = H - h + 1, W - w + 1
+                for y in range(y_begin, min(mh_, y_begin + B)):
+                    xs = np.arange(mw_)
+                    src = int(sizes[k]["off"]) + _mom_index(xs, y, mh_)
+                    dst = int(ring[k]["off"]) + _mom_index(xs, y - y_begin, B)
+                    if channels == 1:
+                        assert np.array_equal(S.view(np.uint64)[dst], full_S.view(np.uint64)[src]), (box, k, y)
+                    else:
+                        for c in range(channels):
+                            assert np.array_equal(S[c * rtotal + dst], full_S[c * total + src]), (box, k, y, c)
+                        assert np.array_equal(R.view(np.uint32)[dst], full_R.view(np.uint32)[src]), (box, k, y)
 
 
 # ---- the tcgen05 kernels on the functional model of tests/emu/tcgen05_model.h -----------------------------------------------
 
-def _host_tensor_maps(emu, image, tmpls, method, mode, N, stages=3, ds=4, EW=8, persist=True, ctas=2, cand_thr=None, box=False):
+def _host_tensor_maps(emu, image, tmpls, method, mode, N, stages=3, ds=4, EW=8, persist=True, ctas=2, cand_thr=None, box=False, band=None):
     """ncc_tc.cu on the host for ONE template group (mode A: up to 8 templates of mixed sizes, zero padded to the largest; mode B:
     one grayscale template x 128 x-offsets): summed-area tables, template statistics, window moments, Toeplitz slabs, then the
     persistent (or the one-tile-per-CTA) kernel.  Returns (maps, number of MMAs issued, candidate records or None)."""
@@ -918,11 +960,14 @@ def _host_tensor_maps(emu, image, tmpls, method, mode, N, stages=3, ds=4, EW=8, 
         h, w = tmpls[k].shape[:2]
         meta[k]["mh"], meta[k]["mw"], meta[k]["map_off"] = H - h + 1, W - w + 1, off
         off += ((H - h + 1) * (W - w + 1) + 31) // 32 * 32
+    mh_max = H - min(t.shape[0] for t in tmpls) + 1
+    band = mh_max if band is None else band                                  # band < the largest map: moments + numerator band by band (ring)
+    assert band == mh_max or box, "only the box-sum kernels write bands"
     for k in order:
         h, w = tmpls[k].shape[:2]
         if not sizes or (sizes[-1][0], sizes[-1][1]) != (h, w):
-            sizes.append((h, w, H - h + 1, W - w + 1, moff))
-            moff += ((H - h + 1) * (W - w + 1) + 31) // 32 * 32
+            sizes.append((h, w, H - h + 1, W - w + 1, moff, band, 0))
+            moff += _mom_segment(W - w + 1, band)
         meta[k]["mom_off"] = sizes[-1][4]
     emu.emu_tmpl_stats(_ptr(arena), _ptr(meta), len(tmpls), C)
     sd = np.zeros(len(sizes), SIZE_DTYPE)
@@ -930,22 +975,27 @@ def _host_tensor_maps(emu, image, tmpls, method, mode, N, stages=3, ds=4, EW=8, 
         sd[k] = v
     S = np.full(moff * max(2, C), 0xDEADBEEF, np.uint32)
     R = np.full(moff, np.nan, np.float32)
-    if box:
-        emu.emu_box_moments(_ptr(buf), ctypes.c_int64(ipitch), C, _ptr(sd), len(sizes), _ptr(S), _ptr(R), ctypes.c_int64(moff), 5)
-    else:
-        emu.emu_moments(0, _ptr(sat_s), _ptr(sat_q32), ctypes.c_int64(spitch), ctypes.c_int64((H + 1) * spitch), _ptr(sd), len(sizes), C,
-                        _ptr(S), _ptr(R), ctypes.c_int64(moff), 2, 1)
     maps = np.full(off + 32, np.nan, np.float32)
     hs, ws = [t.shape[0] for t in tmpls], [t.shape[1] for t in tmpls]
     cand = np.zeros(4096, DEVHIT_DTYPE)
     cand_count = np.zeros(1, np.int32)
     emu.emu_ncc_tc.restype = ctypes.c_longlong
-    n_mma = emu.emu_ncc_tc(_ptr(buf), ctypes.c_int64(ipitch), H, W, C, _ptr(arena), _ptr(meta), _ptr(order), len(tmpls), mode,
-                           max(hs), max(ws), min(hs), min(ws), _ptr(S), _ptr(R), ctypes.c_int64(moff), _ptr(sat_s), _ptr(sat_q),
-                           ctypes.c_int64(spitch), _ptr(maps), method, N, stages, ds, EW, int(persist), ctas,
-                           _ptr(cand) if cand_thr is not None else None, _ptr(cand_count), len(cand),
-                           ctypes.c_float(cand_thr if cand_thr is not None else 0.0))
-    assert n_mma > 0, n_mma
+    n_mma = 0
+    for y_base in range(0, mh_max, band):
+        rows = min(band, mh_max - y_base)
+        if box:
+            emu.emu_box_moments(_ptr(buf), ctypes.c_int64(ipitch), C, _ptr(sd), len(sizes), _ptr(S), _ptr(R), ctypes.c_int64(moff),
+                                5 if C > 1 else -3, y_base, rows)
+        else:
+            emu.emu_moments(0, _ptr(sat_s), _ptr(sat_q32), ctypes.c_int64(spitch), ctypes.c_int64((H + 1) * spitch), _ptr(sd), len(sizes), C,
+                            _ptr(S), _ptr(R), ctypes.c_int64(moff), 2, 1)
+        got = emu.emu_ncc_tc(_ptr(buf), ctypes.c_int64(ipitch), H, W, C, _ptr(arena), _ptr(meta), _ptr(order), len(tmpls), mode,
+                             max(hs), max(ws), min(hs), min(ws), _ptr(S), _ptr(R), ctypes.c_int64(moff), _ptr(sat_s), _ptr(sat_q),
+                             ctypes.c_int64(spitch), _ptr(maps), method, N, stages, ds, EW, int(persist), ctas,
+                             _ptr(cand) if cand_thr is not None else None, _ptr(cand_count), len(cand),
+                             ctypes.c_float(cand_thr if cand_thr is not None else 0.0), y_base, rows, band)
+        assert got > 0, got
+        n_mma += got
     out = [maps[int(m["map_off"]):int(m["map_off"]) + int(m["mh"]) * int(m["mw"])].reshape(int(m["mh"]), int(m["mw"])) for m in meta]
     return out, n_mma, (cand[:int(cand_count[0])] if cand_thr is not None else None)
 
@@ -1039,6 +1089,15 @@ def test_tensor_core_epilogue_lists_the_candidates_and_takes_box_sum_moments(emu
         listed |= {(k, int(x), int(y), 16, 16, float(got[k][y, x])) for y, x in zip(ys, xs)}
     assert len(listed) >= 2
     assert sorted((int(c["tmpl"]), int(c["x"]), int(c["y"]), int(c["w"]), int(c["h"]), float(c["score"])) for c in cand) == sorted(listed)
+    # band by band: the moments of 16 (then 48) output rows go into a ring that the next band overwrites, each band followed by its
+    # numerator launch (what the library does for template groups whose moment maps exceed the ring budget) -- same maps, mixed
+    # sizes (the smaller map ends earlier than the band), bands that are not a multiple of the tile height, both kernels
+    image, tmpls = _planted(rng, 70, 90, 1, [(16, 16), (12, 21), (16, 16)])
+    ref, _, _ = _host_tensor_maps(emu, image, tmpls, 5, 0, 32)
+    for band, opts in ((16, dict()), (48, dict(EW=12, ctas=3)), (16, dict(persist=False))):
+        got, _, _ = _host_tensor_maps(emu, image, tmpls, 5, 0, 32, box=True, band=band, **opts)
+        for k in range(3):
+            assert np.array_equal(got[k].view(np.uint32), ref[k].view(np.uint32)), (band, opts, k)
 
 
 # ---- float32 branch and masked matching (ncc_float.cu) --------------------------------------------------------------------

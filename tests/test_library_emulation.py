@@ -93,6 +93,38 @@ def test_direct_and_tensor_routes_agree(lib_mtm):
         cd.close()
 
 
+def test_banded_moment_ring_through_the_host_code(lib_mtm, monkeypatch):
+    """The window moments of a template group are produced band by band into a ring (mtm_api.cu: compute_maps), each band
+    followed by its numerator launch.  A 64 KB ring forces several bands on a small scene: hit lists (hits-only search), the
+    N_object = 1 search and the score maps must equal the single-band results bit for bit, for one size, mixed sizes and RGB."""
+    from mtm_b200 import _native
+    from oracle import synth
+    rng = np.random.default_rng(12)
+    temps = [("a", synth.make_template(rng, 20, 24)), ("b", synth.make_template(rng, 20, 24)), ("c", synth.make_template(rng, 14, 31))]
+    img, _ = synth.make_scene(150, 200, [t[1] for t in temps], 3, seed=12)
+    rgb = np.stack([img, np.roll(img, 3, axis=0), 255 - img], axis=2)
+    t_rgb = [("r", np.ascontiguousarray(rgb[30:52, 40:70])), ("s", np.ascontiguousarray(rgb[90:110, 100:124]))]
+    results = []
+    for ring_kb in (None, "64"):
+        if ring_kb:
+            monkeypatch.setenv("MTM_B200_RING_KB", ring_kb)
+        ctx = _native.Context(0)
+        try:
+            hits = lib_mtm.matchTemplates(temps, img, score_threshold=0.5, maxOverlap=0.3, context=ctx)
+            launches = ctx.counters()["kernel_launches"]
+            one = lib_mtm.matchTemplates(temps, img, N_object=1, context=ctx)
+            maps = [lib_mtm.computeScoreMap(t, img, context=ctx) for _, t in temps]
+            hits_rgb = lib_mtm.matchTemplates(t_rgb, rgb, score_threshold=0.6, maxOverlap=0.3, context=ctx)
+            results.append((hits, one, maps, hits_rgb, launches))
+        finally:
+            ctx.close()
+    a, b = results
+    assert b[4] > a[4] + 4, "the small ring did not split the search into bands"
+    assert a[0] == b[0] and len(a[0]) >= 6 and a[1] == b[1] and a[3] == b[3] and len(a[3]) >= 2
+    for ma, mb in zip(a[2], b[2]):
+        assert np.array_equal(ma.view(np.uint32), mb.view(np.uint32))
+
+
 def test_device_resident_images_through_the_real_host_code(lib_mtm):
     """The body of tests/test_gpu_zz_device_inputs.py with host pointers dressed as CUDA arrays (the emulated device's memory IS host
     memory): mtm_set_image_device for uint8 / float32 / uint16 / RGB, searchBox crops as pointer arithmetic, no upload of the image,
