@@ -437,12 +437,35 @@ int ensure_geometry(mtm_ctx* ctx)
         bool box = box_moments_enabled() && box_moments_applicable(ctx);
         for (const TcGroup& g : ctx->tc_groups) box = box && !points_path_preferred(ctx, g.first, g.count);
         ctx->box_ok = box;
-        // ring budget: 48 MB (the 126 MB L2 also holds the image, the Toeplitz slabs and the candidate list); MTM_B200_RING_KB
-        // overrides it (read at every geometry change: the tests force many bands on small images with it)
+        // Two placements of the moments (profiles/README.md, round 2):
+        //  * resident (default): every size's whole map, produced by ONE launch per image before the groups' numerator launches;
+        //  * ring (MTM_B200_RING_KB=<budget>, read at every geometry change): per template group and per band of rows into a
+        //    buffer of that size which the next band overwrites, so that the moments never leave L2.  Measured on
+        //    BASELINE configs[4]: the DRAM traffic of the moment stage disappears, but every band costs the fill and drain of one
+        //    more persistent numerator launch (~25 us each), which outweighs it (sync 6.7 -> 8.7 ms at 96 MB, 10.2 ms at 48 MB).
         const char* ring_env = getenv("MTM_B200_RING_KB");
-        const int64_t ring_bytes = ring_env ? (int64_t)std::max(1, atoi(ring_env)) << 10 : (int64_t)48 << 20;
+        ctx->moments_ring = ring_env != nullptr && box;
+        for (size_t gi = 1; gi < ctx->tc_groups.size() && ctx->moments_ring; ++gi)       // a size shared by two groups: its segment
+            if (size_of[ctx->tc_groups[gi].first] == size_of[ctx->tc_groups[gi].first - 1]) ctx->moments_ring = false;   // cannot sit in both rings
+        const int64_t ring_bytes = ring_env ? (int64_t)std::max(1, atoi(ring_env)) << 10 : 0;
         const int64_t entry_bytes = ctx->img.C == 1 ? 8 : 4 * (ctx->img.C + 1);
+        int mh_all = 1;
+        for (const SizeDesc& sd : ctx->h_sizes) mh_all = std::max(mh_all, sd.mh);
+        if (!ctx->moments_ring) {                               // one band; the segments of every size side by side
+            int64_t moff_all = 0;
+            for (SizeDesc& sd : ctx->h_sizes) {
+                sd.off = moff_all; sd.band = mh_all;
+                moff_all += mom_segment(sd.mw, mh_all);
+            }
+            ctx->moments_total = moff_all;
+        }
+        for (TcGroup& g : ctx->tc_groups) {                     // (two groups of equal-sized templates share their sizes)
+            g.size_first = size_of[g.first];
+            g.size_count = size_of[g.first + g.count - 1] - g.size_first + 1;
+            g.band_rows = mh_all;
+        }
         for (TcGroup& g : ctx->tc_groups) {
+            if (!ctx->moments_ring) break;
             g.size_first = size_of[g.first];
             g.size_count = size_of[g.first + g.count - 1] - g.size_first + 1;
             int mh_max = 1;
@@ -654,6 +677,17 @@ int compute_maps(mtm_ctx* ctx, int method, int tmpl, bool hits_ok)
         if (!box) MTM_TRY(ensure_sat(ctx));
     }
     if (tensor16) { MTM_TRY(mtm_reserve(ctx, ctx->d_acc, ctx->acc_cap, (size_t)ctx->maps_total)); ctx->cand_on = false; }
+    if (tensor && !tensor16 && method == MTM_TM_CCOEFF_NORMED && !ctx->moments_ring && ctx->img_dtype == MTM_U8) {
+        // resident placement: the window moments of every distinct size in one launch
+        bool any_tc = false;
+        for (const TcGroup& g : ctx->tc_groups) any_tc = any_tc || !points_path_preferred(ctx, g.first, g.count);
+        if (any_tc) {
+            int mh_all = 1;
+            for (const SizeDesc& sd : ctx->h_sizes) mh_all = std::max(mh_all, sd.mh);
+            if (ctx->box_ok) MTM_TRY(launch_box_moments(ctx, 0, (int)ctx->h_sizes.size(), 0, mh_all));
+            else MTM_TRY(launch_window_moments(ctx, 0, (int)ctx->h_sizes.size()));
+        }
+    }
     MTM_TRY(ncc_bracket_open(ctx));
     ctx->cand_valid = false;
     if (ctx->cand_on) MTM_CUDA(ctx, cudaMemsetAsync(ctx->d_cand_count, 0, sizeof(int32_t), ctx->stream));
@@ -674,8 +708,10 @@ int compute_maps(mtm_ctx* ctx, int method, int tmpl, bool hits_ok)
                 MTM_TRY(launch_ncc_points(ctx, method, g.first, g.count));          // tiny maps of large templates
             } else if (method != MTM_TM_CCOEFF_NORMED) {
                 MTM_TRY(launch_ncc_tc(ctx, g, method, 0, ctx->img.H - g.h_min + 1));       // float64 epilogue on the tables: no moments
+            } else if (!ctx->moments_ring) {
+                MTM_TRY(launch_ncc_tc(ctx, g, method, 0, ctx->img.H - g.h_min + 1));       // resident moments (produced above)
             } else {
-                // default method: the group's window moments band by band (ring in L2), each band followed by its numerator launch
+                // the group's window moments band by band (ring in L2), each band followed by its numerator launch
                 const int mh_max = ctx->img.H - g.h_min + 1;
                 for (int y_base = 0; y_base < mh_max; y_base += g.band_rows) {
                     const int rows = std::min(g.band_rows, mh_max - y_base);

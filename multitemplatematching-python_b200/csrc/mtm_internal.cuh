@@ -173,6 +173,7 @@ struct mtm_ctx {
     uint32_t* d_wS = nullptr; size_t wS_cap = 0;         // window sums S
     float* d_wR = nullptr; size_t wR_cap = 0;            // rsqrt(A*Q - S^2)
     bool moments_valid = false;                          // (unused since the moments are produced per group and band)
+    bool moments_ring = false;                           // moments per group and band into a reused ring (MTM_B200_RING_KB) instead of resident maps
     bool box_ok = false;                                 // window moments by box sums straight from the image (banded); else summed-area tables
     bool tc_attr_set = false;
     bool tcp_attr_set = false;

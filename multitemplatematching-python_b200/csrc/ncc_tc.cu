@@ -499,8 +499,8 @@ __device__ __forceinline__ void epilogue16_c1(const uint32_t (&v)[16], const uin
             bt.idx = better ? idx0 + (uint32_t)(k * mw) : bt.idx;
         }
     }
-    if (any) {
-#pragma unroll 1
+    if (any) {                                                     // rare; unrolled so that r[] stays in registers
+#pragma unroll
         for (int k = 0; k < 16; ++k) {
             const float rc = fminf(1.0f, fmaxf(-1.0f, r[k]));
             if (rc > sink.thr) {
@@ -515,7 +515,9 @@ __device__ __forceinline__ void epilogue16_c1(const uint32_t (&v)[16], const uin
     }
 }
 
-template <int MODE>
+// PIPE: two register sets of moments (the loads run a whole batch ahead; needs ~170 registers: the 8-epilogue-warp kernel).
+// !PIPE: one set, loaded just before the tcgen05.ld of its batch, the next batch prefetched into L1 (128-register kernels).
+template <int MODE, bool PIPE>
 __device__ __forceinline__ void epilogue_tile_c1(const TcParams& p, uint32_t tmem_d, int x0, int y0, int warp, int lane, int parts, BestTrack& bt)
 {
     constexpr bool STORE = MODE != 3;
@@ -541,6 +543,27 @@ __device__ __forceinline__ void epilogue_tile_c1(const TcParams& p, uint32_t tme
     const int c_begin = 16 * ((batches * part) / parts), c_end = 16 * ((batches * (part + 1)) / parts);
     const uint2* sr0 = live ? SRm + mom_index(x, y0 - p.y_base, p.band_rows) : nullptr;      // row c of the tile: sr0 + 16 * c
     auto fast_at = [&](int c0) { return live && !is_const && y0 + c0 + 16 <= t_mh; };
+    if (!PIPE) {
+        for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+            const bool fast = fast_at(c0);
+            uint2 m[16];
+            if (fast) {
+                load_moments16(m, sr0 + 16 * c0);
+                if (c0 + 16 < c_end && fast_at(c0 + 16)) {
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) prefetch_l1(sr0 + 16 * (c0 + 16 + k));
+                }
+            }
+            uint32_t v[16];
+            tmem_ld16(tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c0, v);
+            if (live && y0 + c0 < t_mh) {
+                if (fast) epilogue16_c1<STORE>(v, m, y0 + c0, t_mw, x, area, sumT, ct, out, sink, thr_any, bt, track);
+                else epilogue16<STORE>(v, y0 + c0, t_mh, t_mw, x, (long long)area, (long long)sumT, ct, is_const, SRm, out, sink, false, bt, track,
+                                       p.y_base, p.band_rows);
+            }
+        }
+        return;
+    }
     uint2 m[16], mn[16];
     bool fast = c_begin < c_end && fast_at(c_begin);
     if (fast) load_moments16(m, sr0 + 16 * c_begin);
@@ -690,7 +713,7 @@ ncc_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap)
     __syncthreads();
     tc_fence_after();
     BestTrack bt{-3.0e38f, 0u};
-    if ((MODE == 0 || MODE == 3) && p.C == 1) epilogue_tile_c1<(MODE == 3 ? 3 : 0)>(p, tmem_d, x0, y0, warp, lane, 2, bt);
+    if ((MODE == 0 || MODE == 3) && p.C == 1) epilogue_tile_c1<(MODE == 3 ? 3 : 0), false>(p, tmem_d, x0, y0, warp, lane, 2, bt);
     else epilogue_tile<MODE>(p, tmem_d, x0, y0, warp, lane, 2, bt);
     if (MODE == 3 && p.best) flush_best(p, bt, warp, lane);
     tc_fence_before();
@@ -924,7 +947,7 @@ ncc_tc_persist_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap
             const long long c1 = PROF ? clock64() : 0;
             tc_fence_after();
             if (!PROF || !(p.dbg & 1)) {
-                if ((MODE == 0 || MODE == 3) && p.C == 1) epilogue_tile_c1<(MODE == 3 ? 3 : 0)>(p, tmem_base + (uint32_t)b * acc_stride, x0, y0, warp, lane, EW / 4, bt);
+                if ((MODE == 0 || MODE == 3) && p.C == 1) epilogue_tile_c1<(MODE == 3 ? 3 : 0), EW == 8>(p, tmem_base + (uint32_t)b * acc_stride, x0, y0, warp, lane, EW / 4, bt);
                 else epilogue_tile<MODE>(p, tmem_base + (uint32_t)b * acc_stride, x0, y0, warp, lane, EW / 4, bt);
             }
             tc_fence_before();
