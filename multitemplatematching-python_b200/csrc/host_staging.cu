@@ -106,7 +106,7 @@ CopyPool* copy_pool()
     return pool;
 }
 
-constexpr size_t STAGE_CHUNK = 1 << 20;                        // bytes per pinned chunk
+constexpr size_t STAGE_CHUNK = 512 << 10;                      // bytes per pinned chunk: small enough that a 2 MB image already overlaps copy and DMA
 constexpr int STAGE_BUFS = MTM_STAGE_BUFS;
 
 }  // namespace

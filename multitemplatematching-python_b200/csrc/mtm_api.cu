@@ -801,6 +801,31 @@ struct TmplHasher {
     }
 };
 
+// A hash match alone does not prove that the resident template set is the submitted one (a 64-bit non-cryptographic hash can
+// collide): the pixels are compared with the copy kept from the last upload.
+static bool same_pixels(const mtm_ctx* ctx, int n, const void* const* pixels, const int32_t* h, const int32_t* w, size_t elem_bytes)
+{
+    size_t off = 0;
+    for (int t = 0; t < n; ++t) {
+        const size_t bytes = (size_t)h[t] * w[t] * elem_bytes;
+        if (off + bytes > ctx->h_tmpl_copy.size() || memcmp(ctx->h_tmpl_copy.data() + off, pixels[t], bytes) != 0) return false;
+        off += bytes;
+    }
+    return off == ctx->h_tmpl_copy.size();
+}
+static void keep_pixels(mtm_ctx* ctx, int n, const void* const* pixels, const int32_t* h, const int32_t* w, size_t elem_bytes)
+{
+    size_t total = 0;
+    for (int t = 0; t < n; ++t) total += (size_t)h[t] * w[t] * elem_bytes;
+    ctx->h_tmpl_copy.resize(total);
+    size_t off = 0;
+    for (int t = 0; t < n; ++t) {
+        const size_t bytes = (size_t)h[t] * w[t] * elem_bytes;
+        memcpy(ctx->h_tmpl_copy.data() + off, pixels[t], bytes);
+        off += bytes;
+    }
+}
+
 // The candidate list of a search overflowed (more than MTM_CAND_CAP pixels above the threshold): the peak search must stream
 // the score maps.  A hits-only search has none: compute them (no list this time).
 int candidates_overflowed(mtm_ctx* ctx, int method)
@@ -902,9 +927,10 @@ int mtm_set_templates(mtm_ctx* ctx, int n, const void* const* pixels, const int3
         }
         const int dev_dtype = u16 ? MTM_F32 : dtype;
         if (ctx->n_tmpl == n && ctx->tmpl_hash == hasher.h && ctx->tmpl_C == C && ctx->tmpl_dtype == dev_dtype && ctx->tmpl_u16 == u16 &&
-            ctx->tmpl_hash_valid) return MTM_OK;
+            ctx->tmpl_hash_valid && same_pixels(ctx, n, pixels, h, w, (size_t)C * in_esz)) return MTM_OK;
         ctx->tmpl_hash = hasher.h;
         ctx->tmpl_hash_valid = false;           // set again once the upload below has been queued
+        keep_pixels(ctx, n, pixels, h, w, (size_t)C * in_esz);
     }
     // the previous upload may still be reading the pinned staging buffers
     MTM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1061,9 +1087,10 @@ int mtm_set_templates_transformed(mtm_ctx* ctx, int n, const void* const* pixels
         raw_total += ((size_t)h[t] * w[t] * C * esz + 15) / 16 * 16;
     }
     if (ctx->n_tmpl == n_out && ctx->tmpl_hash == hasher.h && ctx->tmpl_C == C && ctx->tmpl_dtype == dtype && !ctx->tmpl_u16 &&
-        !ctx->masked && ctx->tmpl_hash_valid) return MTM_OK;
+        !ctx->masked && ctx->tmpl_hash_valid && same_pixels(ctx, n, pixels, h, w, (size_t)C * esz)) return MTM_OK;
     ctx->tmpl_hash = hasher.h;
     ctx->tmpl_hash_valid = false;
+    keep_pixels(ctx, n, pixels, h, w, (size_t)C * esz);
     // the previous upload may still be reading the pinned staging buffer
     MTM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     MTM_TRY(reserve_pinned(ctx, ctx->h_tmpl_stage, ctx->tmpl_stage_cap, raw_total + 64));

@@ -152,7 +152,8 @@ struct mtm_ctx {
     TmplPix8* d_pix8 = nullptr; size_t pix8_cap = 0;           // per-template offset / pitch inside an arena
     int64_t slab_plane = 0;                                    // bytes between the high- and low-byte Toeplitz slabs in d_slabs
     double* d_acc = nullptr; size_t acc_cap = 0;               // exact numerator maps (double) of the 16-bit path
-    uint64_t tmpl_hash = 0; bool tmpl_hash_valid = false;   // content hash of the resident template set
+    uint64_t tmpl_hash = 0; bool tmpl_hash_valid = false;   // content hash of the resident template set ...
+    std::vector<uint8_t> h_tmpl_copy;                       // ... and the submitted pixels themselves (compared on a hash match)
     bool geometry_valid = false;         // map offsets computed for (image, templates)
     bool masked = false;                 // templates carry masks (methods 0 / 3): d_tmpl = T*M^2, d_tmpl_centred = M^2
     bool masked_image_valid = false;     // pixf / pixf2 hold the current image

@@ -429,7 +429,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_d
     const uint32_t* Sm = tm ? p.S + tm->mom_off : nullptr;
     const float* Rm = tm ? p.rsD + tm->mom_off : nullptr;
     const uint2* SRm = tm ? reinterpret_cast<const uint2*>(p.S) + tm->mom_off : nullptr;   // C == 1: interleaved {S, rsD}
-    CandSink sink{p.cand, p.cand_count, p.cand_cap, p.cand_thr, tm ? p.order[tsel] : 0, tm ? tm->w : 0, tm ? tm->h : 0};
+    CandSink sink{is_const ? nullptr : p.cand, p.cand_count, p.cand_cap, p.cand_thr, tm ? p.order[tsel] : 0, tm ? tm->w : 0, tm ? tm->h : 0};
     const float thr_eff = p.cand ? p.cand_thr : 3.0e38f;       // scores never exceed 1: no list, no candidates
     // N is a multiple of 16: the `parts` warps of a lane quarter split the 16-column batches
     const int batches = p.N >> 4, part = warp >> 2;
@@ -535,7 +535,8 @@ __device__ __forceinline__ void epilogue_tile_c1(const TcParams& p, uint32_t tme
     const bool is_const = tm ? (tm->is_const != 0) : false;
     float* out = tm ? p.maps + tm->map_off : nullptr;
     const uint2* SRm = tm ? reinterpret_cast<const uint2*>(p.S) + tm->mom_off : nullptr;
-    CandSink sink{p.cand, p.cand_count, p.cand_cap, p.cand_thr, tm ? p.order[tsel] : 0, tm ? tm->w : 0, tm ? tm->h : 0};
+    // (a constant template's TM_CCOEFF_NORMED map is 1 everywhere: peak_local_max of a constant map is empty, so it lists nothing)
+    CandSink sink{is_const ? nullptr : p.cand, p.cand_count, p.cand_cap, p.cand_thr, tm ? p.order[tsel] : 0, tm ? tm->w : 0, tm ? tm->h : 0};
     // the accumulated test runs on the UNclamped score in MODE 3: thresholds outside (-1, 1) are decided by the clamped re-test
     float thr_any = 3.0e38f;                                          // no list: never
     if (p.cand) thr_any = p.cand_thr >= 1.0f ? 3.0e38f : (p.cand_thr < -1.0f ? -3.0e38f : p.cand_thr);

@@ -22,11 +22,12 @@ namespace {
 // test (8 extra loads, L1/L2 hits) is only run for the pixels above the threshold.
 __global__ void peaks2d_kernel(const TmplMeta* __restrict__ meta, const float* __restrict__ maps,
                                float thr32, int minimize, DevHit* __restrict__ hits, int cap,
-                               int32_t* __restrict__ count, int32_t* __restrict__ nontrivial)
+                               int32_t* __restrict__ count, int32_t* __restrict__ nontrivial, int skip_const)
 {
     const TmplMeta& tm = meta[blockIdx.y];
     const int mh = tm.mh, mw = tm.mw;
     if (mh == 1 || mw == 1) return;                          // handled by peaks1d_kernel
+    if (skip_const && tm.is_const) return;                   // TM_CCOEFF_NORMED map of a constant template: all 1 -> no peaks (nontrivial stays 0)
     const int64_t n = (int64_t)mh * mw;
     const float* m = maps + tm.map_off;                      // 128-byte aligned (map offsets are multiples of 32)
     const float sgn = minimize ? -1.0f : 1.0f;
@@ -227,11 +228,11 @@ resolve_candidates_kernel(const TmplMeta* __restrict__ meta, int n_tmpl, DevHit*
 
 // N_object == 1 of a hits-only search: the epilogues of the numerator kernels raised best[t] (flush_best, ncc_tc.cu).
 __global__ void emit_best_keys_kernel(const TmplMeta* __restrict__ meta, int n_tmpl, const unsigned long long* __restrict__ best,
-                                      DevHit* __restrict__ hits, int32_t* __restrict__ count)
+                                      DevHit* __restrict__ hits, int32_t* __restrict__ count, int cap)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t == 0) count[0] = n_tmpl;
-    if (t >= n_tmpl) return;
+    if (t >= n_tmpl || t >= cap) return;
     const TmplMeta& tm = meta[t];
     const unsigned long long key = best[t];
     const uint32_t idx = 0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull);
@@ -266,11 +267,11 @@ __global__ void argbest_kernel(const TmplMeta* __restrict__ meta, const float* _
 
 __global__ void emit_best_kernel(const TmplMeta* __restrict__ meta, int n_tmpl, const float* __restrict__ maps,
                                  const unsigned long long* __restrict__ best, DevHit* __restrict__ hits,
-                                 int32_t* __restrict__ count)
+                                 int32_t* __restrict__ count, int cap)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t == 0) count[0] = n_tmpl;
-    if (t >= n_tmpl) return;
+    if (t == 0) count[0] = n_tmpl;                           // more templates than the block holds: the host grows it and repeats
+    if (t >= n_tmpl || t >= cap) return;
     const TmplMeta& tm = meta[t];
     const uint32_t idx = 0xFFFFFFFFu - (uint32_t)(best[t] & 0xFFFFFFFFull);
     DevHit h;
@@ -298,7 +299,7 @@ int launch_peaks(mtm_ctx* ctx, int method, int64_t n_object, float thr32, double
     if (bx > bx_cap) bx = bx_cap;
     if (bx < 1) bx = 1;
     if (n_object == 1 && ctx->best_valid) {                  // hits-only search: the numerator kernels' epilogues found the arg-max
-        emit_best_keys_kernel<<<(nt + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_meta, nt, ctx->d_best, ctx->hitsA(), ctx->countA());
+        emit_best_keys_kernel<<<(nt + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_meta, nt, ctx->d_best, ctx->hitsA(), ctx->countA(), ctx->hit_cap);
         MTM_LAUNCH_CHECK(ctx);
         return MTM_OK;
     }
@@ -310,7 +311,7 @@ int launch_peaks(mtm_ctx* ctx, int method, int64_t n_object, float thr32, double
         argbest_kernel<<<dim3(bx, nt), 256, 0, ctx->stream>>>(ctx->d_meta, ctx->d_maps, minimize, ctx->d_best);
         MTM_LAUNCH_CHECK(ctx);
         emit_best_kernel<<<(nt + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_meta, nt, ctx->d_maps, ctx->d_best,
-                                                                   ctx->hitsA(), ctx->countA());
+                                                                   ctx->hitsA(), ctx->countA(), ctx->hit_cap);
         MTM_LAUNCH_CHECK(ctx);
         return MTM_OK;
     }
@@ -339,7 +340,7 @@ int launch_peaks(mtm_ctx* ctx, int method, int64_t n_object, float thr32, double
     if (any2d) {
         peaks2d_kernel<<<dim3(bx, nt), 256, 0, ctx->stream>>>(ctx->d_meta, ctx->d_maps, t32, minimize,
                                                               ctx->hitsA(), ctx->hit_cap, ctx->countA(),
-                                                              ctx->d_nontrivial);
+                                                              ctx->d_nontrivial, method == MTM_TM_CCOEFF_NORMED && ctx->img_dtype == MTM_U8 ? 1 : 0);
         MTM_LAUNCH_CHECK(ctx);
     }
     if (any1d) {

@@ -158,7 +158,7 @@ extern "C" int emu_postprocess(const TmplMeta* meta, int nt, const float* maps, 
     if (n_object == 1) {
         memset(best, 0, nt * sizeof(unsigned long long));
         emu_launch_coop(dim3(bx, nt), dim3(256), [&] { argbest_kernel(meta, maps, minimize, best); });
-        emu_launch(dim3((nt + 127) / 128), dim3(128), [&] { emit_best_kernel(meta, nt, maps, best, hitsA, countA); });
+        emu_launch(dim3((nt + 127) / 128), dim3(128), [&] { emit_best_kernel(meta, nt, maps, best, hitsA, countA, cap); });
     } else if (n_cand >= 0) {
         int32_t cc = n_cand;
         emu_launch(dim3(4), dim3(64), [&] { verify_candidates_kernel(meta, nt, maps, cand, &cc, cand_cap, hitsA, cap, countA, nontrivial); });
@@ -166,7 +166,7 @@ extern "C" int emu_postprocess(const TmplMeta* meta, int nt, const float* maps, 
         memset(nontrivial, 0, nt * sizeof(int32_t));
         const float t32 = minimize ? -thr32 : thr32;
         const double t64 = minimize ? -thr : thr;
-        if (any2d) emu_launch_coop(dim3(bx, nt), dim3(256), [&] { peaks2d_kernel(meta, maps, t32, minimize, hitsA, cap, countA, nontrivial); });
+        if (any2d) emu_launch_coop(dim3(bx, nt), dim3(256), [&] { peaks2d_kernel(meta, maps, t32, minimize, hitsA, cap, countA, nontrivial, 0); });
         if (any1d) emu_launch(dim3((nt + 63) / 64), dim3(64), [&] { peaks1d_kernel(meta, nt, maps, t32, t64, minimize, hitsA, cap, countA, nontrivial); });
     }
     *route = 0;

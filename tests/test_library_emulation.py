@@ -100,7 +100,8 @@ def test_banded_moment_ring_through_the_host_code(lib_mtm, monkeypatch):
     from mtm_b200 import _native
     from oracle import synth
     rng = np.random.default_rng(12)
-    temps = [("a", synth.make_template(rng, 20, 24)), ("b", synth.make_template(rng, 20, 24)), ("c", synth.make_template(rng, 14, 31))]
+    # (distinct sizes: a size shared by two launch groups keeps the resident placement)
+    temps = [("a", synth.make_template(rng, 20, 24)), ("b", synth.make_template(rng, 22, 26)), ("c", synth.make_template(rng, 14, 31))]
     img, _ = synth.make_scene(150, 200, [t[1] for t in temps], 3, seed=12)
     rgb = np.stack([img, np.roll(img, 3, axis=0), 255 - img], axis=2)
     t_rgb = [("r", np.ascontiguousarray(rgb[30:52, 40:70])), ("s", np.ascontiguousarray(rgb[90:110, 100:124]))]
