@@ -175,7 +175,7 @@ constexpr int B1_PX = 8;
 constexpr int B1_COLS = B1_THREADS * B1_PX;           // 2048 image columns per strip
 constexpr int B1_WARPS = B1_THREADS / 32;
 
-__global__ void __launch_bounds__(B1_THREADS, 3)
+__global__ void __launch_bounds__(B1_THREADS, 4)
 box_moments_c1_kernel(const BoxParams p)
 {
     __shared__ __align__(16) uint2 P[2][B1_COLS + 8];  // exclusive prefix INSIDE the owning warp's 256 columns: {S, Q mod 2^32}

@@ -780,9 +780,8 @@ __device__ __forceinline__ void issue_rows_any(int nk, uint32_t tmem_d, uint32_t
     }
 }
 
-template <bool PROF, int EW, int MODE>
-__global__ void __launch_bounds__(32 * (EW + 3), 1)   // EW = 8: 352 threads, up to 184 registers (the pipelined epilogue holds two batches of moments); EW = 12: 480 threads, 136
-ncc_tc_persist_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap)
+template <bool PROF, int EW, int MODE, bool PIPE>
+__device__ __forceinline__ void ncc_tc_persist_body(const TcParams& p, const CUtensorMap& tmap)
 {
     constexpr int TCP_THREADS = 32 * (EW + 3);
     constexpr int TCP_EPI_THREADS = 32 * EW;
@@ -948,7 +947,7 @@ ncc_tc_persist_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap
             const long long c1 = PROF ? clock64() : 0;
             tc_fence_after();
             if (!PROF || !(p.dbg & 1)) {
-                if ((MODE == 0 || MODE == 3) && p.C == 1) epilogue_tile_c1<(MODE == 3 ? 3 : 0), EW == 8>(p, tmem_base + (uint32_t)b * acc_stride, x0, y0, warp, lane, EW / 4, bt);
+                if ((MODE == 0 || MODE == 3) && p.C == 1) epilogue_tile_c1<(MODE == 3 ? 3 : 0), PIPE>(p, tmem_base + (uint32_t)b * acc_stride, x0, y0, warp, lane, EW / 4, bt);
                 else epilogue_tile<MODE>(p, tmem_base + (uint32_t)b * acc_stride, x0, y0, warp, lane, EW / 4, bt);
             }
             tc_fence_before();
@@ -961,6 +960,24 @@ ncc_tc_persist_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap
     tc_fence_before();
     __syncthreads();
     if (warp == EW) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// EW = 8: 352 threads, 168 registers (the pipelined epilogue holds two batches of moments); EW = 12: 480 threads, 128.
+template <bool PROF, int EW, int MODE>
+__global__ void __launch_bounds__(32 * (EW + 3), 1)
+ncc_tc_persist_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap)
+{
+    ncc_tc_persist_body<PROF, EW, MODE, EW == 8>(p, tmap);
+}
+
+// The 8-epilogue-warp kernel held to 128 registers (one set of moments, no load pipelining): 11 warps x 4096 registers leave
+// exactly the 20 480 registers a box-moment CTA needs, so that the moment kernel of ANOTHER stream can run beside it (throughput
+// mode: several contexts per GPU).  MTM_B200_LEAN=1.
+template <int MODE>
+__global__ void __maxnreg__(128)                    // (cannot be combined with __launch_bounds__; launched with 352 threads)
+ncc_tc_persist_lean_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap)
+{
+    ncc_tc_persist_body<false, 8, MODE, false>(p, tmap);
 }
 
 // Expands the templates of one group into Toeplitz slabs (see the header comment).
@@ -1121,7 +1138,7 @@ int launch_i8_peak(mtm_ctx* ctx, int n, int iters)
 struct TcEnv {
     int force_n = 0, ds = 0, ew = 0, pdbg = 0, mom_cs = -1;
     size_t smem_soft = 0;
-    bool persist_off = false, prof = false, mom_rows = false, tma_off = false;
+    bool persist_off = false, prof = false, mom_rows = false, tma_off = false, lean = false;
     TcEnv()
     {
         auto num = [](const char* name) { const char* v = getenv(name); return v ? atoi(v) : 0; };
@@ -1135,6 +1152,7 @@ struct TcEnv {
         mom_cs = getenv("MTM_B200_MOM_CS") ? num("MTM_B200_MOM_CS") : -1;
         mom_rows = num("MTM_B200_MOM_ROWS") != 0;
         tma_off = getenv("MTM_B200_TMA") && num("MTM_B200_TMA") == 0;
+        lean = num("MTM_B200_LEAN") != 0;
     }
 };
 static const TcEnv& tc_env()
@@ -1327,6 +1345,8 @@ static int launch_ncc_tc_impl(mtm_ctx* ctx, const TcGroup& g, int method, const 
                 MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_kernel<false, 12, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
                 MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_kernel<false, 8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
                 MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_kernel<false, 12, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+                MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_lean_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+                MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_persist_lean_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
                 ctx->tcp_attr_set = true;
             }
             const int grid_p = std::min(p.tiles_total, ctx->sm_count);
@@ -1348,12 +1368,14 @@ static int launch_ncc_tc_impl(mtm_ctx* ctx, const TcGroup& g, int method, const 
                 else ncc_tc_persist_kernel<false, 8, 1><<<grid_p, 32 * 11, smem_bytes, ctx->stream>>>(p, tmap);
             } else if (kmode == 3) {
                 if (ew == 12) ncc_tc_persist_kernel<false, 12, 3><<<grid_p, 32 * 15, smem_bytes, ctx->stream>>>(p, tmap);
+                else if (tc_env().lean) ncc_tc_persist_lean_kernel<3><<<grid_p, 32 * 11, smem_bytes, ctx->stream>>>(p, tmap);
                 else ncc_tc_persist_kernel<false, 8, 3><<<grid_p, 32 * 11, smem_bytes, ctx->stream>>>(p, tmap);
             } else if (ew == 12) {
                 if (prof) ncc_tc_persist_kernel<true, 12, 0><<<grid_p, 32 * 15, smem_bytes, ctx->stream>>>(p, tmap);
                 else ncc_tc_persist_kernel<false, 12, 0><<<grid_p, 32 * 15, smem_bytes, ctx->stream>>>(p, tmap);
             } else {
                 if (prof) ncc_tc_persist_kernel<true, 8, 0><<<grid_p, 32 * 11, smem_bytes, ctx->stream>>>(p, tmap);
+                else if (tc_env().lean) ncc_tc_persist_lean_kernel<0><<<grid_p, 32 * 11, smem_bytes, ctx->stream>>>(p, tmap);
                 else ncc_tc_persist_kernel<false, 8, 0><<<grid_p, 32 * 11, smem_bytes, ctx->stream>>>(p, tmap);
             }
             MTM_LAUNCH_CHECK(ctx);

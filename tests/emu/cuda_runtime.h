@@ -34,6 +34,7 @@ static dim3 threadIdx, blockIdx, blockDim, gridDim;      // threadIdx follows th
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
+#define __maxnreg__(...)
 #define __grid_constant__
 #define __shared__ static
 #define __align__(n) __attribute__((aligned(n)))
