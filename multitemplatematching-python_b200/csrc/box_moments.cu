@@ -175,7 +175,7 @@ constexpr int B1_PX = 8;
 constexpr int B1_COLS = B1_THREADS * B1_PX;           // 2048 image columns per strip
 constexpr int B1_WARPS = B1_THREADS / 32;
 
-__global__ void __launch_bounds__(B1_THREADS, 4)
+__global__ void __launch_bounds__(B1_THREADS, 3)
 box_moments_c1_kernel(const BoxParams p)
 {
     __shared__ __align__(16) uint2 P[2][B1_COLS + 8];  // exclusive prefix INSIDE the owning warp's 256 columns: {S, Q mod 2^32}
@@ -234,6 +234,8 @@ box_moments_c1_kernel(const BoxParams p)
 
     const uint32_t area = (uint32_t)sd.h * (uint32_t)sd.w;
     uint2* out_base = reinterpret_cast<uint2*>(p.S) + sd.off;
+    const int seg_off = (tid + sd.w) >> 8;
+    const bool wide = sd.w > B1_THREADS;
     uint2 w_in = load_row(y0 + sd.h - 1), w_out = load_row(y0);
     for (int y = y0; y < y1; ++y) {
         const int buf = (y - y0) & 1;
@@ -266,24 +268,32 @@ box_moments_c1_kernel(const BoxParams p)
         wb[0] = make_uint2(0u, 0u);
 #pragma unroll
         for (int k = 0; k < B1_WARPS; ++k) { const uint2 t = wtot[buf][k]; wb[k + 1] = make_uint2(wb[k].x + t.x, wb[k].y + t.y); }
-        // ring entry of (x0 + xl, y): ((x >> 4) * band + r) * 16 + (x & 15); x0 is a multiple of 16, so x & 15 == xl & 15
-        uint2* out_row = out_base + ((int64_t)(x0 >> 4) * sd.band + (y - p.y_begin)) * 16;
+        // Window position xl = tid + 256 j lies in segment j; its right edge xl + w in segment j + seg_off, seg_off = (tid + w) >> 8:
+        // the same for every j of a thread.  Ring entry of (x0 + xl, y): ((x >> 4) * band + r) * 16 + (x & 15) with x0 a multiple of
+        // 16 -> a per-thread base plus j * 16 * band * 16 entries.
+        const uint2* pl = &P[buf][tid];
+        const uint2* pr = pl + sd.w;
+        uint2* outp = out_base + ((int64_t)((x0 >> 4) + (tid >> 4)) * sd.band + (y - p.y_begin)) * 16 + (tid & 15);
+        const int64_t dst_step = (int64_t)sd.band * (B1_THREADS / 16) * 16;
 #pragma unroll
         for (int j = 0; j < B1_PX; ++j) {
-            const int xl = tid + j * B1_THREADS;                    // segment j
+            const int xl = tid + j * B1_THREADS;
             if (xl >= strip_out || x0 + xl >= sd.mw) continue;
-            const int xr = xl + sd.w;                               // segment j or later (w may span several)
-            const uint2 lo = P[buf][xl], hi = P[buf][xr];
-            uint2 hb = wb[j];                                       // xr lies in segment j .. j+4 (w <= 1024): selects, no indexed register array
-            const int seg = xr >> 8;
+            const uint2 lo = pl[j * B1_THREADS], hi = pr[j * B1_THREADS];
+            uint2 hb;
+            if (wide) {                                             // windows wider than a segment (w > 256): general selection
+                hb = wb[j];
 #pragma unroll
-            for (int k = 1; k <= 4; ++k)
-                if (j + k <= B1_WARPS && seg == j + k) hb = wb[j + k];
+                for (int k = 1; k <= 4; ++k)
+                    if (j + k <= B1_WARPS && seg_off == k) hb = wb[j + k];
+            } else {
+                hb = seg_off ? wb[j + 1 <= B1_WARPS ? j + 1 : B1_WARPS] : wb[j];
+            }
             const uint32_t s = (hi.x + hb.x) - (lo.x + wb[j].x);
             const uint32_t qs = (hi.y + hb.y) - (lo.y + wb[j].y);
             const unsigned long long d1 = (unsigned long long)area * qs - (unsigned long long)s * s;
-            const float rs = d1 ? rsqrtf((float)d1) : 0.0f;
-            out_row[(int64_t)(xl >> 4) * sd.band * 16 + (xl & 15)] = make_uint2(s, __float_as_uint(rs));
+            const float rs = d1 ? mtm_rsqrt_normal((float)d1) : 0.0f;      // d1 >= 1: never subnormal
+            outp[j * dst_step] = make_uint2(s, __float_as_uint(rs));
         }
         sub_row(w_out);
         w_in = n_in; w_out = n_out;

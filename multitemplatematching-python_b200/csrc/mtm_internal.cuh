@@ -321,6 +321,19 @@ __device__ __forceinline__ void prep_mode0(DevHit& h, const TmplMeta* __restrict
     h.key = (tm.mh == 1 || tm.mw == 1) ? 1.0f : 0.0f;
 }
 
+// 1 / sqrt(x) for NORMAL positive x (callers pass integers >= 1 converted to float): the bare MUFU.RSQ, without rsqrtf()'s
+// subnormal scaling -- same bits as rsqrtf() on such inputs.
+__device__ __forceinline__ float mtm_rsqrt_normal(float x)
+{
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return rsqrtf(x);
+#endif
+}
+
 __device__ __forceinline__ uint32_t ordered_f32(float f) {
     f += 0.0f;                                    // -0 -> +0
     uint32_t u = __float_as_uint(f);

@@ -420,8 +420,7 @@ finalize_small_kernel(DevHit* __restrict__ hits, int cap, int32_t* __restrict__ 
     uint4* dst = reinterpret_cast<uint4*>(mirror);
     const int tid = threadIdx.x;
     if (tid < 2) dst[tid] = reinterpret_cast<const uint4*>(hdr)[tid];          // 32-byte header
-    for (int i = tid; i < 2 * n; i += blockDim.x) dst[2 + i] = src[i];         // 32-byte hits
-    __threadfence_system();
+    for (int i = tid; i < 2 * n; i += blockDim.x) dst[2 + i] = src[i];         // 32-byte hits (the host reads them after a stream synchronise: no fence needed)
 }
 
 }  // namespace

@@ -114,6 +114,10 @@ static inline void tma_load_2d(void* dst_smem, const CUtensorMap* tmap, int x, i
     emu_mbar_complete_tx(bar, (uint32_t)tmap->box_rows * 16u);
 }
 
+// setmaxnreg (warpgroup register reallocation): nothing to model
+template <uint32_t N> static inline void reg_release() {}
+template <uint32_t N> static inline void reg_acquire() {}
+
 // ---- tensor memory ------------------------------------------------------------------------------------------------
 static uint32_t emu_tmem[128][512];
 static uint32_t emu_tmem_cols = 0;
