@@ -114,10 +114,6 @@ static bool encode_tile_map(CUtensorMap* out, const uint8_t* base, int64_t pitch
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
-// Warpgroup register reallocation (setmaxnreg): the control warps of the persistent kernel (slab producer, MMA issuer, tile
-// loader + one idle warp = one warpgroup) hand most of their registers to the epilogue warpgroups.
-template <uint32_t N> __device__ __forceinline__ void reg_release() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
-template <uint32_t N> __device__ __forceinline__ void reg_acquire() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols)
 {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
@@ -739,7 +735,7 @@ ncc_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap)
 // EW = 12 serves small templates, whose tiles spend longer in the epilogue than in the MMAs.
 constexpr int TCP_MAX_STAGES = 8;
 constexpr double TCP_EPI_CLK_PER_ROW = 100.0;   // measured: epilogue clocks per output row of a tile with 8 epilogue warps
-constexpr int TCP_STAGERS = 64;                 // register staging (fallback when no tensor map can be made): warps EW+2, EW+3
+constexpr int TCP_STAGERS = 32;                 // register staging (fallback when no tensor map can be made): one stager warp
 constexpr size_t TCP_SMEM_SOFT = 188 * 1024;     // preferred ceiling of the persistent kernel's shared memory (see launch_ncc_tc)
 
 // MMAs of `rows` consecutive template rows: NK K-chunks each.  Only the low descriptor words move
@@ -787,8 +783,7 @@ __device__ __forceinline__ void issue_rows_any(int nk, uint32_t tmem_d, uint32_t
 template <bool PROF, int EW, int MODE, bool PIPE>
 __device__ __forceinline__ void ncc_tc_persist_body(const TcParams& p, const CUtensorMap& tmap)
 {
-    constexpr int TCP_THREADS = 32 * (EW + 4);              // EW epilogue warps + one control warpgroup (producer, MMA issuer, tile loader, spare)
-    constexpr uint32_t EPI_REGS = EW == 8 ? 224 : 152;      // after the control warpgroup has shrunk to 56 registers per thread
+    constexpr int TCP_THREADS = 32 * (EW + 3);
     constexpr int TCP_EPI_THREADS = 32 * EW;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -831,8 +826,6 @@ __device__ __forceinline__ void ncc_tc_persist_body(const TcParams& p, const CUt
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp >= EW) {
-    reg_release<56>();                                          // one instruction for the whole control warpgroup, before its roles part
     if (warp == EW) {
         // ===== slab producer: the slab sequence of a tile repeats for every tile; the ring position runs on.
         // The whole warp walks the loop (warp-uniform control flow, uniform registers); one elected lane issues.
@@ -906,8 +899,8 @@ __device__ __forceinline__ void ncc_tc_persist_body(const TcParams& p, const CUt
             q[0] = w_tile; q[1] = w_acc; q[2] = w_full; q[3] = clock64() - m_begin;
         }
         __syncwarp();
-    } else if (p.tma) {
-        // ===== image tile loader: one warp, one elected lane per tile feeds the TMA unit (warp EW + 3 has nothing to do)
+    } else if (warp >= EW + 2 && p.tma) {
+        // ===== image tile loader: one warp, one elected lane per tile feeds the TMA unit (launched with EW + 3 warps)
         if (warp == EW + 2) {
             const uint32_t bytes = tma_tile_bytes(kb_img, p.tma_rc, p.tma_chunks);
             for (int i = 0; i < my_tiles; ++i) {
@@ -922,7 +915,7 @@ __device__ __forceinline__ void ncc_tc_persist_body(const TcParams& p, const CUt
                 __syncwarp();
             }
         }
-    } else {
+    } else if (warp >= EW + 2) {
         // ===== image tile stagers (register staging) =====
         const int t = tid - 32 * (EW + 2);
         long long w_te = 0, w_work = 0;
@@ -940,10 +933,8 @@ __device__ __forceinline__ void ncc_tc_persist_body(const TcParams& p, const CUt
             if (PROF) { w_te += c1 - c0; w_work += clock64() - c1; }
         }
         if (PROF && t == 0) { p.prof[16 * blockIdx.x + 6] = w_te; p.prof[16 * blockIdx.x + 7] = w_work; }
-    }
     } else {
         // ===== epilogue warps =====
-        reg_acquire<EPI_REGS>();
         long long w_af = 0, w_epi = 0;
         BestTrack bt{-3.0e38f, 0u};
         for (int i = 0; i < my_tiles; ++i) {
@@ -971,17 +962,17 @@ __device__ __forceinline__ void ncc_tc_persist_body(const TcParams& p, const CUt
     if (warp == EW) tmem_dealloc(tmem_base, tmem_cols);
 }
 
-// EW = 8: 384 threads launched at 168 registers; EW = 12: 512 threads at 128.  Inside, the control warpgroup drops to 40 registers and
-// the epilogue warpgroups grow to 232 / 152 (setmaxnreg), which is what the pipelined epilogue (two batches of moments) needs.
+// EW = 8: 352 threads, 168 registers (the pipelined epilogue holds two batches of moments); EW = 12: 480 threads, 128.
 template <bool PROF, int EW, int MODE>
-__global__ void __launch_bounds__(32 * (EW + 4), 1)
+__global__ void __launch_bounds__(32 * (EW + 3), 1)
 ncc_tc_persist_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap)
 {
-    ncc_tc_persist_body<PROF, EW, MODE, true>(p, tmap);
+    ncc_tc_persist_body<PROF, EW, MODE, EW == 8>(p, tmap);
 }
 
-// The 8-epilogue-warp kernel held to 128 registers at launch (experiment, MTM_B200_LEAN=1: room for a box-moment CTA of another
-// stream on the same SM; measured neutral, profiles/README.md).
+// The 8-epilogue-warp kernel held to 128 registers (one set of moments, no load pipelining): 11 warps x 4096 registers leave
+// exactly the 20 480 registers a box-moment CTA needs, so that the moment kernel of ANOTHER stream can run beside it (throughput
+// mode: several contexts per GPU).  MTM_B200_LEAN=1.
 template <int MODE>
 __global__ void __maxnreg__(128)                    // (cannot be combined with __launch_bounds__; launched with 352 threads)
 ncc_tc_persist_lean_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap)
@@ -1370,22 +1361,22 @@ static int launch_ncc_tc_impl(mtm_ctx* ctx, const TcGroup& g, int method, const 
             p.dbg = pdbg;
             const int ew = best_ew;
             if (kmode == 2) {
-                if (ew == 12) ncc_tc_persist_kernel<false, 12, 2><<<grid_p, 32 * 16, smem_bytes, ctx->stream>>>(p, tmap);
-                else ncc_tc_persist_kernel<false, 8, 2><<<grid_p, 32 * 12, smem_bytes, ctx->stream>>>(p, tmap);
+                if (ew == 12) ncc_tc_persist_kernel<false, 12, 2><<<grid_p, 32 * 15, smem_bytes, ctx->stream>>>(p, tmap);
+                else ncc_tc_persist_kernel<false, 8, 2><<<grid_p, 32 * 11, smem_bytes, ctx->stream>>>(p, tmap);
             } else if (kmode == 1) {
-                if (ew == 12) ncc_tc_persist_kernel<false, 12, 1><<<grid_p, 32 * 16, smem_bytes, ctx->stream>>>(p, tmap);
-                else ncc_tc_persist_kernel<false, 8, 1><<<grid_p, 32 * 12, smem_bytes, ctx->stream>>>(p, tmap);
+                if (ew == 12) ncc_tc_persist_kernel<false, 12, 1><<<grid_p, 32 * 15, smem_bytes, ctx->stream>>>(p, tmap);
+                else ncc_tc_persist_kernel<false, 8, 1><<<grid_p, 32 * 11, smem_bytes, ctx->stream>>>(p, tmap);
             } else if (kmode == 3) {
-                if (ew == 12) ncc_tc_persist_kernel<false, 12, 3><<<grid_p, 32 * 16, smem_bytes, ctx->stream>>>(p, tmap);
-                else if (tc_env().lean) ncc_tc_persist_lean_kernel<3><<<grid_p, 32 * 12, smem_bytes, ctx->stream>>>(p, tmap);
-                else ncc_tc_persist_kernel<false, 8, 3><<<grid_p, 32 * 12, smem_bytes, ctx->stream>>>(p, tmap);
+                if (ew == 12) ncc_tc_persist_kernel<false, 12, 3><<<grid_p, 32 * 15, smem_bytes, ctx->stream>>>(p, tmap);
+                else if (tc_env().lean) ncc_tc_persist_lean_kernel<3><<<grid_p, 32 * 11, smem_bytes, ctx->stream>>>(p, tmap);
+                else ncc_tc_persist_kernel<false, 8, 3><<<grid_p, 32 * 11, smem_bytes, ctx->stream>>>(p, tmap);
             } else if (ew == 12) {
-                if (prof) ncc_tc_persist_kernel<true, 12, 0><<<grid_p, 32 * 16, smem_bytes, ctx->stream>>>(p, tmap);
-                else ncc_tc_persist_kernel<false, 12, 0><<<grid_p, 32 * 16, smem_bytes, ctx->stream>>>(p, tmap);
+                if (prof) ncc_tc_persist_kernel<true, 12, 0><<<grid_p, 32 * 15, smem_bytes, ctx->stream>>>(p, tmap);
+                else ncc_tc_persist_kernel<false, 12, 0><<<grid_p, 32 * 15, smem_bytes, ctx->stream>>>(p, tmap);
             } else {
-                if (prof) ncc_tc_persist_kernel<true, 8, 0><<<grid_p, 32 * 12, smem_bytes, ctx->stream>>>(p, tmap);
-                else if (tc_env().lean) ncc_tc_persist_lean_kernel<0><<<grid_p, 32 * 12, smem_bytes, ctx->stream>>>(p, tmap);
-                else ncc_tc_persist_kernel<false, 8, 0><<<grid_p, 32 * 12, smem_bytes, ctx->stream>>>(p, tmap);
+                if (prof) ncc_tc_persist_kernel<true, 8, 0><<<grid_p, 32 * 11, smem_bytes, ctx->stream>>>(p, tmap);
+                else if (tc_env().lean) ncc_tc_persist_lean_kernel<0><<<grid_p, 32 * 11, smem_bytes, ctx->stream>>>(p, tmap);
+                else ncc_tc_persist_kernel<false, 8, 0><<<grid_p, 32 * 11, smem_bytes, ctx->stream>>>(p, tmap);
             }
             MTM_LAUNCH_CHECK(ctx);
             if (prof) {

@@ -210,31 +210,6 @@ __device__ void smem_bitonic(DevHit* sh, int npad, const SortCtx& sc)
     }
 }
 
-// Short lists (the common case: tens of hits; npad <= blockDim.x): every thread ranks its own element against all others (one
-// barrier instead of the log^2 barriers of the bitonic network; equal elements -- only the padding -- keep their index order).
-__device__ void smem_rank_sort(DevHit* sh, int npad, const SortCtx& sc)
-{
-    const int tid = threadIdx.x;
-    DevHit h;
-    int rank = 0;
-    if (tid < npad) {
-        h = sh[tid];
-#pragma unroll 1
-        for (int j = 0; j < npad; ++j) {
-            const DevHit o = sh[j];
-            rank += (hit_less(o, h, sc) || (j < tid && !hit_less(h, o, sc))) ? 1 : 0;
-        }
-    }
-    __syncthreads();
-    if (tid < npad) sh[rank] = h;
-    __syncthreads();
-}
-__device__ __forceinline__ void smem_sort(DevHit* sh, int npad, const SortCtx& sc)
-{
-    if (npad <= (int)blockDim.x) smem_rank_sort(sh, npad, sc);
-    else smem_bitonic(sh, npad, sc);
-}
-
 // do_nms == 0: findMatches order -> written back to `hits` (block A), count[0]/[1] updated.
 // do_nms == 1: ... then MTM.NMS -> `out` (block B), out_count[0] = kept, out_count[1] = raw count.
 // PRESORTED / DO_NMS are compile-time: the launch-latency-bound single CTA then walks ~8 KB of code instead of 32 KB
@@ -280,7 +255,7 @@ finalize_small_body(DevHit* __restrict__ hits, int cap, int32_t* __restrict__ co
     __syncthreads();
     if (!presorted && !do_nms) {                                // findMatches order
         SortCtx sc0{meta, 0, minimize};
-        smem_sort(sh, npad, sc0);
+        smem_bitonic(sh, npad, sc0);
 #pragma unroll 1
         for (int i = tid; i < n; i += nth) store_hit(hits + i, sh[i]);
 #pragma unroll 1
@@ -299,7 +274,7 @@ finalize_small_body(DevHit* __restrict__ hits, int cap, int32_t* __restrict__ co
             if (sh[i].tmpl != 0x7fffffff) sh[i].key = ascending ? 1.0f - sh[i].score : sh[i].score;   // seq = row-major index (prep_mode0)
         __syncthreads();
         SortCtx sc2{meta, 2, minimize};
-        smem_sort(sh, npad, sc2);
+        smem_bitonic(sh, npad, sc2);
     }
     if (n <= 1) {
         if (tid == 0) { if (n == 1) out[0] = sh[0]; out_count[0] = n; }
@@ -331,46 +306,12 @@ finalize_small_body(DevHit* __restrict__ hits, int cap, int32_t* __restrict__ co
             if (i < n) sh[i].key = ascending ? 1.0f - sh[i].score : sh[i].score;
         __syncthreads();
         SortCtx sc1{meta, 1, minimize};
-        smem_sort(sh, npad, sc1);
+        smem_bitonic(sh, npad, sc1);
     }
     // greedy scan by warp 0 alone (warp votes instead of block barriers); kept_idx lists the survivors
     __shared__ unsigned short kept_idx[FIN_CAP];
     const long long limit = n_object < 0 ? (long long)n : n_object;
-    constexpr int SUP_N = 256;                                  // lists up to this long: suppression matrix + bit scan
-    __shared__ uint32_t sup_bits[SUP_N][SUP_N / 32];
-    if (n <= SUP_N && n <= nth) {
-        // (1) every thread fills the row of its own hit: bit j set <=> the EARLIER hit j suppresses it (the same overlap rule as the
-        // scan below); (2) one warp walks the list: hit i is kept iff none of the kept earlier hits suppresses it.
-        if (tid < n) {
-            const DevHit cand = sh[tid];
-            uint32_t word = 0u;
-#pragma unroll 1
-            for (int j = 0; j < tid; ++j) {
-                const DevHit& o = sh[j];
-                const bool meet = (cand.x < o.x + o.w && o.x < cand.x + cand.w && cand.y < o.y + o.h && o.y < cand.y + cand.h) ||
-                                  (cand.w * cand.h + o.w * o.h <= 0);
-                if (meet && !(rect_overlap(cand, o) <= max_overlap)) word |= 1u << (j & 31);
-                if ((j & 31) == 31) { sup_bits[tid][j >> 5] = word; word = 0u; }
-            }
-            for (int wd = tid >> 5; wd < SUP_N / 32; ++wd) { sup_bits[tid][wd] = word; word = 0u; }     // the partial word, then zeros
-        }
-        __syncthreads();
-        if (tid < 32) {
-            uint32_t kept_word = 0u;                            // lane l: bits of the kept hits 32 l .. 32 l + 31
-            int kept = 0;
-#pragma unroll 1
-            for (int i = 0; i < n && kept < limit; ++i) {
-                if (!(sh[i].key > thr32)) break;                // sorted by key: the rest fails too
-                const uint32_t row = tid < SUP_N / 32 ? sup_bits[i][tid] : 0u;
-                if (!__any_sync(0xffffffffu, (row & kept_word) != 0u)) {
-                    if (tid == (i >> 5)) kept_word |= 1u << (i & 31);
-                    if (tid == 0) kept_idx[kept] = (unsigned short)i;
-                    ++kept;
-                }
-            }
-            if (tid == 0) s_kept = kept;
-        }
-    } else if (tid < 32) {
+    if (tid < 32) {
         int kept = 0;
 #pragma unroll 1
         for (int i = 0; i < n && kept < limit; ++i) {

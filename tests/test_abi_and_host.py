@@ -242,3 +242,28 @@ def test_hit_buffer_growth_and_strided_inputs_without_a_device(mtm):
     ctx.set_image(rgb[2:12, 3:13])
     tag, ptr, H, W, C, code, stride = ctx._lib.calls[-1]
     assert (H, W, C, code, stride) == (10, 10, 3, _native.MTM_F32, 40 * 3 * 4)
+
+
+def test_rendezvous_hands_the_id_of_rank0_to_every_rank(mtm, monkeypatch):
+    """mtm_b200.rendezvous.exchange_id: the 128 id bytes made on rank 0 reach the other ranks over a socket on
+    MASTER_PORT + 117 (no torch); world 1 needs no socket."""
+    import socket
+    import threading
+    from mtm_b200 import _native, rendezvous
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    monkeypatch.setenv("MASTER_ADDR", "127.0.0.1")
+    monkeypatch.setenv("MTM_B200_COMM_PORT", str(port))
+    payload = bytes(range(128))
+    assert len(payload) == _native.COMM_ID_BYTES
+    got = [None] * 3
+
+    def rank(r):
+        got[r] = rendezvous.exchange_id(r, 3, (lambda: payload) if r == 0 else (lambda: b"never called"), timeout=30.0)
+
+    threads = [threading.Thread(target=rank, args=(r,)) for r in (1, 2, 0)]     # the clients may come up before the listener
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=60)
+    assert got == [payload] * 3
+    assert rendezvous.exchange_id(0, 1, lambda: b"solo") == b"solo"

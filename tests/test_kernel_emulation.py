@@ -303,7 +303,7 @@ extern "C" long long emu_ncc_tc(const uint8_t* img, int64_t pitch, int H, int W,
         p.ds = std::max(1, std::min(h, ds)); p.stages = stages;
         if (stages < 2 || stages > TCP_MAX_STAGES || 256 + 2 * tile_b + (size_t)stages * p.ds * g.slab_bytes > 227 * 1024) return -2;
         p.tiles_x = gx; p.tiles_total = gx * ((p.rows + N - 1) / N);
-        const dim3 grid((unsigned)std::min(p.tiles_total, ctas)), block(32 * (EW + 4));
+        const dim3 grid((unsigned)std::min(p.tiles_total, ctas)), block(32 * (EW + 3));
         if (EW == 12) { if (kmode) emu_launch_coop(grid, block, [&] { ncc_tc_persist_kernel<false, 12, 1>(p, tmap); }); else emu_launch_coop(grid, block, [&] { ncc_tc_persist_kernel<false, 12, 0>(p, tmap); }); }
         else { if (kmode) emu_launch_coop(grid, block, [&] { ncc_tc_persist_kernel<false, 8, 1>(p, tmap); }); else emu_launch_coop(grid, block, [&] { ncc_tc_persist_kernel<false, 8, 0>(p, tmap); }); }
     } else {
@@ -438,7 +438,7 @@ extern "C" long long emu_ncc_tc16(const uint16_t* src, int H, int W, float* pixf
         emu_dyn_smem = smem_store + ((1024 - (reinterpret_cast<uintptr_t>(smem_store) & 1023)) & 1023);
         memset(emu_dyn_smem, 0xCD, 227 * 1024);
         emu_tc_reset();
-        emu_launch_coop(dim3((unsigned)std::min(p.tiles_total, ctas)), dim3(32 * 12), [&] { ncc_tc_persist_kernel<false, 8, 2>(p, tmap); });
+        emu_launch_coop(dim3((unsigned)std::min(p.tiles_total, ctas)), dim3(32 * 11), [&] { ncc_tc_persist_kernel<false, 8, 2>(p, tmap); });
         mmas += emu_mma_count;
     }
     emu_dyn_smem = nullptr;
