@@ -323,11 +323,16 @@ static int set_image_impl(mtm_ctx* ctx, const void* pixels, int H, int W, int C,
         if (C == 2) return mtm_fail(ctx, MTM_ERR_UNSUPPORTED, "mtm_set_image: 2-channel float32 images");
         im.pitch_e = ((int64_t)W * C + 3) / 4 * 4;
         MTM_TRY(mtm_reserve(ctx, im.pixf, ctx->imgf_cap, (size_t)(H * im.pitch_e + 64)));
-        const bool same_shape_f = (im.H == H && im.W == W && im.C == C && ctx->img_dtype == MTM_F32 && ctx->img_u16 == u16);
+        // float32 pixels that are all integers in [0, 65535] (uint16 data cast on the host, mixed uint8 / uint16 inputs after the
+        // reference's float32 cast) take the same exact byte-plane numerator as MTM_U16: detected on the device (MTM_B200_F32_EXACT=0: off)
+        static const bool f32_exact = !(getenv("MTM_B200_F32_EXACT") && atoi(getenv("MTM_B200_F32_EXACT")) == 0);
+        const bool probe = !u16 && C == 1 && f32_exact;
+        const bool same_shape_f = (im.H == H && im.W == W && im.C == C && ctx->img_dtype == MTM_F32 && ctx->img_src_dtype == dtype);
+        ctx->img_src_dtype = dtype;
         im.H = H; im.W = W; im.C = C;
         im.sat_pitch = ((int64_t)W + 1 + 3) / 4 * 4;
         g_marks.mark(ctx, "begin");
-        if (u16) {
+        if (u16 || probe) {
             const int64_t pitch = (((int64_t)W + 64 + 64) + 127) / 128 * 128;      // u8 tile layout of the tensor-core kernel
             const size_t plane_bytes = (size_t)(H * pitch + 256);
             const bool fresh = ctx->img_cap < plane_bytes || ctx->pix_lo_cap < plane_bytes || im.pitch != pitch || !same_shape_f;
@@ -338,6 +343,9 @@ static int set_image_impl(mtm_ctx* ctx, const void* pixels, int H, int W, int C,
                 MTM_CUDA(ctx, cudaMemsetAsync(im.pix_lo, 0, ctx->pix_lo_cap, ctx->stream));
             }
             im.pitch = pitch;
+        }
+        bool planes = u16;
+        if (u16) {
             const uint16_t* src16 = static_cast<const uint16_t*>(pixels);
             int64_t src_stride = row_stride;
             if (!on_device) {
@@ -354,8 +362,13 @@ static int set_image_impl(mtm_ctx* ctx, const void* pixels, int H, int W, int C,
             else
                 MTM_TRY(mtm_upload_rows(ctx, im.pixf, (size_t)im.pitch_e * 4, pixels, (size_t)row_stride, (size_t)W * C * 4, H));
             if (!on_device) ctx->ctr.h2d_bytes += (int64_t)H * W * C * 4;
+            if (probe) {
+                int not_integral = 1;
+                MTM_TRY(launch_f32_split_image(ctx, &not_integral));           // byte planes + "some pixel is no uint16" (one 4-byte read-back)
+                planes = !not_integral;
+            }
         }
-        ctx->img_u16 = u16;
+        ctx->img_u16 = planes;
         dtype = MTM_F32;
         MTM_TRY(mtm_reserve(ctx, im.satf_s, ctx->satf_s_cap, (size_t)C * (H + 1) * im.sat_pitch));
         MTM_TRY(mtm_reserve(ctx, im.satf_q, ctx->satf_q_cap, (size_t)(H + 1) * im.sat_pitch));
@@ -369,8 +382,9 @@ static int set_image_impl(mtm_ctx* ctx, const void* pixels, int H, int W, int C,
     }
     const int64_t pitch = (((int64_t)W * C + 64 * C + 64) + 127) / 128 * 128;
     const bool reshape = (im.H != H || im.W != W || im.C != C);
-    const bool same_shape = !reshape && ctx->img_dtype == dtype && !ctx->img_u16;
+    const bool same_shape = !reshape && ctx->img_dtype == dtype && ctx->img_src_dtype == MTM_U8;
     ctx->img_u16 = false;
+    ctx->img_src_dtype = MTM_U8;
     MTM_TRY(mtm_reserve(ctx, im.pix, ctx->img_cap, (size_t)(H * pitch + 256)));
     if (reshape || !same_shape || im.pitch != pitch) MTM_CUDA(ctx, cudaMemsetAsync(im.pix, 0, ctx->img_cap, ctx->stream));
     im.pitch = pitch; im.H = H; im.W = W; im.C = C;
@@ -926,15 +940,29 @@ int mtm_set_templates(mtm_ctx* ctx, int n, const void* const* pixels, const int3
             hasher.bytes(pixels[t], (size_t)h[t] * w[t] * C * in_esz);
         }
         const int dev_dtype = u16 ? MTM_F32 : dtype;
-        if (ctx->n_tmpl == n && ctx->tmpl_hash == hasher.h && ctx->tmpl_C == C && ctx->tmpl_dtype == dev_dtype && ctx->tmpl_u16 == u16 &&
+        if (ctx->n_tmpl == n && ctx->tmpl_hash == hasher.h && ctx->tmpl_C == C && ctx->tmpl_dtype == dev_dtype && ctx->tmpl_src_dtype == dtype &&
             ctx->tmpl_hash_valid && same_pixels(ctx, n, pixels, h, w, (size_t)C * in_esz)) return MTM_OK;
         ctx->tmpl_hash = hasher.h;
         ctx->tmpl_hash_valid = false;           // set again once the upload below has been queued
         keep_pixels(ctx, n, pixels, h, w, (size_t)C * in_esz);
     }
+    // float32 templates whose pixels are all integers in [0, 65535] get byte planes too (see set_image_impl): with such an image
+    // the numerator is then exact on the tensor cores, otherwise they are plain float32 templates
+    static const bool f32_exact = !(getenv("MTM_B200_F32_EXACT") && atoi(getenv("MTM_B200_F32_EXACT")) == 0);
+    bool f32_planes = dtype == MTM_F32 && C == 1 && f32_exact;
+    for (int t = 0; t < n && f32_planes; ++t) {
+        const float* f = static_cast<const float*>(pixels[t]);
+        const size_t count = (size_t)h[t] * w[t];
+        for (size_t k = 0; k < count; ++k) {
+            const float v = f[k];
+            if (!(v >= 0.0f && v <= 65535.0f && (float)(uint32_t)v == v)) { f32_planes = false; break; }
+        }
+    }
+    const bool planes16 = u16 || f32_planes;
     // the previous upload may still be reading the pinned staging buffers
     MTM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->n_tmpl = 0; ctx->geometry_valid = false;          // a failed upload leaves "no templates set", not a half-updated list
+    ctx->tmpl_src_dtype = dtype;
     ctx->h_meta.assign(n, TmplMeta{});
     size_t total = 0;
     for (int t = 0; t < n; ++t) {
@@ -964,7 +992,7 @@ int mtm_set_templates(mtm_ctx* ctx, int n, const void* const* pixels, const int3
             for (int y = 0; y < m.h; ++y) memcpy(dst + (size_t)y * m.wp, src + (size_t)y * row, row);
         }
     }
-    if (u16) {
+    if (planes16) {
         // byte planes for the exact tensor-core numerator: [high-byte arena][low-byte arena], u8 packing (pitch w rounded up to 4)
         std::vector<TmplPix8> pix8((size_t)n);
         size_t total8 = 0;
@@ -975,9 +1003,10 @@ int mtm_set_templates(mtm_ctx* ctx, int n, const void* const* pixels, const int3
         std::vector<uint8_t> planes(2 * total8, 0);
         for (int t = 0; t < n; ++t) {
             const uint16_t* s16 = static_cast<const uint16_t*>(pixels[t]);
+            const float* f32 = static_cast<const float*>(pixels[t]);
             for (int y = 0; y < h[t]; ++y)
                 for (int x = 0; x < w[t]; ++x) {
-                    const uint16_t v = s16[(size_t)y * w[t] + x];
+                    const uint16_t v = u16 ? s16[(size_t)y * w[t] + x] : (uint16_t)f32[(size_t)y * w[t] + x];
                     planes[(size_t)pix8[t].off + (size_t)y * pix8[t].wp + x] = (uint8_t)(v >> 8);
                     planes[total8 + (size_t)pix8[t].off + (size_t)y * pix8[t].wp + x] = (uint8_t)(v & 255u);
                 }
@@ -990,7 +1019,7 @@ int mtm_set_templates(mtm_ctx* ctx, int n, const void* const* pixels, const int3
         MTM_CUDA(ctx, cudaMemcpyAsync(ctx->d_pix8, pix8.data(), (size_t)n * sizeof(TmplPix8), cudaMemcpyHostToDevice, ctx->stream));
         ctx->ctr.h2d_bytes += (int64_t)(2 * total8);
     }
-    ctx->tmpl_u16 = u16;
+    ctx->tmpl_u16 = planes16;
     if (u16) dtype = MTM_F32;
     MTM_TRY(mtm_reserve(ctx, ctx->d_tmpl, ctx->tmpl_cap, total + 64));
     MTM_CUDA(ctx, cudaMemcpyAsync(ctx->d_tmpl, ctx->h_tmpl_stage, total, cudaMemcpyHostToDevice, ctx->stream));

@@ -144,7 +144,8 @@ struct mtm_ctx {
     uint8_t* h_tmpl_stage = nullptr; size_t tmpl_stage_cap = 0;   // pinned
     int tmpl_C = 0, tmpl_dtype = -1;
     // MTM_U16 uploads: float32 everywhere (img_dtype / tmpl_dtype == MTM_F32) plus the byte planes for the exact tensor-core numerator
-    bool img_u16 = false, tmpl_u16 = false;
+    bool img_u16 = false, tmpl_u16 = false;                    // byte planes are resident (MTM_U16 uploads, and float32 data found to be integers in [0, 65535])
+    int img_src_dtype = -1, tmpl_src_dtype = -1;               // dtypes the resident image / templates were submitted with
     uint16_t* d_raw16 = nullptr; size_t raw16_cap = 0;         // staging of the raw 16-bit image
     size_t pix_lo_cap = 0;
     uint8_t* d_tmpl8 = nullptr; size_t tmpl8_cap = 0;          // packed u8 templates: high-byte arena, then low-byte arena
@@ -293,6 +294,8 @@ int launch_i8_peak(mtm_ctx* ctx, int n, int iters);      // measurement helper: 
 // 16-bit path: one byte-plane product of the group accumulated into ctx->d_acc (img_plane / tmpl_plane: 0 = high, 1 = low bytes)
 int launch_ncc_tc_accum(mtm_ctx* ctx, const TcGroup& g, int img_plane, int tmpl_plane, double weight, bool first);
 int launch_u16_split_image(mtm_ctx* ctx, const uint16_t* src, int64_t src_stride_bytes);
+// byte planes of the resident float32 image (im.pixf) when every pixel is an integer in [0, 65535]; *not_integral otherwise (synchronises)
+int launch_f32_split_image(mtm_ctx* ctx, int* not_integral);
 int launch_cc16_epilogue(mtm_ctx* ctx, int method, int tmpl);
 // augmentation / area downscale (transform.cu)
 int launch_transform(mtm_ctx* ctx, const uint8_t* d_src, uint8_t* d_dst, const XformDesc* d_descs, int n_out,

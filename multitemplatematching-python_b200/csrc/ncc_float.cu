@@ -442,6 +442,22 @@ __global__ void u16_split_image_kernel(const uint16_t* __restrict__ src, int64_t
     }
 }
 
+// float32 image whose pixels may all be integers in [0, 65535]: the same byte planes, and a flag when some pixel is not
+__global__ void f32_split_image_kernel(const float* __restrict__ pixf, int64_t pitch_e, int H, int W, uint8_t* __restrict__ hi,
+                                       uint8_t* __restrict__ lo, int64_t pitch, int32_t* __restrict__ not_integral)
+{
+    const int y = blockIdx.y;
+    int bad = 0;
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < W; x += gridDim.x * blockDim.x) {
+        const float f = pixf[(int64_t)y * pitch_e + x];
+        const uint32_t v = (f >= 0.0f && f <= 65535.0f) ? (uint32_t)f : 0u;
+        if (!((float)v == f)) bad = 1;                       // negative, too large, fractional, NaN
+        hi[(int64_t)y * pitch + x] = (uint8_t)(v >> 8);
+        lo[(int64_t)y * pitch + x] = (uint8_t)(v & 255u);
+    }
+    if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(not_integral, 1);
+}
+
 // exact numerator (double) + float64 window statistics -> OpenCV's epilogue, any method.  blockIdx.y = template.
 __global__ void cc16_epilogue_kernel(const double* __restrict__ acc, float* __restrict__ maps, const TmplMeta* __restrict__ meta,
                                      int tmpl_first, int method, const double* __restrict__ sat_s, const double* __restrict__ sat_q,
@@ -468,6 +484,22 @@ int launch_u16_split_image(mtm_ctx* ctx, const uint16_t* src, int64_t src_stride
     dim3 grid((unsigned)std::min(8, (im.W + 255) / 256), (unsigned)im.H);
     u16_split_image_kernel<<<grid, 256, 0, ctx->stream>>>(src, src_stride_bytes / 2, im.H, im.W, im.pixf, im.pitch_e, im.pix, im.pix_lo, im.pitch);
     MTM_LAUNCH_CHECK(ctx);
+    return MTM_OK;
+}
+
+int launch_f32_split_image(mtm_ctx* ctx, int* not_integral)
+{
+    ImageDev& im = ctx->img;
+    int32_t* flag = ctx->d_cand_count + 8;                   // a spare word of the 64-byte counter block
+    MTM_CUDA(ctx, cudaMemsetAsync(flag, 0, sizeof(int32_t), ctx->stream));
+    dim3 grid((unsigned)std::min(8, (im.W + 255) / 256), (unsigned)im.H);
+    f32_split_image_kernel<<<grid, 256, 0, ctx->stream>>>(im.pixf, im.pitch_e, im.H, im.W, im.pix, im.pix_lo, im.pitch, flag);
+    MTM_LAUNCH_CHECK(ctx);
+    int32_t h = 1;
+    MTM_CUDA(ctx, cudaMemcpyAsync(&h, flag, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    MTM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->ctr.d2h_bytes += (int64_t)sizeof h;
+    *not_integral = h;
     return MTM_OK;
 }
 

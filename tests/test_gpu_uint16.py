@@ -93,13 +93,13 @@ def test_uint16_match_templates_vs_port_and_fp32_kernel(mtm, ctxs):
 
 
 def test_uint16_mixed_inputs_keep_the_float32_route(mtm, ctxs):
-    """uint16 image with a float32 (or RGB) template set is plain float32 data: default context works, the
-    tensor-only context refuses."""
+    """uint16 image with a float32 template that is NOT integer-valued is plain float32 data: default context works, the
+    tensor-only context refuses.  (An integer-valued float32 template takes the exact byte-plane route: next test.)"""
     from mtm_b200 import _native
     from oracle import ncc_exact
     ct, _ = ctxs
     img, temps = _scene16(13)
-    tf = temps[0].astype(np.float32)
+    tf = temps[0].astype(np.float32) + np.float32(0.25)
     got = mtm.computeScoreMap(tf, img)
     exact = ncc_exact.match_template_exact(img.astype(np.float32), tf, use_fft=False)
     assert np.max(np.abs(got.astype(np.float64) - exact)) <= 1e-4
@@ -110,3 +110,52 @@ def test_uint16_mixed_inputs_keep_the_float32_route(mtm, ctxs):
     t8 = np.ascontiguousarray(img8[20:52, 30:62])
     m = mtm.computeScoreMap(t8, img8, context=ct)
     assert np.unravel_index(int(m.argmax()), m.shape) == (20, 30) and abs(float(m.max()) - 1.0) < 1e-6
+
+
+@pytest.mark.parametrize("method", [5, 1])
+def test_float32_integer_valued_data_takes_the_exact_tensor_route(mtm, ctxs, method):
+    """float32 arrays holding integers in [0, 65535] (uint16 data cast by the caller, or a uint16 image with a float32 template after
+    the reference's float32 cast, MTM/__init__.py:71-74) are detected on upload and matched through the byte planes like MTM_U16:
+    the tensor-only context accepts them and the map equals the MTM_U16 one bit for bit."""
+    from mtm_b200 import _native
+    from oracle import ncc_exact
+    ct, cd = ctxs
+    img, temps = _scene16(17 + method, full_range=True)
+    imgf, tf = img.astype(np.float32), temps[0].astype(np.float32)
+    want16 = mtm.computeScoreMap(temps[0], img, method=method, context=ct)
+    for (t_in, i_in) in ((tf, imgf), (tf, img), (temps[0], imgf)):
+        got = mtm.computeScoreMap(t_in, i_in, method=method, context=ct)
+        assert np.array_equal(got, want16)
+    exact = ncc_exact.match_template_exact(imgf, tf, method=method, use_fft=False)
+    assert np.max(np.abs(want16.astype(np.float64) - exact)) <= 1e-4 * max(1.0, float(np.abs(exact).max()))
+    # one fractional / negative / too large pixel anywhere in the image: plain float32 data again
+    for bad in (0.5, -1.0, 65536.0, np.nan):
+        img_bad = imgf.copy()
+        img_bad[-1, -1] = bad
+        with pytest.raises(_native.NativeError):
+            mtm.computeScoreMap(tf, img_bad, method=method, context=ct)
+    img_bad = imgf.copy()
+    img_bad[3, 5] += 0.5
+    got = mtm.computeScoreMap(tf, img_bad, method=method)
+    exact = ncc_exact.match_template_exact(img_bad, tf, method=method, use_fft=False)
+    assert np.max(np.abs(got.astype(np.float64) - exact)) <= 1e-4 * max(1.0, float(np.abs(exact).max()))
+    # ... and the integer image right after it on the same context takes the planes again
+    assert np.array_equal(mtm.computeScoreMap(tf, imgf, method=method, context=ct), want16)
+
+
+def test_float32_integer_valued_match_templates(mtm, ctxs):
+    from oracle import mtm_port
+    ct, _ = ctxs
+    img, temps = _scene16(19, H=300, W=420, sizes=((32, 32), (24, 40), (32, 32), (48, 20)))
+    labelled16 = [("t%d" % i, t) for i, t in enumerate(temps)]
+    labelledf = [(n, t.astype(np.float32)) for n, t in labelled16]
+    imgf = img.astype(np.float32)
+    for kw in (dict(score_threshold=0.5, maxOverlap=0.25), dict(N_object=1)):
+        want = mtm_port.match_templates(labelledf, imgf, **kw)
+        assert len(want) > 0
+        got = mtm.matchTemplates(labelledf, imgf, context=ct, **kw)
+        assert_hits_equal(got, want)
+        assert_hits_equal(got, mtm.matchTemplates(labelled16, img, context=ct, **kw), tol=0.0)
+    batch = mtm.matchTemplatesBatch(labelledf, [imgf, imgf[::-1].copy()], context=ct)
+    assert_hits_equal(batch[0], mtm.matchTemplates(labelledf, imgf, context=ct), tol=0.0)
+    assert_hits_equal(batch[1], mtm.matchTemplates(labelledf, imgf[::-1].copy(), context=ct), tol=0.0)
