@@ -146,6 +146,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Exact A*CC - S*sumT (operands below 2^32, the difference inside +-2^63) rounded to float.  Written in PTX so that the
+// operands stay 32-bit for ptxas: two IMAD.WIDE.U32 (the second with the negated 64-bit addend) and one I2F.S64; the C++
+// form compiled to 64 x 32-bit multiplies with zero high words (six integer instructions per pixel).
+__device__ __forceinline__ float n1_to_float(uint32_t area, uint32_t cc, uint32_t s, uint32_t sumT)
+{
+    float f;
+    asm("{\n\t.reg .u64 t, u;\n\tmul.wide.u32 t, %3, %4;\n\tmul.wide.u32 u, %1, %2;\n\tsub.s64 u, u, t;\n\tcvt.rn.f32.s64 %0, u;\n\t}"
+        : "=f"(f) : "r"(area), "r"(cc), "r"(s), "r"(sumT));
+    return f;
+}
+
 // K-major, no-swizzle shared-memory matrix descriptor (sm_100 "version 1").
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
 {
@@ -183,8 +194,8 @@ __device__ __forceinline__ void prefetch_moments16(const uint2* __restrict__ SR,
 struct BestTrack { float r; uint32_t idx; };
 
 template <bool STORE>
-__device__ __forceinline__ void epilogue16(const uint32_t (&v)[16], int y_first, int mh, int mw, int x, long long area,
-                                           long long sumT, float ct, bool is_const, const uint2* __restrict__ SR,
+__device__ __forceinline__ void epilogue16(const uint32_t (&v)[16], int y_first, int mh, int mw, int x, uint32_t area,
+                                           uint32_t sumT, float ct, bool is_const, const uint2* __restrict__ SR,
                                            float* __restrict__ out, const CandSink& sink, bool prefetch_next,
                                            BestTrack& bt, bool track, int y_base, int band)
 {
@@ -199,8 +210,8 @@ __device__ __forceinline__ void epilogue16(const uint32_t (&v)[16], int y_first,
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
         const int y = y_first + k;
-        const long long n1 = area * (long long)v[k] - (long long)m[k].x * sumT;
-        float r = (float)n1 * __uint_as_float(m[k].y) * ct;
+        // (32-bit operands: A <= 66051 and sumT <= 255 * 66051 on the tensor path)
+        float r = n1_to_float(area, v[k], m[k].x, sumT) * __uint_as_float(m[k].y) * ct;
         r = fminf(1.0f, fmaxf(-1.0f, r));
         if (is_const) r = 1.0f;
         if (y < mh) {
@@ -238,8 +249,7 @@ __device__ __forceinline__ void epilogue16_fast(const uint32_t (&v)[16], int y_f
     }
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-        const long long n1 = (long long)((unsigned long long)area * v[k]) - (long long)((unsigned long long)m[k].x * sumT);
-        float r = (float)n1 * __uint_as_float(m[k].y) * ct;
+        float r = n1_to_float(area, v[k], m[k].x, sumT) * __uint_as_float(m[k].y) * ct;
         r = fminf(1.0f, fmaxf(-1.0f, r));
         if (STORE) o[(uint32_t)(k * mw)] = r;
         if (!STORE && track) { const bool better = r > bt.r; bt.r = better ? r : bt.r; bt.idx = better ? idx0 + (uint32_t)(k * mw) : bt.idx; }
@@ -451,7 +461,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_d
         if (p.C == 1) {
             // the prefetched rows of the next batch must exist: +32
             if (!is_const && y0 + c0 + 32 <= t_mh) epilogue16_fast<STORE>(v, y0 + c0, t_mw, x, (uint32_t)area, (uint32_t)sumT, ct, SRm, out, sink, thr_eff, c0 + 16 < c_end, bt, track, p.y_base, p.band_rows);
-            else epilogue16<STORE>(v, y0 + c0, t_mh, t_mw, x, area, sumT, ct, is_const, SRm, out, sink, c0 + 16 < c_end, bt, track, p.y_base, p.band_rows);
+            else epilogue16<STORE>(v, y0 + c0, t_mh, t_mw, x, (uint32_t)area, (uint32_t)sumT, ct, is_const, SRm, out, sink, c0 + 16 < c_end, bt, track, p.y_base, p.band_rows);
         }
         else if (p.C == 3) epilogue16_mc<3, STORE>(v, y0 + c0, t_mh, t_mw, x, area, sumT_c, ct, is_const, Sm, p.mom_plane, Rm, out, sink, bt, track, p.y_base, p.band_rows);
         else epilogue16_mc<4, STORE>(v, y0 + c0, t_mh, t_mw, x, area, sumT_c, ct, is_const, Sm, p.mom_plane, Rm, out, sink, bt, track, p.y_base, p.band_rows);
@@ -479,8 +489,7 @@ __device__ __forceinline__ void epilogue16_c1(const uint32_t (&v)[16], const uin
     bool any = false;
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-        const long long n1 = (long long)((unsigned long long)area * v[k]) - (long long)((unsigned long long)m[k].x * sumT);
-        float rk = (float)n1 * __uint_as_float(m[k].y) * ct;
+        float rk = n1_to_float(area, v[k], m[k].x, sumT) * __uint_as_float(m[k].y) * ct;
         if (STORE) rk = fminf(1.0f, fmaxf(-1.0f, rk));
         r[k] = rk;
         any = any || (rk > thr_any);
@@ -515,51 +524,88 @@ __device__ __forceinline__ void epilogue16_c1(const uint32_t (&v)[16], const uin
     }
 }
 
+// Per-lane constants of the single-channel default-method epilogue.  The template a TMEM lane serves, its map geometry and the
+// warp's column range do not change from tile to tile of a launch: fetched once per kernel (two dependent global loads and
+// ~300 instructions that every epilogue warp used to repeat for every tile).
+struct LaneC1 {
+    const uint2* SRm; float* out;
+    int t_mh, t_mw, xo;                                          // xo: the lane's x offset inside a tile (xo & 15 == lane & 15)
+    uint32_t area, sumT; float ct, thr_any;
+    int c_begin, c_end;                                          // accumulator columns of this warp
+    int tmpl, w, h;
+    bool has_tmpl, is_const;
+};
+
+__device__ __forceinline__ LaneC1 lane_c1_setup(const TcParams& p, int warp, int lane, int parts)
+{
+    LaneC1 L;
+    const int m_row = 32 * (warp & 3) + lane;
+    int tsel;
+    if (p.mode == 0) { tsel = m_row >> 4; L.xo = m_row & 15; }
+    else { tsel = 0; L.xo = 16 * (7 - (m_row >> 4)) + (m_row & 15); }
+    const TmplMeta* tm = (tsel < p.count) ? &p.meta[p.order[tsel]] : nullptr;
+    L.has_tmpl = tm != nullptr;
+    L.t_mh = tm ? min(tm->mh, p.y_base + p.rows) : 0;           // rows end with the map or with the band
+    L.t_mw = tm ? tm->mw : 0;
+    L.area = tm ? (uint32_t)(tm->h * tm->w) : 0u;
+    L.sumT = tm ? (uint32_t)tm->isum[0] : 0u;                    // <= 255 * 66051 on the tensor path
+    L.ct = tm ? tm->inv_sqrt_d2 : 0.f;
+    L.is_const = tm ? (tm->is_const != 0) : false;
+    L.out = tm ? p.maps + tm->map_off : nullptr;
+    L.SRm = tm ? reinterpret_cast<const uint2*>(p.S) + tm->mom_off : nullptr;
+    L.tmpl = tm ? p.order[tsel] : 0; L.w = tm ? tm->w : 0; L.h = tm ? tm->h : 0;
+    // the accumulated test runs on the UNclamped score in MODE 3: thresholds outside (-1, 1) are decided by the clamped re-test
+    L.thr_any = 3.0e38f;                                          // no list: never
+    if (p.cand) L.thr_any = p.cand_thr >= 1.0f ? 3.0e38f : (p.cand_thr < -1.0f ? -3.0e38f : p.cand_thr);
+    // N is a multiple of 16: the `parts` warps of a lane quarter split the 16-column batches
+    const int batches = p.N >> 4, part = warp >> 2;
+    L.c_begin = 16 * ((batches * part) / parts); L.c_end = 16 * ((batches * (part + 1)) / parts);
+    return L;
+}
+
+// The 16 lanes that serve one template share every 128-byte line of the tile-major moment ring (16 x-offsets = one line, rows
+// 128 bytes apart): ONE prefetch instruction per warp pulls a whole batch into L1 -- lane k of a half fetches row k.
+// `lead`: ring entry of the half's first lane (x & 15 == 0) at tile row 0, nullptr when that lane has no pixel in this tile.
+__device__ __forceinline__ void prefetch_batch(const uint2* lead, int c0, int rows_ok, int lane)
+{
+    const int k = lane & 15;
+    if (lead && k < rows_ok) prefetch_l1(lead + 16 * (c0 + k));
+}
+
 // PIPE: two register sets of moments (the loads run a whole batch ahead; needs ~170 registers: the 8-epilogue-warp kernel).
 // !PIPE: one set, loaded just before the tcgen05.ld of its batch, the next batch prefetched into L1 (128-register kernels).
 template <int MODE, bool PIPE>
-__device__ __forceinline__ void epilogue_tile_c1(const TcParams& p, uint32_t tmem_d, int x0, int y0, int warp, int lane, int parts, BestTrack& bt)
+__device__ __forceinline__ void epilogue_tile_c1(const TcParams& p, const LaneC1& L, uint32_t tmem_d, int x0, int y0, int warp, int lane, BestTrack& bt)
 {
     constexpr bool STORE = MODE != 3;
     const bool track = MODE == 3 && p.best != nullptr;
-    const int m_row = 32 * (warp & 3) + lane;
-    int x, tsel;
-    if (p.mode == 0) { tsel = m_row >> 4; x = x0 + (m_row & 15); }
-    else { tsel = 0; x = x0 + 16 * (7 - (m_row >> 4)) + (m_row & 15); }
-    const TmplMeta* tm = (tsel < p.count) ? &p.meta[p.order[tsel]] : nullptr;
-    const int t_mh = tm ? min(tm->mh, p.y_base + p.rows) : 0, t_mw = tm ? tm->mw : 0;
-    const bool live = tm && (x < t_mw);
-    const uint32_t area = tm ? (uint32_t)(tm->h * tm->w) : 0u;
-    const uint32_t sumT = tm ? (uint32_t)tm->isum[0] : 0u;          // <= 255 * 66051 on the tensor path
-    const float ct = tm ? tm->inv_sqrt_d2 : 0.f;
-    const bool is_const = tm ? (tm->is_const != 0) : false;
-    float* out = tm ? p.maps + tm->map_off : nullptr;
-    const uint2* SRm = tm ? reinterpret_cast<const uint2*>(p.S) + tm->mom_off : nullptr;
+    const int x = x0 + L.xo;
+    const bool live = L.has_tmpl && (x < L.t_mw);
+    const int t_mh = L.t_mh, t_mw = L.t_mw;
+    const uint32_t area = L.area, sumT = L.sumT;
+    const float ct = L.ct;
+    const bool is_const = L.is_const;
+    float* out = L.out;
+    const uint2* SRm = L.SRm;
     // (a constant template's TM_CCOEFF_NORMED map is 1 everywhere: peak_local_max of a constant map is empty, so it lists nothing)
-    CandSink sink{is_const ? nullptr : p.cand, p.cand_count, p.cand_cap, p.cand_thr, tm ? p.order[tsel] : 0, tm ? tm->w : 0, tm ? tm->h : 0};
-    // the accumulated test runs on the UNclamped score in MODE 3: thresholds outside (-1, 1) are decided by the clamped re-test
-    float thr_any = 3.0e38f;                                          // no list: never
-    if (p.cand) thr_any = p.cand_thr >= 1.0f ? 3.0e38f : (p.cand_thr < -1.0f ? -3.0e38f : p.cand_thr);
-    const int batches = p.N >> 4, part = warp >> 2;
-    const int c_begin = 16 * ((batches * part) / parts), c_end = 16 * ((batches * (part + 1)) / parts);
+    CandSink sink{is_const ? nullptr : p.cand, p.cand_count, p.cand_cap, p.cand_thr, L.tmpl, L.w, L.h};
+    const float thr_any = L.thr_any;
+    const int c_begin = L.c_begin, c_end = L.c_end;
     const uint2* sr0 = live ? SRm + mom_index(x, y0 - p.y_base, p.band_rows) : nullptr;      // row c of the tile: sr0 + 16 * c
     auto fast_at = [&](int c0) { return live && !is_const && y0 + c0 + 16 <= t_mh; };
     if (!PIPE) {
+        // the half's first lane: x - (lane & 15); its pixel exists whenever any pixel of the half does
+        const uint2* lead = (L.has_tmpl && !is_const && x - (lane & 15) < t_mw) ? SRm + mom_index(x - (lane & 15), y0 - p.y_base, p.band_rows) : nullptr;
         for (int c0 = c_begin; c0 < c_end; c0 += 16) {
             const bool fast = fast_at(c0);
             uint2 m[16];
-            if (fast) {
-                load_moments16(m, sr0 + 16 * c0);
-                if (c0 + 16 < c_end && fast_at(c0 + 16)) {
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) prefetch_l1(sr0 + 16 * (c0 + 16 + k));
-                }
-            }
+            if (fast) load_moments16(m, sr0 + 16 * c0);
+            if (c0 + 16 < c_end) prefetch_batch(lead, c0 + 16, t_mh - (y0 + c0 + 16), lane);
             uint32_t v[16];
             tmem_ld16(tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c0, v);
             if (live && y0 + c0 < t_mh) {
                 if (fast) epilogue16_c1<STORE>(v, m, y0 + c0, t_mw, x, area, sumT, ct, out, sink, thr_any, bt, track);
-                else epilogue16<STORE>(v, y0 + c0, t_mh, t_mw, x, (long long)area, (long long)sumT, ct, is_const, SRm, out, sink, false, bt, track,
+                else epilogue16<STORE>(v, y0 + c0, t_mh, t_mw, x, area, sumT, ct, is_const, SRm, out, sink, false, bt, track,
                                        p.y_base, p.band_rows);
             }
         }
@@ -575,7 +621,7 @@ __device__ __forceinline__ void epilogue_tile_c1(const TcParams& p, uint32_t tme
         tmem_ld16(tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c0, v);
         if (live && y0 + c0 < t_mh) {
             if (fast) epilogue16_c1<STORE>(v, m, y0 + c0, t_mw, x, area, sumT, ct, out, sink, thr_any, bt, track);
-            else epilogue16<STORE>(v, y0 + c0, t_mh, t_mw, x, (long long)area, (long long)sumT, ct, is_const, SRm, out, sink, false, bt, track,
+            else epilogue16<STORE>(v, y0 + c0, t_mh, t_mw, x, area, sumT, ct, is_const, SRm, out, sink, false, bt, track,
                                    p.y_base, p.band_rows);           // bottom rows of a map / constant template: bounds-tested form
         }
         fast = fast_next;
@@ -587,20 +633,11 @@ __device__ __forceinline__ void epilogue_tile_c1(const TcParams& p, uint32_t tme
 }
 
 // Pulls the window moments of a warp's first batch of the tile into L1 while the accumulator is still being computed.
-__device__ __forceinline__ void epilogue_prefetch_first(const TcParams& p, int x0, int y0, int warp, int lane, int parts)
+__device__ __forceinline__ void epilogue_prefetch_first(const TcParams& p, const LaneC1& L, int x0, int y0, int lane)
 {
-    if (p.C != 1 || p.method != MTM_TM_CCOEFF_NORMED) return;
-    const int m = 32 * (warp & 3) + lane;
-    int x, tsel;
-    if (p.mode == 0) { tsel = m >> 4; x = x0 + (m & 15); }
-    else { tsel = 0; x = x0 + 16 * (7 - (m >> 4)) + (m & 15); }
-    if (tsel >= p.count) return;
-    const TmplMeta* tm = &p.meta[p.order[tsel]];
-    const int t_mh = min(tm->mh, p.y_base + p.rows), t_mw = tm->mw;
-    const int batches = p.N >> 4;
-    const int c_begin = 16 * ((batches * (warp >> 2)) / parts);
-    if (x >= t_mw || y0 + c_begin >= t_mh) return;
-    prefetch_moments16(reinterpret_cast<const uint2*>(p.S) + tm->mom_off, y0 + c_begin - p.y_base, t_mh - p.y_base, p.band_rows, x);
+    const int x_lead = x0 + L.xo - (lane & 15);
+    if (!L.has_tmpl || L.is_const || x_lead >= L.t_mw) return;
+    prefetch_batch(L.SRm + mom_index(x_lead, y0 - p.y_base, p.band_rows), L.c_begin, L.t_mh - (y0 + L.c_begin), lane);
 }
 
 // MODE 3, N_object == 1: the lanes of a warp that serve the same template (mode A: 16, mode B: 32) reduce their best pixel and
@@ -714,7 +751,7 @@ ncc_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap)
     __syncthreads();
     tc_fence_after();
     BestTrack bt{-3.0e38f, 0u};
-    if ((MODE == 0 || MODE == 3) && p.C == 1) epilogue_tile_c1<(MODE == 3 ? 3 : 0), false>(p, tmem_d, x0, y0, warp, lane, 2, bt);
+    if ((MODE == 0 || MODE == 3) && p.C == 1) epilogue_tile_c1<(MODE == 3 ? 3 : 0), false>(p, lane_c1_setup(p, warp, lane, 2), tmem_d, x0, y0, warp, lane, bt);
     else epilogue_tile<MODE>(p, tmem_d, x0, y0, warp, lane, 2, bt);
     if (MODE == 3 && p.best) flush_best(p, bt, warp, lane);
     tc_fence_before();
@@ -743,7 +780,7 @@ constexpr size_t TCP_SMEM_SOFT = 188 * 1024;     // preferred ceiling of the per
 template <int NK>
 __device__ __forceinline__ void issue_rows(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t a_hi, uint32_t b_hi,
                                            uint32_t a_kstep, uint32_t b_kstep, uint32_t slab_step, int rows, uint32_t idesc,
-                                           uint32_t accumulate)
+                                           uint32_t accumulate, uint32_t b_row_step)
 {
     uint32_t al[NK], bl[NK];
 #pragma unroll
@@ -753,29 +790,30 @@ __device__ __forceinline__ void issue_rows(uint32_t tmem_d, uint32_t a_lo, uint3
         for (int k = 0; k < NK; ++k) {
             umma_i8(tmem_d, ((uint64_t)a_hi << 32) | al[k], ((uint64_t)b_hi << 32) | bl[k], idesc, accumulate);
             accumulate = 1;
-            al[k] += slab_step; bl[k] += 1;
+            al[k] += slab_step; bl[k] += b_row_step;
         }
     }
 }
 
+// b_row_step: 1 (one 16-byte image row per template row); 0 only in the profiling knock-out that keeps B in place
 __device__ __forceinline__ void issue_rows_any(int nk, uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t a_hi, uint32_t b_hi,
                                                uint32_t a_kstep, uint32_t b_kstep, uint32_t slab_step, int rows, uint32_t idesc,
-                                               uint32_t accumulate)
+                                               uint32_t accumulate, uint32_t b_row_step)
 {
     switch (nk) {
-        case 1: issue_rows<1>(tmem_d, a_lo, b_lo, a_hi, b_hi, a_kstep, b_kstep, slab_step, rows, idesc, accumulate); break;
-        case 2: issue_rows<2>(tmem_d, a_lo, b_lo, a_hi, b_hi, a_kstep, b_kstep, slab_step, rows, idesc, accumulate); break;
-        case 3: issue_rows<3>(tmem_d, a_lo, b_lo, a_hi, b_hi, a_kstep, b_kstep, slab_step, rows, idesc, accumulate); break;
-        case 4: issue_rows<4>(tmem_d, a_lo, b_lo, a_hi, b_hi, a_kstep, b_kstep, slab_step, rows, idesc, accumulate); break;
-        case 5: issue_rows<5>(tmem_d, a_lo, b_lo, a_hi, b_hi, a_kstep, b_kstep, slab_step, rows, idesc, accumulate); break;
-        case 6: issue_rows<6>(tmem_d, a_lo, b_lo, a_hi, b_hi, a_kstep, b_kstep, slab_step, rows, idesc, accumulate); break;
+        case 1: issue_rows<1>(tmem_d, a_lo, b_lo, a_hi, b_hi, a_kstep, b_kstep, slab_step, rows, idesc, accumulate, b_row_step); break;
+        case 2: issue_rows<2>(tmem_d, a_lo, b_lo, a_hi, b_hi, a_kstep, b_kstep, slab_step, rows, idesc, accumulate, b_row_step); break;
+        case 3: issue_rows<3>(tmem_d, a_lo, b_lo, a_hi, b_hi, a_kstep, b_kstep, slab_step, rows, idesc, accumulate, b_row_step); break;
+        case 4: issue_rows<4>(tmem_d, a_lo, b_lo, a_hi, b_hi, a_kstep, b_kstep, slab_step, rows, idesc, accumulate, b_row_step); break;
+        case 5: issue_rows<5>(tmem_d, a_lo, b_lo, a_hi, b_hi, a_kstep, b_kstep, slab_step, rows, idesc, accumulate, b_row_step); break;
+        case 6: issue_rows<6>(tmem_d, a_lo, b_lo, a_hi, b_hi, a_kstep, b_kstep, slab_step, rows, idesc, accumulate, b_row_step); break;
         default:
             for (int d = 0; d < rows; ++d) {
                 for (int k = 0; k < nk; ++k) {
                     umma_i8(tmem_d, ((uint64_t)a_hi << 32) | (a_lo + k * a_kstep), ((uint64_t)b_hi << 32) | (b_lo + k * b_kstep), idesc, accumulate);
                     accumulate = 1;
                 }
-                a_lo += slab_step; b_lo += 1;
+                a_lo += slab_step; b_lo += b_row_step;
             }
     }
 }
@@ -842,8 +880,11 @@ __device__ __forceinline__ void ncc_tc_persist_body(const TcParams& p, const CUt
                 if (PROF) w_empty += clock64() - c0;
                 const uint32_t bytes = (uint32_t)min(ds, h - dy) * (uint32_t)slab_bytes;
                 if (elect_one()) {
-                    mbar_expect_tx(&full[s], bytes);
-                    bulk_g2s(ring + (size_t)s * stage_bytes, src, bytes, &full[s]);
+                    if (PROF && (p.dbg & 8)) mbar_arrive(&full[s]);          // knock-out: no slab bytes move (what the L2 -> SM stream costs)
+                    else {
+                        mbar_expect_tx(&full[s], bytes);
+                        bulk_g2s(ring + (size_t)s * stage_bytes, (PROF && (p.dbg & 16)) ? slabs : src, bytes, &full[s]);   // 16: always the same 24 KB
+                    }
                 }
                 src += stage_bytes;
                 if (++s == stages) { s = 0; ph ^= 1u; }
@@ -882,9 +923,12 @@ __device__ __forceinline__ void ncc_tc_persist_body(const TcParams& p, const CUt
                 if (PROF) w_full += clock64() - c2;
                 tc_fence_after();
                 if (elect_one()) {
-                    if (!PROF || !(p.dbg & 2))
-                        issue_rows_any(nk, tmem_d, a_lo0 + (uint32_t)s * stage_step, b_lo0 + (uint32_t)dy0, a_hi, b_hi, a_kstep, b_kstep,
-                                       slab_step, min(ds, h - dy0), idesc, dy0 != 0);
+                    if (!PROF || !(p.dbg & 2)) {
+                        // knock-outs (PROF): 32 = B stays on the tile's first rows (no 16-byte row shift), 64 = A always from ring slot 0
+                        const bool b_fixed = PROF && (p.dbg & 32), a_fixed = PROF && (p.dbg & 64);
+                        issue_rows_any(nk, tmem_d, a_lo0 + (a_fixed ? 0u : (uint32_t)s * stage_step), b_lo0 + (b_fixed ? 0u : (uint32_t)dy0), a_hi, b_hi,
+                                       a_kstep, b_kstep, a_fixed ? 0u : slab_step, min(ds, h - dy0), idesc, dy0 != 0, b_fixed ? 0u : 1u);
+                    }
                     umma_commit(&empty[s]);                    // frees the ring slot when these MMAs retire
                 }
                 if (++s == stages) { s = 0; ph ^= 1u; }
@@ -937,17 +981,20 @@ __device__ __forceinline__ void ncc_tc_persist_body(const TcParams& p, const CUt
         // ===== epilogue warps =====
         long long w_af = 0, w_epi = 0;
         BestTrack bt{-3.0e38f, 0u};
+        const bool c1 = (MODE == 0 || MODE == 3) && p.C == 1;
+        LaneC1 L{};
+        if (c1) L = lane_c1_setup(p, warp, lane, EW / 4);
         for (int i = 0; i < my_tiles; ++i) {
             const int b = i & 1, u = i >> 1;
             const int ti = (int)blockIdx.x + i * (int)gridDim.x;
             const int x0 = (ti % p.tiles_x) * xw, y0 = p.y_base + (ti / p.tiles_x) * p.N;
-            if (MODE == 0 || MODE == 3) epilogue_prefetch_first(p, x0, y0, warp, lane, EW / 4);
+            if (c1) epilogue_prefetch_first(p, L, x0, y0, lane);
             const long long c0 = PROF ? clock64() : 0;
             mbar_wait(&acc_full[b], u & 1);
             const long long c1 = PROF ? clock64() : 0;
             tc_fence_after();
             if (!PROF || !(p.dbg & 1)) {
-                if ((MODE == 0 || MODE == 3) && p.C == 1) epilogue_tile_c1<(MODE == 3 ? 3 : 0), PIPE>(p, tmem_base + (uint32_t)b * acc_stride, x0, y0, warp, lane, EW / 4, bt);
+                if (c1) epilogue_tile_c1<(MODE == 3 ? 3 : 0), PIPE>(p, L, tmem_base + (uint32_t)b * acc_stride, x0, y0, warp, lane, bt);
                 else epilogue_tile<MODE>(p, tmem_base + (uint32_t)b * acc_stride, x0, y0, warp, lane, EW / 4, bt);
             }
             tc_fence_before();
@@ -1090,16 +1137,20 @@ window_moments_rows_kernel(SatView sat, const uint32_t* __restrict__ sat_q32, co
 // back-to-back tcgen05.mma kind::i8 M128 x N x K32 from operands resident in shared memory (zeros; two accumulators in
 // turn), no loads, no epilogue: time / (grid * iters * 128 * N * 32) is the dense u8 MAC rate bench.py quotes rooflines against.
 __global__ void __launch_bounds__(128, 1)
-i8_peak_kernel(int iters, int n)
+i8_peak_kernel(int iters, int n, int variant)
 {
+    // variant (MTM_B200_PEAK_VARIANT, experiments): bit 0 = the B descriptor moves one 16-byte row per MMA (64 positions, the
+    // numerator kernel's row shift), bit 1 = A walks over 8 slabs of 4 KB, bit 2 = a tcgen05.commit after every 6 MMAs
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* bar2 = bar + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 16);
-    uint8_t* A = smem + 1024;                                   // [2 k-blocks][128 rows][16 B]
-    uint8_t* B = A + 4096;                                      // [2 k-blocks][n rows][16 B]
+    uint8_t* A = smem + 1024;                                   // 8 x [2 k-blocks][128 rows][16 B]
+    uint8_t* B = A + 8 * 4096;                                  // [2 k-blocks][n + 64 rows][16 B]
     const int tid = threadIdx.x, warp = tid >> 5;
-    for (int i = tid; i < (4096 + 32 * n) / 16; i += blockDim.x) reinterpret_cast<uint4*>(A)[i] = make_uint4(0u, 0u, 0u, 0u);
-    if (tid == 0) mbar_init(bar, 1);
+    const int rows_b = n + 64;
+    for (int i = tid; i < (8 * 4096 + 32 * rows_b) / 16; i += blockDim.x) reinterpret_cast<uint4*>(A)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (tid == 0) { mbar_init(bar, 1); mbar_init(bar2, 1); }
     if (warp == 0) tmem_alloc(tmem_slot, 512);
     fence_async_smem();
     tc_fence_before();
@@ -1108,9 +1159,17 @@ i8_peak_kernel(int iters, int n)
     const uint32_t tmem_base = *tmem_slot;
     if (warp == 1) {
         const uint32_t idesc = (2u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
-        const uint64_t a_desc = umma_desc(smem_u32(A), 128 * 16, 128), b_desc = umma_desc(smem_u32(B), (uint32_t)n * 16, 128);
+        const uint64_t a_desc = umma_desc(smem_u32(A), 128 * 16, 128), b_desc = umma_desc(smem_u32(B), (uint32_t)rows_b * 16, 128);
         if (elect_one()) {
-            for (int i = 0; i < iters; ++i) umma_i8(tmem_base + (uint32_t)(i & 1) * 256u, a_desc, b_desc, idesc, i > 1);
+            if (variant == 0) {
+                for (int i = 0; i < iters; ++i) umma_i8(tmem_base + (uint32_t)(i & 1) * 256u, a_desc, b_desc, idesc, i > 1);
+            } else {
+                const uint32_t bs = variant & 1 ? 1u : 0u, as = variant & 2 ? 256u : 0u;     // descriptor address units of 16 bytes
+                for (int i = 0; i < iters; ++i) {
+                    umma_i8(tmem_base + (uint32_t)((i >> 6) & 1) * 256u, a_desc + as * (uint32_t)(i & 7), b_desc + bs * (uint32_t)(i & 63), idesc, (i & 63) != 0);
+                    if ((variant & 4) && i % 6 == 5) umma_commit(bar2);
+                }
+            }
             umma_commit(bar);
         }
         __syncwarp();
@@ -1125,8 +1184,9 @@ i8_peak_kernel(int iters, int n)
 
 int launch_i8_peak(mtm_ctx* ctx, int n, int iters)
 {
-    const size_t smem_bytes = 1024 + 4096 + (size_t)32 * n;
-    i8_peak_kernel<<<ctx->sm_count, 128, smem_bytes, ctx->stream>>>(iters, n);
+    const size_t smem_bytes = 1024 + 8 * 4096 + (size_t)32 * (n + 64);
+    static const int variant = getenv("MTM_B200_PEAK_VARIANT") ? atoi(getenv("MTM_B200_PEAK_VARIANT")) : 0;
+    i8_peak_kernel<<<ctx->sm_count, 128, smem_bytes, ctx->stream>>>(iters, n, variant);
     MTM_LAUNCH_CHECK(ctx);
     return MTM_OK;
 }

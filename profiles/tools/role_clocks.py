@@ -1,0 +1,20 @@
+"""Role clocks of the persistent numerator kernel (MTM_B200_PROF=1; needs MTM_B200_NO_HITS_ONLY=1: the profiled instantiation
+is the map-writing one).  Prints the library's "[mtm prof]" lines of ONE synchronous call per workload (after a warm-up call).
+
+    MTM_B200_PROF=1 MTM_B200_NO_HITS_ONLY=1 [MTM_B200_PDBG=8] python profiles/tools/role_clocks.py C2 C4 C5
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import MTM  # noqa: E402
+import workloads  # noqa: E402
+
+for name in sys.argv[1:]:
+    image, labelled, params = workloads.config(name)
+    sys.stderr.write("==== %s warm-up\n" % name)
+    MTM.matchTemplates(labelled, image, **params)
+    sys.stderr.write("==== %s measured call\n" % name)
+    hits = MTM.matchTemplates(labelled, image, **params)
+    sys.stderr.write("==== %s: %d hits\n" % (name, len(hits)))

@@ -134,6 +134,12 @@ static inline void prefetch_l1(const void*) {}
 static inline long long clock64() { return 0; }
 static inline void __trap() { fprintf(stderr, "__trap()\n"); abort(); }
 
+// ncc_tc.cu's n1_to_float (PTX: mul.wide.u32 x 2, sub.s64, cvt.rn.f32.s64): same integers, round to nearest even
+static inline float n1_to_float(uint32_t area, uint32_t cc, uint32_t s, uint32_t sumT)
+{
+    return (float)((long long)((unsigned long long)area * cc) - (long long)((unsigned long long)s * sumT));
+}
+
 static inline uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
 {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
