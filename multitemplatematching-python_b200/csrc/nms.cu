@@ -35,7 +35,15 @@ __device__ __forceinline__ bool hit_less(const DevHit& a, const DevHit& b, const
         return a.seq < b.seq;
     }
     if (a.key != b.key) return a.key > b.key;
-    if (s.mode == 2 && a.tmpl != b.tmpl) return a.tmpl < b.tmpl;   // canonical list order without sorting into it first
+    if (s.mode == 2) {                                              // canonical list order without sorting into it first
+        if (a.tmpl != b.tmpl) return a.tmpl < b.tmpl;
+        // minimising methods: two different scores can share the float32 key 1 - score.  The stable sort of the reference keeps
+        // the peak finder's order there (2-D maps: ascending score, then row-major) -- what mode 0 followed by mode 1 produces.
+        if (s.minimize && a.score != b.score && a.tmpl != 0x7fffffff) {
+            const TmplMeta& tm = s.meta[a.tmpl];
+            if (tm.mh != 1 && tm.mw != 1) return a.score < b.score;
+        }
+    }
     return a.seq < b.seq;
 }
 

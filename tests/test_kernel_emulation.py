@@ -769,6 +769,26 @@ def test_peak_sort_nms_kernels_on_the_host(emu, method, n_object):
             assert got_list_g == want_list
 
 
+def test_near_tied_minimising_scores_keep_the_peak_finders_order_on_the_host(emu):
+    """TM_SQDIFF_NORMED: two overlapping hits of one template whose scores differ by one ulp share the float32 NMS key 1 - score.
+    The reference's stable sort keeps the peak finder's order there (ascending score first), so the later pixel with the smaller
+    score wins the overlap: the one-launch route (single sort by key, template, then score) must agree with the general route."""
+    s_hi = np.float32(0.25)
+    s_lo = np.nextafter(s_hi, np.float32(0))
+    assert np.float32(1) - s_hi == np.float32(1) - s_lo and s_lo < s_hi
+    m = np.full((24, 40), 0.9, np.float32)
+    m[2, 20] = s_hi                                  # first in row-major order, worse score
+    m[6, 18] = s_lo                                  # later, better score: overlaps the first box
+    m[15, 5] = 0.125
+    maps, sizes = [m, np.full((9, 9), 0.95, np.float32)], [(12, 9), (5, 5)]
+    for n_object in (float("inf"), 2):
+        want = _port_postprocess(maps, sizes, 1, n_object, 0.5, 0.1, True)
+        assert [h[1][:2] for h in want[:2]] == [(5, 15), (18, 6)], want
+        for force_general in (False, True):
+            got, route = _host_postprocess(emu, maps, sizes, 1, n_object, 0.5, 0.1, True, force_general)
+            assert route == int(force_general) and got == want, (n_object, force_general, got, want)
+
+
 def test_candidate_list_route_on_the_host(emu):
     """verify_candidates_kernel: the pixels above the threshold that the tcgen05 epilogue lists (any order) give the same hit lists as
     the streaming pass; a list that overflowed (a constant map above the threshold always does: the route needs maps larger than the
