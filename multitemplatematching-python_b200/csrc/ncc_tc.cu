@@ -61,6 +61,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
                  : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(200000u) : "memory");
     return ok != 0;
 }
+// one non-blocking poll (no suspend-time hint): true when the phase with this parity has completed
+__device__ __forceinline__ bool mbar_try_wait_once(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
     // try_wait suspends for a bounded time per call; a barrier that never completes (a bug, not a
@@ -818,6 +826,89 @@ __device__ __forceinline__ void issue_rows_any(int nk, uint32_t tmem_d, uint32_t
     }
 }
 
+// The MMA issuer of the persistent kernel.  NK = K chunks per template row (0: run-time p.nk), chosen ONCE per kernel so that
+// no jump table sits in the per-stage path.  What the issuing thread does between two groups of MMAs decides whether the tensor
+// pipe runs dry: the pipe holds about three queued MMAs (measured with i8_peak_kernel: a passing mbarrier wait + fence + commit
+// after every 6 MMAs costs nothing at N = 208 but 30 % at N = 144, 43 % at N = 128), so every barrier is POLLED ONE STEP AHEAD --
+// the try_wait of the next ring stage (next tile) is issued before the MMAs of the current one and its answer is read after
+// them; only a poll that failed falls back to the blocking wait.
+template <bool PROF, int NK>
+__device__ __forceinline__ void mma_issuer_role(const TcParams& p, uint64_t* full, uint64_t* empty, uint64_t* tile_full, uint64_t* tile_empty,
+                                                uint64_t* acc_full, uint64_t* acc_empty, uint32_t tile_addr0, uint32_t tile_bytes,
+                                                uint32_t ring_addr, uint32_t stage_bytes, uint32_t tmem_base, uint32_t acc_stride,
+                                                int my_tiles, int lane)
+{
+    const uint32_t idesc = (2u << 4) | ((uint32_t)(p.N >> 3) << 17) | ((128u >> 4) << 24);   // S32 accum, u8 x u8, K-major
+    const uint32_t lbo_b = (uint32_t)p.R * 16;
+    const int ds = p.ds, h = p.h, nk = NK ? NK : p.nk, stages = p.stages;
+    const uint64_t a_desc0 = umma_desc(ring_addr, (uint32_t)p.a_kblk, 128);
+    const uint32_t a_hi = (uint32_t)(a_desc0 >> 32), a_lo0 = (uint32_t)a_desc0;
+    const uint32_t a_kstep = (uint32_t)(2 * p.a_kblk) >> 4, b_kstep = (2 * lbo_b) >> 4;     // descriptor address unit: 16 B
+    const uint32_t slab_step = (uint32_t)p.slab_bytes >> 4, stage_step = stage_bytes >> 4;
+    // knock-outs (PROF): 2 = no MMAs, 32 = B stays on the tile's first rows (no 16-byte row shift), 64 = A always from ring slot 0
+    const bool no_mma = PROF && (p.dbg & 2), b_fixed = PROF && (p.dbg & 32), a_fixed = PROF && (p.dbg & 64);
+    int s = 0;
+    uint32_t ph = 0;
+    long long w_tile = 0, w_acc = 0, w_full = 0;
+    const long long m_begin = PROF ? clock64() : 0;
+    bool slab_ready = my_tiles > 0 && mbar_try_wait_once(&full[0], 0);
+    bool tile_ready = my_tiles > 0 && mbar_try_wait_once(&tile_full[0], 0);
+    bool acc_ready = true;                                      // fresh barrier
+    for (int i = 0; i < my_tiles; ++i) {
+        const int b = i & 1, u = i >> 1;
+        const long long c0 = PROF ? clock64() : 0;
+        if (!tile_ready) mbar_wait(&tile_full[b], u & 1);
+        const long long c1 = PROF ? clock64() : 0;
+        if (!acc_ready) mbar_wait(&acc_empty[b], (u & 1) ^ 1);  // fresh barrier: parity 1 passes
+        if (PROF) { w_tile += c1 - c0; w_acc += clock64() - c1; }
+        tc_fence_after();
+        const uint64_t b_desc0 = umma_desc(tile_addr0 + (uint32_t)b * tile_bytes, lbo_b, 128);
+        const uint32_t b_hi = (uint32_t)(b_desc0 >> 32), b_lo0 = (uint32_t)b_desc0;
+        const uint32_t tmem_d = tmem_base + (uint32_t)b * acc_stride;
+        for (int dy0 = 0; dy0 < h; dy0 += ds) {
+            const long long c2 = PROF ? clock64() : 0;
+            if (!slab_ready) mbar_wait(&full[s], ph);
+            if (PROF) w_full += clock64() - c2;
+            tc_fence_after();
+            // poll the barriers of the NEXT step now, read the answers after this stage's MMAs have been queued
+            int sn = s + 1;
+            uint32_t phn = ph;
+            if (sn == stages) { sn = 0; phn ^= 1u; }
+            const bool last_stage = dy0 + ds >= h;
+            const bool more = !last_stage || i + 1 < my_tiles;
+            const bool slab_next = more && mbar_try_wait_once(&full[sn], phn);
+            bool tile_next = false, acc_next = false;
+            if (last_stage && i + 1 < my_tiles) {
+                const int bn = (i + 1) & 1, un = (i + 1) >> 1;
+                tile_next = mbar_try_wait_once(&tile_full[bn], un & 1);
+                acc_next = mbar_try_wait_once(&acc_empty[bn], (un & 1) ^ 1);
+            }
+            if (elect_one()) {
+                if (!no_mma) {
+                    const uint32_t a_lo = a_lo0 + (a_fixed ? 0u : (uint32_t)s * stage_step), b_lo = b_lo0 + (b_fixed ? 0u : (uint32_t)dy0);
+                    if (NK) issue_rows<NK ? NK : 1>(tmem_d, a_lo, b_lo, a_hi, b_hi, a_kstep, b_kstep, a_fixed ? 0u : slab_step, min(ds, h - dy0), idesc,
+                                                    dy0 != 0, b_fixed ? 0u : 1u);
+                    else issue_rows_any(nk, tmem_d, a_lo, b_lo, a_hi, b_hi, a_kstep, b_kstep, a_fixed ? 0u : slab_step, min(ds, h - dy0), idesc,
+                                        dy0 != 0, b_fixed ? 0u : 1u);
+                }
+                umma_commit(&empty[s]);                        // frees the ring slot when these MMAs retire
+            }
+            s = sn; ph = phn;
+            slab_ready = slab_next;
+            if (last_stage) { tile_ready = tile_next; acc_ready = acc_next; }
+        }
+        if (elect_one()) {
+            umma_commit(&acc_full[b]);                         // epilogue may read this accumulator
+            umma_commit(&tile_empty[b]);                       // the loader may overwrite this image tile
+        }
+    }
+    if (PROF && lane == 0) {
+        long long* q = p.prof + 16 * blockIdx.x;
+        q[0] = w_tile; q[1] = w_acc; q[2] = w_full; q[3] = clock64() - m_begin;
+    }
+    __syncwarp();
+}
+
 template <bool PROF, int EW, int MODE, bool PIPE>
 __device__ __forceinline__ void ncc_tc_persist_body(const TcParams& p, const CUtensorMap& tmap)
 {
@@ -893,56 +984,17 @@ __device__ __forceinline__ void ncc_tc_persist_body(const TcParams& p, const CUt
         if (PROF && lane == 0) p.prof[16 * blockIdx.x + 8] = w_empty;
         __syncwarp();
     } else if (warp == EW + 1) {
-        // ===== MMA issuer: warp-uniform loop, one elected lane issues.  The issue loop is kept to a few
-        // instructions per MMA: a single warp retires an instruction every few clocks, an MMA lasts ~100.
-        const uint32_t idesc = (2u << 4) | ((uint32_t)(p.N >> 3) << 17) | ((128u >> 4) << 24);   // S32 accum, u8 x u8, K-major
-        const uint32_t lbo_b = (uint32_t)p.R * 16;
-        const int ds = p.ds, h = p.h, nk = p.nk, stages = p.stages;
-        const uint64_t a_desc0 = umma_desc(smem_u32(ring), (uint32_t)p.a_kblk, 128);
-        const uint32_t a_hi = (uint32_t)(a_desc0 >> 32), a_lo0 = (uint32_t)a_desc0;
-        const uint32_t a_kstep = (uint32_t)(2 * p.a_kblk) >> 4, b_kstep = (2 * lbo_b) >> 4;     // descriptor address unit: 16 B
-        const uint32_t slab_step = (uint32_t)p.slab_bytes >> 4, stage_step = stage_bytes >> 4;
-        int s = 0;
-        uint32_t ph = 0;
-        long long w_tile = 0, w_acc = 0, w_full = 0;
-        const long long m_begin = PROF ? clock64() : 0;
-        for (int i = 0; i < my_tiles; ++i) {
-            const int b = i & 1, u = i >> 1;
-            const long long c0 = PROF ? clock64() : 0;
-            mbar_wait(&tile_full[b], u & 1);
-            const long long c1 = PROF ? clock64() : 0;
-            mbar_wait(&acc_empty[b], (u & 1) ^ 1);              // fresh barrier: parity 1 passes
-            if (PROF) { w_tile += c1 - c0; w_acc += clock64() - c1; }
-            tc_fence_after();
-            const uint64_t b_desc0 = umma_desc(smem_u32(tiles + (size_t)b * tile_bytes), lbo_b, 128);
-            const uint32_t b_hi = (uint32_t)(b_desc0 >> 32), b_lo0 = (uint32_t)b_desc0;
-            const uint32_t tmem_d = tmem_base + (uint32_t)b * acc_stride;
-            for (int dy0 = 0; dy0 < h; dy0 += ds) {
-                const long long c2 = PROF ? clock64() : 0;
-                mbar_wait(&full[s], ph);
-                if (PROF) w_full += clock64() - c2;
-                tc_fence_after();
-                if (elect_one()) {
-                    if (!PROF || !(p.dbg & 2)) {
-                        // knock-outs (PROF): 32 = B stays on the tile's first rows (no 16-byte row shift), 64 = A always from ring slot 0
-                        const bool b_fixed = PROF && (p.dbg & 32), a_fixed = PROF && (p.dbg & 64);
-                        issue_rows_any(nk, tmem_d, a_lo0 + (a_fixed ? 0u : (uint32_t)s * stage_step), b_lo0 + (b_fixed ? 0u : (uint32_t)dy0), a_hi, b_hi,
-                                       a_kstep, b_kstep, a_fixed ? 0u : slab_step, min(ds, h - dy0), idesc, dy0 != 0, b_fixed ? 0u : 1u);
-                    }
-                    umma_commit(&empty[s]);                    // frees the ring slot when these MMAs retire
-                }
-                if (++s == stages) { s = 0; ph ^= 1u; }
-            }
-            if (elect_one()) {
-                umma_commit(&acc_full[b]);                     // epilogue may read this accumulator
-                umma_commit(&tile_empty[b]);                   // stagers may overwrite this image tile
-            }
+        // ===== MMA issuer: warp-uniform loop, one elected lane issues (mma_issuer_role below)
+        const uint32_t tile_addr0 = smem_u32(tiles), ring_addr = smem_u32(ring);
+        switch (p.nk) {
+            case 1: mma_issuer_role<PROF, 1>(p, full, empty, tile_full, tile_empty, acc_full, acc_empty, tile_addr0, tile_bytes, ring_addr, stage_bytes, tmem_base, acc_stride, my_tiles, lane); break;
+            case 2: mma_issuer_role<PROF, 2>(p, full, empty, tile_full, tile_empty, acc_full, acc_empty, tile_addr0, tile_bytes, ring_addr, stage_bytes, tmem_base, acc_stride, my_tiles, lane); break;
+            case 3: mma_issuer_role<PROF, 3>(p, full, empty, tile_full, tile_empty, acc_full, acc_empty, tile_addr0, tile_bytes, ring_addr, stage_bytes, tmem_base, acc_stride, my_tiles, lane); break;
+            case 4: mma_issuer_role<PROF, 4>(p, full, empty, tile_full, tile_empty, acc_full, acc_empty, tile_addr0, tile_bytes, ring_addr, stage_bytes, tmem_base, acc_stride, my_tiles, lane); break;
+            case 5: mma_issuer_role<PROF, 5>(p, full, empty, tile_full, tile_empty, acc_full, acc_empty, tile_addr0, tile_bytes, ring_addr, stage_bytes, tmem_base, acc_stride, my_tiles, lane); break;
+            case 6: mma_issuer_role<PROF, 6>(p, full, empty, tile_full, tile_empty, acc_full, acc_empty, tile_addr0, tile_bytes, ring_addr, stage_bytes, tmem_base, acc_stride, my_tiles, lane); break;
+            default: mma_issuer_role<PROF, 0>(p, full, empty, tile_full, tile_empty, acc_full, acc_empty, tile_addr0, tile_bytes, ring_addr, stage_bytes, tmem_base, acc_stride, my_tiles, lane); break;
         }
-        if (PROF && lane == 0) {
-            long long* q = p.prof + 16 * blockIdx.x;
-            q[0] = w_tile; q[1] = w_acc; q[2] = w_full; q[3] = clock64() - m_begin;
-        }
-        __syncwarp();
     } else if (warp >= EW + 2 && p.tma) {
         // ===== image tile loader: one warp, one elected lane per tile feeds the TMA unit (launched with EW + 3 warps)
         if (warp == EW + 2) {
@@ -1140,17 +1192,27 @@ __global__ void __launch_bounds__(128, 1)
 i8_peak_kernel(int iters, int n, int variant)
 {
     // variant (MTM_B200_PEAK_VARIANT, experiments): bit 0 = the B descriptor moves one 16-byte row per MMA (64 positions, the
-    // numerator kernel's row shift), bit 1 = A walks over 8 slabs of 4 KB, bit 2 = a tcgen05.commit after every 6 MMAs
+    // numerator kernel's row shift), bit 1 = A walks over 8 slabs of 4 KB, bit 2 = a tcgen05.commit after every 6 MMAs, bit 3 = pseudo-random operand bytes instead of zeros,
+    // bit 4 = tcgen05.fence::after_thread_sync and bit 5 = a (passing) mbarrier wait after every 6 MMAs
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
     uint64_t* bar2 = bar + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 16);
+    uint64_t* bar3 = bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 32);
     uint8_t* A = smem + 1024;                                   // 8 x [2 k-blocks][128 rows][16 B]
     uint8_t* B = A + 8 * 4096;                                  // [2 k-blocks][n + 64 rows][16 B]
     const int tid = threadIdx.x, warp = tid >> 5;
     const int rows_b = n + 64;
-    for (int i = tid; i < (8 * 4096 + 32 * rows_b) / 16; i += blockDim.x) reinterpret_cast<uint4*>(A)[i] = make_uint4(0u, 0u, 0u, 0u);
-    if (tid == 0) { mbar_init(bar, 1); mbar_init(bar2, 1); }
+    for (int i = tid; i < (8 * 4096 + 32 * rows_b) / 16; i += blockDim.x) {
+        uint4 fill = make_uint4(0u, 0u, 0u, 0u);
+        if (variant & 8) {                                       // pseudo-random operand bytes (data-dependent power)
+            uint32_t x = (uint32_t)i * 2654435761u + blockIdx.x * 40503u + 12345u;
+            x ^= x >> 15; x *= 2246822519u; x ^= x >> 13;
+            fill = make_uint4(x, x * 3266489917u, x * 668265263u + 1u, x * 374761393u + 7u);
+        }
+        reinterpret_cast<uint4*>(A)[i] = fill;
+    }
+    if (tid == 0) { mbar_init(bar, 1); mbar_init(bar2, 1); mbar_init(bar3, 1); }
     if (warp == 0) tmem_alloc(tmem_slot, 512);
     fence_async_smem();
     tc_fence_before();
@@ -1161,13 +1223,17 @@ i8_peak_kernel(int iters, int n, int variant)
         const uint32_t idesc = (2u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
         const uint64_t a_desc = umma_desc(smem_u32(A), 128 * 16, 128), b_desc = umma_desc(smem_u32(B), (uint32_t)rows_b * 16, 128);
         if (elect_one()) {
-            if (variant == 0) {
+            if ((variant & ~8) == 0) {
                 for (int i = 0; i < iters; ++i) umma_i8(tmem_base + (uint32_t)(i & 1) * 256u, a_desc, b_desc, idesc, i > 1);
             } else {
                 const uint32_t bs = variant & 1 ? 1u : 0u, as = variant & 2 ? 256u : 0u;     // descriptor address units of 16 bytes
                 for (int i = 0; i < iters; ++i) {
                     umma_i8(tmem_base + (uint32_t)((i >> 6) & 1) * 256u, a_desc + as * (uint32_t)(i & 7), b_desc + bs * (uint32_t)(i & 63), idesc, (i & 63) != 0);
-                    if ((variant & 4) && i % 6 == 5) umma_commit(bar2);
+                    if (i % 6 == 5) {                                    // what the numerator kernel does once per ring stage
+                        if (variant & 4) umma_commit(bar2);
+                        if (variant & 16) tc_fence_after();
+                        if (variant & 32) mbar_wait(bar3, 1);               // a barrier that never completed a phase: parity 1 passes at once
+                    }
                 }
             }
             umma_commit(bar);
@@ -1196,7 +1262,7 @@ int launch_i8_peak(mtm_ctx* ctx, int n, int iters)
 // measurements under profiles/ can be repeated: tile height, ring stage size, epilogue warps, shared-memory ceiling,
 // the one-tile-per-CTA kernel, per-role clocks and phase knock-outs of the persistent kernel.
 struct TcEnv {
-    int force_n = 0, ds = 0, ew = 0, pdbg = 0, mom_cs = -1;
+    int force_n = 0, ds = 0, ew = 0, pdbg = 0, mom_cs = -1, stage_bytes = 24576;
     size_t smem_soft = 0;
     bool persist_off = false, prof = false, mom_rows = false, tma_off = false, lean = false;
     TcEnv()
@@ -1204,6 +1270,7 @@ struct TcEnv {
         auto num = [](const char* name) { const char* v = getenv(name); return v ? atoi(v) : 0; };
         force_n = num("MTM_B200_FORCE_N");
         ds = num("MTM_B200_DS");
+        if (num("MTM_B200_STAGE_KB") > 0) stage_bytes = num("MTM_B200_STAGE_KB") * 1024;
         ew = getenv("MTM_B200_EW") ? (num("MTM_B200_EW") == 12 ? 12 : 8) : 0;
         pdbg = num("MTM_B200_PDBG");
         smem_soft = getenv("MTM_B200_SMEM_SOFT") ? (size_t)num("MTM_B200_SMEM_SOFT") * 1024 : 0;
@@ -1356,7 +1423,7 @@ static int launch_ncc_tc_impl(mtm_ctx* ctx, const TcGroup& g, int method, const 
     if (!tc_env().persist_off) {
         const int xw_p = g.mode == 0 ? 16 : 128;
         const int gx_p = (p.mw + xw_p - 1) / xw_p;
-        int ds_p = std::max(1, std::min(g.h, 24576 / g.slab_bytes));           // slabs (template rows) per ring stage
+        int ds_p = std::max(1, std::min(g.h, tc_env().stage_bytes / g.slab_bytes));   // slabs (template rows) per ring stage
         if (tc_env().ds) ds_p = std::max(1, std::min(g.h, tc_env().ds));
         const size_t stage_b = (size_t)ds_p * g.slab_bytes;
         const int force_n = tc_env().force_n;

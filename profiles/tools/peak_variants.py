@@ -13,7 +13,7 @@ from mtm_b200 import _native  # noqa: E402
 
 ctx = _native.default_context()
 sm = 148
-for n in (128, 144, 160, 208, 240, 256):
+for n in [int(v) for v in os.environ.get("PEAK_N", "128,144,160,208,240,256").split(",")]:
     tmacs = ctx.measure_i8_peak(n, 4000)
     ms = sm * 4000 * 128.0 * n * 32.0 / (tmacs * 1e12) * 1e3
     print("variant %s N=%3d: %.3f TMAC/s = %.3f POP/s, %.4f ms per 4000 MMAs" % (os.environ.get("MTM_B200_PEAK_VARIANT", "0"), n, tmacs, 2 * tmacs / 1e3, ms))

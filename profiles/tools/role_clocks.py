@@ -11,8 +11,18 @@ sys.path.insert(0, ROOT)
 import MTM  # noqa: E402
 import workloads  # noqa: E402
 
+import numpy as np  # noqa: E402
+
 for name in sys.argv[1:]:
-    image, labelled, params = workloads.config(name)
+    if name.startswith("T:"):                                     # T:h:w:count:H:W -- `count` templates of one size on an H x W scene
+        h, w, n, H, W = (int(v) for v in name.split(":")[1:])
+        rng = np.random.default_rng(0)
+        temps = [workloads.make_template(rng, h, w) for _ in range(n)]
+        image, _ = workloads.make_scene(H, W, temps, 2, 0)
+        labelled = [("t%02d" % i, t) for i, t in enumerate(temps)]
+        params = dict(N_object=float("inf"), score_threshold=0.5, maxOverlap=0.25)
+    else:
+        image, labelled, params = workloads.config(name)
     sys.stderr.write("==== %s warm-up\n" % name)
     MTM.matchTemplates(labelled, image, **params)
     sys.stderr.write("==== %s measured call\n" % name)

@@ -64,6 +64,12 @@ static inline bool mbar_try_wait(uint64_t* bar, uint32_t parity)
     emu_wait_change(&b.phase, parity & 1u);
     return b.phase != (parity & 1u);
 }
+// mbarrier.test_wait: one poll, never parks
+static inline bool mbar_try_wait_once(uint64_t* bar, uint32_t parity)
+{
+    emu_preempt_point();
+    return emu_mbar_at(bar).phase != (parity & 1u);
+}
 static inline void mbar_wait(uint64_t* bar, uint32_t parity)
 {
     while (!mbar_try_wait(bar, parity)) {}
