@@ -236,6 +236,11 @@ box_moments_c1_kernel(const BoxParams p)
     uint2* out_base = reinterpret_cast<uint2*>(p.S) + sd.off;
     const int seg_off = (tid + sd.w) >> 8;
     const bool wide = sd.w > B1_THREADS;
+    const uint32_t seg_mask = seg_off ? 0xFFFFFFFFu : 0u;
+    const int lim = min(strip_out, sd.mw - x0);                        // window positions of this strip
+    const int jn = lim > tid ? (lim - tid + B1_THREADS - 1) / B1_THREADS : 0;     // this thread's positions: tid + 256 j, j < jn
+    const int64_t dst_step = (int64_t)sd.band * (B1_THREADS / 16) * 16;
+    uint2* out_row = out_base + ((int64_t)((x0 >> 4) + (tid >> 4)) * sd.band + (y0 - p.y_begin)) * 16 + (tid & 15);   // row y0 of position j = 0
     uint2 w_in = load_row(y0 + sd.h - 1), w_out = load_row(y0);
     for (int y = y0; y < y1; ++y) {
         const int buf = (y - y0) & 1;
@@ -264,6 +269,31 @@ box_moments_c1_kernel(const BoxParams p)
 #pragma unroll
         for (int j = 0; j < 8; j += 2) dst[j >> 1] = make_uint4(bs + es[j], bq + eq[j], bs + es[j + 1], bq + eq[j + 1]);
         __syncthreads();                                            // the only barrier of the row (buffers alternate)
+        if (!wide) {
+            // Windows no wider than a segment (w <= 256: everything but very wide templates).  Position xl = tid + 256 j lies in
+            // segment j and its right edge in segment j + seg_off, seg_off = (tid + w) >> 8 in {0, 1}: the window sum is the
+            // difference of the two segment-local prefixes plus, when the edge crossed into the next segment, segment j's total
+            // (no running bases).  A thread's positions are a prefix j < jn of the eight; the ring entry of row y is 16 entries
+            // (128 bytes) after row y - 1, the one of position j + 1 dst_step entries after position j.
+            const uint2* pl = &P[buf][tid];
+            const uint2* pr = pl + sd.w;
+            uint2* o = out_row;
+#pragma unroll
+            for (int j = 0; j < B1_PX; ++j) {
+                if (j < jn) {
+                    const uint2 t = wtot[buf][j];
+                    const uint2 lo = pl[j * B1_THREADS], hi = pr[j * B1_THREADS];
+                    const uint32_t s = hi.x - lo.x + (t.x & seg_mask);
+                    const uint32_t qs = hi.y - lo.y + (t.y & seg_mask);
+                    const unsigned long long d1 = (unsigned long long)area * qs - (unsigned long long)s * s;
+                    const float f = (float)d1;                                 // 0 exactly when d1 == 0 (a flat window)
+                    const float rs = f != 0.0f ? mtm_rsqrt_normal(f) : 0.0f;  // d1 >= 1: never subnormal
+                    *o = make_uint2(s, __float_as_uint(rs));
+                }
+                o += dst_step;
+            }
+            out_row += 16;
+        } else {
         uint2 wb[B1_WARPS + 1];                                     // base of every warp's segment; [B1_WARPS] = the strip total
         wb[0] = make_uint2(0u, 0u);
 #pragma unroll
@@ -274,26 +304,21 @@ box_moments_c1_kernel(const BoxParams p)
         const uint2* pl = &P[buf][tid];
         const uint2* pr = pl + sd.w;
         uint2* outp = out_base + ((int64_t)((x0 >> 4) + (tid >> 4)) * sd.band + (y - p.y_begin)) * 16 + (tid & 15);
-        const int64_t dst_step = (int64_t)sd.band * (B1_THREADS / 16) * 16;
 #pragma unroll
         for (int j = 0; j < B1_PX; ++j) {
             const int xl = tid + j * B1_THREADS;
             if (xl >= strip_out || x0 + xl >= sd.mw) continue;
             const uint2 lo = pl[j * B1_THREADS], hi = pr[j * B1_THREADS];
-            uint2 hb;
-            if (wide) {                                             // windows wider than a segment (w > 256): general selection
-                hb = wb[j];
+            uint2 hb = wb[j];                                        // windows wider than a segment (w > 256): general selection
 #pragma unroll
-                for (int k = 1; k <= 4; ++k)
-                    if (j + k <= B1_WARPS && seg_off == k) hb = wb[j + k];
-            } else {
-                hb = seg_off ? wb[j + 1 <= B1_WARPS ? j + 1 : B1_WARPS] : wb[j];
-            }
+            for (int k = 1; k <= 4; ++k)
+                if (j + k <= B1_WARPS && seg_off == k) hb = wb[j + k];
             const uint32_t s = (hi.x + hb.x) - (lo.x + wb[j].x);
             const uint32_t qs = (hi.y + hb.y) - (lo.y + wb[j].y);
             const unsigned long long d1 = (unsigned long long)area * qs - (unsigned long long)s * s;
             const float rs = d1 ? mtm_rsqrt_normal((float)d1) : 0.0f;      // d1 >= 1: never subnormal
             outp[j * dst_step] = make_uint2(s, __float_as_uint(rs));
+        }
         }
         sub_row(w_out);
         w_in = n_in; w_out = n_out;

@@ -779,7 +779,8 @@ ncc_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap)
 //   warps EW+2, EW+3  image tile stagers (global -> registers -> shared memory, [k-block][row][16 B])
 // EW = 12 serves small templates, whose tiles spend longer in the epilogue than in the MMAs.
 constexpr int TCP_MAX_STAGES = 8;
-constexpr double TCP_EPI_CLK_PER_ROW = 100.0;   // measured: epilogue clocks per output row of a tile with 8 epilogue warps
+constexpr double TCP_EPI_CLK_PER_ROW = 70.0;    // measured (role clocks, MMAs knocked out): epilogue clocks per output row of a tile, 8 warps, pipelined loads
+constexpr double TCP_EPI_CLK_PER_ROW_12 = 55.0; // the same with 12 epilogue warps (128 registers, prefetch instead of the second register set)
 constexpr int TCP_STAGERS = 32;                 // register staging (fallback when no tensor map can be made): one stager warp
 constexpr size_t TCP_SMEM_SOFT = 188 * 1024;     // preferred ceiling of the persistent kernel's shared memory (see launch_ncc_tc)
 
@@ -1262,9 +1263,9 @@ int launch_i8_peak(mtm_ctx* ctx, int n, int iters)
 // measurements under profiles/ can be repeated: tile height, ring stage size, epilogue warps, shared-memory ceiling,
 // the one-tile-per-CTA kernel, per-role clocks and phase knock-outs of the persistent kernel.
 struct TcEnv {
-    int force_n = 0, ds = 0, ew = 0, pdbg = 0, mom_cs = -1, stage_bytes = 24576;
+    int force_n = 0, ds = 0, ew = 0, pdbg = 0, mom_cs = -1, stage_bytes = 65536;
     size_t smem_soft = 0;
-    bool persist_off = false, prof = false, mom_rows = false, tma_off = false, lean = false;
+    bool persist_off = false, prof = false, mom_rows = false, tma_off = false, lean = false, plan_dbg = false;
     TcEnv()
     {
         auto num = [](const char* name) { const char* v = getenv(name); return v ? atoi(v) : 0; };
@@ -1280,6 +1281,7 @@ struct TcEnv {
         mom_rows = num("MTM_B200_MOM_ROWS") != 0;
         tma_off = getenv("MTM_B200_TMA") && num("MTM_B200_TMA") == 0;
         lean = num("MTM_B200_LEAN") != 0;
+        plan_dbg = num("MTM_B200_PLAN_DBG") != 0;
     }
 };
 static const TcEnv& tc_env()
@@ -1423,37 +1425,55 @@ static int launch_ncc_tc_impl(mtm_ctx* ctx, const TcGroup& g, int method, const 
     if (!tc_env().persist_off) {
         const int xw_p = g.mode == 0 ? 16 : 128;
         const int gx_p = (p.mw + xw_p - 1) / xw_p;
-        int ds_p = std::max(1, std::min(g.h, tc_env().stage_bytes / g.slab_bytes));   // slabs (template rows) per ring stage
-        if (tc_env().ds) ds_p = std::max(1, std::min(g.h, tc_env().ds));
-        const size_t stage_b = (size_t)ds_p * g.slab_bytes;
-        const int force_n = tc_env().force_n;
-        // Cost model (clocks per CTA).  Per MMA: tensor pipe n/2, shared-memory traffic (A 4 KB read + 4 KB slab write +
-        // 32*n B read at 128 B/clk) 64 + n/4.  The epilogue of a tile (~TCP_EPI_CLK_PER_ROW clocks per row with 8 warps)
-        // overlaps the MMAs of the next one; the first image tile and the last epilogue are exposed.
-        const size_t smem_soft = tc_env().smem_soft ? tc_env().smem_soft : TCP_SMEM_SOFT;
-        int bestN = 0, best_stages = 0, best_ew = 8;
+        const int force_n = tc_env().force_n, force_ew = tc_env().ew, force_ds = tc_env().ds;
+        // Cost model (clocks per CTA), fitted to measurements (profiles/README.md, round 2):
+        //  * one MMA (M128 x n x K32, u8) from shared memory: n/2 + 8 clocks with resident zero operands (i8_peak_kernel),
+        //    ~10 % more on real data;
+        //  * between two ring stages the issuing thread spends ~390 clocks (barrier poll, fence, election, descriptors, commit)
+        //    while the pipe holds about three queued MMAs: every stage costs max(0, 390 - 3 t_mma) clocks of idle pipe, so small
+        //    tiles want MANY template rows per stage (C4: 24-KB stages 0.373 ms, 64-KB stages 0.323 ms);
+        //  * the slab stream needs rate x latency bytes in flight (4 KB per MMA, ~2500 clocks from L2): a ring with fewer bytes
+        //    beyond the stage being consumed runs at in_flight / need of the rate (C2: 2 x 64 KB slower than 3 x 48 KB);
+        //  * the epilogue of a tile (~TCP_EPI_CLK_PER_ROW clocks per row with 8 warps) overlaps the MMAs of the next one; the
+        //    first image tile and the last epilogue are exposed.
+        int bestN = 0, best_stages = 0, best_ew = 8, best_ds = 1;
         double best_cost = 1e300;
-        const int force_ew = tc_env().ew;
+        const int ds_cap = std::max(1, std::min(g.h, tc_env().stage_bytes / g.slab_bytes));
         for (int n = 256; n >= 32; n -= 16) {
             if (force_n && n != force_n) continue;
             const size_t tile_b = ((size_t)2 * g.nk * tc_tile_rows(n, g.h) * 16 + 127) & ~(size_t)127;
-            if (256 + 2 * tile_b + 3 * stage_b > 227 * 1024) continue;
-            // Ring depth: as deep as shared memory allows, but when 4 stages fit under TCP_SMEM_SOFT the rest is left
-            // to the small kernels of other streams (the sort/NMS kernel needs 35 KB) so that they can run beside this one.
-            int stages = (int)std::min<size_t>(TCP_MAX_STAGES, (227 * 1024 - 256 - 2 * tile_b) / stage_b);
-            const size_t soft = smem_soft > 256 + 2 * tile_b ? (smem_soft - 256 - 2 * tile_b) / stage_b : 0;
-            if (soft >= 4) stages = (int)std::min<size_t>(stages, soft);
+            if (256 + 2 * tile_b + 2 * (size_t)g.slab_bytes > 227 * 1024) continue;
+            const size_t ring_space = 227 * 1024 - 256 - 2 * tile_b;
             const long long tiles = (long long)gx_p * ((p.rows + n - 1) / n);
             const long long per_cta = (tiles + ctx->sm_count - 1) / ctx->sm_count;
-            const double mma_tile = (double)g.h * g.nk * std::max(0.5 * n, 64.0 + 0.25 * n);
-            for (int ew = 8; ew <= 12; ew += 4) {
-                if (force_ew && ew != force_ew) continue;
-                const double epi_tile = n * TCP_EPI_CLK_PER_ROW * 8.0 / ew;
-                // EW = 12 fills the register file (no co-resident kernels of other streams): it has to win by 10 %
-                const double cost = ((double)per_cta * std::max(mma_tile, epi_tile) + epi_tile + 40.0 * (n + g.h)) * (ew == 8 ? 1.0 : 1.1);
-                if (cost < best_cost - 1e-9) { best_cost = cost; bestN = n; best_stages = stages; best_ew = ew; }
+            const double t_mma = 1.1 * (0.5 * n + 8.0);
+            const double bubble = std::max(0.0, 390.0 - 3.0 * t_mma);
+            const double need = 2500.0 * 4096.0 / t_mma;                       // bytes in flight that hide the L2 latency
+            for (int ds = 1; ds <= ds_cap; ++ds) {
+                if (force_ds && ds != std::min(force_ds, g.h)) continue;
+                const size_t stage_b = (size_t)ds * g.slab_bytes;
+                const int stages = (int)std::min<size_t>(TCP_MAX_STAGES, ring_space / stage_b);
+                if (stages < 2) break;
+                const double in_flight = (double)(stages - 1) * (double)stage_b;
+                const double starve = std::max(1.0, need / in_flight);
+                const double mma_tile = ((double)g.h * g.nk * t_mma + std::ceil((double)g.h / ds) * bubble) * starve;
+                for (int ew = 8; ew <= 12; ew += 4) {
+                    if (force_ew && ew != force_ew) continue;
+                    const double epi_tile = n * (ew == 8 ? TCP_EPI_CLK_PER_ROW : TCP_EPI_CLK_PER_ROW_12);
+                    // (A/B on C2 / C4 / C5, round 2: 12 epilogue warps win everywhere, 10 % at C4 -- also with several streams per GPU)
+                    // (the two phases of a tile overlap imperfectly: the shorter one still costs a share -- measured: the stage size
+                    // of an epilogue-bound launch changes its time)
+                    const double tile_clk = std::max(mma_tile, epi_tile) + 0.3 * std::min(mma_tile, epi_tile);
+                    const double cost = (double)per_cta * tile_clk + epi_tile + 40.0 * (n + g.h);
+                    if (cost < best_cost - 1e-9) { best_cost = cost; bestN = n; best_stages = stages; best_ew = ew; best_ds = ds; }
+                }
             }
         }
+        const int ds_p = best_ds;
+        const size_t stage_b = (size_t)ds_p * g.slab_bytes;
+        if (tc_env().plan_dbg && bestN)
+            fprintf(stderr, "[mtm plan] h=%d w=%d nk=%d count=%d rows=%d: N=%d ds=%d (%zu KB) stages=%d ew=%d model %.0f clk\n", g.h, g.w, g.nk, g.count, p.rows,
+                    bestN, ds_p, stage_b / 1024, best_stages, best_ew, best_cost);
         if (bestN) {
             const size_t tile_b = ((size_t)2 * g.nk * tc_tile_rows(bestN, g.h) * 16 + 127) & ~(size_t)127;
             p.N = bestN; p.R = tc_tile_rows(bestN, g.h); p.stages = best_stages; p.ds = ds_p;
