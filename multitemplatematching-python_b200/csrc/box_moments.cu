@@ -278,19 +278,22 @@ box_moments_c1_kernel(const BoxParams p)
             const uint2* pl = &P[buf][tid];
             const uint2* pr = pl + sd.w;
             uint2* o = out_row;
+            auto emit = [&](int j) {
+                const uint2 t = wtot[buf][j];
+                const uint2 lo = pl[j * B1_THREADS], hi = pr[j * B1_THREADS];
+                const uint32_t s = hi.x - lo.x + (t.x & seg_mask);
+                const uint32_t qs = hi.y - lo.y + (t.y & seg_mask);
+                const unsigned long long d1 = (unsigned long long)area * qs - (unsigned long long)s * s;
+                const float rs = d1 ? mtm_rsqrt_normal((float)d1) : 0.0f;      // d1 >= 1: never subnormal
+                o[j * dst_step] = make_uint2(s, __float_as_uint(rs));
+            };
+            if (jn == B1_PX) {                                      // every strip but the last one of a row: no per-position tests
 #pragma unroll
-            for (int j = 0; j < B1_PX; ++j) {
-                if (j < jn) {
-                    const uint2 t = wtot[buf][j];
-                    const uint2 lo = pl[j * B1_THREADS], hi = pr[j * B1_THREADS];
-                    const uint32_t s = hi.x - lo.x + (t.x & seg_mask);
-                    const uint32_t qs = hi.y - lo.y + (t.y & seg_mask);
-                    const unsigned long long d1 = (unsigned long long)area * qs - (unsigned long long)s * s;
-                    const float f = (float)d1;                                 // 0 exactly when d1 == 0 (a flat window)
-                    const float rs = f != 0.0f ? mtm_rsqrt_normal(f) : 0.0f;  // d1 >= 1: never subnormal
-                    *o = make_uint2(s, __float_as_uint(rs));
-                }
-                o += dst_step;
+                for (int j = 0; j < B1_PX; ++j) emit(j);
+            } else {
+#pragma unroll
+                for (int j = 0; j < B1_PX; ++j)
+                    if (j < jn) emit(j);
             }
             out_row += 16;
         } else {

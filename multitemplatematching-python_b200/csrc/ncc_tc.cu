@@ -1459,7 +1459,9 @@ static int launch_ncc_tc_impl(mtm_ctx* ctx, const TcGroup& g, int method, const 
                 const double mma_tile = ((double)g.h * g.nk * t_mma + std::ceil((double)g.h / ds) * bubble) * starve;
                 for (int ew = 8; ew <= 12; ew += 4) {
                     if (force_ew && ew != force_ew) continue;
-                    const double epi_tile = n * (ew == 8 ? TCP_EPI_CLK_PER_ROW : TCP_EPI_CLK_PER_ROW_12);
+                    // the ew / 4 warps of a lane quarter split the n / 16 column batches: the slowest one sets the pace
+                    const int parts = ew / 4, n_eff = 16 * parts * ((n / 16 + parts - 1) / parts);
+                    const double epi_tile = n_eff * (ew == 8 ? TCP_EPI_CLK_PER_ROW : TCP_EPI_CLK_PER_ROW_12);
                     // (A/B on C2 / C4 / C5, round 2: 12 epilogue warps win everywhere, 10 % at C4 -- also with several streams per GPU)
                     // (the two phases of a tile overlap imperfectly: the shorter one still costs a share -- measured: the stage size
                     // of an epilogue-bound launch changes its time)
