@@ -36,6 +36,7 @@ struct BoxParams {
     uint32_t* S; float* rsD;                           // the moment ring (tile-major segments, mtm_internal.cuh)
     int64_t mom_plane;
     int y_begin, rows;                                 // output rows [y_begin, y_begin + rows) of every size (clipped to its map)
+    int out_mode;                                      // experiment knob MTM_B200_BOX_OUT: 0 general output loop, 1 predicated lean loop, 2 (default) + branch-free full strips
 };
 
 template <int C>
@@ -269,7 +270,7 @@ box_moments_c1_kernel(const BoxParams p)
 #pragma unroll
         for (int j = 0; j < 8; j += 2) dst[j >> 1] = make_uint4(bs + es[j], bq + eq[j], bs + es[j + 1], bq + eq[j + 1]);
         __syncthreads();                                            // the only barrier of the row (buffers alternate)
-        if (!wide) {
+        if (!wide && p.out_mode != 0) {
             // Windows no wider than a segment (w <= 256: everything but very wide templates).  Position xl = tid + 256 j lies in
             // segment j and its right edge in segment j + seg_off, seg_off = (tid + w) >> 8 in {0, 1}: the window sum is the
             // difference of the two segment-local prefixes plus, when the edge crossed into the next segment, segment j's total
@@ -287,7 +288,7 @@ box_moments_c1_kernel(const BoxParams p)
                 const float rs = d1 ? mtm_rsqrt_normal((float)d1) : 0.0f;      // d1 >= 1: never subnormal
                 o[j * dst_step] = make_uint2(s, __float_as_uint(rs));
             };
-            if (jn == B1_PX) {                                      // every strip but the last one of a row: no per-position tests
+            if (jn == B1_PX && p.out_mode != 1) {                  // every strip but the last one of a row: no per-position tests
 #pragma unroll
                 for (int j = 0; j < B1_PX; ++j) emit(j);
             } else {
@@ -359,6 +360,8 @@ int launch_box_moments(mtm_ctx* ctx, int size_first, int size_count, int y_begin
     p.img = im.pix; p.pitch = im.pitch; p.sizes = ctx->d_sizes + size_first;
     p.S = ctx->d_wS; p.rsD = ctx->d_wR; p.mom_plane = ctx->moments_total;
     p.y_begin = y_begin; p.rows = rows;
+    static const int out_mode = getenv("MTM_B200_BOX_OUT") ? atoi(getenv("MTM_B200_BOX_OUT")) : 2;
+    p.out_mode = out_mode;
     const SizeDesc* sizes = ctx->h_sizes.data() + size_first;
     int strips = 1, mh = 1;
     for (int q = 0; q < size_count; ++q) {

@@ -534,17 +534,17 @@ static int plan_tensor_path(mtm_ctx* ctx)
     if ((ctx->tmpl_C != 1 && ctx->tmpl_C != 3 && ctx->tmpl_C != 4) || (ctx->tmpl_dtype != MTM_U8 && !planes16)) return MTM_OK;
     const int n = ctx->n_tmpl;
     const int TC = ctx->tmpl_C;
-    // Cost model (tensor-pipe clocks per output pixel, up to a constant): a mode-A launch serves up to
-    // 8 templates for h*nk/16, a mode-B launch one template for h*nk/128.  Templates are visited in
-    // (h, w) order; a template joins the open mode-A group (zero padded to the group's size) while
-    // that is cheaper than handling it alone.
-    auto cost = [](const TcGroup& g) { return (double)g.h * g.nk / (g.mode == 0 ? 16.0 : 128.0); };
-    auto alone = [&](int h, int w, TcGroup& best) {
-        TcGroup a{}, b{};
-        const bool okA = tc_plan_group(0, h, w, TC, a), okB = tc_plan_group(1, h, w, TC, b);
-        if (!okA && !okB) return false;
-        best = (okA && (!okB || cost(a) <= cost(b))) ? a : b;
-        return true;
+    // Grouping = the cheapest partition of the (h, w)-sorted templates into launches (dynamic programme over prefixes; a
+    // mode-A launch takes up to 8 CONSECUTIVE templates, zero padded to the largest member, a mode-B launch one template).
+    // Cost of a launch in clocks per output row of a 16-column tile (what the measured role clocks of the persistent kernel
+    // suggest, profiles/README.md): MMAs 0.6 * h * nk (~1.1 (N/2 + 8) clocks each at N ~ 200, h * nk of them per tile), the
+    // epilogue ~55 -- whichever is longer plus a share of the other (they overlap imperfectly); a mode-B launch covers eight
+    // such columns at once for its single template.  The epilogue term is what the first planner missed: a launch of four
+    // templates costs as much as one of eight (C5, 64 sizes: 11 launches, three of them with 4-5 templates -> 8 full ones).
+    auto launch_cost = [](const TcGroup& g) {
+        const double mma = 0.6 * g.h * g.nk, epi = 55.0;
+        const double c = std::max(mma, epi) + 0.3 * std::min(mma, epi);
+        return g.mode == 0 ? c : c / 8.0;
     };
     int64_t arena = 0;
     auto emit = [&](TcGroup g, int first, int count, int h_min, int w_min) {
@@ -553,38 +553,40 @@ static int plan_tensor_path(mtm_ctx* ctx)
         arena += ((int64_t)g.h * g.slab_bytes + 127) / 128 * 128;
         ctx->tc_groups.push_back(g);
     };
-    int i = 0;
-    while (i < n) {
-        const TmplMeta& m0 = ctx->h_meta[ctx->h_order[i]];
-        TcGroup solo{};
-        if (!alone(m0.h, m0.w, solo)) return MTM_OK;
-        TcGroup open{};
-        bool have_open = tc_plan_group(0, m0.h, m0.w, TC, open);
-        double solo_sum = cost(solo);
-        int j = i + 1, hg = m0.h, wg = m0.w, h_min = m0.h, w_min = m0.w;
-        while (have_open && j < n && j - i < 8) {
-            const TmplMeta& mj = ctx->h_meta[ctx->h_order[j]];
-            TcGroup sj{}, grown{};
-            if (!alone(mj.h, mj.w, sj)) return MTM_OK;
-            const int hg2 = std::max(hg, mj.h), wg2 = std::max(wg, mj.w);
-            if (!tc_plan_group(0, hg2, wg2, TC, grown)) break;
-            if (cost(grown) > cost(open) + cost(sj)) break;          // cheaper to start a new group
-            open = grown; hg = hg2; wg = wg2;
-            h_min = std::min(h_min, mj.h); w_min = std::min(w_min, mj.w);
-            solo_sum += cost(sj);
-            ++j;
+    std::vector<double> best((size_t)n + 1, 1e300);
+    std::vector<int> take((size_t)n + 1, 0), mode_of((size_t)n + 1, 0);
+    best[0] = 0.0;
+    for (int i = 1; i <= n; ++i) {
+        int hg = 0, wg = 0;
+        for (int k = 1; k <= 8 && k <= i; ++k) {                     // a mode-A launch of the templates [i - k, i)
+            const TmplMeta& m = ctx->h_meta[ctx->h_order[i - k]];
+            hg = std::max(hg, (int)m.h); wg = std::max(wg, (int)m.w);
+            TcGroup g{};
+            if (!tc_plan_group(0, hg, wg, TC, g)) break;
+            const double c = best[i - k] + launch_cost(g);
+            if (c < best[i] - 1e-12) { best[i] = c; take[i] = k; mode_of[i] = 0; }
         }
-        if (have_open && cost(open) <= solo_sum) {
-            emit(open, i, j - i, h_min, w_min);
-        } else {                                                     // members are cheaper one by one
-            for (int k = i; k < j; ++k) {
-                const TmplMeta& mk = ctx->h_meta[ctx->h_order[k]];
-                TcGroup sk{};
-                if (!alone(mk.h, mk.w, sk)) return MTM_OK;
-                emit(sk, k, 1, mk.h, mk.w);
-            }
+        const TmplMeta& m1 = ctx->h_meta[ctx->h_order[i - 1]];
+        TcGroup b{};
+        if (tc_plan_group(1, m1.h, m1.w, TC, b)) {                   // ... or template i - 1 alone in mode B
+            const double c = best[i - 1] + launch_cost(b);
+            if (c < best[i] - 1e-12) { best[i] = c; take[i] = 1; mode_of[i] = 1; }
         }
-        i = j;
+        if (best[i] >= 1e299) return MTM_OK;                         // a template no tile fits: no tensor path for this set
+    }
+    std::vector<std::pair<int, int>> cuts;                           // (first, count) back to front
+    for (int i = n; i > 0; i -= take[i]) cuts.push_back({i - take[i], take[i] | (mode_of[i] << 8)});
+    for (auto it = cuts.rbegin(); it != cuts.rend(); ++it) {
+        const int first = it->first, count = it->second & 255, mode = it->second >> 8;
+        int hg = 0, wg = 0, h_min = 1 << 30, w_min = 1 << 30;
+        for (int k = first; k < first + count; ++k) {
+            const TmplMeta& m = ctx->h_meta[ctx->h_order[k]];
+            hg = std::max(hg, (int)m.h); wg = std::max(wg, (int)m.w);
+            h_min = std::min(h_min, (int)m.h); w_min = std::min(w_min, (int)m.w);
+        }
+        TcGroup g{};
+        if (!tc_plan_group(mode, hg, wg, TC, g)) return MTM_OK;
+        emit(g, first, count, h_min, w_min);
     }
     ctx->slab_plane = (arena + 127) / 128 * 128;
     MTM_TRY(mtm_reserve(ctx, ctx->d_slabs, ctx->slabs_cap, (size_t)(planes16 ? 2 : 1) * ctx->slab_plane + 128));
