@@ -36,7 +36,6 @@ struct BoxParams {
     uint32_t* S; float* rsD;                           // the moment ring (tile-major segments, mtm_internal.cuh)
     int64_t mom_plane;
     int y_begin, rows;                                 // output rows [y_begin, y_begin + rows) of every size (clipped to its map)
-    int out_mode;                                      // experiment knob MTM_B200_BOX_OUT: 0 general output loop, 1 predicated lean loop, 2 (default) + branch-free full strips
 };
 
 template <int C>
@@ -176,6 +175,9 @@ constexpr int B1_PX = 8;
 constexpr int B1_COLS = B1_THREADS * B1_PX;           // 2048 image columns per strip
 constexpr int B1_WARPS = B1_THREADS / 32;
 
+// LEAN: every window of the launch is at most 256 px wide (one instantiation per output loop: the row loop has to stay small --
+// a kernel that carried both loops, or the eight positions unrolled without their tests, ran 8-17 % slower: instruction fetch).
+template <bool LEAN, bool ROLLED = false>
 __global__ void __launch_bounds__(B1_THREADS, 3)
 box_moments_c1_kernel(const BoxParams p)
 {
@@ -270,7 +272,7 @@ box_moments_c1_kernel(const BoxParams p)
 #pragma unroll
         for (int j = 0; j < 8; j += 2) dst[j >> 1] = make_uint4(bs + es[j], bq + eq[j], bs + es[j + 1], bq + eq[j + 1]);
         __syncthreads();                                            // the only barrier of the row (buffers alternate)
-        if (!wide && p.out_mode != 0) {
+        if (LEAN) {
             // Windows no wider than a segment (w <= 256: everything but very wide templates).  Position xl = tid + 256 j lies in
             // segment j and its right edge in segment j + seg_off, seg_off = (tid + w) >> 8 in {0, 1}: the window sum is the
             // difference of the two segment-local prefixes plus, when the edge crossed into the next segment, segment j's total
@@ -288,9 +290,9 @@ box_moments_c1_kernel(const BoxParams p)
                 const float rs = d1 ? mtm_rsqrt_normal((float)d1) : 0.0f;      // d1 >= 1: never subnormal
                 o[j * dst_step] = make_uint2(s, __float_as_uint(rs));
             };
-            if (jn == B1_PX && p.out_mode != 1) {                  // every strip but the last one of a row: no per-position tests
-#pragma unroll
-                for (int j = 0; j < B1_PX; ++j) emit(j);
+            if (ROLLED) {                                                  // default: the smallest row loop (see launch_box_moments)
+#pragma unroll 1
+                for (int j = 0; j < jn; ++j) emit(j);
             } else {
 #pragma unroll
                 for (int j = 0; j < B1_PX; ++j)
@@ -360,8 +362,6 @@ int launch_box_moments(mtm_ctx* ctx, int size_first, int size_count, int y_begin
     p.img = im.pix; p.pitch = im.pitch; p.sizes = ctx->d_sizes + size_first;
     p.S = ctx->d_wS; p.rsD = ctx->d_wR; p.mom_plane = ctx->moments_total;
     p.y_begin = y_begin; p.rows = rows;
-    static const int out_mode = getenv("MTM_B200_BOX_OUT") ? atoi(getenv("MTM_B200_BOX_OUT")) : 2;
-    p.out_mode = out_mode;
     const SizeDesc* sizes = ctx->h_sizes.data() + size_first;
     int strips = 1, mh = 1;
     for (int q = 0; q < size_count; ++q) {
@@ -385,7 +385,14 @@ int launch_box_moments(mtm_ctx* ctx, int size_first, int size_count, int y_begin
         const int want = 3 * ctx->sm_count;
         const int bands1 = std::max(1, std::min(std::max(1, mh / 8), (want + strips1 * n_sizes - 1) / (strips1 * n_sizes)));
         const dim3 grid1((unsigned)strips1, (unsigned)bands1, (unsigned)n_sizes);
-        box_moments_c1_kernel<<<grid1, B1_THREADS, 0, ctx->stream>>>(p);
+        bool lean = getenv("MTM_B200_BOX_OUT") == nullptr || atoi(getenv("MTM_B200_BOX_OUT")) != 0;       // A/B knob: 0 = general output loop
+        for (int q = 0; q < size_count; ++q) lean = lean && sizes[q].w <= B1_THREADS;
+        // A/B on C5 (64 sizes, ncu): general loop 1.90 ms, lean unrolled 1.71 ms, lean rolled 1.60 ms (default) -- the row loop is
+        // bound by instruction fetch, the smallest body wins.  MTM_B200_BOX_OUT = 0 / 1 select the other two.
+        static const bool rolled = getenv("MTM_B200_BOX_OUT") == nullptr || atoi(getenv("MTM_B200_BOX_OUT")) >= 2;
+        if (lean && rolled) box_moments_c1_kernel<true, true><<<grid1, B1_THREADS, 0, ctx->stream>>>(p);
+        else if (lean) box_moments_c1_kernel<true><<<grid1, B1_THREADS, 0, ctx->stream>>>(p);
+        else box_moments_c1_kernel<false><<<grid1, B1_THREADS, 0, ctx->stream>>>(p);
         MTM_LAUNCH_CHECK(ctx);
         return MTM_OK;
     }

@@ -250,7 +250,11 @@ extern "C" int emu_box_moments(const uint8_t* img, int64_t pitch, int C, const S
             const int strip_out = (B1_COLS - (sizes[k].w - 1)) & ~15;
             strips1 = std::max(strips1, (sizes[k].mw + strip_out - 1) / strip_out);
         }
-        emu_launch_coop(dim3(strips1, -bands, n_sizes), dim3(B1_THREADS), [&] { box_moments_c1_kernel(p); });
+        bool lean = getenv("EMU_BOX_GENERAL_LOOP") == nullptr;      // as launch_box_moments: the lean output loop when every window is <= 256 px wide
+        for (int k = 0; k < n_sizes; ++k) lean = lean && sizes[k].w <= B1_THREADS;
+        if (lean && getenv("EMU_BOX_UNROLLED") == nullptr) emu_launch_coop(dim3(strips1, -bands, n_sizes), dim3(B1_THREADS), [&] { box_moments_c1_kernel<true, true>(p); });
+        else if (lean) emu_launch_coop(dim3(strips1, -bands, n_sizes), dim3(B1_THREADS), [&] { box_moments_c1_kernel<true>(p); });
+        else emu_launch_coop(dim3(strips1, -bands, n_sizes), dim3(B1_THREADS), [&] { box_moments_c1_kernel<false>(p); });
         return strips1;
     }
     const dim3 grid(strips, bands, n_sizes), block(BM_THREADS);
