@@ -21,6 +21,7 @@
 // Experiment knob MTM_B200_MOM_BOX=1 (mtm_api.cu: the summed-area tables are then built on demand only).  Checked on the
 // CPU against window_moments_kernel (tests/test_kernel_emulation.py); NOT YET MEASURED ON THE GPU.
 #include "mtm_internal.cuh"
+#include <algorithm>
 #include <cstdlib>
 
 namespace {
@@ -177,8 +178,8 @@ constexpr int B1_WARPS = B1_THREADS / 32;
 
 // LEAN: every window of the launch is at most 256 px wide (one instantiation per output loop: the row loop has to stay small --
 // a kernel that carried both loops, or the eight positions unrolled without their tests, ran 8-17 % slower: instruction fetch).
-template <bool LEAN, bool ROLLED = false>
-__global__ void __launch_bounds__(B1_THREADS, 3)
+template <bool LEAN, bool ROLLED = false, int OCC = 3>
+__global__ void __launch_bounds__(B1_THREADS, OCC)
 box_moments_c1_kernel(const BoxParams p)
 {
     __shared__ __align__(16) uint2 P[2][B1_COLS + 8];  // exclusive prefix INSIDE the owning warp's 256 columns: {S, Q mod 2^32}
@@ -382,7 +383,9 @@ int launch_box_moments(mtm_ctx* ctx, int size_first, int size_count, int y_begin
             strips1 = std::max(strips1, (sizes[q].mw + strip_out - 1) / strip_out);
         }
         // bands: enough CTAs for three per SM, but a band keeps at least 8 output rows (it first re-adds the h-1 rows above it)
-        const int want = 3 * ctx->sm_count;
+        // CTAs per SM (registers per thread): A/B at C5 (ncu): 3 (72) 1.60 ms, 4 (64) 1.44 ms (default); MTM_B200_BOX_OCC = 3 / 5 for the others
+        static const int occ = getenv("MTM_B200_BOX_OCC") ? std::min(6, std::max(3, atoi(getenv("MTM_B200_BOX_OCC")))) : 4;
+        const int want = occ * ctx->sm_count;
         const int bands1 = std::max(1, std::min(std::max(1, mh / 8), (want + strips1 * n_sizes - 1) / (strips1 * n_sizes)));
         const dim3 grid1((unsigned)strips1, (unsigned)bands1, (unsigned)n_sizes);
         bool lean = getenv("MTM_B200_BOX_OUT") == nullptr || atoi(getenv("MTM_B200_BOX_OUT")) != 0;       // A/B knob: 0 = general output loop
@@ -390,7 +393,10 @@ int launch_box_moments(mtm_ctx* ctx, int size_first, int size_count, int y_begin
         // A/B on C5 (64 sizes, ncu): general loop 1.90 ms, lean unrolled 1.71 ms, lean rolled 1.60 ms (default) -- the row loop is
         // bound by instruction fetch, the smallest body wins.  MTM_B200_BOX_OUT = 0 / 1 select the other two.
         static const bool rolled = getenv("MTM_B200_BOX_OUT") == nullptr || atoi(getenv("MTM_B200_BOX_OUT")) >= 2;
-        if (lean && rolled) box_moments_c1_kernel<true, true><<<grid1, B1_THREADS, 0, ctx->stream>>>(p);
+        if (lean && rolled && occ == 4) box_moments_c1_kernel<true, true, 4><<<grid1, B1_THREADS, 0, ctx->stream>>>(p);
+        else if (lean && rolled && occ == 5) box_moments_c1_kernel<true, true, 5><<<grid1, B1_THREADS, 0, ctx->stream>>>(p);
+        else if (lean && rolled && occ == 6) box_moments_c1_kernel<true, true, 6><<<grid1, B1_THREADS, 0, ctx->stream>>>(p);
+        else if (lean && rolled) box_moments_c1_kernel<true, true><<<grid1, B1_THREADS, 0, ctx->stream>>>(p);
         else if (lean) box_moments_c1_kernel<true><<<grid1, B1_THREADS, 0, ctx->stream>>>(p);
         else box_moments_c1_kernel<false><<<grid1, B1_THREADS, 0, ctx->stream>>>(p);
         MTM_LAUNCH_CHECK(ctx);
