@@ -416,6 +416,7 @@ struct TcParams {
     unsigned long long* best;         // MODE 3, N_object == 1: per template arg-max key (ordered score << 32 | ~map index), nullptr: off
     int C; int64_t mom_plane;         // channels (1, 3, 4) and the element stride between the per-channel S planes
     int stages, tiles_x, tiles_total; // persistent kernel: slab ring depth, tile grid width, number of tiles
+    int ctrl_first;                   // experiment MTM_B200_CTRL_FIRST=1: control warps first, one more (idle) warp per CTA
     long long* prof; int dbg;         // debug only (MTM_B200_PROF / MTM_B200_PDBG): per-CTA role clocks, phase knock-outs
     int method;                       // cv2 method id; != TM_CCOEFF_NORMED takes the float64 epilogue on the summed-area tables
     SatView sat;
@@ -917,6 +918,12 @@ __device__ __forceinline__ void ncc_tc_persist_body(const TcParams& p, const CUt
     constexpr int TCP_EPI_THREADS = 32 * EW;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // Warp roles.  Default: warps 0 .. EW-1 epilogue, EW producer, EW+1 MMA issuer, EW+2 loader.  p.ctrl_first (experiment): the three
+    // control warps come FIRST (0 producer, 1 MMA issuer, 2 loader, 3 idle) and the epilogue warps are 4 .. EW+3 -- the TMEM lane
+    // quarter of an epilogue warp stays warp % 4 either way.
+    const int w_prod = p.ctrl_first ? 0 : EW, w_mma = p.ctrl_first ? 1 : EW + 1, w_load = p.ctrl_first ? 2 : EW + 2;
+    const int ewarp = p.ctrl_first ? warp - 4 : warp;           // index among the epilogue warps (valid for those only)
+    const bool is_epi = p.ctrl_first ? warp >= 4 : warp < EW;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
     uint64_t* full = bars;                                      // [stages]  slab bytes landed
     uint64_t* empty = bars + TCP_MAX_STAGES;                    // [stages]  tcgen05.commit
@@ -945,18 +952,18 @@ __device__ __forceinline__ void ncc_tc_persist_body(const TcParams& p, const CUt
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == EW) tmem_alloc(tmem_slot, tmem_cols);
+    if (warp == w_prod) tmem_alloc(tmem_slot, tmem_cols);
     // register staging (p.tma == 0): the first image tile is staged by the whole CTA (nothing else to do yet); the stagers
     // take over from the second.  With the TMA unit the loader warp issues every tile, the first one included.
-    if (!p.tma) stage_image_tile<TCP_THREADS>(tiles, p.img, p.pitch, p.H, ((int)blockIdx.x % p.tiles_x) * xw * p.C,
-                                              p.y_base + ((int)blockIdx.x / p.tiles_x) * p.N, p.R, kb_img, tid);
+    if (!p.tma && tid < TCP_THREADS) stage_image_tile<TCP_THREADS>(tiles, p.img, p.pitch, p.H, ((int)blockIdx.x % p.tiles_x) * xw * p.C,
+                                                                   p.y_base + ((int)blockIdx.x / p.tiles_x) * p.N, p.R, kb_img, tid);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == EW) {
+    if (warp == w_prod) {
         // ===== slab producer: the slab sequence of a tile repeats for every tile; the ring position runs on.
         // The whole warp walks the loop (warp-uniform control flow, uniform registers); one elected lane issues.
         int s = 0;
@@ -984,7 +991,7 @@ __device__ __forceinline__ void ncc_tc_persist_body(const TcParams& p, const CUt
         }
         if (PROF && lane == 0) p.prof[16 * blockIdx.x + 8] = w_empty;
         __syncwarp();
-    } else if (warp == EW + 1) {
+    } else if (warp == w_mma) {
         // ===== MMA issuer: warp-uniform loop, one elected lane issues (mma_issuer_role below)
         const uint32_t tile_addr0 = smem_u32(tiles), ring_addr = smem_u32(ring);
         switch (p.nk) {
@@ -996,9 +1003,9 @@ __device__ __forceinline__ void ncc_tc_persist_body(const TcParams& p, const CUt
             case 6: mma_issuer_role<PROF, 6>(p, full, empty, tile_full, tile_empty, acc_full, acc_empty, tile_addr0, tile_bytes, ring_addr, stage_bytes, tmem_base, acc_stride, my_tiles, lane); break;
             default: mma_issuer_role<PROF, 0>(p, full, empty, tile_full, tile_empty, acc_full, acc_empty, tile_addr0, tile_bytes, ring_addr, stage_bytes, tmem_base, acc_stride, my_tiles, lane); break;
         }
-    } else if (warp >= EW + 2 && p.tma) {
+    } else if (!is_epi && p.tma) {
         // ===== image tile loader: one warp, one elected lane per tile feeds the TMA unit (launched with EW + 3 warps)
-        if (warp == EW + 2) {
+        if (warp == w_load) {
             const uint32_t bytes = tma_tile_bytes(kb_img, p.tma_rc, p.tma_chunks);
             for (int i = 0; i < my_tiles; ++i) {
                 const int b = i & 1, u = i >> 1;
@@ -1012,9 +1019,9 @@ __device__ __forceinline__ void ncc_tc_persist_body(const TcParams& p, const CUt
                 __syncwarp();
             }
         }
-    } else if (warp >= EW + 2) {
-        // ===== image tile stagers (register staging) =====
-        const int t = tid - 32 * (EW + 2);
+    } else if (!is_epi && warp == w_load) {
+        // ===== image tile stager (register staging) =====
+        const int t = tid - 32 * w_load;
         long long w_te = 0, w_work = 0;
         for (int i = 0; i < my_tiles; ++i) {
             const int b = i & 1, u = i >> 1;
@@ -1030,13 +1037,13 @@ __device__ __forceinline__ void ncc_tc_persist_body(const TcParams& p, const CUt
             if (PROF) { w_te += c1 - c0; w_work += clock64() - c1; }
         }
         if (PROF && t == 0) { p.prof[16 * blockIdx.x + 6] = w_te; p.prof[16 * blockIdx.x + 7] = w_work; }
-    } else {
+    } else if (is_epi) {
         // ===== epilogue warps =====
         long long w_af = 0, w_epi = 0;
         BestTrack bt{-3.0e38f, 0u};
         const bool c1 = (MODE == 0 || MODE == 3) && p.C == 1;
         LaneC1 L{};
-        if (c1) L = lane_c1_setup(p, warp, lane, EW / 4);
+        if (c1) L = lane_c1_setup(p, ewarp, lane, EW / 4);
         for (int i = 0; i < my_tiles; ++i) {
             const int b = i & 1, u = i >> 1;
             const int ti = (int)blockIdx.x + i * (int)gridDim.x;
@@ -1047,24 +1054,24 @@ __device__ __forceinline__ void ncc_tc_persist_body(const TcParams& p, const CUt
             const long long c1 = PROF ? clock64() : 0;
             tc_fence_after();
             if (!PROF || !(p.dbg & 1)) {
-                if (c1) epilogue_tile_c1<(MODE == 3 ? 3 : 0), PIPE>(p, L, tmem_base + (uint32_t)b * acc_stride, x0, y0, warp, lane, bt);
-                else epilogue_tile<MODE>(p, tmem_base + (uint32_t)b * acc_stride, x0, y0, warp, lane, EW / 4, bt);
+                if (c1) epilogue_tile_c1<(MODE == 3 ? 3 : 0), PIPE>(p, L, tmem_base + (uint32_t)b * acc_stride, x0, y0, ewarp, lane, bt);
+                else epilogue_tile<MODE>(p, tmem_base + (uint32_t)b * acc_stride, x0, y0, ewarp, lane, EW / 4, bt);
             }
             tc_fence_before();
             mbar_arrive(&acc_empty[b]);
             if (PROF) { w_af += c1 - c0; w_epi += clock64() - c1; }
         }
-        if (MODE == 3 && p.best) flush_best(p, bt, warp, lane);
-        if (PROF && tid == 0) { p.prof[16 * blockIdx.x + 4] = w_af; p.prof[16 * blockIdx.x + 5] = w_epi; }
+        if (MODE == 3 && p.best) flush_best(p, bt, ewarp, lane);
+        if (PROF && ewarp == 0 && lane == 0) { p.prof[16 * blockIdx.x + 4] = w_af; p.prof[16 * blockIdx.x + 5] = w_epi; }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == EW) tmem_dealloc(tmem_base, tmem_cols);
+    if (warp == w_prod) tmem_dealloc(tmem_base, tmem_cols);
 }
 
 // EW = 8: 352 threads, 168 registers (the pipelined epilogue holds two batches of moments); EW = 12: 480 threads, 128.
 template <bool PROF, int EW, int MODE>
-__global__ void __launch_bounds__(32 * (EW + 3), 1)
+__global__ void __launch_bounds__(32 * (EW + 4), 1)
 ncc_tc_persist_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap)
 {
     ncc_tc_persist_body<PROF, EW, MODE, EW == 8>(p, tmap);
@@ -1265,7 +1272,7 @@ int launch_i8_peak(mtm_ctx* ctx, int n, int iters)
 struct TcEnv {
     int force_n = 0, ds = 0, ew = 0, pdbg = 0, mom_cs = -1, stage_bytes = 65536;
     size_t smem_soft = 0;
-    bool persist_off = false, prof = false, mom_rows = false, tma_off = false, lean = false, plan_dbg = false;
+    bool persist_off = false, prof = false, mom_rows = false, tma_off = false, lean = false, plan_dbg = false, ctrl_first = false;
     TcEnv()
     {
         auto num = [](const char* name) { const char* v = getenv(name); return v ? atoi(v) : 0; };
@@ -1282,6 +1289,7 @@ struct TcEnv {
         tma_off = getenv("MTM_B200_TMA") && num("MTM_B200_TMA") == 0;
         lean = num("MTM_B200_LEAN") != 0;
         plan_dbg = num("MTM_B200_PLAN_DBG") != 0;
+        ctrl_first = num("MTM_B200_CTRL_FIRST") != 0;
     }
 };
 static const TcEnv& tc_env()
@@ -1508,24 +1516,25 @@ static int launch_ncc_tc_impl(mtm_ctx* ctx, const TcGroup& g, int method, const 
                 p.prof = d_prof;
             }
             p.dbg = pdbg;
+            p.ctrl_first = tc_env().ctrl_first ? 1 : 0;
             const int ew = best_ew;
             if (kmode == 2) {
-                if (ew == 12) ncc_tc_persist_kernel<false, 12, 2><<<grid_p, 32 * 15, smem_bytes, ctx->stream>>>(p, tmap);
-                else ncc_tc_persist_kernel<false, 8, 2><<<grid_p, 32 * 11, smem_bytes, ctx->stream>>>(p, tmap);
+                if (ew == 12) ncc_tc_persist_kernel<false, 12, 2><<<grid_p, 32 * (15 + p.ctrl_first), smem_bytes, ctx->stream>>>(p, tmap);
+                else ncc_tc_persist_kernel<false, 8, 2><<<grid_p, 32 * (11 + p.ctrl_first), smem_bytes, ctx->stream>>>(p, tmap);
             } else if (kmode == 1) {
-                if (ew == 12) ncc_tc_persist_kernel<false, 12, 1><<<grid_p, 32 * 15, smem_bytes, ctx->stream>>>(p, tmap);
-                else ncc_tc_persist_kernel<false, 8, 1><<<grid_p, 32 * 11, smem_bytes, ctx->stream>>>(p, tmap);
+                if (ew == 12) ncc_tc_persist_kernel<false, 12, 1><<<grid_p, 32 * (15 + p.ctrl_first), smem_bytes, ctx->stream>>>(p, tmap);
+                else ncc_tc_persist_kernel<false, 8, 1><<<grid_p, 32 * (11 + p.ctrl_first), smem_bytes, ctx->stream>>>(p, tmap);
             } else if (kmode == 3) {
-                if (ew == 12) ncc_tc_persist_kernel<false, 12, 3><<<grid_p, 32 * 15, smem_bytes, ctx->stream>>>(p, tmap);
-                else if (tc_env().lean) ncc_tc_persist_lean_kernel<3><<<grid_p, 32 * 11, smem_bytes, ctx->stream>>>(p, tmap);
-                else ncc_tc_persist_kernel<false, 8, 3><<<grid_p, 32 * 11, smem_bytes, ctx->stream>>>(p, tmap);
+                if (ew == 12) ncc_tc_persist_kernel<false, 12, 3><<<grid_p, 32 * (15 + p.ctrl_first), smem_bytes, ctx->stream>>>(p, tmap);
+                else if (tc_env().lean) ncc_tc_persist_lean_kernel<3><<<grid_p, 32 * (11 + p.ctrl_first), smem_bytes, ctx->stream>>>(p, tmap);
+                else ncc_tc_persist_kernel<false, 8, 3><<<grid_p, 32 * (11 + p.ctrl_first), smem_bytes, ctx->stream>>>(p, tmap);
             } else if (ew == 12) {
-                if (prof) ncc_tc_persist_kernel<true, 12, 0><<<grid_p, 32 * 15, smem_bytes, ctx->stream>>>(p, tmap);
-                else ncc_tc_persist_kernel<false, 12, 0><<<grid_p, 32 * 15, smem_bytes, ctx->stream>>>(p, tmap);
+                if (prof) ncc_tc_persist_kernel<true, 12, 0><<<grid_p, 32 * (15 + p.ctrl_first), smem_bytes, ctx->stream>>>(p, tmap);
+                else ncc_tc_persist_kernel<false, 12, 0><<<grid_p, 32 * (15 + p.ctrl_first), smem_bytes, ctx->stream>>>(p, tmap);
             } else {
-                if (prof) ncc_tc_persist_kernel<true, 8, 0><<<grid_p, 32 * 11, smem_bytes, ctx->stream>>>(p, tmap);
-                else if (tc_env().lean) ncc_tc_persist_lean_kernel<0><<<grid_p, 32 * 11, smem_bytes, ctx->stream>>>(p, tmap);
-                else ncc_tc_persist_kernel<false, 8, 0><<<grid_p, 32 * 11, smem_bytes, ctx->stream>>>(p, tmap);
+                if (prof) ncc_tc_persist_kernel<true, 8, 0><<<grid_p, 32 * (11 + p.ctrl_first), smem_bytes, ctx->stream>>>(p, tmap);
+                else if (tc_env().lean) ncc_tc_persist_lean_kernel<0><<<grid_p, 32 * (11 + p.ctrl_first), smem_bytes, ctx->stream>>>(p, tmap);
+                else ncc_tc_persist_kernel<false, 8, 0><<<grid_p, 32 * (11 + p.ctrl_first), smem_bytes, ctx->stream>>>(p, tmap);
             }
             MTM_LAUNCH_CHECK(ctx);
             if (prof) {
