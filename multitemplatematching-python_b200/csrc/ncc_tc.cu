@@ -1558,21 +1558,38 @@ static int launch_ncc_tc_impl(mtm_ctx* ctx, const TcGroup& g, int method, const 
     // 1.98 waves).  Cost model: waves x (rows + fixed per-tile work expressed in rows).
     const int xw_ = g.mode == 0 ? 16 : 128;
     const int gx = (p.mw + xw_ - 1) / xw_;
-    const size_t ring = (size_t)TC_STAGES * g.ds * g.slab_bytes;
-    auto smem_for = [&](int n) { return (((size_t)2 * g.nk * tc_tile_rows(n, g.h) * 16 + 127) & ~(size_t)127) + ring + 256; };
-    int bestN = g.N;
+    // Tile height AND rows per ring stage together (second session of round 2).  The planned (g.N, g.ds) keeps a 4 x 16-KB ring,
+    // which for 256 x 256 templates (C3: mode B, 7.9-KB slabs that serve 12 MMAs each) capped the tile at 128 rows: 961 tiles, 61 of
+    // them one pixel wide or high, 7 waves.  A mode-B launch needs ~13 KB of slabs in flight, so one row per stage frees 32 KB and
+    // the tile grows to 208 rows: 589 tiles = 3.98 waves.  Cost (clocks per SM): waves x (MMAs of a tile at 1.1 (n/2 + 8) clocks,
+    // stage bubbles and ring starvation as in the persistent model, + tile load and epilogue, which two co-resident CTAs hide).
+    auto smem_for = [&](int n, int ds) { return (((size_t)2 * g.nk * tc_tile_rows(n, g.h) * 16 + 127) & ~(size_t)127) + (size_t)TC_STAGES * ds * g.slab_bytes + 256; };
+    int bestN = 0, best_ds = g.ds;
     double best_cost = 1e300;
-    for (int n = g.N; n >= 32 && n >= g.N / 2; n -= 16) {
-        const int per_sm = (2 * smem_for(n) <= 226 * 1024) ? 2 : 1;          // TMEM (<= 256 columns) also allows 2
-        const long long tiles = (long long)gx * ((p.rows + n - 1) / n);
-        const long long waves = (tiles + (long long)per_sm * ctx->sm_count - 1) / ((long long)per_sm * ctx->sm_count);
-        const double cost = (double)waves * (n + 0.25 * g.h + 16.0) / per_sm;
-        if (cost < best_cost - 1e-9) { best_cost = cost; bestN = n; }
+    for (int ds = g.ds; ds >= 1; --ds) {
+        if (tc_env().ds && ds != std::min(tc_env().ds, g.ds)) continue;
+        for (int n = 256; n >= 32; n -= 16) {
+            if (tc_env().force_n && n != tc_env().force_n) continue;
+            const size_t smem = smem_for(n, ds);
+            if (smem > 227 * 1024 || tc_tile_rows(n, g.h) * 16 >= (1 << 18)) continue;
+            const int per_sm = (2 * smem <= 226 * 1024) ? 2 : 1;              // TMEM (<= 256 columns) also allows 2
+            const long long tiles = (long long)gx * ((p.rows + n - 1) / n);
+            const long long waves = (tiles + (long long)per_sm * ctx->sm_count - 1) / ((long long)per_sm * ctx->sm_count);
+            const double t_mma = 1.1 * (0.5 * n + 8.0);
+            const double need = 2500.0 * ((double)g.slab_bytes / g.nk) / t_mma;
+            const double starve = std::max(1.0, need / ((double)(TC_STAGES - 1) * ds * g.slab_bytes));
+            const double mma_tile = ((double)g.h * g.nk * t_mma + std::ceil((double)g.h / ds) * std::max(0.0, 390.0 - 3.0 * t_mma)) * starve;
+            const double other = 40.0 * (n + g.h) + 70.0 * n;                  // tile load + epilogue (8 warps)
+            const double cost = (double)waves * (per_sm * mma_tile + (per_sm == 1 ? other : 0.3 * other));
+            if (cost < best_cost - 1e-9) { best_cost = cost; bestN = n; best_ds = ds; }
+        }
     }
-    if (tc_env().force_n) bestN = g.N;
-    p.N = bestN; p.R = tc_tile_rows(bestN, g.h);
+    if (!bestN) return mtm_fail(ctx, MTM_ERR_UNSUPPORTED, "tensor path: no tile of a %d x %d template fits shared memory", g.h, g.w);
+    p.N = bestN; p.R = tc_tile_rows(bestN, g.h); p.ds = best_ds;
     plan_tma();
-    const size_t smem_bytes = smem_for(bestN);
+    const size_t smem_bytes = smem_for(bestN, best_ds);
+    if (tc_env().plan_dbg)
+        fprintf(stderr, "[mtm plan] one tile per CTA: h=%d w=%d nk=%d mode=%d: N=%d ds=%d smem=%zu model %.0f clk\n", g.h, g.w, g.nk, g.mode, bestN, best_ds, smem_bytes, best_cost);
     if (!ctx->tc_attr_set) {
         MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
