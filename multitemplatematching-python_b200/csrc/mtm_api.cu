@@ -541,10 +541,15 @@ static int plan_tensor_path(mtm_ctx* ctx)
     // epilogue ~55 -- whichever is longer plus a share of the other (they overlap imperfectly); a mode-B launch covers eight
     // such columns at once for its single template.  The epilogue term is what the first planner missed: a launch of four
     // templates costs as much as one of eight (C5, 64 sizes: 11 launches, three of them with 4-5 templates -> 8 full ones).
-    auto launch_cost = [](const TcGroup& g) {
+    // Every launch also pays ~20 us (launch, first tile, last epilogue: ~40 K clocks), expressed in the same unit through the
+    // score-map area of the resident image (2 MP when none is set yet): on small images fewer launches win, on large ones
+    // the term only breaks ties against single-template launches.
+    const double area = ctx->img.H > 0 ? (double)ctx->img.H * ctx->img.W : 2.0e6;
+    const double per_launch = 40000.0 * ctx->sm_count * 16.0 / std::max(area, 1.0);
+    auto launch_cost = [per_launch](const TcGroup& g) {
         const double mma = 0.6 * g.h * g.nk, epi = 55.0;
         const double c = std::max(mma, epi) + 0.3 * std::min(mma, epi);
-        return g.mode == 0 ? c : c / 8.0;
+        return (g.mode == 0 ? c : c / 8.0) + per_launch;
     };
     int64_t arena = 0;
     auto emit = [&](TcGroup g, int first, int count, int h_min, int w_min) {

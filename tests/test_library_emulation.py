@@ -93,6 +93,28 @@ def test_direct_and_tensor_routes_agree(lib_mtm):
         cd.close()
 
 
+def test_many_template_sizes_are_grouped_into_full_launches(lib_mtm):
+    """A C5-like template set (20 distinct square sizes) through the real host code: plan_tensor_path partitions the (h, w)-sorted
+    list by dynamic programming into mode-A launches of up to eight templates zero padded to the largest member (the first planner
+    left launches with four or five templates at the price of eight); the hit list equals the port's."""
+    from mtm_b200 import _native
+    from oracle import mtm_port, synth
+    rng = np.random.default_rng(21)
+    sides = np.linspace(16, 54, 20).round().astype(int)
+    temps = [synth.make_template(rng, int(s), int(s)) for s in sides]
+    image, _ = synth.make_scene(150, 190, temps[::3], 1, seed=21)
+    labelled = [("t%02d" % i, t) for i, t in enumerate(temps)]
+    ctx = _native.default_context()
+    ctx.reset_counters()
+    got = lib_mtm.matchTemplates(labelled, image, N_object=30, score_threshold=0.5, maxOverlap=0.25)
+    want = mtm_port.match_templates(labelled, image, N_object=30, score_threshold=0.5, maxOverlap=0.25)
+    assert len(want) >= 5
+    gp.assert_hits_equal(got, want)
+    # one tensor map per numerator launch: 20 templates on a small image -> three launches (the per-launch term of the cost model
+    # outweighs what single-template mode-B launches of the smallest templates would save)
+    assert ctx.counters()["tma_launches"] == 3, ctx.counters()
+
+
 def test_banded_moment_ring_through_the_host_code(lib_mtm, monkeypatch):
     """The window moments of a template group are produced band by band into a ring (mtm_api.cu: compute_maps), each band
     followed by its numerator launch.  A 64 KB ring forces several bands on a small scene: hit lists (hits-only search), the
