@@ -34,7 +34,10 @@ typedef enum mtm_status {
 /* MTM_U16: 16-bit unsigned pixels (image AND templates).  The reference casts them to float32 before
  * cv2.matchTemplate (MTM/__init__.py:71-74); here the same float32 semantics are kept for the window statistics and the
  * OpenCV epilogue, while the numerator is computed EXACTLY on the tensor cores from the high/low byte planes
- * (single-channel images; other shapes take the float32 kernels). */
+ * (single-channel images; other shapes take the float32 kernels).
+ * MTM_F32: what the reference's float32 cast produces.  Single-channel float32 images / templates whose pixels are all
+ * integers in [0, 65535] (16-bit data cast by the caller; a uint16 image with float32 templates) are detected on upload and
+ * take the same exact byte-plane route (MTM_B200_F32_EXACT=0 turns the detection off); everything else runs the fp32 kernels. */
 typedef enum mtm_dtype { MTM_U8 = 0, MTM_F32 = 1, MTM_U16 = 2 } mtm_dtype;
 
 /* cv2.TM_* codes, MTM/__init__.py:56 `method` */
