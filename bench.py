@@ -247,14 +247,33 @@ def cpu_port_run(pool, templates, params, steps, warmup):
     return dt, info
 
 
+def cpu_ncc_only_run(pool, templates, steps):
+    """BASELINE.md section 3, baseline B: cv2.matchTemplate(TM_CCOEFF_NORMED) alone -- no peak search, no NMS -- one task per
+    template under the reference's pool (MTM/__init__.py:172-175 with only line 92 inside): isolates the third-party kernel."""
+    import cv2
+    from concurrent.futures import ThreadPoolExecutor
+    arrays = [t[1] for t in templates]
+    workers = round(os.cpu_count() * .5)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        image = pool[i % len(pool)]
+        with ThreadPoolExecutor(max_workers=workers) as ex:
+            list(ex.map(lambda a: cv2.matchTemplate(image, a, cv2.TM_CCOEFF_NORMED), arrays))
+    return (time.perf_counter() - t0) / max(steps, 1)
+
+
 def cpu_baseline(pool, templates, params, name, budget_s=8.0, cpu_steps=None):
     """Bounded sample of the workload on the host cores: whole images (all templates), as many as fit the budget."""
     dt1, _ = cpu_port_run(pool, templates, params, 1, 1)
     steps = cpu_steps if cpu_steps is not None else int(min(100, max(1, round(budget_s / dt1))))
     dt, info = cpu_port_run(pool, templates, params, steps, 0)
+    steps_b = max(1, min(steps, int(round(2.0 / max(dt, 1e-6)))))              # ~2 s of baseline B
+    dt_b = cpu_ncc_only_run(pool, templates, steps_b)
     return {"value": len(templates) / dt, "unit": "matches/s", "cores": info["cores"], "kind": "port",
             "sample": "%d whole %s images (all %d templates each), %.1f s" % (steps, name, len(templates), dt * steps),
-            "ms_per_image": dt * 1e3, **{k: info[k] for k in ("pool_workers", "cv2", "cv2_threads", "ipp")}}
+            "ms_per_image": dt * 1e3, **{k: info[k] for k in ("pool_workers", "cv2", "cv2_threads", "ipp")},
+            "ncc_only": {"value": len(templates) / dt_b, "unit": "matches/s", "ms_per_image": dt_b * 1e3,
+                         "what": "BASELINE.md baseline B: cv2.matchTemplate alone under the same pool, %d images" % steps_b}}
 
 
 def reference_arm(args):
