@@ -1272,7 +1272,7 @@ int launch_i8_peak(mtm_ctx* ctx, int n, int iters)
 struct TcEnv {
     int force_n = 0, ds = 0, ew = 0, pdbg = 0, mom_cs = -1, stage_bytes = 65536;
     size_t smem_soft = 0;
-    bool persist_off = false, prof = false, mom_rows = false, tma_off = false, lean = false, plan_dbg = false, ctrl_first = false;
+    bool persist_off = false, persist_force = false, prof = false, mom_rows = false, tma_off = false, lean = false, plan_dbg = false, ctrl_first = false;
     TcEnv()
     {
         auto num = [](const char* name) { const char* v = getenv(name); return v ? atoi(v) : 0; };
@@ -1283,6 +1283,7 @@ struct TcEnv {
         pdbg = num("MTM_B200_PDBG");
         smem_soft = getenv("MTM_B200_SMEM_SOFT") ? (size_t)num("MTM_B200_SMEM_SOFT") * 1024 : 0;
         persist_off = getenv("MTM_B200_PERSIST") && num("MTM_B200_PERSIST") == 0;
+        persist_force = num("MTM_B200_PERSIST") == 2;
         prof = getenv("MTM_B200_PROF") != nullptr;
         mom_cs = getenv("MTM_B200_MOM_CS") ? num("MTM_B200_MOM_CS") : -1;
         mom_rows = num("MTM_B200_MOM_ROWS") != 0;
@@ -1429,6 +1430,41 @@ static int launch_ncc_tc_impl(mtm_ctx* ctx, const TcGroup& g, int method, const 
         if (p.tma) ctx->ctr.tma_launches++;
     };
 
+    // ---- plan of the one-tile-per-CTA kernel (ncc_tc_kernel).  It is the only choice when two tiles do not fit shared memory
+    // (256 x 256 templates), and it is COMPARED with the persistent plan otherwise: both models count clocks per SM.  Measured on
+    // 2048 x 2048 images (profiles/README.md, run r2ah): 8 templates of 200 x 200 px 1.71 ms persistent (112-row tiles, three
+    // starved ring stages) against 1.15 ms one tile per CTA (240-row tiles); 240 x 240: 2.81 against 1.79 ms; 160 x 160: equal;
+    // every BASELINE config stays persistent by a wide margin of the models.
+    // Tile height AND rows per ring stage together (second session of round 2).  The planned (g.N, g.ds) keeps a 4 x 16-KB ring,
+    // which for 256 x 256 templates (C3: mode B, 7.9-KB slabs that serve 12 MMAs each) capped the tile at 128 rows: 961 tiles, 61 of
+    // them one pixel wide or high, 7 waves.  A mode-B launch needs ~13 KB of slabs in flight, so one row per stage frees 32 KB and
+    // the tile grows to 208 rows: 589 tiles = 3.98 waves.  Cost (clocks per SM): waves x (MMAs of a tile at 1.1 (n/2 + 8) clocks,
+    // stage bubbles and ring starvation as in the persistent model, + tile load and epilogue, which two co-resident CTAs hide).
+    struct OnePlan { int N = 0, ds = 1; double cost = 1e300; } one;
+    auto smem_one = [&](int n, int ds) { return (((size_t)2 * g.nk * tc_tile_rows(n, g.h) * 16 + 127) & ~(size_t)127) + (size_t)TC_STAGES * ds * g.slab_bytes + 256; };
+    {
+        const int xw_1 = g.mode == 0 ? 16 : 128;
+        const int gx_1 = (p.mw + xw_1 - 1) / xw_1;
+        for (int ds = g.ds; ds >= 1; --ds) {
+            if (tc_env().ds && ds != std::min(tc_env().ds, g.ds)) continue;
+            for (int n = 256; n >= 32; n -= 16) {
+                if (tc_env().force_n && n != tc_env().force_n) continue;
+                const size_t smem = smem_one(n, ds);
+                if (smem > 227 * 1024 || tc_tile_rows(n, g.h) * 16 >= (1 << 18)) continue;
+                const int per_sm = (2 * smem <= 226 * 1024) ? 2 : 1;              // TMEM (<= 256 columns) also allows 2
+                const long long tiles = (long long)gx_1 * ((p.rows + n - 1) / n);
+                const long long waves = (tiles + (long long)per_sm * ctx->sm_count - 1) / ((long long)per_sm * ctx->sm_count);
+                const double t_mma = 1.1 * (0.5 * n + 8.0);
+                const double need = 2500.0 * ((double)g.slab_bytes / g.nk) / t_mma;
+                const double starve = std::max(1.0, need / ((double)(TC_STAGES - 1) * ds * g.slab_bytes));
+                const double mma_tile = ((double)g.h * g.nk * t_mma + std::ceil((double)g.h / ds) * std::max(0.0, 390.0 - 3.0 * t_mma)) * starve;
+                const double other = 40.0 * (n + g.h) + 70.0 * n;                  // tile load + epilogue (8 warps)
+                const double cost = (double)waves * (per_sm * mma_tile + (per_sm == 1 ? other : 0.3 * other));
+                if (cost < one.cost - 1e-9) { one.cost = cost; one.N = n; one.ds = ds; }
+            }
+        }
+    }
+
     // ---- persistent pipeline (two image tiles + slab ring in shared memory, two accumulators in TMEM)
     if (!tc_env().persist_off) {
         const int xw_p = g.mode == 0 ? 16 : 128;
@@ -1484,7 +1520,9 @@ static int launch_ncc_tc_impl(mtm_ctx* ctx, const TcGroup& g, int method, const 
         if (tc_env().plan_dbg && bestN)
             fprintf(stderr, "[mtm plan] h=%d w=%d nk=%d count=%d rows=%d: N=%d ds=%d (%zu KB) stages=%d ew=%d model %.0f clk\n", g.h, g.w, g.nk, g.count, p.rows,
                     bestN, ds_p, stage_b / 1024, best_stages, best_ew, best_cost);
-        if (bestN) {
+        // MTM_B200_PERSIST=2 keeps the persistent kernel whenever it fits (A/B runs)
+        const bool one_wins = one.N && one.cost < 0.9 * best_cost && !tc_env().persist_force;
+        if (bestN && !one_wins) {
             const size_t tile_b = ((size_t)2 * g.nk * tc_tile_rows(bestN, g.h) * 16 + 127) & ~(size_t)127;
             p.N = bestN; p.R = tc_tile_rows(bestN, g.h); p.stages = best_stages; p.ds = ds_p;
             p.tiles_x = gx_p; p.tiles_total = gx_p * ((p.rows + bestN - 1) / bestN);
@@ -1552,44 +1590,13 @@ static int launch_ncc_tc_impl(mtm_ctx* ctx, const TcGroup& g, int method, const 
         }
     }
 
-    // ---- one tile per CTA (tiles too large for two buffers, e.g. 256 x 256 templates)
-    // Tile height: the planned g.N is the largest that fits; a smaller multiple of 16 can cut the number
-    // of CTA waves (e.g. C2: 468 tiles of 256 rows = 1.58 waves of 296 slots -> 585 tiles of 208 rows =
-    // 1.98 waves).  Cost model: waves x (rows + fixed per-tile work expressed in rows).
-    const int xw_ = g.mode == 0 ? 16 : 128;
-    const int gx = (p.mw + xw_ - 1) / xw_;
-    // Tile height AND rows per ring stage together (second session of round 2).  The planned (g.N, g.ds) keeps a 4 x 16-KB ring,
-    // which for 256 x 256 templates (C3: mode B, 7.9-KB slabs that serve 12 MMAs each) capped the tile at 128 rows: 961 tiles, 61 of
-    // them one pixel wide or high, 7 waves.  A mode-B launch needs ~13 KB of slabs in flight, so one row per stage frees 32 KB and
-    // the tile grows to 208 rows: 589 tiles = 3.98 waves.  Cost (clocks per SM): waves x (MMAs of a tile at 1.1 (n/2 + 8) clocks,
-    // stage bubbles and ring starvation as in the persistent model, + tile load and epilogue, which two co-resident CTAs hide).
-    auto smem_for = [&](int n, int ds) { return (((size_t)2 * g.nk * tc_tile_rows(n, g.h) * 16 + 127) & ~(size_t)127) + (size_t)TC_STAGES * ds * g.slab_bytes + 256; };
-    int bestN = 0, best_ds = g.ds;
-    double best_cost = 1e300;
-    for (int ds = g.ds; ds >= 1; --ds) {
-        if (tc_env().ds && ds != std::min(tc_env().ds, g.ds)) continue;
-        for (int n = 256; n >= 32; n -= 16) {
-            if (tc_env().force_n && n != tc_env().force_n) continue;
-            const size_t smem = smem_for(n, ds);
-            if (smem > 227 * 1024 || tc_tile_rows(n, g.h) * 16 >= (1 << 18)) continue;
-            const int per_sm = (2 * smem <= 226 * 1024) ? 2 : 1;              // TMEM (<= 256 columns) also allows 2
-            const long long tiles = (long long)gx * ((p.rows + n - 1) / n);
-            const long long waves = (tiles + (long long)per_sm * ctx->sm_count - 1) / ((long long)per_sm * ctx->sm_count);
-            const double t_mma = 1.1 * (0.5 * n + 8.0);
-            const double need = 2500.0 * ((double)g.slab_bytes / g.nk) / t_mma;
-            const double starve = std::max(1.0, need / ((double)(TC_STAGES - 1) * ds * g.slab_bytes));
-            const double mma_tile = ((double)g.h * g.nk * t_mma + std::ceil((double)g.h / ds) * std::max(0.0, 390.0 - 3.0 * t_mma)) * starve;
-            const double other = 40.0 * (n + g.h) + 70.0 * n;                  // tile load + epilogue (8 warps)
-            const double cost = (double)waves * (per_sm * mma_tile + (per_sm == 1 ? other : 0.3 * other));
-            if (cost < best_cost - 1e-9) { best_cost = cost; bestN = n; best_ds = ds; }
-        }
-    }
-    if (!bestN) return mtm_fail(ctx, MTM_ERR_UNSUPPORTED, "tensor path: no tile of a %d x %d template fits shared memory", g.h, g.w);
-    p.N = bestN; p.R = tc_tile_rows(bestN, g.h); p.ds = best_ds;
+    // ---- one tile per CTA (planned above)
+    if (!one.N) return mtm_fail(ctx, MTM_ERR_UNSUPPORTED, "tensor path: no tile of a %d x %d template fits shared memory", g.h, g.w);
+    p.N = one.N; p.R = tc_tile_rows(one.N, g.h); p.ds = one.ds;
     plan_tma();
-    const size_t smem_bytes = smem_for(bestN, best_ds);
+    const size_t smem_bytes = smem_one(one.N, one.ds);
     if (tc_env().plan_dbg)
-        fprintf(stderr, "[mtm plan] one tile per CTA: h=%d w=%d nk=%d mode=%d: N=%d ds=%d smem=%zu model %.0f clk\n", g.h, g.w, g.nk, g.mode, bestN, best_ds, smem_bytes, best_cost);
+        fprintf(stderr, "[mtm plan] one tile per CTA: h=%d w=%d nk=%d mode=%d: N=%d ds=%d smem=%zu model %.0f clk\n", g.h, g.w, g.nk, g.mode, one.N, one.ds, smem_bytes, one.cost);
     if (!ctx->tc_attr_set) {
         MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         MTM_CUDA(ctx, cudaFuncSetAttribute(ncc_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
