@@ -55,7 +55,8 @@ print("knob parity ok")
 KNOBS = [{"MTM_B200_MOM_BOX": "0"}, {"MTM_B200_MOM_BOX": "0", "MTM_B200_MOM_ROWS": "1"}, {"MTM_B200_MOM_BOX": "0", "MTM_B200_MOM_CS": "1"},
          {"MTM_B200_NO_POINTS": "1"}, {"MTM_B200_NO_CAND": "1"}, {"MTM_B200_PERSIST": "0"}, {"MTM_B200_EW": "12"}, {"MTM_B200_EW": "8"},
          # the other two output loops of the single-channel box kernel, small / one-row ring stages of the numerator kernel
-         {"MTM_B200_BOX_OUT": "0"}, {"MTM_B200_BOX_OUT": "1"}, {"MTM_B200_STAGE_KB": "24"}, {"MTM_B200_DS": "1"}, {}]
+         {"MTM_B200_BOX_OUT": "0"}, {"MTM_B200_BOX_OUT": "1"}, {"MTM_B200_STAGE_KB": "24"}, {"MTM_B200_DS": "1"},
+         {"MTM_B200_PERSIST": "2"}, {"MTM_B200_CTRL_FIRST": "1"}, {}]
 
 
 @pytest.mark.parametrize("knob", KNOBS, ids=lambda k: ",".join("%s=%s" % kv for kv in k.items()) or "default")
