@@ -34,6 +34,7 @@ def _maps(mtm, ctx, temps, img):
     ((260, 420), (100, 130), 2, 4),     # two templates -> mode B twice or A padded
     ((70, 75), (64, 64), 3, 5),         # image barely larger than the template
     ((400, 200), (17, 90), 11, 6),      # 8 + 3, non-square
+    ((430, 520), (200, 210), 2, 7),     # between the BASELINE sizes: the launch weighs the persistent kernel against one tile per CTA
 ])
 def test_tensor_path_maps_vs_exact(mtm, ctxs, shape, tshape, n_t, seed):
     from oracle import ncc_exact, synth
